@@ -1,0 +1,1079 @@
+// =============================================================================
+// oracle/plo_oracle.cpp -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+// This file is a CPU restatement of the reference's algorithms for the one
+// hot path this repository accelerates.  It is NOT part
+// of the product: only tests/, __graft_entry__.smoke() and the cpu_baseline /
+// --impl reference legs of bench.py may load it.  The product (plinopt_b200/)
+// never links, imports or calls anything in oracle/.
+//
+// The reference (jgdumas/plinopt) cannot be compiled here: every header pulls
+// <givaro/...> and <linbox/...> (include/plinopt_library.h:41-45), LinBox >= 1.7.0
+// and Givaro >= 4.2.0 (README.md:13, Makefile:27-28) are neither vendored nor
+// installed.  Hence a restatement, in plain C++ on dense arrays, with exact
+// arithmetic (int64 rationals with __int128 intermediates, or Z/pZ).
+//
+// PINNING STATUS
+//   * MMchecker verdicts   : pinned by the reference's `make mmcheck` (Makefile:60-64)
+//                            -> tests/test_oracle_golden.py
+//   * G2 growth factor     : pinned by the values in data/ headers & file names
+//                            (data/2x2x2_7_DPS-integral-12.0662_L.sms:1, ...)
+//   * sparsifier           : pinned only through the invariant M == Res.CoB
+//                            (bin/FDT.sh:64-66 -> plinopt_sparsify.inl:871-907);
+//                            the identity of the chosen CoB is PARITY UNPINNED
+//                            (it depends on LinBox QLUPin / nullspacebasisin
+//                            tie-breaking that is not in the reference tree).
+//                            Within one localSparsifier step, given TM, Coeffs
+//                            and the previous rows, the winner is fully
+//                            determined by plinopt_sparsify.inl:166-197,299-314
+//                            and that is restated literally below.
+//   * orbiter              : PARITY UNPINNED in the reference (time seeds,
+//                            OpenMP arrival order, src/orbiter.cpp:61-62,298-302);
+//                            defined here through a counter-based decode
+//                            (DESIGN.md "orbit candidate decode").
+//
+// Every function cites the reference file:line it follows (paths relative to
+// the reference root).
+// =============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <utility>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc {
+
+typedef __int128 i128;
+static int g_overflow = 0;  // sticky: set if a rational left the int64 range
+
+// ----------------------------------------------------------------------------
+// Exact rationals (stand-in for Givaro::Rational, include/plinopt_library.h:52-60)
+// ----------------------------------------------------------------------------
+struct Rat {
+  int64_t n, d;  // d > 0, gcd(|n|,d) == 1
+};
+static inline i128 iabs128(i128 a) { return a < 0 ? -a : a; }
+static inline i128 gcd128(i128 a, i128 b) {
+  a = iabs128(a); b = iabs128(b);
+  while (b) { i128 t = a % b; a = b; b = t; }
+  return a;
+}
+static inline Rat mkrat(i128 n, i128 d) {
+  if (d < 0) { n = -n; d = -d; }
+  if (n == 0) return Rat{0, 1};
+  i128 g = gcd128(n, d);
+  n /= g; d /= g;
+  const i128 lim = (i128)INT64_MAX;
+  if (iabs128(n) > lim || d > lim) { g_overflow = 1; return Rat{0, 1}; }
+  return Rat{(int64_t)n, (int64_t)d};
+}
+
+struct QField {
+  typedef Rat E;
+  E zero() const { return Rat{0, 1}; }
+  E one() const { return Rat{1, 1}; }
+  E mone() const { return Rat{-1, 1}; }
+  E fromInt(int64_t i) const { return Rat{i, 1}; }
+  E add(const E& a, const E& b) const { return mkrat((i128)a.n * b.d + (i128)b.n * a.d, (i128)a.d * b.d); }
+  E sub(const E& a, const E& b) const { return mkrat((i128)a.n * b.d - (i128)b.n * a.d, (i128)a.d * b.d); }
+  E mul(const E& a, const E& b) const { return mkrat((i128)a.n * b.n, (i128)a.d * b.d); }
+  E neg(const E& a) const { return Rat{-a.n, a.d}; }
+  E rawneg(const E& a) const { return neg(a); }  // operator- on the Element
+  E inv(const E& a) const { return mkrat(a.d, a.n); }
+  E div(const E& a, const E& b) const { return mkrat((i128)a.n * b.d, (i128)a.d * b.n); }
+  bool isZero(const E& a) const { return a.n == 0; }
+  bool isOne(const E& a) const { return a.n == 1 && a.d == 1; }
+  bool isMOne(const E& a) const { return a.n == -1 && a.d == 1; }
+  bool repEq(const E& a, const E& b) const { return a.n == b.n && a.d == b.d; }
+  bool less(const E& a, const E& b) const { return (i128)a.n * b.d < (i128)b.n * a.d; }
+};
+
+// ----------------------------------------------------------------------------
+// Z/pZ (stand-in for Givaro::Modular<Givaro::Integer>, src/sparsifier.cpp:71-76).
+// Elements are kept as signed integers: results of field operations are
+// canonical in [0,p), but raw negations (operator- on the Integer, as used by
+// augment, plinopt_sparsify.inl:27) stay UN-REDUCED.
+// ----------------------------------------------------------------------------
+struct ZpField {
+  int64_t p;
+  typedef int64_t E;
+  E canon(E a) const { a %= p; if (a < 0) a += p; return a; }
+  E zero() const { return 0; }
+  E one() const { return 1 % p; }
+  E mone() const { return canon(-1); }
+  E fromInt(int64_t i) const { return i; }  // Element(i): un-reduced
+  E add(E a, E b) const { return (E)(((i128)canon(a) + canon(b)) % p); }
+  E sub(E a, E b) const { return (E)(((i128)canon(a) + p - canon(b)) % p); }
+  E mul(E a, E b) const { return (E)(((i128)canon(a) * canon(b)) % p); }
+  E neg(E a) const { a = canon(a); return a == 0 ? 0 : p - a; }
+  E rawneg(E a) const { return -a; }
+  E inv(E a) const {
+    int64_t r0 = p, r1 = canon(a), t0 = 0, t1 = 1;
+    if (r1 == 0) { g_overflow = 2; return 0; }
+    while (r1) { int64_t q = r0 / r1, t = r0 - q * r1; r0 = r1; r1 = t; t = t0 - q * t1; t0 = t1; t1 = t; }
+    if (r0 != 1) { g_overflow = 2; return 0; }
+    return canon(t0);
+  }
+  E div(E a, E b) const { return mul(a, inv(b)); }
+  bool isZero(E a) const { return canon(a) == 0; }
+  bool isOne(E a) const { return canon(a) == one(); }
+  bool isMOne(E a) const { return canon(a) == mone(); }
+  bool repEq(E a, E b) const { return a == b; }
+  bool less(E a, E b) const { return a < b; }  // Integer operator< on representatives (Q18)
+};
+
+// ----------------------------------------------------------------------------
+// Dense stand-in for LinBox::SparseMatrix<F,SparseSeq> (plinopt_library.h:62-75):
+// a sparse row is the sequence of its non-zero entries in increasing column
+// order, so "row->size()" == number of non-zeroes of the dense row.
+// ----------------------------------------------------------------------------
+template <class F>
+struct Mat {
+  typedef typename F::E E;
+  size_t r, c;
+  std::vector<E> a;
+  Mat() : r(0), c(0) {}
+  Mat(const F& f, size_t r_, size_t c_) : r(r_), c(c_), a(r_ * c_, f.zero()) {}
+  E& operator()(size_t i, size_t j) { return a[i * c + j]; }
+  const E& operator()(size_t i, size_t j) const { return a[i * c + j]; }
+};
+
+template <class F>
+static size_t rowSize(const F& f, const Mat<F>& M, size_t i) {
+  size_t s = 0;
+  for (size_t j = 0; j < M.c; ++j) s += !f.isZero(M(i, j));
+  return s;
+}
+// include/plinopt_library.inl:238-245
+template <class F>
+static size_t density(const F& f, const Mat<F>& M) {
+  size_t s = 0;
+  for (size_t i = 0; i < M.r; ++i) s += rowSize(f, M, i);
+  return s;
+}
+// include/plinopt_library.inl:17-24
+template <class F>
+static Mat<F> Transpose(const F& f, const Mat<F>& A) {
+  Mat<F> T(f, A.c, A.r);
+  for (size_t i = 0; i < A.r; ++i) for (size_t j = 0; j < A.c; ++j) T(j, i) = A(i, j);
+  return T;
+}
+template <class F>
+static Mat<F> matmul(const F& f, const Mat<F>& A, const Mat<F>& B) {
+  Mat<F> C(f, A.r, B.c);
+  for (size_t i = 0; i < A.r; ++i)
+    for (size_t k = 0; k < A.c; ++k) {
+      if (f.isZero(A(i, k))) continue;
+      for (size_t j = 0; j < B.c; ++j)
+        if (!f.isZero(B(k, j))) C(i, j) = f.add(C(i, j), f.mul(A(i, k), B(k, j)));
+    }
+  return C;
+}
+template <class F>
+static Mat<F> identity(const F& f, size_t n) {
+  Mat<F> I(f, n, n);
+  for (size_t i = 0; i < n; ++i) I(i, i) = f.one();
+  return I;
+}
+
+// ----------------------------------------------------------------------------
+// Sparse elimination "with reordering" standing in for LinBox
+// GaussDomain::QLUPin (call sites plinopt_sparsify.inl:401,452,545).  LinBox is
+// not in the tree => PARITY UNPINNED; the pivot rule is the one documented in
+// SURVEY.md Appendix B and DESIGN.md:
+//   step k: among remaining rows take the one with the fewest non-zeroes
+//           (first among ties; empty rows are skipped), swap it to position k;
+//           in that row take as pivot the entry whose column has the fewest
+//           non-zeroes among the remaining rows (first among ties).
+// Produces  A = Pr^T . L . U  with row order `rowperm` (U row k is the
+// eliminated original row rowperm[k]), unit lower-triangular multipliers in L
+// (indexed in permuted order) and pivot columns `pivcol`.
+// ----------------------------------------------------------------------------
+template <class F>
+struct Elim {
+  size_t rank;
+  std::vector<size_t> rowperm;  // U row k came from original row rowperm[k]
+  std::vector<size_t> pivcol;   // pivot column of step k (k < rank)
+  Mat<F> U;                     // eliminated rows in permuted order (m x n)
+  Mat<F> L;                     // m x m unit lower triangular (permuted order)
+};
+
+template <class F>
+static Elim<F> eliminate(const F& f, const Mat<F>& A) {
+  const size_t m = A.r, n = A.c;
+  Elim<F> e;
+  e.U = A;
+  e.L = identity(f, m);
+  e.rowperm.resize(m);
+  std::iota(e.rowperm.begin(), e.rowperm.end(), 0);
+  e.rank = 0;
+  Mat<F>& U = e.U;
+  Mat<F>& L = e.L;
+  for (size_t k = 0; k < m; ++k) {
+    // sparsest non-empty remaining row
+    size_t best = m, bestsz = n + 1;
+    for (size_t i = k; i < m; ++i) {
+      size_t s = rowSize(f, U, i);
+      if (s > 0 && s < bestsz) { bestsz = s; best = i; }
+    }
+    if (best == m) break;  // only empty rows remain
+    if (best != k) {
+      for (size_t j = 0; j < n; ++j) std::swap(U(k, j), U(best, j));
+      for (size_t j = 0; j < k; ++j) std::swap(L(k, j), L(best, j));
+      std::swap(e.rowperm[k], e.rowperm[best]);
+    }
+    // pivot column: sparsest column (over remaining rows) among the row's entries
+    size_t pc = n, pcsz = m + 1;
+    for (size_t j = 0; j < n; ++j) {
+      if (f.isZero(U(k, j))) continue;
+      size_t s = 0;
+      for (size_t i = k; i < m; ++i) s += !f.isZero(U(i, j));
+      if (s < pcsz) { pcsz = s; pc = j; }
+    }
+    e.pivcol.push_back(pc);
+    const typename F::E ip = f.inv(U(k, pc));
+    for (size_t i = k + 1; i < m; ++i) {
+      if (f.isZero(U(i, pc))) continue;
+      const typename F::E mult = f.mul(U(i, pc), ip);
+      L(i, k) = mult;
+      for (size_t j = 0; j < n; ++j)
+        if (!f.isZero(U(k, j))) U(i, j) = f.sub(U(i, j), f.mul(mult, U(k, j)));
+    }
+    ++e.rank;
+  }
+  return e;
+}
+
+// include/plinopt_sparsify.inl:38-45 (rank of a copy; any exact elimination
+// yields the same number).
+template <class F>
+static size_t rank(const F& f, const Mat<F>& A) {
+  Mat<F> U = A;
+  const size_t m = U.r, n = U.c;
+  size_t rk = 0;
+  for (size_t j = 0; j < n && rk < m; ++j) {
+    size_t piv = m;
+    for (size_t i = rk; i < m; ++i) if (!f.isZero(U(i, j))) { piv = i; break; }
+    if (piv == m) continue;
+    if (piv != rk) for (size_t t = 0; t < n; ++t) std::swap(U(rk, t), U(piv, t));
+    const typename F::E ip = f.inv(U(rk, j));
+    for (size_t i = rk + 1; i < m; ++i) {
+      if (f.isZero(U(i, j))) continue;
+      const typename F::E mult = f.mul(U(i, j), ip);
+      for (size_t t = j; t < n; ++t) U(i, t) = f.sub(U(i, t), f.mul(mult, U(rk, t)));
+    }
+    ++rk;
+  }
+  return rk;
+}
+
+// Inverse by Gauss-Jordan (exact => unique).  plinopt_sparsify.inl:380-414.
+template <class F>
+static Mat<F> inverse(const F& f, const Mat<F>& A) {
+  const size_t n = A.r;
+  Mat<F> W = A, I = identity(f, n);
+  for (size_t j = 0; j < n; ++j) {
+    size_t piv = n;
+    for (size_t i = j; i < n; ++i) if (!f.isZero(W(i, j))) { piv = i; break; }
+    if (piv == n) { g_overflow = 3; return I; }
+    if (piv != j) for (size_t t = 0; t < n; ++t) { std::swap(W(j, t), W(piv, t)); std::swap(I(j, t), I(piv, t)); }
+    const typename F::E ip = f.inv(W(j, j));
+    for (size_t t = 0; t < n; ++t) { W(j, t) = f.mul(W(j, t), ip); I(j, t) = f.mul(I(j, t), ip); }
+    for (size_t i = 0; i < n; ++i) {
+      if (i == j || f.isZero(W(i, j))) continue;
+      const typename F::E mult = W(i, j);
+      for (size_t t = 0; t < n; ++t) {
+        W(i, t) = f.sub(W(i, t), f.mul(mult, W(j, t)));
+        I(i, t) = f.sub(I(i, t), f.mul(mult, I(j, t)));
+      }
+    }
+  }
+  return I;
+}
+// plinopt_sparsify.inl:431-465
+template <class F>
+static Mat<F> inverseTranspose(const F& f, const Mat<F>& A) { return Transpose(f, inverse(f, A)); }
+
+// First vector of the right nullspace basis, standing in for LinBox
+// GaussDomain::nullspacebasisin column 0 (plinopt_sparsify.inl:235-239).
+// PARITY UNPINNED; rule: eliminate with the pivot rule above, the free
+// columns are the non-pivot columns in increasing order, the returned vector
+// has 1 at the first free column, 0 at the other free columns.
+template <class F>
+static bool nullspaceVector(const F& f, const Mat<F>& N, std::vector<typename F::E>& x) {
+  const size_t n = N.c;
+  Elim<F> e = eliminate(f, N);
+  std::vector<char> isp(n, 0);
+  for (size_t k = 0; k < e.rank; ++k) isp[e.pivcol[k]] = 1;
+  size_t fc = n;
+  for (size_t j = 0; j < n; ++j) if (!isp[j]) { fc = j; break; }
+  x.assign(n, f.zero());
+  if (fc == n) return false;
+  x[fc] = f.one();
+  for (size_t kk = e.rank; kk-- > 0;) {
+    typename F::E s = f.zero();
+    for (size_t j = 0; j < n; ++j)
+      if (j != e.pivcol[kk] && !f.isZero(e.U(kk, j)) && !f.isZero(x[j])) s = f.add(s, f.mul(e.U(kk, j), x[j]));
+    x[e.pivcol[kk]] = f.neg(f.div(s, e.U(kk, e.pivcol[kk])));
+  }
+  return true;
+}
+
+// ----------------------------------------------------------------------------
+// include/plinopt_sparsify.inl:20-35  augment: v gets i, -i, 1/i, -1/i if i is new
+// ----------------------------------------------------------------------------
+template <class F>
+static void augment(const F& f, std::vector<typename F::E>& v, const typename F::E& r) {
+  for (const auto& x : v) if (f.repEq(x, r)) return;
+  v.push_back(r);
+  v.push_back(f.rawneg(r));
+  typename F::E t = f.inv(r);
+  v.push_back(t);
+  v.push_back(f.neg(t));
+}
+
+// include/plinopt_sparsify.inl:256-268  candidate coefficient list
+template <class F>
+static std::vector<typename F::E> buildCoeffs(const F& f, const Mat<F>& TM, size_t maxnumcoeff) {
+  std::vector<typename F::E> C{f.fromInt(0), f.fromInt(1), f.rawneg(f.fromInt(1))};
+  for (size_t i = 0; i < TM.r; ++i)
+    for (size_t j = 0; j < TM.c; ++j)
+      if (!f.isZero(TM(i, j))) augment(f, C, TM(i, j));
+  for (size_t i = 2; C.size() < maxnumcoeff; ++i) augment(f, C, f.fromInt((int64_t)i));
+  if (C.size() > maxnumcoeff) C.resize(maxnumcoeff);
+  return C;
+}
+
+// One record per (block,num) step of localSparsifier: what the quad loop chose.
+struct StepTrace {
+  int32_t block, num, rl, cl;
+  int64_t index;     // winning (i,j,k,l) index ((i*c+j)*c+k)*c+l, -1 if the seed/fallback won
+  int32_t fallback;  // canonical vector index used by the fallback loop, -1 if none
+  int32_t c;         // number of coefficients of this call
+};
+static std::vector<StepTrace> g_trace;
+static bool g_trace_on = false;
+
+// ----------------------------------------------------------------------------
+// include/plinopt_sparsify.inl:166-197  testLinComb, literal.
+// ----------------------------------------------------------------------------
+template <class F>
+static bool testLinComb(const F& f, std::pair<int, int>& weight, Mat<F>& LCoB, Mat<F>& Cand, size_t num,
+                        const std::vector<typename F::E>& w, const Mat<F>& TM) {
+  for (size_t j = 0; j < Cand.c; ++j) Cand(num, j) = (j < w.size() ? w[j] : f.zero());  // setRow(Cand,num,w)
+  const size_t r = rank(f, Cand);                                                    // :173
+  if (r > num) {
+    int rlHw = 0, clHw = 0;
+    for (size_t j = 0; j < TM.c; ++j) {  // v = TM^T w, :176
+      typename F::E s = f.zero();
+      for (size_t i = 0; i < TM.r; ++i)
+        if (!f.isZero(w[i]) && !f.isZero(TM(i, j))) s = f.add(s, f.mul(w[i], TM(i, j)));
+      rlHw += f.isZero(s);  // :179
+    }
+    for (size_t i = 0; i < w.size(); ++i) clHw += f.isZero(w[i]);  // :180
+    if ((rlHw > weight.first) || ((rlHw == weight.first) && (clHw > weight.second))) {  // :183-184
+      weight.first = rlHw;
+      weight.second = clHw;
+      for (size_t j = 0; j < LCoB.c; ++j) LCoB(num, j) = w[j];  // :192
+      return true;
+    }
+  }
+  return false;
+}
+
+// include/plinopt_sparsify.inl:299-314: the quad loop for one (block,num) step.
+// Returns the index of the last accepted candidate (== the first maximiser,
+// Q2), or -1.  `found` / `weight` / LCoB are updated like the reference does.
+template <class F>
+static int64_t quadLoop(const F& f, const std::vector<typename F::E>& Coeffs, std::pair<int, int>& weight,
+                        Mat<F>& LCoB, Mat<F>& A, size_t offsetblock, size_t num, size_t multiple, const Mat<F>& TM,
+                        bool& found, int nthreads_unused = 1) {
+  (void)nthreads_unused;
+  const size_t c = Coeffs.size();
+  std::vector<typename F::E> w;
+  int64_t bestidx = -1;
+  for (size_t i = 0; i < c; ++i)
+    for (size_t j = 0; j < c; ++j)
+      for (size_t k = 0; k < c; ++k)
+        for (size_t l = 0; l < c; ++l) {
+          w.assign(multiple, f.zero());
+          // note: earlier positions of w are zero here because the reference
+          // only ever writes the current block (w is cleared per block, :283)
+          w[0 + offsetblock] = Coeffs[i];
+          w[1 + offsetblock] = Coeffs[j];
+          w[2 + offsetblock] = Coeffs[k];
+          w[3 + offsetblock] = Coeffs[l];
+          w.resize(TM.r);  // :311 (truncation on the last partial block, Q4)
+          if (testLinComb(f, weight, LCoB, A, num + offsetblock, w, TM)) {
+            found = true;
+            bestidx = (int64_t)(((i * c + j) * c + k) * c + l);
+          }
+        }
+  return bestidx;
+}
+
+// ----------------------------------------------------------------------------
+// include/plinopt_sparsify.inl:205-347  localSparsifier
+// ----------------------------------------------------------------------------
+template <class F>
+static void localSparsifier(const F& f, Mat<F>& TCoB, Mat<F>& TM, size_t maxnumcoeff) {
+  const size_t n = TCoB.r;
+  Mat<F> LCoB(f, n, n);
+  int cnHw = -1, rnHw = -1;
+
+  if (TM.r > 1) {  // :227-252 nullspace prelude
+    Mat<F> N = Transpose(f, TM);
+    {  // std::sort(N.rowBegin(), N.rowEnd(), sizeSup) :229 -- same std::sort call
+      std::vector<std::vector<std::pair<size_t, typename F::E>>> rows(N.r);
+      for (size_t i = 0; i < N.r; ++i)
+        for (size_t j = 0; j < N.c; ++j)
+          if (!f.isZero(N(i, j))) rows[i].emplace_back(j, N(i, j));
+      std::sort(rows.begin(), rows.end(), [](const auto& a, const auto& b) { return a.size() > b.size(); });
+      Mat<F> S(f, N.r, N.c);
+      for (size_t i = 0; i < N.r; ++i) for (const auto& e : rows[i]) S(i, e.first) = e.second;
+      N = S;
+    }
+    while (N.r > 0 && rank(f, N) == N.c) {  // :230-232
+      N.a.resize((N.r - 1) * N.c);
+      N.r -= 1;
+    }
+    if (N.r > 0) {
+      std::vector<typename F::E> x;
+      nullspaceVector(f, N, x);  // :235
+      for (size_t i = 0; i < n; ++i) if (!f.isZero(x[i])) LCoB(0, i) = x[i];
+      cnHw = (int)rowSize(f, LCoB, 0);  // :242 (sic: number of NON-zeroes, Q1)
+      rnHw = 0;
+      for (size_t j = 0; j < TM.c; ++j) {  // :241,243
+        typename F::E s = f.zero();
+        for (size_t i = 0; i < TM.r; ++i)
+          if (!f.isZero(LCoB(0, i)) && !f.isZero(TM(i, j))) s = f.add(s, f.mul(LCoB(0, i), TM(i, j)));
+        rnHw += f.isZero(s);
+      }
+    }
+  }
+
+  const std::vector<typename F::E> Coeffs = buildCoeffs(f, TM, maxnumcoeff);  // :256-268
+
+  const size_t numlargeblocks = TM.r >> 2;  // :274-277
+  const size_t lastblock = TM.r - (numlargeblocks << 2);
+  const size_t numblocks = lastblock ? numlargeblocks + 1 : numlargeblocks;
+  const size_t multiple = numblocks << 2;
+
+  for (size_t block = 0; block < numblocks; ++block) {
+    const size_t offsetblock = block << 2;
+    const size_t firstcolumns = std::min<size_t>(4u, LCoB.r - offsetblock);
+    for (size_t num = 0; num < firstcolumns; ++num) {
+      Mat<F> A = LCoB;  // :289
+      std::pair<int, int> weight{-1, -1};
+      bool found = (block == 0) && (num == 0);  // :291 (Q5)
+      if (found) { weight.first = rnHw; weight.second = cnHw; }
+      int64_t idx = quadLoop(f, Coeffs, weight, LCoB, A, offsetblock, num, multiple, TM, found);
+      int fb = -1;
+      for (size_t p = 0; !found; ++p) {  // :317-326
+        weight = {-1, -1};
+        std::vector<typename F::E> w(TM.r, f.zero());
+        if (p >= TM.r) { g_overflow = 4; break; }
+        w[p] = f.one();
+        found |= testLinComb(f, weight, LCoB, A, num + offsetblock, w, TM);
+        if (found) fb = (int)p;
+      }
+      if (g_trace_on)
+        g_trace.push_back(StepTrace{(int32_t)block, (int32_t)num, weight.first, weight.second, idx, fb, (int32_t)Coeffs.size()});
+    }
+  }
+  TM = matmul(f, LCoB, TM);      // :339,343
+  TCoB = matmul(f, LCoB, TCoB);  // :340,344
+}
+
+// include/plinopt_sparsify.inl:354-375  FactorDiagonals (Q18: std::map order,
+// max_element keeps the FIRST maximum => smallest Element among equally frequent)
+template <class F>
+static void FactorDiagonals(const F& f, Mat<F>& TCoB, Mat<F>& TM) {
+  for (size_t i = 0; i < TM.r; ++i) {
+    if (rowSize(f, TM, i) == 0) continue;
+    auto cmp = [&f](const typename F::E& a, const typename F::E& b) { return f.less(a, b); };
+    std::map<typename F::E, int, decltype(cmp)> count(cmp);
+    for (size_t j = 0; j < TM.c; ++j) if (!f.isZero(TM(i, j))) ++count[TM(i, j)];
+    auto best = count.begin();
+    for (auto it = count.begin(); it != count.end(); ++it) if (best->second < it->second) best = it;
+    const typename F::E r = best->first;
+    if (!f.isOne(r)) {
+      for (size_t j = 0; j < TM.c; ++j) if (!f.isZero(TM(i, j))) TM(i, j) = f.div(TM(i, j), r);
+      for (size_t j = 0; j < TCoB.c; ++j) if (!f.isZero(TCoB(i, j))) TCoB(i, j) = f.div(TCoB(i, j), r);
+    }
+  }
+}
+
+// include/plinopt_sparsify.inl:523-568  sparseLU:  A <- (QL)^{-1}.A, QL <- Q.L,
+// only if the eliminated matrix is sparser.  With A = Pr^T.L.U (see eliminate):
+// the new A is U with rows put back in ORIGINAL order... the reference applies
+// P.applyLeft(B,R) (column permutation undone) and Q.applyRight(C,S); we keep
+// columns in place (our elimination never permutes columns physically) and
+// return QL = Pr^T.L so that  A_old == QL . A_new  holds exactly.
+template <class F>
+static bool sparseLU(const F& f, Mat<F>& QL, Mat<F>& A, size_t sparsity) {
+  Elim<F> e = eliminate(f, A);
+  const bool sparser = density(f, e.U) < sparsity;  // :547
+  if (sparser) {
+    const size_t m = A.r;
+    Mat<F> C(f, m, m);
+    for (size_t k = 0; k < m; ++k)
+      for (size_t j = 0; j < m; ++j) C(e.rowperm[k], j) = e.L(k, j);
+    A = e.U;
+    QL = C;
+  }
+  return sparser;
+}
+
+// include/plinopt_sparsify.inl:417-428  R s.t. A == TICoB . R
+template <class F>
+static Mat<F> applyInverse(const F& f, const Mat<F>& TICoB, const Mat<F>& A) { return matmul(f, inverse(f, TICoB), A); }
+
+// include/plinopt_sparsify.inl:576-604  sparseILU
+template <class F>
+static bool sparseILU(const F& f, Mat<F>& TC, Mat<F>& A, size_t sparsity) {
+  Mat<F> QL = identity(f, A.r);
+  const bool sparser = sparseLU(f, QL, A, sparsity);
+  if (sparser) TC = applyInverse(f, QL, TC);
+  return sparser;
+}
+
+static inline size_t totalDensity(const std::vector<size_t>&) { return 0; }
+
+// include/plinopt_sparsify.inl:473-513  SparseFactor
+template <class F>
+static size_t SparseFactor(const F& f, Mat<F>& TICoB, Mat<F>& TM, size_t start, size_t increment, size_t threshold) {
+  size_t s2 = density(f, TM), ss;
+  size_t numcoeffs = start;
+  do {
+    ss = s2;
+    localSparsifier(f, TICoB, TM, numcoeffs);
+    FactorDiagonals(f, TICoB, TM);
+    s2 = density(f, TM);
+    if (numcoeffs < threshold) numcoeffs += increment;
+  } while (s2 < ss);
+  return s2;
+}
+
+#ifndef COEFFICIENT_SEARCH
+#define COEFFICIENT_SEARCH 11u  // include/plinopt_sparsify.h:36-38
+#endif
+
+// include/plinopt_sparsify.inl:609-661  sparseAlternate
+template <class F>
+static void sparseAlternate(const F& f, Mat<F>& CoB, Mat<F>& Res, const Mat<F>& M, size_t maxnumcoeff) {
+  const size_t n = M.c;
+  Mat<F> TM = Transpose(f, M);
+  Mat<F> TICoB = identity(f, n);
+  FactorDiagonals(f, TICoB, TM);                 // :629
+  sparseILU(f, TICoB, TM, density(f, TM));       // :631
+  SparseFactor(f, TICoB, TM, 3u, 4u, COEFFICIENT_SEARCH);        // :640 (Q8)
+  SparseFactor(f, TICoB, TM, maxnumcoeff, 1u, maxnumcoeff);      // :642
+  CoB = inverseTranspose(f, TICoB);              // :647
+  Res = Transpose(f, TM);                        // :652
+}
+
+// include/plinopt_sparsify.inl:666-748  blockSparsifier
+template <class F>
+static void blockSparsifier(const F& f, Mat<F>& CoB, Mat<F>& Res, const Mat<F>& M, size_t blocksize,
+                            size_t maxnumcoeff, bool initialElimination) {
+  if (blocksize <= 1) { sparseAlternate(f, CoB, Res, M, maxnumcoeff); return; }
+  const size_t m = M.r, n = M.c;
+  Mat<F> U(f, n, m), L = identity(f, n);
+  bool reduced = initialElimination;
+  if (initialElimination) {
+    U = Transpose(f, M);
+    reduced = sparseLU(f, L, U, density(f, U));  // :691
+  }
+  const Mat<F> A = reduced ? Transpose(f, U) : M;  // :700-701
+  // separateColumnBlocks :88-114
+  std::vector<Mat<F>> vA, vC, vR;
+  for (size_t c0 = 0; c0 < n; c0 += blocksize) {
+    const size_t w = std::min(blocksize, n - c0);
+    Mat<F> B(f, m, w);
+    for (size_t i = 0; i < m; ++i) for (size_t j = 0; j < w; ++j) B(i, j) = A(i, c0 + j);
+    vA.push_back(B);
+  }
+  for (const auto& mat : vA) {
+    Mat<F> C(f, mat.c, mat.c), R(f, mat.r, mat.c);
+    sparseAlternate(f, C, R, mat, maxnumcoeff);  // :714
+    vC.push_back(C);
+    vR.push_back(R);
+  }
+  Res = Mat<F>(f, m, n);  // augmentedMatrix :726
+  {
+    size_t c0 = 0;
+    for (const auto& R : vR) {
+      for (size_t i = 0; i < m; ++i) for (size_t j = 0; j < R.c; ++j) Res(i, c0 + j) = R(i, j);
+      c0 += R.c;
+    }
+  }
+  CoB = Mat<F>(f, n, n);
+  if (reduced) {  // :728-741   TCoB = [ L_blk_i . vC_i^T ]_i ; CoB = TCoB^T
+    Mat<F> TCoB(f, n, n);
+    size_t c0 = 0;
+    for (size_t b = 0; b < vC.size(); ++b) {
+      const size_t w = vC[b].c;
+      Mat<F> Lb(f, n, w);
+      for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < w; ++j) Lb(i, j) = L(i, c0 + j);
+      Mat<F> B = matmul(f, Lb, Transpose(f, vC[b]));
+      for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < w; ++j) TCoB(i, c0 + j) = B(i, j);
+      c0 += w;
+    }
+    CoB = Transpose(f, TCoB);
+  } else {  // diagonalMatrix :743
+    size_t c0 = 0;
+    for (const auto& C : vC) {
+      for (size_t i = 0; i < C.r; ++i) for (size_t j = 0; j < C.c; ++j) CoB(c0 + i, c0 + j) = C(i, j);
+      c0 += C.r;
+    }
+  }
+}
+
+// include/plinopt_sparsify.inl:871-907  consistency: M == R.C ?
+template <class F>
+static bool consistency(const F& f, const Mat<F>& M, const Mat<F>& R, const Mat<F>& C) {
+  Mat<F> A = matmul(f, R, C);
+  for (size_t i = 0; i < M.r; ++i)
+    for (size_t j = 0; j < M.c; ++j)
+      if (!f.isZero(f.sub(A(i, j), M(i, j)))) return false;
+  return true;
+}
+
+// ----------------------------------------------------------------------------
+// Orbit candidates.
+// Reference: src/orbiter.cpp:59-75,125-136 (zoiRandomMatrix, default branch):
+//   M[P[i]][Q[i]] = D[i] ? 1 : -1 ; M[P[i]][Q[j]] = zoRandomElt in {-1,0,1}, j>i
+// The reference draws P,Q,D and the trits from a wall-clock seeded generator
+// (unreproducible); here they come from a digit stream
+// that is a pure function of (mode, seed, index) -- DESIGN.md "orbit candidate
+// decode".  Digit order per matrix: Fisher-Yates digits of P (radices s,s-1,..,2),
+// of Q, s sign digits (radix 2), s(s-1)/2 trits (radix 3, row-major over i<j).
+// ----------------------------------------------------------------------------
+static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                 uint32_t out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct DigitStream {
+  int mode;  // 0 = exhaustive mixed radix of `index`, 1 = Philox4x32-10(seed; index)
+  uint64_t seed, index;
+  uint64_t rem;       // mode 0: remaining quotient
+  uint32_t x;         // mode 1: current word
+  uint64_t R;         // mode 1: product of radices drawn from the current word
+  uint32_t buf[4];
+  uint32_t nwords;    // words consumed so far
+  DigitStream(int mode_, uint64_t seed_, uint64_t index_) : mode(mode_), seed(seed_), index(index_), rem(index_), x(0), R(0), nwords(0) {}
+  void newWord() {
+    if ((nwords & 3u) == 0)
+      philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), nwords >> 2, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+    x = buf[nwords & 3u];
+    ++nwords;
+    R = 1;
+  }
+  void startMatrix() { if (mode == 1) newWord(); }  // every matrix starts on a fresh word
+  uint32_t digit(uint32_t radix) {
+    if (mode == 0) { uint32_t d = (uint32_t)(rem % radix); rem /= radix; return d; }
+    if (R * radix > (1u << 20)) newWord();
+    const uint64_t t = (uint64_t)x * radix;
+    x = (uint32_t)t;
+    R *= radix;
+    return (uint32_t)(t >> 32);
+  }
+};
+
+static void zoiDecode(DigitStream& ds, int s, int32_t* M) {
+  ds.startMatrix();
+  std::vector<int> P(s), Q(s), D(s);
+  std::iota(P.begin(), P.end(), 0);
+  std::iota(Q.begin(), Q.end(), 0);
+  for (int i = 0; i + 1 < s; ++i) { int d = (int)ds.digit((uint32_t)(s - i)); std::swap(P[i], P[i + d]); }
+  for (int i = 0; i + 1 < s; ++i) { int d = (int)ds.digit((uint32_t)(s - i)); std::swap(Q[i], Q[i + d]); }
+  for (int i = 0; i < s; ++i) D[i] = (int)ds.digit(2u);
+  for (int i = 0; i < s * s; ++i) M[i] = 0;
+  for (int i = 0; i < s; ++i) M[P[i] * s + Q[i]] = D[i] ? 1 : -1;  // orbiter.cpp:127-128
+  for (int i = 0; i < s; ++i)
+    for (int j = i + 1; j < s; ++j) M[P[i] * s + Q[j]] = (int)ds.digit(3u) - 1;  // :130-135, library.inl:416-422
+}
+
+static void orbitDecode(int m, int k, int n, int mode, uint64_t seed, uint64_t index, int32_t* U, int32_t* V, int32_t* W) {
+  DigitStream ds(mode, seed, index);
+  zoiDecode(ds, m, U);
+  zoiDecode(ds, k, V);
+  zoiDecode(ds, n, W);
+}
+
+// include/plinopt_library.inl:210-223  Tensor (Kronecker product)
+template <class F>
+static Mat<F> Tensor(const F& f, const Mat<F>& A, const Mat<F>& B) {
+  Mat<F> T(f, A.r * B.r, A.c * B.c);
+  for (size_t ia = 0; ia < A.r; ++ia) for (size_t ja = 0; ja < A.c; ++ja) {
+    if (f.isZero(A(ia, ja))) continue;
+    for (size_t ib = 0; ib < B.r; ++ib) for (size_t jb = 0; jb < B.c; ++jb)
+      if (!f.isZero(B(ib, jb))) T(ia * B.r + ib, ja * B.c + jb) = f.mul(A(ia, ja), B(ib, jb));
+  }
+  return T;
+}
+
+// include/plinopt_library.inl:258-269,279-284  nonzeroes: (nnz, #entries not in {0,+-1})
+template <class F>
+static void nonzeroes(const F& f, const Mat<F>& M, size_t& nnz, size_t& nno) {
+  for (const auto& e : M.a)
+    if (!f.isZero(e)) { ++nnz; if (!(f.isOne(e) || f.isMOne(e))) ++nno; }
+}
+
+static inline double toDouble(const QField&, const Rat& a) { return (double)a.n / (double)a.d; }
+
+// src/growthfactor.cpp:41-44 norm2 over the stored (non-zero) entries of a row,
+// each converted to double first (:25-28)
+static double norm2row(const QField& f, const Mat<QField>& M, size_t i) {
+  double s = 0.;
+  for (size_t j = 0; j < M.c; ++j)
+    if (!f.isZero(M(i, j))) { const double x = toDouble(f, M(i, j)); s += x * x; }
+  return std::sqrt(s);
+}
+// src/growthfactor.cpp:117-125  G2 = sum_i ||L_i|| ||R_i|| ||(P^T)_i||
+static double G2(const QField& f, const Mat<QField>& L, const Mat<QField>& R, const Mat<QField>& P) {
+  Mat<QField> Pt = Transpose(f, P);
+  double s = 0.;
+  for (size_t i = 0; i < P.c; ++i) s += norm2row(f, L, i) * norm2row(f, R, i) * norm2row(f, Pt, i);
+  return s;
+}
+
+// include/plinopt_library.h:177-181  LRP2MM
+static void LRP2MM(size_t Lc, size_t Rc, size_t Pr, size_t& m, size_t& k, size_t& n) {
+  n = (size_t)std::sqrt((double)(Rc * Pr / Lc));
+  m = Pr / n;
+  k = Rc / n;
+}
+
+// src/orbiter.cpp:274-296: one candidate, literal (inverses, Kronecker
+// products, full products), over Q.
+struct OrbitScore { size_t nnz, nno; double g2; };
+template <class F>
+static void orbitApply(const F& f, int m, int k, int n, const Mat<F>& L, const Mat<F>& R, const Mat<F>& P,
+                       const int32_t* Ui, const int32_t* Vi, const int32_t* Wi, Mat<F>& Lj, Mat<F>& Rg, Mat<F>& hP) {
+  Mat<F> U(f, m, m), V(f, k, k), W(f, n, n);
+  auto conv = [&f](int32_t x) { return x == 0 ? f.zero() : (x > 0 ? f.one() : f.mone()); };
+  for (int i = 0; i < m * m; ++i) U.a[i] = conv(Ui[i]);
+  for (int i = 0; i < k * k; ++i) V.a[i] = conv(Vi[i]);
+  for (int i = 0; i < n * n; ++i) W.a[i] = conv(Wi[i]);
+  Mat<F> iVT = inverseTranspose(f, V), iU = inverse(f, U), iW = inverse(f, W);  // :280-282
+  Mat<F> J = Tensor(f, iU, V), G = Tensor(f, iVT, W), H = Tensor(f, U, iW);     // :284-286
+  Lj = matmul(f, L, J); Rg = matmul(f, R, G); hP = matmul(f, H, P);             // :292-294
+}
+
+}  // namespace orc
+
+// =============================================================================
+// C ABI for ctypes (tests / bench cpu_baseline).  Rationals cross the boundary
+// as (num, den) int64 arrays; Z/pZ entries as int64 residues.
+// =============================================================================
+using namespace orc;
+
+template <class F> struct Loader;
+template <> struct Loader<QField> {
+  static Mat<QField> load(const QField& f, size_t r, size_t c, const int64_t* num, const int64_t* den) {
+    Mat<QField> M(f, r, c);
+    for (size_t i = 0; i < r * c; ++i) M.a[i] = mkrat(num[i], den ? den[i] : 1);
+    return M;
+  }
+  static void store(const Mat<QField>& M, int64_t* num, int64_t* den) {
+    for (size_t i = 0; i < M.a.size(); ++i) { num[i] = M.a[i].n; if (den) den[i] = M.a[i].d; }
+  }
+};
+template <> struct Loader<ZpField> {
+  static Mat<ZpField> load(const ZpField& f, size_t r, size_t c, const int64_t* num, const int64_t* den) {
+    Mat<ZpField> M(f, r, c);
+    for (size_t i = 0; i < r * c; ++i) M.a[i] = den ? f.div(f.canon(num[i]), f.canon(den[i])) : f.canon(num[i]);
+    return M;
+  }
+  static void store(const Mat<ZpField>& M, int64_t* num, int64_t* den) {
+    for (size_t i = 0; i < M.a.size(); ++i) { num[i] = M.a[i]; if (den) den[i] = 1; }
+  }
+};
+
+template <class F>
+static int sparsifier_impl(const F& f, int rows, int cols, const int64_t* num, const int64_t* den, int blocksize,
+                           int maxnumcoeff, int initialElimination, int64_t* cob_num, int64_t* cob_den,
+                           int64_t* res_num, int64_t* res_den, int* consistent) {
+  g_overflow = 0;
+  Mat<F> M = Loader<F>::load(f, rows, cols, num, den);
+  Mat<F> CoB(f, cols, cols), Res(f, rows, cols);
+  blockSparsifier(f, CoB, Res, M, (size_t)blocksize, (size_t)maxnumcoeff, initialElimination != 0);
+  Loader<F>::store(CoB, cob_num, cob_den);
+  Loader<F>::store(Res, res_num, res_den);
+  *consistent = consistency(f, M, Res, CoB) ? 1 : 0;
+  return g_overflow ? -g_overflow : 0;
+}
+
+template <class F>
+static int lincomb_impl(const F& f, int n, int m, const int64_t* tm_num, const int64_t* tm_den, int off, int num, int c,
+                        const int64_t* cf_num, const int64_t* cf_den, const int64_t* lcob_num, const int64_t* lcob_den,
+                        int init_rl, int init_cl, int* best_rl, int* best_cl, int64_t* best_index) {
+  g_overflow = 0;
+  Mat<F> TM = Loader<F>::load(f, n, m, tm_num, tm_den);
+  Mat<F> LCoB = Loader<F>::load(f, n, n, lcob_num, lcob_den);
+  Mat<F> Cf = Loader<F>::load(f, 1, c, cf_num, cf_den);
+  std::vector<typename F::E> Coeffs(Cf.a.begin(), Cf.a.end());
+  Mat<F> A = LCoB;
+  std::pair<int, int> weight{init_rl, init_cl};
+  bool found = false;
+  const size_t numblocks = ((size_t)n + 3) >> 2;
+  int64_t idx = quadLoop(f, Coeffs, weight, LCoB, A, (size_t)off, (size_t)num, numblocks << 2, TM, found);
+  *best_rl = weight.first; *best_cl = weight.second; *best_index = idx;
+  return g_overflow ? -g_overflow : 0;
+}
+
+extern "C" {
+
+int orc_num_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+// Whole sparsifier pipeline (src/sparsifier.cpp:20-55 TSparsifier -> blockSparsifier).
+// p == 0: over Q, entries (num/den); p > 0: over Z/pZ (a/b -> a.b^-1 mod p, :71-76).
+int orc_sparsifier(int64_t p, int rows, int cols, const int64_t* num, const int64_t* den, int blocksize, int maxnumcoeff,
+                   int initialElimination, int64_t* cob_num, int64_t* cob_den, int64_t* res_num, int64_t* res_den,
+                   int* consistent) {
+  if (p == 0) { QField f; return sparsifier_impl(f, rows, cols, num, den, blocksize, maxnumcoeff, initialElimination, cob_num, cob_den, res_num, res_den, consistent); }
+  ZpField f{p};
+  return sparsifier_impl(f, rows, cols, num, den, blocksize, maxnumcoeff, initialElimination, cob_num, cob_den, res_num, res_den, consistent);
+}
+
+// Trace of every (block,num) step of the last orc_sparsifier call when tracing is on.
+void orc_trace_enable(int on) { g_trace_on = on != 0; g_trace.clear(); }
+int orc_trace_size() { return (int)g_trace.size(); }
+void orc_trace_get(int i, int32_t* block, int32_t* num, int32_t* rl, int32_t* cl, int64_t* index, int32_t* fallback, int32_t* c) {
+  const StepTrace& t = g_trace[(size_t)i];
+  *block = t.block; *num = t.num; *rl = t.rl; *cl = t.cl; *index = t.index; *fallback = t.fallback; *c = t.c;
+}
+
+// Coefficient list of plinopt_sparsify.inl:256-268 for TM (n x m).  Returns its length.
+int orc_coeffs(int64_t p, int n, int m, const int64_t* tm_num, const int64_t* tm_den, int maxnumcoeff, int64_t* out_num, int64_t* out_den) {
+  g_overflow = 0;
+  if (p == 0) {
+    QField f; Mat<QField> TM = Loader<QField>::load(f, n, m, tm_num, tm_den);
+    auto C = buildCoeffs(f, TM, (size_t)maxnumcoeff);
+    for (size_t i = 0; i < C.size(); ++i) { out_num[i] = C[i].n; out_den[i] = C[i].d; }
+    return g_overflow ? -g_overflow : (int)C.size();
+  }
+  ZpField f{p}; Mat<ZpField> TM = Loader<ZpField>::load(f, n, m, tm_num, tm_den);
+  auto C = buildCoeffs(f, TM, (size_t)maxnumcoeff);
+  for (size_t i = 0; i < C.size(); ++i) { out_num[i] = C[i]; out_den[i] = 1; }
+  return g_overflow ? -g_overflow : (int)C.size();
+}
+
+// One (block,num) step of the quad loop (plinopt_sparsify.inl:299-314), literal:
+// every candidate goes through setRow + rank + applyTranspose + two counts.
+// LCoB holds the rows chosen so far (rows >= off+num are zero).
+int orc_lincomb_search(int64_t p, int n, int m, const int64_t* tm_num, const int64_t* tm_den, int off, int num, int c,
+                       const int64_t* cf_num, const int64_t* cf_den, const int64_t* lcob_num, const int64_t* lcob_den,
+                       int init_rl, int init_cl, int* best_rl, int* best_cl, int64_t* best_index) {
+  if (p == 0) { QField f; return lincomb_impl(f, n, m, tm_num, tm_den, off, num, c, cf_num, cf_den, lcob_num, lcob_den, init_rl, init_cl, best_rl, best_cl, best_index); }
+  ZpField f{p};
+  return lincomb_impl(f, n, m, tm_num, tm_den, off, num, c, cf_num, cf_den, lcob_num, lcob_den, init_rl, init_cl, best_rl, best_cl, best_index);
+}
+
+// Timed variant for the CPU baseline: the same literal loop restricted to the
+// first-coefficient range [i_lo, i_hi) (an added `omp parallel for` over i, as
+// planned in BASELINE.md section 2; the reference loop itself is sequential).
+// Returns the number of candidates scored.
+int64_t orc_lincomb_bench(int64_t p, int n, int m, const int64_t* tm_num, const int64_t* tm_den, int off, int num, int c,
+                          const int64_t* cf_num, const int64_t* cf_den, const int64_t* lcob_num, const int64_t* lcob_den,
+                          int i_lo, int i_hi, int nthreads, int* best_rl, int* best_cl, int64_t* best_index) {
+  ZpField fz{p ? p : 2};
+  QField fq;
+  int64_t total = 0;
+  int grl = -1, gcl = -1; int64_t gidx = -1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+  for (int i = i_lo; i < i_hi; ++i) {
+    int rl = -1, cl = -1; int64_t idx = -1;
+    auto run = [&](auto f) {
+      typedef decltype(f) F;
+      Mat<F> TM = Loader<F>::load(f, n, m, tm_num, tm_den);
+      Mat<F> LCoB = Loader<F>::load(f, n, n, lcob_num, lcob_den);
+      Mat<F> Cf = Loader<F>::load(f, 1, c, cf_num, cf_den);
+      Mat<F> A = LCoB;
+      std::pair<int, int> weight{-1, -1};
+      std::vector<typename F::E> w;
+      const size_t multiple = (((size_t)n + 3) >> 2) << 2;
+      for (int j = 0; j < c; ++j) for (int k = 0; k < c; ++k) for (int l = 0; l < c; ++l) {
+        w.assign(multiple, f.zero());
+        w[0 + off] = Cf.a[i]; w[1 + off] = Cf.a[j]; w[2 + off] = Cf.a[k]; w[3 + off] = Cf.a[l];
+        w.resize(TM.r);
+        if (testLinComb(f, weight, LCoB, A, (size_t)(num + off), w, TM))
+          idx = (((int64_t)i * c + j) * c + k) * c + l;
+      }
+      rl = weight.first; cl = weight.second;
+    };
+    if (p == 0) run(fq); else run(fz);
+    total += (int64_t)c * c * c;
+#pragma omp critical
+    {
+      if (idx >= 0 && (rl > grl || (rl == grl && cl > gcl) || (rl == grl && cl == gcl && idx < gidx))) { grl = rl; gcl = cl; gidx = idx; }
+    }
+  }
+  *best_rl = grl; *best_cl = gcl; *best_index = gidx;
+  return total;
+}
+
+// Orbit candidate decode; U m x m, V k x k, W n x n row-major.
+void orc_orbit_decode(int m, int k, int n, int mode, uint64_t seed, uint64_t index, int32_t* U, int32_t* V, int32_t* W) {
+  orbitDecode(m, k, n, mode, seed, index, U, V, W);
+}
+
+// Scores of the candidates lo..hi-1 (src/orbiter.cpp:274-296 + library.inl:258-284
+// + growthfactor.cpp:117-125), over Q (p == 0) or mod p.  L r x mk, R r x kn,
+// P mn x r as (num, den).  Outputs per candidate: nnz, nno (uint32) and G2
+// (double; only over Q, NaN otherwise).  Also applies the engine's
+// deterministic acceptance rule (lexicographic minimum, lowest index) and
+// returns the winner for measure 0 (nnz,nno) or 3 (G2).
+int orc_orbit_sweep(int64_t p, int m, int k, int n, int r, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn,
+                    const int64_t* Rd, const int64_t* Pn, const int64_t* Pd, int measure, int mode, uint64_t seed,
+                    uint64_t lo, uint64_t hi, int nthreads, uint32_t* out_nnz, uint32_t* out_nno, double* out_g2,
+                    uint64_t* best_index, uint32_t* best_nnz, uint32_t* best_nno, double* best_g2) {
+  g_overflow = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  uint64_t bidx = UINT64_MAX; uint32_t bnnz = UINT32_MAX, bnno = UINT32_MAX; double bg2 = INFINITY;
+  auto better = [&](uint32_t nnz, uint32_t nno, double g2, uint64_t idx) {
+    if (measure == 3) return g2 < bg2 || (g2 == bg2 && idx < bidx);
+    if (nnz != bnnz) return nnz < bnnz;
+    if (nno != bnno) return nno < bnno;
+    return idx < bidx;
+  };
+#pragma omp parallel
+  {
+    QField fq; ZpField fz{p ? p : 2};
+    Mat<QField> Lq, Rq, Pq; Mat<ZpField> Lz, Rz, Pz;
+    if (p == 0) {
+      Lq = Loader<QField>::load(fq, r, m * k, Ln, Ld); Rq = Loader<QField>::load(fq, r, k * n, Rn, Rd); Pq = Loader<QField>::load(fq, m * n, r, Pn, Pd);
+    } else {
+      Lz = Loader<ZpField>::load(fz, r, m * k, Ln, Ld); Rz = Loader<ZpField>::load(fz, r, k * n, Rn, Rd); Pz = Loader<ZpField>::load(fz, m * n, r, Pn, Pd);
+    }
+    std::vector<int32_t> U(m * m), V(k * k), W(n * n);
+#pragma omp for schedule(static)
+    for (uint64_t idx = lo; idx < hi; ++idx) {
+      orbitDecode(m, k, n, mode, seed, idx, U.data(), V.data(), W.data());
+      size_t nnz = 0, nno = 0; double g2 = NAN;
+      if (p == 0) {
+        Mat<QField> Lj, Rg, hP;
+        orbitApply(fq, m, k, n, Lq, Rq, Pq, U.data(), V.data(), W.data(), Lj, Rg, hP);
+        nonzeroes(fq, Lj, nnz, nno); nonzeroes(fq, Rg, nnz, nno); nonzeroes(fq, hP, nnz, nno);
+        g2 = G2(fq, Lj, Rg, hP);
+      } else {
+        Mat<ZpField> Lj, Rg, hP;
+        orbitApply(fz, m, k, n, Lz, Rz, Pz, U.data(), V.data(), W.data(), Lj, Rg, hP);
+        nonzeroes(fz, Lj, nnz, nno); nonzeroes(fz, Rg, nnz, nno); nonzeroes(fz, hP, nnz, nno);
+      }
+      if (out_nnz) out_nnz[idx - lo] = (uint32_t)nnz;
+      if (out_nno) out_nno[idx - lo] = (uint32_t)nno;
+      if (out_g2) out_g2[idx - lo] = g2;
+#pragma omp critical
+      {
+        if (better((uint32_t)nnz, (uint32_t)nno, g2, idx)) { bidx = idx; bnnz = (uint32_t)nnz; bnno = (uint32_t)nno; bg2 = g2; }
+      }
+    }
+  }
+  *best_index = bidx; *best_nnz = bnnz; *best_nno = bnno; *best_g2 = bg2;
+  return g_overflow ? -g_overflow : 0;
+}
+
+// Transformed triple of ONE candidate given explicit U,V,W (over Q).
+int orc_orbit_apply(int m, int k, int n, int r, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                    const int64_t* Pn, const int64_t* Pd, const int32_t* U, const int32_t* V, const int32_t* W,
+                    int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd, int64_t* oPn, int64_t* oPd) {
+  g_overflow = 0;
+  QField f;
+  Mat<QField> L = Loader<QField>::load(f, r, m * k, Ln, Ld), R = Loader<QField>::load(f, r, k * n, Rn, Rd), P = Loader<QField>::load(f, m * n, r, Pn, Pd);
+  Mat<QField> Lj, Rg, hP;
+  orbitApply(f, m, k, n, L, R, P, U, V, W, Lj, Rg, hP);
+  Loader<QField>::store(Lj, oLn, oLd); Loader<QField>::store(Rg, oRn, oRd); Loader<QField>::store(hP, oPn, oPd);
+  return g_overflow ? -g_overflow : 0;
+}
+
+// src/growthfactor.cpp:117-125 on one triple (L r x a, R r x b, P c x r).
+double orc_growth_G2(int r, int a, int b, int c, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                     const int64_t* Pn, const int64_t* Pd) {
+  QField f;
+  Mat<QField> L = Loader<QField>::load(f, r, a, Ln, Ld), R = Loader<QField>::load(f, r, b, Rn, Rd), P = Loader<QField>::load(f, c, r, Pn, Pd);
+  return G2(f, L, R, P);
+}
+
+// include/plinopt_library.h:177-181
+void orc_LRP2MM(int Lc, int Rc, int Pr, int* m, int* k, int* n) {
+  size_t a, b, c; LRP2MM((size_t)Lc, (size_t)Rc, (size_t)Pr, a, b, c); *m = (int)a; *k = (int)b; *n = (int)c;
+}
+
+// include/plinopt_library.inl:472-558  MMchecker on CSR inputs mod p, for the
+// sample vectors (ua, ub) supplied by the caller (the reference draws them
+// from a clock-seeded generator, :497-500).  Returns 0 correct / 1 not an MM
+// algorithm / 3 outer dimension mismatch.
+int orc_mmcheck_modp(int64_t p, int r, int Lc, int Rc, int Pr, const int64_t* Lptr, const int32_t* Lcol, const int64_t* Lval,
+                     const int64_t* Rptr, const int32_t* Rcol, const int64_t* Rval, const int64_t* Pptr,
+                     const int32_t* Pcol, const int64_t* Pval, const int64_t* ua, const int64_t* ub) {
+  size_t m, k, n; LRP2MM((size_t)Lc, (size_t)Rc, (size_t)Pr, m, k, n);
+  if ((size_t)Lc != m * k || (size_t)Rc != k * n || (size_t)Pr != m * n) return 3;  // :487-495
+  ZpField f{p};
+  std::vector<int64_t> va(r), vb(r), vc(r), wc(Pr);
+  for (int i = 0; i < r; ++i) {  // :504-505
+    int64_t s = 0; for (int64_t t = Lptr[i]; t < Lptr[i + 1]; ++t) s = f.add(s, f.mul(Lval[t], ua[Lcol[t]])); va[i] = s;
+    s = 0; for (int64_t t = Rptr[i]; t < Rptr[i + 1]; ++t) s = f.add(s, f.mul(Rval[t], ub[Rcol[t]])); vb[i] = s;
+    vc[i] = f.mul(va[i], vb[i]);  // :507
+  }
+  for (int i = 0; i < Pr; ++i) {  // :509
+    int64_t s = 0; for (int64_t t = Pptr[i]; t < Pptr[i + 1]; ++t) s = f.add(s, f.mul(Pval[t], vc[Pcol[t]])); wc[i] = s;
+  }
+  for (size_t i = 0; i < m; ++i) for (size_t j = 0; j < n; ++j) {  // :513-528
+    int64_t s = 0; for (size_t t = 0; t < k; ++t) s = f.add(s, f.mul(ua[i * k + t], ub[t * n + j]));
+    if (!f.isZero(f.sub(wc[i * n + j], s))) return 1;
+  }
+  return 0;
+}
+
+// Same over Q on dense (num,den) inputs (small cases).
+int orc_mmcheck_q(int r, int Lc, int Rc, int Pr, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                  const int64_t* Pn, const int64_t* Pd, const int64_t* ua, const int64_t* ub) {
+  g_overflow = 0;
+  size_t m, k, n; LRP2MM((size_t)Lc, (size_t)Rc, (size_t)Pr, m, k, n);
+  if ((size_t)Lc != m * k || (size_t)Rc != k * n || (size_t)Pr != m * n) return 3;
+  QField f;
+  Mat<QField> L = Loader<QField>::load(f, r, Lc, Ln, Ld), R = Loader<QField>::load(f, r, Rc, Rn, Rd), P = Loader<QField>::load(f, Pr, r, Pn, Pd);
+  Mat<QField> a(f, Lc, 1), b(f, Rc, 1);
+  for (int i = 0; i < Lc; ++i) a.a[i] = Rat{ua[i], 1};
+  for (int i = 0; i < Rc; ++i) b.a[i] = Rat{ub[i], 1};
+  Mat<QField> va = matmul(f, L, a), vb = matmul(f, R, b), vc(f, r, 1);
+  for (int i = 0; i < r; ++i) vc.a[i] = f.mul(va.a[i], vb.a[i]);
+  Mat<QField> wc = matmul(f, P, vc);
+  for (size_t i = 0; i < m; ++i) for (size_t j = 0; j < n; ++j) {
+    Rat s = f.zero(); for (size_t t = 0; t < k; ++t) s = f.add(s, f.mul(a.a[i * k + t], b.a[t * n + j]));
+    if (!f.isZero(f.sub(wc.a[i * n + j], s))) return 1;
+  }
+  return g_overflow ? -g_overflow : 0;
+}
+
+}  // extern "C"
