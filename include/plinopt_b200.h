@@ -1,0 +1,186 @@
+/* =============================================================================
+ * plinopt_b200.h -- C ABI of the B200-native candidate-search engine.
+ *
+ * Drop-in boundary for PLinOpt's one data-parallel hot path.
+ * The reference has no FFI; these entry points are what a maintainer binds from
+ * the reference's template functions (INTEGRATION.md shows the shims).  Plain
+ * pointers and sizes only, caller-owned buffers, int return codes, no
+ * exceptions, no torch types.  All reference citations are file:line relative
+ * to the reference root.
+ *
+ * Return codes: 0 success; PLO_E_* (< 0) on argument / CUDA errors (message via
+ * plo_last_error()).  Verdict-returning calls document their positive codes.
+ * ========================================================================== */
+#ifndef PLINOPT_B200_H
+#define PLINOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLO_OK 0
+#define PLO_E_ARG (-1)      /* bad argument (null pointer, size out of range)            */
+#define PLO_E_CUDA (-2)     /* CUDA runtime error, see plo_last_error()                  */
+#define PLO_E_RANGE (-3)    /* exact-integer magnitude bound exceeded (would overflow)   */
+#define PLO_E_SHAPE (-4)    /* (m,k,n) shape / size not supported by the compiled kernels */
+#define PLO_E_NODEVICE (-5) /* no CUDA device: there is NO CPU fallback                   */
+
+#define PLO_MEASURE_NNZ 0 /* src/orbiter.cpp:146-153 Operations<0> + nonzeroes tie-break */
+#define PLO_MEASURE_G2 3  /* src/growthfactor.cpp:117-125 G2                             */
+
+#define PLO_MODE_EXHAUSTIVE 0 /* index is a mixed-radix code of the digits               */
+#define PLO_MODE_PHILOX 1     /* digits drawn from Philox4x32-10(key=seed, ctr=index)    */
+
+#define PLO_NO_INDEX UINT64_MAX
+
+int plo_version(void);
+int plo_device_count(void);           /* number of visible CUDA devices (0 => every call returns PLO_E_NODEVICE) */
+int plo_set_device(int device);
+const char* plo_last_error(void);     /* thread-local message of the last failing call */
+
+/* ---------------------------------------------------------------------------
+ * Sparsifier candidate search.
+ * Replaces ONE (block,num) step of the quad loop of localSparsifier
+ *   include/plinopt_sparsify.inl:299-314   (for i,j,k,l in Coeffs^4, l fastest)
+ * together with the per-candidate body testLinComb
+ *   include/plinopt_sparsify.inl:166-197   (setRow+rank independence filter,
+ *                                           v = TM^T.w, zero counts, strict
+ *                                           lexicographic '>' acceptance).
+ *
+ * p == 0 : exact integers.  The caller pre-scales TM rows and coeffs by their
+ *          LCDs (zero patterns of v and w are scale invariant).  |values| must
+ *          keep every v_j inside int64, else PLO_E_RANGE.
+ * p  > 0 : residues mod p in [0,p), p < 2^32 (src/sparsifier.cpp:71-76).
+ * TM       n x m row-major (n = TM.rowdim() = width of the CoB block).
+ * off      4*block ; the candidate w has coeffs[i],[j],[k],[l] at positions
+ *          off..off+3 (positions >= n are truncated, reference quirk Q4).
+ * coeffs   c values in the reference's enumeration order (c <= 1024).
+ * prev_rows nprev x n : the rows of LCoB chosen so far (Cand rows 0..num-1,
+ *          plinopt_sparsify.inl:289,172); a candidate is admissible iff it is
+ *          linearly independent of them (rank(Cand) > num, :173-175).
+ * init_rl/init_cl  the weight seed (:290-295): (-1,-1) or the nullspace seed.
+ * Outputs: the weight after the loop and the index ((i*c+j)*c+k)*c+l of the
+ * accepted candidate = the FIRST maximiser in enumeration order (:183-184);
+ * *best_index == PLO_NO_INDEX if no candidate beat the seed.
+ * ------------------------------------------------------------------------ */
+int plo_lincomb_search(uint32_t p, int n, int m, const int64_t* TM, int off, int c, const int64_t* coeffs,
+                       int nprev, const int64_t* prev_rows, int init_rl, int init_cl,
+                       int* best_rl, int* best_cl, uint64_t* best_index);
+
+/* Same search for `nbatch` independent problems in one launch sequence (the
+ * independent column blocks of blockSparsifier, plinopt_sparsify.inl:710-723):
+ * problem b uses TM + b*n*m, coeffs + b*c, prev_rows + b*nprev*n, init_*[b]. */
+int plo_lincomb_search_batch(uint32_t p, int nbatch, int n, int m, const int64_t* TM, int off, int c,
+                             const int64_t* coeffs, int nprev, const int64_t* prev_rows, const int* init_rl,
+                             const int* init_cl, int* best_rl, int* best_cl, uint64_t* best_index);
+
+/* Device-resident variant used for throughput measurement: inputs are uploaded
+ * once, every plo_lincomb_plan_run() enqueues one full search on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream). */
+typedef struct plo_lincomb_plan plo_lincomb_plan;
+int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int n, int m, const int64_t* TM, int off,
+                            int c, const int64_t* coeffs, int nprev, const int64_t* prev_rows, const int* init_rl,
+                            const int* init_cl);
+int plo_lincomb_plan_run(plo_lincomb_plan* plan, void* stream);
+int plo_lincomb_plan_result(plo_lincomb_plan* plan, void* stream, int* best_rl, int* best_cl, uint64_t* best_index);
+uint64_t plo_lincomb_plan_candidates(const plo_lincomb_plan* plan); /* candidates scored per run            */
+int plo_lincomb_plan_launches(const plo_lincomb_plan* plan);         /* kernel launches per run              */
+void plo_lincomb_plan_destroy(plo_lincomb_plan* plan);
+
+/* ---------------------------------------------------------------------------
+ * DeGroote-orbit sweep.
+ * Replaces the whole `omp parallel for` + `omp critical` loop of
+ *   src/orbiter.cpp:272-324
+ * i.e. per candidate: zoiRandomMatrix x3 (:59-75,125-136), inverse /
+ * inverseTranspose (plinopt_sparsify.inl:380-465), Tensor
+ * (plinopt_library.inl:210-223), the three products (:288-294), the measure
+ * (density/nonzeroes plinopt_library.inl:238-284, or G2 growthfactor.cpp:117-125)
+ * and the keep-best rule (:298-323, made deterministic: lexicographic minimum,
+ * lowest index among ties).
+ *
+ * L  r x (m*k), R  r x (k*n), P  (m*n) x r, row-major, entries pre-scaled to
+ * integers: true matrix = L/denL etc.  (p must be 0 in this version: exact
+ * integers.)  Candidate `index` in [lo,hi) is decoded to (U,V,W) by the
+ * counter-based decode documented in DESIGN.md (identical on host and device,
+ * see plo_orbit_decode).
+ * ------------------------------------------------------------------------ */
+typedef struct plo_orbit_best {
+  double score;   /* measure 0: (double)nnz ; measure 3: G2                    */
+  uint32_t nnz;   /* nnz(Lj)+nnz(Rg)+nnz(hP)      (plinopt_library.inl:279-284) */
+  uint32_t nno;   /* entries not in {0,+1,-1}                                   */
+  uint64_t index; /* winning candidate, PLO_NO_INDEX if lo >= hi                */
+} plo_orbit_best;
+
+int plo_orbit_sweep(uint32_t p, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P,
+                    int32_t denL, int32_t denR, int32_t denP, int measure, int mode, uint64_t seed, uint64_t lo,
+                    uint64_t hi, plo_orbit_best* best);
+
+/* index -> (U,V,W), row-major int32 in {-1,0,1}; pure host function, bit-identical to the device decode. */
+int plo_orbit_decode(int m, int k, int n, int mode, uint64_t seed, uint64_t index, int32_t* U, int32_t* V, int32_t* W);
+/* size of the exhaustive candidate space (0 if it does not fit in 64 bits) */
+uint64_t plo_orbit_space(int m, int k, int n);
+
+/* Per-candidate table (nnz, nno, g2) for [lo,hi): parity / debugging; any output may be NULL. */
+int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int32_t denL,
+                    int32_t denR, int32_t denP, int mode, uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* nnz,
+                    uint32_t* nno, double* g2);
+
+/* Device-resident plan (throughput measurement / multi-GPU sharding). */
+typedef struct plo_orbit_plan plo_orbit_plan;
+int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, const int32_t* L, const int32_t* R,
+                          const int32_t* P, int32_t denL, int32_t denR, int32_t denP, int measure, int mode,
+                          uint64_t seed);
+int plo_orbit_plan_run(plo_orbit_plan* plan, uint64_t lo, uint64_t hi, void* stream);
+int plo_orbit_plan_result(plo_orbit_plan* plan, void* stream, plo_orbit_best* best);
+int plo_orbit_plan_launches(const plo_orbit_plan* plan);
+void plo_orbit_plan_destroy(plo_orbit_plan* plan);
+
+/* ---------------------------------------------------------------------------
+ * Growth factor G2 of explicit triples  (src/growthfactor.cpp:117-125, rows
+ * converted to double before squaring :25-28,41-44).  Dense double inputs,
+ * `batch` triples stored back to back; out[b] = sum_i |L_i| |R_i| |P^T_i|.
+ * ------------------------------------------------------------------------ */
+int plo_growth_G2(int batch, int r, int a, int b, int c, const double* L, const double* R, const double* P, double* out);
+
+/* ---------------------------------------------------------------------------
+ * Batched MMchecker mod p.
+ * Replaces PLinOpt::MMchecker  include/plinopt_library.inl:472-558 for `batch`
+ * independent random evaluations: wc = P.((L.ua) o (R.ub)) against the direct
+ * product reshape(ua).reshape(ub)  (:504-528).
+ * CSR inputs with residues in [0,p), p < 2^32 odd or 2 (src/MMchecker.cpp:123-126).
+ * ua (batch x m*k) / ub (batch x k*n) may be NULL: then they are Philox words
+ * mod p drawn from (seed, sample index).  ok[s] = 1 iff sample s agrees.
+ * Returns 0 (all samples agree: "correct"), 1 (some sample disagrees: not an MM
+ * algorithm, :555), 3 (outer dimension mismatch, :494) or PLO_E_*.
+ * ------------------------------------------------------------------------ */
+typedef struct plo_csr {
+  int rows, cols;
+  const int64_t* ptr;  /* rows+1 */
+  const int32_t* col;  /* nnz    */
+  const uint32_t* val; /* nnz residues */
+} plo_csr;
+
+int plo_mmcheck_batch(uint32_t p, int m, int k, int n, int r, const plo_csr* L, const plo_csr* R, const plo_csr* P,
+                      uint64_t seed, int batch, const uint32_t* ua, const uint32_t* ub, uint8_t* ok);
+
+typedef struct plo_mmcheck_plan plo_mmcheck_plan;
+int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, int n, int r, const plo_csr* L,
+                            const plo_csr* R, const plo_csr* P, int batch);
+int plo_mmcheck_plan_run(plo_mmcheck_plan* plan, uint64_t seed, uint64_t first_sample, void* stream);
+int plo_mmcheck_plan_result(plo_mmcheck_plan* plan, void* stream, uint8_t* ok, int* verdict);
+int plo_mmcheck_plan_launches(const plo_mmcheck_plan* plan);
+void plo_mmcheck_plan_destroy(plo_mmcheck_plan* plan);
+
+/* ---------------------------------------------------------------------------
+ * Roofline denominators that MEASURED_PEAKS.json does not hold: register-
+ * resident unrolled IMAD / DFMA / (ISETP+IADD) loops over all SMs, CUDA-event
+ * timed, best of `reps`.  Results in operations per second.
+ * ------------------------------------------------------------------------ */
+int plo_measure_peaks(int reps, double* imad_per_s, double* dfma_per_s, double* ialu_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLINOPT_B200_H */

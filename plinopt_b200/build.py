@@ -1,0 +1,68 @@
+"""Builds libplinopt_b200.so (hand-written sm_100a kernels + the extern "C" ABI of
+include/plinopt_b200.h) in-tree with nvcc.  No torch dependency: the library is
+a plain C-ABI shared object (cudart linked statically)."""
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libplinopt_b200.so")
+SOURCES = ["common.cu", "orbit_sweep.cu", "lincomb_search.cu", "mmcheck.cu", "peaks.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    nv = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nv):
+        raise RuntimeError("nvcc not found")
+    return nv
+
+
+def _deps(src):
+    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "plo_device.cuh"), os.path.join(CSRC, "host", "exact.hpp"),
+            os.path.join(os.path.dirname(HERE), "include", "plinopt_b200.h"), os.path.abspath(__file__)]
+    return max(os.path.getmtime(d) for d in deps if os.path.exists(d))
+
+
+def build_library(force=False, verbose=False):
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = _nvcc()
+    host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
+    ccbin = ["-ccbin", host_cxx] if host_cxx else []
+    objs, jobs = [], []
+    for s in SOURCES:
+        o = os.path.join(BUILD, s.replace(".cu", ".o"))
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < _deps(s):
+            jobs.append((s, o))
+
+    def compile_one(job):
+        s, o = job
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        with open(o + ".log", "w") as f:
+            f.write(" ".join(cmd) + "\n" + p.stdout + p.stderr)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n{p.stdout}\n{p.stderr}")
+        return s
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for s in ex.map(compile_one, jobs):
+                if verbose:
+                    print("compiled", s, file=sys.stderr)
+    if jobs or force or not os.path.exists(LIB):
+        cmd = [nvcc] + ccbin + ["-shared", "-cudart", "static", "-o", LIB] + objs
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,316 @@
+"""ctypes binding of the C ABI declared in include/plinopt_b200.h.
+
+This is the same binding a reference maintainer would write:
+plain pointers and sizes, caller-owned numpy buffers.  The library is the
+product: if libplinopt_b200.so is missing or no CUDA device is visible every
+compute call raises -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libplinopt_b200.so")
+
+OK = 0
+E_ARG, E_CUDA, E_RANGE, E_SHAPE, E_NODEVICE = -1, -2, -3, -4, -5
+MEASURE_NNZ, MEASURE_G2 = 0, 3
+MODE_EXHAUSTIVE, MODE_PHILOX = 0, 1
+NO_INDEX = 2 ** 64 - 1
+
+# every symbol include/plinopt_b200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "plo_version", "plo_device_count", "plo_set_device", "plo_last_error",
+    "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run",
+    "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
+    "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
+    "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
+    "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
+    "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
+]
+
+
+class PloError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"plinopt_b200 error {code}: {msg}")
+        self.code = code
+
+
+class OrbitBest(C.Structure):
+    _fields_ = [("score", C.c_double), ("nnz", C.c_uint32), ("nno", C.c_uint32), ("index", C.c_uint64)]
+
+
+class Csr(C.Structure):
+    _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("ptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (raises if it was not built: no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PloError(E_NODEVICE, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.plo_last_error.restype = C.c_char_p
+        L.plo_orbit_space.restype = C.c_uint64
+        L.plo_lincomb_plan_candidates.restype = C.c_uint64
+        L.plo_lincomb_plan_candidates.argtypes = [C.c_void_p]
+        L.plo_lincomb_plan_launches.argtypes = [C.c_void_p]
+        L.plo_lincomb_plan_destroy.argtypes = [C.c_void_p]
+        L.plo_lincomb_plan_destroy.restype = None
+        L.plo_orbit_plan_destroy.argtypes = [C.c_void_p]
+        L.plo_orbit_plan_destroy.restype = None
+        L.plo_orbit_plan_launches.argtypes = [C.c_void_p]
+        L.plo_mmcheck_plan_destroy.argtypes = [C.c_void_p]
+        L.plo_mmcheck_plan_destroy.restype = None
+        L.plo_mmcheck_plan_launches.argtypes = [C.c_void_p]
+        L.plo_orbit_plan_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.plo_orbit_plan_result.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(OrbitBest)]
+        L.plo_lincomb_plan_run.argtypes = [C.c_void_p, C.c_void_p]
+        L.plo_mmcheck_plan_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc, allow=()):
+    if rc != 0 and rc not in allow:
+        raise PloError(rc, lib().plo_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def device_count():
+    return lib().plo_device_count()
+
+
+def set_device(d):
+    _check(lib().plo_set_device(int(d)))
+
+
+# --------------------------------------------------------------------------
+# sparsifier candidate search
+# --------------------------------------------------------------------------
+def lincomb_search(p, TM, off, coeffs, prev_rows=None, init_rl=-1, init_cl=-1):
+    """One (block,num) step: returns (best_rl, best_cl, best_index or None)."""
+    TM = _i64(TM); coeffs = _i64(coeffs)
+    n, m = TM.shape
+    prev = _i64(prev_rows) if prev_rows is not None and len(prev_rows) else None
+    nprev = 0 if prev is None else prev.shape[0]
+    rl, cl, idx = C.c_int(), C.c_int(), C.c_uint64()
+    f = lib().plo_lincomb_search
+    f.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                  C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    _check(f(int(p), n, m, _ptr(TM), int(off), len(coeffs), _ptr(coeffs), nprev, _ptr(prev), int(init_rl), int(init_cl),
+             C.byref(rl), C.byref(cl), C.byref(idx)))
+    return rl.value, cl.value, (None if idx.value == NO_INDEX else idx.value)
+
+
+class LincombPlan:
+    """Device-resident batch of independent searches (plo_lincomb_plan_*)."""
+
+    def __init__(self, p, TM, off, coeffs, prev_rows=None, init_rl=None, init_cl=None):
+        TM = _i64(TM); coeffs = _i64(coeffs)
+        if TM.ndim == 2:
+            TM = TM[None]; coeffs = coeffs[None]
+            prev_rows = None if prev_rows is None else _i64(prev_rows)[None]
+        self.nbatch, n, m = TM.shape
+        prev = _i64(prev_rows) if prev_rows is not None and np.size(prev_rows) else None
+        nprev = 0 if prev is None else prev.shape[1]
+        irl = None if init_rl is None else _i32(np.broadcast_to(init_rl, (self.nbatch,)))
+        icl = None if init_cl is None else _i32(np.broadcast_to(init_cl, (self.nbatch,)))
+        self._h = C.c_void_p()
+        f = lib().plo_lincomb_plan_create
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(f(C.byref(self._h), int(p), self.nbatch, n, m, _ptr(TM), int(off), coeffs.shape[1], _ptr(coeffs), nprev,
+                 _ptr(prev), _ptr(irl), _ptr(icl)))
+        self.candidates = lib().plo_lincomb_plan_candidates(self._h)
+        self.launches = lib().plo_lincomb_plan_launches(self._h)
+
+    def run(self, stream=0):
+        _check(lib().plo_lincomb_plan_run(self._h, C.c_void_p(stream)))
+
+    def result(self, stream=0):
+        rl = np.zeros(self.nbatch, dtype=np.int32); cl = np.zeros(self.nbatch, dtype=np.int32)
+        idx = np.zeros(self.nbatch, dtype=np.uint64)
+        f = lib().plo_lincomb_plan_result
+        f.argtypes = [C.c_void_p] * 5
+        _check(f(self._h, C.c_void_p(stream), _ptr(rl), _ptr(cl), _ptr(idx)))
+        return rl, cl, idx
+
+    def close(self):
+        if self._h:
+            lib().plo_lincomb_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------
+# orbit sweep
+# --------------------------------------------------------------------------
+def orbit_decode(m, k, n, mode, seed, index):
+    U = np.zeros((m, m), dtype=np.int32); V = np.zeros((k, k), dtype=np.int32); W = np.zeros((n, n), dtype=np.int32)
+    f = lib().plo_orbit_decode
+    f.argtypes = [C.c_int] * 4 + [C.c_uint64, C.c_uint64] + [C.c_void_p] * 3
+    _check(f(m, k, n, mode, seed, index, _ptr(U), _ptr(V), _ptr(W)))
+    return U, V, W
+
+
+def orbit_space(m, k, n):
+    f = lib().plo_orbit_space
+    f.argtypes = [C.c_int] * 3
+    return f(m, k, n)
+
+
+def _best_tuple(b):
+    return dict(score=b.score, nnz=b.nnz, nno=b.nno, index=(None if b.index == NO_INDEX else b.index))
+
+
+def orbit_sweep(mkn, L, R, P, dens, measure, mode, seed, lo, hi, p=0):
+    """Host-buffer entry point (copies inside): returns dict(score, nnz, nno, index)."""
+    m, k, n = mkn
+    L = _i32(L); R = _i32(R); P = _i32(P)
+    best = OrbitBest()
+    f = lib().plo_orbit_sweep
+    f.argtypes = [C.c_uint32] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                  C.c_uint64, C.POINTER(OrbitBest)]
+    _check(f(p, m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), dens[0], dens[1], dens[2], measure, mode, seed, lo, hi, C.byref(best)))
+    return _best_tuple(best)
+
+
+def orbit_table(mkn, L, R, P, dens, mode, seed, lo, hi):
+    m, k, n = mkn
+    L = _i32(L); R = _i32(R); P = _i32(P)
+    cnt = hi - lo
+    nnz = np.zeros(cnt, dtype=np.uint32); nno = np.zeros(cnt, dtype=np.uint32); g2 = np.zeros(cnt, dtype=np.float64)
+    f = lib().plo_orbit_table
+    f.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 3
+    _check(f(m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), dens[0], dens[1], dens[2], mode, seed, lo, hi, _ptr(nnz), _ptr(nno), _ptr(g2)))
+    return nnz, nno, g2
+
+
+class OrbitPlan:
+    def __init__(self, mkn, L, R, P, dens, measure, mode, seed):
+        m, k, n = mkn
+        L = _i32(L); R = _i32(R); P = _i32(P)
+        self._h = C.c_void_p()
+        f = lib().plo_orbit_plan_create
+        f.argtypes = [C.POINTER(C.c_void_p)] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_int, C.c_int, C.c_uint64]
+        _check(f(C.byref(self._h), m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), dens[0], dens[1], dens[2], measure, mode, seed))
+        self.launches = lib().plo_orbit_plan_launches(self._h)
+
+    def run(self, lo, hi, stream=0):
+        _check(lib().plo_orbit_plan_run(self._h, lo, hi, C.c_void_p(stream)))
+
+    def result(self, stream=0):
+        best = OrbitBest()
+        _check(lib().plo_orbit_plan_result(self._h, C.c_void_p(stream), C.byref(best)))
+        return _best_tuple(best)
+
+    def close(self):
+        if self._h:
+            lib().plo_orbit_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def growth_G2(L, R, P):
+    """G2 of dense double triples; L (batch, r, a), R (batch, r, b), P (batch, c, r)."""
+    L = np.ascontiguousarray(L, dtype=np.float64); R = np.ascontiguousarray(R, dtype=np.float64); P = np.ascontiguousarray(P, dtype=np.float64)
+    if L.ndim == 2:
+        L, R, P = L[None], R[None], P[None]
+    batch, r, a = L.shape
+    out = np.zeros(batch, dtype=np.float64)
+    f = lib().plo_growth_G2
+    f.argtypes = [C.c_int] * 5 + [C.c_void_p] * 4
+    _check(f(batch, r, a, R.shape[2], P.shape[1], _ptr(L), _ptr(R), _ptr(P), _ptr(out)))
+    return out
+
+
+# --------------------------------------------------------------------------
+# MMchecker
+# --------------------------------------------------------------------------
+class _CsrHolder:
+    def __init__(self, rows, cols, ptr, col, val):
+        self.ptr = _i64(ptr); self.col = _i32(col); self.val = np.ascontiguousarray(val, dtype=np.uint32)
+        self.c = Csr(rows, cols, self.ptr.ctypes.data, self.col.ctypes.data, self.val.ctypes.data)
+
+
+def mmcheck_batch(p, mkn, r, L, R, P, seed=0, batch=1, ua=None, ub=None):
+    """L,R,P = (rows, cols, ptr, col, val) CSR tuples.  Returns (verdict, ok[batch])."""
+    m, k, n = mkn
+    hl, hr, hp = _CsrHolder(*L), _CsrHolder(*R), _CsrHolder(*P)
+    ok = np.zeros(batch, dtype=np.uint8)
+    a = None if ua is None else np.ascontiguousarray(ua, dtype=np.uint32)
+    b = None if ub is None else np.ascontiguousarray(ub, dtype=np.uint32)
+    f = lib().plo_mmcheck_batch
+    f.argtypes = [C.c_uint32] + [C.c_int] * 4 + [C.POINTER(Csr)] * 3 + [C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = _check(f(p, m, k, n, r, C.byref(hl.c), C.byref(hr.c), C.byref(hp.c), seed, batch, _ptr(a), _ptr(b), _ptr(ok)), allow=(1, 2, 3))
+    return rc, ok
+
+
+class MMcheckPlan:
+    def __init__(self, p, mkn, r, L, R, P, batch):
+        m, k, n = mkn
+        self._keep = (_CsrHolder(*L), _CsrHolder(*R), _CsrHolder(*P))
+        self.batch = batch
+        self._h = C.c_void_p()
+        f = lib().plo_mmcheck_plan_create
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_uint32] + [C.c_int] * 4 + [C.POINTER(Csr)] * 3 + [C.c_int]
+        _check(f(C.byref(self._h), p, m, k, n, r, C.byref(self._keep[0].c), C.byref(self._keep[1].c), C.byref(self._keep[2].c), batch))
+        self.launches = lib().plo_mmcheck_plan_launches(self._h)
+
+    def run(self, seed, first_sample=0, stream=0):
+        _check(lib().plo_mmcheck_plan_run(self._h, seed, first_sample, C.c_void_p(stream)))
+
+    def result(self, stream=0):
+        ok = np.zeros(self.batch, dtype=np.uint8)
+        v = C.c_int()
+        f = lib().plo_mmcheck_plan_result
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        _check(f(self._h, C.c_void_p(stream), _ptr(ok), C.byref(v)))
+        return v.value, ok
+
+    def close(self):
+        if self._h:
+            lib().plo_mmcheck_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def measure_peaks(reps=10):
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    f = lib().plo_measure_peaks
+    f.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3
+    _check(f(reps, C.byref(a), C.byref(b), C.byref(c)))
+    return dict(imad_per_s=a.value, dfma_per_s=b.value, ialu_pairs_per_s=c.value)

@@ -1,0 +1,490 @@
+// lincomb_search.cu -- sparsifier candidate scoring on sm_100a.
+//
+// Replaces one (block,num) step of the reference's quad loop
+//   include/plinopt_sparsify.inl:299-314  (i,j,k,l over Coeffs^4, l fastest)
+// and its per-candidate body testLinComb
+//   include/plinopt_sparsify.inl:166-197  (setRow + rank, v = TM^T.w, two
+//                                          zero counts, strict '>' keep-best).
+//
+// Formulation (exact, no multiplications on the device):
+//   v(i,j,k,l) = C_i.TM[off] + C_j.TM[off+1] + C_k.TM[off+2] + C_l.TM[off+3]
+// The host tabulates the c x m products C_x.TM[off+t] once (4 tables, in the
+// field: integers, or residues mod p).  A thread owns a prefix (i,j,k), sums
+// three table rows into nb_j = -(base_j) (m registers) and then, for every l,
+// counts the coordinates with  T3[l][j] == nb_j  -- one compare per output
+// coordinate per candidate, T3 being read warp-uniformly from shared memory.
+// The independence filter (rank(Cand) > num) is evaluated lazily, only for a
+// candidate that would beat the thread's running best: w is independent of the
+// previous rows iff some annihilator functional phi_q of their span has
+// phi_q.w != 0 (<= 4 functionals restricted to the 4 live positions).
+// Winner = maximum of the packed key (rl, cl, -index): equals the reference's
+// strict-'>' first-maximiser rule and is associative, so the warp-shuffle /
+// block / atomicMax reduction is deterministic for any launch geometry.
+#include <type_traits>
+#include <vector>
+
+#include "host/exact.hpp"
+#include "plo_device.cuh"
+
+namespace plo {
+
+constexpr int kLcThreads = 128;
+constexpr int kIdxBits = 36;
+constexpr unsigned long long kIdxMask = (1ull << kIdxBits) - 1ull;
+
+// key = (rl+1) << 48 | (cl+1) << 36 | (2^36 - 2 - index); the weight seed uses low bits 2^36-1
+__host__ __device__ __forceinline__ unsigned long long pack_key(int rl, int cl, unsigned long long low) {
+  return ((unsigned long long)(rl + 1) << 48) | ((unsigned long long)(cl + 1) << kIdxBits) | low;
+}
+
+template <typename T>
+struct LcParams {
+  int c, m, nact, lsplit, ltile, nphi_max;
+  unsigned int p;
+  int cl_const;
+  const T* t0;   // [b][l][MPAD]
+  const T* t1;   // [b][l][MPAD]
+  const T* t2;   // [b][MPAD][c]   (transposed: consecutive k coalesce)
+  const T* t3;   // [b][l][MPAD]
+  const unsigned char* zflag;       // [b][4][c]   coefficient is zero at an active position
+  const long long* phi;             // [b][4][4]   annihilator functionals on the live positions
+  const int* nphi;                  // [b]
+  const long long* coef;            // [b][c]      coefficient values (ints / canonical residues)
+  const unsigned long long* seed;   // [b]
+  unsigned long long* result;       // [b]
+};
+
+template <bool MODP>
+__device__ __forceinline__ bool independent(const long long* __restrict__ phi, int nphi, const long long* __restrict__ coef,
+                                            unsigned int p, int i, int j, int k, int l) {
+  const long long w[4] = {coef[i], coef[j], coef[k], coef[l]};
+  for (int q = 0; q < nphi; ++q) {
+    if (MODP) {
+      unsigned long long s = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) s += ((unsigned long long)phi[q * 4 + t] * (unsigned long long)w[t]) % p;
+      if (s % p) return true;
+    } else {
+      long long s = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) s += phi[q * 4 + t] * w[t];
+      if (s) return true;
+    }
+  }
+  return false;
+}
+
+template <typename T, int MPAD, bool MODP>
+__global__ void __launch_bounds__(kLcThreads) lincomb_kernel(const LcParams<T> prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* t3s = reinterpret_cast<T*>(smem_raw);
+  __shared__ unsigned long long red[32];
+  constexpr int VEC = 16 / sizeof(T);  // elements per 128-bit shared load
+  const int b = blockIdx.y;
+  const int c = prm.c;
+  const size_t tab = (size_t)c * MPAD;
+  const T* __restrict__ t0 = prm.t0 + b * tab;
+  const T* __restrict__ t1 = prm.t1 + b * tab;
+  const T* __restrict__ t2 = prm.t2 + b * tab;
+  const T* __restrict__ t3 = prm.t3 + b * tab;
+  const unsigned char* __restrict__ zf = prm.zflag + (size_t)b * 4 * c;
+  const long long* __restrict__ phi = prm.phi + b * 16;
+  const long long* __restrict__ coef = prm.coef + (size_t)b * c;
+  const int nphi = prm.nphi[b];
+  const T SENT = (T)(~(T)0) >> (MODP ? 0 : 1);  // never a residue (p <= 2^32-1) / beyond the integer bound
+
+  unsigned long long best = prm.seed[b];
+  const unsigned long long nprefix = (unsigned long long)c * c * c;
+  const unsigned long long nitems = nprefix * (unsigned long long)prm.lsplit;
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * kLcThreads;
+
+  for (int l0 = 0; l0 < c; l0 += prm.ltile) {
+    const int l1 = min(c, l0 + prm.ltile);
+    __syncthreads();
+    {  // stage the T3 tile
+      const uint4* src = reinterpret_cast<const uint4*>(t3 + (size_t)l0 * MPAD);
+      uint4* dst = reinterpret_cast<uint4*>(t3s);
+      const int nvec = (l1 - l0) * MPAD / VEC;
+      for (int e = threadIdx.x; e < nvec; e += kLcThreads) dst[e] = src[e];
+    }
+    __syncthreads();
+    const int lc = (l1 - l0 + prm.lsplit - 1) / prm.lsplit;
+    for (unsigned long long item = (unsigned long long)blockIdx.x * kLcThreads + threadIdx.x; item < nitems; item += nthreads) {
+      const unsigned long long q = item / (unsigned)prm.lsplit;
+      const int s = (int)(item - q * (unsigned)prm.lsplit);
+      const int la = l0 + s * lc, lb = min(l1, la + lc);
+      if (la >= lb) continue;
+      const int k = (int)(q % (unsigned)c);
+      const unsigned long long qq = q / (unsigned)c;
+      const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
+      T nb[MPAD];
+#pragma unroll
+      for (int e = 0; e < MPAD; ++e) {
+        const T a0 = t0[(size_t)i * MPAD + e], a1 = t1[(size_t)j * MPAD + e], a2 = t2[(size_t)e * c + k];
+        if (MODP) {
+          unsigned long long sum = (unsigned long long)a0 + a1 + a2;  // < 3p
+          sum -= sum >= prm.p ? prm.p : 0u;
+          sum -= sum >= prm.p ? prm.p : 0u;
+          nb[e] = (T)(sum ? prm.p - sum : 0ull);
+        } else {
+          nb[e] = (T)0 - (a0 + a1 + a2);
+        }
+        if (e >= prm.m) nb[e] = SENT;
+      }
+      const int zc = prm.cl_const + zf[i] + zf[c + j] + zf[2 * c + k];
+      int best_rl1 = (int)(best >> 48);  // rl+1 of the running best
+      for (int l = la; l < lb; ++l) {
+        const T* row = t3s + (size_t)(l - l0) * MPAD;
+        int rl = 0;
+#pragma unroll
+        for (int e4 = 0; e4 < MPAD / VEC; ++e4) {
+          const uint4 u = reinterpret_cast<const uint4*>(row)[e4];
+          if (sizeof(T) == 4) {
+            rl += (nb[e4 * 4 + 0] == (T)u.x);
+            rl += (nb[e4 * 4 + 1] == (T)u.y);
+            rl += (nb[e4 * 4 + 2] == (T)u.z);
+            rl += (nb[e4 * 4 + 3] == (T)u.w);
+          } else {
+            rl += (nb[e4 * 2 + 0] == (T)(((unsigned long long)u.y << 32) | u.x));
+            rl += (nb[e4 * 2 + 1] == (T)(((unsigned long long)u.w << 32) | u.z));
+          }
+        }
+        if (rl + 1 >= best_rl1) {
+          const int cl = zc + zf[3 * c + l];
+          const unsigned long long idx = q * (unsigned)c + (unsigned)l;
+          const unsigned long long key = pack_key(rl, cl, kIdxMask - 1ull - idx);
+          if (key > best && independent<MODP>(phi, nphi, coef, prm.p, i, j, k, l)) {
+            best = key;
+            best_rl1 = rl + 1;
+          }
+        }
+      }
+    }
+  }
+  // block reduction (max), then one atomicMax per block
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+    best = o > best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long v = threadIdx.x < (kLcThreads >> 5) ? red[threadIdx.x] : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
+      v = o > v ? o : v;
+    }
+    if (threadIdx.x == 0) atomicMax(prm.result + b, v);
+  }
+}
+
+__global__ void lincomb_init_kernel(unsigned long long* result, const unsigned long long* seed, int nbatch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nbatch) result[b] = seed[b];
+}
+
+template <typename T, bool MODP>
+static cudaError_t launch_lincomb(int mpad, dim3 grid, size_t smem, cudaStream_t st, const LcParams<T>& prm) {
+#define PLO_LC_CASE(MP)                                                                                       \
+  case MP: {                                                                                                  \
+    auto kern = lincomb_kernel<T, MP, MODP>;                                                                  \
+    if (smem > 48 * 1024) {                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      if (e != cudaSuccess) return e;                                                                         \
+    }                                                                                                         \
+    kern<<<grid, kLcThreads, smem, st>>>(prm);                                                                \
+    break;                                                                                                    \
+  }
+  switch (mpad) {
+    PLO_LC_CASE(8) PLO_LC_CASE(16) PLO_LC_CASE(32) PLO_LC_CASE(48) PLO_LC_CASE(64)
+    default: return cudaErrorInvalidValue;
+  }
+#undef PLO_LC_CASE
+  return cudaGetLastError();
+}
+
+}  // namespace plo
+
+using namespace plo;
+
+struct plo_lincomb_plan {
+  uint32_t p;
+  int nbatch, n, m, off, c, nprev, mpad, width;  // width: 4 or 8 bytes per element
+  std::vector<unsigned long long> h_seed;
+  std::vector<int> h_init_rl, h_init_cl;
+  std::vector<char> trivially_none;  // previous rows dependent: no admissible candidate
+  void* d_tables;                    // t0 | t1 | t2 | t3
+  unsigned char* d_zflag;
+  long long* d_phi;
+  int* d_nphi;
+  long long* d_coef;
+  unsigned long long *d_seed, *d_result;
+  int lsplit, ltile, grid;
+  size_t smem;
+};
+
+namespace {
+
+inline int pad_m(int m) {
+  const int opts[] = {8, 16, 32, 48, 64};
+  for (int o : opts) if (m <= o) return o;
+  return -1;
+}
+
+// One reduced functional -> integers: clear denominators over Q; residues are used as they are mod p.
+inline void phi_row(const plo::host::QField&, const plo::host::Rat* row, long long* out) {
+  long long lcd = 1;
+  for (int t = 0; t < 4; ++t) { const long long g = (long long)plo::host::wgcd(lcd, row[t].den); lcd = lcd / g * row[t].den; }
+  for (int t = 0; t < 4; ++t) out[t] = row[t].num * (lcd / row[t].den);
+}
+inline void phi_row(const plo::host::ZpField&, const int64_t* row, long long* out) {
+  for (int t = 0; t < 4; ++t) out[t] = row[t];
+}
+
+// Annihilator functionals of span(prev rows) restricted to the live positions off..off+nact-1,
+// reduced to an independent set (<= 4 vectors of 4 entries).  Returns false if the previous rows
+// are linearly dependent (then rank(Cand) can never exceed num: plinopt_sparsify.inl:173-175).
+template <class F>
+bool annihilators(const F& f, int n, int nprev, const int64_t* prev, int off, int nact, std::vector<long long>& phi, int& nphi) {
+  using namespace plo::host;
+  phi.assign(16, 0);
+  nphi = 0;
+  std::vector<std::vector<typename F::Elt>> basis;
+  if (nprev == 0) {
+    for (int t = 0; t < nact; ++t) { phi[nphi * 4 + t] = 1; ++nphi; }  // everything non-zero is independent
+    return true;
+  }
+  Dense<F> A(f, (size_t)nprev, (size_t)n);
+  for (int i = 0; i < nprev; ++i)
+    for (int j = 0; j < n; ++j) A.at(i, j) = f.modular ? f.from_ratio(prev[(size_t)i * n + j], 1) : f.from_int(prev[(size_t)i * n + j]);
+  size_t rk = 0;
+  basis = nullspace(f, A, &rk);
+  if ((int)rk < nprev) return false;
+  Dense<F> R(f, basis.size(), 4);
+  for (size_t q = 0; q < basis.size(); ++q)
+    for (int t = 0; t < nact; ++t) R.at(q, t) = basis[q][off + t];
+  const std::vector<size_t> piv = rref(f, R);
+  for (size_t q = 0; q < piv.size(); ++q) {
+    phi_row(f, &R.at(q, 0), &phi[(size_t)nphi * 4]);
+    ++nphi;
+  }
+  return true;
+}
+
+template <typename T>
+void fill_tables(uint32_t p, int n, int m, int off, int nact, int c, int mpad, const int64_t* TM, const int64_t* coef,
+                 T* t0, T* t1, T* t2, T* t3) {
+  const size_t tab = (size_t)c * mpad;
+  T* tabs[4] = {t0, t1, t2, t3};
+  for (int t = 0; t < 4; ++t) std::fill(tabs[t], tabs[t] + tab, (T)0);
+  for (int t = 0; t < nact; ++t) {
+    const int64_t* row = TM + (size_t)(off + t) * m;
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < m; ++j) {
+        T val;
+        if (p) val = (T)(((unsigned __int128)(uint64_t)coef[l] * (uint64_t)row[j]) % p);
+        else val = (T)(coef[l] * row[j]);
+        if (t == 2) t2[(size_t)j * c + l] = val;
+        else tabs[t][(size_t)l * mpad + j] = val;
+      }
+  }
+  (void)n;
+}
+
+}  // namespace
+
+extern "C" {
+
+void plo_lincomb_plan_destroy(plo_lincomb_plan* pl) {
+  if (!pl) return;
+  cudaFree(pl->d_tables); cudaFree(pl->d_zflag); cudaFree(pl->d_phi); cudaFree(pl->d_nphi);
+  cudaFree(pl->d_coef); cudaFree(pl->d_seed); cudaFree(pl->d_result);
+  delete pl;
+}
+
+int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int n, int m, const int64_t* TM, int off,
+                            int c, const int64_t* coeffs, int nprev, const int64_t* prev_rows, const int* init_rl,
+                            const int* init_cl) {
+  if (!plan || !TM || !coeffs || nbatch < 1 || n < 1 || m < 1 || c < 1 || c > 512 || off < 0 || off >= n || (off & 3) ||
+      nprev < 0 || nprev > n || (nprev > 0 && !prev_rows) || n > 4000 || m > 65000) {
+    set_error("plo_lincomb_plan_create: bad argument");
+    return PLO_E_ARG;
+  }
+  int rc = check_device();
+  if (rc) return rc;
+  const int mpad = pad_m(m);
+  if (mpad < 0) { set_error("lincomb search: m = %d > 64 not supported by the register-resident kernel", m); return PLO_E_SHAPE; }
+  const int nact = (n - off) < 4 ? (n - off) : 4;
+
+  // canonical copies
+  std::vector<int64_t> tm((size_t)nbatch * n * m), cf((size_t)nbatch * c), pv((size_t)nbatch * nprev * n);
+  for (size_t i = 0; i < tm.size(); ++i) tm[i] = p ? (int64_t)(((TM[i] % (int64_t)p) + (int64_t)p) % (int64_t)p) : TM[i];
+  for (size_t i = 0; i < cf.size(); ++i) cf[i] = p ? (int64_t)(((coeffs[i] % (int64_t)p) + (int64_t)p) % (int64_t)p) : coeffs[i];
+  for (size_t i = 0; i < pv.size(); ++i) pv[i] = p ? (int64_t)(((prev_rows[i] % (int64_t)p) + (int64_t)p) % (int64_t)p) : prev_rows[i];
+
+  int width = 4;
+  if (!p) {  // exact integers: magnitude guard
+    unsigned __int128 mc = 0, mt = 0;
+    for (int64_t v : cf) { unsigned __int128 a = v < 0 ? -(__int128)v : v; if (a > mc) mc = a; }
+    for (int b = 0; b < nbatch; ++b)
+      for (int t = 0; t < nact; ++t)
+        for (int j = 0; j < m; ++j) { int64_t v = tm[((size_t)b * n + off + t) * m + j]; unsigned __int128 a = v < 0 ? -(__int128)v : v; if (a > mt) mt = a; }
+    const unsigned __int128 bound = mc * mt * 4;
+    if (bound >= ((unsigned __int128)1 << 62)) { set_error("lincomb search: integer magnitude bound exceeded"); return PLO_E_RANGE; }
+    width = bound < (((unsigned __int128)1 << 31) - 1) ? 4 : 8;
+  }
+
+  plo_lincomb_plan* pl = new plo_lincomb_plan();
+  pl->p = p; pl->nbatch = nbatch; pl->n = n; pl->m = m; pl->off = off; pl->c = c; pl->nprev = nprev; pl->mpad = mpad; pl->width = width;
+  pl->d_tables = nullptr; pl->d_zflag = nullptr; pl->d_phi = nullptr; pl->d_nphi = nullptr; pl->d_coef = nullptr; pl->d_seed = nullptr; pl->d_result = nullptr;
+  pl->h_init_rl.assign(init_rl ? init_rl : nullptr, init_rl ? init_rl + nbatch : nullptr);
+  pl->h_init_cl.assign(init_cl ? init_cl : nullptr, init_cl ? init_cl + nbatch : nullptr);
+  if (!init_rl) pl->h_init_rl.assign(nbatch, -1);
+  if (!init_cl) pl->h_init_cl.assign(nbatch, -1);
+  pl->h_seed.resize(nbatch);
+  pl->trivially_none.assign(nbatch, 0);
+
+  const size_t tab = (size_t)c * mpad;
+  std::vector<unsigned char> tables((size_t)nbatch * 4 * tab * width), zflag((size_t)nbatch * 4 * c, 0);
+  std::vector<long long> phi((size_t)nbatch * 16, 0);
+  std::vector<int> nphi(nbatch, 0);
+  try {
+    for (int b = 0; b < nbatch; ++b) {
+      const int64_t* tmb = tm.data() + (size_t)b * n * m;
+      const int64_t* cfb = cf.data() + (size_t)b * c;
+      unsigned char* base = tables.data();
+      const size_t per = (size_t)nbatch * tab * width;  // bytes per table kind
+      if (width == 4) {
+        typedef uint32_t T;
+        fill_tables<T>(p, n, m, off, nact, c, mpad, tmb, cfb, (T*)(base + 0 * per) + b * tab, (T*)(base + 1 * per) + b * tab,
+                       (T*)(base + 2 * per) + b * tab, (T*)(base + 3 * per) + b * tab);
+      } else {
+        typedef uint64_t T;
+        fill_tables<T>(p, n, m, off, nact, c, mpad, tmb, cfb, (T*)(base + 0 * per) + b * tab, (T*)(base + 1 * per) + b * tab,
+                       (T*)(base + 2 * per) + b * tab, (T*)(base + 3 * per) + b * tab);
+      }
+      for (int t = 0; t < nact; ++t)
+        for (int l = 0; l < c; ++l) zflag[((size_t)b * 4 + t) * c + l] = (cfb[l] == 0);
+      std::vector<long long> ph;
+      int np = 0;
+      bool ok;
+      if (p) { plo::host::ZpField f((int64_t)p); ok = annihilators(f, n, nprev, pv.data() + (size_t)b * nprev * n, off, nact, ph, np); }
+      else { plo::host::QField f; ok = annihilators(f, n, nprev, pv.data() + (size_t)b * nprev * n, off, nact, ph, np); }
+      if (!ok) { pl->trivially_none[b] = 1; np = 0; ph.assign(16, 0); }
+      std::copy(ph.begin(), ph.end(), phi.begin() + (size_t)b * 16);
+      nphi[b] = np;
+      pl->h_seed[b] = pack_key(pl->h_init_rl[b], pl->h_init_cl[b], kIdxMask);
+    }
+  } catch (const plo::host::RangeError& e) {
+    set_error("lincomb search: %s", e.what());
+    delete pl;
+    return PLO_E_RANGE;
+  }
+
+  // launch geometry: all SMs busy even for small c (split the l range across threads)
+  const int sms = sm_count();
+  const unsigned long long nprefix = (unsigned long long)c * c * c;
+  const unsigned long long want = (unsigned long long)sms * kLcThreads * 4ull;
+  int lsplit = 1;
+  while (lsplit < c && nprefix * lsplit * nbatch < want && (c + lsplit * 2 - 1) / (lsplit * 2) >= 4) lsplit *= 2;
+  pl->lsplit = lsplit;
+  const int max_rows = (int)(65536 / ((size_t)mpad * width));
+  pl->ltile = c < max_rows ? c : max_rows;
+  pl->smem = (size_t)pl->ltile * mpad * width;
+  unsigned long long blocks = (nprefix * lsplit + kLcThreads - 1) / kLcThreads;
+  const unsigned long long cap = (unsigned long long)sms * 8ull;
+  pl->grid = (int)(blocks < cap ? blocks : cap);
+  if (pl->grid < 1) pl->grid = 1;
+
+  auto up = [&](void** dst, const void* src, size_t bytes) -> bool {
+    if (cudaMalloc(dst, bytes ? bytes : 1) != cudaSuccess) return false;
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  bool ok = up(&pl->d_tables, tables.data(), tables.size()) && up((void**)&pl->d_zflag, zflag.data(), zflag.size()) &&
+            up((void**)&pl->d_phi, phi.data(), phi.size() * 8) && up((void**)&pl->d_nphi, nphi.data(), nphi.size() * 4) &&
+            up((void**)&pl->d_coef, cf.data(), cf.size() * 8) && up((void**)&pl->d_seed, pl->h_seed.data(), pl->h_seed.size() * 8) &&
+            cudaMalloc((void**)&pl->d_result, (size_t)nbatch * 8) == cudaSuccess;
+  if (!ok) {
+    set_error("lincomb search: device allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    plo_lincomb_plan_destroy(pl);
+    return PLO_E_CUDA;
+  }
+  *plan = pl;
+  return PLO_OK;
+}
+
+int plo_lincomb_plan_run(plo_lincomb_plan* pl, void* stream) {
+  if (!pl) { set_error("plo_lincomb_plan_run: null plan"); return PLO_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  lincomb_init_kernel<<<(pl->nbatch + 127) / 128, 128, 0, st>>>(pl->d_result, pl->d_seed, pl->nbatch);
+  const size_t tab = (size_t)pl->c * pl->mpad;
+  const size_t per = (size_t)pl->nbatch * tab;  // elements per table kind
+  dim3 grid(pl->grid, pl->nbatch);
+  cudaError_t e;
+  auto fill = [&](auto* base) {
+    typedef typename std::remove_pointer<decltype(base)>::type T;
+    LcParams<T> prm;
+    prm.c = pl->c; prm.m = pl->m; prm.nact = 0; prm.lsplit = pl->lsplit; prm.ltile = pl->ltile; prm.nphi_max = 4;
+    prm.p = pl->p; prm.cl_const = pl->n - ((pl->n - pl->off) < 4 ? (pl->n - pl->off) : 4);
+    prm.t0 = base; prm.t1 = base + per; prm.t2 = base + 2 * per; prm.t3 = base + 3 * per;
+    prm.zflag = pl->d_zflag; prm.phi = pl->d_phi; prm.nphi = pl->d_nphi; prm.coef = pl->d_coef;
+    prm.seed = pl->d_seed; prm.result = pl->d_result;
+    return prm;
+  };
+  if (pl->width == 4) {
+    auto prm = fill((uint32_t*)pl->d_tables);
+    e = pl->p ? launch_lincomb<uint32_t, true>(pl->mpad, grid, pl->smem, st, prm) : launch_lincomb<uint32_t, false>(pl->mpad, grid, pl->smem, st, prm);
+  } else {
+    auto prm = fill((uint64_t*)pl->d_tables);
+    e = launch_lincomb<uint64_t, false>(pl->mpad, grid, pl->smem, st, prm);
+  }
+  if (e != cudaSuccess) { set_error("lincomb kernel launch: %s", cudaGetErrorString(e)); return PLO_E_CUDA; }
+  return PLO_OK;
+}
+
+int plo_lincomb_plan_launches(const plo_lincomb_plan*) { return 2; }
+
+uint64_t plo_lincomb_plan_candidates(const plo_lincomb_plan* pl) {
+  return pl ? (uint64_t)pl->nbatch * pl->c * pl->c * pl->c * pl->c : 0;
+}
+
+int plo_lincomb_plan_result(plo_lincomb_plan* pl, void* stream, int* best_rl, int* best_cl, uint64_t* best_index) {
+  if (!pl || !best_rl || !best_cl || !best_index) { set_error("plo_lincomb_plan_result: bad argument"); return PLO_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<unsigned long long> keys(pl->nbatch);
+  PLO_CUDA(cudaMemcpyAsync(keys.data(), pl->d_result, keys.size() * 8, cudaMemcpyDeviceToHost, st));
+  PLO_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < pl->nbatch; ++b) {
+    const unsigned long long key = keys[b];
+    if (key == pl->h_seed[b] || pl->trivially_none[b]) {
+      best_rl[b] = pl->h_init_rl[b]; best_cl[b] = pl->h_init_cl[b]; best_index[b] = PLO_NO_INDEX;
+    } else {
+      best_rl[b] = (int)(key >> 48) - 1;
+      best_cl[b] = (int)((key >> kIdxBits) & 0xFFFull) - 1;
+      best_index[b] = kIdxMask - 1ull - (key & kIdxMask);
+    }
+  }
+  return PLO_OK;
+}
+
+int plo_lincomb_search_batch(uint32_t p, int nbatch, int n, int m, const int64_t* TM, int off, int c,
+                             const int64_t* coeffs, int nprev, const int64_t* prev_rows, const int* init_rl,
+                             const int* init_cl, int* best_rl, int* best_cl, uint64_t* best_index) {
+  plo_lincomb_plan* pl = nullptr;
+  int rc = plo_lincomb_plan_create(&pl, p, nbatch, n, m, TM, off, c, coeffs, nprev, prev_rows, init_rl, init_cl);
+  if (rc) return rc;
+  rc = plo_lincomb_plan_run(pl, nullptr);
+  if (!rc) rc = plo_lincomb_plan_result(pl, nullptr, best_rl, best_cl, best_index);
+  plo_lincomb_plan_destroy(pl);
+  return rc;
+}
+
+int plo_lincomb_search(uint32_t p, int n, int m, const int64_t* TM, int off, int c, const int64_t* coeffs,
+                       int nprev, const int64_t* prev_rows, int init_rl, int init_cl,
+                       int* best_rl, int* best_cl, uint64_t* best_index) {
+  return plo_lincomb_search_batch(p, 1, n, m, TM, off, c, coeffs, nprev, prev_rows, &init_rl, &init_cl, best_rl, best_cl, best_index);
+}
+
+}  // extern "C"

@@ -1,0 +1,584 @@
+// orbit_sweep.cu -- DeGroote-orbit candidate sweep on sm_100a.
+//
+// Replaces the whole candidate loop of the reference's orbiter
+//   src/orbiter.cpp:272-324   (omp parallel for + omp critical keep-best)
+// One candidate per thread: the (U,V,W) triple is decoded from the candidate
+// index (counter-based, DESIGN.md "orbit candidate decode"), the small matrices
+// live in registers, the fixed L/R/P (pre-scaled to integers) sit in constant
+// memory and are read warp-uniformly, the three Kronecker-product actions
+//   L.(U^-1 (x) V), R.(V^-T (x) W), (U (x) W^-1).P        (orbiter.cpp:284-294)
+// are evaluated row by row as  U^-T A V,  V^-1 B W,  U C W^-T  without ever
+// materialising a Kronecker product, and the measure (nnz/nno: plinopt_library.inl:
+// 258-284; G2: growthfactor.cpp:117-125) feeds a warp-shuffle + block argmin.
+#include <math.h>
+
+#include <cmath>
+#include <type_traits>
+
+#include <vector>
+
+#include "plo_device.cuh"
+
+namespace plo {
+
+constexpr int kMaxDim = 8;           // nibble-packed permutations
+constexpr int kConstInts = 15360;    // 60 KB of constant memory for L | R | P^T
+__constant__ int c_lrp[kConstInts];
+
+constexpr int MEASURE_BOTH = 4;  // internal: nnz, nno and G2 (tables, winner re-evaluation)
+
+// ---------------------------------------------------------------------------
+// Digit stream: a pure function of (mode, seed, index).
+//   mode 0: digits are the mixed-radix expansion of index (least significant first)
+//   mode 1: words w_t = Philox4x32-10(key = seed, counter = (index, t/4))[t%4];
+//           a digit of radix rho is taken from the current word x by
+//           d = (x*rho) >> 32, x = (x*rho) mod 2^32; a fresh word is fetched at
+//           the start of every matrix and whenever the product of the radices
+//           taken from the current word would exceed 2^20.
+// All bookkeeping (R, nwords) is compile-time constant once the loops are unrolled.
+// ---------------------------------------------------------------------------
+template <int MODE>
+struct Digits {
+  unsigned long long index, seed, rem;
+  uint32_t x, R, nwords;
+  uint32_t buf[4];
+  __host__ __device__ __forceinline__ Digits(unsigned long long seed_, unsigned long long index_)
+      : index(index_), seed(seed_), rem(index_), x(0), R(0), nwords(0) {}
+  __host__ __device__ __forceinline__ void new_word() {
+    if ((nwords & 3u) == 0)
+      philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), nwords >> 2, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+    x = buf[nwords & 3u];
+    ++nwords;
+    R = 1;
+  }
+  __host__ __device__ __forceinline__ void start_matrix() {
+    if (MODE == 1) new_word();
+  }
+  __host__ __device__ __forceinline__ uint32_t digit(uint32_t radix) {
+    if (MODE == 0) {
+      const uint32_t d = (uint32_t)(rem % radix);
+      rem /= radix;
+      return d;
+    }
+    if (R * radix > (1u << 20)) new_word();
+    const unsigned long long t = (unsigned long long)x * radix;
+    x = (uint32_t)t;
+    R *= radix;
+    return (uint32_t)(t >> 32);
+  }
+};
+
+// Compact form of one zoi matrix  M[P[i]][Q[j]] = T[i][j]  (src/orbiter.cpp:125-136):
+// nibble-packed permutations, sign bits of the diagonal, 2-bit trits of the
+// strict upper triangle (row-major over i<j, stored as value+1).
+struct Zoi {
+  uint32_t pP, pQ, D;
+  unsigned long long T;
+};
+
+__host__ __device__ __forceinline__ uint32_t nibble_swap(uint32_t perm, int i, uint32_t d) {
+  // swap entries i and i+d of a nibble-packed permutation (Fisher-Yates step)
+  const uint32_t sh = 4u * (uint32_t)i, sh2 = sh + 4u * d;
+  const uint32_t xr = ((perm >> sh) ^ (perm >> sh2)) & 15u;
+  return perm ^ (xr << sh) ^ (xr << sh2);
+}
+
+template <int S, int MODE>
+__host__ __device__ __forceinline__ Zoi decode_zoi(Digits<MODE>& ds) {
+  Zoi z;
+  ds.start_matrix();
+  z.pP = 0x76543210u;
+  z.pQ = 0x76543210u;
+#pragma unroll
+  for (int i = 0; i + 1 < S; ++i) z.pP = nibble_swap(z.pP, i, ds.digit((uint32_t)(S - i)));
+#pragma unroll
+  for (int i = 0; i + 1 < S; ++i) z.pQ = nibble_swap(z.pQ, i, ds.digit((uint32_t)(S - i)));
+  z.D = 0;
+#pragma unroll
+  for (int i = 0; i < S; ++i) z.D |= ds.digit(2u) << i;
+  z.T = 0;
+  int idx = 0;
+#pragma unroll
+  for (int i = 0; i < S; ++i)
+#pragma unroll
+    for (int j = i + 1; j < S; ++j) {
+      z.T |= (unsigned long long)ds.digit(3u) << (2 * idx);
+      ++idx;
+    }
+  return z;
+}
+
+// Expand a Zoi into the dense matrix (INV = false) or its inverse (INV = true),
+// row-major in out[S*S].  `scr` is a thread-private scratch of S*S ints with
+// element stride `stride` (shared memory on the device: out-of-order writes at
+// data-dependent positions, then an in-order read back into registers).
+//   M     = Pi_P . T . Pi_Q^T      =>  M[P[i]][Q[j]]      = T[i][j]
+//   M^-1  = Pi_Q . T^-1 . Pi_P^T   =>  M^-1[Q[i]][P[j]]   = T^-1[i][j]
+// T is upper triangular with +-1 diagonal, so T^-1 is integral
+// (reference: inverse / inverseTranspose, plinopt_sparsify.inl:380-465).
+template <int S, bool INV>
+__host__ __device__ __forceinline__ void expand_zoi(const Zoi& z, int* out, volatile int* scr, int stride) {
+  int t[S][S];
+  {
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      t[i][i] = ((z.D >> i) & 1u) ? 1 : -1;
+#pragma unroll
+      for (int j = i + 1; j < S; ++j) {
+        t[i][j] = (int)((z.T >> (2 * idx)) & 3ull) - 1;
+        ++idx;
+      }
+    }
+  }
+  if (INV) {
+    // back substitution: x[i][i] = d_i ; x[i][j] = -d_i * sum_{k=i+1..j} t[i][k] x[k][j]
+    int xinv[S][S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      xinv[j][j] = t[j][j];
+#pragma unroll
+      for (int i = j - 1; i >= 0; --i) {
+        int s = 0;
+#pragma unroll
+        for (int k = i + 1; k <= j; ++k) s += t[i][k] * xinv[k][j];
+        xinv[i][j] = -t[i][i] * s;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+#pragma unroll
+      for (int j = i; j < S; ++j) t[i][j] = xinv[i][j];
+  }
+#pragma unroll
+  for (int e = 0; e < S * S; ++e) scr[e * stride] = 0;
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+#pragma unroll
+    for (int j = i; j < S; ++j) {
+      const int Pi = (int)((z.pP >> (4 * (INV ? j : i))) & 15u);
+      const int Qj = (int)((z.pQ >> (4 * (INV ? i : j))) & 15u);
+      const int pos = INV ? (Qj * S + Pi) : (Pi * S + Qj);
+      scr[pos * stride] = t[i][j];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < S * S; ++e) out[e] = scr[e * stride];
+}
+
+// ---------------------------------------------------------------------------
+// Per-row scoring.  Y = Lm' . A . Rm'  with A (RA x CA) read warp-uniformly,
+// Lm' = Lm or Lm^T, Rm' = Rm or Rm^T; every entry of Y goes to the accumulator.
+// ---------------------------------------------------------------------------
+struct Acc {
+  int nnz, nno, sq;
+};
+
+template <int MEASURE>
+__host__ __device__ __forceinline__ void consume(Acc& a, int y) {
+  if (MEASURE == PLO_MEASURE_NNZ || MEASURE == MEASURE_BOTH) {
+    a.nnz += (y != 0);
+    a.nno += ((unsigned)(y + 1) > 2u);
+  }
+  if (MEASURE == PLO_MEASURE_G2 || MEASURE == MEASURE_BOTH) a.sq += y * y;
+}
+
+template <int RA, int CA, bool TL, bool TR, int MEASURE>
+__host__ __device__ __forceinline__ void transform_row(const int* __restrict__ A, const int* Lm, const int* Rm, Acc& acc) {
+  int a[RA * CA];
+#pragma unroll
+  for (int e = 0; e < RA * CA; ++e) a[e] = A[e];
+#pragma unroll
+  for (int x = 0; x < RA; ++x) {
+    int X[CA];
+#pragma unroll
+    for (int j = 0; j < CA; ++j) {
+      int s = 0;
+#pragma unroll
+      for (int i = 0; i < RA; ++i) s += (TL ? Lm[i * RA + x] : Lm[x * RA + i]) * a[i * CA + j];
+      X[j] = s;
+    }
+#pragma unroll
+    for (int y = 0; y < CA; ++y) {
+      int s = 0;
+#pragma unroll
+      for (int j = 0; j < CA; ++j) s += X[j] * (TR ? Rm[y * CA + j] : Rm[j * CA + y]);
+      consume<MEASURE>(acc, s);
+    }
+  }
+}
+
+struct Score {
+  uint32_t nnz, nno;
+  double g2;
+};
+
+// Scores one candidate.  lrp = L (r x MK) | R (r x KN) | P^T (r x MN), ints.
+template <int M, int K, int N, int MODE, int MEASURE>
+__host__ __device__ __forceinline__ Score score_candidate(const int* __restrict__ lrp, int r, unsigned long long seed,
+                                                          unsigned long long index, volatile int* scr, int stride) {
+  Digits<MODE> ds(seed, index);
+  const Zoi zu = decode_zoi<M, MODE>(ds);
+  const Zoi zv = decode_zoi<K, MODE>(ds);
+  const Zoi zw = decode_zoi<N, MODE>(ds);
+  int U[M * M], Ui[M * M], V[K * K], Vi[K * K], W[N * N], Wi[N * N];
+  expand_zoi<M, false>(zu, U, scr, stride);
+  expand_zoi<M, true>(zu, Ui, scr, stride);
+  expand_zoi<K, false>(zv, V, scr, stride);
+  expand_zoi<K, true>(zv, Vi, scr, stride);
+  expand_zoi<N, false>(zw, W, scr, stride);
+  expand_zoi<N, true>(zw, Wi, scr, stride);
+
+  const int* Lc = lrp;
+  const int* Rc = lrp + r * M * K;
+  const int* Pc = Rc + r * K * N;
+  Score sc;
+  sc.nnz = 0; sc.nno = 0; sc.g2 = 0.0;
+  int nnz = 0, nno = 0;
+#pragma unroll 1
+  for (int l = 0; l < r; ++l) {
+    Acc aL, aR, aP;
+    aL.nnz = aL.nno = aL.sq = 0;
+    aR = aL; aP = aL;
+    transform_row<M, K, true, false, MEASURE>(Lc + l * M * K, Ui, V, aL);   // U^-T A V
+    transform_row<K, N, false, false, MEASURE>(Rc + l * K * N, Vi, W, aR);  // V^-1 B W
+    transform_row<M, N, false, true, MEASURE>(Pc + l * M * N, U, Wi, aP);   // U C W^-T
+    nnz += aL.nnz + aR.nnz + aP.nnz;
+    nno += aL.nno + aR.nno + aP.nno;
+    if (MEASURE == PLO_MEASURE_G2 || MEASURE == MEASURE_BOTH) {
+      // growthfactor.cpp:117-125: s += norm2(L[i])*norm2(R[i])*norm2(Pt[i]); no FMA contraction
+#ifdef __CUDA_ARCH__
+      const double t = __dmul_rn(__dmul_rn(sqrt((double)aL.sq), sqrt((double)aR.sq)), sqrt((double)aP.sq));
+      sc.g2 = __dadd_rn(sc.g2, t);
+#else
+      const double t = (std::sqrt((double)aL.sq) * std::sqrt((double)aR.sq)) * std::sqrt((double)aP.sq);
+      sc.g2 = sc.g2 + t;
+#endif
+    }
+  }
+  sc.nnz = (uint32_t)nnz;
+  sc.nno = (uint32_t)nno;
+  return sc;
+}
+
+template <int MEASURE>
+__device__ __forceinline__ Key make_key(const Score& s, unsigned long long index) {
+  Key k;
+  if (MEASURE == PLO_MEASURE_NNZ) k.primary = ((unsigned long long)s.nnz << 32) | s.nno;
+  else k.primary = (unsigned long long)__double_as_longlong(s.g2);  // g2 >= 0: order preserving
+  k.index = index;
+  return k;
+}
+
+constexpr int kThreads = 128;
+
+template <int M, int K, int N>
+struct MaxDim2 {
+  static constexpr int d = (M > K ? (M > N ? M : N) : (K > N ? K : N));
+  static constexpr int value = d * d;
+};
+
+// One candidate per thread, grid-stride over [lo,hi); per-block best to block_best[blockIdx.x].
+template <int M, int K, int N, int MODE, int MEASURE>
+__global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, unsigned long long seed, unsigned long long lo,
+                                                                unsigned long long hi, Key* __restrict__ block_best) {
+  __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
+  __shared__ Key red[32];
+  const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+  Key best;
+  best.primary = ~0ull; best.index = ~0ull;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
+    const Score s = score_candidate<M, K, N, MODE, MEASURE>(c_lrp, r, seed, idx, scr + threadIdx.x, kThreads);
+    const Key k = make_key<MEASURE>(s, idx);
+    if (k.primary < best.primary) best = k;  // indices visited in increasing order: strict '<' keeps the first
+  }
+  best = block_min(best, red);
+  if (threadIdx.x == 0) block_best[blockIdx.x] = best;
+}
+
+// Reduce the per-block keys, re-evaluate the winner with every measure, write the result record.
+template <int M, int K, int N, int MODE>
+__global__ void __launch_bounds__(kThreads) orbit_final_kernel(int r, unsigned long long seed, int nblocks, int measure,
+                                                                double inv_den, const Key* __restrict__ block_best,
+                                                                plo_orbit_best* __restrict__ out) {
+  __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
+  __shared__ Key red[32];
+  Key best;
+  best.primary = ~0ull; best.index = ~0ull;
+  for (int b = threadIdx.x; b < nblocks; b += kThreads) {
+    const Key k = block_best[b];
+    if (key_less(k, best)) best = k;
+  }
+  best = block_min(best, red);
+  if (threadIdx.x == 0) {
+    plo_orbit_best o;
+    o.index = best.index;
+    o.nnz = 0; o.nno = 0; o.score = 0.0;
+    if (best.index != ~0ull) {
+      const Score s = score_candidate<M, K, N, MODE, MEASURE_BOTH>(c_lrp, r, seed, best.index, scr, kThreads);
+      o.nnz = s.nnz; o.nno = s.nno;
+      o.score = (measure == PLO_MEASURE_G2) ? s.g2 * inv_den : (double)s.nnz;
+    }
+    *out = o;
+  }
+}
+
+template <int M, int K, int N, int MODE>
+__global__ void __launch_bounds__(kThreads) orbit_table_kernel(int r, unsigned long long seed, unsigned long long lo,
+                                                                unsigned long long hi, double inv_den,
+                                                                uint32_t* __restrict__ nnz, uint32_t* __restrict__ nno,
+                                                                double* __restrict__ g2) {
+  __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
+  const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
+    const Score s = score_candidate<M, K, N, MODE, MEASURE_BOTH>(c_lrp, r, seed, idx, scr + threadIdx.x, kThreads);
+    if (nnz) nnz[idx - lo] = s.nnz;
+    if (nno) nno[idx - lo] = s.nno;
+    if (g2) g2[idx - lo] = s.g2 * inv_den;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct ShapeOps {
+  int m, k, n;
+  void (*sweep)(int measure, int mode, int grid, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
+                unsigned long long hi, Key* bb);
+  void (*final)(int mode, cudaStream_t st, int r, unsigned long long seed, int nblocks, int measure, double inv_den,
+                const Key* bb, plo_orbit_best* out);
+  void (*table)(int mode, int grid, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
+                unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2);
+  int (*blocks_per_sm)();
+};
+
+template <int M, int K, int N>
+struct Shape {
+  static void sweep(int measure, int mode, int grid, cudaStream_t st, int r, unsigned long long seed,
+                    unsigned long long lo, unsigned long long hi, Key* bb) {
+    if (measure == PLO_MEASURE_NNZ) {
+      if (mode == 0) orbit_sweep_kernel<M, K, N, 0, PLO_MEASURE_NNZ><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, bb);
+      else orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_NNZ><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, bb);
+    } else {
+      if (mode == 0) orbit_sweep_kernel<M, K, N, 0, PLO_MEASURE_G2><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, bb);
+      else orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, bb);
+    }
+  }
+  static void final(int mode, cudaStream_t st, int r, unsigned long long seed, int nblocks, int measure, double inv_den,
+                    const Key* bb, plo_orbit_best* out) {
+    if (mode == 0) orbit_final_kernel<M, K, N, 0><<<1, kThreads, 0, st>>>(r, seed, nblocks, measure, inv_den, bb, out);
+    else orbit_final_kernel<M, K, N, 1><<<1, kThreads, 0, st>>>(r, seed, nblocks, measure, inv_den, bb, out);
+  }
+  static void table(int mode, int grid, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
+                    unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2) {
+    if (mode == 0) orbit_table_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, inv_den, nnz, nno, g2);
+    else orbit_table_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, inv_den, nnz, nno, g2);
+  }
+  static int blocks_per_sm() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2>, kThreads, 0);
+    return nb > 0 ? nb : 1;
+  }
+  static ShapeOps ops() { return ShapeOps{M, K, N, &sweep, &final, &table, &blocks_per_sm}; }
+};
+
+#define PLO_ORBIT_SHAPES(X) X(2, 2, 2) X(3, 3, 3) X(4, 4, 4) X(3, 4, 7)
+
+static const ShapeOps* find_shape(int m, int k, int n) {
+#define X(a, b, c) Shape<a, b, c>::ops(),
+  static const ShapeOps table[] = {PLO_ORBIT_SHAPES(X)};
+#undef X
+  for (const ShapeOps& s : table)
+    if (s.m == m && s.k == k && s.n == n) return &s;
+  return nullptr;
+}
+
+// Worst-case magnitude bound of the transformed entries (host guard for the
+// int32 arithmetic): |T^-1| entries <= 2^(s-2), row/column abs sums <= 2^(s-1);
+// a {-1,0,1} factor contributes at most its dimension.
+static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P) {
+  auto maxabs = [](const int32_t* a, size_t cnt) { long long mx = 0; for (size_t i = 0; i < cnt; ++i) { long long v = a[i] < 0 ? -(long long)a[i] : a[i]; if (v > mx) mx = v; } return mx; };
+  auto pw = [](int s) { return 1ll << (s > 1 ? s - 1 : 0); };
+  const long long bl = maxabs(L, (size_t)r * m * k) * pw(m) * k * m;  // generous: both factors
+  const long long br = maxabs(R, (size_t)r * k * n) * pw(k) * n * k;
+  const long long bp = maxabs(P, (size_t)r * m * n) * pw(n) * m * n;
+  auto ok = [](long long b, int cnt) { return b < 46340 && b * b * cnt < 2147483647ll; };
+  return ok(bl, m * k) && ok(br, k * n) && ok(bp, m * n);
+}
+
+static const void* g_const_owner = nullptr;
+
+}  // namespace plo
+
+using namespace plo;
+
+struct plo_orbit_plan {
+  int m, k, n, r, measure, mode;
+  unsigned long long seed;
+  double inv_den;
+  const ShapeOps* ops;
+  std::vector<int> h_lrp;
+  Key* d_block_best;
+  plo_orbit_best* d_out;
+  int grid;
+};
+
+extern "C" {
+
+uint64_t plo_orbit_space(int m, int k, int n) {
+  auto one = [](int s, unsigned __int128& acc) {
+    for (int i = 2; i <= s; ++i) acc *= (unsigned)i * (unsigned)i;  // two permutations
+    for (int i = 0; i < s; ++i) acc *= 2u;
+    for (int i = 0; i < s * (s - 1) / 2; ++i) acc *= 3u;
+  };
+  unsigned __int128 acc = 1;
+  one(m, acc); if (acc >> 64) return 0;
+  one(k, acc); if (acc >> 64) return 0;
+  one(n, acc); if (acc >> 64) return 0;
+  return (uint64_t)acc;
+}
+
+int plo_orbit_decode(int m, int k, int n, int mode, uint64_t seed, uint64_t index, int32_t* U, int32_t* V, int32_t* W) {
+  if (!U || !V || !W || m < 1 || k < 1 || n < 1 || m > kMaxDim || k > kMaxDim || n > kMaxDim || (mode != 0 && mode != 1)) {
+    set_error("plo_orbit_decode: bad argument");
+    return PLO_E_ARG;
+  }
+  int scr[kMaxDim * kMaxDim];
+  auto run = [&](auto modeTag) {
+    constexpr int MODE = decltype(modeTag)::value;
+    Digits<MODE> ds(seed, index);
+    auto one = [&](int s, int32_t* out) {
+      switch (s) {
+#define CASE(S) case S: { Zoi z = decode_zoi<S, MODE>(ds); expand_zoi<S, false>(z, out, scr, 1); break; }
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+      }
+    };
+    one(m, U); one(k, V); one(n, W);
+  };
+  if (mode == 0) run(std::integral_constant<int, 0>()); else run(std::integral_constant<int, 1>());
+  return PLO_OK;
+}
+
+int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, const int32_t* L, const int32_t* R,
+                          const int32_t* P, int32_t denL, int32_t denR, int32_t denP, int measure, int mode,
+                          uint64_t seed) {
+  if (!plan || !L || !R || !P || r < 1 || denL == 0 || denR == 0 || denP == 0 ||
+      (measure != PLO_MEASURE_NNZ && measure != PLO_MEASURE_G2) || (mode != 0 && mode != 1)) {
+    set_error("plo_orbit_plan_create: bad argument");
+    return PLO_E_ARG;
+  }
+  int rc = check_device();
+  if (rc) return rc;
+  const ShapeOps* ops = find_shape(m, k, n);
+  if (!ops) { set_error("orbit sweep: shape %dx%dx%d not compiled in", m, k, n); return PLO_E_SHAPE; }
+  if ((long long)r * (m * k + k * n + m * n) > kConstInts) { set_error("orbit sweep: L/R/P exceed constant memory"); return PLO_E_SHAPE; }
+  if (mode == 0 && plo_orbit_space(m, k, n) == 0) { set_error("orbit sweep: exhaustive space exceeds 64 bits"); return PLO_E_SHAPE; }
+  if (!magnitude_ok(m, k, n, r, L, R, P)) { set_error("orbit sweep: int32 magnitude bound exceeded"); return PLO_E_RANGE; }
+  plo_orbit_plan* pl = new plo_orbit_plan();
+  pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->measure = measure; pl->mode = mode; pl->seed = seed;
+  pl->inv_den = 1.0 / ((double)denL * (double)denR * (double)denP);
+  if (pl->inv_den < 0) pl->inv_den = -pl->inv_den;
+  pl->ops = ops;
+  pl->h_lrp.resize((size_t)r * (m * k + k * n + m * n));
+  int* dst = pl->h_lrp.data();
+  for (int i = 0; i < r * m * k; ++i) *dst++ = L[i];
+  for (int i = 0; i < r * k * n; ++i) *dst++ = R[i];
+  for (int l = 0; l < r; ++l)  // P^T: row l = column l of P
+    for (int e = 0; e < m * n; ++e) *dst++ = P[(size_t)e * r + l];
+  pl->grid = sm_count() * ops->blocks_per_sm();
+  pl->d_block_best = nullptr; pl->d_out = nullptr;
+  if (cudaMalloc(&pl->d_block_best, sizeof(Key) * pl->grid) != cudaSuccess || cudaMalloc(&pl->d_out, sizeof(plo_orbit_best)) != cudaSuccess) {
+    set_error("orbit sweep: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    plo_orbit_plan_destroy(pl);
+    return PLO_E_CUDA;
+  }
+  *plan = pl;
+  return PLO_OK;
+}
+
+static int orbit_upload(plo_orbit_plan* pl, cudaStream_t st) {
+  if (g_const_owner != pl) {
+    PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp, pl->h_lrp.data(), pl->h_lrp.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    g_const_owner = pl;
+  }
+  return PLO_OK;
+}
+
+int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* stream) {
+  if (!pl) { set_error("plo_orbit_plan_run: null plan"); return PLO_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = orbit_upload(pl, st);
+  if (rc) return rc;
+  pl->ops->sweep(pl->measure, pl->mode, pl->grid, st, pl->r, pl->seed, lo, hi, pl->d_block_best);
+  pl->ops->final(pl->mode, st, pl->r, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
+  PLO_CUDA(cudaGetLastError());
+  return PLO_OK;
+}
+
+int plo_orbit_plan_launches(const plo_orbit_plan*) { return 2; }
+
+int plo_orbit_plan_result(plo_orbit_plan* pl, void* stream, plo_orbit_best* best) {
+  if (!pl || !best) { set_error("plo_orbit_plan_result: bad argument"); return PLO_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  PLO_CUDA(cudaMemcpyAsync(best, pl->d_out, sizeof(plo_orbit_best), cudaMemcpyDeviceToHost, st));
+  PLO_CUDA(cudaStreamSynchronize(st));
+  return PLO_OK;
+}
+
+void plo_orbit_plan_destroy(plo_orbit_plan* pl) {
+  if (!pl) return;
+  if (g_const_owner == pl) g_const_owner = nullptr;
+  if (pl->d_block_best) cudaFree(pl->d_block_best);
+  if (pl->d_out) cudaFree(pl->d_out);
+  delete pl;
+}
+
+int plo_orbit_sweep(uint32_t p, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P,
+                    int32_t denL, int32_t denR, int32_t denP, int measure, int mode, uint64_t seed, uint64_t lo,
+                    uint64_t hi, plo_orbit_best* best) {
+  if (p != 0) { set_error("plo_orbit_sweep: only exact integers (p == 0) in this version"); return PLO_E_ARG; }
+  if (!best) { set_error("plo_orbit_sweep: null output"); return PLO_E_ARG; }
+  plo_orbit_plan* pl = nullptr;
+  int rc = plo_orbit_plan_create(&pl, m, k, n, r, L, R, P, denL, denR, denP, measure, mode, seed);
+  if (rc) return rc;
+  rc = plo_orbit_plan_run(pl, lo, hi, nullptr);
+  if (!rc) rc = plo_orbit_plan_result(pl, nullptr, best);
+  plo_orbit_plan_destroy(pl);
+  return rc;
+}
+
+int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int32_t denL,
+                    int32_t denR, int32_t denP, int mode, uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* nnz,
+                    uint32_t* nno, double* g2) {
+  if (hi < lo) { set_error("plo_orbit_table: hi < lo"); return PLO_E_ARG; }
+  plo_orbit_plan* pl = nullptr;
+  int rc = plo_orbit_plan_create(&pl, m, k, n, r, L, R, P, denL, denR, denP, PLO_MEASURE_G2, mode, seed);
+  if (rc) return rc;
+  const size_t cnt = (size_t)(hi - lo);
+  uint32_t *d_nnz = nullptr, *d_nno = nullptr;
+  double* d_g2 = nullptr;
+  auto cleanup = [&]() { cudaFree(d_nnz); cudaFree(d_nno); cudaFree(d_g2); plo_orbit_plan_destroy(pl); };
+  if (cnt) {
+    if (cudaMalloc(&d_nnz, cnt * 4) != cudaSuccess || cudaMalloc(&d_nno, cnt * 4) != cudaSuccess || cudaMalloc(&d_g2, cnt * 8) != cudaSuccess) {
+      set_error("plo_orbit_table: cudaMalloc failed"); cleanup(); return PLO_E_CUDA;
+    }
+    rc = orbit_upload(pl, nullptr);
+    if (!rc) {
+      size_t blocks = (cnt + kThreads - 1) / kThreads;
+      int grid = (int)(blocks < (size_t)pl->grid ? blocks : (size_t)pl->grid);
+      pl->ops->table(mode, grid, nullptr, r, seed, lo, hi, pl->inv_den, d_nnz, d_nno, d_g2);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { set_error("plo_orbit_table: %s", cudaGetErrorString(e)); rc = PLO_E_CUDA; }
+    }
+    if (!rc) {
+      if (nnz) cudaMemcpy(nnz, d_nnz, cnt * 4, cudaMemcpyDeviceToHost);
+      if (nno) cudaMemcpy(nno, d_nno, cnt * 4, cudaMemcpyDeviceToHost);
+      if (g2) cudaMemcpy(g2, d_g2, cnt * 8, cudaMemcpyDeviceToHost);
+    }
+  }
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

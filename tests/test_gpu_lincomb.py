@@ -1,0 +1,186 @@
+"""GPU parity: plo_lincomb_search (CUDA, through the C ABI) vs the CPU oracle's literal
+restatement of plinopt_sparsify.inl:166-197,299-314 on the same inputs.  Bit-exact:
+identical (rlHw, clHw, winning index) for every (block,num) step."""
+import math
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+P31 = 2147483647
+
+
+def col_scaled(TM):
+    """Integer matrix with every COLUMN of TM multiplied by its LCD (zero pattern of TM^T.w is invariant)."""
+    n, m = len(TM), len(TM[0])
+    A = np.zeros((n, m), dtype=np.int64)
+    for j in range(m):
+        l = 1
+        for i in range(n):
+            l = l * TM[i][j].denominator // math.gcd(l, TM[i][j].denominator)
+        for i in range(n):
+            A[i, j] = int(TM[i][j] * l)
+    return A
+
+
+def run_steps(capi, TM, p, c, nsteps_blocks=None):
+    """Walks the (block,num) steps of one localSparsifier call, checking GPU == oracle at every step."""
+    n, m = len(TM), len(TM[0])
+    if p == 0:
+        tm_num, tm_den = O.numden(TM)
+        cf_num, cf_den = O.coeffs(TM, 0, c)
+        lc = 1
+        for d in cf_den:
+            lc = lc * int(d) // math.gcd(lc, int(d))
+        cf_int = np.array([int(a) * (lc // int(d)) for a, d in zip(cf_num, cf_den)], dtype=np.int64)
+        tm_int = col_scaled(TM)
+    else:
+        tm_num = np.array([[(v.numerator % p) * pow(v.denominator % p, -1, p) % p for v in row] for row in TM], dtype=np.int64)
+        tm_den = np.ones_like(tm_num)
+        cf_num, cf_den = O.coeffs(tm_num.tolist(), p, c)
+        cf_int = cf_num.copy()
+        tm_int = tm_num
+    lcob_num = np.zeros((n, n), dtype=np.int64); lcob_den = np.ones((n, n), dtype=np.int64)
+    lcob_int = np.zeros((n, n), dtype=np.int64)
+    nblocks = (n + 3) // 4
+    checked = 0
+    for block in range(nblocks):
+        off = 4 * block
+        for num in range(min(4, n - off)):
+            exp = O.lincomb_search(p, tm_num, tm_den, off, num, cf_num, cf_den, lcob_num, lcob_den)
+            got = capi.lincomb_search(p, tm_int, off, cf_int, lcob_int[:off + num] if off + num else None)
+            exp_idx = None if exp[2] < 0 else exp[2]
+            assert (got[0], got[1], got[2]) == (exp[0], exp[1], exp_idx), (block, num, got, exp)
+            checked += 1
+            cc = len(cf_num)
+            if exp_idx is None:  # reference fallback: canonical vector (plinopt_sparsify.inl:317-326)
+                for pos in range(n):
+                    trial = lcob_int.copy(); trial[off + num, :] = 0; trial[off + num, pos] = 1
+                    if np.linalg.matrix_rank(trial[:off + num + 1].astype(float)) == off + num + 1:
+                        lcob_int[off + num] = trial[off + num]; lcob_num[off + num] = trial[off + num]
+                        break
+                continue
+            idx = exp_idx
+            ids = [idx // cc ** 3, (idx // cc ** 2) % cc, (idx // cc) % cc, idx % cc]
+            for t in range(4):
+                if off + t < n:
+                    lcob_num[off + num, off + t] = cf_num[ids[t]]; lcob_den[off + num, off + t] = cf_den[ids[t]]
+                    lcob_int[off + num, off + t] = cf_int[ids[t]]
+    return checked
+
+
+def transpose(M):
+    return [list(r) for r in zip(*M)]
+
+
+@pytest.mark.parametrize("c", [3, 4, 7, 11])
+def test_c1_smallrat_over_Q(capi, c):
+    M = O.dense_fractions("2x2x2_7_DPS-smallrat-12.2034_L")
+    assert run_steps(capi, transpose(M), 0, c) == 4
+
+
+@pytest.mark.parametrize("c", [3, 7, 11, 20])
+@pytest.mark.parametrize("blk", [0, 2])
+def test_c3_4x4x4_mod_p31(capi, c, blk):
+    M = O.dense_fractions("4x4x4_48_rational_L")  # 48 x 16
+    TM = [row[4 * blk:4 * blk + 4] for row in M]
+    assert run_steps(capi, transpose(TM), P31, c) == 4
+
+
+@pytest.mark.parametrize("name,c", [("3x4x7_63_rational_R", 5), ("3x4x7_63_rational_R", 9), ("4x4x4_48_rational_R", 13)])
+def test_blocks_over_Q(capi, name, c):
+    M = O.dense_fractions(name)
+    TM = [row[4:8] for row in M]
+    assert run_steps(capi, transpose(TM), 0, c) == 4
+
+
+def test_mod7_duplicate_coefficients(capi):
+    """-q 7 -c 5 (bin/FDT.sh:64): un-reduced negatives make value-duplicates in Coeffs (Q3)."""
+    M = O.dense_fractions("2x2x2_7_Winograd_R")
+    assert run_steps(capi, transpose(M), 7, 5) == 4
+
+
+def test_partial_last_block(capi):
+    """n = 6: second block has 2 live positions, k/l loops enumerate duplicates (Q4)."""
+    M = O.dense_fractions("3x4x7_63_rational_L")  # 63 x 12
+    TM = [row[:6] for row in M]
+    assert run_steps(capi, transpose(TM), 0, 4) == 6
+    assert run_steps(capi, transpose(TM), 13, 4) == 6
+
+
+def test_two_full_blocks_wide(capi):
+    """n = 8 (blocksize 8): previous rows of block 0 constrain block 1 (Q6)."""
+    M = O.dense_fractions("4x4x4_48_rational_R")
+    TM = [row[:8] for row in M]
+    assert run_steps(capi, transpose(TM), 0, 5) == 8
+
+
+def test_seed_weight_and_dense_previous_row(capi):
+    """A nullspace-like dense previous row and a weight seed that only better candidates may beat."""
+    M = O.dense_fractions("2x2x2_7_DPS-smallrat-12.2034_L")
+    TM = transpose(M)
+    tm_num, tm_den = O.numden(TM)
+    cf_num, cf_den = O.coeffs(TM, 0, 7)
+    lc = 1
+    for d in cf_den:
+        lc = lc * int(d) // math.gcd(lc, int(d))
+    cf_int = np.array([int(a) * (lc // int(d)) for a, d in zip(cf_num, cf_den)], dtype=np.int64)
+    tm_int = col_scaled(TM)
+    lcob = np.zeros((4, 4), dtype=np.int64); lcob[0] = [1, -2, 3, 1]
+    lden = np.ones((4, 4), dtype=np.int64)
+    for seed in [(-1, -1), (3, 1), (5, 2), (6, 3), (7, 4)]:
+        exp = O.lincomb_search(0, tm_num, tm_den, 0, 1, cf_num, cf_den, lcob, lden, seed[0], seed[1])
+        got = capi.lincomb_search(0, tm_int, 0, cf_int, lcob[:1], seed[0], seed[1])
+        assert got == (exp[0], exp[1], None if exp[2] < 0 else exp[2]), (seed, got, exp)
+
+
+def test_batch_of_blocks_matches_single(capi):
+    """The four independent column blocks of 4x4x4_48_rational_L in one batched call."""
+    M = O.dense_fractions("4x4x4_48_rational_L")
+    c = 9
+    tms, cfs, singles = [], [], []
+    for blk in range(4):
+        TM = transpose([row[4 * blk:4 * blk + 4] for row in M])
+        tm = np.array([[(v.numerator % P31) * pow(v.denominator % P31, -1, P31) % P31 for v in row] for row in TM], dtype=np.int64)
+        cf, _ = O.coeffs(tm.tolist(), P31, c)
+        tms.append(tm); cfs.append(cf)
+        singles.append(capi.lincomb_search(P31, tm, 0, cf))
+    plan = capi.LincombPlan(P31, np.stack(tms), 0, np.stack(cfs))
+    plan.run(); rl, cl, idx = plan.result()
+    for b in range(4):
+        assert (int(rl[b]), int(cl[b]), int(idx[b])) == singles[b]
+    assert plan.candidates == 4 * c ** 4
+    plan.close()
+
+
+def test_large_c_property(capi):
+    """c = 64 (1.7e7 candidates): too slow for the literal oracle; check via properties --
+    the winner's score recomputed exactly on the host equals the reported one, no sampled
+    candidate beats it, and the result is stable under a different launch geometry (batch of 2)."""
+    M = O.dense_fractions("4x4x4_48_rational_L")
+    TM = transpose([row[0:4] for row in M])
+    p = P31
+    tm = np.array([[(v.numerator % p) * pow(v.denominator % p, -1, p) % p for v in row] for row in TM], dtype=np.int64)
+    c = 64
+    cf, _ = O.coeffs(tm.tolist(), p, c)
+    rl, cl, idx = capi.lincomb_search(p, tm, 0, cf)
+    assert idx is not None
+    cc = len(cf)
+
+    def score(ix):
+        ids = [ix // cc ** 3, (ix // cc ** 2) % cc, (ix // cc) % cc, ix % cc]
+        w = [int(cf[t]) % p for t in ids]
+        v = [sum(w[t] * int(tm[t, j]) for t in range(4)) % p for j in range(tm.shape[1])]
+        return sum(1 for x in v if x == 0), sum(1 for x in w if x == 0)
+    assert score(idx) == (rl, cl)
+    rng = np.random.default_rng(7)
+    for ix in rng.integers(0, cc ** 4, 3000):
+        s = score(int(ix))
+        assert s < (rl, cl) or (s == (rl, cl) and int(ix) >= idx) or all(int(cf[t]) % p == 0 for t in [int(ix) // cc ** 3, (int(ix) // cc ** 2) % cc, (int(ix) // cc) % cc, int(ix) % cc])
+    plan = capi.LincombPlan(p, np.stack([tm, tm]), 0, np.stack([cf, cf]))
+    plan.run(); r2, c2, i2 = plan.result(); plan.close()
+    assert (int(r2[0]), int(c2[0]), int(i2[0])) == (rl, cl, idx) and (int(r2[1]), int(c2[1]), int(i2[1])) == (rl, cl, idx)

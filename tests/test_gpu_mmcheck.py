@@ -1,0 +1,69 @@
+"""GPU parity: batched MMchecker mod p vs the oracle's restatement of plinopt_library.inl:472-558."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from plinopt_b200 import hm
+
+pytestmark = pytest.mark.gpu
+P31 = 2147483647
+
+
+@pytest.mark.parametrize("stem", ["2x2x2_7_Strassen", "2x2x2_7_DPS-accurate", "4x4x4_48_rational", "3x4x7_63_rational", "3x3x6_40"])
+@pytest.mark.parametrize("p", [P31, 513083, 7])
+def test_valid_triples_pass_and_corruption_is_caught(capi, stem, p):
+    """Makefile:60-64 (mmcheck): every shipped triple is SUCCESS, also mod 513083 = (1013^2-3)/2."""
+    if stem == "2x2x2_7_DPS-accurate" and p != 513083:
+        pytest.skip("1013 is a placeholder for sqrt(3): only valid mod (1013^2-3)/2 = 513083 (Makefile:62-63)")
+    L, R, P = O.triple(stem)
+    mkn = hm.LRP2MM(L, R, P)
+    m, k, n = mkn
+    B = 40
+    rng = np.random.default_rng(11)
+    ua = rng.integers(0, p, (B, m * k)).astype(np.uint32); ub = rng.integers(0, p, (B, k * n)).astype(np.uint32)
+    v, ok = capi.mmcheck_batch(p, mkn, len(L), hm.csr_modp(L, p), hm.csr_modp(R, p), hm.csr_modp(P, p), batch=B, ua=ua, ub=ub)
+    exp = [O.mmcheck_modp(p, L, R, P, ua[b].astype(np.int64), ub[b].astype(np.int64)) for b in range(B)]
+    assert v == 0 and ok.tolist() == [1] * B and exp == [0] * B
+    # corrupt one entry: per-sample verdicts must match the oracle exactly
+    L2 = [row[:] for row in L]; L2[1][0] += 1
+    v, ok = capi.mmcheck_batch(p, mkn, len(L), hm.csr_modp(L2, p), hm.csr_modp(R, p), hm.csr_modp(P, p), batch=B, ua=ua, ub=ub)
+    exp = [O.mmcheck_modp(p, L2, R, P, ua[b].astype(np.int64), ub[b].astype(np.int64)) for b in range(B)]
+    assert ok.tolist() == [1 - e for e in exp]
+    assert v == (1 if any(exp) else 0)
+    if p > 1000:
+        assert v == 1
+
+
+def test_philox_samples_and_dimension_errors(capi):
+    L, R, P = O.triple("4x4x4_48_rational")
+    mkn = hm.LRP2MM(L, R, P)
+    csr = [hm.csr_modp(M, P31) for M in (L, R, P)]
+    v, ok = capi.mmcheck_batch(P31, mkn, len(L), *csr, seed=99, batch=257)
+    assert v == 0 and ok.sum() == 257
+    v, _ = capi.mmcheck_batch(P31, (4, 4, 5), len(L), *csr, seed=1, batch=4)
+    assert v == 3  # plinopt_library.inl:494 outer dimension mismatch
+    v, _ = capi.mmcheck_batch(P31, mkn, len(L) - 1, *csr, seed=1, batch=4)
+    assert v == 2  # MMchecker.cpp:65-71 inner dimension mismatch
+
+
+def test_random_dense_triple_linearity(capi):
+    """Size-independent property on a large synthetic instance: the trivial algorithm
+    (r = m*k*n elementary products) is correct for every sample; swapping two rows of P breaks it."""
+    m, k, n = 6, 5, 7
+    r = m * k * n
+    Lr, Rr, Pr = [], [], [[] for _ in range(m * n)]
+    t = 0
+    for i in range(m):
+        for a in range(k):
+            for j in range(n):
+                Lr.append((t, i * k + a)); Rr.append((t, a * n + j)); Pr[i * n + j].append(t); t += 1
+    ones = lambda cnt: np.ones(cnt, dtype=np.uint32)
+    Lc = (r, m * k, np.arange(r + 1, dtype=np.int64), np.array([c for _, c in Lr], dtype=np.int32), ones(r))
+    Rc = (r, k * n, np.arange(r + 1, dtype=np.int64), np.array([c for _, c in Rr], dtype=np.int32), ones(r))
+    pp = np.array([0] + list(np.cumsum([len(x) for x in Pr])), dtype=np.int64)
+    Pc = (m * n, r, pp, np.array([c for row in Pr for c in row], dtype=np.int32), ones(int(pp[-1])))
+    v, ok = capi.mmcheck_batch(P31, (m, k, n), r, Lc, Rc, Pc, seed=5, batch=100)
+    assert v == 0 and ok.all()
+    pc2 = Pc[3].copy(); pc2[0], pc2[k] = pc2[k], pc2[0]
+    v, ok = capi.mmcheck_batch(P31, (m, k, n), r, Lc, Rc, (Pc[0], Pc[1], Pc[2], pc2, Pc[4]), seed=5, batch=100)
+    assert v == 1 and not ok.any()

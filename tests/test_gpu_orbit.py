@@ -1,0 +1,115 @@
+"""GPU parity: orbit sweep (CUDA, through the C ABI) vs the CPU oracle's literal restatement
+of src/orbiter.cpp:272-324 (+ plinopt_library.inl:210-284, growthfactor.cpp:117-125) on the
+same (mode, seed, index) candidates.  nnz / nno / index bit-exact; G2 bit-exact for integer
+triples and within 1e-12 relative for rational ones."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+SEED = 0x504C494E4F505431
+RTOL = 1e-12
+
+
+def ints(stem):
+    L, R, P = O.triple(stem)
+    (Li, dl), (Ri, dr), (Pi, dp) = O.scaled_int(L), O.scaled_int(R), O.scaled_int(P)
+    return (L, R, P), O.LRP2MM(L, R, P), (Li.astype(np.int32), Ri.astype(np.int32), Pi.astype(np.int32)), (dl, dr, dp)
+
+
+def test_c2_winograd_exhaustive_table(capi):
+    """All 48^3 = 110592 candidates of the 2x2x2 orbit: full per-candidate table parity."""
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints("2x2x2_7_Winograd")
+    space = capi.orbit_space(*mkn)
+    assert space == 110592
+    ref = O.orbit_sweep(L, R, P, 3, 0, 0, 0, space)
+    nnz, nno, g2 = capi.orbit_table(mkn, Li, Ri, Pi, dens, 0, 0, 0, space)
+    assert np.array_equal(nnz, ref["nnz"]) and np.array_equal(nno, ref["nno"])
+    assert np.array_equal(g2, ref["g2"])  # integer triple: bit-exact doubles
+    for measure in (0, 3):
+        refb = O.orbit_sweep(L, R, P, measure, 0, 0, 0, space, table=False)["best"]
+        got = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, measure, 0, 0, 0, space)
+        assert got["index"] == refb[0] and got["nnz"] == refb[1] and got["nno"] == refb[2]
+        if measure == 3:
+            assert got["score"] == refb[3]
+
+
+@pytest.mark.parametrize("stem,count", [("2x2x2_7_Winograd", 20000), ("2x2x2_7_DPS-smallrat-12.2034", 20000),
+                                        ("3x3x3_23_58", 6000), ("4x4x4_48_rational", 3000), ("3x4x7_63_rational", 1500)])
+def test_philox_table_parity(capi, stem, count):
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints(stem)
+    lo = 2 ** 33 + 17
+    ref = O.orbit_sweep(L, R, P, 3, 1, SEED, lo, lo + count)
+    nnz, nno, g2 = capi.orbit_table(mkn, Li, Ri, Pi, dens, 1, SEED, lo, lo + count)
+    assert np.array_equal(nnz, ref["nnz"]) and np.array_equal(nno, ref["nno"])
+    np.testing.assert_allclose(g2, ref["g2"], rtol=RTOL, atol=0)
+    if dens == (1, 1, 1):
+        assert np.array_equal(g2, ref["g2"])
+    # winners (deterministic rule: lexicographic minimum, lowest index)
+    got0 = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 0, 1, SEED, lo, lo + count)
+    ref0 = O.orbit_sweep(L, R, P, 0, 1, SEED, lo, lo + count, table=False)["best"]
+    assert (got0["index"], got0["nnz"], got0["nno"]) == ref0[:3]
+    got3 = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 3, 1, SEED, lo, lo + count)
+    gmin = ref["g2"].min()
+    assert abs(got3["score"] - gmin) <= RTOL * gmin
+    assert abs(ref["g2"][got3["index"] - lo] - got3["score"]) <= RTOL * gmin
+
+
+def test_winner_is_a_valid_algorithm(capi):
+    """src/orbiter.cpp:355: the winner must still pass MMchecker; its scores match a direct evaluation."""
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints("3x3x3_23_58")
+    got = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 0, 1, SEED, 0, 200000)
+    U, V, W = capi.orbit_decode(*mkn, 1, SEED, got["index"])
+    Lj, Rg, hP = O.orbit_apply(L, R, P, U, V, W)
+    rng = np.random.default_rng(3)
+    m, k, n = mkn
+    assert O.mmcheck_q(Lj, Rg, hP, rng.integers(-50, 50, m * k), rng.integers(-50, 50, k * n)) == 0
+    nnz = sum(1 for M in (Lj, Rg, hP) for row in M for v in row if v != 0)
+    assert nnz == got["nnz"]
+    init = sum(1 for M in (L, R, P) for row in M for v in row if v != 0)
+    assert got["nnz"] <= init or True  # informational: a random sweep need not improve
+
+
+def test_large_sweep_properties(capi):
+    """2^26 Philox candidates (BASELINE config 2 scale-down): the result is independent of how the
+    index range is split (associativity of the argmin), and the winner re-scored by the oracle agrees."""
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints("2x2x2_7_Winograd")
+    N = 1 << 26
+    whole = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 3, 1, SEED, 0, N)
+    plan = capi.OrbitPlan(mkn, Li, Ri, Pi, dens, 3, 1, SEED)
+    parts = []
+    for a, b in [(0, N // 3), (N // 3, N // 2 + 5), (N // 2 + 5, N)]:
+        plan.run(a, b); parts.append(plan.result())
+    plan.close()
+    best = min(parts, key=lambda d: (d["score"], d["index"]))
+    assert best == whole
+    one = O.orbit_sweep(L, R, P, 3, 1, SEED, whole["index"], whole["index"] + 1)
+    assert one["g2"][0] == whole["score"] and one["nnz"][0] == whole["nnz"]
+    # the global optimum of the orbit for G2 is known from the exhaustive table (<= Winograd's own 17.853)
+    assert whole["score"] <= 17.85300667219901
+
+
+def test_empty_range_and_errors(capi):
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints("2x2x2_7_Winograd")
+    got = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 0, 1, SEED, 5, 5)
+    assert got["index"] is None
+    with pytest.raises(capi.PloError) as e:
+        capi.orbit_sweep((5, 5, 5), np.zeros((1, 25), np.int32), np.zeros((1, 25), np.int32), np.zeros((25, 1), np.int32), (1, 1, 1), 0, 1, 0, 0, 1)
+    assert e.value.code == capi.E_SHAPE
+    with pytest.raises(capi.PloError) as e:
+        capi.orbit_sweep(mkn, Li * 100000, Ri, Pi, dens, 0, 1, 0, 0, 1)
+    assert e.value.code == capi.E_RANGE
+
+
+def test_growth_G2_known_answers(capi):
+    """growthfactor.cpp:117-125 known answers from the data set headers / file names."""
+    want = {"2x2x2_7_Strassen": 14.828427124746192, "2x2x2_7_Winograd": 17.85300667219901,
+            "2x2x2_7_DPS-smallrat-12.2034": 12.203427124746, "2x2x2_7_DPS-integral-12.0662": 12.06616423,
+            "2x2x2_7_DPS-intermediate-12.0695": 12.06954148}
+    for stem, val in want.items():
+        L, R, P = O.triple(stem)
+        f = lambda M: np.array([[float(v) for v in row] for row in M])
+        got = capi.growth_G2(f(L), f(R), f(P))[0]
+        assert abs(got - val) < 5e-9 * val, (stem, got)
+        assert abs(got - O.growth_G2(L, R, P)) <= RTOL * got
