@@ -174,17 +174,19 @@ struct Acc {
   int nnz, nno, sq;
 };
 
+// `den` is the common denominator of the matrix: the true entry is y/den, so it is +-1 iff |y| == den
+// (isAbsOne, include/plinopt_library.h:188-191).
 template <int MEASURE>
-__host__ __device__ __forceinline__ void consume(Acc& a, int y) {
+__host__ __device__ __forceinline__ void consume(Acc& a, int y, int den) {
   if (MEASURE == PLO_MEASURE_NNZ || MEASURE == MEASURE_BOTH) {
     a.nnz += (y != 0);
-    a.nno += ((unsigned)(y + 1) > 2u);
+    a.nno += (y != 0) & (y != den) & (y != -den);
   }
   if (MEASURE == PLO_MEASURE_G2 || MEASURE == MEASURE_BOTH) a.sq += y * y;
 }
 
 template <int RA, int CA, bool TL, bool TR, int MEASURE>
-__host__ __device__ __forceinline__ void transform_row(const int* __restrict__ A, const int* Lm, const int* Rm, Acc& acc) {
+__host__ __device__ __forceinline__ void transform_row(const int* __restrict__ A, const int* Lm, const int* Rm, int den, Acc& acc) {
   int a[RA * CA];
 #pragma unroll
   for (int e = 0; e < RA * CA; ++e) a[e] = A[e];
@@ -203,7 +205,7 @@ __host__ __device__ __forceinline__ void transform_row(const int* __restrict__ A
       int s = 0;
 #pragma unroll
       for (int j = 0; j < CA; ++j) s += X[j] * (TR ? Rm[y * CA + j] : Rm[j * CA + y]);
-      consume<MEASURE>(acc, s);
+      consume<MEASURE>(acc, s, den);
     }
   }
 }
@@ -215,7 +217,7 @@ struct Score {
 
 // Scores one candidate.  lrp = L (r x MK) | R (r x KN) | P^T (r x MN), ints.
 template <int M, int K, int N, int MODE, int MEASURE>
-__host__ __device__ __forceinline__ Score score_candidate(const int* __restrict__ lrp, int r, unsigned long long seed,
+__host__ __device__ __forceinline__ Score score_candidate(const int* __restrict__ lrp, int r, int3 den, unsigned long long seed,
                                                           unsigned long long index, volatile int* scr, int stride) {
   Digits<MODE> ds(seed, index);
   const Zoi zu = decode_zoi<M, MODE>(ds);
@@ -240,9 +242,9 @@ __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict_
     Acc aL, aR, aP;
     aL.nnz = aL.nno = aL.sq = 0;
     aR = aL; aP = aL;
-    transform_row<M, K, true, false, MEASURE>(Lc + l * M * K, Ui, V, aL);   // U^-T A V
-    transform_row<K, N, false, false, MEASURE>(Rc + l * K * N, Vi, W, aR);  // V^-1 B W
-    transform_row<M, N, false, true, MEASURE>(Pc + l * M * N, U, Wi, aP);   // U C W^-T
+    transform_row<M, K, true, false, MEASURE>(Lc + l * M * K, Ui, V, den.x, aL);   // U^-T A V
+    transform_row<K, N, false, false, MEASURE>(Rc + l * K * N, Vi, W, den.y, aR);  // V^-1 B W
+    transform_row<M, N, false, true, MEASURE>(Pc + l * M * N, U, Wi, den.z, aP);   // U C W^-T
     nnz += aL.nnz + aR.nnz + aP.nnz;
     nno += aL.nno + aR.nno + aP.nno;
     if (MEASURE == PLO_MEASURE_G2 || MEASURE == MEASURE_BOTH) {
@@ -280,7 +282,7 @@ struct MaxDim2 {
 
 // One candidate per thread, grid-stride over [lo,hi); per-block best to block_best[blockIdx.x].
 template <int M, int K, int N, int MODE, int MEASURE>
-__global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, unsigned long long seed, unsigned long long lo,
+__global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo,
                                                                 unsigned long long hi, Key* __restrict__ block_best) {
   __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
   __shared__ Key red[32];
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, unsigned l
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
-    const Score s = score_candidate<M, K, N, MODE, MEASURE>(c_lrp, r, seed, idx, scr + threadIdx.x, kThreads);
+    const Score s = score_candidate<M, K, N, MODE, MEASURE>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads);
     const Key k = make_key<MEASURE>(s, idx);
     if (k.primary < best.primary) best = k;  // indices visited in increasing order: strict '<' keeps the first
   }
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, unsigned l
 
 // Reduce the per-block keys, re-evaluate the winner with every measure, write the result record.
 template <int M, int K, int N, int MODE>
-__global__ void __launch_bounds__(kThreads) orbit_final_kernel(int r, unsigned long long seed, int nblocks, int measure,
+__global__ void __launch_bounds__(kThreads) orbit_final_kernel(int r, int3 den, unsigned long long seed, int nblocks, int measure,
                                                                 double inv_den, const Key* __restrict__ block_best,
                                                                 plo_orbit_best* __restrict__ out) {
   __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) orbit_final_kernel(int r, unsigned l
     o.index = best.index;
     o.nnz = 0; o.nno = 0; o.score = 0.0;
     if (best.index != ~0ull) {
-      const Score s = score_candidate<M, K, N, MODE, MEASURE_BOTH>(c_lrp, r, seed, best.index, scr, kThreads);
+      const Score s = score_candidate<M, K, N, MODE, MEASURE_BOTH>(c_lrp, r, den, seed, best.index, scr, kThreads);
       o.nnz = s.nnz; o.nno = s.nno;
       o.score = (measure == PLO_MEASURE_G2) ? s.g2 * inv_den : (double)s.nnz;
     }
@@ -324,14 +326,14 @@ __global__ void __launch_bounds__(kThreads) orbit_final_kernel(int r, unsigned l
 }
 
 template <int M, int K, int N, int MODE>
-__global__ void __launch_bounds__(kThreads) orbit_table_kernel(int r, unsigned long long seed, unsigned long long lo,
+__global__ void __launch_bounds__(kThreads) orbit_table_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo,
                                                                 unsigned long long hi, double inv_den,
                                                                 uint32_t* __restrict__ nnz, uint32_t* __restrict__ nno,
                                                                 double* __restrict__ g2) {
   __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
   const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
-    const Score s = score_candidate<M, K, N, MODE, MEASURE_BOTH>(c_lrp, r, seed, idx, scr + threadIdx.x, kThreads);
+    const Score s = score_candidate<M, K, N, MODE, MEASURE_BOTH>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads);
     if (nnz) nnz[idx - lo] = s.nnz;
     if (nno) nno[idx - lo] = s.nno;
     if (g2) g2[idx - lo] = s.g2 * inv_den;
@@ -343,36 +345,36 @@ __global__ void __launch_bounds__(kThreads) orbit_table_kernel(int r, unsigned l
 // ---------------------------------------------------------------------------
 struct ShapeOps {
   int m, k, n;
-  void (*sweep)(int measure, int mode, int grid, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
+  void (*sweep)(int measure, int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
                 unsigned long long hi, Key* bb);
-  void (*final)(int mode, cudaStream_t st, int r, unsigned long long seed, int nblocks, int measure, double inv_den,
+  void (*final)(int mode, cudaStream_t st, int r, int3 den, unsigned long long seed, int nblocks, int measure, double inv_den,
                 const Key* bb, plo_orbit_best* out);
-  void (*table)(int mode, int grid, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
+  void (*table)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
                 unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2);
   int (*blocks_per_sm)();
 };
 
 template <int M, int K, int N>
 struct Shape {
-  static void sweep(int measure, int mode, int grid, cudaStream_t st, int r, unsigned long long seed,
+  static void sweep(int measure, int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed,
                     unsigned long long lo, unsigned long long hi, Key* bb) {
     if (measure == PLO_MEASURE_NNZ) {
-      if (mode == 0) orbit_sweep_kernel<M, K, N, 0, PLO_MEASURE_NNZ><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, bb);
-      else orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_NNZ><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, bb);
+      if (mode == 0) orbit_sweep_kernel<M, K, N, 0, PLO_MEASURE_NNZ><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, bb);
+      else orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_NNZ><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, bb);
     } else {
-      if (mode == 0) orbit_sweep_kernel<M, K, N, 0, PLO_MEASURE_G2><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, bb);
-      else orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, bb);
+      if (mode == 0) orbit_sweep_kernel<M, K, N, 0, PLO_MEASURE_G2><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, bb);
+      else orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, bb);
     }
   }
-  static void final(int mode, cudaStream_t st, int r, unsigned long long seed, int nblocks, int measure, double inv_den,
+  static void final(int mode, cudaStream_t st, int r, int3 den, unsigned long long seed, int nblocks, int measure, double inv_den,
                     const Key* bb, plo_orbit_best* out) {
-    if (mode == 0) orbit_final_kernel<M, K, N, 0><<<1, kThreads, 0, st>>>(r, seed, nblocks, measure, inv_den, bb, out);
-    else orbit_final_kernel<M, K, N, 1><<<1, kThreads, 0, st>>>(r, seed, nblocks, measure, inv_den, bb, out);
+    if (mode == 0) orbit_final_kernel<M, K, N, 0><<<1, kThreads, 0, st>>>(r, den, seed, nblocks, measure, inv_den, bb, out);
+    else orbit_final_kernel<M, K, N, 1><<<1, kThreads, 0, st>>>(r, den, seed, nblocks, measure, inv_den, bb, out);
   }
-  static void table(int mode, int grid, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
+  static void table(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
                     unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2) {
-    if (mode == 0) orbit_table_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, inv_den, nnz, nno, g2);
-    else orbit_table_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, seed, lo, hi, inv_den, nnz, nno, g2);
+    if (mode == 0) orbit_table_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2);
+    else orbit_table_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2);
   }
   static int blocks_per_sm() {
     int nb = 0;
@@ -416,6 +418,7 @@ struct plo_orbit_plan {
   int m, k, n, r, measure, mode;
   unsigned long long seed;
   double inv_den;
+  int3 den;
   const ShapeOps* ops;
   std::vector<int> h_lrp;
   Key* d_block_best;
@@ -479,6 +482,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->measure = measure; pl->mode = mode; pl->seed = seed;
   pl->inv_den = 1.0 / ((double)denL * (double)denR * (double)denP);
   if (pl->inv_den < 0) pl->inv_den = -pl->inv_den;
+  pl->den = make_int3(denL < 0 ? -denL : denL, denR < 0 ? -denR : denR, denP < 0 ? -denP : denP);
   pl->ops = ops;
   pl->h_lrp.resize((size_t)r * (m * k + k * n + m * n));
   int* dst = pl->h_lrp.data();
@@ -510,8 +514,8 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   cudaStream_t st = (cudaStream_t)stream;
   int rc = orbit_upload(pl, st);
   if (rc) return rc;
-  pl->ops->sweep(pl->measure, pl->mode, pl->grid, st, pl->r, pl->seed, lo, hi, pl->d_block_best);
-  pl->ops->final(pl->mode, st, pl->r, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
+  pl->ops->sweep(pl->measure, pl->mode, pl->grid, st, pl->r, pl->den, pl->seed, lo, hi, pl->d_block_best);
+  pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());
   return PLO_OK;
 }
@@ -567,7 +571,7 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
     if (!rc) {
       size_t blocks = (cnt + kThreads - 1) / kThreads;
       int grid = (int)(blocks < (size_t)pl->grid ? blocks : (size_t)pl->grid);
-      pl->ops->table(mode, grid, nullptr, r, seed, lo, hi, pl->inv_den, d_nnz, d_nno, d_g2);
+      pl->ops->table(mode, grid, nullptr, r, pl->den, seed, lo, hi, pl->inv_den, d_nnz, d_nno, d_g2);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { set_error("plo_orbit_table: %s", cudaGetErrorString(e)); rc = PLO_E_CUDA; }
     }

@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing of a sweep: disjoint contiguous index ranges per rank and ONE tiny
+min-allreduce that picks the global winner (the reference analogue is the `omp parallel for`
++ `omp critical` of src/orbiter.cpp:272,298).  torch.distributed is plumbing only; no other
+inter-GPU traffic exists on this path."""
+import struct
+
+INT64_MAX = 2 ** 63 - 1
+SLOT = 4  # int64 words per rank: score key, index, nnz, nno
+
+
+def shard_range(lo, hi, rank, world):
+    """Contiguous, disjoint, ascending shards of [lo,hi): shard r precedes shard r+1, so the
+    'lowest index among ties' rule equals 'lowest rank among ties'."""
+    total = max(0, hi - lo)
+    base, rem = divmod(total, world)
+    a = lo + rank * base + min(rank, rem)
+    return a, a + base + (1 if rank < rem else 0)
+
+
+def score_key(score):
+    """Order-preserving int64 image of a non-negative double (IEEE bits of x >= 0 sort like integers)."""
+    if score != score or score < 0:
+        raise ValueError("score must be a non-negative number")
+    return struct.unpack("<q", struct.pack("<d", float(score)))[0]
+
+
+def key_score(key):
+    return struct.unpack("<d", struct.pack("<q", int(key)))[0]
+
+
+def pack_local(best, rank, world):
+    """world*SLOT int64 words: INT64_MAX everywhere except this rank's slot (score key, index, nnz, nno)."""
+    words = [INT64_MAX] * (world * SLOT)
+    if best is not None and best.get("index") is not None:
+        idx = best["index"]
+        if idx > INT64_MAX:
+            raise ValueError("candidate index exceeds 63 bits")
+        words[rank * SLOT:(rank + 1) * SLOT] = [score_key(best["score"]), idx, best["nnz"], best["nno"]]
+    return words
+
+
+def pick_global(words, world, measure_nnz=False):
+    """Deterministic winner of the gathered table: minimum (score[, nno], index)."""
+    best = None
+    for r in range(world):
+        k, idx, nnz, nno = words[r * SLOT:(r + 1) * SLOT]
+        if idx == INT64_MAX:
+            continue
+        key = (k, nno, idx) if measure_nnz else (k, idx)
+        if best is None or key < best[0]:
+            best = (key, dict(score=key_score(k), index=idx, nnz=nnz, nno=nno, rank=r))
+    return None if best is None else best[1]
+
+
+def allreduce_best(best, measure_nnz=False, device=None):
+    """One all_reduce(MIN) over world*SLOT int64 words (256 B at 8 ranks)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None if best is None or best.get("index") is None else dict(best, rank=0)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    t = torch.tensor(pack_local(best, rank, world), dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return pick_global(t.tolist(), world, measure_nnz)
