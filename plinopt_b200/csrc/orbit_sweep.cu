@@ -118,6 +118,25 @@ __host__ __device__ __forceinline__ Zoi decode_zoi(Digits<MODE>& ds) {
 // (reference: inverse / inverseTranspose, plinopt_sparsify.inl:380-465).
 template <int S, bool INV>
 __host__ __device__ __forceinline__ void expand_zoi(const Zoi& z, int* out, volatile int* scr, int stride) {
+  if (S == 1) {
+    out[0] = (z.D & 1u) ? 1 : -1;
+    return;
+  }
+  if (S == 2) {
+    // T = [d0 t; 0 d1], T^-1 = [d0 -d0 t d1; 0 d1]; a 2x2 permutation is identity or swap, so
+    // M[a][b] = T[a^sp][b^sq] and M^-1[a][b] = T^-1[a^sq][b^sp]: four selects, no scratch.
+    const int d0 = (z.D & 1u) ? 1 : -1, d1 = (z.D & 2u) ? 1 : -1;
+    const int tt = (int)(z.T & 3ull) - 1;
+    const int off = INV ? -d0 * tt * d1 : tt;
+    const bool sp = (z.pP & 15u) != 0u, sq = (z.pQ & 15u) != 0u;
+    const bool sr = INV ? sq : sp, sc = INV ? sp : sq;  // row / column swaps
+    // rows of T (or T^-1): r0 = (d0, off), r1 = (0, d1)
+    const int a0 = sr ? 0 : d0, a1 = sr ? d1 : off;   // row 0 before the column swap
+    const int b0 = sr ? d0 : 0, b1 = sr ? off : d1;   // row 1 before the column swap
+    out[0] = sc ? a1 : a0; out[1] = sc ? a0 : a1;
+    out[2] = sc ? b1 : b0; out[3] = sc ? b0 : b1;
+    return;
+  }
   int t[S][S];
   {
     int idx = 0;
@@ -216,9 +235,27 @@ struct Score {
 };
 
 // Scores one candidate.  lrp = L (r x MK) | R (r x KN) | P^T (r x MN), ints.
-template <int M, int K, int N, int MODE, int MEASURE>
+// sqrt of a small non-negative integer: table lookup (the table holds the correctly rounded
+// sqrt((double)s), so the value is bit-identical to computing it).  LF = the table covers every
+// reachable value (host-side bound); otherwise values beyond the table take an out-of-line sqrt.
+#ifdef __CUDACC__
+__device__ __noinline__ double slow_isqrt(int s) { return sqrt((double)s); }
+#endif
+template <bool LF>
+__host__ __device__ __forceinline__ double isqrt_lut(int s, const double* lut, int lutn) {
+#ifdef __CUDA_ARCH__
+  if (LF || s < lutn) return lut[s];
+  return slow_isqrt(s);
+#else
+  (void)lut; (void)lutn;
+  return std::sqrt((double)s);
+#endif
+}
+
+template <int M, int K, int N, int MODE, int MEASURE, int RU = 0, bool LF = false>
 __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict__ lrp, int r, int3 den, unsigned long long seed,
-                                                          unsigned long long index, volatile int* scr, int stride) {
+                                                          unsigned long long index, volatile int* scr, int stride,
+                                                          const double* lut = nullptr, int lutn = 0) {
   Digits<MODE> ds(seed, index);
   const Zoi zu = decode_zoi<M, MODE>(ds);
   const Zoi zv = decode_zoi<K, MODE>(ds);
@@ -237,8 +274,9 @@ __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict_
   Score sc;
   sc.nnz = 0; sc.nno = 0; sc.g2 = 0.0;
   int nnz = 0, nno = 0;
-#pragma unroll 1
-  for (int l = 0; l < r; ++l) {
+  const int rows = RU > 0 ? RU : r;
+#pragma unroll(RU > 0 ? RU : 1)
+  for (int l = 0; l < rows; ++l) {
     Acc aL, aR, aP;
     aL.nnz = aL.nno = aL.sq = 0;
     aR = aL; aP = aL;
@@ -250,7 +288,7 @@ __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict_
     if (MEASURE == PLO_MEASURE_G2 || MEASURE == MEASURE_BOTH) {
       // growthfactor.cpp:117-125: s += norm2(L[i])*norm2(R[i])*norm2(Pt[i]); no FMA contraction
 #ifdef __CUDA_ARCH__
-      const double t = __dmul_rn(__dmul_rn(sqrt((double)aL.sq), sqrt((double)aR.sq)), sqrt((double)aP.sq));
+      const double t = __dmul_rn(__dmul_rn(isqrt_lut<LF>(aL.sq, lut, lutn), isqrt_lut<LF>(aR.sq, lut, lutn)), isqrt_lut<LF>(aP.sq, lut, lutn));
       sc.g2 = __dadd_rn(sc.g2, t);
 #else
       const double t = (std::sqrt((double)aL.sq) * std::sqrt((double)aR.sq)) * std::sqrt((double)aP.sq);
@@ -281,16 +319,23 @@ struct MaxDim2 {
 };
 
 // One candidate per thread, grid-stride over [lo,hi); per-block best to block_best[blockIdx.x].
-template <int M, int K, int N, int MODE, int MEASURE>
+// Dynamic shared memory: lutn doubles (sqrt table, G2 only) then the expansion scratch.
+template <int M, int K, int N, int MODE, int MEASURE, int RU, bool LF>
 __global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo,
-                                                                unsigned long long hi, Key* __restrict__ block_best) {
-  __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
+                                                                unsigned long long hi, int lutn, Key* __restrict__ block_best) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  double* lut = reinterpret_cast<double*>(dyn_smem);
+  int* scr = reinterpret_cast<int*>(dyn_smem + (size_t)lutn * sizeof(double));
   __shared__ Key red[32];
+  if (MEASURE == PLO_MEASURE_G2) {
+    for (int e = threadIdx.x; e < lutn; e += kThreads) lut[e] = sqrt((double)e);
+    __syncthreads();
+  }
   const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
-    const Score s = score_candidate<M, K, N, MODE, MEASURE>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads);
+    const Score s = score_candidate<M, K, N, MODE, MEASURE, RU, LF>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads, lut, lutn);
     const Key k = make_key<MEASURE>(s, idx);
     if (k.primary < best.primary) best = k;  // indices visited in increasing order: strict '<' keeps the first
   }
@@ -344,27 +389,31 @@ __global__ void __launch_bounds__(kThreads) orbit_table_kernel(int r, int3 den, 
 // host side
 // ---------------------------------------------------------------------------
 struct ShapeOps {
-  int m, k, n;
-  void (*sweep)(int measure, int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
-                unsigned long long hi, Key* bb);
+  int m, k, n, ru;  // ru > 0: kernel with the row loop fully unrolled for r == ru
+  void (*sweep)(int measure, int mode, int grid, size_t smem, cudaStream_t st, int r, int3 den, unsigned long long seed,
+                unsigned long long lo, unsigned long long hi, int lutn, bool lutfull, Key* bb);
   void (*final)(int mode, cudaStream_t st, int r, int3 den, unsigned long long seed, int nblocks, int measure, double inv_den,
                 const Key* bb, plo_orbit_best* out);
   void (*table)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
                 unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2);
-  int (*blocks_per_sm)();
+  int (*blocks_per_sm)(size_t smem);
+  cudaError_t (*allow_smem)(size_t smem);
 };
 
-template <int M, int K, int N>
+template <int M, int K, int N, int RU>
 struct Shape {
-  static void sweep(int measure, int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed,
-                    unsigned long long lo, unsigned long long hi, Key* bb) {
+  static constexpr size_t scratch_bytes = (size_t)MaxDim2<M, K, N>::value * kThreads * sizeof(int);
+  static void sweep(int measure, int mode, int grid, size_t smem, cudaStream_t st, int r, int3 den, unsigned long long seed,
+                    unsigned long long lo, unsigned long long hi, int lutn, bool lutfull, Key* bb) {
+#define PLO_SW(MODE_, MEAS_, LF_) orbit_sweep_kernel<M, K, N, MODE_, MEAS_, RU, LF_><<<grid, kThreads, smem, st>>>(r, den, seed, lo, hi, lutn, bb)
     if (measure == PLO_MEASURE_NNZ) {
-      if (mode == 0) orbit_sweep_kernel<M, K, N, 0, PLO_MEASURE_NNZ><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, bb);
-      else orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_NNZ><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, bb);
+      if (mode == 0) PLO_SW(0, PLO_MEASURE_NNZ, false); else PLO_SW(1, PLO_MEASURE_NNZ, false);
+    } else if (lutfull) {
+      if (mode == 0) PLO_SW(0, PLO_MEASURE_G2, true); else PLO_SW(1, PLO_MEASURE_G2, true);
     } else {
-      if (mode == 0) orbit_sweep_kernel<M, K, N, 0, PLO_MEASURE_G2><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, bb);
-      else orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, bb);
+      if (mode == 0) PLO_SW(0, PLO_MEASURE_G2, false); else PLO_SW(1, PLO_MEASURE_G2, false);
     }
+#undef PLO_SW
   }
   static void final(int mode, cudaStream_t st, int r, int3 den, unsigned long long seed, int nblocks, int measure, double inv_den,
                     const Key* bb, plo_orbit_best* out) {
@@ -376,36 +425,51 @@ struct Shape {
     if (mode == 0) orbit_table_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2);
     else orbit_table_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2);
   }
-  static int blocks_per_sm() {
+  static int blocks_per_sm(size_t smem) {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2, RU, false>, kThreads, smem);
     return nb > 0 ? nb : 1;
   }
-  static ShapeOps ops() { return ShapeOps{M, K, N, &sweep, &final, &table, &blocks_per_sm}; }
+  static cudaError_t allow_smem(size_t smem) {
+    cudaError_t e = cudaSuccess;
+#define PLO_ALLOW(MODE_, MEAS_, LF_) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(orbit_sweep_kernel<M, K, N, MODE_, MEAS_, RU, LF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PLO_ALLOW(0, PLO_MEASURE_NNZ, false) PLO_ALLOW(1, PLO_MEASURE_NNZ, false) PLO_ALLOW(0, PLO_MEASURE_G2, false)
+    PLO_ALLOW(1, PLO_MEASURE_G2, false) PLO_ALLOW(0, PLO_MEASURE_G2, true) PLO_ALLOW(1, PLO_MEASURE_G2, true)
+#undef PLO_ALLOW
+    return e;
+  }
+  static ShapeOps ops() { return ShapeOps{M, K, N, RU, &sweep, &final, &table, &blocks_per_sm, &allow_smem}; }
 };
 
-#define PLO_ORBIT_SHAPES(X) X(2, 2, 2) X(3, 3, 3) X(4, 4, 4) X(3, 4, 7)
+// (m, k, n, unrolled r); r-specialised entries come first, the generic (ru = 0) entry of a shape last
+#define PLO_ORBIT_SHAPES(X) X(2, 2, 2, 7) X(2, 2, 2, 0) X(3, 3, 3, 0) X(4, 4, 4, 0) X(3, 4, 7, 0)
 
-static const ShapeOps* find_shape(int m, int k, int n) {
-#define X(a, b, c) Shape<a, b, c>::ops(),
+static const ShapeOps* find_shape(int m, int k, int n, int r) {
+#define X(a, b, c, d) Shape<a, b, c, d>::ops(),
   static const ShapeOps table[] = {PLO_ORBIT_SHAPES(X)};
 #undef X
   for (const ShapeOps& s : table)
-    if (s.m == m && s.k == k && s.n == n) return &s;
+    if (s.m == m && s.k == k && s.n == n && (s.ru == 0 || s.ru == r)) return &s;
   return nullptr;
 }
 
 // Worst-case magnitude bound of the transformed entries (host guard for the
 // int32 arithmetic): |T^-1| entries <= 2^(s-2), row/column abs sums <= 2^(s-1);
 // a {-1,0,1} factor contributes at most its dimension.
-static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P) {
+static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, long long* smax) {
   auto maxabs = [](const int32_t* a, size_t cnt) { long long mx = 0; for (size_t i = 0; i < cnt; ++i) { long long v = a[i] < 0 ? -(long long)a[i] : a[i]; if (v > mx) mx = v; } return mx; };
   auto pw = [](int s) { return 1ll << (s > 1 ? s - 1 : 0); };
-  const long long bl = maxabs(L, (size_t)r * m * k) * pw(m) * k * m;  // generous: both factors
-  const long long br = maxabs(R, (size_t)r * k * n) * pw(k) * n * k;
-  const long long bp = maxabs(P, (size_t)r * m * n) * pw(n) * m * n;
+  const long long bl = maxabs(L, (size_t)r * m * k) * pw(m) * k;  // |U^-T A V| <= max|A| * colsum|U^-1| * colsum|V|
+  const long long br = maxabs(R, (size_t)r * k * n) * pw(k) * n;
+  const long long bp = maxabs(P, (size_t)r * m * n) * pw(n) * m;
   auto ok = [](long long b, int cnt) { return b < 46340 && b * b * cnt < 2147483647ll; };
-  return ok(bl, m * k) && ok(br, k * n) && ok(bp, m * n);
+  if (!(ok(bl, m * k) && ok(br, k * n) && ok(bp, m * n))) return false;
+  long long s = bl * bl * m * k;
+  if (br * br * k * n > s) s = br * br * k * n;
+  if (bp * bp * m * n > s) s = bp * bp * m * n;
+  *smax = s;
+  return true;
 }
 
 static const void* g_const_owner = nullptr;
@@ -423,7 +487,9 @@ struct plo_orbit_plan {
   std::vector<int> h_lrp;
   Key* d_block_best;
   plo_orbit_best* d_out;
-  int grid;
+  int grid, lutn;
+  bool lutfull;
+  size_t smem;
 };
 
 extern "C" {
@@ -473,11 +539,12 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   }
   int rc = check_device();
   if (rc) return rc;
-  const ShapeOps* ops = find_shape(m, k, n);
+  const ShapeOps* ops = find_shape(m, k, n, r);
   if (!ops) { set_error("orbit sweep: shape %dx%dx%d not compiled in", m, k, n); return PLO_E_SHAPE; }
   if ((long long)r * (m * k + k * n + m * n) > kConstInts) { set_error("orbit sweep: L/R/P exceed constant memory"); return PLO_E_SHAPE; }
   if (mode == 0 && plo_orbit_space(m, k, n) == 0) { set_error("orbit sweep: exhaustive space exceeds 64 bits"); return PLO_E_SHAPE; }
-  if (!magnitude_ok(m, k, n, r, L, R, P)) { set_error("orbit sweep: int32 magnitude bound exceeded"); return PLO_E_RANGE; }
+  long long smax = 0;
+  if (!magnitude_ok(m, k, n, r, L, R, P, &smax)) { set_error("orbit sweep: int32 magnitude bound exceeded"); return PLO_E_RANGE; }
   plo_orbit_plan* pl = new plo_orbit_plan();
   pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->measure = measure; pl->mode = mode; pl->seed = seed;
   pl->inv_den = 1.0 / ((double)denL * (double)denR * (double)denP);
@@ -490,7 +557,17 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   for (int i = 0; i < r * k * n; ++i) *dst++ = R[i];
   for (int l = 0; l < r; ++l)  // P^T: row l = column l of P
     for (int e = 0; e < m * n; ++e) *dst++ = P[(size_t)e * r + l];
-  pl->grid = sm_count() * ops->blocks_per_sm();
+  // sqrt table: covers every reachable row norm^2 when that fits in 32 KB, else the first 4096 values
+  pl->lutn = measure == PLO_MEASURE_G2 ? (int)(smax + 1 < 4096 ? smax + 1 : 4096) : 0;
+  pl->lutfull = measure == PLO_MEASURE_G2 && smax + 1 <= 4096;
+  int dmax = m > k ? (m > n ? m : n) : (k > n ? k : n);
+  pl->smem = (size_t)pl->lutn * sizeof(double) + (dmax > 2 ? (size_t)dmax * dmax * kThreads * sizeof(int) : 0);
+  if (pl->smem > 48 * 1024 && ops->allow_smem(pl->smem) != cudaSuccess) {
+    set_error("orbit sweep: cannot reserve %zu bytes of shared memory", pl->smem);
+    delete pl;
+    return PLO_E_CUDA;
+  }
+  pl->grid = sm_count() * ops->blocks_per_sm(pl->smem);
   pl->d_block_best = nullptr; pl->d_out = nullptr;
   if (cudaMalloc(&pl->d_block_best, sizeof(Key) * pl->grid) != cudaSuccess || cudaMalloc(&pl->d_out, sizeof(plo_orbit_best)) != cudaSuccess) {
     set_error("orbit sweep: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -514,7 +591,7 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   cudaStream_t st = (cudaStream_t)stream;
   int rc = orbit_upload(pl, st);
   if (rc) return rc;
-  pl->ops->sweep(pl->measure, pl->mode, pl->grid, st, pl->r, pl->den, pl->seed, lo, hi, pl->d_block_best);
+  pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());
   return PLO_OK;
