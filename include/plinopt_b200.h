@@ -49,14 +49,16 @@ const char* plo_last_error(void);     /* thread-local message of the last failin
  *                                           v = TM^T.w, zero counts, strict
  *                                           lexicographic '>' acceptance).
  *
- * p == 0 : exact integers.  The caller pre-scales TM rows and coeffs by their
- *          LCDs (zero patterns of v and w are scale invariant).  |values| must
+ * p == 0 : exact integers.  The caller pre-scales every COLUMN of TM by its LCD
+ *          and coeffs by their common LCD (zero patterns of v = TM^T.w and of
+ *          w are invariant under column / global scalings; rows of TM must NOT
+ *          be scaled individually).  |values| must
  *          keep every v_j inside int64, else PLO_E_RANGE.
  * p  > 0 : residues mod p in [0,p), p < 2^32 (src/sparsifier.cpp:71-76).
  * TM       n x m row-major (n = TM.rowdim() = width of the CoB block).
  * off      4*block ; the candidate w has coeffs[i],[j],[k],[l] at positions
  *          off..off+3 (positions >= n are truncated, reference quirk Q4).
- * coeffs   c values in the reference's enumeration order (c <= 1024).
+ * coeffs   c values in the reference's enumeration order (c <= 512).
  * prev_rows nprev x n : the rows of LCoB chosen so far (Cand rows 0..num-1,
  *          plinopt_sparsify.inl:289,172); a candidate is admissible iff it is
  *          linearly independent of them (rank(Cand) > num, :173-175).
@@ -179,6 +181,51 @@ void plo_mmcheck_plan_destroy(plo_mmcheck_plan* plan);
  * timed, best of `reps`.  Results in operations per second.
  * ------------------------------------------------------------------------ */
 int plo_measure_peaks(int reps, double* imad_per_s, double* dfma_per_s, double* ialu_per_s);
+
+/* ---------------------------------------------------------------------------
+ * Host-level entry points (C++ host orchestration around the kernels above;
+ * plinopt_b200/csrc/host/).  Rationals cross the boundary as (num, den) int64
+ * arrays, row-major.
+ * ------------------------------------------------------------------------ */
+
+/* blockSparsifier  include/plinopt_sparsify.inl:666-748  as driven by TSparsifier
+ * src/sparsifier.cpp:20-55: M (rows x cols) -> CoB (cols x cols), Res (rows x cols) with
+ * M == Res.CoB (consistency(), :871-907, reported in *consistent).  q == 0: over Q; q > 0: over
+ * Z/qZ (entries a/b -> a.b^-1 mod q, src/sparsifier.cpp:71-76; outputs are residues with den 1).
+ * stats (may be NULL): [0] candidates scored on the GPU, [1] GPU searches, [2] canonical fallbacks.
+ * log_fd: file descriptor for the reference's '# [SPRF] ...' progress lines (-1: silent). */
+int plo_sparsifier(uint64_t q, int rows, int cols, const int64_t* num, const int64_t* den, int blocksize,
+                   int maxnumcoeff, int initialElimination, int64_t* cob_num, int64_t* cob_den,
+                   int64_t* res_num, int64_t* res_den, int* consistent, uint64_t* stats, int log_fd);
+
+/* Orbiter<Measure>::operator()  src/orbiter.cpp:215-360  over Q: sweeps candidates [0, loops),
+ * applies the acceptance rule against the input (:330-331) and, if the winner improves on it,
+ * returns the transformed triple (exact rationals) and re-checks it with MMchecker (:355). */
+typedef struct plo_orbiter_report {
+  uint32_t init_nnz, init_nno;
+  double init_score;
+  plo_orbit_best best;
+  int improved;    /* 1: outputs hold the transformed triple, 0: outputs hold the input */
+  int mm_verdict;  /* MMchecker verdict of the returned triple (0 = correct) */
+  int m, k, n;
+} plo_orbiter_report;
+
+int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int Lcols, int Rcols, int Prows,
+                const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd, const int64_t* Pn,
+                const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd, int64_t* oPn, int64_t* oPd,
+                plo_orbiter_report* report);
+
+/* fMMchecker + MMchecker  src/MMchecker.cpp:48-81, include/plinopt_library.inl:472-558 on dense
+ * rational inputs.  modulus == 0: the reference checks over Q with `bitsize`-bit random inputs; this
+ * engine checks modulo the word-size prime 2^31-1 (next prime below if a denominator vanishes),
+ * `batch` independent samples.  modulus > 0: factors of 2 are stripped first (:123-126).
+ * Returns 0 correct / 1 not an MM algorithm / 2 inner / 3 outer dimension mismatch / PLO_E_*. */
+int plo_mmchecker(uint64_t modulus, uint64_t seed, int batch, int Lrows, int Lcols, int Rrows, int Rcols, int Prows,
+                  int Pcols, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                  const int64_t* Pn, const int64_t* Pd, uint32_t* nnz_nno /* [2], may be NULL */);
+
+/* include/plinopt_library.h:177-181 */
+void plo_LRP2MM(int Lcols, int Rcols, int Prows, int* m, int* k, int* n);
 
 #ifdef __cplusplus
 }

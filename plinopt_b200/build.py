@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libplinopt_b200.so")
-SOURCES = ["common.cu", "orbit_sweep.cu", "lincomb_search.cu", "mmcheck.cu", "peaks.cu"]
+SOURCES = ["common.cu", "orbit_sweep.cu", "lincomb_search.cu", "mmcheck.cu", "peaks.cu", "host/host_api.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
 
@@ -24,7 +24,7 @@ def _nvcc():
 
 
 def _deps(src):
-    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "plo_device.cuh"), os.path.join(CSRC, "host", "exact.hpp"),
+    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "plo_device.cuh"), os.path.join(CSRC, "host", "exact.hpp"), os.path.join(CSRC, "host", "sparsify_host.hpp"), os.path.join(CSRC, "host", "matrix_io.hpp"),
             os.path.join(os.path.dirname(HERE), "include", "plinopt_b200.h"), os.path.abspath(__file__)]
     return max(os.path.getmtime(d) for d in deps if os.path.exists(d))
 
@@ -36,14 +36,14 @@ def build_library(force=False, verbose=False):
     ccbin = ["-ccbin", host_cxx] if host_cxx else []
     objs, jobs = [], []
     for s in SOURCES:
-        o = os.path.join(BUILD, s.replace(".cu", ".o"))
+        o = os.path.join(BUILD, os.path.basename(s).replace(".cu", ".o").replace(".cpp", ".o"))
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < _deps(s):
             jobs.append((s, o))
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + ccbin + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + (["-x", "cu"] if s.endswith(".cpp") else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         p = subprocess.run(cmd, capture_output=True, text=True)
         with open(o + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + p.stdout + p.stderr)
@@ -64,5 +64,29 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+CLI_DIR = os.path.join(HERE, "cli")
+BIN_DIR = os.path.join(os.path.dirname(HERE), "bin")
+CLIS = ["sparsifier", "orbiter", "MMchecker"]
+
+
+def build_clis(force=False):
+    """bin/sparsifier, bin/orbiter, bin/MMchecker: host C++ drivers linked against the library."""
+    os.makedirs(BIN_DIR, exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    out = []
+    for name in CLIS:
+        src = os.path.join(CLI_DIR, name + ".cpp")
+        exe = os.path.join(BIN_DIR, name)
+        deps = [src, os.path.join(CLI_DIR, "cli_common.hpp"), os.path.join(CSRC, "host", "matrix_io.hpp"), os.path.join(CSRC, "host", "exact.hpp"), LIB]
+        if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+            cmd = [cxx, "-O2", "-std=c++17", "-o", exe, src, "-L" + HERE, "-lplinopt_b200", "-Wl,-rpath,$ORIGIN/../plinopt_b200"]
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            if p.returncode != 0:
+                raise RuntimeError(f"g++ failed on {name}:\n{p.stdout}\n{p.stderr}")
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_clis(force="--force" in sys.argv))

@@ -28,6 +28,7 @@ SYMBOLS = [
     "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
+    "plo_sparsifier", "plo_orbiter", "plo_mmchecker", "plo_LRP2MM",
 ]
 
 
@@ -314,3 +315,71 @@ def measure_peaks(reps=10):
     f.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3
     _check(f(reps, C.byref(a), C.byref(b), C.byref(c)))
     return dict(imad_per_s=a.value, dfma_per_s=b.value, ialu_pairs_per_s=c.value)
+
+
+# --------------------------------------------------------------------------
+# host-level entry points (reference drivers restated around the kernels)
+# --------------------------------------------------------------------------
+class OrbiterReport(C.Structure):
+    _fields_ = [("init_nnz", C.c_uint32), ("init_nno", C.c_uint32), ("init_score", C.c_double), ("best", OrbitBest),
+                ("improved", C.c_int), ("mm_verdict", C.c_int), ("m", C.c_int), ("k", C.c_int), ("n", C.c_int)]
+
+
+def _numden(M):
+    """list of rows of Fraction / int -> (num, den) int64 arrays."""
+    from fractions import Fraction
+    r, c = len(M), len(M[0])
+    num = np.zeros((r, c), dtype=np.int64); den = np.ones((r, c), dtype=np.int64)
+    for i in range(r):
+        for j in range(c):
+            v = Fraction(M[i][j])
+            num[i, j] = v.numerator; den[i, j] = v.denominator
+    return num, den
+
+
+def _fractions(num, den):
+    from fractions import Fraction
+    return [[Fraction(int(num[i, j]), int(den[i, j])) for j in range(num.shape[1])] for i in range(num.shape[0])]
+
+
+def sparsifier(M, q=0, blocksize=4, maxnumcoeff=11, initial_elimination=True, log_fd=-1):
+    """blockSparsifier through the GPU search.  Returns (CoB, Res, consistent, stats dict)."""
+    num, den = _numden(M)
+    r, c = num.shape
+    cn = np.zeros((c, c), dtype=np.int64); cd = np.ones((c, c), dtype=np.int64)
+    rn = np.zeros((r, c), dtype=np.int64); rd = np.ones((r, c), dtype=np.int64)
+    ok = C.c_int(0)
+    stats = np.zeros(3, dtype=np.uint64)
+    f = lib().plo_sparsifier
+    f.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_int), C.c_void_p, C.c_int]
+    _check(f(q, r, c, _ptr(num), _ptr(den), blocksize, maxnumcoeff, 1 if initial_elimination else 0, _ptr(cn), _ptr(cd), _ptr(rn), _ptr(rd),
+             C.byref(ok), _ptr(stats), log_fd))
+    st = dict(candidates=int(stats[0]), searches=int(stats[1]), fallbacks=int(stats[2]))
+    if q == 0:
+        return _fractions(cn, cd), _fractions(rn, rd), bool(ok.value), st
+    return cn.tolist(), rn.tolist(), bool(ok.value), st
+
+
+def orbiter(L, R, P, measure=MEASURE_NNZ, mode=MODE_PHILOX, seed=0, loops=100):
+    """Orbiter over Q.  Returns (Lj, Rg, hP, report dict)."""
+    Ln, Ld = _numden(L); Rn, Rd = _numden(R); Pn, Pd = _numden(P)
+    outs = [np.zeros_like(a) for a in (Ln, Ld, Rn, Rd, Pn, Pd)]
+    rep = OrbiterReport()
+    f = lib().plo_orbiter
+    f.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 12 + [C.POINTER(OrbiterReport)]
+    _check(f(measure, mode, seed, loops, len(L), len(L[0]), len(R[0]), len(P), _ptr(Ln), _ptr(Ld), _ptr(Rn), _ptr(Rd), _ptr(Pn), _ptr(Pd),
+             *[_ptr(o) for o in outs], C.byref(rep)))
+    report = dict(init_nnz=rep.init_nnz, init_nno=rep.init_nno, init_score=rep.init_score, best=_best_tuple(rep.best),
+                  improved=bool(rep.improved), mm_verdict=rep.mm_verdict, mkn=(rep.m, rep.k, rep.n))
+    return _fractions(outs[0], outs[1]), _fractions(outs[2], outs[3]), _fractions(outs[4], outs[5]), report
+
+
+def mmchecker(L, R, P, modulus=0, seed=0, batch=32):
+    """fMMchecker on dense rational matrices.  Returns (verdict, (nnz, nno))."""
+    Ln, Ld = _numden(L); Rn, Rd = _numden(R); Pn, Pd = _numden(P)
+    cnt = np.zeros(2, dtype=np.uint32)
+    f = lib().plo_mmchecker
+    f.argtypes = [C.c_uint64, C.c_uint64, C.c_int] + [C.c_int] * 6 + [C.c_void_p] * 7
+    rc = _check(f(modulus, seed, batch, len(L), len(L[0]), len(R), len(R[0]), len(P), len(P[0]), _ptr(Ln), _ptr(Ld), _ptr(Rn), _ptr(Rd),
+                  _ptr(Pn), _ptr(Pd), _ptr(cnt)), allow=(1, 2, 3))
+    return rc, (int(cnt[0]), int(cnt[1]))

@@ -1,0 +1,275 @@
+// host_api.cpp -- extern "C" host-level entry points: the reference's drivers restated around
+// the GPU kernels (TSparsifier src/sparsifier.cpp:20-55, Orbiter src/orbiter.cpp:215-360,
+// fMMchecker src/MMchecker.cpp:48-81).  No CUDA code here; everything heavy goes through the
+// kernel-level C ABI (plo_lincomb_search, plo_orbit_*, plo_mmcheck_*).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <ostream>
+#include <streambuf>
+#include <vector>
+
+#include <unistd.h>
+
+#include "../plo_device.cuh"
+#include "matrix_io.hpp"
+#include "sparsify_host.hpp"
+
+using namespace plo::host;
+
+namespace {
+
+// minimal ostream over a file descriptor (progress lines of the reference go to std::clog)
+class FdBuf : public std::streambuf {
+  int fd_;
+ protected:
+  int overflow(int c) override { if (c != EOF) { char ch = (char)c; if (::write(fd_, &ch, 1) != 1) return EOF; } return c; }
+  std::streamsize xsputn(const char* s, std::streamsize n) override { return ::write(fd_, s, (size_t)n); }
+ public:
+  explicit FdBuf(int fd) : fd_(fd) {}
+};
+
+template <class F>
+Dense<F> load(const F& f, size_t r, size_t c, const int64_t* num, const int64_t* den) {
+  Dense<F> M(f, r, c);
+  for (size_t e = 0; e < r * c; ++e) M.v[e] = f.from_ratio(num[e], den ? den[e] : 1);
+  return M;
+}
+void store(const Dense<QField>& M, int64_t* num, int64_t* den) {
+  for (size_t e = 0; e < M.v.size(); ++e) { num[e] = M.v[e].num; if (den) den[e] = M.v[e].den; }
+}
+void store(const Dense<ZpField>& M, int64_t* num, int64_t* den) {
+  for (size_t e = 0; e < M.v.size(); ++e) { num[e] = M.v[e]; if (den) den[e] = 1; }
+}
+
+template <class F>
+int run_sparsifier(const F& f, int rows, int cols, const int64_t* num, const int64_t* den, int blocksize, int maxnumcoeff,
+                   int initialElimination, int64_t* cob_num, int64_t* cob_den, int64_t* res_num, int64_t* res_den,
+                   int* consistent, uint64_t* stats, std::ostream* log) {
+  Dense<F> M = load(f, (size_t)rows, (size_t)cols, num, den);
+  Sparsifier<F> sp(f, log);
+  if (log) { size_t sc; sp.densityProfile(*log << "# [SPRF] Initial profile: ", sc, M) << std::endl; *log << std::string(30, '#') << std::endl; }
+  Dense<F> CoB(f, (size_t)cols, (size_t)cols), Res(f, (size_t)rows, (size_t)cols);
+  sp.blockSparsifier(CoB, Res, M, (size_t)blocksize, (size_t)maxnumcoeff, initialElimination != 0);
+  store(CoB, cob_num, cob_den);
+  store(Res, res_num, res_den);
+  if (consistent) *consistent = sp.consistency(M, Res, CoB) ? 1 : 0;
+  if (stats) { stats[0] = sp.stats.candidates; stats[1] = sp.stats.searches; stats[2] = sp.stats.fallbacks; }
+  return PLO_OK;
+}
+
+int64_t lcd_of(const int64_t* den, size_t cnt) {
+  int64_t l = 1;
+  for (size_t e = 0; e < cnt; ++e) {
+    const int64_t d = den ? (den[e] < 0 ? -den[e] : den[e]) : 1;
+    if (d == 0) throw RangeError("zero denominator");
+    const wide v = (wide)l / wgcd(l, d) * d;
+    if (v > (wide)INT32_MAX) throw RangeError("common denominator exceeds 31 bits");
+    l = (int64_t)v;
+  }
+  return l;
+}
+std::vector<int32_t> scale_int32(const int64_t* num, const int64_t* den, size_t cnt, int64_t lcd) {
+  std::vector<int32_t> out(cnt);
+  for (size_t e = 0; e < cnt; ++e) {
+    const int64_t d = den ? den[e] : 1;
+    const wide v = (wide)num[e] * (lcd / d);
+    if (wabs(v) > (wide)INT32_MAX) throw RangeError("scaled entry exceeds 31 bits");
+    out[e] = (int32_t)v;
+  }
+  return out;
+}
+
+void count_nonzeroes(const Dense<QField>& M, uint32_t& nnz, uint32_t& nno) {  // plinopt_library.inl:258-269
+  for (const Rat& e : M.v)
+    if (e.num != 0) { ++nnz; if (!(e.den == 1 && (e.num == 1 || e.num == -1))) ++nno; }
+}
+double growth_G2(const Dense<QField>& L, const Dense<QField>& R, const Dense<QField>& P) {  // growthfactor.cpp:117-125
+  double s = 0.;
+  for (size_t i = 0; i < P.cols; ++i) {
+    double a = 0., b = 0., c = 0.;
+    for (size_t j = 0; j < L.cols; ++j) { const double x = (double)L.at(i, j).num / (double)L.at(i, j).den; a += x * x; }
+    for (size_t j = 0; j < R.cols; ++j) { const double x = (double)R.at(i, j).num / (double)R.at(i, j).den; b += x * x; }
+    for (size_t j = 0; j < P.rows; ++j) { const double x = (double)P.at(j, i).num / (double)P.at(j, i).den; c += x * x; }
+    s += std::sqrt(a) * std::sqrt(b) * std::sqrt(c);
+  }
+  return s;
+}
+
+struct CsrHost {
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> col;
+  std::vector<uint32_t> val;
+  plo_csr view(int rows, int cols) const { plo_csr c; c.rows = rows; c.cols = cols; c.ptr = ptr.data(); c.col = col.data(); c.val = val.data(); return c; }
+};
+// a/b -> a.b^-1 mod p ; returns false if some denominator vanishes mod p
+bool to_csr(const Dense<QField>& M, int64_t p, CsrHost& out) {
+  ZpField Z(p);
+  out.ptr.assign(1, 0); out.col.clear(); out.val.clear();
+  for (size_t i = 0; i < M.rows; ++i) {
+    for (size_t j = 0; j < M.cols; ++j) {
+      const Rat& e = M.at(i, j);
+      if (e.num == 0) continue;
+      if (Z.canon(e.den) == 0) return false;
+      const int64_t v = Z.div(Z.canon(e.num), Z.canon(e.den));
+      if (v) { out.col.push_back((int32_t)j); out.val.push_back((uint32_t)v); }
+    }
+    out.ptr.push_back((int64_t)out.col.size());
+  }
+  return true;
+}
+bool is_prime(uint64_t x) {
+  if (x < 2) return false;
+  for (uint64_t d = 2; d * d <= x; ++d) if (x % d == 0) return false;
+  return true;
+}
+
+int mmcheck_dense(uint64_t modulus, uint64_t seed, int batch, const Dense<QField>& L, const Dense<QField>& R, const Dense<QField>& P) {
+  int m, k, n;
+  plo_LRP2MM((int)L.cols, (int)R.cols, (int)P.rows, &m, &k, &n);
+  if (L.rows != R.rows || L.rows != P.cols) return 2;                                                   // MMchecker.cpp:65-71
+  if ((int)L.cols != m * k || (int)R.cols != k * n || (int)P.rows != m * n) return 3;                  // library.inl:487-495
+  uint64_t p = modulus;
+  if (p > 0) { while ((p % 2) == 0) p >>= 1; if (p == 1) p = 2; }                                      // MMchecker.cpp:123-126
+  CsrHost cl, cr, cp;
+  if (p == 0) {
+    for (p = 2147483647ull; p > 2; p -= 2) {
+      if (!is_prime(p)) continue;
+      if (to_csr(L, (int64_t)p, cl) && to_csr(R, (int64_t)p, cr) && to_csr(P, (int64_t)p, cp)) break;
+    }
+  } else {
+    if (p >= (1ull << 32)) { plo::set_error("mmchecker: modulus must be below 2^32 after stripping factors of 2"); return PLO_E_ARG; }
+    if (!(to_csr(L, (int64_t)p, cl) && to_csr(R, (int64_t)p, cr) && to_csr(P, (int64_t)p, cp))) {
+      plo::set_error("mmchecker: a denominator is not invertible modulo %llu", (unsigned long long)p);
+      return PLO_E_ARG;
+    }
+  }
+  const plo_csr vl = cl.view((int)L.rows, (int)L.cols), vr = cr.view((int)R.rows, (int)R.cols), vp = cp.view((int)P.rows, (int)P.cols);
+  return plo_mmcheck_batch((uint32_t)p, m, k, n, (int)L.rows, &vl, &vr, &vp, seed, batch, nullptr, nullptr, nullptr);
+}
+
+}  // namespace
+
+extern "C" {
+
+void plo_LRP2MM(int Lcols, int Rcols, int Prows, int* m, int* k, int* n) {
+  const size_t nn = (size_t)std::sqrt((double)((size_t)Rcols * (size_t)Prows / (size_t)(Lcols ? Lcols : 1)));
+  *n = (int)nn;
+  *m = nn ? (int)((size_t)Prows / nn) : 0;
+  *k = nn ? (int)((size_t)Rcols / nn) : 0;
+}
+
+int plo_sparsifier(uint64_t q, int rows, int cols, const int64_t* num, const int64_t* den, int blocksize,
+                   int maxnumcoeff, int initialElimination, int64_t* cob_num, int64_t* cob_den,
+                   int64_t* res_num, int64_t* res_den, int* consistent, uint64_t* stats, int log_fd) {
+  if (!num || !cob_num || !res_num || rows < 1 || cols < 1 || blocksize < 0 || maxnumcoeff < 1 || q >= (1ull << 32)) {
+    plo::set_error("plo_sparsifier: bad argument");
+    return PLO_E_ARG;
+  }
+  int rc = plo::check_device();
+  if (rc) return rc;
+  FdBuf buf(log_fd);
+  std::ostream logstream(&buf);
+  std::ostream* log = log_fd >= 0 ? &logstream : nullptr;
+  try {
+    if (q == 0) { QField f; return run_sparsifier(f, rows, cols, num, den, blocksize, maxnumcoeff, initialElimination, cob_num, cob_den, res_num, res_den, consistent, stats, log); }
+    ZpField f((int64_t)q);
+    return run_sparsifier(f, rows, cols, num, den, blocksize, maxnumcoeff, initialElimination, cob_num, cob_den, res_num, res_den, consistent, stats, log);
+  } catch (const EngineError& e) {
+    plo::set_error("plo_sparsifier: %s", e.what());
+    return e.code;
+  } catch (const RangeError& e) {
+    plo::set_error("plo_sparsifier: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
+int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int Lcols, int Rcols, int Prows,
+                const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd, const int64_t* Pn,
+                const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd, int64_t* oPn, int64_t* oPd,
+                plo_orbiter_report* rep) {
+  if (!Ln || !Rn || !Pn || !oLn || !oRn || !oPn || !oLd || !oRd || !oPd || !rep || r < 1 || Lcols < 1 || Rcols < 1 || Prows < 1) {
+    plo::set_error("plo_orbiter: bad argument");
+    return PLO_E_ARG;
+  }
+  int rc = plo::check_device();
+  if (rc) return rc;
+  try {
+    QField Q;
+    int m, k, n;
+    plo_LRP2MM(Lcols, Rcols, Prows, &m, &k, &n);
+    if (Lcols != m * k || Rcols != k * n || Prows != m * n) { plo::set_error("plo_orbiter: outer dimension mismatch"); return 3; }
+    Dense<QField> L = load(Q, (size_t)r, (size_t)Lcols, Ln, Ld), R = load(Q, (size_t)r, (size_t)Rcols, Rn, Rd), P = load(Q, (size_t)Prows, (size_t)r, Pn, Pd);
+    memset(rep, 0, sizeof(*rep));
+    rep->m = m; rep->k = k; rep->n = n;
+    count_nonzeroes(L, rep->init_nnz, rep->init_nno); count_nonzeroes(R, rep->init_nnz, rep->init_nno); count_nonzeroes(P, rep->init_nnz, rep->init_nno);
+    rep->init_score = measure == PLO_MEASURE_G2 ? growth_G2(L, R, P) : (double)rep->init_nnz;
+    // integer images
+    std::vector<int64_t> ld(L.v.size()), rd(R.v.size()), pd(P.v.size()), ln(L.v.size()), rn(R.v.size()), pn(P.v.size());
+    for (size_t e = 0; e < L.v.size(); ++e) { ln[e] = L.v[e].num; ld[e] = L.v[e].den; }
+    for (size_t e = 0; e < R.v.size(); ++e) { rn[e] = R.v[e].num; rd[e] = R.v[e].den; }
+    for (size_t e = 0; e < P.v.size(); ++e) { pn[e] = P.v[e].num; pd[e] = P.v[e].den; }
+    const int64_t dl = lcd_of(ld.data(), ld.size()), dr = lcd_of(rd.data(), rd.size()), dp = lcd_of(pd.data(), pd.size());
+    const std::vector<int32_t> Li = scale_int32(ln.data(), ld.data(), ln.size(), dl), Ri = scale_int32(rn.data(), rd.data(), rn.size(), dr),
+                               Pi = scale_int32(pn.data(), pd.data(), pn.size(), dp);
+    rc = plo_orbit_sweep(0, m, k, n, r, Li.data(), Ri.data(), Pi.data(), (int32_t)dl, (int32_t)dr, (int32_t)dp, measure, mode, seed, 0, loops, &rep->best);
+    if (rc) return rc;
+    // acceptance against the input, src/orbiter.cpp:330-331
+    bool improved = false;
+    if (rep->best.index != PLO_NO_INDEX) {
+      if (measure == PLO_MEASURE_G2) improved = rep->best.score < rep->init_score;
+      else improved = rep->best.nnz < rep->init_nnz || (rep->best.nnz == rep->init_nnz && rep->best.nno < rep->init_nno);
+    }
+    Dense<QField> Lj = L, Rg = R, hP = P;
+    if (improved) {
+      std::vector<int32_t> U((size_t)m * m), V((size_t)k * k), W((size_t)n * n);
+      plo_orbit_decode(m, k, n, mode, seed, rep->best.index, U.data(), V.data(), W.data());
+      Sparsifier<QField> la(Q, nullptr);
+      auto tomat = [&](const std::vector<int32_t>& a, int s) { Dense<QField> M(Q, (size_t)s, (size_t)s); for (size_t e = 0; e < a.size(); ++e) M.v[e] = Rat(a[e]); return M; };
+      const Dense<QField> Um = tomat(U, m), Vm = tomat(V, k), Wm = tomat(W, n);
+      const Dense<QField> iU = la.inverse(Um), iV = la.inverse(Vm), iW = la.inverse(Wm);
+      const Dense<QField> iUT = la.transpose(iU), iWT = la.transpose(iW);
+      // row l of L.(U^-1 (x) V) = vec(U^-T A_l V), of R.(V^-T (x) W) = vec(V^-1 B_l W); column l of (U (x) W^-1).P = vec(U C_l W^-T)
+      for (int l = 0; l < r; ++l) {
+        Dense<QField> A(Q, (size_t)m, (size_t)k), B(Q, (size_t)k, (size_t)n), C(Q, (size_t)m, (size_t)n);
+        for (int e = 0; e < m * k; ++e) A.v[e] = L.at((size_t)l, (size_t)e);
+        for (int e = 0; e < k * n; ++e) B.v[e] = R.at((size_t)l, (size_t)e);
+        for (int e = 0; e < m * n; ++e) C.v[e] = P.at((size_t)e, (size_t)l);
+        const Dense<QField> Y1 = la.mul(la.mul(iUT, A), Vm), Y2 = la.mul(la.mul(iV, B), Wm), Y3 = la.mul(la.mul(Um, C), iWT);
+        for (int e = 0; e < m * k; ++e) Lj.at((size_t)l, (size_t)e) = Y1.v[e];
+        for (int e = 0; e < k * n; ++e) Rg.at((size_t)l, (size_t)e) = Y2.v[e];
+        for (int e = 0; e < m * n; ++e) hP.at((size_t)e, (size_t)l) = Y3.v[e];
+      }
+    }
+    rep->improved = improved ? 1 : 0;
+    store(Lj, oLn, oLd); store(Rg, oRn, oRd); store(hP, oPn, oPd);
+    rep->mm_verdict = mmcheck_dense(0, seed ^ 0x4D4D636865636Bull, 32, Lj, Rg, hP);  // :355
+    return PLO_OK;
+  } catch (const RangeError& e) {
+    plo::set_error("plo_orbiter: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
+int plo_mmchecker(uint64_t modulus, uint64_t seed, int batch, int Lrows, int Lcols, int Rrows, int Rcols, int Prows,
+                  int Pcols, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                  const int64_t* Pn, const int64_t* Pd, uint32_t* nnz_nno) {
+  if (!Ln || !Rn || !Pn || batch < 1 || Lrows < 1 || Lcols < 1 || Rrows < 1 || Rcols < 1 || Prows < 1 || Pcols < 1) {
+    plo::set_error("plo_mmchecker: bad argument");
+    return PLO_E_ARG;
+  }
+  try {
+    QField Q;
+    const Dense<QField> L = load(Q, (size_t)Lrows, (size_t)Lcols, Ln, Ld), R = load(Q, (size_t)Rrows, (size_t)Rcols, Rn, Rd), P = load(Q, (size_t)Prows, (size_t)Pcols, Pn, Pd);
+    if (nnz_nno) { nnz_nno[0] = nnz_nno[1] = 0; count_nonzeroes(L, nnz_nno[0], nnz_nno[1]); count_nonzeroes(R, nnz_nno[0], nnz_nno[1]); count_nonzeroes(P, nnz_nno[0], nnz_nno[1]); }
+    if (L.rows != R.rows || L.rows != P.cols) return 2;
+    int rc = plo::check_device();
+    if (rc) return rc;
+    return mmcheck_dense(modulus, seed, batch, L, R, P);
+  } catch (const RangeError& e) {
+    plo::set_error("plo_mmchecker: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+"""GPU tests of the drop-in CLIs (same flags / streams / files as src/sparsifier.cpp, src/orbiter.cpp, src/MMchecker.cpp)."""
+import os
+import subprocess
+
+import pytest
+
+import oracle_lib as O
+from plinopt_b200 import hm
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin")
+
+
+def write_triple(tmp_path, stem):
+    paths = []
+    for x, M in zip("LRP", O.triple(stem)):
+        p = tmp_path / f"{stem}_{x}.sms"
+        hm.write_sms(M, str(p))
+        paths.append(str(p))
+    return paths
+
+
+def test_sparsifier_cli_fdt_style(capi, tmp_path):
+    """bin/FDT.sh:64-66: `sparsifier -c 5 f` and `sparsifier -q 7 -c 5 f` must print SUCCESS; -S output parses back to the oracle's CoB."""
+    M = O.dense_fractions("2x2x2_7_DPS-smallrat-12.2034_L")
+    f = tmp_path / "m.sms"
+    hm.write_sms(M, str(f))
+    for extra in ([], ["-q", "7"]):
+        p = subprocess.run([os.path.join(BIN, "sparsifier"), "-S", "-c", "5"] + extra + [str(f)], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr
+        assert "SUCCESS: consistent factorization!" in p.stderr and "# [SPRF] linear combination coefficients:" in p.stderr
+        CoB = hm.read_sms(p.stdout.splitlines())
+        eC, eR, ok, _ = O.sparsifier(M, 7 if extra else 0, 4, 5, True)
+        assert CoB == [[O.Fraction(v) for v in row] for row in eC]
+    # stdin input and -c 4 (BASELINE config 1)
+    p = subprocess.run([os.path.join(BIN, "sparsifier"), "-c", "4"], input=open(f).read(), capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "SUCCESS" in p.stderr and "7x4 by 4x4" in p.stderr
+
+
+def test_orbiter_cli_writes_nnz_sms(capi, tmp_path):
+    files = write_triple(tmp_path, "2x2x2_7_Winograd")
+    p = subprocess.run([os.path.join(BIN, "orbiter"), "-g", "-O", "20000", "--seed", "77"] + files, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "# Init. ops:" in p.stderr and "# Search(20000):" in p.stderr and "Rdcd. opt" in p.stderr
+    outs = [f.replace(".sms", ".nnz.sms") for f in files]
+    Lj, Rg, hP = (hm.read_sms(o) for o in outs)
+    assert O.growth_G2(Lj, Rg, hP) < 15.0  # Winograd (17.85) -> 14.83 point of its orbit
+    q = subprocess.run([os.path.join(BIN, "MMchecker")] + outs, capture_output=True, text=True, timeout=300)
+    assert q.returncode == 0 and "SUCCESS: correct 2x2x2" in q.stderr
+
+
+def test_mmchecker_cli_exit_codes(capi, tmp_path):
+    """Makefile:60-64 mmcheck targets + the error codes of src/MMchecker.cpp:65-71 / plinopt_library.inl:494,555."""
+    s = write_triple(tmp_path, "2x2x2_7_Strassen")
+    a = write_triple(tmp_path, "2x2x2_7_DPS-accurate")
+    run = lambda args: subprocess.run([os.path.join(BIN, "MMchecker")] + args, capture_output=True, text=True, timeout=300)
+    assert run(s).returncode == 0
+    assert run(["-m", "513083"] + a).returncode == 0
+    assert run(["-r", "1013", "2", "3"] + a).returncode == 0
+    r = run(a)
+    assert r.returncode == 1 and "ERROR, not a 2x2x2 MM algorithm" in r.stderr
+    w = write_triple(tmp_path, "3x3x3_23_58")
+    assert run([s[0], w[1], s[2]]).returncode == 2

@@ -1,0 +1,102 @@
+"""GPU parity of the host-level drivers (reference CLIs restated around the kernels) vs the CPU oracle:
+the whole sparsifier pipeline must return the SAME CoB and residue as the oracle's literal pipeline
+(same documented pivot rule on both sides, quad loops on the GPU vs literal testLinComb on the CPU)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from plinopt_b200 import hm
+
+pytestmark = pytest.mark.gpu
+
+FDT = ["2x2x2_7_DPS-smallrat-12.2034_L", "2x2x2_7_Winograd_R", "2x2x2_7_DPS-accurate_P", "3x3x3_23_58_L", "3x3x6_40_R",
+       "4x4x4_48_rational_L", "4x4x4_48_rational_R", "4x4x4_48_accurate_L", "3x4x7_63_rational_L", "3x4x7_63_rational_R",
+       "3x4x7_63_rational_P", "4x4x4_49_156_P", "6x3x3_40_L", "cyclic"]
+
+
+@pytest.mark.parametrize("name", FDT)
+@pytest.mark.parametrize("q,c", [(0, 5), (7, 5)])
+def test_sparsifier_matches_oracle_pipeline(capi, name, q, c):
+    """bin/FDT.sh:64-66 configurations (`-c 5`, `-q 7 -c 5`): consistent factorisation, identical to the oracle's."""
+    M = O.dense_fractions(name)
+    CoB, Res, ok, st = capi.sparsifier(M, q, 4, c, True)
+    eC, eR, eok, _ = O.sparsifier(M, q, 4, c, True)
+    assert ok and eok
+    assert Res == eR and CoB == eC
+    assert st["searches"] > 0 and st["candidates"] >= st["searches"] * 81
+
+
+def test_c1_config_trace(capi):
+    """BASELINE config 1: sparsifier -c 4 data/2x2x2_7_DPS-smallrat-12.2034_L.sms."""
+    M = O.dense_fractions("2x2x2_7_DPS-smallrat-12.2034_L")
+    CoB, Res, ok, st = capi.sparsifier(M, 0, 4, 4, True)
+    eC, eR, eok, tr = O.sparsifier(M, 0, 4, 4, True, trace=True)
+    assert ok and (CoB, Res) == (eC, eR)
+    assert st["searches"] == len(tr) and st["candidates"] == sum(t["c"] ** 4 for t in tr)
+    # Res . CoB == M exactly
+    prod = [[sum(Res[i][t] * CoB[t][j] for t in range(4)) for j in range(4)] for i in range(7)]
+    assert prod == M
+
+
+@pytest.mark.parametrize("opts", [dict(blocksize=1, maxnumcoeff=4, initial_elimination=True), dict(blocksize=4, maxnumcoeff=6, initial_elimination=False),
+                                  dict(blocksize=8, maxnumcoeff=4, initial_elimination=True)])
+def test_sparsifier_flag_variants(capi, opts):
+    """-b / -U variants: whole-matrix mode (blocksize <= 1), no initial LU, wide blocks (n = 8: two 4-blocks per call)."""
+    M = O.dense_fractions("3x3x3_23_58_L") if opts["blocksize"] != 8 else O.dense_fractions("4x4x4_48_rational_R")
+    if opts["blocksize"] == 1:
+        M = [row[:6] for row in M]
+    a = capi.sparsifier(M, 0, **opts)
+    b = O.sparsifier(M, 0, opts["blocksize"], opts["maxnumcoeff"], opts["initial_elimination"])
+    assert a[2] and (a[0], a[1]) == (b[0], b[1])
+
+
+def test_c3_config_mod_p31(capi):
+    """BASELINE config 3 (single GPU part): sparsifier -q 2147483647 on 4x4x4_48_rational_L, default -c 11."""
+    M = O.dense_fractions("4x4x4_48_rational_L")
+    q = 2147483647
+    CoB, Res, ok, st = capi.sparsifier(M, q, 4, 11, True)
+    eC, eR, eok, _ = O.sparsifier(M, q, 4, 11, True)
+    assert ok and (CoB, Res) == (eC, eR)
+    assert sum(1 for r in Res for v in r if v) < sum(1 for r in M for v in r if v)
+
+
+def test_orbiter_driver(capi):
+    """src/orbiter.cpp:215-360: the returned triple is the oracle's transform of the winner, passes MMchecker,
+    and obeys the acceptance rule against the input (:330-331)."""
+    for stem, loops in [("2x2x2_7_Winograd", 5000), ("3x3x3_23_58", 20000), ("4x4x4_48_rational", 2000)]:
+        L, R, P = O.triple(stem)
+        for measure in (0, 3):
+            Lj, Rg, hP, rep = capi.orbiter(L, R, P, measure, 1, 77, loops)
+            ref = O.orbit_sweep(L, R, P, measure, 1, 77, 0, loops, table=False)["best"]
+            assert rep["best"]["index"] == ref[0] and rep["best"]["nnz"] == ref[1] and rep["best"]["nno"] == ref[2]
+            assert rep["mm_verdict"] == 0
+            if rep["improved"]:
+                U, V, W = capi.orbit_decode(*rep["mkn"], 1, 77, rep["best"]["index"])
+                assert (Lj, Rg, hP) == O.orbit_apply(L, R, P, U, V, W)
+                nnz = sum(1 for M in (Lj, Rg, hP) for row in M for v in row if v != 0)
+                assert nnz == rep["best"]["nnz"]
+                if measure == 0:
+                    assert (nnz, rep["best"]["nno"]) < (rep["init_nnz"], rep["init_nno"])
+                else:
+                    assert abs(O.growth_G2(Lj, Rg, hP) - rep["best"]["score"]) <= 1e-12 * rep["best"]["score"] < rep["init_score"]
+            else:
+                assert (Lj, Rg, hP) == (L, R, P)
+    # Winograd -> a Strassen-like 14.83 point of the orbit must be found within 5000 candidates
+    L, R, P = O.triple("2x2x2_7_Winograd")
+    _, _, _, rep = capi.orbiter(L, R, P, 3, 1, 77, 5000)
+    assert rep["improved"] and rep["best"]["score"] < 15.0
+
+
+def test_mmchecker_driver(capi):
+    """Makefile:60-64 mmcheck targets through the driver: Strassen over Q; DPS-accurate -m 513083 and -r 1013 2 3."""
+    L, R, P = O.triple("2x2x2_7_Strassen")
+    assert capi.mmchecker(L, R, P)[0] == 0
+    assert capi.mmchecker(L, R, P)[1] == (36, 0)
+    L, R, P = O.triple("2x2x2_7_DPS-accurate")
+    assert capi.mmchecker(L, R, P, modulus=513083)[0] == 0
+    assert capi.mmchecker(L, R, P, modulus=1013 ** 2 - 3)[0] == 0   # factors of 2 stripped (MMchecker.cpp:123-126)
+    assert capi.mmchecker(L, R, P)[0] == 1                           # 1013 is only sqrt(3) modulo 513083
+    L, R, P = O.triple("3x4x7_63_rational")
+    assert capi.mmchecker(L, R, P, batch=64)[0] == 0
+    assert capi.mmchecker(L, R[:-1], P)[0] == 2
+    assert capi.mmchecker(L, [row[:-1] for row in R], P)[0] == 3
