@@ -11,6 +11,7 @@
 // materialising a Kronecker product, and the measure (nnz/nno: plinopt_library.inl:
 // 258-284; G2: growthfactor.cpp:117-125) feeds a warp-shuffle + block argmin.
 #include <math.h>
+#include <stdlib.h>
 
 #include <cmath>
 #include <type_traits>
@@ -229,6 +230,55 @@ __host__ __device__ __forceinline__ void transform_row(const int* __restrict__ A
   }
 }
 
+// ---------------------------------------------------------------------------
+// Two-lane variant: two rows x0,x1 of Y = Lm'.A.Rm' travel in one 32-bit register as
+// v = y[x0] + 65536*y[x1] (plain integer arithmetic is linear in this encoding, so both stages
+// of the product act on both lanes with ONE IMAD each); lanes are split only to be scored:
+// hi = (v + 0x8000) >> 16, lo = sign-extended low half.  Valid while every |entry| < 2^15
+// (host-side magnitude bound).  Halves the IMAD count of the transforms.
+// ---------------------------------------------------------------------------
+template <int RA, bool TL>
+__device__ __forceinline__ void pack_left(const int* Lm, int* LmP) {
+  // LmP[xp*RA + i] = Lm'[2xp][i] + (Lm'[2xp+1][i] << 16), Lm' = TL ? Lm^T : Lm
+#pragma unroll
+  for (int xp = 0; xp < (RA + 1) / 2; ++xp)
+#pragma unroll
+    for (int i = 0; i < RA; ++i) {
+      const int x0 = 2 * xp, x1 = 2 * xp + 1;
+      const int lo = TL ? Lm[i * RA + x0] : Lm[x0 * RA + i];
+      const int hi = x1 < RA ? (TL ? Lm[i * RA + x1] : Lm[x1 * RA + i]) : 0;
+      LmP[xp * RA + i] = lo + hi * 65536;
+    }
+}
+
+template <int RA, int CA, bool TR, int MEASURE>
+__device__ __forceinline__ void transform_row_packed(const int* __restrict__ A, const int* LmP, const int* Rm, int den, Acc& acc) {
+  int a[RA * CA];
+#pragma unroll
+  for (int e = 0; e < RA * CA; ++e) a[e] = A[e];
+#pragma unroll
+  for (int xp = 0; xp < (RA + 1) / 2; ++xp) {
+    int X[CA];
+#pragma unroll
+    for (int j = 0; j < CA; ++j) {
+      int s = 0;
+#pragma unroll
+      for (int i = 0; i < RA; ++i) s += LmP[xp * RA + i] * a[i * CA + j];
+      X[j] = s;
+    }
+#pragma unroll
+    for (int y = 0; y < CA; ++y) {
+      int v = 0;
+#pragma unroll
+      for (int j = 0; j < CA; ++j) v += X[j] * (TR ? Rm[y * CA + j] : Rm[j * CA + y]);
+      const int hi = (v + 0x8000) >> 16;
+      const int lo = (int)(short)(v & 0xFFFF);
+      consume<MEASURE>(acc, lo, den);
+      if (2 * xp + 1 < RA) consume<MEASURE>(acc, hi, den);
+    }
+  }
+}
+
 struct Score {
   uint32_t nnz, nno;
   double g2;
@@ -252,7 +302,7 @@ __host__ __device__ __forceinline__ double isqrt_lut(int s, const double* lut, i
 #endif
 }
 
-template <int M, int K, int N, int MODE, int MEASURE, int RU = 0, bool LF = false>
+template <int M, int K, int N, int MODE, int MEASURE, int RU = 0, bool LF = false, bool PACK = false>
 __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict__ lrp, int r, int3 den, unsigned long long seed,
                                                           unsigned long long index, volatile int* scr, int stride,
                                                           const double* lut = nullptr, int lutn = 0) {
@@ -271,6 +321,14 @@ __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict_
   const int* Lc = lrp;
   const int* Rc = lrp + r * M * K;
   const int* Pc = Rc + r * K * N;
+#ifdef __CUDA_ARCH__
+  int UiTP[((M + 1) / 2) * M], ViP[((K + 1) / 2) * K], UP[((M + 1) / 2) * M];
+  if (PACK) {
+    pack_left<M, true>(Ui, UiTP);
+    pack_left<K, false>(Vi, ViP);
+    pack_left<M, false>(U, UP);
+  }
+#endif
   Score sc;
   sc.nnz = 0; sc.nno = 0; sc.g2 = 0.0;
   int nnz = 0, nno = 0;
@@ -280,9 +338,18 @@ __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict_
     Acc aL, aR, aP;
     aL.nnz = aL.nno = aL.sq = 0;
     aR = aL; aP = aL;
-    transform_row<M, K, true, false, MEASURE>(Lc + l * M * K, Ui, V, den.x, aL);   // U^-T A V
-    transform_row<K, N, false, false, MEASURE>(Rc + l * K * N, Vi, W, den.y, aR);  // V^-1 B W
-    transform_row<M, N, false, true, MEASURE>(Pc + l * M * N, U, Wi, den.z, aP);   // U C W^-T
+#ifdef __CUDA_ARCH__
+    if (PACK) {
+      transform_row_packed<M, K, false, MEASURE>(Lc + l * M * K, UiTP, V, den.x, aL);
+      transform_row_packed<K, N, false, MEASURE>(Rc + l * K * N, ViP, W, den.y, aR);
+      transform_row_packed<M, N, true, MEASURE>(Pc + l * M * N, UP, Wi, den.z, aP);
+    } else
+#endif
+    {
+      transform_row<M, K, true, false, MEASURE>(Lc + l * M * K, Ui, V, den.x, aL);   // U^-T A V
+      transform_row<K, N, false, false, MEASURE>(Rc + l * K * N, Vi, W, den.y, aR);  // V^-1 B W
+      transform_row<M, N, false, true, MEASURE>(Pc + l * M * N, U, Wi, den.z, aP);   // U C W^-T
+    }
     nnz += aL.nnz + aR.nnz + aP.nnz;
     nno += aL.nno + aR.nno + aP.nno;
     if (MEASURE == PLO_MEASURE_G2 || MEASURE == MEASURE_BOTH) {
@@ -320,7 +387,7 @@ struct MaxDim2 {
 
 // One candidate per thread, grid-stride over [lo,hi); per-block best to block_best[blockIdx.x].
 // Dynamic shared memory: lutn doubles (sqrt table, G2 only) then the expansion scratch.
-template <int M, int K, int N, int MODE, int MEASURE, int RU, bool LF>
+template <int M, int K, int N, int MODE, int MEASURE, int RU, bool LF, bool PACK>
 __global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo,
                                                                 unsigned long long hi, int lutn, Key* __restrict__ block_best) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -335,7 +402,7 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, int3 den, 
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
-    const Score s = score_candidate<M, K, N, MODE, MEASURE, RU, LF>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads, lut, lutn);
+    const Score s = score_candidate<M, K, N, MODE, MEASURE, RU, LF, PACK>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads, lut, lutn);
     const Key k = make_key<MEASURE>(s, idx);
     if (k.primary < best.primary) best = k;  // indices visited in increasing order: strict '<' keeps the first
   }
@@ -391,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) orbit_table_kernel(int r, int3 den, 
 struct ShapeOps {
   int m, k, n, ru;  // ru > 0: kernel with the row loop fully unrolled for r == ru
   void (*sweep)(int measure, int mode, int grid, size_t smem, cudaStream_t st, int r, int3 den, unsigned long long seed,
-                unsigned long long lo, unsigned long long hi, int lutn, bool lutfull, Key* bb);
+                unsigned long long lo, unsigned long long hi, int lutn, bool lutfull, bool pack, Key* bb);
   void (*final)(int mode, cudaStream_t st, int r, int3 den, unsigned long long seed, int nblocks, int measure, double inv_den,
                 const Key* bb, plo_orbit_best* out);
   void (*table)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
@@ -404,15 +471,13 @@ template <int M, int K, int N, int RU>
 struct Shape {
   static constexpr size_t scratch_bytes = (size_t)MaxDim2<M, K, N>::value * kThreads * sizeof(int);
   static void sweep(int measure, int mode, int grid, size_t smem, cudaStream_t st, int r, int3 den, unsigned long long seed,
-                    unsigned long long lo, unsigned long long hi, int lutn, bool lutfull, Key* bb) {
-#define PLO_SW(MODE_, MEAS_, LF_) orbit_sweep_kernel<M, K, N, MODE_, MEAS_, RU, LF_><<<grid, kThreads, smem, st>>>(r, den, seed, lo, hi, lutn, bb)
-    if (measure == PLO_MEASURE_NNZ) {
-      if (mode == 0) PLO_SW(0, PLO_MEASURE_NNZ, false); else PLO_SW(1, PLO_MEASURE_NNZ, false);
-    } else if (lutfull) {
-      if (mode == 0) PLO_SW(0, PLO_MEASURE_G2, true); else PLO_SW(1, PLO_MEASURE_G2, true);
-    } else {
-      if (mode == 0) PLO_SW(0, PLO_MEASURE_G2, false); else PLO_SW(1, PLO_MEASURE_G2, false);
-    }
+                    unsigned long long lo, unsigned long long hi, int lutn, bool lutfull, bool pack, Key* bb) {
+#define PLO_SW(MODE_, MEAS_, LF_, PK_) orbit_sweep_kernel<M, K, N, MODE_, MEAS_, RU, LF_, PK_><<<grid, kThreads, smem, st>>>(r, den, seed, lo, hi, lutn, bb)
+#define PLO_SW2(MEAS_, LF_, PK_) do { if (mode == 0) PLO_SW(0, MEAS_, LF_, PK_); else PLO_SW(1, MEAS_, LF_, PK_); } while (0)
+    if (measure == PLO_MEASURE_NNZ) { if (pack) PLO_SW2(PLO_MEASURE_NNZ, false, true); else PLO_SW2(PLO_MEASURE_NNZ, false, false); }
+    else if (lutfull) { if (pack) PLO_SW2(PLO_MEASURE_G2, true, true); else PLO_SW2(PLO_MEASURE_G2, true, false); }
+    else { if (pack) PLO_SW2(PLO_MEASURE_G2, false, true); else PLO_SW2(PLO_MEASURE_G2, false, false); }
+#undef PLO_SW2
 #undef PLO_SW
   }
   static void final(int mode, cudaStream_t st, int r, int3 den, unsigned long long seed, int nblocks, int measure, double inv_den,
@@ -427,13 +492,14 @@ struct Shape {
   }
   static int blocks_per_sm(size_t smem) {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2, RU, false>, kThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2, RU, false, false>, kThreads, smem);
     return nb > 0 ? nb : 1;
   }
   static cudaError_t allow_smem(size_t smem) {
     cudaError_t e = cudaSuccess;
 #define PLO_ALLOW(MODE_, MEAS_, LF_) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(orbit_sweep_kernel<M, K, N, MODE_, MEAS_, RU, LF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(orbit_sweep_kernel<M, K, N, MODE_, MEAS_, RU, LF_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(orbit_sweep_kernel<M, K, N, MODE_, MEAS_, RU, LF_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     PLO_ALLOW(0, PLO_MEASURE_NNZ, false) PLO_ALLOW(1, PLO_MEASURE_NNZ, false) PLO_ALLOW(0, PLO_MEASURE_G2, false)
     PLO_ALLOW(1, PLO_MEASURE_G2, false) PLO_ALLOW(0, PLO_MEASURE_G2, true) PLO_ALLOW(1, PLO_MEASURE_G2, true)
 #undef PLO_ALLOW
@@ -457,7 +523,7 @@ static const ShapeOps* find_shape(int m, int k, int n, int r) {
 // Worst-case magnitude bound of the transformed entries (host guard for the
 // int32 arithmetic): |T^-1| entries <= 2^(s-2), row/column abs sums <= 2^(s-1);
 // a {-1,0,1} factor contributes at most its dimension.
-static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, long long* smax) {
+static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, long long* smax, bool* lanes16) {
   auto maxabs = [](const int32_t* a, size_t cnt) { long long mx = 0; for (size_t i = 0; i < cnt; ++i) { long long v = a[i] < 0 ? -(long long)a[i] : a[i]; if (v > mx) mx = v; } return mx; };
   auto pw = [](int s) { return 1ll << (s > 1 ? s - 1 : 0); };
   const long long bl = maxabs(L, (size_t)r * m * k) * pw(m) * k;  // |U^-T A V| <= max|A| * colsum|U^-1| * colsum|V|
@@ -469,6 +535,7 @@ static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int
   if (br * br * k * n > s) s = br * br * k * n;
   if (bp * bp * m * n > s) s = bp * bp * m * n;
   *smax = s;
+  *lanes16 = bl < 32768 && br < 32768 && bp < 32768;  // two-lane packing stays exact
   return true;
 }
 
@@ -488,7 +555,7 @@ struct plo_orbit_plan {
   Key* d_block_best;
   plo_orbit_best* d_out;
   int grid, lutn;
-  bool lutfull;
+  bool lutfull, pack;
   size_t smem;
 };
 
@@ -544,7 +611,8 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   if ((long long)r * (m * k + k * n + m * n) > kConstInts) { set_error("orbit sweep: L/R/P exceed constant memory"); return PLO_E_SHAPE; }
   if (mode == 0 && plo_orbit_space(m, k, n) == 0) { set_error("orbit sweep: exhaustive space exceeds 64 bits"); return PLO_E_SHAPE; }
   long long smax = 0;
-  if (!magnitude_ok(m, k, n, r, L, R, P, &smax)) { set_error("orbit sweep: int32 magnitude bound exceeded"); return PLO_E_RANGE; }
+  bool lanes16 = false;
+  if (!magnitude_ok(m, k, n, r, L, R, P, &smax, &lanes16)) { set_error("orbit sweep: int32 magnitude bound exceeded"); return PLO_E_RANGE; }
   plo_orbit_plan* pl = new plo_orbit_plan();
   pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->measure = measure; pl->mode = mode; pl->seed = seed;
   pl->inv_den = 1.0 / ((double)denL * (double)denR * (double)denP);
@@ -560,6 +628,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   // sqrt table: covers every reachable row norm^2 when that fits in 32 KB, else the first 4096 values
   pl->lutn = measure == PLO_MEASURE_G2 ? (int)(smax + 1 < 4096 ? smax + 1 : 4096) : 0;
   pl->lutfull = measure == PLO_MEASURE_G2 && smax + 1 <= 4096;
+  pl->pack = lanes16 && getenv("PLO_ORBIT_NOPACK") == nullptr;
   int dmax = m > k ? (m > n ? m : n) : (k > n ? k : n);
   pl->smem = (size_t)pl->lutn * sizeof(double) + (dmax > 2 ? (size_t)dmax * dmax * kThreads * sizeof(int) : 0);
   if (pl->smem > 48 * 1024 && ops->allow_smem(pl->smem) != cudaSuccess) {
@@ -591,7 +660,7 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   cudaStream_t st = (cudaStream_t)stream;
   int rc = orbit_upload(pl, st);
   if (rc) return rc;
-  pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->d_block_best);
+  pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());
   return PLO_OK;
