@@ -224,6 +224,16 @@ int plo_mmchecker(uint64_t modulus, uint64_t seed, int batch, int Lrows, int Lco
                   int Pcols, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
                   const int64_t* Pn, const int64_t* Pd, uint32_t* nnz_nno /* [2], may be NULL */);
 
+/* Straight-line program -> matrix: matrixBuilder  include/plinopt_programs.inl:1459-1608 (with the
+ * parser :618-686 and parenthesisExpand :1615-1679; driver src/SLPchecker.cpp:22-40, rule
+ * data/Makefile:31-32).  Needed to regenerate data/32x32x32_15096_{L,R,P}.sms, which the reference
+ * ships only as .slp (.MISSING_LARGE_BLOBS:1-3).  Two-step: build, then export into caller buffers
+ * (CSR with rational values num/den). */
+typedef struct plo_slp_matrix plo_slp_matrix;
+int plo_slp_build(const char* text, char outchar, plo_slp_matrix** out, int* rows, int* cols, int64_t* nnz);
+int plo_slp_export(const plo_slp_matrix* m, int64_t* ptr, int32_t* col, int64_t* num, int64_t* den);
+void plo_slp_free(plo_slp_matrix* m);
+
 /* include/plinopt_library.h:177-181 */
 void plo_LRP2MM(int Lcols, int Rcols, int Prows, int* m, int* k, int* n);
 

@@ -28,7 +28,7 @@ SYMBOLS = [
     "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
-    "plo_sparsifier", "plo_orbiter", "plo_mmchecker", "plo_LRP2MM",
+    "plo_sparsifier", "plo_orbiter", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
 ]
 
 
@@ -383,3 +383,23 @@ def mmchecker(L, R, P, modulus=0, seed=0, batch=32):
     rc = _check(f(modulus, seed, batch, len(L), len(L[0]), len(R), len(R[0]), len(P), len(P[0]), _ptr(Ln), _ptr(Ld), _ptr(Rn), _ptr(Rd),
                   _ptr(Pn), _ptr(Pd), _ptr(cnt)), allow=(1, 2, 3))
     return rc, (int(cnt[0]), int(cnt[1]))
+
+
+def slp_to_csr(text, outchar="o"):
+    """SLP text -> (rows, cols, ptr, col, num, den): matrixBuilder on the host (no GPU needed)."""
+    h = C.c_void_p()
+    rows, cols, nnz = C.c_int(), C.c_int(), C.c_int64()
+    f = lib().plo_slp_build
+    f.argtypes = [C.c_char_p, C.c_char, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    _check(f(text.encode(), outchar.encode(), C.byref(h), C.byref(rows), C.byref(cols), C.byref(nnz)))
+    ptr = np.zeros(rows.value + 1, dtype=np.int64); col = np.zeros(nnz.value, dtype=np.int32)
+    num = np.zeros(nnz.value, dtype=np.int64); den = np.ones(nnz.value, dtype=np.int64)
+    g = lib().plo_slp_export
+    g.argtypes = [C.c_void_p] * 5
+    try:
+        _check(g(h, _ptr(ptr), _ptr(col), _ptr(num), _ptr(den)))
+    finally:
+        lib().plo_slp_free.argtypes = [C.c_void_p]
+        lib().plo_slp_free.restype = None
+        lib().plo_slp_free(h)
+    return rows.value, cols.value, ptr, col, num, den

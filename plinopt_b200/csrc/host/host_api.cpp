@@ -13,6 +13,7 @@
 
 #include "../plo_device.cuh"
 #include "matrix_io.hpp"
+#include "slp.hpp"
 #include "sparsify_host.hpp"
 
 using namespace plo::host;
@@ -158,6 +159,37 @@ void plo_LRP2MM(int Lcols, int Rcols, int Prows, int* m, int* k, int* n) {
   *m = nn ? (int)((size_t)Prows / nn) : 0;
   *k = nn ? (int)((size_t)Rcols / nn) : 0;
 }
+
+struct plo_slp_matrix_impl { plo::host::SparseRows M; };
+
+int plo_slp_build(const char* text, char outchar, plo_slp_matrix** out, int* rows, int* cols, int64_t* nnz) {
+  if (!text || !out) { plo::set_error("plo_slp_build: bad argument"); return PLO_E_ARG; }
+  try {
+    plo::host::SlpBuilder b;
+    plo_slp_matrix_impl* h = new plo_slp_matrix_impl();
+    h->M = b.build(text, outchar ? outchar : 'o');
+    *out = reinterpret_cast<plo_slp_matrix*>(h);
+    if (rows) *rows = (int)h->M.rows;
+    if (cols) *cols = (int)h->M.cols;
+    if (nnz) *nnz = (int64_t)h->M.nnz();
+    return PLO_OK;
+  } catch (const std::exception& e) {
+    plo::set_error("plo_slp_build: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+int plo_slp_export(const plo_slp_matrix* m, int64_t* ptr, int32_t* col, int64_t* num, int64_t* den) {
+  if (!m || !ptr || !col || !num || !den) { plo::set_error("plo_slp_export: bad argument"); return PLO_E_ARG; }
+  const plo::host::SparseRows& M = reinterpret_cast<const plo_slp_matrix_impl*>(m)->M;
+  int64_t t = 0;
+  ptr[0] = 0;
+  for (size_t i = 0; i < M.rows; ++i) {
+    for (const auto& e : M.r[i]) { col[t] = e.first; num[t] = e.second.num; den[t] = e.second.den; ++t; }
+    ptr[i + 1] = t;
+  }
+  return PLO_OK;
+}
+void plo_slp_free(plo_slp_matrix* m) { delete reinterpret_cast<plo_slp_matrix_impl*>(m); }
 
 int plo_sparsifier(uint64_t q, int rows, int cols, const int64_t* num, const int64_t* den, int blocksize,
                    int maxnumcoeff, int initialElimination, int64_t* cob_num, int64_t* cob_den,

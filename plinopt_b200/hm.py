@@ -106,3 +106,22 @@ def strip_modulus(q):
     while q % 2 == 0 and q > 0:
         q >>= 1
     return 2 if q == 1 else q
+
+
+def load_large_csr(p, path=None):
+    """The regenerated 32x32x32_15096 triple (tools/regen_32x32x32.py) reduced mod p:
+    returns (mkn, r, (L, R, P) CSR tuples) or None when the cache file is absent."""
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "large", "32x32x32_15096.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    out = []
+    for x in "LRP":
+        rows, cols = (int(v) for v in z[f"{x}_shape"])
+        num = z[f"{x}_num"].astype(np.int64) % p
+        den = z[f"{x}_den"].astype(np.int64) % p
+        inv = {int(d): pow(int(d), -1, p) for d in np.unique(den)}
+        val = (num * np.array([inv[int(d)] for d in den], dtype=np.int64)) % p if p < (1 << 31) else np.array([(int(a) * inv[int(d)]) % p for a, d in zip(num, den)], dtype=np.int64)
+        out.append((rows, cols, z[f"{x}_ptr"].astype(np.int64), z[f"{x}_col"].astype(np.int32), val.astype(np.uint32)))
+    return (32, 32, 32), 15096, tuple(out)

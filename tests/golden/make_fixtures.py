@@ -28,6 +28,11 @@ STEMS = [
     "3x4x7_63_rational", "3x4x7_63_rational-ALT", "3x4x7_63_rational-CoB",
 ]
 SINGLES = ["cyclic"]
+# straight-line programs the reference ships next to the .sms they were generated from (data/Makefile:31-32):
+# golden pairs for the SLP -> matrix builder
+SLP_OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "slp_programs.json")
+SLP_STEMS = ["2x2x2_7_Winograd", "3x3x3_23_58", "3x4x7_63_rational", "3x4x7_63_rational-ALT", "3x4x7_63_rational-CoB",
+             "4x4x4_48_rational", "4x4x4_48_rational-CoB", "4x4x4_48_accurate", "4x4x4_49_156"]
 
 
 def read_sms(path):
@@ -67,6 +72,10 @@ def main():
     with open(OUT, "w") as f:
         json.dump(out, f, separators=(",", ":"), sort_keys=True)
     print("wrote", OUT, len(out), "matrices", os.path.getsize(OUT), "bytes")
+    slp = {f"{stem}_{x}": open(os.path.join(REF, "data", f"{stem}_{x}.slp")).read() for stem in SLP_STEMS for x in "LRP"}
+    with open(SLP_OUT, "w") as f:
+        json.dump(slp, f, separators=(",", ":"), sort_keys=True)
+    print("wrote", SLP_OUT, len(slp), "programs", os.path.getsize(SLP_OUT), "bytes")
 
 
 if __name__ == "__main__":
