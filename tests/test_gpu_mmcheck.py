@@ -67,3 +67,25 @@ def test_random_dense_triple_linearity(capi):
     pc2 = Pc[3].copy(); pc2[0], pc2[k] = pc2[k], pc2[0]
     v, ok = capi.mmcheck_batch(P31, (m, k, n), r, Lc, Rc, (Pc[0], Pc[1], Pc[2], pc2, Pc[4]), seed=5, batch=100)
     assert v == 1 and not ok.any()
+
+
+def test_regenerated_32x32x32_15096_passes_and_corruption_is_caught(capi):
+    """BASELINE config 5: the 32x32x32_15096 triple (regenerated from the reference's .slp)
+    is a correct MM algorithm for every Philox sample mod 2^31-1; flipping one residue of P breaks every sample
+    whose evaluation touches it (plinopt_library.inl:472-558)."""
+    big = hm.load_large_csr(P31)
+    assert big is not None, "tests/golden/large/32x32x32_15096.npz missing"
+    mkn, r, (L, R, P) = big
+    for B in (1, 33, 256):
+        v, ok = capi.mmcheck_batch(P31, mkn, r, L, R, P, seed=7, batch=B)
+        assert v == 0 and ok.sum() == B
+    val = P[4].copy(); val[12345] = (int(val[12345]) + 1) % P31
+    v, ok = capi.mmcheck_batch(P31, mkn, r, L, R, (P[0], P[1], P[2], P[3], val), seed=7, batch=64)
+    assert v == 1 and ok.sum() == 0
+    # given samples: agree with a numpy evaluation mod a 20-bit prime
+    p = 1000003
+    _, _, (L2, R2, P2) = hm.load_large_csr(p)
+    rng = np.random.default_rng(5)
+    ua = rng.integers(0, p, (3, 1024)).astype(np.uint32); ub = rng.integers(0, p, (3, 1024)).astype(np.uint32)
+    v, ok = capi.mmcheck_batch(p, mkn, r, L2, R2, P2, batch=3, ua=ua, ub=ub)
+    assert v == 0 and ok.all()
