@@ -4,17 +4,50 @@
 // of independent random evaluations (the reference does one per call):
 //   va = L.ua, vb = R.ub (:504-505), vc = va o vb (:507), wc = P.vc (:509),
 //   compare with the direct product reshape(ua).reshape(ub)  (:513-528).
-// Layout: sample-minor vectors X[j][b] so that the 32 lanes of a warp (32
-// samples of one matrix row) read one coalesced 128 B line per CSR entry while
-// (col,val) are warp-uniform.  Products accumulate exactly in 96 bits
-// (mad.lo.cc / madc.hi.cc / addc) and are reduced mod p once per output.
+//
+// Design (B200): the three sparse products are one warp-specialised kernel,
+// mm_slab_spmm_kernel.  Samples are grouped by 32 (lane = sample) and every
+// vector is stored group-major  V[g][j][lane], so the slice of X that a sparse
+// product needs for one sample group and one slab of 1024 columns is ONE
+// contiguous 128 KB block: it is brought into shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier) and stays there while the CTA streams matrix rows
+// against it.  The matrix itself is pre-cut on the host into self-contained
+// "chunk blobs" (row offsets + (column byte offset, value) pairs of a run of
+// rows inside one slab, ~equal non-zero counts); a producer warp streams the
+// blobs through a 4-stage shared-memory ring with bulk copies, 16 consumer
+// warps take rows from the current blob through a shared counter (rows are
+// 16..1024 entries long) and do, per entry, one broadcast LDS.128 per two
+// entries + one LDS + one IMAD.WIDE.U32 with carry-out (+ half an IADD3.X):
+// exact 96-bit accumulation, one Barrett reduction mod p per output.
+// Bound: shared-memory bandwidth (one 128 B wavefront per multiply-add per
+// warp) -- DESIGN.md section 5.3.
+#include <algorithm>
 #include <vector>
 
 #include "plo_device.cuh"
 
 namespace plo {
 
-constexpr int kMmThreads = 128;
+constexpr int kSlabCols = 1024;                         // columns of X resident per CTA
+constexpr int kSlabBytes = kSlabCols * 32 * 4;          // 128 KB
+constexpr int kStages = 4;                              // blob ring depth
+constexpr int kChunkEnt = 2560;                         // max padded entries per blob
+constexpr int kChunkRows = 255;                         // max rows per blob
+constexpr int kHdrBytes = (kChunkRows + 1) * 4;         // 1 KB of row offsets
+constexpr int kStageBytes = kHdrBytes + kChunkEnt * 8;  // 21.5 KB
+constexpr int kConsumerWarps = 24;
+constexpr int kSpThreads = (kConsumerWarps + 1) * 32;   // + one producer warp
+constexpr int kZeroColBytes = 128;                      // slab column 1024: 32 zero words (padding target of the grouped format)
+constexpr int kRingBase = kSlabBytes + kZeroColBytes;
+constexpr int kSpSmem = kRingBase + kStages * kStageBytes;
+constexpr int kGroupedMinAvg = 6;                       // value-grouped format when a (row, value) group averages >= this many entries
+
+struct ChunkDesc {
+  int slab, row0, nrows, bytes;  // blob = [nrows+1 offsets, padded to 16 B][stream]; stream = (colbyte, val) pairs (plain format)
+                                 // or, per (row, value) group, {val, nwords} + nwords x 4 columns, two per 32-bit word (grouped format)
+  unsigned long long off;        // byte offset of the blob
+  unsigned long long pad_;
+};
 
 struct Acc96 {
   unsigned int a0, a1, a2;
@@ -27,127 +60,298 @@ __device__ __forceinline__ void mac96(Acc96& a, unsigned int x, unsigned int y) 
       : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2)
       : "r"(x), "r"(y));
 }
-__device__ __forceinline__ unsigned int reduce96(const Acc96& a, unsigned int p) {
-  unsigned long long r = a.a2 % p;
-  r = ((r << 32) | a.a1) % p;
-  r = ((r << 32) | a.a0) % p;
+__device__ __forceinline__ void add96(Acc96& a, const Acc96& b) {
+  asm volatile(
+      "add.cc.u32 %0, %0, %3;\n\t"
+      "addc.cc.u32 %1, %1, %4;\n\t"
+      "addc.u32 %2, %2, %5;"
+      : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2)
+      : "r"(b.a0), "r"(b.a1), "r"(b.a2));
+}
+// x mod p for any 64-bit x: Barrett with M = floor((2^64-1)/p); q is at most 2 short.
+__device__ __forceinline__ unsigned int barrett64(unsigned long long x, unsigned int p, unsigned long long M) {
+  const unsigned long long q = __umul64hi(x, M);
+  unsigned long long r = x - q * p;
+  if (r >= p) r -= p;
+  if (r >= p) r -= p;
   return (unsigned int)r;
 }
-
-// ua[j][b], ub[j][b] = Philox words mod p; counter = (sample, j / 4, which), key = seed.
-__global__ void mm_gen_kernel(unsigned int p, unsigned long long seed, unsigned long long first_sample, int batch, int len_a,
-                              int len_b, unsigned int* __restrict__ ua, unsigned int* __restrict__ ub) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
-  const unsigned long long s = first_sample + (unsigned long long)b;
-  for (int which = 0; which < 2; ++which) {
-    const int len = which ? len_b : len_a;
-    unsigned int* dst = which ? ub : ua;
-    for (int j0 = 0; j0 < len; j0 += 4) {
-      uint32_t w[4];
-      philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)(j0 >> 2), (uint32_t)which, (uint32_t)seed, (uint32_t)(seed >> 32), w);
-      for (int t = 0; t < 4 && j0 + t < len; ++t) dst[(size_t)(j0 + t) * batch + b] = w[t] % p;
-    }
-  }
+__device__ __forceinline__ unsigned int reduce96(const Acc96& a, unsigned int p, unsigned long long M) {
+  const unsigned int t = barrett64(((unsigned long long)a.a2 << 32) | a.a1, p, M);
+  return barrett64(((unsigned long long)t << 32) | a.a0, p, M);
 }
 
-// [batch][len] (caller layout) -> [len][batch], reduced mod p
+// ---- mbarrier / TMA bulk copy (PTX ISA 8.x, sm_90+) -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ unsigned int lds_u32(uint32_t addr) {
+  unsigned int v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ua[g][j][lane], ub[g][j][lane] = Philox words mod p; counter = (sample, j / 4, which), key = seed.
+// One thread per (sample, quad of coordinates); lanes = samples, so the stores are coalesced.
+__global__ void mm_gen_kernel(unsigned int p, unsigned long long seed, unsigned long long first_sample, int batch, int len_a,
+                              int len_b, unsigned int* __restrict__ ua, unsigned int* __restrict__ ub) {
+  const int qa = (len_a + 3) >> 2, qb = (len_b + 3) >> 2;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)batch * (qa + qb)) return;
+  const int b = (int)(e % batch);
+  int q = (int)(e / batch);
+  const int which = q >= qa;
+  if (which) q -= qa;
+  const int len = which ? len_b : len_a;
+  const unsigned long long s = first_sample + (unsigned long long)b;
+  uint32_t w[4];
+  philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)q, (uint32_t)which, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  unsigned int* dst = (which ? ub : ua) + ((size_t)(b >> 5) * len + (size_t)q * 4) * 32 + (b & 31);
+  for (int t = 0; t < 4 && q * 4 + t < len; ++t) dst[(size_t)t * 32] = w[t] % p;
+}
+
+// [batch][len] (caller layout) -> [g][len][lane], reduced mod p
 __global__ void mm_transpose_kernel(unsigned int p, int batch, int len, const unsigned int* __restrict__ src, unsigned int* __restrict__ dst) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (size_t)batch * len) return;
-  const int b = (int)(e % batch), j = (int)(e / batch);
-  dst[e] = src[(size_t)b * len + j] % p;
+  const int j = (int)(e % len), b = (int)(e / len);
+  dst[((size_t)(b >> 5) * len + j) * 32 + (b & 31)] = src[e] % p;
 }
 
-// Partial sparse product: out[part][row][b] = sum over the part-th slice of row's entries of val * X[col][b]  (mod p)
-__global__ void __launch_bounds__(kMmThreads) mm_spmm_kernel(unsigned int p, int rows, int batch, int parts, const long long* __restrict__ ptr,
-                                                             const int* __restrict__ col, const unsigned int* __restrict__ val,
-                                                             const unsigned int* __restrict__ X, unsigned int* __restrict__ out) {
-  const int groups = (batch + 31) >> 5;
-  const long long warp = ((long long)blockIdx.x * kMmThreads + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)rows * parts * groups;
-  if (warp >= total) return;
-  const int g = (int)(warp % groups);
-  const long long rp = warp / groups;
-  const int part = (int)(rp % parts);
-  const int row = (int)(rp / parts);
-  const int b = g * 32 + lane;
-  const long long beg = ptr[row], end = ptr[row + 1];
-  const long long len = end - beg, chunk = (len + parts - 1) / parts;
-  const long long lo = beg + chunk * part, hi = (lo + chunk < end) ? lo + chunk : end;
-  Acc96 acc;
-  acc.a0 = acc.a1 = acc.a2 = 0;
-  if (b < batch) {
-    long long t = lo;
-    for (; t + 4 <= hi; t += 4) {  // 4 independent loads in flight
-      const int c0 = col[t], c1 = col[t + 1], c2 = col[t + 2], c3 = col[t + 3];
-      const unsigned int v0 = val[t], v1 = val[t + 1], v2 = val[t + 2], v3 = val[t + 3];
-      const unsigned int x0 = X[(size_t)c0 * batch + b], x1 = X[(size_t)c1 * batch + b], x2 = X[(size_t)c2 * batch + b], x3 = X[(size_t)c3 * batch + b];
-      mac96(acc, v0, x0); mac96(acc, v1, x1); mac96(acc, v2, x2); mac96(acc, v3, x3);
+struct SpmmArgs {
+  unsigned int p;
+  unsigned long long M;  // floor((2^64-1)/p)
+  int rows, xlen, groups, nchunks;
+  const ChunkDesc* chunk;
+  const unsigned char* blob;
+  const unsigned int* X;    // [groups][xlen][32]
+  unsigned int* out;        // [nslabs][groups][rows][32]
+  const unsigned int* mul;  // optional [groups][rows][32]: out = (A X) o mul  (fused Hadamard step, single-slab matrices)
+};
+
+__device__ __forceinline__ void addwide(unsigned long long& s, unsigned int x, unsigned int one) {
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s) : "r"(x), "r"(one));  // 64-bit accumulate on the fma pipe
+}
+
+// Grouped format: a 32-bit word packs two slab columns, one in bits [10:0], one in bits [31:21].
+// Shared-memory address of this lane's X word = column * 128 + xl:
+//   low field : (w & 0x7ff) * 128 + xl            (LOP3 + IMAD)
+//   high field: hi32(w * 2^18) + xl = (w >> 14) + xl, clean because bits [20:11] of w are zero  (one IMAD.HI)
+__device__ __forceinline__ uint32_t col_lo_addr(unsigned int w, uint32_t xl) {
+  uint32_t t, a;
+  asm volatile("and.b32 %0, %1, 0x7ff;" : "=r"(t) : "r"(w));
+  asm volatile("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(t), "r"(xl));
+  return a;
+}
+__device__ __forceinline__ uint32_t col_hi_addr(unsigned int w, uint32_t xl) {
+  uint32_t a;
+  asm volatile("mad.hi.u32 %0, %1, 262144, %2;" : "=r"(a) : "r"(w), "r"(xl));
+  return a;
+}
+
+template <bool GROUPED>
+__global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full[kStages], empty[kStages], slabbar;
+  __shared__ int cnt[kStages];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long T = (long long)a.groups * a.nchunks;
+  const long long i0 = (long long)blockIdx.x * T / gridDim.x, i1 = (long long)(blockIdx.x + 1) * T / gridDim.x;
+  const int nitems = (int)(i1 - i0);
+  if (tid < 32) reinterpret_cast<unsigned int*>(smem + kSlabBytes)[tid] = 0u;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    mbar_init(&slabbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int pg = -1, ps = -1;
+  if (warp == kConsumerWarps) {
+    // ---- producer: one thread feeds the slab and the blob ring ----
+    if (lane != 0) return;
+    for (int k = 0; k < nitems; ++k) {
+      const long long i = i0 + k;
+      const int g = (int)(i / a.nchunks), c = (int)(i - (long long)g * a.nchunks);
+      const ChunkDesc ch = a.chunk[c];
+      const int stage = k & (kStages - 1);
+      if (g != pg || ch.slab != ps) {
+        // every consumer must be done with the old slab: drain the ring
+        for (int j = k > kStages ? k - kStages : 0; j < k; ++j) mbar_wait(&empty[j & (kStages - 1)], (j / kStages) & 1);
+        const int ncols = min(kSlabCols, a.xlen - ch.slab * kSlabCols);
+        const unsigned quarter = (unsigned)ncols * 32u;
+        const unsigned char* src = (const unsigned char*)(a.X + ((size_t)g * a.xlen + (size_t)ch.slab * kSlabCols) * 32);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&slabbar, quarter * 4u);
+        for (int q = 0; q < 4; ++q) bulk_g2s(smem + q * quarter, src + (size_t)q * quarter, quarter, &slabbar);
+        pg = g; ps = ch.slab;
+      } else if (k >= kStages) {
+        mbar_wait(&empty[stage], ((k / kStages) - 1) & 1);
+      }
+      cnt[stage] = 0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&full[stage], (unsigned)ch.bytes);
+      bulk_g2s(smem + kRingBase + stage * kStageBytes, a.blob + ch.off, (unsigned)ch.bytes, &full[stage]);
     }
-    for (; t < hi; ++t) mac96(acc, val[t], X[(size_t)col[t] * batch + b]);
-    out[((size_t)part * rows + row) * batch + b] = reduce96(acc, p);
+    return;
+  }
+  // ---- consumers: lane = sample of the group, warp takes rows of the current blob ----
+  const uint32_t xl = smem_u32(smem) + lane * 4;  // this lane's word of slab column 0
+  unsigned int one;
+  asm volatile("mov.u32 %0, 1;" : "=r"(one));
+  unsigned slabphase = 0;
+  for (int k = 0; k < nitems; ++k) {
+    const long long i = i0 + k;
+    const int g = (int)(i / a.nchunks), c = (int)(i - (long long)g * a.nchunks);
+    const int4 ch = *reinterpret_cast<const int4*>(a.chunk + c);  // slab, row0, nrows, bytes
+    const int stage = k & (kStages - 1);
+    if (g != pg || ch.x != ps) { mbar_wait(&slabbar, slabphase); slabphase ^= 1; pg = g; ps = ch.x; }
+    mbar_wait(&full[stage], (k / kStages) & 1);
+    const unsigned char* sb = smem + kRingBase + stage * kStageBytes;
+    const unsigned int* hdr = reinterpret_cast<const unsigned int*>(sb);
+    const uint4* ent = reinterpret_cast<const uint4*>(sb + (((ch.z + 1) * 4 + 15) & ~15));
+    const size_t obase = (((size_t)ch.x * a.groups + g) * a.rows + ch.y) * 32 + lane;
+    unsigned int* outp = a.out + obase;
+    const unsigned int* mulp = a.mul ? a.mul + obase : nullptr;
+    int cur = 0;
+    if (lane == 0) cur = atomicAdd(&cnt[stage], 1);
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    while (cur < ch.z) {
+      int nxt = 0;
+      if (lane == 0) nxt = atomicAdd(&cnt[stage], 1);
+      const unsigned o0 = hdr[cur], o1 = hdr[cur + 1];
+      Acc96 A, B;
+      A.a0 = A.a1 = A.a2 = 0;
+      B.a0 = B.a1 = B.a2 = 0;
+      if (GROUPED) {
+        // stream of 8-byte words: {val, nwords} then nwords words of 4 columns; out += val * sum_cols X[col]
+        const uint2* st = reinterpret_cast<const uint2*>(ent);
+        unsigned w = o0;
+        while (w < o1) {
+          const uint2 h = st[w];
+          const uint2* cw = st + w + 1;
+          unsigned long long s0 = 0, s1 = 0;
+#pragma unroll 2
+          for (unsigned j = 0; j < h.y; ++j) {
+            const uint2 c = cw[j];
+            const unsigned x0 = lds_u32(col_lo_addr(c.x, xl));
+            const unsigned x1 = lds_u32(col_hi_addr(c.x, xl));
+            const unsigned x2 = lds_u32(col_lo_addr(c.y, xl));
+            const unsigned x3 = lds_u32(col_hi_addr(c.y, xl));
+            addwide(s0, x0, one);
+            addwide(s1, x1, one);
+            addwide(s0, x2, one);
+            addwide(s1, x3, one);
+          }
+          s0 += s1;  // < 2^45: at most 2^13 terms below 2^32
+          mac96(A, h.x, (unsigned)s0);
+          asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(B.a1), "+r"(B.a2) : "r"(h.x), "r"((unsigned)(s0 >> 32)));
+          w += h.y + 1;
+        }
+        B.a0 = 0;
+      } else {
+        const uint4* e = ent + (o0 >> 1);
+        const int n = (int)((o1 - o0) >> 1);  // uint4 = 2 entries; rows are padded to 4 entries
+#pragma unroll 2
+        for (int t = 0; t < n; t += 2) {
+          const uint4 q0 = e[t], q1 = e[t + 1];
+          const unsigned x0 = lds_u32(xl + q0.x);
+          const unsigned x1 = lds_u32(xl + q0.z);
+          const unsigned x2 = lds_u32(xl + q1.x);
+          const unsigned x3 = lds_u32(xl + q1.z);
+          mac96(A, q0.y, x0);
+          mac96(B, q0.w, x1);
+          mac96(A, q1.y, x2);
+          mac96(B, q1.w, x3);
+        }
+      }
+      add96(A, B);
+      unsigned int res = reduce96(A, a.p, a.M);
+      if (mulp) res = barrett64((unsigned long long)res * mulp[(size_t)cur * 32], a.p, a.M);
+      outp[(size_t)cur * 32] = res;
+      cur = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
   }
 }
 
-// vc[i][b] = (sum_parts va) * (sum_parts vb) mod p
-__global__ void mm_hadamard_kernel(unsigned int p, int r, int batch, int parts, const unsigned int* __restrict__ va,
+// vc[e] = (sum_parts va) * (sum_parts vb) mod p   (all in the group-major layout)
+__global__ void mm_hadamard_kernel(unsigned int p, unsigned long long M, size_t count, int partsA, int partsB, const unsigned int* __restrict__ va,
                                    const unsigned int* __restrict__ vb, unsigned int* __restrict__ vc) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (size_t)r * batch) return;
-  unsigned long long a = 0, b = 0;
-  for (int q = 0; q < parts; ++q) { a += va[(size_t)q * r * batch + e]; b += vb[(size_t)q * r * batch + e]; }
-  vc[e] = (unsigned int)(((a % p) * (b % p)) % p);
+  if (e >= count) return;
+  unsigned long long x = 0, y = 0;
+  for (int q = 0; q < partsA; ++q) x += va[(size_t)q * count + e];
+  for (int q = 0; q < partsB; ++q) y += vb[(size_t)q * count + e];
+  vc[e] = barrett64((unsigned long long)barrett64(x, p, M) * barrett64(y, p, M), p, M);
 }
 
-// ok[b] &= (sum_parts wc[o][b] == sum_t ua[i*k+t][b] * ub[t*n+j][b])  for o = i*n + j
-__global__ void mm_verify_kernel(unsigned int p, int m, int k, int n, int batch, int parts, const unsigned int* __restrict__ wc,
-                                 const unsigned int* __restrict__ ua, const unsigned int* __restrict__ ub, unsigned int* __restrict__ bad) {
+// bad[b] |= (sum_parts wc[g][o][lane] != sum_t ua[g][i*k+t][lane] * ub[g][t*n+j][lane])  for o = i*n + j, b = 32 g + lane
+__global__ void mm_verify_kernel(unsigned int p, unsigned long long M, int m, int k, int n, int batch, int groups, int parts,
+                                 const unsigned int* __restrict__ wc, const unsigned int* __restrict__ ua, const unsigned int* __restrict__ ub,
+                                 unsigned int* __restrict__ bad) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (size_t)m * n * batch) return;
-  const int b = (int)(e % batch);
-  const int o = (int)(e / batch), i = o / n, j = o % n;
+  const int mn = m * n;
+  if (e >= (size_t)groups * mn * 32) return;
+  const int lane = (int)(e & 31);
+  const int o = (int)((e >> 5) % mn), g = (int)((e >> 5) / mn), i = o / n, j = o % n;
+  const int b = g * 32 + lane;
+  if (b >= batch) return;
   unsigned long long w = 0;
-  for (int q = 0; q < parts; ++q) w += wc[(size_t)q * m * n * batch + e];
+  for (int q = 0; q < parts; ++q) w += wc[(size_t)q * groups * mn * 32 + e];
   Acc96 acc;
   acc.a0 = acc.a1 = acc.a2 = 0;
-  for (int t = 0; t < k; ++t) mac96(acc, ua[(size_t)(i * k + t) * batch + b], ub[(size_t)(t * n + j) * batch + b]);
-  if ((unsigned int)(w % p) != reduce96(acc, p)) atomicOr(bad + b, 1u);
+  const unsigned int* pa = ua + ((size_t)g * m * k + (size_t)i * k) * 32 + lane;
+  const unsigned int* pb = ub + ((size_t)g * k * n + j) * 32 + lane;
+  for (int t = 0; t < k; ++t) mac96(acc, pa[(size_t)t * 32], pb[(size_t)t * n * 32]);
+  if (barrett64(w, p, M) != reduce96(acc, p, M)) atomicOr(bad + b, 1u);
 }
 
 }  // namespace plo
 
 using namespace plo;
 
-struct DevCsr {
-  int rows, cols;
+// Device form of one sparse matrix: chunk blobs + chunk table (see the header comment).
+struct DevSlabCsr {
+  int rows, cols, nslabs, nchunks;
+  bool grouped;
   long long nnz;
-  long long* ptr;
-  int* col;
-  unsigned int* val;
+  ChunkDesc* chunk;
+  unsigned char* blob;
 };
 
 struct plo_mmcheck_plan {
   uint32_t p;
-  int m, k, n, r, batch;
-  DevCsr L, R, P;
-  int partsLR, partsP;
+  unsigned long long M;
+  int m, k, n, r, batch, groups, grid_cap;
+  DevSlabCsr L, R, P;
   unsigned int *ua, *ub, *va, *vb, *vc, *wc, *bad, *stage;
 };
-
-static int upload_csr(const plo_csr* h, DevCsr* d) {
-  d->rows = h->rows; d->cols = h->cols; d->nnz = h->ptr[h->rows];
-  d->ptr = nullptr; d->col = nullptr; d->val = nullptr;
-  PLO_CUDA(cudaMalloc(&d->ptr, sizeof(long long) * (h->rows + 1)));
-  PLO_CUDA(cudaMalloc(&d->col, sizeof(int) * (d->nnz ? d->nnz : 1)));
-  PLO_CUDA(cudaMalloc(&d->val, sizeof(unsigned int) * (d->nnz ? d->nnz : 1)));
-  PLO_CUDA(cudaMemcpy(d->ptr, h->ptr, sizeof(long long) * (h->rows + 1), cudaMemcpyHostToDevice));
-  PLO_CUDA(cudaMemcpy(d->col, h->col, sizeof(int) * d->nnz, cudaMemcpyHostToDevice));
-  PLO_CUDA(cudaMemcpy(d->val, h->val, sizeof(unsigned int) * d->nnz, cudaMemcpyHostToDevice));
-  return PLO_OK;
-}
-static void free_csr(DevCsr* d) { cudaFree(d->ptr); cudaFree(d->col); cudaFree(d->val); }
 
 static bool csr_valid(const plo_csr* c, uint32_t p) {
   if (!c || !c->ptr || c->rows < 1 || c->cols < 1 || c->ptr[0] != 0) return false;
@@ -158,21 +362,120 @@ static bool csr_valid(const plo_csr* c, uint32_t p) {
   return true;
 }
 
-static int pick_parts(const DevCsr& A, int batch) {
-  // enough warps to fill the machine: rows * parts * ceil(batch/32) >= ~8 warps per SM-quadrant slot
-  const long long groups = (batch + 31) / 32;
-  const long long want = (long long)sm_count() * 32;
-  long long parts = 1;
-  const long long avg = A.rows ? A.nnz / A.rows : 0;
-  while (A.rows * parts * groups < want && avg / (parts * 2) >= 32 && parts < 64) parts *= 2;
-  return (int)parts;
+// Cuts the CSR into slabs of kSlabCols columns and, inside a slab, into runs of rows of about equal
+// cost; serialises every run as a blob and uploads blobs + table.  Format: value-grouped when the
+// matrix has few distinct values per row (HM matrices do: 25-31 distinct values in 32x32x32_15096),
+// plain (column, value) pairs otherwise.
+static int build_slab_csr(const plo_csr* h, int groups, DevSlabCsr* d) {
+  d->rows = h->rows; d->cols = h->cols; d->nnz = h->ptr[h->rows];
+  d->nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
+  d->chunk = nullptr; d->blob = nullptr; d->nchunks = 0; d->grouped = false;
+  const int rows = h->rows, nslabs = d->nslabs;
+  // entries bucketed by (slab, row), each bucket sorted by (value, column)
+  std::vector<long long> start((size_t)nslabs * rows + 1, 0);
+  for (int i = 0; i < rows; ++i)
+    for (long long t = h->ptr[i]; t < h->ptr[i + 1]; ++t) ++start[(size_t)(h->col[t] / kSlabCols) * rows + i + 1];
+  for (size_t q = 1; q < start.size(); ++q) start[q] += start[q - 1];
+  std::vector<uint2> sorted((size_t)d->nnz);  // (local column, value)
+  {
+    std::vector<long long> fill(start.begin(), start.end() - 1);
+    for (int i = 0; i < rows; ++i)
+      for (long long t = h->ptr[i]; t < h->ptr[i + 1]; ++t) {
+        const int s = h->col[t] / kSlabCols;
+        sorted[(size_t)fill[(size_t)s * rows + i]++] = make_uint2((unsigned)(h->col[t] - s * kSlabCols), h->val[t]);
+      }
+  }
+  long long ngroups = 0;
+  for (size_t q = 0; q + 1 < start.size(); ++q) {
+    std::sort(sorted.begin() + start[q], sorted.begin() + start[q + 1], [](const uint2& x, const uint2& y) { return x.y != y.y ? x.y < y.y : x.x < y.x; });
+    for (long long t = start[q]; t < start[q + 1]; ++t) ngroups += (t == start[q] || sorted[(size_t)t].y != sorted[(size_t)t - 1].y);
+  }
+  const bool grouped = ngroups > 0 && d->nnz >= (long long)kGroupedMinAvg * ngroups;
+  d->grouped = grouped;
+  // per bucket: stream length in 8-byte words and cost in multiply-add slots
+  std::vector<unsigned> words(start.size() - 1), cost(start.size() - 1);
+  long long total_cost = 0;
+  for (size_t q = 0; q + 1 < start.size(); ++q) {
+    long long w = 0, c = 0;
+    if (grouped) {
+      long long t = start[q];
+      while (t < start[q + 1]) {
+        long long u = t;
+        while (u < start[q + 1] && sorted[(size_t)u].y == sorted[(size_t)t].y) ++u;
+        const long long nw = (u - t + 3) / 4;
+        w += 1 + nw; c += 4 * nw + 4;
+        t = u;
+      }
+    } else {
+      w = (start[q + 1] - start[q] + 3) & ~3ll; c = w;
+    }
+    if (w > kChunkEnt - 1) { set_error("mmcheck: a row has too many entries inside one %d-column slab (duplicate columns?)", kSlabCols); return PLO_E_ARG; }
+    words[q] = (unsigned)w; cost[q] = (unsigned)c; total_cost += c;
+  }
+  long long target = total_cost * groups / ((long long)sm_count() * 16);
+  if (target < 64) target = 64;
+  if (target > 4 * kChunkEnt) target = 4 * kChunkEnt;
+  std::vector<ChunkDesc> table;
+  std::vector<unsigned char> blob;
+  for (int s = 0; s < nslabs; ++s) {
+    int row = 0;
+    while (row < rows) {
+      int nrows = 0;
+      long long w = 0, c = 0;
+      while (row + nrows < rows && nrows < kChunkRows) {
+        const size_t q = (size_t)s * rows + row + nrows;
+        if (nrows > 0 && (c + cost[q] > target || w + words[q] > kChunkEnt - 1)) break;
+        w += words[q]; c += cost[q]; ++nrows;
+      }
+      const size_t hdr = (((size_t)nrows + 1) * 4 + 15) & ~(size_t)15;
+      ChunkDesc ch;
+      ch.slab = s; ch.row0 = row; ch.nrows = nrows; ch.bytes = (int)((hdr + (size_t)w * 8 + 15) & ~(size_t)15);  // bulk copies move multiples of 16 B
+      ch.off = blob.size(); ch.pad_ = 0;
+      blob.resize(blob.size() + (size_t)ch.bytes, 0);
+      unsigned int* ho = reinterpret_cast<unsigned int*>(blob.data() + ch.off);
+      uint2* eo = reinterpret_cast<uint2*>(blob.data() + ch.off + hdr);
+      unsigned o = 0;
+      for (int qq = 0; qq < nrows; ++qq) {
+        ho[qq] = o;
+        const size_t q = (size_t)s * rows + row + qq;
+        if (grouped) {
+          long long t = start[q];
+          while (t < start[q + 1]) {
+            long long u = t;
+            while (u < start[q + 1] && sorted[(size_t)u].y == sorted[(size_t)t].y) ++u;
+            const unsigned nw = (unsigned)((u - t + 3) / 4);
+            eo[o++] = make_uint2(sorted[(size_t)t].y, nw);
+            for (unsigned j = 0; j < nw; ++j) {
+              unsigned c4[4];
+              for (int z = 0; z < 4; ++z) c4[z] = t + 4 * j + z < u ? sorted[(size_t)(t + 4 * j + z)].x : (unsigned)kSlabCols;  // padding -> zero column
+              eo[o++] = make_uint2(c4[0] | (c4[1] << 21), c4[2] | (c4[3] << 21));
+            }
+            t = u;
+          }
+        } else {
+          for (long long t = start[q]; t < start[q + 1]; ++t) eo[o++] = make_uint2(sorted[(size_t)t].x * 128u, sorted[(size_t)t].y);
+          while (o & 3) eo[o++] = make_uint2(0u, 0u);  // padding: 0 * X[slab column 0]
+        }
+      }
+      ho[nrows] = o;
+      table.push_back(ch);
+      row += nrows;
+    }
+  }
+  d->nchunks = (int)table.size();
+  PLO_CUDA(cudaMalloc(&d->chunk, sizeof(ChunkDesc) * table.size()));
+  PLO_CUDA(cudaMalloc(&d->blob, blob.size() ? blob.size() : 16));
+  PLO_CUDA(cudaMemcpy(d->chunk, table.data(), sizeof(ChunkDesc) * table.size(), cudaMemcpyHostToDevice));
+  PLO_CUDA(cudaMemcpy(d->blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  return PLO_OK;
 }
+static void free_slab_csr(DevSlabCsr* d) { cudaFree(d->chunk); cudaFree(d->blob); }
 
 extern "C" {
 
 void plo_mmcheck_plan_destroy(plo_mmcheck_plan* pl) {
   if (!pl) return;
-  free_csr(&pl->L); free_csr(&pl->R); free_csr(&pl->P);
+  free_slab_csr(&pl->L); free_slab_csr(&pl->R); free_slab_csr(&pl->P);
   cudaFree(pl->ua); cudaFree(pl->ub); cudaFree(pl->va); cudaFree(pl->vb); cudaFree(pl->vc); cudaFree(pl->wc); cudaFree(pl->bad); cudaFree(pl->stage);
   delete pl;
 }
@@ -187,37 +490,54 @@ int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, i
   if (L->cols != m * k || R->cols != k * n || P->rows != m * n) { set_error("mmcheck: outer dimension mismatch"); return 3; }  // library.inl:487-495
   int rc = check_device();
   if (rc) return rc;
+  PLO_CUDA(cudaFuncSetAttribute(mm_slab_spmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
+  PLO_CUDA(cudaFuncSetAttribute(mm_slab_spmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
   plo_mmcheck_plan* pl = new plo_mmcheck_plan();
   memset(pl, 0, sizeof(*pl));
-  pl->p = p; pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->batch = batch;
-  rc = upload_csr(L, &pl->L);
-  if (!rc) rc = upload_csr(R, &pl->R);
-  if (!rc) rc = upload_csr(P, &pl->P);
+  pl->p = p; pl->M = ~0ull / p; pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->batch = batch;
+  pl->groups = (batch + 31) / 32;
+  pl->grid_cap = sm_count();
+  rc = build_slab_csr(L, pl->groups, &pl->L);
+  if (!rc) rc = build_slab_csr(R, pl->groups, &pl->R);
+  if (!rc) rc = build_slab_csr(P, pl->groups, &pl->P);
   if (rc) { plo_mmcheck_plan_destroy(pl); return rc; }
-  pl->partsLR = pick_parts(pl->L, batch);
-  { int q = pick_parts(pl->R, batch); if (q > pl->partsLR) pl->partsLR = q; }
-  pl->partsP = pick_parts(pl->P, batch);
-  const size_t B = (size_t)batch;
-  const size_t stage = B * (size_t)(m * k > k * n ? m * k : k * n);
-  bool ok = cudaMalloc(&pl->ua, 4 * B * m * k) == cudaSuccess && cudaMalloc(&pl->ub, 4 * B * k * n) == cudaSuccess &&
-            cudaMalloc(&pl->va, 4 * B * r * pl->partsLR) == cudaSuccess && cudaMalloc(&pl->vb, 4 * B * r * pl->partsLR) == cudaSuccess &&
-            cudaMalloc(&pl->vc, 4 * B * r) == cudaSuccess && cudaMalloc(&pl->wc, 4 * B * m * n * pl->partsP) == cudaSuccess &&
-            cudaMalloc(&pl->bad, 4 * B) == cudaSuccess && cudaMalloc(&pl->stage, 4 * stage) == cudaSuccess;
+  const size_t G32 = (size_t)pl->groups * 32;
+  const size_t stage = (size_t)batch * (size_t)(m * k > k * n ? m * k : k * n);
+  auto zalloc = [](unsigned int** ptr, size_t words) { return cudaMalloc(ptr, 4 * words) == cudaSuccess && cudaMemset(*ptr, 0, 4 * words) == cudaSuccess; };
+  const bool ok = zalloc(&pl->ua, G32 * m * k) && zalloc(&pl->ub, G32 * k * n) && zalloc(&pl->va, G32 * r * pl->L.nslabs) &&
+                  zalloc(&pl->vb, G32 * r * pl->R.nslabs) && zalloc(&pl->vc, G32 * r) && zalloc(&pl->wc, G32 * m * n * pl->P.nslabs) &&
+                  zalloc(&pl->bad, (size_t)batch) && zalloc(&pl->stage, stage);
   if (!ok) { set_error("mmcheck: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())); plo_mmcheck_plan_destroy(pl); return PLO_E_CUDA; }
   *plan = pl;
   return PLO_OK;
 }
 
+static void launch_spmm(const plo_mmcheck_plan* pl, const DevSlabCsr& A, const unsigned int* X, unsigned int* out, const unsigned int* mul, cudaStream_t st) {
+  SpmmArgs a;
+  a.mul = mul;
+  a.p = pl->p; a.M = pl->M; a.rows = A.rows; a.xlen = A.cols; a.groups = pl->groups; a.nchunks = A.nchunks;
+  a.chunk = A.chunk; a.blob = A.blob; a.X = X; a.out = out;
+  const long long T = (long long)pl->groups * A.nchunks;
+  const int grid = (int)std::min<long long>(T, pl->grid_cap);
+  if (A.grouped) mm_slab_spmm_kernel<true><<<grid, kSpThreads, kSpSmem, st>>>(a);
+  else mm_slab_spmm_kernel<false><<<grid, kSpThreads, kSpSmem, st>>>(a);
+}
+
 static int mm_pipeline(plo_mmcheck_plan* pl, cudaStream_t st) {
-  const int B = pl->batch, groups = (B + 31) / 32;
-  auto blocks = [](long long warps) { return (unsigned)((warps * 32 + kMmThreads - 1) / kMmThreads); };
+  const int B = pl->batch;
+  const size_t G32 = (size_t)pl->groups * 32;
   PLO_CUDA(cudaMemsetAsync(pl->bad, 0, 4 * (size_t)B, st));
-  mm_spmm_kernel<<<blocks((long long)pl->r * pl->partsLR * groups), kMmThreads, 0, st>>>(pl->p, pl->r, B, pl->partsLR, pl->L.ptr, pl->L.col, pl->L.val, pl->ua, pl->va);
-  mm_spmm_kernel<<<blocks((long long)pl->r * pl->partsLR * groups), kMmThreads, 0, st>>>(pl->p, pl->r, B, pl->partsLR, pl->R.ptr, pl->R.col, pl->R.val, pl->ub, pl->vb);
-  mm_hadamard_kernel<<<(unsigned)(((size_t)pl->r * B + 255) / 256), 256, 0, st>>>(pl->p, pl->r, B, pl->partsLR, pl->va, pl->vb, pl->vc);
-  const int mn = pl->m * pl->n;
-  mm_spmm_kernel<<<blocks((long long)mn * pl->partsP * groups), kMmThreads, 0, st>>>(pl->p, mn, B, pl->partsP, pl->P.ptr, pl->P.col, pl->P.val, pl->vc, pl->wc);
-  mm_verify_kernel<<<(unsigned)(((size_t)mn * B + 255) / 256), 256, 0, st>>>(pl->p, pl->m, pl->k, pl->n, B, pl->partsP, pl->wc, pl->ua, pl->ub, pl->bad);
+  launch_spmm(pl, pl->L, pl->ua, pl->va, nullptr, st);
+  if (pl->L.nslabs == 1 && pl->R.nslabs == 1) {
+    launch_spmm(pl, pl->R, pl->ub, pl->vc, pl->va, st);  // vc = (R ub) o (L ua) in the epilogue
+  } else {
+    launch_spmm(pl, pl->R, pl->ub, pl->vb, nullptr, st);
+    const size_t cnt = G32 * pl->r;
+    mm_hadamard_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(pl->p, pl->M, cnt, pl->L.nslabs, pl->R.nslabs, pl->va, pl->vb, pl->vc);
+  }
+  launch_spmm(pl, pl->P, pl->vc, pl->wc, nullptr, st);
+  const size_t vcnt = G32 * pl->m * pl->n;
+  mm_verify_kernel<<<(unsigned)((vcnt + 255) / 256), 256, 0, st>>>(pl->p, pl->M, pl->m, pl->k, pl->n, B, pl->groups, pl->P.nslabs, pl->wc, pl->ua, pl->ub, pl->bad);
   PLO_CUDA(cudaGetLastError());
   return PLO_OK;
 }
@@ -225,11 +545,12 @@ static int mm_pipeline(plo_mmcheck_plan* pl, cudaStream_t st) {
 int plo_mmcheck_plan_run(plo_mmcheck_plan* pl, uint64_t seed, uint64_t first_sample, void* stream) {
   if (!pl) { set_error("plo_mmcheck_plan_run: null plan"); return PLO_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  mm_gen_kernel<<<(pl->batch + 127) / 128, 128, 0, st>>>(pl->p, seed, first_sample, pl->batch, pl->m * pl->k, pl->k * pl->n, pl->ua, pl->ub);
+  const size_t gthreads = (size_t)pl->batch * ((pl->m * pl->k + 3) / 4 + (pl->k * pl->n + 3) / 4);
+  mm_gen_kernel<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(pl->p, seed, first_sample, pl->batch, pl->m * pl->k, pl->k * pl->n, pl->ua, pl->ub);
   return mm_pipeline(pl, st);
 }
 
-int plo_mmcheck_plan_launches(const plo_mmcheck_plan*) { return 6; }
+int plo_mmcheck_plan_launches(const plo_mmcheck_plan* pl) { return pl && pl->L.nslabs == 1 && pl->R.nslabs == 1 ? 5 : 6; }
 
 // Run on caller-provided sample vectors ua (batch x mk), ub (batch x kn), host pointers.
 static int mm_run_given(plo_mmcheck_plan* pl, const uint32_t* ua, const uint32_t* ub, cudaStream_t st) {

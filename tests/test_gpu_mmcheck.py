@@ -89,3 +89,31 @@ def test_regenerated_32x32x32_15096_passes_and_corruption_is_caught(capi):
     ua = rng.integers(0, p, (3, 1024)).astype(np.uint32); ub = rng.integers(0, p, (3, 1024)).astype(np.uint32)
     v, ok = capi.mmcheck_batch(p, mkn, r, L2, R2, P2, batch=3, ua=ua, ub=ub)
     assert v == 0 and ok.all()
+
+
+def _trivial_algorithm(m, k, n, rng=None, p=P31):
+    """r = m*k*n elementary products (optionally scaled by random units a, b, 1/(ab)) as CSR triples."""
+    r = m * k * n
+    t = np.arange(r)
+    i, a, j = t // (k * n), (t // n) % k, t % n
+    la = rng.integers(1, p, r) if rng is not None else np.ones(r, dtype=np.int64)
+    lb = rng.integers(1, p, r) if rng is not None else np.ones(r, dtype=np.int64)
+    lc = np.array([pow(int(x) * int(y) % p, -1, p) for x, y in zip(la, lb)], dtype=np.int64) if rng is not None else np.ones(r, dtype=np.int64)
+    Lc = (r, m * k, np.arange(r + 1, dtype=np.int64), (i * k + a).astype(np.int32), la.astype(np.uint32))
+    Rc = (r, k * n, np.arange(r + 1, dtype=np.int64), (a * n + j).astype(np.int32), lb.astype(np.uint32))
+    order = np.lexsort((t, i * n + j))  # rows of P = outputs (i, j), k products each
+    Pc = (m * n, r, np.arange(m * n + 1, dtype=np.int64) * k, t[order].astype(np.int32), lc[order].astype(np.uint32))
+    return r, Lc, Rc, Pc
+
+
+@pytest.mark.parametrize("mkn,scaled", [((40, 30, 2), False), ((40, 30, 2), True), ((3, 400, 3), True)])
+def test_wide_matrices_span_several_column_slabs(capi, mkn, scaled):
+    """Operands wider than one 1024-column shared-memory slab (L: 1200 columns, P: 2400/3600 columns) take the
+    partial-sum path; all-distinct random values take the plain (column, value) format, all-ones the grouped one."""
+    m, k, n = mkn
+    r, Lc, Rc, Pc = _trivial_algorithm(m, k, n, np.random.default_rng(1) if scaled else None)
+    v, ok = capi.mmcheck_batch(P31, mkn, r, Lc, Rc, Pc, seed=3, batch=70)
+    assert v == 0 and ok.all()
+    val = Pc[4].copy(); val[-1] = (int(val[-1]) + 1) % P31
+    v, ok = capi.mmcheck_batch(P31, mkn, r, Lc, Rc, (Pc[0], Pc[1], Pc[2], Pc[3], val), seed=3, batch=70)
+    assert v == 1 and not ok.any()
