@@ -73,6 +73,31 @@ def lincomb_cases(peaks):
         plan.close()
 
 
+def orbit_cases(peaks):
+    """Orbit sweep (src/orbiter.cpp:272-324) on every instantiated shape, both measures; ops per candidate as in SURVEY.md 8d."""
+    cases = [("2x2x2_7_Winograd", 28), ("3x3x3_23_58", 24), ("4x4x4_48_rational", 22), ("3x4x7_63_rational", 21)]
+    for stem, lg in cases:
+        L, R, P = hm.load_fixture(stem)
+        mkn = hm.LRP2MM(L, R, P)
+        m, k, n = mkn
+        r = len(L)
+        (Li, dl), (Ri, dr), (Pi, dp) = (hm.scaled(M, np.int32) for M in (L, R, P))
+        ops = r * (m * m * k + m * k * k + k * k * n + k * n * n + m * m * n + m * n * n) + r * (m * k + k * n + m * n)
+        for measure, name in ((capi.MEASURE_NNZ, "nnz"), (capi.MEASURE_G2, "G2")):
+            try:
+                plan = capi.OrbitPlan(mkn, Li, Ri, Pi, (dl, dr, dp), measure, capi.MODE_PHILOX, 0x504C494E4F505431)
+            except capi.PloError as e:
+                print(json.dumps({"kernel": "orbit_sweep_kernel", "case": f"{stem} {name}", "error": str(e)}))
+                continue
+            B = 1 << lg
+            ms = time_plan(lambda s: plan.run(0, B, s), 5)
+            best = plan.result()
+            print(json.dumps({"kernel": f"orbit_sweep_kernel<{m},{k},{n},philox,{name}>", "case": f"{stem}, 2^{lg} candidates", "ms": ms,
+                              "candidates_per_s": B / ms * 1e3, "int32_ops_per_candidate": ops, "int32_ops_per_s": ops * B / ms * 1e3,
+                              "frac_of_imad_peak": ops * B / ms * 1e3 / peaks["imad_per_s"], "best": best}))
+            plan.close()
+
+
 def mmcheck_case():
     rng = np.random.default_rng(0)
     m = k = n = 32
@@ -106,6 +131,10 @@ if __name__ == "__main__":
     capi.set_device(0)
     peaks = capi.measure_peaks(5)
     print(json.dumps({"peaks": peaks}))
+    if "--orbit-only" in sys.argv:
+        orbit_cases(peaks)
+        sys.exit(0)
     if "--mm-only" not in sys.argv:
         lincomb_cases(peaks)
+        orbit_cases(peaks)
     mmcheck_case()
