@@ -176,6 +176,35 @@ int plo_mmcheck_plan_launches(const plo_mmcheck_plan* plan);
 void plo_mmcheck_plan_destroy(plo_mmcheck_plan* plan);
 
 /* ---------------------------------------------------------------------------
+ * Factorizer random restarts  (SURVEY.md section 8 row f2).
+ * Replaces the `omp parallel for` over `randomloops` calls of backSolver in
+ * PLinOpt::Factorizer  include/plinopt_sparsify.inl:960-985  (backSolver :755-867,
+ * order tricOpCount :914-921).  Candidate `index` = one random row order of M
+ * (plo_factor_decode); its score is (nnz(Alt), #entries of Alt not in {0,+-1},
+ * nnz(CoB)) of the factorisation M = Alt.CoB that backSolver builds from that
+ * order, inner dimension k (n <= k <= r).  M: r x n residues mod an odd prime
+ * p < 2^31, full column rank (candidates whose first rows never reach rank n
+ * score as "none").  Lexicographic minimum, lowest index among ties.
+ * table (may be NULL): 3 x (hi-lo) words (nnz_alt, nno_alt, nnz_cob) per candidate.
+ * ------------------------------------------------------------------------ */
+typedef struct plo_factor_best {
+  uint32_t nnz_alt, nno_alt, nnz_cob, pad_;
+  uint64_t index; /* PLO_NO_INDEX if no candidate */
+} plo_factor_best;
+
+int plo_factor_sweep(uint32_t p, int r, int n, int k, const uint32_t* M, uint64_t seed, uint64_t lo, uint64_t hi,
+                     plo_factor_best* best, uint32_t* table);
+/* perm[t] = original row standing at position t of candidate `index` (host function, same digits as the device) */
+int plo_factor_decode(int r, uint64_t seed, uint64_t index, int32_t* perm);
+
+typedef struct plo_factor_plan plo_factor_plan;
+int plo_factor_plan_create(plo_factor_plan** plan, uint32_t p, int r, int n, int k, const uint32_t* M, uint64_t seed);
+int plo_factor_plan_run(plo_factor_plan* plan, uint64_t lo, uint64_t hi, void* stream);
+int plo_factor_plan_result(plo_factor_plan* plan, void* stream, plo_factor_best* best);
+int plo_factor_plan_launches(const plo_factor_plan* plan);
+void plo_factor_plan_destroy(plo_factor_plan* plan);
+
+/* ---------------------------------------------------------------------------
  * Roofline denominators that MEASURED_PEAKS.json does not hold: register-
  * resident unrolled IMAD / DFMA / (ISETP+IADD) loops over all SMs, CUDA-event
  * timed, best of `reps`.  Results in operations per second.

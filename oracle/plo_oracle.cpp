@@ -31,6 +31,13 @@
 //                            OpenMP arrival order, src/orbiter.cpp:61-62,298-302);
 //                            defined here through a counter-based decode
 //                            (DESIGN.md "orbit candidate decode").
+//   * Factorizer           : PARITY UNPINNED in the reference (RANDOM_TIES row
+//                            permutations are time-seeded, plinopt_sparsify.inl:775-779;
+//                            the free coordinates of GaussDomain::solve depend on
+//                            LinBox).  Restated with a counter-based row order and
+//                            the "extra rows get coordinate zero" rule; pinned through
+//                            the invariant M == Alt.CoB (consistency(), :871-907) and
+//                            the reference's own -ALT/-CoB fixture pairs.
 //
 // Every function cites the reference file:line it follows (paths relative to
 // the reference root).
@@ -784,6 +791,78 @@ static void orbitApply(const F& f, int m, int k, int n, const Mat<F>& L, const M
 // C ABI for ctypes (tests / bench cpu_baseline).  Rationals cross the boundary
 // as (num, den) int64 arrays; Z/pZ entries as int64 residues.
 // =============================================================================
+namespace orc {
+// ----------------------------------------------------------------------------
+// backSolver  include/plinopt_sparsify.inl:755-867  for one row order `perm`
+// (perm[t] = original row at position t: the RANDOM_TIES permutation S, :775-779).
+//   :786-802  greedy choice of n independent rows, a chosen row at position j
+//             swapped to position i (setRow + rank + T.permute + swap);
+//   :803-805  rows at positions rk..k-1 complete CoB;
+//   :807-850  the other rows are solved for: x.CoB = row.  LinBox's
+//             QLUPin/solve is not in the tree => PARITY UNPINNED; rule:
+//             coordinates on the k-n extra rows are zero, the rest is row.B^-1
+//             with B = the n independent rows (unique);
+//   :852-860  rows brought back to the original order (T then S);
+//   :863-864  Tricounter (nnz(Res), non-+-1 of Res, density(CoB)).
+// Returns false if M has not full column rank for this order.
+// ----------------------------------------------------------------------------
+template <class F>
+static bool backSolver(const F& f, Mat<F>& CoB, Mat<F>& Res, const Mat<F>& iM, size_t k, const std::vector<int>& perm, size_t ops[3]) {
+  const size_t r = iM.r, n = iM.c;
+  std::vector<int> pos(perm);  // pos[t] = original row standing at position t
+  Mat<F> M(f, r, n);
+  for (size_t t = 0; t < r; ++t) for (size_t j = 0; j < n; ++j) M(t, j) = iM((size_t)pos[t], j);
+  CoB = Mat<F>(f, k, n);
+  size_t rk = 0;
+  for (size_t i = 0; i < n; ++i) {
+    for (size_t j = i; j < r; ++j) {
+      for (size_t c = 0; c < n; ++c) CoB(i, c) = M(j, c);  // setRow(CoB, i, M, j)
+      rk = rank(f, CoB);
+      if (rk == i + 1) {
+        if (i != j) { std::swap(pos[i], pos[j]); for (size_t c = 0; c < n; ++c) std::swap(M(i, c), M(j, c)); }
+        break;
+      }
+    }
+    if (rk != i + 1) return false;
+  }
+  for (size_t j = rk; j < k; ++j) for (size_t c = 0; c < n; ++c) CoB(j, c) = M(j, c);
+  Mat<F> B(f, n, n);
+  for (size_t i = 0; i < n; ++i) for (size_t c = 0; c < n; ++c) B(i, c) = M(i, c);
+  const Mat<F> Bi = inverse(f, B);
+  Res = Mat<F>(f, r, k);
+  for (size_t t = 0; t < r; ++t) {
+    const size_t orig = (size_t)pos[t];
+    if (t < k) { Res(orig, t) = f.one(); continue; }
+    for (size_t j = 0; j < n; ++j) {
+      typename F::E x = f.zero();
+      for (size_t c = 0; c < n; ++c) if (!f.isZero(M(t, c)) && !f.isZero(Bi(c, j))) x = f.add(x, f.mul(M(t, c), Bi(c, j)));
+      Res(orig, j) = x;
+    }
+  }
+  size_t nnz = 0, nno = 0;
+  nonzeroes(f, Res, nnz, nno);
+  ops[0] = nnz; ops[1] = nno; ops[2] = density(f, CoB);
+  return true;
+}
+
+// Row order of candidate `index`: Fisher-Yates driven by the Philox digit stream.
+static std::vector<int> factorOrder(size_t r, uint64_t seed, uint64_t index) {
+  std::vector<int> perm(r);
+  std::iota(perm.begin(), perm.end(), 0);
+  DigitStream ds(1, seed, index);
+  ds.startMatrix();
+  for (size_t i = 0; i + 1 < r; ++i) { const uint32_t d = ds.digit((uint32_t)(r - i)); std::swap(perm[i], perm[i + d]); }
+  return perm;
+}
+
+// Factorizer random restarts, include/plinopt_sparsify.inl:960-985, with the engine's
+// deterministic acceptance (tricOpCount :914-921, lowest index among ties).
+template <class F>
+static int factor_sweep_impl(const F& f, int r, int n, int k, const int64_t* num, const int64_t* den, uint64_t seed, uint64_t lo,
+                             uint64_t hi, int nthreads, uint32_t* table, uint64_t* best_index, uint32_t* best_ops,
+                             int64_t* alt_num, int64_t* alt_den, int64_t* cob_num, int64_t* cob_den);
+}  // namespace orc
+
 using namespace orc;
 
 template <class F> struct Loader;
@@ -1076,4 +1155,58 @@ int orc_mmcheck_q(int r, int Lc, int Rc, int Pr, const int64_t* Ln, const int64_
   return g_overflow ? -g_overflow : 0;
 }
 
+}  // extern "C"
+
+namespace orc {
+template <class F>
+static int factor_sweep_impl(const F& f, int r, int n, int k, const int64_t* num, const int64_t* den, uint64_t seed, uint64_t lo,
+                             uint64_t hi, int nthreads, uint32_t* table, uint64_t* best_index, uint32_t* best_ops,
+                             int64_t* alt_num, int64_t* alt_den, int64_t* cob_num, int64_t* cob_den) {
+  g_overflow = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  const Mat<F> M = Loader<F>::load(f, r, n, num, den);
+  uint64_t bidx = UINT64_MAX;
+  size_t bops[3] = {SIZE_MAX, SIZE_MAX, SIZE_MAX};
+#pragma omp parallel for schedule(dynamic, 16)
+  for (uint64_t idx = lo; idx < hi; ++idx) {
+    Mat<F> CoB, Res;
+    size_t ops[3] = {SIZE_MAX, SIZE_MAX, SIZE_MAX};
+    const bool ok = backSolver(f, CoB, Res, M, (size_t)k, factorOrder((size_t)r, seed, idx), ops);
+    if (table) for (int t = 0; t < 3; ++t) table[(idx - lo) * 3 + t] = ok ? (uint32_t)ops[t] : (t == 0 ? UINT32_MAX : 0u);
+    if (!ok) continue;
+#pragma omp critical
+    {
+      const bool less = ops[0] != bops[0] ? ops[0] < bops[0] : ops[1] != bops[1] ? ops[1] < bops[1] : ops[2] != bops[2] ? ops[2] < bops[2] : idx < bidx;
+      if (less) { bidx = idx; bops[0] = ops[0]; bops[1] = ops[1]; bops[2] = ops[2]; }
+    }
+  }
+  *best_index = bidx;
+  for (int t = 0; t < 3; ++t) best_ops[t] = bidx == UINT64_MAX ? UINT32_MAX : (uint32_t)bops[t];
+  if (bidx != UINT64_MAX && alt_num && cob_num) {
+    Mat<F> CoB, Res;
+    size_t ops[3];
+    backSolver(f, CoB, Res, M, (size_t)k, factorOrder((size_t)r, seed, bidx), ops);
+    Loader<F>::store(Res, alt_num, alt_den);
+    Loader<F>::store(CoB, cob_num, cob_den);
+  }
+  return g_overflow ? -g_overflow : 0;
+}
+}  // namespace orc
+
+extern "C" {
+// Factorizer sweep over candidates lo..hi-1 (p == 0: over Q, else mod p); table: 3 words per candidate;
+// best_ops[3] = (nnz Alt, non-+-1 Alt, nnz CoB); alt (r x k) / cob (k x n) of the winner if requested.
+int orc_factor_sweep(int64_t p, int r, int n, int k, const int64_t* num, const int64_t* den, uint64_t seed, uint64_t lo, uint64_t hi,
+                     int nthreads, uint32_t* table, uint64_t* best_index, uint32_t* best_ops, int64_t* alt_num, int64_t* alt_den,
+                     int64_t* cob_num, int64_t* cob_den) {
+  if (p == 0) { QField f; return factor_sweep_impl(f, r, n, k, num, den, seed, lo, hi, nthreads, table, best_index, best_ops, alt_num, alt_den, cob_num, cob_den); }
+  ZpField f{p};
+  return factor_sweep_impl(f, r, n, k, num, den, seed, lo, hi, nthreads, table, best_index, best_ops, alt_num, alt_den, cob_num, cob_den);
+}
+void orc_factor_decode(int r, uint64_t seed, uint64_t index, int32_t* perm) {
+  const std::vector<int> o = factorOrder((size_t)r, seed, index);
+  for (int t = 0; t < r; ++t) perm[t] = o[(size_t)t];
+}
 }  // extern "C"

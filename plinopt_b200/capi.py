@@ -29,6 +29,8 @@ SYMBOLS = [
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
     "plo_sparsifier", "plo_orbiter", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
+    "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
+    "plo_factor_plan_launches", "plo_factor_plan_destroy",
 ]
 
 
@@ -403,3 +405,71 @@ def slp_to_csr(text, outchar="o"):
         lib().plo_slp_free.restype = None
         lib().plo_slp_free(h)
     return rows.value, cols.value, ptr, col, num, den
+
+
+# --------------------------------------------------------------------------
+# Factorizer random restarts
+# --------------------------------------------------------------------------
+class FactorBest(C.Structure):
+    _fields_ = [("nnz_alt", C.c_uint32), ("nno_alt", C.c_uint32), ("nnz_cob", C.c_uint32), ("pad_", C.c_uint32), ("index", C.c_uint64)]
+
+
+def _factor_tuple(b):
+    return (b.nnz_alt, b.nno_alt, b.nnz_cob, None if b.index == NO_INDEX else b.index)
+
+
+def factor_sweep(p, M, k, seed, lo, hi, table=False):
+    """M: r x n residues mod p.  Returns (nnz_alt, nno_alt, nnz_cob, index)[, table (hi-lo) x 3]."""
+    M = np.ascontiguousarray(M, dtype=np.uint32)
+    r, n = M.shape
+    best = FactorBest()
+    tab = np.zeros((max(hi - lo, 0), 3), dtype=np.uint32) if table else None
+    f = lib().plo_factor_sweep
+    f.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(FactorBest), C.c_void_p]
+    _check(f(p, r, n, k, _ptr(M), seed, lo, hi, C.byref(best), _ptr(tab) if table else None))
+    return (_factor_tuple(best), tab) if table else _factor_tuple(best)
+
+
+def factor_decode(r, seed, index):
+    perm = np.zeros(r, dtype=np.int32)
+    f = lib().plo_factor_decode
+    f.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
+    _check(f(r, seed, index, _ptr(perm)))
+    return perm
+
+
+class FactorPlan:
+    def __init__(self, p, M, k, seed):
+        M = np.ascontiguousarray(M, dtype=np.uint32)
+        r, n = M.shape
+        self._h = C.c_void_p()
+        f = lib().plo_factor_plan_create
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+        _check(f(C.byref(self._h), p, r, n, k, _ptr(M), seed))
+        self.launches = lib().plo_factor_plan_launches(self._h)
+
+    def run(self, lo, hi, stream=0):
+        f = lib().plo_factor_plan_run
+        f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        _check(f(self._h, lo, hi, C.c_void_p(stream)))
+
+    def result(self, stream=0):
+        best = FactorBest()
+        f = lib().plo_factor_plan_result
+        f.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FactorBest)]
+        _check(f(self._h, C.c_void_p(stream), C.byref(best)))
+        return _factor_tuple(best)
+
+    def close(self):
+        if self._h:
+            f = lib().plo_factor_plan_destroy
+            f.argtypes = [C.c_void_p]
+            f.restype = None
+            f(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

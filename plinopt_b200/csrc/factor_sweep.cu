@@ -1,0 +1,374 @@
+// factor_sweep.cu -- random-restart search of  PLinOpt::Factorizer / backSolver
+// (include/plinopt_sparsify.inl:755-867, 924-990) on sm_100a.
+//
+// One candidate = one random row order S of M (r x n, full column rank).
+// backSolver, restated (:773-866):
+//   * walk the rows in the order S, keep the first n independent ones; a kept row
+//     found at position j is swapped to position i  (T.permute(i,j); swap(M[i],M[j]) :786-797);
+//   * CoB = rows at positions 0..k-1 (the n independent ones + k-n "extra" rows, :803-805);
+//   * every other row is solved for:  x . CoB = row  (:842-850).  With B = the n independent
+//     rows, x = [row . B^-1 | 0]  (the coordinates on the extra rows are the free variables of
+//     the solve and are set to zero -- the documented rule that stands in for LinBox's
+//     GaussDomain::solve);
+//   * score = (nnz(Res), #entries of Res not in {0,+-1}, nnz(CoB))  (:863-864), minimised
+//     lexicographically (tricOpCount :914-921), lowest candidate index among ties.
+//
+// Mapping: one WARP per candidate, lane j = column j (n <= 32).  The independent rows are kept
+// as a reduced row echelon basis R (pivots normalised to 1) together with the transformation
+// T (R = T.B), both column-distributed in registers: lane j holds R[.][j] and T[.][j].
+// A row v is reduced with n shuffles (c_i = v[pivot column i], all independent because the
+// basis is *reduced*) + n lazy multiply-adds per lane (exact 96-bit accumulation, one Barrett
+// reduction); accepting a row costs one modular inverse (31 squarings, computed by all lanes)
+// and one rank-1 update of R and T.  Arithmetic: Montgomery residues mod an odd p < 2^31.
+// Rationals are scored modulo p on the device; the host layer recomputes the winner over Q
+// (plo_factorizer, host_api.cpp) and verifies the score.
+#include <algorithm>
+#include <vector>
+
+#include "plo_device.cuh"
+
+namespace plo {
+
+constexpr int kFsWarps = 4;  // candidates in flight per block
+constexpr int kFsThreads = kFsWarps * 32;
+constexpr int kFsMaxRows = 256;
+
+struct FsParams {
+  uint32_t p, pinv, one, mone;  // pinv = -p^-1 mod 2^32; one / mone = Montgomery forms of +-1
+  unsigned long long M64;       // floor((2^64-1)/p)
+  int r, n, k;
+  unsigned long long seed;
+};
+
+__device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, uint32_t p, uint32_t pinv) {
+  const unsigned long long x = (unsigned long long)a * b;
+  const uint32_t m = (uint32_t)x * pinv;
+  const uint32_t t = (uint32_t)((x + (unsigned long long)m * p) >> 32);  // < 2p, no overflow for p < 2^31
+  return t >= p ? t - p : t;
+}
+__device__ __forceinline__ uint32_t sub_mod(uint32_t a, uint32_t b, uint32_t p) { return a >= b ? a - b : a + p - b; }
+
+struct FsAcc {
+  unsigned int a0, a1, a2;
+};
+__device__ __forceinline__ void fs_mac(FsAcc& a, unsigned int x, unsigned int y) {
+  asm volatile(
+      "mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;"
+      : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2)
+      : "r"(x), "r"(y));
+}
+__device__ __forceinline__ uint32_t fs_barrett(unsigned long long x, uint32_t p, unsigned long long M) {
+  const unsigned long long q = __umul64hi(x, M);
+  unsigned long long r = x - q * p;
+  if (r >= p) r -= p;
+  if (r >= p) r -= p;
+  return (uint32_t)r;
+}
+// sum of products of Montgomery residues -> Montgomery residue of the sum of products
+__device__ __forceinline__ uint32_t fs_reduce(const FsAcc& a, const FsParams& P) {
+  const uint32_t t = fs_barrett(((unsigned long long)a.a2 << 32) | a.a1, P.p, P.M64);
+  const uint32_t s = fs_barrett(((unsigned long long)t << 32) | a.a0, P.p, P.M64);
+  // s = (sum aR.bR) mod p = (sum ab) R^2 ; one REDC brings it back to (sum ab) R
+  const uint32_t m = s * P.pinv;
+  const uint32_t u = (uint32_t)(((unsigned long long)s + (unsigned long long)m * P.p) >> 32);
+  return u >= P.p ? u - P.p : u;
+}
+// a^-1 in the Montgomery domain: (aR)^(p-2) by square and multiply (p prime)
+__device__ __forceinline__ uint32_t mont_inv(uint32_t a, const FsParams& P) {
+  uint32_t result = P.one, base = a;
+  uint32_t e = P.p - 2;
+  while (e) {
+    if (e & 1u) result = mont_mul(result, base, P.p, P.pinv);
+    base = mont_mul(base, base, P.p, P.pinv);
+    e >>= 1;
+  }
+  return result;
+}
+
+// Philox digit stream of the row order (same definition as the orbit decode)
+struct FsDigits {
+  unsigned long long index, seed;
+  uint32_t x, R, nwords;
+  uint32_t buf[4];
+  __host__ __device__ __forceinline__ FsDigits(unsigned long long seed_, unsigned long long index_) : index(index_), seed(seed_), x(0), R(0), nwords(0) {}
+  __host__ __device__ __forceinline__ void new_word() {
+    if ((nwords & 3u) == 0) philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), nwords >> 2, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+    x = buf[nwords & 3u];
+    ++nwords;
+    R = 1;
+  }
+  __host__ __device__ __forceinline__ uint32_t digit(uint32_t radix) {
+    if (R == 0 || R * radix > (1u << 20)) new_word();
+    const unsigned long long t = (unsigned long long)x * radix;
+    x = (uint32_t)t;
+    R *= radix;
+    return (uint32_t)(t >> 32);
+  }
+};
+
+// score key: nnz(Res) << 40 | nno(Res) << 20 | nnz(CoB)
+__host__ __device__ __forceinline__ unsigned long long fs_pack(uint32_t nnz_alt, uint32_t nno_alt, uint32_t nnz_cob) {
+  return ((unsigned long long)nnz_alt << 40) | ((unsigned long long)nno_alt << 20) | nnz_cob;
+}
+
+template <int N>
+__global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams P, const uint32_t* __restrict__ Mg /* r x 32, Montgomery */,
+                                                                  const uint32_t* __restrict__ rownnz_g, unsigned long long lo,
+                                                                  unsigned long long hi, Key* __restrict__ block_best,
+                                                                  uint32_t* __restrict__ table /* 3 x (hi-lo) or null */) {
+  extern __shared__ uint32_t fs_smem[];
+  uint32_t* Msh = fs_smem;                             // r x 32
+  uint32_t* nnzsh = Msh + (size_t)P.r * 32;            // r
+  unsigned char* permall = reinterpret_cast<unsigned char*>(nnzsh + P.r);
+  __shared__ Key red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* perm = permall + (size_t)warp * kFsMaxRows;
+  for (int e = threadIdx.x; e < P.r * 32; e += kFsThreads) Msh[e] = Mg[e];
+  for (int e = threadIdx.x; e < P.r; e += kFsThreads) nnzsh[e] = rownnz_g[e];
+  __syncthreads();
+
+  Key best;
+  best.primary = ~0ull; best.index = ~0ull;
+  const unsigned long long nwarps = (unsigned long long)gridDim.x * kFsWarps;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kFsWarps + warp; idx < hi; idx += nwarps) {
+    // ---- row order S: Fisher-Yates from the digit stream (all lanes compute the digits, lane 0 swaps) ----
+    for (int t = lane; t < P.r; t += 32) perm[t] = (unsigned char)t;
+    __syncwarp();
+    {
+      FsDigits ds(P.seed, idx);
+      for (int i = 0; i + 1 < P.r; ++i) {
+        const uint32_t d = ds.digit((uint32_t)(P.r - i));
+        if (lane == 0 && d) { const unsigned char a = perm[i]; perm[i] = perm[i + d]; perm[i + d] = a; }
+      }
+    }
+    __syncwarp();
+    // ---- selection pass: reduced echelon basis R with transformation T, column-distributed ----
+    uint32_t Rj[N], Tj[N];
+    int pc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { Rj[i] = 0; Tj[i] = 0; pc[i] = 0; }
+    int nb = 0;
+    for (int t = 0; t < P.r && nb < P.n; ++t) {
+      const int row = perm[t];
+      const uint32_t v = Msh[row * 32 + lane];
+      FsAcc ar, at;
+      ar.a0 = ar.a1 = ar.a2 = 0;
+      at.a0 = at.a1 = at.a2 = 0;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i < nb) {
+          const uint32_t c = __shfl_sync(0xffffffffu, v, pc[i]);
+          fs_mac(ar, c, Rj[i]);
+          fs_mac(at, c, Tj[i]);
+        }
+      const uint32_t vr = sub_mod(v, fs_reduce(ar, P), P.p);  // v - sum c_i R_i
+      const unsigned nzmask = __ballot_sync(0xffffffffu, vr != 0);
+      if (nzmask == 0) continue;  // dependent on the rows kept so far
+      uint32_t vt = fs_reduce(at, P);
+      vt = sub_mod(lane == nb ? P.one : 0u, vt, P.p);  // e_nb - sum c_i T_i
+      const int pcn = __ffs(nzmask) - 1;
+      const uint32_t ip = mont_inv(__shfl_sync(0xffffffffu, vr, pcn), P);
+      const uint32_t wr = mont_mul(vr, ip, P.p, P.pinv), wt = mont_mul(vt, ip, P.p, P.pinv);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (i < nb) {
+          const uint32_t f = __shfl_sync(0xffffffffu, Rj[i], pcn);
+          Rj[i] = sub_mod(Rj[i], mont_mul(f, wr, P.p, P.pinv), P.p);
+          Tj[i] = sub_mod(Tj[i], mont_mul(f, wt, P.p, P.pinv), P.p);
+        }
+        if (i == nb) { Rj[i] = wr; Tj[i] = wt; pc[i] = pcn; }
+      }
+      if (lane == 0 && t != nb) { const unsigned char a = perm[nb]; perm[nb] = perm[t]; perm[t] = a; }  // :793-796
+      ++nb;
+    }
+    __syncwarp();
+    // ---- score ----
+    unsigned long long key = ~0ull;
+    uint32_t nnz_alt = 0, nno_alt = 0, nnz_cob = 0;
+    if (nb == P.n) {
+      for (int t = 0; t < P.r; ++t) {
+        const int row = perm[t];
+        if (t < P.k) { nnz_alt += 1; nnz_cob += nnzsh[row]; continue; }  // identity row of Res, row of CoB
+        const uint32_t v = Msh[row * 32 + lane];
+        FsAcc ax;
+        ax.a0 = ax.a1 = ax.a2 = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+          if (i < nb) fs_mac(ax, __shfl_sync(0xffffffffu, v, pc[i]), Tj[i]);
+        const uint32_t x = fs_reduce(ax, P);  // coordinate of `row` on the lane-th independent row
+        const bool nz = lane < P.n && x != 0;
+        nnz_alt += __popc(__ballot_sync(0xffffffffu, nz));
+        nno_alt += __popc(__ballot_sync(0xffffffffu, nz && x != P.one && x != P.mone));
+      }
+      key = fs_pack(nnz_alt, nno_alt, nnz_cob);
+    }
+    if (table && lane == 0) {
+      const unsigned long long o = (idx - lo) * 3;
+      table[o] = nb == P.n ? nnz_alt : 0xffffffffu; table[o + 1] = nno_alt; table[o + 2] = nnz_cob;
+    }
+    if (key < best.primary || (key == best.primary && idx < best.index)) { best.primary = key; best.index = idx; }
+    __syncwarp();
+  }
+  // every lane of a warp holds the same `best`; block minimum over the warps
+  if (lane == 0) red[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Key b = red[0];
+    for (int w = 1; w < kFsWarps; ++w) if (key_less(red[w], b)) b = red[w];
+    block_best[blockIdx.x] = b;
+  }
+}
+
+typedef void (*FsLaunch)(int grid, size_t smem, cudaStream_t st, const FsParams& P, const uint32_t* M, const uint32_t* nnz,
+                         unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* table);
+template <int N>
+static void fs_launch(int grid, size_t smem, cudaStream_t st, const FsParams& P, const uint32_t* M, const uint32_t* nnz,
+                      unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* table) {
+  factor_sweep_kernel<N><<<grid, kFsThreads, smem, st>>>(P, M, nnz, lo, hi, bb, table);
+}
+template <int N>
+static int fs_blocks_per_sm(size_t smem) {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_sweep_kernel<N>, kFsThreads, smem);
+  return nb > 0 ? nb : 1;
+}
+
+static uint32_t host_to_mont(uint64_t a, uint32_t p) { return (uint32_t)((((unsigned __int128)a) << 32) % p); }
+
+}  // namespace plo
+
+using namespace plo;
+
+struct plo_factor_plan {
+  FsParams P;
+  int npad, grid;
+  size_t smem;
+  FsLaunch launch;
+  uint32_t *d_M, *d_nnz;
+  Key* d_bb;
+};
+
+extern "C" {
+
+void plo_factor_plan_destroy(plo_factor_plan* pl) {
+  if (!pl) return;
+  cudaFree(pl->d_M); cudaFree(pl->d_nnz); cudaFree(pl->d_bb);
+  delete pl;
+}
+
+int plo_factor_plan_create(plo_factor_plan** plan, uint32_t p, int r, int n, int k, const uint32_t* M, uint64_t seed) {
+  if (!plan || !M || r < 1 || n < 1 || n > 32 || r > kFsMaxRows - 1 || k < n || k > r || p < 3 || !(p & 1u) || p >= (1u << 31)) {
+    set_error("plo_factor_plan_create: need 1 <= n <= 32, n <= k <= r <= %d, odd prime 3 <= p < 2^31", kFsMaxRows - 1);
+    return PLO_E_ARG;
+  }
+  for (size_t e = 0; e < (size_t)r * n; ++e)
+    if (M[e] >= p) { set_error("plo_factor_plan_create: residue >= p"); return PLO_E_ARG; }
+  int rc = check_device();
+  if (rc) return rc;
+  plo_factor_plan* pl = new plo_factor_plan();
+  memset(pl, 0, sizeof(*pl));
+  FsParams& P = pl->P;
+  P.p = p; P.r = r; P.n = n; P.k = k; P.seed = seed; P.M64 = ~0ull / p;
+  uint32_t inv = 1;  // Newton: p * inv == 1 mod 2^32
+  for (int i = 0; i < 5; ++i) inv *= 2u - p * inv;
+  P.pinv = 0u - inv;
+  P.one = host_to_mont(1, p); P.mone = host_to_mont(p - 1, p);
+  std::vector<uint32_t> hM((size_t)r * 32, 0), hn(r, 0);
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < n; ++j) { hM[(size_t)i * 32 + j] = host_to_mont(M[(size_t)i * n + j], p); hn[i] += M[(size_t)i * n + j] != 0; }
+  pl->npad = (n + 3) & ~3;
+  switch (pl->npad) {
+#define PLO_FS_CASE(NN) case NN: pl->launch = &fs_launch<NN>; break;
+    PLO_FS_CASE(4) PLO_FS_CASE(8) PLO_FS_CASE(12) PLO_FS_CASE(16) PLO_FS_CASE(20) PLO_FS_CASE(24) PLO_FS_CASE(28) PLO_FS_CASE(32)
+#undef PLO_FS_CASE
+  }
+  pl->smem = ((size_t)r * 32 + r) * 4 + (size_t)kFsWarps * kFsMaxRows;
+  int bps = 1;
+  switch (pl->npad) {
+#define PLO_FS_CASE(NN) case NN: bps = fs_blocks_per_sm<NN>(pl->smem); break;
+    PLO_FS_CASE(4) PLO_FS_CASE(8) PLO_FS_CASE(12) PLO_FS_CASE(16) PLO_FS_CASE(20) PLO_FS_CASE(24) PLO_FS_CASE(28) PLO_FS_CASE(32)
+#undef PLO_FS_CASE
+  }
+  pl->grid = sm_count() * bps;
+  const bool ok = cudaMalloc(&pl->d_M, hM.size() * 4) == cudaSuccess && cudaMalloc(&pl->d_nnz, hn.size() * 4) == cudaSuccess &&
+                  cudaMalloc(&pl->d_bb, sizeof(Key) * pl->grid) == cudaSuccess &&
+                  cudaMemcpy(pl->d_M, hM.data(), hM.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMemcpy(pl->d_nnz, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) { set_error("plo_factor_plan_create: %s", cudaGetErrorString(cudaGetLastError())); plo_factor_plan_destroy(pl); return PLO_E_CUDA; }
+  *plan = pl;
+  return PLO_OK;
+}
+
+static int fs_grid(const plo_factor_plan* pl, uint64_t lo, uint64_t hi) {
+  const uint64_t need = (hi - lo + kFsWarps - 1) / kFsWarps;
+  return (int)(need < (uint64_t)pl->grid ? (need ? need : 1) : (uint64_t)pl->grid);
+}
+
+int plo_factor_plan_run(plo_factor_plan* pl, uint64_t lo, uint64_t hi, void* stream) {
+  if (!pl) { set_error("plo_factor_plan_run: null plan"); return PLO_E_ARG; }
+  const int grid = fs_grid(pl, lo, hi);
+  Key none;
+  none.primary = ~0ull; none.index = ~0ull;
+  std::vector<Key> init(pl->grid, none);
+  PLO_CUDA(cudaMemcpyAsync(pl->d_bb, init.data(), sizeof(Key) * pl->grid, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  if (hi > lo) pl->launch(grid, pl->smem, (cudaStream_t)stream, pl->P, pl->d_M, pl->d_nnz, lo, hi, pl->d_bb, nullptr);
+  PLO_CUDA(cudaGetLastError());
+  return PLO_OK;
+}
+
+int plo_factor_plan_result(plo_factor_plan* pl, void* stream, plo_factor_best* best) {
+  if (!pl || !best) { set_error("plo_factor_plan_result: bad argument"); return PLO_E_ARG; }
+  std::vector<Key> bb(pl->grid);
+  PLO_CUDA(cudaMemcpyAsync(bb.data(), pl->d_bb, sizeof(Key) * pl->grid, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PLO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  Key b = bb[0];
+  for (const Key& x : bb) if (key_less(x, b)) b = x;
+  best->index = b.index;
+  if (b.primary == ~0ull) { best->nnz_alt = best->nno_alt = best->nnz_cob = 0xffffffffu; best->index = PLO_NO_INDEX; }
+  else { best->nnz_alt = (uint32_t)(b.primary >> 40); best->nno_alt = (uint32_t)((b.primary >> 20) & 0xfffffu); best->nnz_cob = (uint32_t)(b.primary & 0xfffffu); }
+  return PLO_OK;
+}
+
+int plo_factor_plan_launches(const plo_factor_plan*) { return 1; }
+
+int plo_factor_sweep(uint32_t p, int r, int n, int k, const uint32_t* M, uint64_t seed, uint64_t lo, uint64_t hi,
+                     plo_factor_best* best, uint32_t* table) {
+  plo_factor_plan* pl = nullptr;
+  int rc = plo_factor_plan_create(&pl, p, r, n, k, M, seed);
+  if (rc) return rc;
+  if (!table) {
+    rc = plo_factor_plan_run(pl, lo, hi, nullptr);
+  } else {
+    uint32_t* d_tab = nullptr;
+    const size_t cnt = (size_t)(hi > lo ? hi - lo : 0) * 3;
+    Key none;
+    none.primary = ~0ull; none.index = ~0ull;
+    std::vector<Key> init(pl->grid, none);
+    if (cudaMemcpy(pl->d_bb, init.data(), sizeof(Key) * pl->grid, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMalloc(&d_tab, cnt ? cnt * 4 : 4) != cudaSuccess) {
+      set_error("plo_factor_sweep: %s", cudaGetErrorString(cudaGetLastError())); plo_factor_plan_destroy(pl); return PLO_E_CUDA;
+    }
+    if (hi > lo) pl->launch(fs_grid(pl, lo, hi), pl->smem, nullptr, pl->P, pl->d_M, pl->d_nnz, lo, hi, pl->d_bb, d_tab);
+    if (cudaMemcpy(table, d_tab, cnt * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("plo_factor_sweep: %s", cudaGetErrorString(cudaGetLastError())); rc = PLO_E_CUDA; }
+    cudaFree(d_tab);
+  }
+  if (!rc && best) rc = plo_factor_plan_result(pl, nullptr, best);
+  plo_factor_plan_destroy(pl);
+  return rc;
+}
+
+// Row order of candidate `index`: perm[t] = original row at position t (before the selection swaps).
+int plo_factor_decode(int r, uint64_t seed, uint64_t index, int32_t* perm) {
+  if (r < 1 || !perm) { set_error("plo_factor_decode: bad argument"); return PLO_E_ARG; }
+  for (int t = 0; t < r; ++t) perm[t] = t;
+  FsDigits ds(seed, index);
+  for (int i = 0; i + 1 < r; ++i) {
+    const uint32_t d = ds.digit((uint32_t)(r - i));
+    std::swap(perm[i], perm[i + d]);
+  }
+  return PLO_OK;
+}
+
+}  // extern "C"

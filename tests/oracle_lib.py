@@ -258,3 +258,39 @@ def mmcheck_q(L, R, P, ua, ub):
     f.argtypes = [C.c_int] * 4 + [_i64p] * 6 + [_i64p, _i64p]
     return f(len(L), len(L[0]), len(R[0]), len(P), Ln, Ld, Rn, Rd, Pn, Pd,
              np.ascontiguousarray(ua, dtype=np.int64), np.ascontiguousarray(ub, dtype=np.int64))
+
+
+def factor_sweep(M, k, seed, lo, hi, p=0, nthreads=0, table=True, matrices=False):
+    """Factorizer random restarts (plinopt_sparsify.inl:924-990) over candidates lo..hi-1; M as Fractions.
+    Returns dict(best=(nnz_alt, nno_alt, nnz_cob, index), table=(hi-lo) x 3, alt=, cob=)."""
+    L = lib()
+    r, n = len(M), len(M[0])
+    num, den = numden(M)
+    cnt = hi - lo
+    tab = np.zeros((cnt, 3), dtype=np.uint32) if table else None
+    bidx = C.c_uint64(); bops = (C.c_uint32 * 3)()
+    an = np.zeros((r, k), dtype=np.int64); ad = np.ones((r, k), dtype=np.int64)
+    cn = np.zeros((k, n), dtype=np.int64); cd = np.ones((k, n), dtype=np.int64)
+    f = L.orc_factor_sweep
+    f.restype = C.c_int
+    f.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p,
+                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = f(p, r, n, k, num.ctypes.data, den.ctypes.data, seed, lo, hi, nthreads, tab.ctypes.data if table else None, C.byref(bidx), bops,
+           an.ctypes.data if matrices else None, ad.ctypes.data if matrices else None, cn.ctypes.data if matrices else None,
+           cd.ctypes.data if matrices else None)
+    assert rc == 0, f"oracle overflow/invalid ({rc})"
+    idx = None if bidx.value == 0xFFFFFFFFFFFFFFFF else bidx.value
+    out = {"best": (bops[0], bops[1], bops[2], idx), "table": tab}
+    if matrices:
+        out["alt"] = [[Fraction(int(a), int(b)) for a, b in zip(ra, rb)] for ra, rb in zip(an, ad)]
+        out["cob"] = [[Fraction(int(a), int(b)) for a, b in zip(ra, rb)] for ra, rb in zip(cn, cd)]
+    return out
+
+
+def factor_decode(r, seed, index):
+    perm = np.zeros(r, dtype=np.int32)
+    f = lib().orc_factor_decode
+    f.restype = None
+    f.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
+    f(r, seed, index, perm.ctypes.data)
+    return perm
