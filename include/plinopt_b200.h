@@ -253,6 +253,17 @@ int plo_mmchecker(uint64_t modulus, uint64_t seed, int batch, int Lrows, int Lco
                   int Pcols, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
                   const int64_t* Pn, const int64_t* Pd, uint32_t* nnz_nno /* [2], may be NULL */);
 
+/* Factorizer  include/plinopt_sparsify.inl:924-990  (driver TFactorizer src/factorizer.cpp:28-97 without the
+ * optional initial sparsification): M (rows x cols, full column rank) -> Alt (rows x k) . CoB (k x cols),
+ * k = innerdim (0: cols), minimising (nnz(Alt), non-+-1 of Alt, nnz(CoB)) over `loops` random row orders
+ * (candidates 0..loops-1 of plo_factor_sweep), starting from the trivial M = M.I (:958).  q == 0: over Q -- the
+ * device scores candidates modulo a 31-bit prime, the winner is rebuilt exactly and its score verified;
+ * q > 0: over Z/qZ.  Returns 0, -1 (inner dimension outside [cols, rows], :936-942) or PLO_E_*.
+ * report (may be NULL, 8 words): initial (nnz, non-+-1, cols), final (nnz Alt, non-+-1 Alt, nnz CoB),
+ * winning candidate (PLO_NO_INDEX: the trivial factorisation was kept), consistency M == Alt.CoB (:871-907). */
+int plo_factorizer(uint64_t q, int rows, int cols, const int64_t* num, const int64_t* den, int innerdim, uint64_t loops,
+                   uint64_t seed, int64_t* alt_num, int64_t* alt_den, int64_t* cob_num, int64_t* cob_den, uint64_t* report);
+
 /* Straight-line program -> matrix: matrixBuilder  include/plinopt_programs.inl:1459-1608 (with the
  * parser :618-686 and parenthesisExpand :1615-1679; driver src/SLPchecker.cpp:22-40, rule
  * data/Makefile:31-32).  Needed to regenerate data/32x32x32_15096_{L,R,P}.sms, which the reference

@@ -30,7 +30,7 @@ SYMBOLS = [
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
     "plo_sparsifier", "plo_orbiter", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
     "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
-    "plo_factor_plan_launches", "plo_factor_plan_destroy",
+    "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer",
 ]
 
 
@@ -473,3 +473,21 @@ class FactorPlan:
             self.close()
         except Exception:
             pass
+
+
+def factorizer(M, q=0, innerdim=0, loops=30, seed=0):
+    """plo_factorizer: M (Fractions) -> (rc, Alt, CoB, report dict).  rc -1 = inner dimension outside [cols, rows]."""
+    num, den = _numden(M)
+    r, n = num.shape
+    k = innerdim or n
+    an = np.zeros((r, max(k, 1)), dtype=np.int64); ad = np.ones_like(an)
+    cn = np.zeros((max(k, 1), n), dtype=np.int64); cd = np.ones_like(cn)
+    rep = np.zeros(8, dtype=np.uint64)
+    f = lib().plo_factorizer
+    f.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 5
+    rc = f(q, r, n, _ptr(num), _ptr(den), innerdim, loops, seed, _ptr(an), _ptr(ad), _ptr(cn), _ptr(cd), _ptr(rep))
+    if not (rc == -1 and lib().plo_last_error().startswith(b"Fail: inner dimension")):  # the reference's own -1 (:937-942) vs PLO_E_ARG
+        _check(rc)
+    report = dict(initial=tuple(int(v) for v in rep[:3]), final=tuple(int(v) for v in rep[3:6]),
+                  index=None if int(rep[6]) == NO_INDEX else int(rep[6]), consistent=bool(rep[7]))
+    return rc, _fractions(an, ad), _fractions(cn, cd), report

@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include "../plo_device.cuh"
+#include "factor_host.hpp"
 #include "matrix_io.hpp"
 #include "slp.hpp"
 #include "sparsify_host.hpp"
@@ -151,6 +152,77 @@ int mmcheck_dense(uint64_t modulus, uint64_t seed, int batch, const Dense<QField
 
 }  // namespace
 
+// Factorizer  include/plinopt_sparsify.inl:924-990.  F = field of the search (Q or Z/qZ).
+template <class F>
+static int run_factorizer(const F& f, const char* const* primes_unused, int rows, int cols, const int64_t* num, const int64_t* den, int innerdim,
+                          uint64_t loops, uint64_t seed, int64_t* alt_num, int64_t* alt_den, int64_t* cob_num, int64_t* cob_den, uint64_t* report) {
+  (void)primes_unused;
+  typedef Dense<F> Mat;
+  const size_t r = (size_t)rows, n = (size_t)cols;
+  const size_t k = innerdim == 0 ? n : (size_t)innerdim;
+  if (k > r || k < n) {  // :936-942
+    plo::set_error("Fail: inner dimension has to be between %d and %d.", cols, rows);
+    return -1;
+  }
+  const Mat M = load(f, r, n, num, den);
+  FactorHost<F> fh(f);
+  Sparsifier<F> la(f, nullptr);
+  Mat Alt(f, r, k), CoB(f, k, n);
+  const auto sc = fh.nonzeroes(M);
+  Tricounter nbops{sc.first, sc.second, n};  // "Start with M and Identity" :958
+  uint64_t windex = PLO_NO_INDEX;
+  if (r == n) {  // :945-951 identity factorization
+    CoB = M;
+    for (size_t i = 0; i < r; ++i) Alt.at(i, i) = f.one();
+  } else {
+    for (size_t i = 0; i < r; ++i) for (size_t j = 0; j < n; ++j) Alt.at(i, j) = M.at(i, j);  // sparse2sparse(Alt, M) :953
+    for (size_t i = 0; i < n; ++i) CoB.at(i, i) = f.one();
+    if (la.rank(M) != n) { plo::set_error("plo_factorizer: the matrix has not full column rank (backSolver precondition, :754)"); return PLO_E_ARG; }
+    // modulus of the device search: q itself, or a 31-bit prime for rational input (scores are re-derived exactly below)
+    const uint32_t qprimes[3] = {2147483647u, 2147483629u, 2147483587u};
+    const int tries = F::modular ? 1 : 3;
+    bool done = false;
+    for (int attempt = 0; attempt < tries && !done; ++attempt) {
+      const uint32_t p = F::modular ? (uint32_t)f.characteristic() : qprimes[attempt];
+      ZpField Z((int64_t)p);
+      std::vector<uint32_t> res(r * n);
+      bool invertible = true;
+      for (size_t e = 0; e < r * n && invertible; ++e) {
+        const int64_t d = den ? den[e] : 1;
+        if (Z.canon(d) == 0) { invertible = false; break; }
+        res[e] = (uint32_t)Z.div(Z.canon(num[e]), Z.canon(d));
+      }
+      if (!invertible) {
+        if (F::modular) { plo::set_error("plo_factorizer: a denominator is not invertible modulo %u", p); return PLO_E_ARG; }
+        continue;
+      }
+      plo_factor_best best;
+      const int rc = plo_factor_sweep(p, rows, cols, (int)k, res.data(), seed, 0, loops, &best, nullptr);
+      if (rc) return rc;
+      done = true;
+      if (best.index == PLO_NO_INDEX) break;
+      const Tricounter gpu{best.nnz_alt, best.nno_alt, best.nnz_cob};
+      if (!tricOpCount(gpu, nbops)) break;  // nothing beats M = M.I  (:968)
+      std::vector<int32_t> order32(r);
+      plo_factor_decode(rows, seed, best.index, order32.data());
+      Mat lAlt, lCoB;
+      Tricounter exact{0, 0, 0};
+      const bool ok = fh.backSolver(lCoB, lAlt, M, k, std::vector<int>(order32.begin(), order32.end()), exact);
+      if (!ok || exact != gpu) { done = false; continue; }  // a residue vanished modulo p by accident: search again with another prime
+      nbops = exact; Alt = lAlt; CoB = lCoB; windex = best.index;
+    }
+    if (!done) { plo::set_error("plo_factorizer: the modular scores disagreed with the exact ones for every prime tried"); return PLO_E_RANGE; }
+  }
+  store(Alt, alt_num, alt_den);
+  store(CoB, cob_num, cob_den);
+  if (report) {
+    report[0] = sc.first; report[1] = sc.second; report[2] = n;
+    report[3] = nbops[0]; report[4] = nbops[1]; report[5] = nbops[2];
+    report[6] = windex; report[7] = la.consistency(M, Alt, CoB) ? 1 : 0;
+  }
+  return PLO_OK;
+}
+
 extern "C" {
 
 void plo_LRP2MM(int Lcols, int Rcols, int Prows, int* m, int* k, int* n) {
@@ -279,6 +351,23 @@ int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int
     return PLO_OK;
   } catch (const RangeError& e) {
     plo::set_error("plo_orbiter: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
+int plo_factorizer(uint64_t q, int rows, int cols, const int64_t* num, const int64_t* den, int innerdim, uint64_t loops, uint64_t seed,
+                   int64_t* alt_num, int64_t* alt_den, int64_t* cob_num, int64_t* cob_den, uint64_t* report) {
+  if (!num || !alt_num || !cob_num || rows < 1 || cols < 1 || innerdim < 0) { plo::set_error("plo_factorizer: bad argument"); return PLO_E_ARG; }
+  if (cols > 32 && rows != cols) { plo::set_error("plo_factorizer: more than 32 columns are not supported by the device search"); return PLO_E_SHAPE; }
+  try {
+    if (q == 0) { QField Q; return run_factorizer(Q, nullptr, rows, cols, num, den, innerdim, loops, seed, alt_num, alt_den, cob_num, cob_den, report); }
+    uint64_t p = q;
+    while ((p % 2) == 0) p >>= 1;
+    if (p < 3 || p >= (1ull << 31) || !is_prime(p)) { plo::set_error("plo_factorizer: the modulus must be an odd prime below 2^31"); return PLO_E_ARG; }
+    ZpField Z((int64_t)p);
+    return run_factorizer(Z, nullptr, rows, cols, num, den, innerdim, loops, seed, alt_num, alt_den, cob_num, cob_den, report);
+  } catch (const RangeError& e) {
+    plo::set_error("plo_factorizer: %s", e.what());
     return PLO_E_RANGE;
   }
 }

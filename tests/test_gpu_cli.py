@@ -61,3 +61,23 @@ def test_mmchecker_cli_exit_codes(capi, tmp_path):
     assert r.returncode == 1 and "ERROR, not a 2x2x2 MM algorithm" in r.stderr
     w = write_triple(tmp_path, "3x3x3_23_58")
     assert run([s[0], w[1], s[2]]).returncode == 2
+
+
+def test_factorizer_cli(capi, tmp_path):
+    """src/factorizer.cpp:139-206 flags; CoB on stdout (-S parses back), Alt + SUCCESS line on stderr, -k outside range -> -1."""
+    M = O.dense_fractions("4x4x4_48_rational_L")
+    f = tmp_path / "m.sms"
+    hm.write_sms(M, str(f))
+    exe = os.path.join(BIN, "factorizer")
+    p = subprocess.run([exe, "-S", "-O", "300", "-s", "99", str(f)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "# [FCTZ] Initial profile:" in p.stderr and "SUCCESS: consistent factorization!" in p.stderr and "48x16 by 16x16" in p.stderr
+    CoB = hm.read_sms(p.stdout.splitlines())
+    ref = O.factor_sweep(M, 16, 99, 0, 300, matrices=True)
+    assert CoB == ref["cob"]
+    p = subprocess.run([exe, "-k", "20", "-O", "100", "-q", "513083", str(f)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "48x20 by 20x16" in p.stderr and "SUCCESS" in p.stderr
+    p = subprocess.run([exe, "-V", "1", "-c", "5", "-O", "100", str(f)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "SUCCESS: consistent factorization!" in p.stderr
+    p = subprocess.run([exe, "-k", "5", str(f)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 255 and "inner dimension has to be between 16 and 48" in p.stderr

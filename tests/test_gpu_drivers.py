@@ -100,3 +100,38 @@ def test_mmchecker_driver(capi):
     assert capi.mmchecker(L, R, P, batch=64)[0] == 0
     assert capi.mmchecker(L, R[:-1], P)[0] == 2
     assert capi.mmchecker(L, [row[:-1] for row in R], P)[0] == 3
+
+
+@pytest.mark.parametrize("name,k,q", [("2x2x2_7_Winograd_L", 0, 0), ("4x4x4_48_rational_L", 0, 0), ("4x4x4_48_rational_R", 20, 0),
+                                      ("3x4x7_63_rational_R", 0, 0), ("3x3x3_23_58_L", 12, 0), ("4x4x4_48_rational_L", 0, 513083)])
+def test_factorizer_matches_oracle_pipeline(capi, name, k, q):
+    """plo_factorizer (Factorizer, plinopt_sparsify.inl:924-990): same winner, same Alt and CoB as the oracle's exact sweep
+    over the same candidates, M == Alt.CoB (consistency :871-907), never worse than the trivial M = M.I (:958)."""
+    M = O.dense_fractions(name)
+    r, n = len(M), len(M[0])
+    kk = k or n
+    loops = 400
+    rc, Alt, CoB, rep = capi.factorizer(M, q=q, innerdim=k, loops=loops, seed=99)
+    assert rc == 0 and rep["consistent"]
+    ref = O.factor_sweep(M, kk, 99, 0, loops, p=q, matrices=True)
+    init = (sum(1 for row in M for v in row if v != 0), sum(1 for row in M for v in row if v != 0 and abs(v) != 1), n)
+    if q == 0:
+        assert rep["initial"] == init
+    if ref["best"][:3] < rep["initial"]:
+        assert rep["index"] == ref["best"][3] and rep["final"] == ref["best"][:3]
+        assert Alt == ref["alt"] and CoB == ref["cob"]
+    else:
+        assert rep["index"] is None and rep["final"] == rep["initial"]
+    if q == 0:
+        assert [[sum(Alt[i][t] * CoB[t][j] for t in range(kk)) for j in range(n)] for i in range(r)] == M
+
+
+def test_factorizer_error_codes(capi):
+    M = O.dense_fractions("2x2x2_7_Winograd_L")
+    assert capi.factorizer(M, innerdim=3)[0] == -1 and capi.factorizer(M, innerdim=8)[0] == -1  # :936-942
+    sq = [row[:] for row in M[:4]]
+    rc, Alt, CoB, rep = capi.factorizer(sq)  # square input: identity factorization (:945-951)
+    assert rc == 0 and CoB == sq and Alt == [[O.Fraction(int(i == j)) for j in range(4)] for i in range(4)]
+    dep = [row[:3] + [row[0]] for row in M]
+    with pytest.raises(capi.PloError):
+        capi.factorizer(dep)  # not full column rank: backSolver's precondition
