@@ -205,6 +205,27 @@ int plo_factor_plan_launches(const plo_factor_plan* plan);
 void plo_factor_plan_destroy(plo_factor_plan* plan);
 
 /* ---------------------------------------------------------------------------
+ * dependency `Explore`  (SURVEY.md section 8 row f3).
+ * Replaces the recursive enumeration of src/dependency.cpp:73-100 (driver Depender :106-169):
+ * for every start row i and every choice of 1 <= d <= level-1 further rows i < q_1 < .. < q_d with
+ * coefficients C[v_1..v_d], test W = base[i] + sum_t prod[q_t][v_t] for being zero (pos = -1) or having
+ * exactly one non-zero coordinate (pos = that coordinate).  base (r x n) = the rows of M, prod
+ * (r x c x n) = C[v].M[q], both in the field: residues mod p (p > 0) or integers scaled by a common
+ * denominator (p == 0, |entries| <= 2^60).  Hits come back in the reference's depth-first order
+ * (a combination before its extensions); at most max_hits are stored, *nhits is the total found,
+ * *ncand the number of combinations tested.
+ * ------------------------------------------------------------------------ */
+typedef struct plo_dep_hit {
+  int32_t depth;    /* number of added rows d */
+  int32_t pos;      /* -1: zero vector; else the single non-zero coordinate */
+  int32_t rows[5];  /* i, q_1 .. q_d ; -1 beyond */
+  int32_t coefs[5]; /* -1 (the start row has coefficient one), v_1 .. v_d ; -1 beyond */
+} plo_dep_hit;
+
+int plo_dependency_explore(uint32_t p, int r, int n, int c, int level, const int64_t* base, const int64_t* prod,
+                           uint64_t max_hits, plo_dep_hit* hits, uint64_t* nhits, uint64_t* ncand);
+
+/* ---------------------------------------------------------------------------
  * Roofline denominators that MEASURED_PEAKS.json does not hold: register-
  * resident unrolled IMAD / DFMA / (ISETP+IADD) loops over all SMs, CUDA-event
  * timed, best of `reps`.  Results in operations per second.
@@ -263,6 +284,16 @@ int plo_mmchecker(uint64_t modulus, uint64_t seed, int batch, int Lrows, int Lco
  * winning candidate (PLO_NO_INDEX: the trivial factorisation was kept), consistency M == Alt.CoB (:871-907). */
 int plo_factorizer(uint64_t q, int rows, int cols, const int64_t* num, const int64_t* den, int innerdim, uint64_t loops,
                    uint64_t seed, int64_t* alt_num, int64_t* alt_den, int64_t* cob_num, int64_t* cob_den, uint64_t* report);
+
+/* Depender  src/dependency.cpp:106-169: coefficient list ({1,-1} + user values + numerators and denominators of
+ * the entries + 2,3,.., truncated to maxnumcoeff, images in the field, :118-146), then Explore (plo_dependency_explore)
+ * with `level` monomials at most.  q == 0: over Q (exact, scaled integers); q > 0: over Z/qZ, q prime.
+ * hits/nhits/ncand as in plo_dependency_explore; text (may be NULL): the reference's stdout, one line per stored hit
+ * ("+o3-o5*2;" / "-i7+o3...;" showOut/showLC :47-71), NUL-terminated, *text_len = full length.
+ * coef_num/coef_den (may be NULL, maxnumcoeff entries): the coefficient list used; *ncoef its length. */
+int plo_depender(uint64_t q, int rows, int cols, const int64_t* num, const int64_t* den, int nuser, const int64_t* user_num,
+                 const int64_t* user_den, int maxnumcoeff, int level, uint64_t max_hits, plo_dep_hit* hits, uint64_t* nhits,
+                 uint64_t* ncand, char* text, uint64_t text_cap, uint64_t* text_len, int64_t* coef_num, int64_t* coef_den, int* ncoef);
 
 /* Straight-line program -> matrix: matrixBuilder  include/plinopt_programs.inl:1459-1608 (with the
  * parser :618-686 and parenthesisExpand :1615-1679; driver src/SLPchecker.cpp:22-40, rule

@@ -1210,3 +1210,117 @@ void orc_factor_decode(int r, uint64_t seed, uint64_t index, int32_t* perm) {
   for (int t = 0; t < r; ++t) perm[t] = o[(size_t)t];
 }
 }  // extern "C"
+
+// =============================================================================
+// dependency  (src/dependency.cpp): literal restatement of Explore and of the
+// coefficient list of Depender.  Deterministic in the reference (no seeds): the
+// GPU path must return the same hits in the same order.
+// =============================================================================
+namespace orc {
+struct DepHit { int depth, pos; int rows[5], coefs[5]; };
+
+// src/dependency.cpp:20-43
+template <class F> static bool depIsZero(const F& f, const std::vector<typename F::E>& v) { for (const auto& e : v) if (!f.isZero(e)) return false; return true; }
+template <class F> static int depIsCano(const F& f, const std::vector<typename F::E>& v) {
+  int loc = -1;
+  for (size_t i = 0; i < v.size(); ++i) if (!f.isZero(v[i])) { if (loc != -1) return -1; loc = (int)i; }
+  return loc;
+}
+// src/dependency.cpp:73-100 (LC as (row, coefficient index); hits in print order)
+template <class F>
+static void Explore(const F& f, std::vector<DepHit>& hits, uint64_t& ncand, std::vector<std::pair<int, int>>& LC, std::vector<typename F::E>& W,
+                    const Mat<F>& M, size_t m, const std::vector<typename F::E>& Coeffs, size_t level) {
+  if (level == 0) return;
+  for (size_t q = m + 1; q < M.r; ++q) {
+    typename F::E prevv = f.zero(), currv = f.zero();
+    for (size_t v = 0; v < Coeffs.size(); ++v) {
+      currv = f.sub(Coeffs[v], prevv); prevv = Coeffs[v];
+      LC.emplace_back((int)q, (int)v);
+      for (size_t j = 0; j < M.c; ++j) if (!f.isZero(M(q, j))) W[j] = f.add(W[j], f.mul(currv, M(q, j)));  // axpyin
+      ++ncand;
+      int pos = -2;
+      if (depIsZero(f, W)) pos = -1;
+      else { const int i = depIsCano(f, W); if (i != -1) pos = i; }
+      if (pos != -2) {
+        DepHit h; h.depth = (int)LC.size() - 1; h.pos = pos;
+        for (int t = 0; t < 5; ++t) { h.rows[t] = -1; h.coefs[t] = -1; }
+        for (size_t t = 0; t < LC.size() && t < 5; ++t) { h.rows[t] = LC[t].first; h.coefs[t] = LC[t].second; }
+        hits.push_back(h);
+      }
+      Explore(f, hits, ncand, LC, W, M, q, Coeffs, level - 1);
+      LC.pop_back();
+    }
+    for (size_t j = 0; j < M.c; ++j) if (!f.isZero(M(q, j))) W[j] = f.sub(W[j], f.mul(prevv, M(q, j)));  // maxpyin
+  }
+}
+
+// src/dependency.cpp:118-143 coefficient list
+static std::vector<Rat> depCoeffsQ(const Mat<QField>& B, const std::vector<Rat>& user, size_t maxnumcoeff) {
+  QField Q;
+  std::vector<Rat> C{Q.one(), Q.mone()};
+  C.insert(C.end(), user.begin(), user.end());
+  auto aug = [&](const Rat& r) {
+    for (const Rat& e : C) if (Q.repEq(e, r)) return;
+    C.push_back(r); C.push_back(Q.neg(r)); const Rat t = Q.inv(r); C.push_back(t); C.push_back(Q.neg(t));
+  };
+  for (size_t e = 0; e < B.a.size(); ++e) if (B.a[e].n != 0) { aug(Rat{B.a[e].n, 1}); aug(Rat{B.a[e].d, 1}); }
+  for (int64_t i = 2; C.size() < maxnumcoeff; ++i) aug(Rat{i, 1});
+  if (C.size() > maxnumcoeff) C.resize(maxnumcoeff);
+  return C;
+}
+
+template <class F>
+static int depender_impl(const F& f, int rows, int cols, const int64_t* num, const int64_t* den, int nuser, const int64_t* un, const int64_t* ud,
+                         int maxnumcoeff, int level, uint64_t max_hits, int32_t* hits_out /* 12 ints per hit */, uint64_t* nhits, uint64_t* ncand,
+                         int64_t* coef_num, int64_t* coef_den, int* ncoef) {
+  g_overflow = 0;
+  QField Q;
+  const Mat<QField> B = Loader<QField>::load(Q, rows, cols, num, den);
+  const Mat<F> M = Loader<F>::load(f, rows, cols, num, den);
+  std::vector<Rat> user;
+  for (int u = 0; u < nuser; ++u) user.push_back(mkrat(un[u], ud ? ud[u] : 1));
+  const std::vector<Rat> CQ = depCoeffsQ(B, user, (size_t)maxnumcoeff);
+  std::vector<typename F::E> C;
+  {
+    Mat<F> tmp(f, 1, 1);
+    for (const Rat& e : CQ) {
+      const int64_t n1 = e.n, d1 = e.d;
+      const Mat<F> one = Loader<F>::load(f, 1, 1, &n1, &d1);
+      if (g_overflow) { g_overflow = 0; continue; }  // denominator not invertible mod p
+      const typename F::E x = one.a[0];
+      if (f.isZero(x)) continue;
+      bool seen = false;
+      for (const auto& y : C) if (f.repEq(y, x)) seen = true;
+      if (!seen) C.push_back(x);
+    }
+  }
+  *ncoef = (int)C.size();
+  if (coef_num) { Mat<F> t(f, 1, C.size()); t.a = C; Loader<F>::store(t, coef_num, coef_den); }
+  std::vector<DepHit> hits;
+  uint64_t cand = 0;
+  std::vector<std::pair<int, int>> LC;
+  std::vector<typename F::E> W((size_t)cols, f.zero());
+  for (size_t i = 0; i < M.r; ++i) {  // :153-160
+    LC.emplace_back((int)i, -1);
+    for (size_t j = 0; j < M.c; ++j) W[j] = M(i, j);
+    if (level >= 1) Explore(f, hits, cand, LC, W, M, i, C, (size_t)level - 1);
+    for (size_t j = 0; j < M.c; ++j) W[j] = f.zero();
+    LC.pop_back();
+  }
+  *nhits = hits.size(); *ncand = cand;
+  for (uint64_t h = 0; h < hits.size() && h < max_hits; ++h) {
+    int32_t* o = hits_out + h * 12;
+    o[0] = hits[h].depth; o[1] = hits[h].pos;
+    for (int t = 0; t < 5; ++t) { o[2 + t] = hits[h].rows[t]; o[7 + t] = hits[h].coefs[t]; }
+  }
+  return g_overflow ? -g_overflow : 0;
+}
+}  // namespace orc
+
+extern "C" int orc_depender(int64_t p, int rows, int cols, const int64_t* num, const int64_t* den, int nuser, const int64_t* un, const int64_t* ud,
+                            int maxnumcoeff, int level, uint64_t max_hits, int32_t* hits_out, uint64_t* nhits, uint64_t* ncand,
+                            int64_t* coef_num, int64_t* coef_den, int* ncoef) {
+  if (p == 0) { QField f; return depender_impl(f, rows, cols, num, den, nuser, un, ud, maxnumcoeff, level, max_hits, hits_out, nhits, ncand, coef_num, coef_den, ncoef); }
+  ZpField f{p};
+  return depender_impl(f, rows, cols, num, den, nuser, un, ud, maxnumcoeff, level, max_hits, hits_out, nhits, ncand, coef_num, coef_den, ncoef);
+}

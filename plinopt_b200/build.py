@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libplinopt_b200.so")
-SOURCES = ["common.cu", "orbit_sweep.cu", "lincomb_search.cu", "mmcheck.cu", "factor_sweep.cu", "peaks.cu", "host/host_api.cpp"]
+SOURCES = ["common.cu", "orbit_sweep.cu", "lincomb_search.cu", "mmcheck.cu", "factor_sweep.cu", "dependency_explore.cu", "peaks.cu", "host/host_api.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
 
@@ -24,7 +24,7 @@ def _nvcc():
 
 
 def _deps(src):
-    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "plo_device.cuh"), os.path.join(CSRC, "host", "exact.hpp"), os.path.join(CSRC, "host", "sparsify_host.hpp"), os.path.join(CSRC, "host", "matrix_io.hpp"), os.path.join(CSRC, "host", "slp.hpp"), os.path.join(CSRC, "host", "factor_host.hpp"),
+    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "plo_device.cuh"), os.path.join(CSRC, "host", "exact.hpp"), os.path.join(CSRC, "host", "sparsify_host.hpp"), os.path.join(CSRC, "host", "matrix_io.hpp"), os.path.join(CSRC, "host", "slp.hpp"), os.path.join(CSRC, "host", "factor_host.hpp"), os.path.join(CSRC, "host", "dependency_host.hpp"),
             os.path.join(os.path.dirname(HERE), "include", "plinopt_b200.h"), os.path.abspath(__file__)]
     return max(os.path.getmtime(d) for d in deps if os.path.exists(d))
 
@@ -66,7 +66,7 @@ def build_library(force=False, verbose=False):
 
 CLI_DIR = os.path.join(HERE, "cli")
 BIN_DIR = os.path.join(os.path.dirname(HERE), "bin")
-CLIS = ["sparsifier", "orbiter", "MMchecker", "factorizer"]
+CLIS = ["sparsifier", "orbiter", "MMchecker", "factorizer", "dependency"]
 
 
 def build_clis(force=False):

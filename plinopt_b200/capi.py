@@ -30,7 +30,7 @@ SYMBOLS = [
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
     "plo_sparsifier", "plo_orbiter", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
     "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
-    "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer",
+    "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender",
 ]
 
 
@@ -491,3 +491,31 @@ def factorizer(M, q=0, innerdim=0, loops=30, seed=0):
     report = dict(initial=tuple(int(v) for v in rep[:3]), final=tuple(int(v) for v in rep[3:6]),
                   index=None if int(rep[6]) == NO_INDEX else int(rep[6]), consistent=bool(rep[7]))
     return rc, _fractions(an, ad), _fractions(cn, cd), report
+
+
+# --------------------------------------------------------------------------
+# dependency Explore
+# --------------------------------------------------------------------------
+class DepHit(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("pos", C.c_int32), ("rows", C.c_int32 * 5), ("coefs", C.c_int32 * 5)]
+
+
+def depender(M, level, maxnumcoeff=11, q=0, user=(), max_hits=1 << 20, text_cap=1 << 24):
+    """plo_depender: returns dict(hits=[(depth, pos, rows, coefs)], nhits, ncand, coeffs, text)."""
+    from fractions import Fraction
+    num, den = _numden(M)
+    r, n = num.shape
+    un = np.array([Fraction(u).numerator for u in user], dtype=np.int64); ud = np.array([Fraction(u).denominator for u in user], dtype=np.int64)
+    hits = (DepHit * max_hits)()
+    nh, nc, tl, ncoef = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+    text = C.create_string_buffer(text_cap)
+    cn = np.zeros(maxnumcoeff, dtype=np.int64); cd = np.ones(maxnumcoeff, dtype=np.int64)
+    f = lib().plo_depender
+    f.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p,
+                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    _check(f(q, r, n, _ptr(num), _ptr(den), len(user), _ptr(un) if len(user) else None, _ptr(ud) if len(user) else None, maxnumcoeff, level,
+             max_hits, C.cast(hits, C.c_void_p), C.byref(nh), C.byref(nc), text, text_cap, C.byref(tl), _ptr(cn), _ptr(cd), C.byref(ncoef)))
+    k = min(nh.value, max_hits)
+    out = [(h.depth, h.pos, tuple(h.rows), tuple(h.coefs)) for h in hits[:k]]
+    coeffs = [Fraction(int(a), int(b)) for a, b in zip(cn[:ncoef.value], cd[:ncoef.value])]
+    return dict(hits=out, nhits=nh.value, ncand=nc.value, coeffs=coeffs, text=text.value.decode())

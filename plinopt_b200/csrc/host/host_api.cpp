@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include "../plo_device.cuh"
+#include "dependency_host.hpp"
 #include "factor_host.hpp"
 #include "matrix_io.hpp"
 #include "slp.hpp"
@@ -223,6 +224,65 @@ static int run_factorizer(const F& f, const char* const* primes_unused, int rows
   return PLO_OK;
 }
 
+static inline int64_t store_one(const ZpField& f, int64_t e) { return f.canon(e); }
+static inline int64_t store_one(const QField&, const Rat&) { return 0; }
+static inline int64_t num_of(const Rat& e) { return e.num; }
+static inline int64_t den_of(const Rat& e) { return e.den; }
+static inline int64_t num_of(int64_t e) { return e; }
+static inline int64_t den_of(int64_t) { return 1; }
+// Depender  src/dependency.cpp:106-169 over the field F.
+template <class F>
+static int run_depender(const F& f, const Dense<QField>& B, const std::vector<Rat>& user, size_t maxnumcoeff, int level, uint64_t max_hits,
+                        plo_dep_hit* hits, uint64_t* nhits, uint64_t* ncand, char* text, size_t text_cap, size_t* text_len,
+                        int64_t* coef_num, int64_t* coef_den, int* ncoef) {
+  typedef typename F::Elt Elt;
+  const size_t r = B.rows, n = B.cols;
+  Dense<F> M(f, r, n);
+  for (size_t e = 0; e < B.v.size(); ++e) M.v[e] = f.from_ratio(B.v[e].num, B.v[e].den);
+  const std::vector<Elt> C = field_coefficients(f, dependency_coefficients(B, user, maxnumcoeff));
+  const size_t c = C.size();
+  if (ncoef) *ncoef = (int)c;
+  if (coef_num) {
+    Dense<F> tmp(f, 1, c);
+    for (size_t v = 0; v < c; ++v) tmp.v[v] = C[v];
+    store(tmp, coef_num, coef_den);
+  }
+  if (c == 0 || level < 2) { if (nhits) *nhits = 0; if (ncand) *ncand = 0; if (text_len) *text_len = 0; return PLO_OK; }
+  // tables in the field: residues, or integers scaled by the common denominator D
+  std::vector<int64_t> base(r * n), prod(r * c * n);
+  uint32_t p = 0;
+  if (F::modular) {
+    p = (uint32_t)f.characteristic();
+    for (size_t e = 0; e < r * n; ++e) base[e] = store_one(f, M.v[e]);
+    for (size_t q = 0; q < r; ++q) for (size_t v = 0; v < c; ++v) for (size_t j = 0; j < n; ++j) prod[(q * c + v) * n + j] = store_one(f, f.mul(C[v], M.at(q, j)));
+  } else {
+    std::vector<Elt> pe(r * c * n);
+    for (size_t q = 0; q < r; ++q) for (size_t v = 0; v < c; ++v) for (size_t j = 0; j < n; ++j) pe[(q * c + v) * n + j] = f.mul(C[v], M.at(q, j));
+    wide D = 1;
+    auto fold = [&D](int64_t den) { D = D / wgcd(D, den) * den; if (D > ((wide)1 << 60)) throw RangeError("common denominator exceeds 60 bits"); };
+    for (const Elt& e : M.v) fold(den_of(e));
+    for (const Elt& e : pe) fold(den_of(e));
+    auto scale = [&D](const Elt& e) { const wide v = (wide)num_of(e) * (D / den_of(e)); if (wabs(v) > ((wide)1 << 60)) throw RangeError("scaled entry exceeds 60 bits"); return (int64_t)v; };
+    for (size_t e = 0; e < r * n; ++e) base[e] = scale(M.v[e]);
+    for (size_t e = 0; e < pe.size(); ++e) prod[e] = scale(pe[e]);
+  }
+  uint64_t found = 0;
+  const int rc = plo_dependency_explore(p, (int)r, (int)n, (int)c, level, base.data(), prod.data(), max_hits, hits, &found, ncand);
+  if (rc) return rc;
+  if (nhits) *nhits = found;
+  if (text) {
+    DependencyHost<F> dh(f);
+    std::string all;
+    const uint64_t stored = found < max_hits ? found : max_hits;
+    for (uint64_t h = 0; h < stored; ++h) { all += dh.line(M, C, hits[h]); all += '\n'; }
+    const size_t len = all.size() < text_cap ? all.size() : (text_cap ? text_cap - 1 : 0);
+    memcpy(text, all.data(), len);
+    if (text_cap) text[len] = 0;
+    if (text_len) *text_len = all.size();
+  }
+  return PLO_OK;
+}
+
 extern "C" {
 
 void plo_LRP2MM(int Lcols, int Rcols, int Prows, int* m, int* k, int* n) {
@@ -368,6 +428,34 @@ int plo_factorizer(uint64_t q, int rows, int cols, const int64_t* num, const int
     return run_factorizer(Z, nullptr, rows, cols, num, den, innerdim, loops, seed, alt_num, alt_den, cob_num, cob_den, report);
   } catch (const RangeError& e) {
     plo::set_error("plo_factorizer: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
+int plo_depender(uint64_t q, int rows, int cols, const int64_t* num, const int64_t* den, int nuser, const int64_t* user_num,
+                 const int64_t* user_den, int maxnumcoeff, int level, uint64_t max_hits, plo_dep_hit* hits, uint64_t* nhits,
+                 uint64_t* ncand, char* text, uint64_t text_cap, uint64_t* text_len, int64_t* coef_num, int64_t* coef_den, int* ncoef) {
+  if (!num || rows < 1 || cols < 1 || maxnumcoeff < 1 || level < 1 || (max_hits && !hits) || (nuser > 0 && !user_num)) {
+    plo::set_error("plo_depender: bad argument");
+    return PLO_E_ARG;
+  }
+  try {
+    QField Q;
+    const Dense<QField> B = load(Q, (size_t)rows, (size_t)cols, num, den);
+    std::vector<Rat> user;
+    for (int u = 0; u < nuser; ++u) user.push_back(Rat::make(user_num[u], user_den ? user_den[u] : 1));
+    size_t tl = 0;
+    int rc;
+    if (q == 0) rc = run_depender(Q, B, user, (size_t)maxnumcoeff, level, max_hits, hits, nhits, ncand, text, (size_t)text_cap, &tl, coef_num, coef_den, ncoef);
+    else {
+      if (q >= (1ull << 32) || !is_prime(q)) { plo::set_error("plo_depender: the modulus must be a prime below 2^32"); return PLO_E_ARG; }
+      ZpField Z((int64_t)q);
+      rc = run_depender(Z, B, user, (size_t)maxnumcoeff, level, max_hits, hits, nhits, ncand, text, (size_t)text_cap, &tl, coef_num, coef_den, ncoef);
+    }
+    if (text_len) *text_len = tl;
+    return rc;
+  } catch (const RangeError& e) {
+    plo::set_error("plo_depender: %s", e.what());
     return PLO_E_RANGE;
   }
 }

@@ -294,3 +294,24 @@ def factor_decode(r, seed, index):
     f.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
     f(r, seed, index, perm.ctypes.data)
     return perm
+
+
+def depender(M, level, maxnumcoeff=11, p=0, user=(), max_hits=1 << 20):
+    """dependency (src/dependency.cpp:106-169): returns dict(hits=[(depth, pos, rows, coefs)], nhits, ncand, coeffs)."""
+    r, n = len(M), len(M[0])
+    num, den = numden(M)
+    un = np.array([Fraction(u).numerator for u in user], dtype=np.int64); ud = np.array([Fraction(u).denominator for u in user], dtype=np.int64)
+    hits = np.zeros((max_hits, 12), dtype=np.int32)
+    nh, nc, ncoef = C.c_uint64(), C.c_uint64(), C.c_int()
+    cn = np.zeros(maxnumcoeff, dtype=np.int64); cd = np.ones(maxnumcoeff, dtype=np.int64)
+    f = lib().orc_depender
+    f.restype = C.c_int
+    f.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p,
+                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    rc = f(p, r, n, num.ctypes.data, den.ctypes.data, len(user), un.ctypes.data if len(user) else None, ud.ctypes.data if len(user) else None,
+           maxnumcoeff, level, max_hits, hits.ctypes.data, C.byref(nh), C.byref(nc), cn.ctypes.data, cd.ctypes.data, C.byref(ncoef))
+    assert rc == 0, f"oracle overflow ({rc})"
+    k = min(nh.value, max_hits)
+    out = [(int(h[0]), int(h[1]), tuple(int(x) for x in h[2:7]), tuple(int(x) for x in h[7:12])) for h in hits[:k]]
+    coeffs = [Fraction(int(a), int(b)) for a, b in zip(cn[:ncoef.value], cd[:ncoef.value])]
+    return dict(hits=out, nhits=nh.value, ncand=nc.value, coeffs=coeffs)

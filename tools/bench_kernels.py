@@ -98,6 +98,29 @@ def orbit_cases(peaks):
             plan.close()
 
 
+def factor_cases():
+    """Factorizer random restarts (plinopt_sparsify.inl:924-990): candidates (row orders) per second; the oracle's exact
+    rational backSolver on all host threads beside it."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    for stem, x, lg in (("4x4x4_48_rational", "L", 22), ("3x4x7_63_rational", "R", 21), ("3x4x7_63_rational", "L", 22)):
+        M = O.dense_fractions(f"{stem}_{x}")
+        r, n = len(M), len(M[0])
+        A = np.array([[(v.numerator % P31) * pow(v.denominator % P31, -1, P31) % P31 for v in row] for row in M], dtype=np.uint32)
+        plan = capi.FactorPlan(P31, A, n, 0x504C494E4F505431)
+        B = 1 << lg
+        ms = time_plan(lambda s: plan.run(0, B, s), 3)
+        best = plan.result()
+        plan.close()
+        t0 = time.perf_counter()
+        cnt = 4000
+        ref = O.factor_sweep(M, n, 0x504C494E4F505431, 0, cnt, table=False)
+        cpu = cnt / (time.perf_counter() - t0)
+        print(json.dumps({"kernel": f"factor_sweep_kernel<{(n + 3) // 4 * 4}>", "case": f"{stem}_{x} ({r}x{n}), k={n}, 2^{lg} row orders", "ms": ms,
+                          "candidates_per_s": B / ms * 1e3, "best": best, "cpu_oracle_candidates_per_s": cpu,
+                          "cpu_threads": O.lib().orc_num_threads(), "cpu_sample": cnt, "cpu_best_of_sample": ref["best"]}))
+
+
 def mmcheck_case():
     rng = np.random.default_rng(0)
     m = k = n = 32
@@ -134,7 +157,11 @@ if __name__ == "__main__":
     if "--orbit-only" in sys.argv:
         orbit_cases(peaks)
         sys.exit(0)
+    if "--factor-only" in sys.argv:
+        factor_cases()
+        sys.exit(0)
     if "--mm-only" not in sys.argv:
         lincomb_cases(peaks)
         orbit_cases(peaks)
+        factor_cases()
     mmcheck_case()
