@@ -62,3 +62,21 @@ def allreduce_best(best, measure_nnz=False, device=None):
     t = torch.tensor(pack_local(best, rank, world), dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return pick_global(t.tolist(), world, measure_nnz)
+
+
+def allreduce_factor_best(best, device=None):
+    """Factorizer sweep (plo_factor_sweep) over sharded index ranges: best = (nnz_alt, nno_alt, nnz_cob, index|None).
+    Same single all_reduce(MIN) over world*4 int64 words; lexicographic minimum, lowest index among ties."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return best
+    rank, world = dist.get_rank(), dist.get_world_size()
+    words = [INT64_MAX] * (world * SLOT)
+    if best is not None and best[3] is not None:
+        words[rank * SLOT:(rank + 1) * SLOT] = [int(v) for v in best]
+    t = torch.tensor(words, dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    rows = [tuple(t[r * SLOT:(r + 1) * SLOT].tolist()) for r in range(world)]
+    rows = [r for r in rows if r[3] != INT64_MAX]
+    return min(rows) if rows else (0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, None)

@@ -45,7 +45,9 @@ def _worker(rank, world, port, q):
     assert lo <= local["index"] < hi
     g = S.allreduce_best(local)
     e = S.allreduce_best(None if rank == 0 else dict(score=3.0, index=999, nnz=1, nno=0))
-    q.put((rank, g, e))
+    f = S.allreduce_factor_best((196, 100, 168, 40 + rank) if rank == 1 else (196, 100, 168, 77))
+    f0 = S.allreduce_factor_best((1, 2, 3, None))
+    q.put((rank, g, e, f, f0))
     dist.destroy_process_group()
 
 
@@ -57,6 +59,7 @@ def test_allreduce_min_with_index_gloo_world2():
     [p.start() for p in ps]
     out = [q.get(timeout=120) for _ in ps]
     [p.join(60) for p in ps]
-    for rank, g, e in out:
+    for rank, g, e, f, f0 in out:
         assert g["index"] == 123 and g["rank"] == 0 and g["score"] == 12.0 and g["nnz"] == 40
         assert e["index"] == 999 and e["rank"] == 1
+        assert f == (196, 100, 168, 41) and f0[3] is None  # tie on the score: lowest index wins; no candidate anywhere

@@ -121,6 +121,28 @@ def factor_cases():
                           "cpu_threads": O.lib().orc_num_threads(), "cpu_sample": cnt, "cpu_best_of_sample": ref["best"]}))
 
 
+def dependency_cases(peaks):
+    """dependency Explore (src/dependency.cpp:73-100): combinations tested per second (one compare per coordinate per
+    combination), the oracle's literal recursion (1 thread, as the reference) on a smaller level beside it."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    for name, level, c, q in (("4x4x4_48_rational_L", 4, 11, 0), ("4x4x4_48_rational_L", 4, 11, 2147483647), ("3x4x7_63_rational_R", 4, 7, 2147483647),
+                              ("3x3x3_23_58_L", 5, 11, 2147483647)):
+        M = O.dense_fractions(name)
+        capi.depender(M, 2, c, q=q)  # warm-up (context, module load)
+        t0 = time.perf_counter()
+        got = capi.depender(M, level, c, q=q, max_hits=1 << 18)
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ref = O.depender(M, level - 1, c, p=q)
+        cpu_dt = time.perf_counter() - t0
+        n = len(M[0])
+        print(json.dumps({"kernel": "dependency_kernel", "case": f"{name} level {level} c={len(got['coeffs'])} " + ("over Q (int64)" if q == 0 else f"mod {q}"),
+                          "combinations": got["ncand"], "hits": got["nhits"], "wall_s_incl_host": dt, "combinations_per_s": got["ncand"] / dt,
+                          "compare_pairs_per_s": got["ncand"] * n / dt, "ialu_pair_peak": peaks["ialu_pairs_per_s"],
+                          "cpu_oracle_combinations_per_s": ref["ncand"] / cpu_dt, "cpu_threads": 1, "cpu_sample": f"level {level - 1}: {ref['ncand']} combinations"}))
+
+
 def mmcheck_case():
     rng = np.random.default_rng(0)
     m = k = n = 32
@@ -157,6 +179,9 @@ if __name__ == "__main__":
     if "--orbit-only" in sys.argv:
         orbit_cases(peaks)
         sys.exit(0)
+    if "--dep-only" in sys.argv:
+        dependency_cases(peaks)
+        sys.exit(0)
     if "--factor-only" in sys.argv:
         factor_cases()
         sys.exit(0)
@@ -164,4 +189,5 @@ if __name__ == "__main__":
         lincomb_cases(peaks)
         orbit_cases(peaks)
         factor_cases()
+        dependency_cases(peaks)
     mmcheck_case()
