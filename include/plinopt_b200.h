@@ -103,8 +103,9 @@ void plo_lincomb_plan_destroy(plo_lincomb_plan* plan);
  * lowest index among ties).
  *
  * L  r x (m*k), R  r x (k*n), P  (m*n) x r, row-major, entries pre-scaled to
- * integers: true matrix = L/denL etc.  (p must be 0 in this version: exact
- * integers.)  Candidate `index` in [lo,hi) is decoded to (U,V,W) by the
+ * integers: true matrix = L/denL etc. (p == 0), or residues in [0,p) with the
+ * denominators ignored (2 <= p < 2^31: `orbiter -m p`, the search runs in Z/pZ,
+ * src/orbiter.cpp:232-234,419-426; sparsity measure only).  Candidate `index` in [lo,hi) is decoded to (U,V,W) by the
  * counter-based decode documented in DESIGN.md (identical on host and device,
  * see plo_orbit_decode).
  * ------------------------------------------------------------------------ */
@@ -128,6 +129,10 @@ uint64_t plo_orbit_space(int m, int k, int n);
 int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int32_t denL,
                     int32_t denR, int32_t denP, int mode, uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* nnz,
                     uint32_t* nno, double* g2);
+
+/* The same table over Z/pZ (residues in, (nnz, nno) per candidate out). */
+int plo_orbit_table_modp(uint32_t p, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int mode,
+                         uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* nnz, uint32_t* nno);
 
 /* Device-resident plan (throughput measurement / multi-GPU sharding). */
 typedef struct plo_orbit_plan plo_orbit_plan;
@@ -273,6 +278,13 @@ int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int
 int plo_mmchecker(uint64_t modulus, uint64_t seed, int batch, int Lrows, int Lcols, int Rrows, int Rcols, int Prows,
                   int Pcols, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
                   const int64_t* Pn, const int64_t* Pd, uint32_t* nnz_nno /* [2], may be NULL */);
+
+/* The same over Z/qZ (`orbiter -m q`, src/orbiter.cpp:419-426): factors of 2 are stripped from q (:421-422), the
+ * matrices are reduced first (:232-234), the search, the acceptance and the final MMchecker run in the field
+ * (sparsity measure, Orbiter<0>).  Outputs are residues. */
+int plo_orbiter_modp(uint64_t q, int mode, uint64_t seed, uint64_t loops, int r, int Lcols, int Rcols, int Prows,
+                     const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd, const int64_t* Pn,
+                     const int64_t* Pd, int64_t* oL, int64_t* oR, int64_t* oP, plo_orbiter_report* rep);
 
 /* Factorizer  include/plinopt_sparsify.inl:924-990  (driver TFactorizer src/factorizer.cpp:28-97 without the
  * optional initial sparsification): M (rows x cols, full column rank) -> Alt (rows x k) . CoB (k x cols),

@@ -25,10 +25,10 @@ SYMBOLS = [
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
-    "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
+    "plo_orbit_table_modp", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
-    "plo_sparsifier", "plo_orbiter", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
+    "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
     "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
     "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender",
 ]
@@ -212,6 +212,18 @@ def orbit_table(mkn, L, R, P, dens, mode, seed, lo, hi):
     return nnz, nno, g2
 
 
+def orbit_table_modp(p, mkn, L, R, P, mode, seed, lo, hi):
+    """Per-candidate (nnz, nno) over Z/pZ; L, R, P hold residues."""
+    m, k, n = mkn
+    L = _i32(L); R = _i32(R); P = _i32(P)
+    cnt = hi - lo
+    nnz = np.zeros(cnt, dtype=np.uint32); nno = np.zeros(cnt, dtype=np.uint32)
+    f = lib().plo_orbit_table_modp
+    f.argtypes = [C.c_uint32] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 2
+    _check(f(p, m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), mode, seed, lo, hi, _ptr(nnz), _ptr(nno)))
+    return nnz, nno
+
+
 class OrbitPlan:
     def __init__(self, mkn, L, R, P, dens, measure, mode, seed):
         m, k, n = mkn
@@ -374,6 +386,20 @@ def orbiter(L, R, P, measure=MEASURE_NNZ, mode=MODE_PHILOX, seed=0, loops=100):
     report = dict(init_nnz=rep.init_nnz, init_nno=rep.init_nno, init_score=rep.init_score, best=_best_tuple(rep.best),
                   improved=bool(rep.improved), mm_verdict=rep.mm_verdict, mkn=(rep.m, rep.k, rep.n))
     return _fractions(outs[0], outs[1]), _fractions(outs[2], outs[3]), _fractions(outs[4], outs[5]), report
+
+
+def orbiter_modp(L, R, P, q, mode=MODE_PHILOX, seed=0, loops=100):
+    """plo_orbiter_modp: returns (Lj, Rg, hP) as residue lists and the report dict."""
+    Ln, Ld = _numden(L); Rn, Rd = _numden(R); Pn, Pd = _numden(P)
+    oL, oR, oP = np.zeros_like(Ln), np.zeros_like(Rn), np.zeros_like(Pn)
+    rep = OrbiterReport()
+    f = lib().plo_orbiter_modp
+    f.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 9 + [C.POINTER(OrbiterReport)]
+    _check(f(q, mode, seed, loops, Ln.shape[0], Ln.shape[1], Rn.shape[1], Pn.shape[0], _ptr(Ln), _ptr(Ld), _ptr(Rn), _ptr(Rd), _ptr(Pn), _ptr(Pd),
+             _ptr(oL), _ptr(oR), _ptr(oP), C.byref(rep)))
+    report = dict(init=(rep.init_nnz, rep.init_nno), best=_best_tuple(rep.best), improved=bool(rep.improved), mm_verdict=rep.mm_verdict,
+                  mkn=(rep.m, rep.k, rep.n))
+    return oL.tolist(), oR.tolist(), oP.tolist(), report
 
 
 def mmchecker(L, R, P, modulus=0, seed=0, batch=32):

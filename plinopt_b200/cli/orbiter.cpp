@@ -3,6 +3,7 @@
 // Flags of the reference are kept; -z/-c (SLP-operation and canonical measures) and -P/-I
 // (polynomial quotient) are out of scope and rejected.  Added: -g (minimise the growth factor G2
 // instead of the sparsity), --seed N, --exhaustive.
+#include <algorithm>
 #include <cstdlib>
 
 #include "cli_common.hpp"
@@ -57,8 +58,15 @@ int main(int argc, char** argv) {
   std::vector<int64_t> oLn(l.num.size()), oLd(l.num.size()), oRn(r.num.size()), oRd(r.num.size()), oPn(p.num.size()), oPd(p.num.size());
   plo_orbiter_report rep;
   cli::Timer timer;
-  const int rc = plo_orbiter(measure, mode, seed, loops, l.rows, l.cols, r.cols, p.rows, l.num.data(), l.den.data(), r.num.data(), r.den.data(), p.num.data(),
-                             p.den.data(), oLn.data(), oLd.data(), oRn.data(), oRd.data(), oPn.data(), oPd.data(), &rep);
+  int rc;
+  if (modulus > 0) {  // Orbiter<0>()(QQ, F, ...): the search runs in Z/pZ (src/orbiter.cpp:419-426)
+    if (measure != PLO_MEASURE_NNZ) { std::cerr << "# \033[1;31m****** ERROR, -g needs the rationals ******\033[0m" << std::endl; return -1; }
+    std::fill(oLd.begin(), oLd.end(), 1); std::fill(oRd.begin(), oRd.end(), 1); std::fill(oPd.begin(), oPd.end(), 1);
+    rc = plo_orbiter_modp(modulus, mode, seed, loops, l.rows, l.cols, r.cols, p.rows, l.num.data(), l.den.data(), r.num.data(), r.den.data(), p.num.data(),
+                          p.den.data(), oLn.data(), oRn.data(), oPn.data(), &rep);
+  } else
+    rc = plo_orbiter(measure, mode, seed, loops, l.rows, l.cols, r.cols, p.rows, l.num.data(), l.den.data(), r.num.data(), r.den.data(), p.num.data(),
+                     p.den.data(), oLn.data(), oLd.data(), oRn.data(), oRd.data(), oPn.data(), oPd.data(), &rep);
   if (rc != PLO_OK) { std::cerr << "# \033[1;31m****** ERROR " << rc << ": " << plo_last_error() << " ******\033[0m" << std::endl; return rc; }
   std::clog << "# Init. ops: " << rep.init_score << ", {" << rep.init_nnz << ',' << rep.init_nno << '}' << std::endl;
   std::clog << "# Search(" << loops << "): " << timer.seconds() << "s" << std::endl;

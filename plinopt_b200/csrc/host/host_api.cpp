@@ -224,6 +224,33 @@ static int run_factorizer(const F& f, const char* const* primes_unused, int rows
   return PLO_OK;
 }
 
+// Orbit action on a triple (src/orbiter.cpp:284-294) without the Kronecker products:
+// row l of L.(U^-1 (x) V) = vec(U^-T A_l V), of R.(V^-T (x) W) = vec(V^-1 B_l W); column l of (U (x) W^-1).P = vec(U C_l W^-T)
+template <class F>
+static void orbit_transform(const F& f, int m, int k, int n, int r, const Dense<F>& L, const Dense<F>& R, const Dense<F>& P,
+                            const std::vector<int32_t>& U, const std::vector<int32_t>& V, const std::vector<int32_t>& W,
+                            Dense<F>& Lj, Dense<F>& Rg, Dense<F>& hP) {
+  Sparsifier<F> la(f, nullptr);
+  auto tomat = [&](const std::vector<int32_t>& a, int s) {
+    Dense<F> M(f, (size_t)s, (size_t)s);
+    for (size_t e = 0; e < a.size(); ++e) M.v[e] = f.from_ratio(a[e], 1);
+    return M;
+  };
+  const Dense<F> Um = tomat(U, m), Vm = tomat(V, k), Wm = tomat(W, n);
+  const Dense<F> iU = la.inverse(Um), iV = la.inverse(Vm), iW = la.inverse(Wm);
+  const Dense<F> iUT = la.transpose(iU), iWT = la.transpose(iW);
+  for (int l = 0; l < r; ++l) {
+    Dense<F> A(f, (size_t)m, (size_t)k), B(f, (size_t)k, (size_t)n), C(f, (size_t)m, (size_t)n);
+    for (int e = 0; e < m * k; ++e) A.v[e] = L.at((size_t)l, (size_t)e);
+    for (int e = 0; e < k * n; ++e) B.v[e] = R.at((size_t)l, (size_t)e);
+    for (int e = 0; e < m * n; ++e) C.v[e] = P.at((size_t)e, (size_t)l);
+    const Dense<F> Y1 = la.mul(la.mul(iUT, A), Vm), Y2 = la.mul(la.mul(iV, B), Wm), Y3 = la.mul(la.mul(Um, C), iWT);
+    for (int e = 0; e < m * k; ++e) Lj.at((size_t)l, (size_t)e) = Y1.v[e];
+    for (int e = 0; e < k * n; ++e) Rg.at((size_t)l, (size_t)e) = Y2.v[e];
+    for (int e = 0; e < m * n; ++e) hP.at((size_t)e, (size_t)l) = Y3.v[e];
+  }
+}
+
 static inline int64_t store_one(const ZpField& f, int64_t e) { return f.canon(e); }
 static inline int64_t store_one(const QField&, const Rat&) { return 0; }
 static inline int64_t num_of(const Rat& e) { return e.num; }
@@ -388,22 +415,7 @@ int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int
     if (improved) {
       std::vector<int32_t> U((size_t)m * m), V((size_t)k * k), W((size_t)n * n);
       plo_orbit_decode(m, k, n, mode, seed, rep->best.index, U.data(), V.data(), W.data());
-      Sparsifier<QField> la(Q, nullptr);
-      auto tomat = [&](const std::vector<int32_t>& a, int s) { Dense<QField> M(Q, (size_t)s, (size_t)s); for (size_t e = 0; e < a.size(); ++e) M.v[e] = Rat(a[e]); return M; };
-      const Dense<QField> Um = tomat(U, m), Vm = tomat(V, k), Wm = tomat(W, n);
-      const Dense<QField> iU = la.inverse(Um), iV = la.inverse(Vm), iW = la.inverse(Wm);
-      const Dense<QField> iUT = la.transpose(iU), iWT = la.transpose(iW);
-      // row l of L.(U^-1 (x) V) = vec(U^-T A_l V), of R.(V^-T (x) W) = vec(V^-1 B_l W); column l of (U (x) W^-1).P = vec(U C_l W^-T)
-      for (int l = 0; l < r; ++l) {
-        Dense<QField> A(Q, (size_t)m, (size_t)k), B(Q, (size_t)k, (size_t)n), C(Q, (size_t)m, (size_t)n);
-        for (int e = 0; e < m * k; ++e) A.v[e] = L.at((size_t)l, (size_t)e);
-        for (int e = 0; e < k * n; ++e) B.v[e] = R.at((size_t)l, (size_t)e);
-        for (int e = 0; e < m * n; ++e) C.v[e] = P.at((size_t)e, (size_t)l);
-        const Dense<QField> Y1 = la.mul(la.mul(iUT, A), Vm), Y2 = la.mul(la.mul(iV, B), Wm), Y3 = la.mul(la.mul(Um, C), iWT);
-        for (int e = 0; e < m * k; ++e) Lj.at((size_t)l, (size_t)e) = Y1.v[e];
-        for (int e = 0; e < k * n; ++e) Rg.at((size_t)l, (size_t)e) = Y2.v[e];
-        for (int e = 0; e < m * n; ++e) hP.at((size_t)e, (size_t)l) = Y3.v[e];
-      }
+      orbit_transform(Q, m, k, n, r, L, R, P, U, V, W, Lj, Rg, hP);
     }
     rep->improved = improved ? 1 : 0;
     store(Lj, oLn, oLd); store(Rg, oRn, oRd); store(hP, oPn, oPd);
@@ -456,6 +468,64 @@ int plo_depender(uint64_t q, int rows, int cols, const int64_t* num, const int64
     return rc;
   } catch (const RangeError& e) {
     plo::set_error("plo_depender: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
+// Orbiter over Z/qZ (`orbiter -m q`, src/orbiter.cpp:419-426 -> Orbiter<0>()(QQ, F, ...)): the matrices are reduced
+// modulo q first (:232-234) and the whole search, the acceptance (:330-331) and the final check run in the field.
+int plo_orbiter_modp(uint64_t q, int mode, uint64_t seed, uint64_t loops, int r, int Lcols, int Rcols, int Prows, const int64_t* Ln,
+                     const int64_t* Ld, const int64_t* Rn, const int64_t* Rd, const int64_t* Pn, const int64_t* Pd, int64_t* oL,
+                     int64_t* oR, int64_t* oP, plo_orbiter_report* rep) {
+  if (!Ln || !Rn || !Pn || !oL || !oR || !oP || !rep || r < 1 || Lcols < 1 || Rcols < 1 || Prows < 1) {
+    plo::set_error("plo_orbiter_modp: bad argument");
+    return PLO_E_ARG;
+  }
+  uint64_t p = q;
+  while (p && (p % 2) == 0) p >>= 1;  // :421-422
+  if (p == 1) p = 2;
+  if (p < 2 || p >= (1ull << 31) || !is_prime(p)) { plo::set_error("plo_orbiter_modp: the modulus (factors of 2 stripped) must be a prime below 2^31"); return PLO_E_ARG; }
+  int rc = plo::check_device();
+  if (rc) return rc;
+  try {
+    ZpField Z((int64_t)p);
+    int m, k, n;
+    plo_LRP2MM(Lcols, Rcols, Prows, &m, &k, &n);
+    if (Lcols != m * k || Rcols != k * n || Prows != m * n) { plo::set_error("plo_orbiter_modp: outer dimension mismatch"); return 3; }
+    const Dense<ZpField> L = load(Z, (size_t)r, (size_t)Lcols, Ln, Ld), R = load(Z, (size_t)r, (size_t)Rcols, Rn, Rd), P = load(Z, (size_t)Prows, (size_t)r, Pn, Pd);
+    memset(rep, 0, sizeof(*rep));
+    rep->m = m; rep->k = k; rep->n = n;
+    auto count = [&](const Dense<ZpField>& M) { for (int64_t e : M.v) if (e != 0) { ++rep->init_nnz; if (!(Z.is_one(e) || Z.is_mone(e))) ++rep->init_nno; } };
+    count(L); count(R); count(P);
+    rep->init_score = (double)rep->init_nnz;
+    std::vector<int32_t> Li(L.v.begin(), L.v.end()), Ri(R.v.begin(), R.v.end()), Pi(P.v.begin(), P.v.end());
+    rc = plo_orbit_sweep((uint32_t)p, m, k, n, r, Li.data(), Ri.data(), Pi.data(), 1, 1, 1, PLO_MEASURE_NNZ, mode, seed, 0, loops, &rep->best);
+    if (rc) return rc;
+    const bool improved = rep->best.index != PLO_NO_INDEX &&
+                          (rep->best.nnz < rep->init_nnz || (rep->best.nnz == rep->init_nnz && rep->best.nno < rep->init_nno));
+    Dense<ZpField> Lj = L, Rg = R, hP = P;
+    if (improved) {
+      std::vector<int32_t> U((size_t)m * m), V((size_t)k * k), W((size_t)n * n);
+      plo_orbit_decode(m, k, n, mode, seed, rep->best.index, U.data(), V.data(), W.data());
+      orbit_transform(Z, m, k, n, r, L, R, P, U, V, W, Lj, Rg, hP);
+    }
+    rep->improved = improved ? 1 : 0;
+    store(Lj, oL, nullptr); store(Rg, oR, nullptr); store(hP, oP, nullptr);
+    // MMchecker of the returned triple in the field (:355)
+    auto csr_of = [&](const Dense<ZpField>& M, CsrHost& out) {
+      out.ptr.assign(1, 0); out.col.clear(); out.val.clear();
+      for (size_t i = 0; i < M.rows; ++i) {
+        for (size_t j = 0; j < M.cols; ++j) if (M.at(i, j) != 0) { out.col.push_back((int32_t)j); out.val.push_back((uint32_t)M.at(i, j)); }
+        out.ptr.push_back((int64_t)out.col.size());
+      }
+    };
+    CsrHost cl, cr, cp;
+    csr_of(Lj, cl); csr_of(Rg, cr); csr_of(hP, cp);
+    const plo_csr vl = cl.view(r, Lcols), vr = cr.view(r, Rcols), vp = cp.view(Prows, r);
+    rep->mm_verdict = plo_mmcheck_batch((uint32_t)p, m, k, n, r, &vl, &vr, &vp, seed ^ 0x4D4D636865636Bull, 32, nullptr, nullptr, nullptr);
+    return PLO_OK;
+  } catch (const RangeError& e) {
+    plo::set_error("plo_orbiter_modp: %s", e.what());
     return PLO_E_RANGE;
   }
 }

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <type_traits>
 
+#include <algorithm>
 #include <vector>
 
 #include "plo_device.cuh"
@@ -453,6 +454,121 @@ __global__ void __launch_bounds__(kThreads) orbit_table_kernel(int r, int3 den, 
 }
 
 // ---------------------------------------------------------------------------
+// Orbit sweep over Z/pZ  (`orbiter -m p`: FMatrix L(BL,FF) ... src/orbiter.cpp:232-234, 419-426;
+// the whole search then runs in the field, measure = sparsity, Orbiter<0>).
+// L, R, P^T hold residues in [0,p), p < 2^31.  U, V, W and their inverses are small integers,
+// so a transformed entry is an integer combination of residues: both stages of the product are
+// accumulated exactly in 64 bits (|.| < 2^31 . 2^8 . 2^8) and reduced ONCE, by a Barrett
+// reduction of (value + bias) with bias a multiple of p above 2^48.
+// ---------------------------------------------------------------------------
+struct ModP {
+  unsigned int p;
+  unsigned long long M64;   // floor((2^64-1)/p)
+  unsigned long long bias;  // multiple of p, >= 2^48
+};
+__host__ __device__ __forceinline__ unsigned int modp_reduce(long long v, const ModP& mp) {
+  const unsigned long long x = (unsigned long long)(v + (long long)mp.bias);
+#ifdef __CUDA_ARCH__
+  const unsigned long long q = __umul64hi(x, mp.M64);
+#else
+  const unsigned long long q = (unsigned long long)(((unsigned __int128)x * mp.M64) >> 64);
+#endif
+  unsigned long long r = x - q * mp.p;
+  if (r >= mp.p) r -= mp.p;
+  if (r >= mp.p) r -= mp.p;
+  return (unsigned int)r;
+}
+template <int RA, int CA, bool TL, bool TR>
+__host__ __device__ __forceinline__ void transform_row_modp(const int* __restrict__ A, const int* Lm, const int* Rm, const ModP& mp, Acc& acc) {
+  int a[RA * CA];
+#pragma unroll
+  for (int e = 0; e < RA * CA; ++e) a[e] = A[e];
+#pragma unroll
+  for (int x = 0; x < RA; ++x) {
+    long long X[CA];
+#pragma unroll
+    for (int j = 0; j < CA; ++j) {
+      long long s = 0;
+#pragma unroll
+      for (int i = 0; i < RA; ++i) s += (long long)(TL ? Lm[i * RA + x] : Lm[x * RA + i]) * (long long)a[i * CA + j];
+      X[j] = s;
+    }
+#pragma unroll
+    for (int y = 0; y < CA; ++y) {
+      long long s = 0;
+#pragma unroll
+      for (int j = 0; j < CA; ++j) s += X[j] * (long long)(TR ? Rm[y * CA + j] : Rm[j * CA + y]);
+      const unsigned int v = modp_reduce(s, mp);
+      acc.nnz += (v != 0u);
+      acc.nno += (v != 0u) & (v != 1u) & (v != mp.p - 1u);  // isAbsOne in the field
+    }
+  }
+}
+template <int M, int K, int N, int MODE>
+__host__ __device__ __forceinline__ Score score_candidate_modp(const int* __restrict__ lrp, int r, const ModP& mp, unsigned long long seed,
+                                                               unsigned long long index, volatile int* scr, int stride) {
+  Digits<MODE> ds(seed, index);
+  const Zoi zu = decode_zoi<M, MODE>(ds);
+  const Zoi zv = decode_zoi<K, MODE>(ds);
+  const Zoi zw = decode_zoi<N, MODE>(ds);
+  int U[M * M], Ui[M * M], V[K * K], Vi[K * K], W[N * N], Wi[N * N];
+  expand_zoi<M, false>(zu, U, scr, stride);
+  expand_zoi<M, true>(zu, Ui, scr, stride);
+  expand_zoi<K, false>(zv, V, scr, stride);
+  expand_zoi<K, true>(zv, Vi, scr, stride);
+  expand_zoi<N, false>(zw, W, scr, stride);
+  expand_zoi<N, true>(zw, Wi, scr, stride);
+  const int* Lc = lrp;
+  const int* Rc = lrp + r * M * K;
+  const int* Pc = Rc + r * K * N;
+  Acc acc;
+  acc.nnz = acc.nno = acc.sq = 0;
+  for (int l = 0; l < r; ++l) {
+    transform_row_modp<M, K, true, false>(Lc + l * M * K, Ui, V, mp, acc);   // U^-T A V
+    transform_row_modp<K, N, false, false>(Rc + l * K * N, Vi, W, mp, acc);  // V^-1 B W
+    transform_row_modp<M, N, false, true>(Pc + l * M * N, U, Wi, mp, acc);   // U C W^-T
+  }
+  Score sc;
+  sc.nnz = (uint32_t)acc.nnz; sc.nno = (uint32_t)acc.nno; sc.g2 = 0.0;
+  return sc;
+}
+
+template <int M, int K, int N, int MODE>
+__global__ void __launch_bounds__(kThreads) orbit_modp_kernel(int r, ModP mp, unsigned long long seed, unsigned long long lo, unsigned long long hi,
+                                                               Key* __restrict__ block_best, uint32_t* __restrict__ tnnz, uint32_t* __restrict__ tnno) {
+  __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
+  __shared__ Key red[32];
+  const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+  Key best;
+  best.primary = ~0ull; best.index = ~0ull;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
+    const Score s = score_candidate_modp<M, K, N, MODE>(c_lrp, r, mp, seed, idx, scr + threadIdx.x, kThreads);
+    if (tnnz) tnnz[idx - lo] = s.nnz;
+    if (tnno) tnno[idx - lo] = s.nno;
+    const Key k = make_key<PLO_MEASURE_NNZ>(s, idx);
+    if (k.primary < best.primary) best = k;
+  }
+  best = block_min(best, red);
+  if (threadIdx.x == 0) block_best[blockIdx.x] = best;
+}
+
+typedef void (*ModpLaunch)(int mode, int grid, cudaStream_t st, int r, ModP mp, unsigned long long seed, unsigned long long lo,
+                           unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno);
+template <int M, int K, int N>
+static void modp_launch(int mode, int grid, cudaStream_t st, int r, ModP mp, unsigned long long seed, unsigned long long lo,
+                        unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno) {
+  if (mode == 0) orbit_modp_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, mp, seed, lo, hi, bb, tnnz, tnno);
+  else orbit_modp_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, mp, seed, lo, hi, bb, tnnz, tnno);
+}
+static ModpLaunch find_modp(int m, int k, int n) {
+  if (m == 2 && k == 2 && n == 2) return &modp_launch<2, 2, 2>;
+  if (m == 3 && k == 3 && n == 3) return &modp_launch<3, 3, 3>;
+  if (m == 4 && k == 4 && n == 4) return &modp_launch<4, 4, 4>;
+  if (m == 3 && k == 4 && n == 7) return &modp_launch<3, 4, 7>;
+  return nullptr;
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct ShapeOps {
@@ -558,6 +674,60 @@ struct plo_orbit_plan {
   bool lutfull, pack;
   size_t smem;
 };
+
+// Z/pZ sweep: residues in, winner (and optional per-candidate table) out.  Synchronous.
+static int orbit_modp(uint32_t p, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int mode, uint64_t seed,
+                      uint64_t lo, uint64_t hi, plo_orbit_best* best, uint32_t* tnnz, uint32_t* tnno) {
+  if (!L || !R || !P || r < 1 || p < 2 || p >= (1u << 31) || (mode != 0 && mode != 1) || hi < lo) {
+    set_error("orbit sweep mod p: bad argument (need 2 <= p < 2^31)");
+    return PLO_E_ARG;
+  }
+  int rc = check_device();
+  if (rc) return rc;
+  const ModpLaunch launch = find_modp(m, k, n);
+  if (!launch) { set_error("orbit sweep: shape %dx%dx%d not compiled in", m, k, n); return PLO_E_SHAPE; }
+  const size_t total = (size_t)r * (m * k + k * n + m * n);
+  if ((long long)total > kConstInts) { set_error("orbit sweep: L/R/P exceed constant memory"); return PLO_E_SHAPE; }
+  if (mode == 0 && plo_orbit_space(m, k, n) == 0) { set_error("orbit sweep: exhaustive space exceeds 64 bits"); return PLO_E_SHAPE; }
+  std::vector<int> h(total);
+  int* dst = h.data();
+  auto put = [&](int32_t v) -> bool { if (v < 0 || (uint32_t)v >= p) return false; *dst++ = v; return true; };
+  bool ok = true;
+  for (int i = 0; i < r * m * k && ok; ++i) ok = put(L[i]);
+  for (int i = 0; i < r * k * n && ok; ++i) ok = put(R[i]);
+  for (int l = 0; l < r && ok; ++l) for (int e = 0; e < m * n && ok; ++e) ok = put(P[(size_t)e * r + l]);
+  if (!ok) { set_error("orbit sweep mod p: residue out of range"); return PLO_E_ARG; }
+  ModP mp;
+  mp.p = p; mp.M64 = ~0ull / p;
+  mp.bias = (((1ull << 48) + p - 1) / p) * p;
+  const uint64_t cnt = hi - lo;
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((cnt + kThreads - 1) / kThreads, (uint64_t)sm_count() * 4));
+  Key* d_bb = nullptr;
+  uint32_t *d_nnz = nullptr, *d_nno = nullptr;
+  auto cleanup = [&]() { cudaFree(d_bb); cudaFree(d_nnz); cudaFree(d_nno); };
+  g_const_owner = nullptr;
+  cudaError_t e = cudaMemcpyToSymbol(c_lrp, h.data(), total * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&d_bb, sizeof(Key) * grid);
+  if (e == cudaSuccess && tnnz && cnt) e = cudaMalloc(&d_nnz, cnt * 4);
+  if (e == cudaSuccess && tnno && cnt) e = cudaMalloc(&d_nno, cnt * 4);
+  if (e == cudaSuccess) {
+    launch(mode, grid, nullptr, r, mp, seed, lo, hi, d_bb, d_nnz, d_nno);
+    e = cudaGetLastError();
+  }
+  std::vector<Key> bb(grid);
+  if (e == cudaSuccess) e = cudaMemcpy(bb.data(), d_bb, sizeof(Key) * grid, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && d_nnz) e = cudaMemcpy(tnnz, d_nnz, cnt * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && d_nno) e = cudaMemcpy(tnno, d_nno, cnt * 4, cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) { set_error("orbit sweep mod p: %s", cudaGetErrorString(e)); return PLO_E_CUDA; }
+  if (best) {
+    Key b = bb[0];
+    for (const Key& x : bb) if (key_less(x, b)) b = x;
+    best->index = b.index; best->nnz = 0; best->nno = 0; best->score = 0.0;
+    if (b.index != ~0ull) { best->nnz = (uint32_t)(b.primary >> 32); best->nno = (uint32_t)b.primary; best->score = (double)best->nnz; }
+  }
+  return PLO_OK;
+}
 
 extern "C" {
 
@@ -687,8 +857,11 @@ void plo_orbit_plan_destroy(plo_orbit_plan* pl) {
 int plo_orbit_sweep(uint32_t p, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P,
                     int32_t denL, int32_t denR, int32_t denP, int measure, int mode, uint64_t seed, uint64_t lo,
                     uint64_t hi, plo_orbit_best* best) {
-  if (p != 0) { set_error("plo_orbit_sweep: only exact integers (p == 0) in this version"); return PLO_E_ARG; }
   if (!best) { set_error("plo_orbit_sweep: null output"); return PLO_E_ARG; }
+  if (p != 0) {
+    if (measure != PLO_MEASURE_NNZ) { set_error("plo_orbit_sweep: only the sparsity measure exists over Z/pZ (src/orbiter.cpp:426)"); return PLO_E_ARG; }
+    return orbit_modp(p, m, k, n, r, L, R, P, mode, seed, lo, hi, best, nullptr, nullptr);
+  }
   plo_orbit_plan* pl = nullptr;
   int rc = plo_orbit_plan_create(&pl, m, k, n, r, L, R, P, denL, denR, denP, measure, mode, seed);
   if (rc) return rc;
@@ -729,6 +902,11 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
   }
   cleanup();
   return rc;
+}
+
+int plo_orbit_table_modp(uint32_t p, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int mode,
+                         uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* nnz, uint32_t* nno) {
+  return orbit_modp(p, m, k, n, r, L, R, P, mode, seed, lo, hi, nullptr, nnz, nno);
 }
 
 }  // extern "C"

@@ -81,3 +81,15 @@ def test_factorizer_cli(capi, tmp_path):
     assert p.returncode == 0 and "SUCCESS: consistent factorization!" in p.stderr
     p = subprocess.run([exe, "-k", "5", str(f)], capture_output=True, text=True, timeout=300)
     assert p.returncode == 255 and "inner dimension has to be between 16 and 48" in p.stderr
+
+
+def test_orbiter_cli_modular(capi, tmp_path):
+    """-m p: the reference runs Orbiter<0> over Z/pZ (src/orbiter.cpp:419-426); outputs are residues and pass MMchecker -m p."""
+    files = write_triple(tmp_path, "2x2x2_7_DPS-accurate")
+    p = subprocess.run([os.path.join(BIN, "orbiter"), "-m", "513083", "-O", "20000", "--seed", "3"] + files, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "SUCCESS: correct 2x2x2" in p.stderr and "# Search(20000):" in p.stderr
+    if "Rdcd. opt" in p.stderr:
+        outs = [f.replace(".sms", ".nnz.sms") for f in files]
+        q = subprocess.run([os.path.join(BIN, "MMchecker"), "-m", "513083"] + outs, capture_output=True, text=True, timeout=300)
+        assert q.returncode == 0 and "SUCCESS: correct 2x2x2" in q.stderr

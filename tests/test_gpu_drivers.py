@@ -135,3 +135,23 @@ def test_factorizer_error_codes(capi):
     dep = [row[:3] + [row[0]] for row in M]
     with pytest.raises(capi.PloError):
         capi.factorizer(dep)  # not full column rank: backSolver's precondition
+
+
+@pytest.mark.parametrize("stem,q", [("2x2x2_7_Winograd", 2147483647), ("3x3x3_23_58", 101), ("2x2x2_7_DPS-accurate", 2 * 513083)])
+def test_modular_orbiter_driver(capi, stem, q):
+    """`orbiter -m q`: factors of 2 stripped (src/orbiter.cpp:421-422), search and acceptance in Z/pZ; the returned triple is the
+    oracle's winner transformed in the field and is still a matrix-multiplication algorithm (:355)."""
+    L, R, P = O.triple(stem)
+    p = q // 2 if q % 2 == 0 else q
+    loops = 3000
+    Lj, Rg, hP, rep = capi.orbiter_modp(L, R, P, q, seed=5, loops=loops)
+    ref = O.orbit_sweep(L, R, P, 0, 1, 5, 0, loops, p=p, table=False)["best"]
+    assert (rep["best"]["index"], rep["best"]["nnz"], rep["best"]["nno"]) == ref[:3]
+    assert rep["mm_verdict"] == 0
+    red = lambda M: [[(v.numerator % p) * pow(v.denominator % p, -1, p) % p for v in row] for row in M]
+    if rep["improved"]:
+        assert rep["best"]["nnz"] <= rep["init"][0]
+        nnz = sum(1 for M in (Lj, Rg, hP) for row in M for v in row if v % p)
+        assert nnz == rep["best"]["nnz"]
+    else:
+        assert (Lj, Rg, hP) == (red(L), red(R), red(P))

@@ -113,3 +113,29 @@ def test_growth_G2_known_answers(capi):
         got = capi.growth_G2(f(L), f(R), f(P))[0]
         assert abs(got - val) < 5e-9 * val, (stem, got)
         assert abs(got - O.growth_G2(L, R, P)) <= RTOL * got
+
+
+def residues(M, p):
+    return np.array([[(v.numerator % p) * pow(v.denominator % p, -1, p) % p for v in row] for row in M], dtype=np.int32)
+
+
+@pytest.mark.parametrize("stem,count,p", [("2x2x2_7_Winograd", 20000, 2147483647), ("2x2x2_7_DPS-accurate", 8000, 513083),
+                                          ("3x3x3_23_58", 4000, 101), ("4x4x4_48_rational", 2000, 2147483647),
+                                          ("3x4x7_63_rational", 1000, 1000003), ("2x2x2_7_Strassen", 5000, 3)])
+def test_modular_orbit_sweep(capi, stem, count, p):
+    """`orbiter -m p` (src/orbiter.cpp:232-234, 419-426): the whole search runs in Z/pZ; per-candidate (nnz, nno) and the
+    winner are bit-exact against the oracle over the same field."""
+    L, R, P = O.triple(stem)
+    mkn = O.LRP2MM(L, R, P)
+    Lr, Rr, Pr = residues(L, p), residues(R, p), residues(P, p)
+    ref = O.orbit_sweep(L, R, P, 0, 1, SEED, 100, 100 + count, p=p)
+    nnz, nno = capi.orbit_table_modp(p, mkn, Lr, Rr, Pr, 1, SEED, 100, 100 + count)
+    assert np.array_equal(nnz, ref["nnz"]) and np.array_equal(nno, ref["nno"])
+    got = capi.orbit_sweep(mkn, Lr, Rr, Pr, (1, 1, 1), 0, 1, SEED, 100, 100 + count, p=p)
+    assert (got["index"], got["nnz"], got["nno"]) == ref["best"][:3]
+    if p > 10 ** 6 and stem != "2x2x2_7_DPS-accurate":
+        # a large prime sees the same zero / +-1 pattern as the rationals
+        exact = O.orbit_sweep(L, R, P, 0, 1, SEED, 100, 100 + count)
+        assert np.array_equal(nnz, exact["nnz"]) and np.array_equal(nno, exact["nno"])
+    with pytest.raises(capi.PloError):
+        capi.orbit_sweep(mkn, Lr, Rr, Pr, (1, 1, 1), 3, 1, SEED, 0, 10, p=p)  # no growth factor in a finite field
