@@ -28,6 +28,7 @@ WORKLOAD = "orbit sweep of 2x2x2_7_Winograd_{L,R,P}, measure G2 (growthfactor.cp
 INT_OPS_PER_CAND = 336 + 84
 FP64_OPS_PER_CAND = 21 + 14 + 7
 METRIC = "candidates scored/sec"
+NCU_DRAM_BYTES_PER_LAUNCH = 26624  # ncu --set full, profiles/ncu_r01_orbit_sweep.md: 26.6 KB read + 0 B written per launch
 
 
 def env_int(name, default):
@@ -257,7 +258,9 @@ def main():
         achieved = int_ops / (kern_ms * 1e-3) / 1e12
         peak = peaks["imad_per_s"] / 1e12
         roof = {"bound": "int32", "achieved": achieved, "peak": peak, "unit": "TIOP/s (IMAD-class int32 ops)", "frac": achieved / peak,
-                "traffic": None, "kernel": "orbit_sweep_kernel<2,2,2,philox,G2>", "kernel_ms": kern_ms,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/ncu_r01_orbit_sweep.md (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch; "
+                "independent of the candidate count: constants + one 16 B key per block)",
+                "kernel": "orbit_sweep_kernel<2,2,2,philox,G2>", "kernel_ms": kern_ms,
                 "ops_per_candidate": {"int32": INT_OPS_PER_CAND, "fp64": FP64_OPS_PER_CAND},
                 "peak_source": "plo_measure_peaks (register-resident IMAD loop, all SMs, best of 5, measured in this run); MEASURED_PEAKS.json has no int32/fp64 entry",
                 "fp64": {"achieved_tflop": FP64_OPS_PER_CAND * B / (kern_ms * 1e-3) / 1e12, "peak_dfma_tflop": 2 * peaks["dfma_per_s"] / 1e12},

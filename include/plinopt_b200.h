@@ -86,6 +86,10 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
                             int c, const int64_t* coeffs, int nprev, const int64_t* prev_rows, const int* init_rl,
                             const int* init_cl);
 int plo_lincomb_plan_run(plo_lincomb_plan* plan, void* stream);
+/* The same restricted to the candidates whose prefix (i*c+j)*c+k lies in [prefix_lo, prefix_hi): one GPU's share of a
+ * search sharded over several devices (the partial winners are merged by the caller: lexicographic maximum of
+ * (rl, cl, -index)). */
+int plo_lincomb_plan_run_range(plo_lincomb_plan* plan, uint64_t prefix_lo, uint64_t prefix_hi, void* stream);
 int plo_lincomb_plan_result(plo_lincomb_plan* plan, void* stream, int* best_rl, int* best_cl, uint64_t* best_index);
 uint64_t plo_lincomb_plan_candidates(const plo_lincomb_plan* plan); /* candidates scored per run            */
 int plo_lincomb_plan_launches(const plo_lincomb_plan* plan);         /* kernel launches per run              */

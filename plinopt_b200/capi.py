@@ -22,7 +22,7 @@ NO_INDEX = 2 ** 64 - 1
 # every symbol include/plinopt_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "plo_version", "plo_device_count", "plo_set_device", "plo_last_error",
-    "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run",
+    "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
     "plo_orbit_table_modp", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
@@ -147,6 +147,12 @@ class LincombPlan:
 
     def run(self, stream=0):
         _check(lib().plo_lincomb_plan_run(self._h, C.c_void_p(stream)))
+
+    def run_range(self, prefix_lo, prefix_hi, stream=0):
+        """Only the candidates whose prefix (i*c+j)*c+k is in [prefix_lo, prefix_hi): one shard of the search."""
+        f = lib().plo_lincomb_plan_run_range
+        f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        _check(f(self._h, prefix_lo, prefix_hi, C.c_void_p(stream)))
 
     def result(self, stream=0):
         rl = np.zeros(self.nbatch, dtype=np.int32); cl = np.zeros(self.nbatch, dtype=np.int32)

@@ -40,6 +40,7 @@ __host__ __device__ __forceinline__ unsigned long long pack_key(int rl, int cl, 
 template <typename T>
 struct LcParams {
   int c, m, nact, lsplit, ltile, nphi_max;
+  unsigned long long qlo, qhi;  // prefix range (i*c+j)*c+k of this launch (multi-GPU sharding of one search)
   unsigned int p;
   int cl_const;
   const T* t0;   // [b][l][MPAD]
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_kernel(const LcParams<T> p
   const T SENT = (T)(~(T)0) >> (MODP ? 0 : 1);  // never a residue (p <= 2^32-1) / beyond the integer bound
 
   unsigned long long best = prm.seed[b];
-  const unsigned long long nprefix = (unsigned long long)c * c * c;
-  const unsigned long long nitems = nprefix * (unsigned long long)prm.lsplit;
+  const unsigned long long item0 = prm.qlo * (unsigned long long)prm.lsplit;
+  const unsigned long long nitems = prm.qhi * (unsigned long long)prm.lsplit;
   const unsigned long long nthreads = (unsigned long long)gridDim.x * kLcThreads;
 
   for (int l0 = 0; l0 < c; l0 += prm.ltile) {
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_kernel(const LcParams<T> p
     }
     __syncthreads();
     const int lc = (l1 - l0 + prm.lsplit - 1) / prm.lsplit;
-    for (unsigned long long item = (unsigned long long)blockIdx.x * kLcThreads + threadIdx.x; item < nitems; item += nthreads) {
+    for (unsigned long long item = item0 + (unsigned long long)blockIdx.x * kLcThreads + threadIdx.x; item < nitems; item += nthreads) {
       const unsigned long long q = item / (unsigned)prm.lsplit;
       const int s = (int)(item - q * (unsigned)prm.lsplit);
       const int la = l0 + s * lc, lb = min(l1, la + lc);
@@ -417,6 +418,14 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
 
 int plo_lincomb_plan_run(plo_lincomb_plan* pl, void* stream) {
   if (!pl) { set_error("plo_lincomb_plan_run: null plan"); return PLO_E_ARG; }
+  return plo_lincomb_plan_run_range(pl, 0, (uint64_t)pl->c * pl->c * pl->c, stream);
+}
+
+int plo_lincomb_plan_run_range(plo_lincomb_plan* pl, uint64_t prefix_lo, uint64_t prefix_hi, void* stream) {
+  if (!pl) { set_error("plo_lincomb_plan_run_range: null plan"); return PLO_E_ARG; }
+  const uint64_t nprefix = (uint64_t)pl->c * pl->c * pl->c;
+  if (prefix_hi > nprefix) prefix_hi = nprefix;
+  if (prefix_lo > prefix_hi) prefix_lo = prefix_hi;
   cudaStream_t st = (cudaStream_t)stream;
   lincomb_init_kernel<<<(pl->nbatch + 127) / 128, 128, 0, st>>>(pl->d_result, pl->d_seed, pl->nbatch);
   const size_t tab = (size_t)pl->c * pl->mpad;
@@ -427,6 +436,7 @@ int plo_lincomb_plan_run(plo_lincomb_plan* pl, void* stream) {
     typedef typename std::remove_pointer<decltype(base)>::type T;
     LcParams<T> prm;
     prm.c = pl->c; prm.m = pl->m; prm.nact = 0; prm.lsplit = pl->lsplit; prm.ltile = pl->ltile; prm.nphi_max = 4;
+    prm.qlo = prefix_lo; prm.qhi = prefix_hi;
     prm.p = pl->p; prm.cl_const = pl->n - ((pl->n - pl->off) < 4 ? (pl->n - pl->off) : 4);
     prm.t0 = base; prm.t1 = base + per; prm.t2 = base + 2 * per; prm.t3 = base + 3 * per;
     prm.zflag = pl->d_zflag; prm.phi = pl->d_phi; prm.nphi = pl->d_nphi; prm.coef = pl->d_coef;

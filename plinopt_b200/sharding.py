@@ -80,3 +80,32 @@ def allreduce_factor_best(best, device=None):
     rows = [tuple(t[r * SLOT:(r + 1) * SLOT].tolist()) for r in range(world)]
     rows = [r for r in rows if r[3] != INT64_MAX]
     return min(rows) if rows else (0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, None)
+
+
+LC_IDX_BITS = 36
+
+
+def lincomb_key(rl, cl, idx):
+    """Order-preserving int64 image of a sparsifier search result: maximum of (rl, cl, -index)
+    (strict '>' acceptance of plinopt_sparsify.inl:183-184 = first maximiser in enumeration order).
+    idx None (no candidate beat the seed) maps below every real candidate of the same weight."""
+    low = 0 if idx is None else (1 << LC_IDX_BITS) - 1 - int(idx)
+    return ((int(rl) + 1) << 48) | ((int(cl) + 1) << LC_IDX_BITS) | low
+
+
+def lincomb_unkey(key):
+    low = key & ((1 << LC_IDX_BITS) - 1)
+    return (key >> 48) - 1, ((key >> LC_IDX_BITS) & 0xFFF) - 1, (None if low == 0 else (1 << LC_IDX_BITS) - 1 - low)
+
+
+def allreduce_lincomb(results, device=None):
+    """results: list of (rl, cl, idx|None), one per independent problem of the batch, from this rank's prefix shard
+    (LincombPlan.run_range).  One all_reduce(MAX) over nbatch int64 words returns the global winners."""
+    import torch
+    import torch.distributed as dist
+    keys = [lincomb_key(*r) for r in results]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor(keys, dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        keys = t.tolist()
+    return [lincomb_unkey(k) for k in keys]

@@ -184,3 +184,32 @@ def test_large_c_property(capi):
     plan = capi.LincombPlan(p, np.stack([tm, tm]), 0, np.stack([cf, cf]))
     plan.run(); r2, c2, i2 = plan.result(); plan.close()
     assert (int(r2[0]), int(c2[0]), int(i2[0])) == (rl, cl, idx) and (int(r2[1]), int(c2[1]), int(i2[1])) == (rl, cl, idx)
+
+
+def test_prefix_range_shards_reproduce_the_full_search(capi):
+    """Multi-GPU sharding of ONE search (BASELINE config 3): any partition of the prefix range (i*c+j)*c+k gives, after the
+    max-merge of plinopt_b200.sharding, the winner of the unsharded search."""
+    from plinopt_b200 import sharding as S
+    L = O.dense_fractions("4x4x4_48_rational_L")
+    p = 2147483647
+    c = 20
+    tms, cfs = [], []
+    for blk in range(4):
+        TM = [[L[i][4 * blk + t] for i in range(len(L))] for t in range(4)]
+        tm_num, tm_den = O.numden(TM)
+        tm = np.array([[(int(a) % p) * pow(int(b) % p, -1, p) % p for a, b in zip(ra, rb)] for ra, rb in zip(tm_num, tm_den)], dtype=np.int64)
+        cn, cd = O.coeffs(TM, p, c)
+        tms.append(tm); cfs.append(np.array([(int(a) % p) * pow(int(b) % p, -1, p) % p for a, b in zip(cn, cd)], dtype=np.int64))
+    plan = capi.LincombPlan(p, np.stack(tms), 0, np.stack(cfs))
+    plan.run()
+    full = [(int(a), int(b), int(i)) for a, b, i in zip(*plan.result())]
+    nprefix = c ** 3
+    for world in (2, 3, 8):
+        parts = []
+        for rank in range(world):
+            lo, hi = S.shard_range(0, nprefix, rank, world)
+            plan.run_range(lo, hi)
+            parts.append([(int(a), int(b), None if int(i) == capi.NO_INDEX else int(i)) for a, b, i in zip(*plan.result())])
+        merged = [S.lincomb_unkey(max(S.lincomb_key(*parts[r][b]) for r in range(world))) for b in range(4)]
+        assert merged == full
+    plan.close()

@@ -32,6 +32,12 @@ def test_pick_global_tie_goes_to_lowest_index():
     assert S.pick_global(merged, 3)["index"] == 100
 
 
+def test_lincomb_key_roundtrip_and_order():
+    assert S.lincomb_unkey(S.lincomb_key(24, 2, 130)) == (24, 2, 130) and S.lincomb_unkey(S.lincomb_key(-1, -1, None)) == (-1, -1, None)
+    assert S.lincomb_key(24, 2, 130) > S.lincomb_key(24, 2, 131) > S.lincomb_key(24, 1, 0) > S.lincomb_key(23, 4, 0)
+    assert S.lincomb_key(5, 5, 2 ** 36 - 2) > S.lincomb_key(5, 5, None)
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
@@ -47,7 +53,8 @@ def _worker(rank, world, port, q):
     e = S.allreduce_best(None if rank == 0 else dict(score=3.0, index=999, nnz=1, nno=0))
     f = S.allreduce_factor_best((196, 100, 168, 40 + rank) if rank == 1 else (196, 100, 168, 77))
     f0 = S.allreduce_factor_best((1, 2, 3, None))
-    q.put((rank, g, e, f, f0))
+    lc = S.allreduce_lincomb([(24, 2, 500 + rank), (10, 1, None) if rank == 0 else (10, 1, 7), (-1, -1, None)])
+    q.put((rank, g, e, f, f0, lc))
     dist.destroy_process_group()
 
 
@@ -59,7 +66,8 @@ def test_allreduce_min_with_index_gloo_world2():
     [p.start() for p in ps]
     out = [q.get(timeout=120) for _ in ps]
     [p.join(60) for p in ps]
-    for rank, g, e, f, f0 in out:
+    for rank, g, e, f, f0, lc in out:
+        assert lc == [(24, 2, 500), (10, 1, 7), (-1, -1, None)]  # first maximiser in enumeration order; seed kept if nobody beat it
         assert g["index"] == 123 and g["rank"] == 0 and g["score"] == 12.0 and g["nnz"] == 40
         assert e["index"] == 999 and e["rank"] == 1
         assert f == (196, 100, 168, 41) and f0[3] is None  # tie on the score: lowest index wins; no candidate anywhere
