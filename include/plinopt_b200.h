@@ -311,6 +311,21 @@ int plo_depender(uint64_t q, int rows, int cols, const int64_t* num, const int64
                  const int64_t* user_den, int maxnumcoeff, int level, uint64_t max_hits, plo_dep_hit* hits, uint64_t* nhits,
                  uint64_t* ncand, char* text, uint64_t text_cap, uint64_t* text_len, int64_t* coef_num, int64_t* coef_den, int* ncoef);
 
+/* negater  src/negater.cpp:117-209 (host only, exact over Q): per product i, the common divisors of the numerators and of the
+ * denominators of row i of L and of R move into column i of P (unless only_sign), then two of (L_i, R_i, P^T_i) change sign when
+ * that lowers the number of negative coefficients.  Outputs have the input shapes.  stats (may be NULL, 12 words): common
+ * divisors before, after, rows flipped, negatives before in L,R,P, after in L,R,P, non-zeroes of L,R,P. */
+int plo_negater(int only_sign, int r, int Lcols, int Rcols, int Prows, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn,
+                const int64_t* Rd, const int64_t* Pn, const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd,
+                int64_t* oPn, int64_t* oPd, uint64_t* stats);
+
+/* rotater  bin/rotater.sh:75-83 (with src/columns-swap.cpp:41-52 and matrix-transpose): the cyclic rotation of an <m,k,n>
+ * algorithm, left (right = 0): L' = R (r x kn), R' = (P^T)_s (r x nm), P' = (L_s)^T (km x r), an <k,n,m> algorithm; right:
+ * L' = (P^T)_s (r x nm), R' = L (r x mk), P' = (R_s)^T (nk x r), an <n,m,k> algorithm.  Returns 3 on an outer dimension mismatch. */
+int plo_rotater(int right, int r, int Lcols, int Rcols, int Prows, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn,
+                const int64_t* Rd, const int64_t* Pn, const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd,
+                int64_t* oPn, int64_t* oPd);
+
 /* Straight-line program -> matrix: matrixBuilder  include/plinopt_programs.inl:1459-1608 (with the
  * parser :618-686 and parenthesisExpand :1615-1679; driver src/SLPchecker.cpp:22-40, rule
  * data/Makefile:31-32).  Needed to regenerate data/32x32x32_15096_{L,R,P}.sms, which the reference

@@ -1324,3 +1324,90 @@ extern "C" int orc_depender(int64_t p, int rows, int cols, const int64_t* num, c
   ZpField f{p};
   return depender_impl(f, rows, cols, num, den, nuser, un, ud, maxnumcoeff, level, max_hits, hits_out, nhits, ncand, coef_num, coef_den, ncoef);
 }
+
+// =============================================================================
+// negater (src/negater.cpp) and rotater (bin/rotater.sh, src/columns-swap.cpp): literal restatements.
+// Deterministic in the reference; host-only passes.
+// =============================================================================
+namespace orc {
+// src/negater.cpp:29-53 ndGCD: (gcd of numerators, gcd of denominators) of the stored entries, in the reference's
+// update order; returns how many of the two are neither 0 nor +-1.
+static size_t ndGCD(int64_t nd[2], const Mat<QField>& M, size_t i) {
+  nd[0] = nd[1] = 0;
+  for (size_t j = 0; j < M.c; ++j) {
+    const Rat& e = M(i, j);
+    if (e.n == 0) continue;  // not stored
+    const int64_t an = e.n < 0 ? -e.n : e.n;
+    if (an != 1) nd[0] = (int64_t)gcd128(nd[0], an); else nd[0] = 1;
+    if (e.d != 1) nd[1] = (int64_t)gcd128(nd[1], e.d); else nd[1] = 1;
+  }
+  return (size_t)(nd[0] != 0 && nd[0] != 1) + (size_t)(nd[1] != 0 && nd[1] != 1);
+}
+// :56-63
+static void swapMultipliers(const QField& f, Mat<QField>& divM, Mat<QField>& mulM, size_t i, int64_t c) {
+  if (c == 0 || c == 1 || c == -1) return;
+  for (size_t j = 0; j < divM.c; ++j) if (divM(i, j).n != 0) divM(i, j) = f.div(divM(i, j), Rat{c, 1});
+  for (size_t j = 0; j < mulM.c; ++j) if (mulM(i, j).n != 0) mulM(i, j) = f.mul(mulM(i, j), Rat{c, 1});
+}
+// :117-205
+static void negater(const QField& f, Mat<QField>& L, Mat<QField>& R, Mat<QField>& Pt, bool only_sign, uint64_t st[12]) {
+  for (int t = 0; t < 12; ++t) st[t] = 0;
+  for (size_t i = 0; i < L.r; ++i) {
+    if (!only_sign) {
+      int64_t ndL[2], ndR[2], ndP[2];
+      st[0] += ndGCD(ndL, L, i) + ndGCD(ndR, R, i) + ndGCD(ndP, Pt, i);
+      swapMultipliers(f, L, Pt, i, ndL[0]);
+      swapMultipliers(f, Pt, L, i, ndL[1]);
+      swapMultipliers(f, R, Pt, i, ndR[0]);
+      swapMultipliers(f, Pt, R, i, ndR[1]);
+      st[1] += ndGCD(ndL, L, i) + ndGCD(ndR, R, i) + ndGCD(ndP, Pt, i);
+    }
+    const size_t sl = rowSize(f, L, i), sr = rowSize(f, R, i), sp = rowSize(f, Pt, i);
+    size_t Lnegs = 0, Rnegs = 0, Pnegs = 0;
+    for (size_t j = 0; j < L.c; ++j) Lnegs += L(i, j).n < 0;
+    for (size_t j = 0; j < R.c; ++j) Rnegs += R(i, j).n < 0;
+    for (size_t j = 0; j < Pt.c; ++j) Pnegs += Pt(i, j).n < 0;
+    st[9] += sl; st[10] += sr; st[11] += sp;
+    st[3] += Lnegs; st[4] += Rnegs; st[5] += Pnegs;
+    const size_t None = Lnegs + Rnegs + Pnegs;
+    const size_t NLR = sl - Lnegs + sr - Rnegs + Pnegs, NLP = sl - Lnegs + Rnegs + sp - Pnegs, NRP = Lnegs + sr - Rnegs + sp - Pnegs;
+    auto flip = [&](Mat<QField>& M) { for (size_t j = 0; j < M.c; ++j) M(i, j) = f.neg(M(i, j)); };
+    if ((NLR < None) && (NLR <= NLP) && (NLR <= NRP)) { flip(L); flip(R); ++st[2]; st[6] += sl - Lnegs; st[7] += sr - Rnegs; st[8] += Pnegs; }
+    else if ((NLP < None) && (NLP < NLR) && (NLP <= NRP)) { flip(L); flip(Pt); ++st[2]; st[6] += sl - Lnegs; st[7] += Rnegs; st[8] += sp - Pnegs; }
+    else if ((NRP < None) && (NRP < NLP) && (NRP < NLR)) { flip(R); flip(Pt); ++st[2]; st[6] += Lnegs; st[7] += sr - Rnegs; st[8] += sp - Pnegs; }
+    else { st[6] += Lnegs; st[7] += Rnegs; st[8] += Pnegs; }
+  }
+}
+// src/columns-swap.cpp:41-52
+static Mat<QField> columnsSwap(const QField& f, const Mat<QField>& A, size_t m) {
+  const size_t n = A.c / m;
+  Mat<QField> As(f, A.r, A.c);
+  for (size_t r = 0; r < A.r; ++r) for (size_t col = 0; col < A.c; ++col) { const size_t i = col % m, j = (col - i) / m; As(r, i * n + j) = A(r, col); }
+  return As;
+}
+}  // namespace orc
+
+extern "C" {
+int orc_negater(int only_sign, int r, int Lc, int Rc, int Pr, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                const int64_t* Pn, const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd, int64_t* oPn, int64_t* oPd, uint64_t* stats) {
+  g_overflow = 0;
+  QField f;
+  Mat<QField> L = Loader<QField>::load(f, r, Lc, Ln, Ld), R = Loader<QField>::load(f, r, Rc, Rn, Rd);
+  Mat<QField> Pt = Transpose(f, Loader<QField>::load(f, Pr, r, Pn, Pd));
+  negater(f, L, R, Pt, only_sign != 0, stats);
+  Loader<QField>::store(L, oLn, oLd); Loader<QField>::store(R, oRn, oRd); Loader<QField>::store(Transpose(f, Pt), oPn, oPd);
+  return g_overflow ? -g_overflow : 0;
+}
+// bin/rotater.sh:75-83
+int orc_rotater(int right, int m, int k, int n, int r, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd, const int64_t* Pn,
+                const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd, int64_t* oPn, int64_t* oPd) {
+  g_overflow = 0;
+  QField f;
+  const Mat<QField> L = Loader<QField>::load(f, r, m * k, Ln, Ld), R = Loader<QField>::load(f, r, k * n, Rn, Rd), P = Loader<QField>::load(f, m * n, r, Pn, Pd);
+  Mat<QField> Lr, Rr, Pr;
+  if (right) { Lr = columnsSwap(f, Transpose(f, P), (size_t)n); Rr = L; Pr = Transpose(f, columnsSwap(f, R, (size_t)n)); }
+  else { Lr = R; Rr = columnsSwap(f, Transpose(f, P), (size_t)n); Pr = Transpose(f, columnsSwap(f, L, (size_t)k)); }
+  Loader<QField>::store(Lr, oLn, oLd); Loader<QField>::store(Rr, oRn, oRd); Loader<QField>::store(Pr, oPn, oPd);
+  return g_overflow ? -g_overflow : 0;
+}
+}  // extern "C"

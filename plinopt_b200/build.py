@@ -24,7 +24,7 @@ def _nvcc():
 
 
 def _deps(src):
-    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "plo_device.cuh"), os.path.join(CSRC, "host", "exact.hpp"), os.path.join(CSRC, "host", "sparsify_host.hpp"), os.path.join(CSRC, "host", "matrix_io.hpp"), os.path.join(CSRC, "host", "slp.hpp"), os.path.join(CSRC, "host", "factor_host.hpp"), os.path.join(CSRC, "host", "dependency_host.hpp"),
+    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "plo_device.cuh"), os.path.join(CSRC, "host", "exact.hpp"), os.path.join(CSRC, "host", "sparsify_host.hpp"), os.path.join(CSRC, "host", "matrix_io.hpp"), os.path.join(CSRC, "host", "slp.hpp"), os.path.join(CSRC, "host", "factor_host.hpp"), os.path.join(CSRC, "host", "dependency_host.hpp"), os.path.join(CSRC, "host", "negate_host.hpp"),
             os.path.join(os.path.dirname(HERE), "include", "plinopt_b200.h"), os.path.abspath(__file__)]
     return max(os.path.getmtime(d) for d in deps if os.path.exists(d))
 
@@ -66,7 +66,7 @@ def build_library(force=False, verbose=False):
 
 CLI_DIR = os.path.join(HERE, "cli")
 BIN_DIR = os.path.join(os.path.dirname(HERE), "bin")
-CLIS = ["sparsifier", "orbiter", "MMchecker", "factorizer", "dependency"]
+CLIS = ["sparsifier", "orbiter", "MMchecker", "factorizer", "dependency", "negater", "rotater"]
 
 
 def build_clis(force=False):

@@ -30,7 +30,7 @@ SYMBOLS = [
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
     "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
     "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
-    "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender",
+    "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender", "plo_negater", "plo_rotater",
 ]
 
 
@@ -551,3 +551,36 @@ def depender(M, level, maxnumcoeff=11, q=0, user=(), max_hits=1 << 20, text_cap=
     out = [(h.depth, h.pos, tuple(h.rows), tuple(h.coefs)) for h in hits[:k]]
     coeffs = [Fraction(int(a), int(b)) for a, b in zip(cn[:ncoef.value], cd[:ncoef.value])]
     return dict(hits=out, nhits=nh.value, ncand=nc.value, coeffs=coeffs, text=text.value.decode())
+
+
+# --------------------------------------------------------------------------
+# host-only passes around a sweep
+# --------------------------------------------------------------------------
+def _triple_pass(fname, head, L, R, P, shapes, stats_words=0):
+    Ln, Ld = _numden(L); Rn, Rd = _numden(R); Pn, Pd = _numden(P)
+    outs = []
+    for shp in shapes:
+        outs += [np.zeros(shp, dtype=np.int64), np.ones(shp, dtype=np.int64)]
+    st = np.zeros(max(stats_words, 1), dtype=np.uint64)
+    f = getattr(lib(), fname)
+    f.argtypes = [C.c_int] * len(head) + [C.c_void_p] * (12 + (1 if stats_words else 0))
+    args = list(head) + [_ptr(a) for a in (Ln, Ld, Rn, Rd, Pn, Pd)] + [_ptr(o) for o in outs] + ([_ptr(st)] if stats_words else [])
+    rc = _check(f(*args), allow=(3,))
+    return rc, [_fractions(outs[2 * t], outs[2 * t + 1]) for t in range(3)], [int(v) for v in st]
+
+
+def negater(L, R, P, only_sign=False):
+    """plo_negater: returns ((L', R', P'), stats[12])."""
+    _, mats, st = _triple_pass("plo_negater", [1 if only_sign else 0, len(L), len(L[0]), len(R[0]), len(P)], L, R, P,
+                               [(len(L), len(L[0])), (len(R), len(R[0])), (len(P), len(P[0]))], 12)
+    return mats, st
+
+
+def rotater(L, R, P, right=False):
+    """plo_rotater: returns (rc, (L', R', P'))."""
+    from . import hm
+    m, k, n = hm.LRP2MM(L, R, P)
+    r = len(L)
+    shapes = [(r, m * n), (r, m * k), (n * k, r)] if right else [(r, k * n), (r, m * n), (m * k, r)]
+    rc, mats, _ = _triple_pass("plo_rotater", [1 if right else 0, r, len(L[0]), len(R[0]), len(P)], L, R, P, shapes)
+    return rc, mats

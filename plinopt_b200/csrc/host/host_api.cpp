@@ -15,6 +15,7 @@
 #include "dependency_host.hpp"
 #include "factor_host.hpp"
 #include "matrix_io.hpp"
+#include "negate_host.hpp"
 #include "slp.hpp"
 #include "sparsify_host.hpp"
 
@@ -526,6 +527,52 @@ int plo_orbiter_modp(uint64_t q, int mode, uint64_t seed, uint64_t loops, int r,
     return PLO_OK;
   } catch (const RangeError& e) {
     plo::set_error("plo_orbiter_modp: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
+int plo_negater(int only_sign, int r, int Lcols, int Rcols, int Prows, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                const int64_t* Pn, const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd, int64_t* oPn, int64_t* oPd,
+                uint64_t* stats) {
+  if (!Ln || !Rn || !Pn || !oLn || !oLd || !oRn || !oRd || !oPn || !oPd || r < 1 || Lcols < 1 || Rcols < 1 || Prows < 1) {
+    plo::set_error("plo_negater: bad argument");
+    return PLO_E_ARG;
+  }
+  try {
+    QField Q;
+    Dense<QField> L = load(Q, (size_t)r, (size_t)Lcols, Ln, Ld), R = load(Q, (size_t)r, (size_t)Rcols, Rn, Rd);
+    Dense<QField> Pt = transposed(load(Q, (size_t)Prows, (size_t)r, Pn, Pd));
+    const NegaterStats st = Negater().run(L, R, Pt, only_sign != 0);
+    store(L, oLn, oLd); store(R, oRn, oRd); store(transposed(Pt), oPn, oPd);
+    if (stats) {
+      stats[0] = st.gcd_before; stats[1] = st.gcd_after; stats[2] = st.swaps;
+      for (int t = 0; t < 3; ++t) { stats[3 + t] = st.neg_before[t]; stats[6 + t] = st.neg_after[t]; stats[9 + t] = st.entries[t]; }
+    }
+    return PLO_OK;
+  } catch (const RangeError& e) {
+    plo::set_error("plo_negater: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
+int plo_rotater(int right, int r, int Lcols, int Rcols, int Prows, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                const int64_t* Pn, const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd, int64_t* oPn, int64_t* oPd) {
+  if (!Ln || !Rn || !Pn || !oLn || !oLd || !oRn || !oRd || !oPn || !oPd || r < 1 || Lcols < 1 || Rcols < 1 || Prows < 1) {
+    plo::set_error("plo_rotater: bad argument");
+    return PLO_E_ARG;
+  }
+  int m, k, n;
+  plo_LRP2MM(Lcols, Rcols, Prows, &m, &k, &n);
+  if (Lcols != m * k || Rcols != k * n || Prows != m * n) { plo::set_error("plo_rotater: outer dimension mismatch"); return 3; }
+  try {
+    QField Q;
+    const Dense<QField> L = load(Q, (size_t)r, (size_t)Lcols, Ln, Ld), R = load(Q, (size_t)r, (size_t)Rcols, Rn, Rd), P = load(Q, (size_t)Prows, (size_t)r, Pn, Pd);
+    Dense<QField> Lr, Rr, Pr;
+    rotate(right != 0, (size_t)k, (size_t)n, L, R, P, Lr, Rr, Pr);
+    store(Lr, oLn, oLd); store(Rr, oRn, oRd); store(Pr, oPn, oPd);
+    return PLO_OK;
+  } catch (const RangeError& e) {
+    plo::set_error("plo_rotater: %s", e.what());
     return PLO_E_RANGE;
   }
 }

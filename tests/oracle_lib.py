@@ -315,3 +315,33 @@ def depender(M, level, maxnumcoeff=11, p=0, user=(), max_hits=1 << 20):
     out = [(int(h[0]), int(h[1]), tuple(int(x) for x in h[2:7]), tuple(int(x) for x in h[7:12])) for h in hits[:k]]
     coeffs = [Fraction(int(a), int(b)) for a, b in zip(cn[:ncoef.value], cd[:ncoef.value])]
     return dict(hits=out, nhits=nh.value, ncand=nc.value, coeffs=coeffs)
+
+
+def _triple_call(fname, head_args, L, R, P, out_shapes, stats_words=0):
+    Ln, Ld = numden(L); Rn, Rd = numden(R); Pn, Pd = numden(P)
+    outs = []
+    for shp in out_shapes:
+        outs += [np.zeros(shp, dtype=np.int64), np.ones(shp, dtype=np.int64)]
+    st = np.zeros(max(stats_words, 1), dtype=np.uint64)
+    f = getattr(lib(), fname)
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * len(head_args) + [C.c_void_p] * (12 + (1 if stats_words else 0))
+    args = list(head_args) + [a.ctypes.data for a in (Ln, Ld, Rn, Rd, Pn, Pd)] + [o.ctypes.data for o in outs] + ([st.ctypes.data] if stats_words else [])
+    rc = f(*args)
+    assert rc == 0, f"oracle error {rc}"
+    mats = [[[Fraction(int(a), int(b)) for a, b in zip(ra, rb)] for ra, rb in zip(outs[2 * t], outs[2 * t + 1])] for t in range(3)]
+    return mats, [int(v) for v in st]
+
+
+def negater(L, R, P, only_sign=False):
+    """src/negater.cpp:117-209: returns ((L', R', P'), stats[12])."""
+    return _triple_call("orc_negater", [1 if only_sign else 0, len(L), len(L[0]), len(R[0]), len(P)], L, R, P,
+                        [(len(L), len(L[0])), (len(R), len(R[0])), (len(P), len(P[0]))], 12)
+
+
+def rotater(L, R, P, right=False):
+    """bin/rotater.sh:75-83: the rotated triple."""
+    m, k, n = LRP2MM(L, R, P)
+    r = len(L)
+    shapes = [(r, m * n), (r, m * k), (n * k, r)] if right else [(r, k * n), (r, m * n), (m * k, r)]
+    return _triple_call("orc_rotater", [1 if right else 0, m, k, n, r], L, R, P, shapes)[0]

@@ -93,3 +93,19 @@ def test_orbiter_cli_modular(capi, tmp_path):
         outs = [f.replace(".sms", ".nnz.sms") for f in files]
         q = subprocess.run([os.path.join(BIN, "MMchecker"), "-m", "513083"] + outs, capture_output=True, text=True, timeout=300)
         assert q.returncode == 0 and "SUCCESS: correct 2x2x2" in q.stderr
+
+
+def test_negater_and_rotater_cli(capi, tmp_path):
+    """src/negater.cpp (L.neg.sms ...) and bin/rotater.sh (<stem>_left_L.sms ..., then MMchecker of the rotated algorithm)."""
+    files = write_triple(tmp_path, "3x4x7_63_rational")
+    p = subprocess.run([os.path.join(BIN, "negater")] + files, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "# NEGs:" in p.stderr and "# GCDs:" in p.stderr, p.stderr
+    outs = [f.replace(".sms", ".neg.sms") for f in files]
+    (eL, eR, eP), _ = O.negater(*O.triple("3x4x7_63_rational"))
+    assert [hm.read_sms(o) for o in outs] == [eL, eR, eP]
+    q = subprocess.run([os.path.join(BIN, "MMchecker")] + outs, capture_output=True, text=True, timeout=300)
+    assert q.returncode == 0 and "SUCCESS: correct 3x4x7" in q.stderr
+    p = subprocess.run([os.path.join(BIN, "rotater"), "-r"] + files, capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert p.returncode == 0 and "SUCCESS: correct 7x3x4" in p.stderr, p.stderr
+    rot = [hm.read_sms(str(tmp_path / f"3x4x7_63_rational_right_{x}.sms")) for x in "LRP"]
+    assert rot == O.rotater(*O.triple("3x4x7_63_rational"), right=True)
