@@ -272,10 +272,21 @@ __device__ __forceinline__ void transform_row_packed(const int* __restrict__ A, 
       int v = 0;
 #pragma unroll
       for (int j = 0; j < CA; ++j) v += X[j] * (TR ? Rm[y * CA + j] : Rm[j * CA + y]);
-      const int hi = (v + 0x8000) >> 16;
-      const int lo = (int)(short)(v & 0xFFFF);
-      consume<MEASURE>(acc, lo, den);
-      if (2 * xp + 1 < RA) consume<MEASURE>(acc, hi, den);
+      if (MEASURE == PLO_MEASURE_NNZ) {
+        // both lanes are classified in packed form (DPX 16x2 min): w holds lane + 0x8000 in each half (the +0x8000 of the low
+        // half also absorbs the borrow of the encoding), a half of w ^ c is zero iff the lane equals c - 0x8000.
+        // acc.nnz += [lane != 0], acc.nno += [|lane| != den], per half; score_candidate turns the second count into nno
+        // (a phantom upper lane of an odd last pair is 0: it adds nothing to nnz and 1 to the second count, like every zero).
+        const unsigned w = (unsigned)v + 0x80008000u;
+        const unsigned d2 = (unsigned)den * 0x00010001u;
+        acc.nnz += (int)__vimin3_u16x2(w ^ 0x80008000u, 0x00010001u, 0x00010001u);
+        acc.nno += (int)__vimin3_u16x2(w ^ (0x80008000u + d2), w ^ (0x80008000u - d2), 0x00010001u);
+      } else {
+        const int hi = (v + 0x8000) >> 16;
+        const int lo = (int)(short)(v & 0xFFFF);
+        consume<MEASURE>(acc, lo, den);
+        if (2 * xp + 1 < RA) consume<MEASURE>(acc, hi, den);
+      }
     }
   }
 }
@@ -351,8 +362,20 @@ __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict_
       transform_row<K, N, false, false, MEASURE>(Rc + l * K * N, Vi, W, den.y, aR);  // V^-1 B W
       transform_row<M, N, false, true, MEASURE>(Pc + l * M * N, U, Wi, den.z, aP);   // U C W^-T
     }
-    nnz += aL.nnz + aR.nnz + aP.nnz;
-    nno += aL.nno + aR.nno + aP.nno;
+#ifdef __CUDA_ARCH__
+    if (PACK && MEASURE == PLO_MEASURE_NNZ) {
+      // packed per-half counters: nnz = sum of halves; nno = nnz - #(|y| == den) = nnz - (lanes - #(|y| != den))
+      constexpr int lanesL = 2 * ((M + 1) / 2) * K, lanesR = 2 * ((K + 1) / 2) * N, lanesP = 2 * ((M + 1) / 2) * N;
+      const int zL = (aL.nnz & 0xFFFF) + (aL.nnz >> 16), zR = (aR.nnz & 0xFFFF) + (aR.nnz >> 16), zP = (aP.nnz & 0xFFFF) + (aP.nnz >> 16);
+      const int dL = (aL.nno & 0xFFFF) + (aL.nno >> 16), dR = (aR.nno & 0xFFFF) + (aR.nno >> 16), dP = (aP.nno & 0xFFFF) + (aP.nno >> 16);
+      nnz += zL + zR + zP;
+      nno += (zL + zR + zP) - (lanesL + lanesR + lanesP - dL - dR - dP);
+    } else
+#endif
+    {
+      nnz += aL.nnz + aR.nnz + aP.nnz;
+      nno += aL.nno + aR.nno + aP.nno;
+    }
     if (MEASURE == PLO_MEASURE_G2 || MEASURE == MEASURE_BOTH) {
       // growthfactor.cpp:117-125: s += norm2(L[i])*norm2(R[i])*norm2(Pt[i]); no FMA contraction
 #ifdef __CUDA_ARCH__
