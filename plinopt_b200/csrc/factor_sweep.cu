@@ -168,8 +168,12 @@ __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams
       if (nzmask == 0) continue;  // dependent on the rows kept so far
       uint32_t vt = fs_reduce(at, P);
       vt = sub_mod(lane == nb ? P.one : 0u, vt, P.p);  // e_nb - sum c_i T_i
-      const int pcn = __ffs(nzmask) - 1;
-      const uint32_t ip = mont_inv(__shfl_sync(0xffffffffu, vr, pcn), P);
+      // pivot: a coordinate equal to +-1 if there is one (its inverse is itself: no modular inversion), else the first
+      // non-zero one.  The coordinates x of the solved rows do not depend on this choice (x.B = row has one solution).
+      const unsigned unit = __ballot_sync(0xffffffffu, vr == P.one || vr == P.mone);
+      const int pcn = __ffs(unit ? unit : nzmask) - 1;
+      const uint32_t pv = __shfl_sync(0xffffffffu, vr, pcn);
+      const uint32_t ip = unit ? pv : mont_inv(pv, P);
       const uint32_t wr = mont_mul(vr, ip, P.p, P.pinv), wt = mont_mul(vt, ip, P.p, P.pinv);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
