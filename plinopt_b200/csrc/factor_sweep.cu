@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if (i < nb) {
-          const uint32_t c = __shfl_sync(0xffffffffu, v, pc[i]);
+          const uint32_t c = Msh[row * 32 + pc[i]];  // v[pivot column i]: warp-uniform address, one broadcast LDS
           fs_mac(ar, c, Rj[i]);
           fs_mac(at, c, Tj[i]);
         }
@@ -195,12 +195,10 @@ __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams
       for (int t = 0; t < P.r; ++t) {
         const int row = perm[t];
         if (t < P.k) { nnz_alt += 1; nnz_cob += nnzsh[row]; continue; }  // identity row of Res, row of CoB
-        const uint32_t v = Msh[row * 32 + lane];
         FsAcc ax;
         ax.a0 = ax.a1 = ax.a2 = 0;
 #pragma unroll
-        for (int i = 0; i < N; ++i)
-          if (i < nb) fs_mac(ax, __shfl_sync(0xffffffffu, v, pc[i]), Tj[i]);
+        for (int i = 0; i < N; ++i) fs_mac(ax, Msh[row * 32 + pc[i]], Tj[i]);  // rows i >= n of T are zero: no guard needed
         const uint32_t x = fs_reduce(ax, P);  // coordinate of `row` on the lane-th independent row
         const bool nz = lane < P.n && x != 0;
         nnz_alt += __popc(__ballot_sync(0xffffffffu, nz));
