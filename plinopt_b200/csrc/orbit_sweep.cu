@@ -588,6 +588,9 @@ static ModpLaunch find_modp(int m, int k, int n) {
   if (m == 3 && k == 3 && n == 3) return &modp_launch<3, 3, 3>;
   if (m == 4 && k == 4 && n == 4) return &modp_launch<4, 4, 4>;
   if (m == 3 && k == 4 && n == 7) return &modp_launch<3, 4, 7>;
+  if (m == 3 && k == 3 && n == 6) return &modp_launch<3, 3, 6>;
+  if (m == 3 && k == 6 && n == 3) return &modp_launch<3, 6, 3>;
+  if (m == 6 && k == 3 && n == 3) return &modp_launch<6, 3, 3>;
   return nullptr;
 }
 
@@ -648,7 +651,7 @@ struct Shape {
 };
 
 // (m, k, n, unrolled r); r-specialised entries come first, the generic (ru = 0) entry of a shape last
-#define PLO_ORBIT_SHAPES(X) X(2, 2, 2, 7) X(2, 2, 2, 0) X(3, 3, 3, 0) X(4, 4, 4, 0) X(3, 4, 7, 0)
+#define PLO_ORBIT_SHAPES(X) X(2, 2, 2, 7) X(2, 2, 2, 0) X(3, 3, 3, 0) X(4, 4, 4, 0) X(3, 4, 7, 0) X(3, 3, 6, 0) X(3, 6, 3, 0) X(6, 3, 3, 0)
 
 static const ShapeOps* find_shape(int m, int k, int n, int r) {
 #define X(a, b, c, d) Shape<a, b, c, d>::ops(),

@@ -36,7 +36,8 @@ def test_c2_winograd_exhaustive_table(capi):
 
 
 @pytest.mark.parametrize("stem,count", [("2x2x2_7_Winograd", 20000), ("2x2x2_7_DPS-smallrat-12.2034", 20000),
-                                        ("3x3x3_23_58", 6000), ("4x4x4_48_rational", 3000), ("3x4x7_63_rational", 1500)])
+                                        ("3x3x3_23_58", 6000), ("4x4x4_48_rational", 3000), ("3x4x7_63_rational", 1500),
+                                        ("3x3x6_40", 1500), ("3x6x3_40", 1500), ("6x3x3_40", 1500)])
 def test_philox_table_parity(capi, stem, count):
     (L, R, P), mkn, (Li, Ri, Pi), dens = ints(stem)
     lo = 2 ** 33 + 17
@@ -121,7 +122,8 @@ def residues(M, p):
 
 @pytest.mark.parametrize("stem,count,p", [("2x2x2_7_Winograd", 20000, 2147483647), ("2x2x2_7_DPS-accurate", 8000, 513083),
                                           ("3x3x3_23_58", 4000, 101), ("4x4x4_48_rational", 2000, 2147483647),
-                                          ("3x4x7_63_rational", 1000, 1000003), ("2x2x2_7_Strassen", 5000, 3)])
+                                          ("3x4x7_63_rational", 1000, 1000003), ("2x2x2_7_Strassen", 5000, 3),
+                                          ("3x6x3_40", 800, 2147483647), ("6x3x3_40", 800, 513083)])
 def test_modular_orbit_sweep(capi, stem, count, p):
     """`orbiter -m p` (src/orbiter.cpp:232-234, 419-426): the whole search runs in Z/pZ; per-candidate (nnz, nno) and the
     winner are bit-exact against the oracle over the same field."""
