@@ -117,3 +117,20 @@ def test_wide_matrices_span_several_column_slabs(capi, mkn, scaled):
     val = Pc[4].copy(); val[-1] = (int(val[-1]) + 1) % P31
     v, ok = capi.mmcheck_batch(P31, mkn, r, Lc, Rc, (Pc[0], Pc[1], Pc[2], Pc[3], val), seed=3, batch=70)
     assert v == 1 and not ok.any()
+
+
+@pytest.mark.parametrize("p", [2, 3, 65537, 4294967291])
+@pytest.mark.parametrize("stem", ["2x2x2_7_Strassen", "3x3x3_23_58", "4x4x4_49_156"])
+def test_extreme_moduli(capi, stem, p):
+    """Smallest moduli (factors of 2 are stripped down to 2, src/MMchecker.cpp:123-126) and the largest 32-bit prime:
+    per-sample verdicts equal the oracle's, also for a corrupted triple."""
+    L, R, P = O.triple(stem)  # integer coefficients: valid modulo every p
+    mkn = hm.LRP2MM(L, R, P)
+    m, k, n = mkn
+    B = 33
+    rng = np.random.default_rng(p % 1000)
+    ua = rng.integers(0, p, (B, m * k)).astype(np.uint32); ub = rng.integers(0, p, (B, k * n)).astype(np.uint32)
+    for LL in (L, [[v + (1 if (i, j) == (2, 1) else 0) for j, v in enumerate(row)] for i, row in enumerate(L)]):
+        v, ok = capi.mmcheck_batch(p, mkn, len(L), hm.csr_modp(LL, p), hm.csr_modp(R, p), hm.csr_modp(P, p), batch=B, ua=ua, ub=ub)
+        exp = [O.mmcheck_modp(p, LL, R, P, ua[b].astype(np.int64), ub[b].astype(np.int64)) for b in range(B)]
+        assert ok.tolist() == [1 - e for e in exp] and v == (1 if any(exp) else 0)
