@@ -39,6 +39,7 @@ int plo_version(void);
 int plo_device_count(void);           /* number of visible CUDA devices (0 => every call returns PLO_E_NODEVICE) */
 int plo_set_device(int device);
 const char* plo_last_error(void);     /* thread-local message of the last failing call */
+void plo_release_workspace(void);     /* returns the cached device blocks of destroyed plans to the driver */
 
 /* ---------------------------------------------------------------------------
  * Sparsifier candidate search.

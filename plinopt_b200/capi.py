@@ -21,6 +21,7 @@ NO_INDEX = 2 ** 64 - 1
 
 # every symbol include/plinopt_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
+    "plo_release_workspace",
     "plo_version", "plo_device_count", "plo_set_device", "plo_last_error",
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",

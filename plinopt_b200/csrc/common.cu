@@ -1,6 +1,11 @@
 // common.cu -- error plumbing, device queries, version.
 #include <stdarg.h>
 
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
 #include "plo_device.cuh"
 
 namespace plo {
@@ -31,9 +36,77 @@ int sm_count() {
   return n > 0 ? n : 148;
 }
 
+// ---- device workspace pool (see plo_device.cuh) ----
+namespace {
+struct Pool {
+  std::mutex mu;
+  std::map<std::pair<int, size_t>, std::vector<void*>> free_blocks;  // (device, class bytes) -> cached blocks
+  std::unordered_map<void*, std::pair<int, size_t>> owner;           // live and cached blocks
+  size_t cached_bytes = 0;
+};
+Pool& pool() { static Pool p; return p; }
+size_t size_class(size_t bytes) {
+  if (bytes < 512) return 512;
+  if (bytes > (64u << 20)) return (bytes + (16u << 20) - 1) / (16u << 20) * (16u << 20);
+  size_t c = 512;
+  while (c < bytes) c <<= 1;
+  return c;
+}
+constexpr size_t kPoolCap = 8ull << 30;  // bytes kept cached per process
+}  // namespace
+
+cudaError_t pool_alloc_bytes(void** p, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const size_t cls = size_class(bytes);
+  Pool& P = pool();
+  {
+    std::lock_guard<std::mutex> g(P.mu);
+    auto it = P.free_blocks.find({dev, cls});
+    if (it != P.free_blocks.end() && !it->second.empty()) {
+      *p = it->second.back();
+      it->second.pop_back();
+      P.cached_bytes -= cls;
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(p, cls);
+  if (e != cudaSuccess) {  // give the cache back and retry once
+    cudaGetLastError();
+    plo_release_workspace();
+    e = cudaMalloc(p, cls);
+    if (e != cudaSuccess) return e;
+  }
+  std::lock_guard<std::mutex> g(P.mu);
+  P.owner[*p] = {dev, cls};
+  return cudaSuccess;
+}
+
+void pool_free(void* p) {
+  if (!p) return;
+  cudaDeviceSynchronize();  // nothing in flight may still use the block when it is handed out again
+  Pool& P = pool();
+  std::lock_guard<std::mutex> g(P.mu);
+  auto it = P.owner.find(p);
+  if (it == P.owner.end()) { cudaFree(p); return; }
+  if (P.cached_bytes + it->second.second > kPoolCap) { cudaFree(p); P.owner.erase(it); return; }
+  P.free_blocks[it->second].push_back(p);
+  P.cached_bytes += it->second.second;
+}
+
 }  // namespace plo
 
 extern "C" {
+
+void plo_release_workspace(void) {
+  plo::Pool& P = plo::pool();
+  std::lock_guard<std::mutex> g(P.mu);
+  for (auto& kv : P.free_blocks)
+    for (void* b : kv.second) { cudaFree(b); P.owner.erase(b); }
+  P.free_blocks.clear();
+  P.cached_bytes = 0;
+}
 
 int plo_version(void) { return 100; }
 

@@ -167,9 +167,9 @@ static int dep_run(uint32_t p, int r, int n, int c, int level, const int64_t* ba
   unsigned char* d_combos = nullptr;
   DepBlock* d_blocks = nullptr;
   const uint64_t cap = max_hits ? max_hits : 1;
-  auto cleanup = [&]() { cudaFree(d_base); cudaFree(d_prod); cudaFree(d_counter); cudaFree(d_hits); cudaFree(d_combos); cudaFree(d_blocks); };
-  if (cudaMalloc(&d_base, hbase.size() * sizeof(T)) != cudaSuccess || cudaMalloc(&d_prod, hprod.size() * sizeof(T)) != cudaSuccess ||
-      cudaMalloc(&d_counter, 8) != cudaSuccess || cudaMalloc(&d_hits, cap * sizeof(DepRawHit)) != cudaSuccess ||
+  auto cleanup = [&]() { pool_free(d_base); pool_free(d_prod); pool_free(d_counter); pool_free(d_hits); pool_free(d_combos); pool_free(d_blocks); };
+  if (pool_alloc(&d_base, hbase.size() * sizeof(T)) != cudaSuccess || pool_alloc(&d_prod, hprod.size() * sizeof(T)) != cudaSuccess ||
+      pool_alloc(&d_counter, 8) != cudaSuccess || pool_alloc(&d_hits, cap * sizeof(DepRawHit)) != cudaSuccess ||
       cudaMemcpy(d_base, hbase.data(), hbase.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d_prod, hprod.data(), hprod.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
     set_error("plo_dependency_explore: %s", cudaGetErrorString(cudaGetLastError()));
@@ -214,9 +214,9 @@ static int dep_run(uint32_t p, int r, int n, int c, int level, const int64_t* ba
       }
     }
     if (blocks.empty()) continue;
-    cudaFree(d_combos); cudaFree(d_blocks);
+    pool_free(d_combos); pool_free(d_blocks);
     d_combos = nullptr; d_blocks = nullptr;
-    if (cudaMalloc(&d_combos, combos.size()) != cudaSuccess || cudaMalloc(&d_blocks, blocks.size() * sizeof(DepBlock)) != cudaSuccess ||
+    if (pool_alloc(&d_combos, combos.size()) != cudaSuccess || pool_alloc(&d_blocks, blocks.size() * sizeof(DepBlock)) != cudaSuccess ||
         cudaMemcpy(d_combos, combos.data(), combos.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(d_blocks, blocks.data(), blocks.size() * sizeof(DepBlock), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(d_counter, 0, 8) != cudaSuccess) {

@@ -256,7 +256,7 @@ extern "C" {
 
 void plo_factor_plan_destroy(plo_factor_plan* pl) {
   if (!pl) return;
-  cudaFree(pl->d_M); cudaFree(pl->d_nnz); cudaFree(pl->d_bb);
+  pool_free(pl->d_M); pool_free(pl->d_nnz); pool_free(pl->d_bb);
   delete pl;
 }
 
@@ -294,8 +294,8 @@ int plo_factor_plan_create(plo_factor_plan** plan, uint32_t p, int r, int n, int
 #undef PLO_FS_CASE
   }
   pl->grid = sm_count() * bps;
-  const bool ok = cudaMalloc(&pl->d_M, hM.size() * 4) == cudaSuccess && cudaMalloc(&pl->d_nnz, hn.size() * 4) == cudaSuccess &&
-                  cudaMalloc(&pl->d_bb, sizeof(Key) * pl->grid) == cudaSuccess &&
+  const bool ok = pool_alloc(&pl->d_M, hM.size() * 4) == cudaSuccess && pool_alloc(&pl->d_nnz, hn.size() * 4) == cudaSuccess &&
+                  pool_alloc(&pl->d_bb, sizeof(Key) * pl->grid) == cudaSuccess &&
                   cudaMemcpy(pl->d_M, hM.data(), hM.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
                   cudaMemcpy(pl->d_nnz, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { set_error("plo_factor_plan_create: %s", cudaGetErrorString(cudaGetLastError())); plo_factor_plan_destroy(pl); return PLO_E_CUDA; }
@@ -349,12 +349,12 @@ int plo_factor_sweep(uint32_t p, int r, int n, int k, const uint32_t* M, uint64_
     none.primary = ~0ull; none.index = ~0ull;
     std::vector<Key> init(pl->grid, none);
     if (cudaMemcpy(pl->d_bb, init.data(), sizeof(Key) * pl->grid, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMalloc(&d_tab, cnt ? cnt * 4 : 4) != cudaSuccess) {
+        pool_alloc(&d_tab, cnt ? cnt * 4 : 4) != cudaSuccess) {
       set_error("plo_factor_sweep: %s", cudaGetErrorString(cudaGetLastError())); plo_factor_plan_destroy(pl); return PLO_E_CUDA;
     }
     if (hi > lo) pl->launch(fs_grid(pl, lo, hi), pl->smem, nullptr, pl->P, pl->d_M, pl->d_nnz, lo, hi, pl->d_bb, d_tab);
     if (cudaMemcpy(table, d_tab, cnt * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("plo_factor_sweep: %s", cudaGetErrorString(cudaGetLastError())); rc = PLO_E_CUDA; }
-    cudaFree(d_tab);
+    pool_free(d_tab);
   }
   if (!rc && best) rc = plo_factor_plan_result(pl, nullptr, best);
   plo_factor_plan_destroy(pl);

@@ -300,8 +300,8 @@ extern "C" {
 
 void plo_lincomb_plan_destroy(plo_lincomb_plan* pl) {
   if (!pl) return;
-  cudaFree(pl->d_tables); cudaFree(pl->d_zflag); cudaFree(pl->d_phi); cudaFree(pl->d_nphi);
-  cudaFree(pl->d_coef); cudaFree(pl->d_seed); cudaFree(pl->d_result);
+  pool_free(pl->d_tables); pool_free(pl->d_zflag); pool_free(pl->d_phi); pool_free(pl->d_nphi);
+  pool_free(pl->d_coef); pool_free(pl->d_seed); pool_free(pl->d_result);
   delete pl;
 }
 
@@ -400,13 +400,13 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
   if (pl->grid < 1) pl->grid = 1;
 
   auto up = [&](void** dst, const void* src, size_t bytes) -> bool {
-    if (cudaMalloc(dst, bytes ? bytes : 1) != cudaSuccess) return false;
+    if (pool_alloc(dst, bytes ? bytes : 1) != cudaSuccess) return false;
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
   bool ok = up(&pl->d_tables, tables.data(), tables.size()) && up((void**)&pl->d_zflag, zflag.data(), zflag.size()) &&
             up((void**)&pl->d_phi, phi.data(), phi.size() * 8) && up((void**)&pl->d_nphi, nphi.data(), nphi.size() * 4) &&
             up((void**)&pl->d_coef, cf.data(), cf.size() * 8) && up((void**)&pl->d_seed, pl->h_seed.data(), pl->h_seed.size() * 8) &&
-            cudaMalloc((void**)&pl->d_result, (size_t)nbatch * 8) == cudaSuccess;
+            pool_alloc(&pl->d_result, (size_t)nbatch * 8) == cudaSuccess;
   if (!ok) {
     set_error("lincomb search: device allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     plo_lincomb_plan_destroy(pl);

@@ -463,20 +463,20 @@ static int build_slab_csr(const plo_csr* h, int groups, DevSlabCsr* d) {
     }
   }
   d->nchunks = (int)table.size();
-  PLO_CUDA(cudaMalloc(&d->chunk, sizeof(ChunkDesc) * table.size()));
-  PLO_CUDA(cudaMalloc(&d->blob, blob.size() ? blob.size() : 16));
+  PLO_CUDA(pool_alloc(&d->chunk, sizeof(ChunkDesc) * table.size()));
+  PLO_CUDA(pool_alloc(&d->blob, blob.size() ? blob.size() : 16));
   PLO_CUDA(cudaMemcpy(d->chunk, table.data(), sizeof(ChunkDesc) * table.size(), cudaMemcpyHostToDevice));
   PLO_CUDA(cudaMemcpy(d->blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   return PLO_OK;
 }
-static void free_slab_csr(DevSlabCsr* d) { cudaFree(d->chunk); cudaFree(d->blob); }
+static void free_slab_csr(DevSlabCsr* d) { pool_free(d->chunk); pool_free(d->blob); }
 
 extern "C" {
 
 void plo_mmcheck_plan_destroy(plo_mmcheck_plan* pl) {
   if (!pl) return;
   free_slab_csr(&pl->L); free_slab_csr(&pl->R); free_slab_csr(&pl->P);
-  cudaFree(pl->ua); cudaFree(pl->ub); cudaFree(pl->va); cudaFree(pl->vb); cudaFree(pl->vc); cudaFree(pl->wc); cudaFree(pl->bad); cudaFree(pl->stage);
+  pool_free(pl->ua); pool_free(pl->ub); pool_free(pl->va); pool_free(pl->vb); pool_free(pl->vc); pool_free(pl->wc); pool_free(pl->bad); pool_free(pl->stage);
   delete pl;
 }
 
@@ -503,7 +503,7 @@ int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, i
   if (rc) { plo_mmcheck_plan_destroy(pl); return rc; }
   const size_t G32 = (size_t)pl->groups * 32;
   const size_t stage = (size_t)batch * (size_t)(m * k > k * n ? m * k : k * n);
-  auto zalloc = [](unsigned int** ptr, size_t words) { return cudaMalloc(ptr, 4 * words) == cudaSuccess && cudaMemset(*ptr, 0, 4 * words) == cudaSuccess; };
+  auto zalloc = [](unsigned int** ptr, size_t words) { return pool_alloc(ptr, 4 * words) == cudaSuccess && cudaMemset(*ptr, 0, 4 * words) == cudaSuccess; };
   const bool ok = zalloc(&pl->ua, G32 * m * k) && zalloc(&pl->ub, G32 * k * n) && zalloc(&pl->va, G32 * r * pl->L.nslabs) &&
                   zalloc(&pl->vb, G32 * r * pl->R.nslabs) && zalloc(&pl->vc, G32 * r) && zalloc(&pl->wc, G32 * m * n * pl->P.nslabs) &&
                   zalloc(&pl->bad, (size_t)batch) && zalloc(&pl->stage, stage);

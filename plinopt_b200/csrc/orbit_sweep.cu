@@ -730,12 +730,12 @@ static int orbit_modp(uint32_t p, int m, int k, int n, int r, const int32_t* L, 
   const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((cnt + kThreads - 1) / kThreads, (uint64_t)sm_count() * 4));
   Key* d_bb = nullptr;
   uint32_t *d_nnz = nullptr, *d_nno = nullptr;
-  auto cleanup = [&]() { cudaFree(d_bb); cudaFree(d_nnz); cudaFree(d_nno); };
+  auto cleanup = [&]() { pool_free(d_bb); pool_free(d_nnz); pool_free(d_nno); };
   g_const_owner = nullptr;
   cudaError_t e = cudaMemcpyToSymbol(c_lrp, h.data(), total * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&d_bb, sizeof(Key) * grid);
-  if (e == cudaSuccess && tnnz && cnt) e = cudaMalloc(&d_nnz, cnt * 4);
-  if (e == cudaSuccess && tnno && cnt) e = cudaMalloc(&d_nno, cnt * 4);
+  if (e == cudaSuccess) e = pool_alloc(&d_bb, sizeof(Key) * grid);
+  if (e == cudaSuccess && tnnz && cnt) e = pool_alloc(&d_nnz, cnt * 4);
+  if (e == cudaSuccess && tnno && cnt) e = pool_alloc(&d_nno, cnt * 4);
   if (e == cudaSuccess) {
     launch(mode, grid, nullptr, r, mp, seed, lo, hi, d_bb, d_nnz, d_nno);
     e = cudaGetLastError();
@@ -834,7 +834,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   }
   pl->grid = sm_count() * ops->blocks_per_sm(pl->smem);
   pl->d_block_best = nullptr; pl->d_out = nullptr;
-  if (cudaMalloc(&pl->d_block_best, sizeof(Key) * pl->grid) != cudaSuccess || cudaMalloc(&pl->d_out, sizeof(plo_orbit_best)) != cudaSuccess) {
+  if (pool_alloc(&pl->d_block_best, sizeof(Key) * pl->grid) != cudaSuccess || pool_alloc(&pl->d_out, sizeof(plo_orbit_best)) != cudaSuccess) {
     set_error("orbit sweep: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     plo_orbit_plan_destroy(pl);
     return PLO_E_CUDA;
@@ -875,8 +875,8 @@ int plo_orbit_plan_result(plo_orbit_plan* pl, void* stream, plo_orbit_best* best
 void plo_orbit_plan_destroy(plo_orbit_plan* pl) {
   if (!pl) return;
   if (g_const_owner == pl) g_const_owner = nullptr;
-  if (pl->d_block_best) cudaFree(pl->d_block_best);
-  if (pl->d_out) cudaFree(pl->d_out);
+  if (pl->d_block_best) pool_free(pl->d_block_best);
+  if (pl->d_out) pool_free(pl->d_out);
   delete pl;
 }
 
@@ -907,9 +907,9 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
   const size_t cnt = (size_t)(hi - lo);
   uint32_t *d_nnz = nullptr, *d_nno = nullptr;
   double* d_g2 = nullptr;
-  auto cleanup = [&]() { cudaFree(d_nnz); cudaFree(d_nno); cudaFree(d_g2); plo_orbit_plan_destroy(pl); };
+  auto cleanup = [&]() { pool_free(d_nnz); pool_free(d_nno); pool_free(d_g2); plo_orbit_plan_destroy(pl); };
   if (cnt) {
-    if (cudaMalloc(&d_nnz, cnt * 4) != cudaSuccess || cudaMalloc(&d_nno, cnt * 4) != cudaSuccess || cudaMalloc(&d_g2, cnt * 8) != cudaSuccess) {
+    if (pool_alloc(&d_nnz, cnt * 4) != cudaSuccess || pool_alloc(&d_nno, cnt * 4) != cudaSuccess || pool_alloc(&d_g2, cnt * 8) != cudaSuccess) {
       set_error("plo_orbit_table: cudaMalloc failed"); cleanup(); return PLO_E_CUDA;
     }
     rc = orbit_upload(pl, nullptr);

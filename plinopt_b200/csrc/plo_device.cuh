@@ -25,6 +25,15 @@ int check_device();  // PLO_OK or PLO_E_NODEVICE (there is no CPU fallback)
 
 int sm_count();
 
+// ---- device workspace pool ---------------------------------------------------
+// cudaMalloc / cudaFree cost milliseconds each and a sparsifier run creates and destroys one search plan per
+// localSparsifier step: device blocks are therefore cached per device in size classes and reused
+// (plo_release_workspace() returns them to the driver).  pool_free() synchronises the device first, like cudaFree.
+cudaError_t pool_alloc_bytes(void** p, size_t bytes);
+void pool_free(void* p);
+template <class T>
+inline cudaError_t pool_alloc(T** p, size_t bytes) { return pool_alloc_bytes(reinterpret_cast<void**>(p), bytes); }
+
 // ---- Philox4x32-10 (Salmon et al. 2011); key = seed, counter = (index, block) ----
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                        uint32_t k1, uint32_t out[4]) {
