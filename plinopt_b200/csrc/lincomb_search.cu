@@ -20,6 +20,7 @@
 // Winner = maximum of the packed key (rl, cl, -index): equals the reference's
 // strict-'>' first-maximiser rule and is associative, so the warp-shuffle /
 // block / atomicMax reduction is deterministic for any launch geometry.
+#include <algorithm>
 #include <type_traits>
 #include <vector>
 
@@ -181,6 +182,118 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_kernel(const LcParams<T> p
   }
 }
 
+// ---------------------------------------------------------------------------
+// Wide outputs (m > 64, e.g. 32x32x32_15096: TM is 4 x 15096).  The m coordinates are cut into tiles of 64;
+// a block stages the T3 rows of one tile in shared memory and every thread sweeps prefixes (i,j,k) against it
+// exactly as above, but a candidate's zero count is now spread over the tiles: partial counts are accumulated
+// with one RED per (candidate, tile) into counts[c^4]; lincomb_big_pick_kernel then applies the keep-best rule.
+// ---------------------------------------------------------------------------
+constexpr int kBigTile = 64;
+
+template <typename T, bool MODP>
+__global__ void __launch_bounds__(kLcThreads) lincomb_big_count_kernel(const LcParams<T> prm, int mpad, int tiles_per_group,
+                                                                       unsigned int* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* t3s = reinterpret_cast<T*>(smem_raw);  // [c][64]
+  constexpr int VEC = 16 / sizeof(T);
+  const int b = blockIdx.z, c = prm.c;
+  const size_t tab = (size_t)c * mpad;
+  const T* __restrict__ t0 = prm.t0 + b * tab;
+  const T* __restrict__ t1 = prm.t1 + b * tab;
+  const T* __restrict__ t2 = prm.t2 + b * tab;
+  const T* __restrict__ t3 = prm.t3 + b * tab;
+  unsigned int* __restrict__ cnt = counts + (size_t)b * c * c * c * c;
+  const T SENT = (T)(~(T)0) >> (MODP ? 0 : 1);
+  const int ntiles = mpad / kBigTile;
+  const int tile0 = blockIdx.y * tiles_per_group, tile1 = min(ntiles, tile0 + tiles_per_group);
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * kLcThreads;
+  for (int tile = tile0; tile < tile1; ++tile) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < c * kBigTile / VEC; e += kLcThreads) {
+      const int l = e / (kBigTile / VEC), v = e % (kBigTile / VEC);
+      reinterpret_cast<uint4*>(t3s)[e] = reinterpret_cast<const uint4*>(t3 + (size_t)l * mpad + (size_t)tile * kBigTile)[v];
+    }
+    __syncthreads();
+    for (unsigned long long q = prm.qlo + (unsigned long long)blockIdx.x * kLcThreads + threadIdx.x; q < prm.qhi; q += nthreads) {
+      const int k = (int)(q % (unsigned)c);
+      const unsigned long long qq = q / (unsigned)c;
+      const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
+      T nb[kBigTile];
+#pragma unroll
+      for (int e = 0; e < kBigTile; ++e) {
+        const int col = tile * kBigTile + e;
+        const T a0 = t0[(size_t)i * mpad + col], a1 = t1[(size_t)j * mpad + col], a2 = t2[(size_t)col * c + k];
+        if (MODP) {
+          unsigned long long sum = (unsigned long long)a0 + a1 + a2;
+          sum -= sum >= prm.p ? prm.p : 0u;
+          sum -= sum >= prm.p ? prm.p : 0u;
+          nb[e] = (T)(sum ? prm.p - sum : 0ull);
+        } else {
+          nb[e] = (T)0 - (a0 + a1 + a2);
+        }
+        if (col >= prm.m) nb[e] = SENT;
+      }
+      for (int l = 0; l < c; ++l) {
+        const T* row = t3s + (size_t)l * kBigTile;
+        int rl = 0;
+#pragma unroll
+        for (int e4 = 0; e4 < kBigTile / VEC; ++e4) {
+          const uint4 u = reinterpret_cast<const uint4*>(row)[e4];
+          if (sizeof(T) == 4) {
+            rl += (nb[e4 * 4 + 0] == (T)u.x);
+            rl += (nb[e4 * 4 + 1] == (T)u.y);
+            rl += (nb[e4 * 4 + 2] == (T)u.z);
+            rl += (nb[e4 * 4 + 3] == (T)u.w);
+          } else {
+            rl += (nb[e4 * 2 + 0] == (T)(((unsigned long long)u.y << 32) | u.x));
+            rl += (nb[e4 * 2 + 1] == (T)(((unsigned long long)u.w << 32) | u.z));
+          }
+        }
+        if (rl) atomicAdd(cnt + q * (unsigned)c + (unsigned)l, (unsigned)rl);
+      }
+    }
+  }
+}
+
+template <typename T, bool MODP>
+__global__ void __launch_bounds__(kLcThreads) lincomb_big_pick_kernel(const LcParams<T> prm, const unsigned int* __restrict__ counts) {
+  __shared__ unsigned long long red[32];
+  const int b = blockIdx.y, c = prm.c;
+  const unsigned char* __restrict__ zf = prm.zflag + (size_t)b * 4 * c;
+  const long long* __restrict__ phi = prm.phi + b * 16;
+  const long long* __restrict__ coef = prm.coef + (size_t)b * c;
+  const int nphi = prm.nphi[b];
+  const unsigned int* __restrict__ cnt = counts + (size_t)b * c * c * c * c;
+  unsigned long long best = prm.seed[b];
+  const unsigned long long lo = prm.qlo * (unsigned)c, hi = prm.qhi * (unsigned)c;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kLcThreads + threadIdx.x; idx < hi; idx += (unsigned long long)gridDim.x * kLcThreads) {
+    const int l = (int)(idx % (unsigned)c);
+    unsigned long long q = idx / (unsigned)c;
+    const int k = (int)(q % (unsigned)c); q /= (unsigned)c;
+    const int j = (int)(q % (unsigned)c), i = (int)(q / (unsigned)c);
+    const int rl = (int)cnt[idx];
+    const int cl = prm.cl_const + zf[i] + zf[c + j] + zf[2 * c + k] + zf[3 * c + l];
+    const unsigned long long key = pack_key(rl, cl, kIdxMask - 1ull - idx);
+    if (key > best && independent<MODP>(phi, nphi, coef, prm.p, i, j, k, l)) best = key;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+    best = o > best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long v = threadIdx.x < (kLcThreads >> 5) ? red[threadIdx.x] : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
+      v = o > v ? o : v;
+    }
+    if (threadIdx.x == 0) atomicMax(prm.result + b, v);
+  }
+}
+
 __global__ void lincomb_init_kernel(unsigned long long* result, const unsigned long long* seed, int nbatch) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < nbatch) result[b] = seed[b];
@@ -224,6 +337,9 @@ struct plo_lincomb_plan {
   unsigned long long *d_seed, *d_result;
   int lsplit, ltile, grid;
   size_t smem;
+  bool big;                // m > 64: tiled count + pick kernels
+  unsigned int* d_counts;  // [nbatch][c^4] zero counts (big path)
+  int tiles_per_group, tile_groups;
 };
 
 namespace {
@@ -301,7 +417,7 @@ extern "C" {
 void plo_lincomb_plan_destroy(plo_lincomb_plan* pl) {
   if (!pl) return;
   pool_free(pl->d_tables); pool_free(pl->d_zflag); pool_free(pl->d_phi); pool_free(pl->d_nphi);
-  pool_free(pl->d_coef); pool_free(pl->d_seed); pool_free(pl->d_result);
+  pool_free(pl->d_coef); pool_free(pl->d_seed); pool_free(pl->d_result); pool_free(pl->d_counts);
   delete pl;
 }
 
@@ -315,8 +431,12 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
   }
   int rc = check_device();
   if (rc) return rc;
-  const int mpad = pad_m(m);
-  if (mpad < 0) { set_error("lincomb search: m = %d > 64 not supported by the register-resident kernel", m); return PLO_E_SHAPE; }
+  const bool big = m > 64;
+  const int mpad = big ? (m + kBigTile - 1) / kBigTile * kBigTile : pad_m(m);
+  if (big && (c > 64 || (unsigned long long)nbatch * c * c * c * c > (1ull << 28))) {
+    set_error("lincomb search: m = %d > 64 needs c <= 64 and nbatch * c^4 <= 2^28", m);
+    return PLO_E_SHAPE;
+  }
   const int nact = (n - off) < 4 ? (n - off) : 4;
 
   // canonical copies
@@ -339,6 +459,7 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
 
   plo_lincomb_plan* pl = new plo_lincomb_plan();
   pl->p = p; pl->nbatch = nbatch; pl->n = n; pl->m = m; pl->off = off; pl->c = c; pl->nprev = nprev; pl->mpad = mpad; pl->width = width;
+  pl->big = big; pl->d_counts = nullptr; pl->tiles_per_group = 1; pl->tile_groups = 1;
   pl->d_tables = nullptr; pl->d_zflag = nullptr; pl->d_phi = nullptr; pl->d_nphi = nullptr; pl->d_coef = nullptr; pl->d_seed = nullptr; pl->d_result = nullptr;
   pl->h_init_rl.assign(init_rl ? init_rl : nullptr, init_rl ? init_rl + nbatch : nullptr);
   pl->h_init_cl.assign(init_cl ? init_cl : nullptr, init_cl ? init_cl + nbatch : nullptr);
@@ -399,6 +520,21 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
   pl->grid = (int)(blocks < cap ? blocks : cap);
   if (pl->grid < 1) pl->grid = 1;
 
+  if (big) {
+    const int ntiles = mpad / kBigTile;
+    // enough (prefix block, tile group) pairs to fill the machine; a group sweeps its tiles one after the other
+    const unsigned long long pblocks = (nprefix + kLcThreads - 1) / kLcThreads;
+    int groups = (int)std::min<unsigned long long>((unsigned long long)ntiles, std::max<unsigned long long>(1, (unsigned long long)sms * 4ull / (pblocks * nbatch)));
+    pl->tiles_per_group = (ntiles + groups - 1) / groups;
+    pl->tile_groups = (ntiles + pl->tiles_per_group - 1) / pl->tiles_per_group;
+    pl->grid = (int)std::min<unsigned long long>(pblocks, (unsigned long long)sms * 8ull);
+    pl->smem = (size_t)c * kBigTile * width;
+    if (pool_alloc(&pl->d_counts, (size_t)nbatch * c * c * c * c * 4) != cudaSuccess) {
+      set_error("lincomb search: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      plo_lincomb_plan_destroy(pl);
+      return PLO_E_CUDA;
+    }
+  }
   auto up = [&](void** dst, const void* src, size_t bytes) -> bool {
     if (pool_alloc(dst, bytes ? bytes : 1) != cudaSuccess) return false;
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -443,7 +579,27 @@ int plo_lincomb_plan_run_range(plo_lincomb_plan* pl, uint64_t prefix_lo, uint64_
     prm.seed = pl->d_seed; prm.result = pl->d_result;
     return prm;
   };
-  if (pl->width == 4) {
+  if (pl->big) {
+    const size_t c4 = (size_t)pl->c * pl->c * pl->c * pl->c;
+    PLO_CUDA(cudaMemsetAsync(pl->d_counts, 0, (size_t)pl->nbatch * c4 * 4, st));
+    const dim3 cgrid(pl->grid, pl->tile_groups, pl->nbatch);
+    const unsigned long long ncand = (prefix_hi - prefix_lo) * (unsigned long long)pl->c;
+    const dim3 pgrid((unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>((ncand + kLcThreads - 1) / kLcThreads, (unsigned long long)sm_count() * 8ull)), pl->nbatch);
+    auto go = [&](auto prm, auto modp) {
+      typedef decltype(prm) P;
+      typedef typename std::remove_const<typename std::remove_pointer<decltype(P::t0)>::type>::type T;
+      constexpr bool MP = decltype(modp)::value;
+      lincomb_big_count_kernel<T, MP><<<cgrid, kLcThreads, pl->smem, st>>>(prm, pl->mpad, pl->tiles_per_group, pl->d_counts);
+      lincomb_big_pick_kernel<T, MP><<<pgrid, kLcThreads, 0, st>>>(prm, pl->d_counts);
+    };
+    if (pl->width == 4) {
+      auto prm = fill((uint32_t*)pl->d_tables);
+      if (pl->p) go(prm, std::true_type()); else go(prm, std::false_type());
+    } else {
+      go(fill((uint64_t*)pl->d_tables), std::false_type());
+    }
+    e = cudaGetLastError();
+  } else if (pl->width == 4) {
     auto prm = fill((uint32_t*)pl->d_tables);
     e = pl->p ? launch_lincomb<uint32_t, true>(pl->mpad, grid, pl->smem, st, prm) : launch_lincomb<uint32_t, false>(pl->mpad, grid, pl->smem, st, prm);
   } else {
@@ -454,7 +610,7 @@ int plo_lincomb_plan_run_range(plo_lincomb_plan* pl, uint64_t prefix_lo, uint64_
   return PLO_OK;
 }
 
-int plo_lincomb_plan_launches(const plo_lincomb_plan*) { return 2; }
+int plo_lincomb_plan_launches(const plo_lincomb_plan* pl) { return pl && pl->big ? 3 : 2; }
 
 uint64_t plo_lincomb_plan_candidates(const plo_lincomb_plan* pl) {
   return pl ? (uint64_t)pl->nbatch * pl->c * pl->c * pl->c * pl->c : 0;

@@ -213,3 +213,45 @@ def test_prefix_range_shards_reproduce_the_full_search(capi):
         merged = [S.lincomb_unkey(max(S.lincomb_key(*parts[r][b]) for r in range(world))) for b in range(4)]
         assert merged == full
     plan.close()
+
+
+def _wide_tm(m, seed, dens=(1, 1, 2, 4)):
+    rng = np.random.default_rng(seed)
+    vals = [0, 0, 0, 1, -1, 1, -1, 2, -2, 3]
+    return [[Fraction(int(rng.choice(vals)), int(rng.choice(dens))) for _ in range(m)] for _ in range(4)]
+
+
+@pytest.mark.parametrize("m,p,c", [(65, 0, 5), (200, P31, 7), (1000, 0, 5), (1000, P31, 7), (777, 7, 5)])
+def test_wide_outputs_tiled_path(capi, m, p, c):
+    """m > 64 (C5 has TM 4 x 15096): the tiled count + pick kernels walk the same (block,num) steps as the
+    register-resident kernel and return the oracle's (rlHw, clHw, index) at every step, over Q and mod p."""
+    TM = _wide_tm(m, seed=m + c)
+    assert run_steps(capi, TM, p, c) == 4
+
+
+def test_c5_first_block_of_32x32x32(capi):
+    """BASELINE C5 shape: the first column block of 32x32x32_15096_L (TM = 4 x 15096) mod 2^31-1, c = 5: every step equals the
+    oracle; and the prefix-range shards of the tiled path merge to the same winner."""
+    from plinopt_b200 import hm, sharding as S
+    big = hm.load_large_csr(P31)
+    assert big is not None
+    _, r, (L, _, _) = big
+    rows, cols, ptr, col, val = L
+    TMr = np.zeros((4, rows), dtype=np.int64)
+    for i in range(rows):
+        for t in range(ptr[i], ptr[i + 1]):
+            if col[t] < 4:
+                TMr[col[t], i] = int(val[t])
+    TM = [[Fraction(int(v)) for v in row] for row in TMr]
+    assert run_steps(capi, TM, P31, 5) == 4
+    cf = O.coeffs(TMr.tolist(), P31, 5)[0]
+    plan = capi.LincombPlan(P31, TMr, 0, cf)
+    plan.run()
+    full = [(int(a), int(b), int(i)) for a, b, i in zip(*plan.result())]
+    parts = []
+    for rank in range(3):
+        lo, hi = S.shard_range(0, 5 ** 3, rank, 3)
+        plan.run_range(lo, hi)
+        parts.append([(int(a), int(b), None if int(i) == capi.NO_INDEX else int(i)) for a, b, i in zip(*plan.result())])
+    assert [S.lincomb_unkey(max(S.lincomb_key(*parts[r][0]) for r in range(3)))] == full
+    plan.close()

@@ -73,6 +73,30 @@ def lincomb_cases(peaks):
         plan.close()
 
 
+def lincomb_c5_case(peaks):
+    """BASELINE C5 shape of the sparsifier search: column blocks of 32x32x32_15096_L (TM = 4 x 15096 per block) mod 2^31-1;
+    tiled count + pick kernels (m > 64)."""
+    big = hm.load_large_csr(P31)
+    if big is None:
+        return
+    _, r, (L, _, _) = big
+    rows, cols, ptr, col, val = L
+    nb, c = 16, 20
+    TM = np.zeros((nb, 4, rows), dtype=np.int64)
+    rowidx = np.repeat(np.arange(rows), np.diff(ptr))
+    sel = col < 4 * nb
+    TM[col[sel] // 4, col[sel] % 4, rowidx[sel]] = val[sel]
+    cfs = np.stack([coeff_list(TM[b].tolist(), P31, c) for b in range(nb)])
+    plan = capi.LincombPlan(P31, TM, 0, cfs)
+    ms = time_plan(lambda s: plan.run(s), 5)
+    rl, cl, idx = plan.result()
+    cand = plan.candidates
+    print(json.dumps({"kernel": "lincomb_big_count_kernel<u32,modp> + lincomb_big_pick_kernel", "case": f"32x32x32_15096_L, {nb} column blocks (TM 4x15096), c={c}",
+                      "candidates": cand, "ms": ms, "candidates_per_s": cand / ms * 1e3, "compare_add_pairs_per_s": cand * rows / ms * 1e3,
+                      "frac_of_ialu_pair_peak": cand * rows / ms * 1e3 / peaks["ialu_pairs_per_s"], "best_block0": [int(rl[0]), int(cl[0]), int(idx[0])]}))
+    plan.close()
+
+
 def orbit_cases(peaks):
     """Orbit sweep (src/orbiter.cpp:272-324) on every instantiated shape, both measures; ops per candidate as in SURVEY.md 8d."""
     cases = [("2x2x2_7_Winograd", 28), ("3x3x3_23_58", 24), ("4x4x4_48_rational", 22), ("3x4x7_63_rational", 21)]
@@ -185,8 +209,12 @@ if __name__ == "__main__":
     if "--factor-only" in sys.argv:
         factor_cases()
         sys.exit(0)
+    if "--c5-only" in sys.argv:
+        lincomb_c5_case(peaks)
+        sys.exit(0)
     if "--mm-only" not in sys.argv:
         lincomb_cases(peaks)
+        lincomb_c5_case(peaks)
         orbit_cases(peaks)
         factor_cases()
         dependency_cases(peaks)
