@@ -41,6 +41,7 @@ __host__ __device__ __forceinline__ unsigned long long pack_key(int rl, int cl, 
 template <typename T>
 struct LcParams {
   int c, m, nact, lsplit, ltile, nphi_max;
+  int rl_const;                 // zero coordinates shared by every candidate (columns of TM that vanish on the live rows; wide path)
   unsigned long long qlo, qhi;  // prefix range (i*c+j)*c+k of this launch (multi-GPU sharding of one search)
   unsigned int p;
   int cl_const;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_big_pick_kernel(const LcPa
     unsigned long long q = idx / (unsigned)c;
     const int k = (int)(q % (unsigned)c); q /= (unsigned)c;
     const int j = (int)(q % (unsigned)c), i = (int)(q / (unsigned)c);
-    const int rl = (int)cnt[idx];
+    const int rl = (int)cnt[idx] + prm.rl_const;
     const int cl = prm.cl_const + zf[i] + zf[c + j] + zf[2 * c + k] + zf[3 * c + l];
     const unsigned long long key = pack_key(rl, cl, kIdxMask - 1ull - idx);
     if (key > best && independent<MODP>(phi, nphi, coef, prm.p, i, j, k, l)) best = key;
@@ -340,6 +341,7 @@ struct plo_lincomb_plan {
   bool big;                // m > 64: tiled count + pick kernels
   unsigned int* d_counts;  // [nbatch][c^4] zero counts (big path)
   int tiles_per_group, tile_groups;
+  int m_eff, rl_const;     // wide path: columns kept after dropping those that vanish on the live rows
 };
 
 namespace {
@@ -432,12 +434,12 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
   int rc = check_device();
   if (rc) return rc;
   const bool big = m > 64;
-  const int mpad = big ? (m + kBigTile - 1) / kBigTile * kBigTile : pad_m(m);
+  int mpad = big ? (m + kBigTile - 1) / kBigTile * kBigTile : pad_m(m);
+  const int nact = (n - off) < 4 ? (n - off) : 4;
   if (big && (c > 64 || (unsigned long long)nbatch * c * c * c * c > (1ull << 28))) {
     set_error("lincomb search: m = %d > 64 needs c <= 64 and nbatch * c^4 <= 2^28", m);
     return PLO_E_SHAPE;
   }
-  const int nact = (n - off) < 4 ? (n - off) : 4;
 
   // canonical copies
   std::vector<int64_t> tm((size_t)nbatch * n * m), cf((size_t)nbatch * c), pv((size_t)nbatch * nprev * n);
@@ -445,13 +447,36 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
   for (size_t i = 0; i < cf.size(); ++i) cf[i] = p ? (int64_t)(((coeffs[i] % (int64_t)p) + (int64_t)p) % (int64_t)p) : coeffs[i];
   for (size_t i = 0; i < pv.size(); ++i) pv[i] = p ? (int64_t)(((prev_rows[i] % (int64_t)p) + (int64_t)p) % (int64_t)p) : prev_rows[i];
 
+  // wide path: a column of TM that is zero on the live rows off..off+nact-1 is a zero coordinate of EVERY candidate; such
+  // columns are dropped from the tables and counted once (HM matrices are sparse: 70 % of the 15096 columns for C5)
+  int m_eff = m, rl_const = 0;
+  if (big) {
+    std::vector<std::vector<int>> keep(nbatch);
+    m_eff = 1;
+    for (int b = 0; b < nbatch; ++b) {
+      for (int j = 0; j < m; ++j) {
+        bool nz = false;
+        for (int t = 0; t < nact && !nz; ++t) nz = tm[((size_t)b * n + off + t) * m + j] != 0;
+        if (nz) keep[b].push_back(j);
+      }
+      if ((int)keep[b].size() > m_eff) m_eff = (int)keep[b].size();
+    }
+    std::vector<int64_t> tmc((size_t)nbatch * n * m_eff, 0);
+    for (int b = 0; b < nbatch; ++b)
+      for (int t = 0; t < nact; ++t)
+        for (size_t q = 0; q < keep[b].size(); ++q) tmc[((size_t)b * n + off + t) * m_eff + q] = tm[((size_t)b * n + off + t) * m + keep[b][q]];
+    tm.swap(tmc);
+    rl_const = m - m_eff;  // dropped columns, minus the all-zero padding columns of the shorter problems (counted by the kernel)
+  }
+  const int m_tab = m_eff;  // row length of the tables
+  if (big) mpad = (m_eff + kBigTile - 1) / kBigTile * kBigTile;
   int width = 4;
   if (!p) {  // exact integers: magnitude guard
     unsigned __int128 mc = 0, mt = 0;
     for (int64_t v : cf) { unsigned __int128 a = v < 0 ? -(__int128)v : v; if (a > mc) mc = a; }
     for (int b = 0; b < nbatch; ++b)
       for (int t = 0; t < nact; ++t)
-        for (int j = 0; j < m; ++j) { int64_t v = tm[((size_t)b * n + off + t) * m + j]; unsigned __int128 a = v < 0 ? -(__int128)v : v; if (a > mt) mt = a; }
+        for (int j = 0; j < m_tab; ++j) { int64_t v = tm[((size_t)b * n + off + t) * m_tab + j]; unsigned __int128 a = v < 0 ? -(__int128)v : v; if (a > mt) mt = a; }
     const unsigned __int128 bound = mc * mt * 4;
     if (bound >= ((unsigned __int128)1 << 62)) { set_error("lincomb search: integer magnitude bound exceeded"); return PLO_E_RANGE; }
     width = bound < (((unsigned __int128)1 << 31) - 1) ? 4 : 8;
@@ -459,7 +484,7 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
 
   plo_lincomb_plan* pl = new plo_lincomb_plan();
   pl->p = p; pl->nbatch = nbatch; pl->n = n; pl->m = m; pl->off = off; pl->c = c; pl->nprev = nprev; pl->mpad = mpad; pl->width = width;
-  pl->big = big; pl->d_counts = nullptr; pl->tiles_per_group = 1; pl->tile_groups = 1;
+  pl->big = big; pl->m_eff = m_eff; pl->rl_const = rl_const; pl->d_counts = nullptr; pl->tiles_per_group = 1; pl->tile_groups = 1;
   pl->d_tables = nullptr; pl->d_zflag = nullptr; pl->d_phi = nullptr; pl->d_nphi = nullptr; pl->d_coef = nullptr; pl->d_seed = nullptr; pl->d_result = nullptr;
   pl->h_init_rl.assign(init_rl ? init_rl : nullptr, init_rl ? init_rl + nbatch : nullptr);
   pl->h_init_cl.assign(init_cl ? init_cl : nullptr, init_cl ? init_cl + nbatch : nullptr);
@@ -474,17 +499,17 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
   std::vector<int> nphi(nbatch, 0);
   try {
     for (int b = 0; b < nbatch; ++b) {
-      const int64_t* tmb = tm.data() + (size_t)b * n * m;
+      const int64_t* tmb = tm.data() + (size_t)b * n * m_tab;
       const int64_t* cfb = cf.data() + (size_t)b * c;
       unsigned char* base = tables.data();
       const size_t per = (size_t)nbatch * tab * width;  // bytes per table kind
       if (width == 4) {
         typedef uint32_t T;
-        fill_tables<T>(p, n, m, off, nact, c, mpad, tmb, cfb, (T*)(base + 0 * per) + b * tab, (T*)(base + 1 * per) + b * tab,
+        fill_tables<T>(p, n, m_tab, off, nact, c, mpad, tmb, cfb, (T*)(base + 0 * per) + b * tab, (T*)(base + 1 * per) + b * tab,
                        (T*)(base + 2 * per) + b * tab, (T*)(base + 3 * per) + b * tab);
       } else {
         typedef uint64_t T;
-        fill_tables<T>(p, n, m, off, nact, c, mpad, tmb, cfb, (T*)(base + 0 * per) + b * tab, (T*)(base + 1 * per) + b * tab,
+        fill_tables<T>(p, n, m_tab, off, nact, c, mpad, tmb, cfb, (T*)(base + 0 * per) + b * tab, (T*)(base + 1 * per) + b * tab,
                        (T*)(base + 2 * per) + b * tab, (T*)(base + 3 * per) + b * tab);
       }
       for (int t = 0; t < nact; ++t)
@@ -571,7 +596,7 @@ int plo_lincomb_plan_run_range(plo_lincomb_plan* pl, uint64_t prefix_lo, uint64_
   auto fill = [&](auto* base) {
     typedef typename std::remove_pointer<decltype(base)>::type T;
     LcParams<T> prm;
-    prm.c = pl->c; prm.m = pl->m; prm.nact = 0; prm.lsplit = pl->lsplit; prm.ltile = pl->ltile; prm.nphi_max = 4;
+    prm.c = pl->c; prm.m = pl->big ? pl->m_eff : pl->m; prm.rl_const = pl->big ? pl->rl_const : 0; prm.nact = 0; prm.lsplit = pl->lsplit; prm.ltile = pl->ltile; prm.nphi_max = 4;
     prm.qlo = prefix_lo; prm.qhi = prefix_hi;
     prm.p = pl->p; prm.cl_const = pl->n - ((pl->n - pl->off) < 4 ? (pl->n - pl->off) : 4);
     prm.t0 = base; prm.t1 = base + per; prm.t2 = base + 2 * per; prm.t3 = base + 3 * per;
