@@ -190,7 +190,7 @@ def mmcheck_case():
         ms = time_plan(lambda s: plan.run(1, 0, s), 10)
         v, ok = plan.result()
         bytes_csr = nnz * 8
-        print(json.dumps({"kernel": "mm_spmm_kernel (x3) + hadamard + verify", "case": f"{name}, batch={B}",
+        print(json.dumps({"kernel": "mm_slab_spmm_kernel x3 (Hadamard step fused) + gen + verify", "case": f"{name}, batch={B}",
                           "ms": ms, "samples_per_s": B / ms * 1e3, "modmac_per_s": (nnz + r + m * k * n) * B / ms * 1e3,
                           "csr_stream_GBs_if_read_once": bytes_csr / ms * 1e-6, "verdict": v, "samples_ok": int(ok.sum())}))
         plan.close()
