@@ -156,9 +156,8 @@ int mmcheck_dense(uint64_t modulus, uint64_t seed, int batch, const Dense<QField
 
 // Factorizer  include/plinopt_sparsify.inl:924-990.  F = field of the search (Q or Z/qZ).
 template <class F>
-static int run_factorizer(const F& f, const char* const* primes_unused, int rows, int cols, const int64_t* num, const int64_t* den, int innerdim,
+static int run_factorizer(const F& f, int rows, int cols, const int64_t* num, const int64_t* den, int innerdim,
                           uint64_t loops, uint64_t seed, int64_t* alt_num, int64_t* alt_den, int64_t* cob_num, int64_t* cob_den, uint64_t* report) {
-  (void)primes_unused;
   typedef Dense<F> Mat;
   const size_t r = (size_t)rows, n = (size_t)cols;
   const size_t k = innerdim == 0 ? n : (size_t)innerdim;
@@ -433,12 +432,12 @@ int plo_factorizer(uint64_t q, int rows, int cols, const int64_t* num, const int
   if (!num || !alt_num || !cob_num || rows < 1 || cols < 1 || innerdim < 0) { plo::set_error("plo_factorizer: bad argument"); return PLO_E_ARG; }
   if (cols > 32 && rows != cols) { plo::set_error("plo_factorizer: more than 32 columns are not supported by the device search"); return PLO_E_SHAPE; }
   try {
-    if (q == 0) { QField Q; return run_factorizer(Q, nullptr, rows, cols, num, den, innerdim, loops, seed, alt_num, alt_den, cob_num, cob_den, report); }
+    if (q == 0) { QField Q; return run_factorizer(Q, rows, cols, num, den, innerdim, loops, seed, alt_num, alt_den, cob_num, cob_den, report); }
     uint64_t p = q;
     while ((p % 2) == 0) p >>= 1;
     if (p < 3 || p >= (1ull << 31) || !is_prime(p)) { plo::set_error("plo_factorizer: the modulus must be an odd prime below 2^31"); return PLO_E_ARG; }
     ZpField Z((int64_t)p);
-    return run_factorizer(Z, nullptr, rows, cols, num, den, innerdim, loops, seed, alt_num, alt_den, cob_num, cob_den, report);
+    return run_factorizer(Z, rows, cols, num, den, innerdim, loops, seed, alt_num, alt_den, cob_num, cob_den, report);
   } catch (const RangeError& e) {
     plo::set_error("plo_factorizer: %s", e.what());
     return PLO_E_RANGE;
