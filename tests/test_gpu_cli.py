@@ -109,3 +109,31 @@ def test_negater_and_rotater_cli(capi, tmp_path):
     assert p.returncode == 0 and "SUCCESS: correct 7x3x4" in p.stderr, p.stderr
     rot = [hm.read_sms(str(tmp_path / f"3x4x7_63_rational_right_{x}.sms")) for x in "LRP"]
     assert rot == O.rotater(*O.triple("3x4x7_63_rational"), right=True)
+
+
+def test_mmchecker_cli_on_the_regenerated_32x32x32(capi, tmp_path):
+    """BASELINE config 5 through the drop-in CLI: the 32x32x32_15096 triple (regenerated from the reference's .slp, written back
+    as SMS with its rational coefficients) is a correct algorithm over Q-reduced-mod-p; a corrupted P is not."""
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "large", "32x32x32_15096.npz"))
+    files = []
+    for x in "LRP":
+        rows, cols = (int(v) for v in z[f"{x}_shape"])
+        ptr, col, num, den = z[f"{x}_ptr"], z[f"{x}_col"], z[f"{x}_num"], z[f"{x}_den"]
+        ri = np.repeat(np.arange(rows), np.diff(ptr))
+        f = tmp_path / f"32x32x32_15096_{x}.sms"
+        with open(f, "w") as fh:
+            fh.write(f"{rows} {cols} R\n")
+            fh.write("\n".join(f"{i + 1} {c + 1} {n}" + (f"/{d}" if d != 1 else "") for i, c, n, d in zip(ri.tolist(), col.tolist(), num.tolist(), den.tolist())))
+            fh.write("\n0 0 0\n")
+        files.append(str(f))
+    run = lambda args: subprocess.run([os.path.join(BIN, "MMchecker")] + args, capture_output=True, text=True, timeout=600)
+    p = run(["-m", "2147483647"] + files)
+    assert p.returncode == 0 and "SUCCESS: correct 32x32x32" in p.stderr, p.stderr[-500:]
+    bad = tmp_path / "bad_P.sms"
+    lines = open(files[2]).read().splitlines()
+    i, c, v = lines[5].split()
+    lines[5] = f"{i} {c} 5"
+    bad.write_text("\n".join(lines) + "\n")
+    q = run(["-m", "2147483647", files[0], files[1], str(bad)])
+    assert q.returncode == 1 and "not a 32x32x32 MM algorithm" in q.stderr
