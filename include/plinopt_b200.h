@@ -40,6 +40,7 @@ int plo_device_count(void);           /* number of visible CUDA devices (0 => ev
 int plo_set_device(int device);
 const char* plo_last_error(void);     /* thread-local message of the last failing call */
 void plo_release_workspace(void);     /* returns the cached device blocks of destroyed plans to the driver */
+int plo_set_sweep_devices(int n);     /* host-level orbit sweeps (plo_orbiter) are sharded over the first n devices (default 1) */
 
 /* ---------------------------------------------------------------------------
  * Sparsifier candidate search.
@@ -124,6 +125,13 @@ typedef struct plo_orbit_best {
 int plo_orbit_sweep(uint32_t p, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P,
                     int32_t denL, int32_t denR, int32_t denP, int measure, int mode, uint64_t seed, uint64_t lo,
                     uint64_t hi, plo_orbit_best* best);
+
+/* The exact sweep sharded over the first `ndev` CUDA devices of the calling process (clamped to the devices present): contiguous
+ * ascending index shards, asynchronous launches from one host thread, same winner as the single-device call.  This is what
+ * `bin/orbiter --gpus N` uses; multi-process runs shard with plo_orbit_plan_run + one all-reduce instead. */
+int plo_orbit_sweep_devices(int ndev, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P,
+                            int32_t denL, int32_t denR, int32_t denP, int measure, int mode, uint64_t seed, uint64_t lo,
+                            uint64_t hi, plo_orbit_best* best);
 
 /* index -> (U,V,W), row-major int32 in {-1,0,1}; pure host function, bit-identical to the device decode. */
 int plo_orbit_decode(int m, int k, int n, int mode, uint64_t seed, uint64_t index, int32_t* U, int32_t* V, int32_t* W);

@@ -21,7 +21,7 @@ NO_INDEX = 2 ** 64 - 1
 
 # every symbol include/plinopt_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "plo_release_workspace",
+    "plo_release_workspace", "plo_set_sweep_devices", "plo_orbit_sweep_devices",
     "plo_version", "plo_device_count", "plo_set_device", "plo_last_error",
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
@@ -205,6 +205,17 @@ def orbit_sweep(mkn, L, R, P, dens, measure, mode, seed, lo, hi, p=0):
     f.argtypes = [C.c_uint32] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                   C.c_uint64, C.POINTER(OrbitBest)]
     _check(f(p, m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), dens[0], dens[1], dens[2], measure, mode, seed, lo, hi, C.byref(best)))
+    return _best_tuple(best)
+
+
+def orbit_sweep_devices(ndev, mkn, L, R, P, dens, measure, mode, seed, lo, hi):
+    """One process, `ndev` devices: the sharded form of orbit_sweep (same winner)."""
+    m, k, n = mkn
+    L = _i32(L); R = _i32(R); P = _i32(P)
+    best = OrbitBest()
+    f = lib().plo_orbit_sweep_devices
+    f.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(OrbitBest)]
+    _check(f(ndev, m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), dens[0], dens[1], dens[2], measure, mode, seed, lo, hi, C.byref(best)))
     return _best_tuple(best)
 
 

@@ -15,7 +15,8 @@ static void usage(const char* prg, size_t loops) {
             << "  [-r r e s]: check is modulo (r^e-s) or ((r^e-s)/2^k) (default no)\n"
             << "  [-s|-g]: search sparser|lower growth factor (default is sparser)\n"
             << "  [-O #]: randomized search with that many loops (default " << loops << " loops)\n"
-            << "  [--seed #] [--exhaustive]: candidate enumeration (default Philox, seed 0x504C494E4F505431)\n";
+            << "  [--seed #] [--exhaustive]: candidate enumeration (default Philox, seed 0x504C494E4F505431)\n"
+            << "  [--gpus #]: shard the sweep over that many GPUs of this box (default 1)\n";
   exit(-1);
 }
 
@@ -26,6 +27,7 @@ int main(int argc, char** argv) {
   for (int i = 1; i < argc; ++i) {
     const std::string a(argv[i]);
     if (a == "--seed" && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 0);
+    else if (a == "--gpus" && i + 1 < argc) plo_set_sweep_devices(atoi(argv[++i]));
     else if (a == "--exhaustive") mode = PLO_MODE_EXHAUSTIVE;
     else if (a[0] == '-' && a.size() > 1) {
       if (a[1] == 'h') usage(argv[0], loops);

@@ -251,6 +251,8 @@ static void orbit_transform(const F& f, int m, int k, int n, int r, const Dense<
   }
 }
 
+static int g_sweep_devices = 1;  // devices a host-level sweep is sharded over (plo_set_sweep_devices)
+
 static inline int64_t store_one(const ZpField& f, int64_t e) { return f.canon(e); }
 static inline int64_t store_one(const QField&, const Rat&) { return 0; }
 static inline int64_t num_of(const Rat& e) { return e.num; }
@@ -403,7 +405,7 @@ int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int
     const int64_t dl = lcd_of(ld.data(), ld.size()), dr = lcd_of(rd.data(), rd.size()), dp = lcd_of(pd.data(), pd.size());
     const std::vector<int32_t> Li = scale_int32(ln.data(), ld.data(), ln.size(), dl), Ri = scale_int32(rn.data(), rd.data(), rn.size(), dr),
                                Pi = scale_int32(pn.data(), pd.data(), pn.size(), dp);
-    rc = plo_orbit_sweep(0, m, k, n, r, Li.data(), Ri.data(), Pi.data(), (int32_t)dl, (int32_t)dr, (int32_t)dp, measure, mode, seed, 0, loops, &rep->best);
+    rc = plo_orbit_sweep_devices(g_sweep_devices, m, k, n, r, Li.data(), Ri.data(), Pi.data(), (int32_t)dl, (int32_t)dr, (int32_t)dp, measure, mode, seed, 0, loops, &rep->best);
     if (rc) return rc;
     // acceptance against the input, src/orbiter.cpp:330-331
     bool improved = false;
@@ -574,6 +576,12 @@ int plo_rotater(int right, int r, int Lcols, int Rcols, int Prows, const int64_t
     plo::set_error("plo_rotater: %s", e.what());
     return PLO_E_RANGE;
   }
+}
+
+int plo_set_sweep_devices(int n) {
+  if (n < 1) { plo::set_error("plo_set_sweep_devices: need n >= 1"); return PLO_E_ARG; }
+  g_sweep_devices = n;
+  return PLO_OK;
 }
 
 int plo_mmchecker(uint64_t modulus, uint64_t seed, int batch, int Lrows, int Lcols, int Rrows, int Rcols, int Prows,

@@ -681,7 +681,14 @@ static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int
   return true;
 }
 
-static const void* g_const_owner = nullptr;
+// which plan's L/R/P currently sits in the constant bank of each device (constant memory is per device)
+constexpr int kMaxDevices = 64;
+static const void* g_const_owner_dev[kMaxDevices] = {nullptr};
+static const void*& const_owner() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return g_const_owner_dev[(d >= 0 && d < kMaxDevices) ? d : 0];
+}
 
 }  // namespace plo
 
@@ -731,7 +738,7 @@ static int orbit_modp(uint32_t p, int m, int k, int n, int r, const int32_t* L, 
   Key* d_bb = nullptr;
   uint32_t *d_nnz = nullptr, *d_nno = nullptr;
   auto cleanup = [&]() { pool_free(d_bb); pool_free(d_nnz); pool_free(d_nno); };
-  g_const_owner = nullptr;
+  const_owner() = nullptr;
   cudaError_t e = cudaMemcpyToSymbol(c_lrp, h.data(), total * sizeof(int));
   if (e == cudaSuccess) e = pool_alloc(&d_bb, sizeof(Key) * grid);
   if (e == cudaSuccess && tnnz && cnt) e = pool_alloc(&d_nnz, cnt * 4);
@@ -844,9 +851,9 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
 }
 
 static int orbit_upload(plo_orbit_plan* pl, cudaStream_t st) {
-  if (g_const_owner != pl) {
+  if (const_owner() != pl) {
     PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp, pl->h_lrp.data(), pl->h_lrp.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    g_const_owner = pl;
+    const_owner() = pl;
   }
   return PLO_OK;
 }
@@ -874,7 +881,7 @@ int plo_orbit_plan_result(plo_orbit_plan* pl, void* stream, plo_orbit_best* best
 
 void plo_orbit_plan_destroy(plo_orbit_plan* pl) {
   if (!pl) return;
-  if (g_const_owner == pl) g_const_owner = nullptr;
+  for (int d = 0; d < kMaxDevices; ++d) if (g_const_owner_dev[d] == pl) g_const_owner_dev[d] = nullptr;
   if (pl->d_block_best) pool_free(pl->d_block_best);
   if (pl->d_out) pool_free(pl->d_out);
   delete pl;
@@ -894,6 +901,50 @@ int plo_orbit_sweep(uint32_t p, int m, int k, int n, int r, const int32_t* L, co
   rc = plo_orbit_plan_run(pl, lo, hi, nullptr);
   if (!rc) rc = plo_orbit_plan_result(pl, nullptr, best);
   plo_orbit_plan_destroy(pl);
+  return rc;
+}
+
+// The same sweep sharded over the first `ndev` devices of this process (one host thread: the launches are asynchronous, so the
+// devices work concurrently); contiguous ascending shards, winner = lexicographic minimum with the lowest index among ties.
+int plo_orbit_sweep_devices(int ndev, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int32_t denL,
+                            int32_t denR, int32_t denP, int measure, int mode, uint64_t seed, uint64_t lo, uint64_t hi,
+                            plo_orbit_best* best) {
+  if (!best || ndev < 1 || hi < lo) { set_error("plo_orbit_sweep_devices: bad argument"); return PLO_E_ARG; }
+  int have = 0, prev = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) { cudaGetLastError(); return check_device(); }
+  if (ndev > have) ndev = have;
+  if (ndev > kMaxDevices) ndev = kMaxDevices;
+  cudaGetDevice(&prev);
+  std::vector<plo_orbit_plan*> plans((size_t)ndev, nullptr);
+  int rc = PLO_OK;
+  const uint64_t total = hi - lo, base = total / (uint64_t)ndev, rem = total % (uint64_t)ndev;
+  uint64_t a = lo;
+  for (int d = 0; d < ndev && !rc; ++d) {
+    const uint64_t b = a + base + ((uint64_t)d < rem ? 1 : 0);
+    if (cudaSetDevice(d) != cudaSuccess) { set_error("plo_orbit_sweep_devices: cudaSetDevice(%d) failed", d); rc = PLO_E_CUDA; break; }
+    rc = plo_orbit_plan_create(&plans[(size_t)d], m, k, n, r, L, R, P, denL, denR, denP, measure, mode, seed);
+    if (!rc) rc = plo_orbit_plan_run(plans[(size_t)d], a, b, nullptr);
+    a = b;
+  }
+  plo_orbit_best win;
+  win.index = PLO_NO_INDEX; win.nnz = 0; win.nno = 0; win.score = 0.0;
+  for (int d = 0; d < ndev; ++d) {
+    if (!plans[(size_t)d]) continue;
+    cudaSetDevice(d);
+    plo_orbit_best b;
+    if (!rc) rc = plo_orbit_plan_result(plans[(size_t)d], nullptr, &b);
+    if (!rc && b.index != PLO_NO_INDEX) {
+      bool better = win.index == PLO_NO_INDEX;
+      if (!better) {
+        if (measure == PLO_MEASURE_G2) better = b.score < win.score;  // shards are ascending: ties keep the earlier shard
+        else better = b.nnz < win.nnz || (b.nnz == win.nnz && b.nno < win.nno);
+      }
+      if (better) win = b;
+    }
+    plo_orbit_plan_destroy(plans[(size_t)d]);
+  }
+  cudaSetDevice(prev);
+  if (!rc) *best = win;
   return rc;
 }
 

@@ -141,3 +141,16 @@ def test_modular_orbit_sweep(capi, stem, count, p):
         assert np.array_equal(nnz, exact["nnz"]) and np.array_equal(nno, exact["nno"])
     with pytest.raises(capi.PloError):
         capi.orbit_sweep(mkn, Lr, Rr, Pr, (1, 1, 1), 3, 1, SEED, 0, 10, p=p)  # no growth factor in a finite field
+
+
+def test_multi_device_sweep_in_one_process(capi):
+    """plo_orbit_sweep_devices / bin/orbiter --gpus N: index shards over the devices of this process give the single-device winner
+    (with one visible device the call degenerates to it; with several, every shard runs on its own GPU)."""
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints("4x4x4_48_rational")
+    ndev = capi.device_count()
+    for measure in (0, 3):
+        one = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, measure, 1, SEED, 5, 5 + 200000)
+        for n in sorted({1, 2, ndev, ndev + 3}):
+            got = capi.orbit_sweep_devices(n, mkn, Li, Ri, Pi, dens, measure, 1, SEED, 5, 5 + 200000)
+            assert got == one, (measure, n)
+    assert capi.orbit_sweep_devices(2, mkn, Li, Ri, Pi, dens, 0, 1, SEED, 9, 9)["index"] is None
