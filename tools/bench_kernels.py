@@ -66,7 +66,18 @@ def lincomb_cases(peaks):
         rl, cl, idx = plan.result()
         cand = plan.candidates
         m = 48
-        print(json.dumps({"kernel": "lincomb_kernel<u32,48,modp>", "case": f"4x4x4_48_rational_L, 4 blocks, c={c}", "candidates": cand,
+        cpu = {}
+        if c == 20:  # the oracle's literal testLinComb loop on the same block-0 problem: 1 core (the reference loop is sequential) and all cores
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as O
+            z = np.zeros((4, 4), dtype=np.int64)
+            for nt, key in ((1, "cpu_oracle_candidates_per_s_1core"), (0, "cpu_oracle_candidates_per_s_allcores")):
+                i_hi = 2 if nt == 1 else c
+                t0 = time.perf_counter()
+                tot = O.lincomb_bench(P31, tms[0], np.ones_like(tms[0]), 0, 0, cfs[0], np.ones_like(cfs[0]), z, np.ones_like(z), 0, i_hi, nthreads=nt)[0]
+                cpu[key] = tot / (time.perf_counter() - t0)
+            cpu["cpu_threads_all"] = O.lib().orc_num_threads()
+        print(json.dumps({"kernel": "lincomb_kernel<u32,48,modp>", "case": f"4x4x4_48_rational_L, 4 blocks, c={c}", "candidates": cand, **cpu,
                           "ms": ms, "candidates_per_s": cand / ms * 1e3, "compare_add_pairs_per_s": cand * m / ms * 1e3,
                           "ialu_pair_peak": peaks["ialu_pairs_per_s"], "frac_of_ialu_pair_peak": cand * m / ms * 1e3 / peaks["ialu_pairs_per_s"],
                           "best": [int(rl[0]), int(cl[0]), int(idx[0])]}))
