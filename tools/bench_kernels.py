@@ -71,12 +71,12 @@ def lincomb_cases(peaks):
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib as O
             z = np.zeros((4, 4), dtype=np.int64)
-            for nt, key in ((1, "cpu_oracle_candidates_per_s_1core"), (0, "cpu_oracle_candidates_per_s_allcores")):
+            for nt, key in ((1, "cpu_oracle_candidates_per_s_1core"), (os.cpu_count() or 1, "cpu_oracle_candidates_per_s_allcores")):
                 i_hi = 2 if nt == 1 else c
                 t0 = time.perf_counter()
                 tot = O.lincomb_bench(P31, tms[0], np.ones_like(tms[0]), 0, 0, cfs[0], np.ones_like(cfs[0]), z, np.ones_like(z), 0, i_hi, nthreads=nt)[0]
                 cpu[key] = tot / (time.perf_counter() - t0)
-            cpu["cpu_threads_all"] = O.lib().orc_num_threads()
+            cpu["cpu_threads_all"] = os.cpu_count() or 1
         print(json.dumps({"kernel": "lincomb_kernel<u32,48,modp>", "case": f"4x4x4_48_rational_L, 4 blocks, c={c}", "candidates": cand, **cpu,
                           "ms": ms, "candidates_per_s": cand / ms * 1e3, "compare_add_pairs_per_s": cand * m / ms * 1e3,
                           "ialu_pair_peak": peaks["ialu_pairs_per_s"], "frac_of_ialu_pair_peak": cand * m / ms * 1e3 / peaks["ialu_pairs_per_s"],
