@@ -97,13 +97,23 @@ def load_problem():
     return (L, R, P), mkn, (Li, Ri, Pi), (dl, dr, dp)
 
 
+def host_threads():
+    """Every host core this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arms override it explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_rate(fr, target_s, threads=0):
     """Times the oracle (literal restatement of the orbiter loop body, OpenMP over candidates, all host
     threads) on a bounded sample sized for ~target_s seconds.  Returns (candidates/s, cores, sample count)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     L, R, P = fr
-    cores = O.lib().orc_num_threads() if threads == 0 else threads
+    if threads == 0:
+        threads = host_threads()
+    cores = threads
     t0 = time.perf_counter()
     O.orbit_sweep(L, R, P, 3, 1, SEED, 0, 20000, nthreads=threads, table=False)
     dt = time.perf_counter() - t0
@@ -125,10 +135,10 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     for _ in range(args.warmup):
-        O.orbit_sweep(*fr, 3, 1, SEED, 0, max(1000, n // 8), table=False)
+        O.orbit_sweep(*fr, 3, 1, SEED, 0, max(1000, n // 8), nthreads=cores, table=False)
     t0 = time.perf_counter()
     for s in range(args.steps):
-        O.orbit_sweep(*fr, 3, 1, SEED, s * n, (s + 1) * n, table=False)
+        O.orbit_sweep(*fr, 3, 1, SEED, s * n, (s + 1) * n, nthreads=cores, table=False)
     dt = time.perf_counter() - t0
     val = args.steps * n / dt
     line = {
