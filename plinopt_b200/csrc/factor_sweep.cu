@@ -113,34 +113,46 @@ __host__ __device__ __forceinline__ unsigned long long fs_pack(uint32_t nnz_alt,
   return ((unsigned long long)nnz_alt << 40) | ((unsigned long long)nno_alt << 20) | nnz_cob;
 }
 
-template <int N>
+constexpr int kFsStride = 33;  // row stride of M in shared memory (words): candidates of one warp read different rows
+
+// W lanes per candidate (W = 4, 8, 16 or 32 >= N): a warp carries 32 / W candidates side by side, each group of W lanes doing
+// exactly what the comments below say for "the warp" of the W = 32 case; ballots are cut into per-group masks, shuffles use
+// width W, and the data-dependent steps (row dependent / accepted, unit pivot / inversion) are predicated per group.
+template <int N, int W>
 __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams P, const uint32_t* __restrict__ Mg /* r x 32, Montgomery */,
                                                                   const uint32_t* __restrict__ rownnz_g, unsigned long long lo,
                                                                   unsigned long long hi, Key* __restrict__ block_best,
                                                                   uint32_t* __restrict__ table /* 3 x (hi-lo) or null */) {
+  constexpr int G = 32 / W;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr unsigned kGroupMask = W == 32 ? 0xffffffffu : ((1u << (W & 31)) - 1u);
   extern __shared__ uint32_t fs_smem[];
-  uint32_t* Msh = fs_smem;                             // r x 32
-  uint32_t* nnzsh = Msh + (size_t)P.r * 32;            // r
+  uint32_t* Msh = fs_smem;                                  // r x kFsStride
+  uint32_t* nnzsh = Msh + (size_t)P.r * kFsStride;          // r
   unsigned char* permall = reinterpret_cast<unsigned char*>(nnzsh + P.r);
   __shared__ Key red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* perm = permall + (size_t)warp * kFsMaxRows;
-  for (int e = threadIdx.x; e < P.r * 32; e += kFsThreads) Msh[e] = Mg[e];
+  const int sub = lane / W, j = lane % W;                   // group within the warp, column within the group
+  const int gshift = sub * W;
+  unsigned char* perm = permall + (size_t)(warp * G + sub) * kFsMaxRows;
+  for (int e = threadIdx.x; e < P.r * 32; e += kFsThreads) Msh[(e >> 5) * kFsStride + (e & 31)] = Mg[e];
   for (int e = threadIdx.x; e < P.r; e += kFsThreads) nnzsh[e] = rownnz_g[e];
   __syncthreads();
 
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
-  const unsigned long long nwarps = (unsigned long long)gridDim.x * kFsWarps;
-  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kFsWarps + warp; idx < hi; idx += nwarps) {
-    // ---- row order S: Fisher-Yates from the digit stream (all lanes compute the digits, lane 0 swaps) ----
-    for (int t = lane; t < P.r; t += 32) perm[t] = (unsigned char)t;
+  const unsigned long long step = (unsigned long long)gridDim.x * kFsWarps * G;
+  for (unsigned long long base = lo + ((unsigned long long)blockIdx.x * kFsWarps + warp) * G; base < hi; base += step) {
+    const unsigned long long idx = base + (unsigned)sub;
+    const bool valid = idx < hi;
+    // ---- row order S: Fisher-Yates from the digit stream (every lane of the group computes the digits, its first lane swaps) ----
+    for (int t = j; t < P.r; t += W) perm[t] = (unsigned char)t;
     __syncwarp();
     {
       FsDigits ds(P.seed, idx);
       for (int i = 0; i + 1 < P.r; ++i) {
         const uint32_t d = ds.digit((uint32_t)(P.r - i));
-        if (lane == 0 && d) { const unsigned char a = perm[i]; perm[i] = perm[i + d]; perm[i + d] = a; }
+        if (j == 0 && d) { const unsigned char a = perm[i]; perm[i] = perm[i + d]; perm[i + d] = a; }
       }
     }
     __syncwarp();
@@ -150,70 +162,81 @@ __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams
 #pragma unroll
     for (int i = 0; i < N; ++i) { Rj[i] = 0; Tj[i] = 0; pc[i] = 0; }
     int nb = 0;
-    for (int t = 0; t < P.r && nb < P.n; ++t) {
+    for (int t = 0; t < P.r; ++t) {
+      const bool active = valid && nb < P.n;
+      if (!__any_sync(kFull, active)) break;
       const int row = perm[t];
-      const uint32_t v = Msh[row * 32 + lane];
+      const uint32_t v = Msh[row * kFsStride + j];
       FsAcc ar, at;
       ar.a0 = ar.a1 = ar.a2 = 0;
       at.a0 = at.a1 = at.a2 = 0;
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if (i < nb) {
-          const uint32_t c = Msh[row * 32 + pc[i]];  // v[pivot column i]: warp-uniform address, one broadcast LDS
+          const uint32_t c = Msh[row * kFsStride + pc[i]];  // v[pivot column i]: one address per group (broadcast LDS)
           fs_mac(ar, c, Rj[i]);
           fs_mac(at, c, Tj[i]);
         }
       const uint32_t vr = sub_mod(v, fs_reduce(ar, P), P.p);  // v - sum c_i R_i
-      const unsigned nzmask = __ballot_sync(0xffffffffu, vr != 0);
-      if (nzmask == 0) continue;  // dependent on the rows kept so far
+      const unsigned nzmask = (__ballot_sync(kFull, active && vr != 0) >> gshift) & kGroupMask;
+      const bool accept = nzmask != 0;  // else: dependent on the rows kept so far (or nothing left to do for this group)
       uint32_t vt = fs_reduce(at, P);
-      vt = sub_mod(lane == nb ? P.one : 0u, vt, P.p);  // e_nb - sum c_i T_i
+      vt = sub_mod(j == nb ? P.one : 0u, vt, P.p);  // e_nb - sum c_i T_i
       // pivot: a coordinate equal to +-1 if there is one (its inverse is itself: no modular inversion), else the first
       // non-zero one.  The coordinates x of the solved rows do not depend on this choice (x.B = row has one solution).
-      const unsigned unit = __ballot_sync(0xffffffffu, vr == P.one || vr == P.mone);
-      const int pcn = __ffs(unit ? unit : nzmask) - 1;
-      const uint32_t pv = __shfl_sync(0xffffffffu, vr, pcn);
-      const uint32_t ip = unit ? pv : mont_inv(pv, P);
+      if (!__any_sync(kFull, accept)) continue;
+      const unsigned unit = (__ballot_sync(kFull, active && (vr == P.one || vr == P.mone)) >> gshift) & kGroupMask;
+      const int pcn = accept ? __ffs(unit ? unit : nzmask) - 1 : 0;
+      const uint32_t pv = __shfl_sync(kFull, vr, pcn, W);
+      uint32_t ip = pv;
+      if (__any_sync(kFull, accept && !unit)) { const uint32_t inv = mont_inv(pv, P); if (!unit) ip = inv; }
       const uint32_t wr = mont_mul(vr, ip, P.p, P.pinv), wt = mont_mul(vt, ip, P.p, P.pinv);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        if (i < nb) {
-          const uint32_t f = __shfl_sync(0xffffffffu, Rj[i], pcn);
+        const uint32_t f = __shfl_sync(kFull, Rj[i], pcn, W);
+        if (accept && i < nb) {
           Rj[i] = sub_mod(Rj[i], mont_mul(f, wr, P.p, P.pinv), P.p);
           Tj[i] = sub_mod(Tj[i], mont_mul(f, wt, P.p, P.pinv), P.p);
         }
-        if (i == nb) { Rj[i] = wr; Tj[i] = wt; pc[i] = pcn; }
+        if (accept && i == nb) { Rj[i] = wr; Tj[i] = wt; pc[i] = pcn; }
       }
-      if (lane == 0 && t != nb) { const unsigned char a = perm[nb]; perm[nb] = perm[t]; perm[t] = a; }  // :793-796
-      ++nb;
+      if (accept && j == 0 && t != nb) { const unsigned char a = perm[nb]; perm[nb] = perm[t]; perm[t] = a; }  // :793-796
+      nb += accept ? 1 : 0;
     }
     __syncwarp();
     // ---- score ----
-    unsigned long long key = ~0ull;
+    const bool ok = valid && nb == P.n;
     uint32_t nnz_alt = 0, nno_alt = 0, nnz_cob = 0;
-    if (nb == P.n) {
+    if (__any_sync(kFull, ok)) {
       for (int t = 0; t < P.r; ++t) {
         const int row = perm[t];
         if (t < P.k) { nnz_alt += 1; nnz_cob += nnzsh[row]; continue; }  // identity row of Res, row of CoB
         FsAcc ax;
         ax.a0 = ax.a1 = ax.a2 = 0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) fs_mac(ax, Msh[row * 32 + pc[i]], Tj[i]);  // rows i >= n of T are zero: no guard needed
-        const uint32_t x = fs_reduce(ax, P);  // coordinate of `row` on the lane-th independent row
-        const bool nz = lane < P.n && x != 0;
-        nnz_alt += __popc(__ballot_sync(0xffffffffu, nz));
-        nno_alt += __popc(__ballot_sync(0xffffffffu, nz && x != P.one && x != P.mone));
+        for (int i = 0; i < N; ++i) fs_mac(ax, Msh[row * kFsStride + pc[i]], Tj[i]);  // rows i >= n of T are zero: no guard needed
+        const uint32_t x = fs_reduce(ax, P);  // coordinate of `row` on the j-th independent row
+        const bool nz = j < P.n && x != 0;
+        nnz_alt += __popc((__ballot_sync(kFull, nz) >> gshift) & kGroupMask);
+        nno_alt += __popc((__ballot_sync(kFull, nz && x != P.one && x != P.mone) >> gshift) & kGroupMask);
       }
-      key = fs_pack(nnz_alt, nno_alt, nnz_cob);
     }
-    if (table && lane == 0) {
+    const unsigned long long key = ok ? fs_pack(nnz_alt, nno_alt, nnz_cob) : ~0ull;
+    if (table && j == 0 && valid) {
       const unsigned long long o = (idx - lo) * 3;
-      table[o] = nb == P.n ? nnz_alt : 0xffffffffu; table[o + 1] = nno_alt; table[o + 2] = nnz_cob;
+      table[o] = ok ? nnz_alt : 0xffffffffu; table[o + 1] = nno_alt; table[o + 2] = nnz_cob;
     }
-    if (key < best.primary || (key == best.primary && idx < best.index)) { best.primary = key; best.index = idx; }
+    if (valid && (key < best.primary || (key == best.primary && idx < best.index))) { best.primary = key; best.index = idx; }
     __syncwarp();
   }
-  // every lane of a warp holds the same `best`; block minimum over the warps
+  // lanes of a group hold the same `best`: minimum over the groups of the warp, then over the warps of the block
+#pragma unroll
+  for (int d = W; d < 32; d <<= 1) {
+    Key o;
+    o.primary = __shfl_xor_sync(kFull, best.primary, d);
+    o.index = __shfl_xor_sync(kFull, best.index, d);
+    if (key_less(o, best)) best = o;
+  }
   if (lane == 0) red[warp] = best;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -226,14 +249,16 @@ __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams
 typedef void (*FsLaunch)(int grid, size_t smem, cudaStream_t st, const FsParams& P, const uint32_t* M, const uint32_t* nnz,
                          unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* table);
 template <int N>
+struct FsWidth { static constexpr int value = N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32; };
+template <int N>
 static void fs_launch(int grid, size_t smem, cudaStream_t st, const FsParams& P, const uint32_t* M, const uint32_t* nnz,
                       unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* table) {
-  factor_sweep_kernel<N><<<grid, kFsThreads, smem, st>>>(P, M, nnz, lo, hi, bb, table);
+  factor_sweep_kernel<N, FsWidth<N>::value><<<grid, kFsThreads, smem, st>>>(P, M, nnz, lo, hi, bb, table);
 }
 template <int N>
 static int fs_blocks_per_sm(size_t smem) {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_sweep_kernel<N>, kFsThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_sweep_kernel<N, FsWidth<N>::value>, kFsThreads, smem);
   return nb > 0 ? nb : 1;
 }
 
@@ -245,7 +270,7 @@ using namespace plo;
 
 struct plo_factor_plan {
   FsParams P;
-  int npad, grid;
+  int npad, grid, group;
   size_t smem;
   FsLaunch launch;
   uint32_t *d_M, *d_nnz;
@@ -286,7 +311,9 @@ int plo_factor_plan_create(plo_factor_plan** plan, uint32_t p, int r, int n, int
     PLO_FS_CASE(4) PLO_FS_CASE(8) PLO_FS_CASE(12) PLO_FS_CASE(16) PLO_FS_CASE(20) PLO_FS_CASE(24) PLO_FS_CASE(28) PLO_FS_CASE(32)
 #undef PLO_FS_CASE
   }
-  pl->smem = ((size_t)r * 32 + r) * 4 + (size_t)kFsWarps * kFsMaxRows;
+  const int width = pl->npad <= 4 ? 4 : pl->npad <= 8 ? 8 : pl->npad <= 16 ? 16 : 32;  // lanes per candidate
+  pl->group = 32 / width;
+  pl->smem = ((size_t)r * kFsStride + r) * 4 + (size_t)kFsWarps * pl->group * kFsMaxRows;
   int bps = 1;
   switch (pl->npad) {
 #define PLO_FS_CASE(NN) case NN: bps = fs_blocks_per_sm<NN>(pl->smem); break;
@@ -304,7 +331,8 @@ int plo_factor_plan_create(plo_factor_plan** plan, uint32_t p, int r, int n, int
 }
 
 static int fs_grid(const plo_factor_plan* pl, uint64_t lo, uint64_t hi) {
-  const uint64_t need = (hi - lo + kFsWarps - 1) / kFsWarps;
+  const uint64_t per_block = (uint64_t)kFsWarps * (uint64_t)pl->group;
+  const uint64_t need = (hi - lo + per_block - 1) / per_block;
   return (int)(need < (uint64_t)pl->grid ? (need ? need : 1) : (uint64_t)pl->grid);
 }
 
