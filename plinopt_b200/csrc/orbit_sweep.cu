@@ -575,6 +575,113 @@ __global__ void __launch_bounds__(kThreads) orbit_modp_kernel(int r, ModP mp, un
   if (threadIdx.x == 0) block_best[blockIdx.x] = best;
 }
 
+// ---------------------------------------------------------------------------
+// Wide exact path: int32 inputs whose transforms (or squares) would leave 32 bits -- e.g. 2x2x2_7_DPS-integral-12.0662, common
+// denominators ~10^9.  Both stages of the product are accumulated exactly in 64 bits (|.| < 2^31 . 2^8 . 2^8, as in the modular
+// path); sparsity is classified on the exact integers; for the growth factor every entry becomes a double first
+// (value / denominator, growthfactor.cpp:25-28), then square / sum / sqrt per row (:41-44, 117-125): within 1e-12 relative of the
+// reference formula, not bit-identical (the reference truncates the rational -> double conversion).
+// ---------------------------------------------------------------------------
+struct AccW {
+  int nnz, nno;
+  double sq;
+};
+template <int RA, int CA, bool TL, bool TR>
+__host__ __device__ __forceinline__ void transform_row_wide(const int* __restrict__ A, const int* Lm, const int* Rm, long long den, double inv_den, AccW& acc) {
+  int a[RA * CA];
+#pragma unroll
+  for (int e = 0; e < RA * CA; ++e) a[e] = A[e];
+#pragma unroll
+  for (int x = 0; x < RA; ++x) {
+    long long X[CA];
+#pragma unroll
+    for (int j = 0; j < CA; ++j) {
+      long long s = 0;
+#pragma unroll
+      for (int i = 0; i < RA; ++i) s += (long long)(TL ? Lm[i * RA + x] : Lm[x * RA + i]) * (long long)a[i * CA + j];
+      X[j] = s;
+    }
+#pragma unroll
+    for (int y = 0; y < CA; ++y) {
+      long long s = 0;
+#pragma unroll
+      for (int j = 0; j < CA; ++j) s += X[j] * (long long)(TR ? Rm[y * CA + j] : Rm[j * CA + y]);
+      acc.nnz += (s != 0);
+      acc.nno += (s != 0) & (s != den) & (s != -den);
+      const double v = (double)s * inv_den;
+      acc.sq += v * v;
+    }
+  }
+}
+template <int M, int K, int N, int MODE>
+__host__ __device__ __forceinline__ Score score_candidate_wide(const int* __restrict__ lrp, int r, int3 den, double3 inv_den, unsigned long long seed,
+                                                               unsigned long long index, volatile int* scr, int stride) {
+  Digits<MODE> ds(seed, index);
+  const Zoi zu = decode_zoi<M, MODE>(ds);
+  const Zoi zv = decode_zoi<K, MODE>(ds);
+  const Zoi zw = decode_zoi<N, MODE>(ds);
+  int U[M * M], Ui[M * M], V[K * K], Vi[K * K], W[N * N], Wi[N * N];
+  expand_zoi<M, false>(zu, U, scr, stride);
+  expand_zoi<M, true>(zu, Ui, scr, stride);
+  expand_zoi<K, false>(zv, V, scr, stride);
+  expand_zoi<K, true>(zv, Vi, scr, stride);
+  expand_zoi<N, false>(zw, W, scr, stride);
+  expand_zoi<N, true>(zw, Wi, scr, stride);
+  const int* Lc = lrp;
+  const int* Rc = lrp + r * M * K;
+  const int* Pc = Rc + r * K * N;
+  Score sc;
+  sc.nnz = 0; sc.nno = 0; sc.g2 = 0.0;
+  for (int l = 0; l < r; ++l) {
+    AccW aL, aR, aP;
+    aL.nnz = aL.nno = 0; aL.sq = 0.0;
+    aR = aL; aP = aL;
+    transform_row_wide<M, K, true, false>(Lc + l * M * K, Ui, V, den.x, inv_den.x, aL);
+    transform_row_wide<K, N, false, false>(Rc + l * K * N, Vi, W, den.y, inv_den.y, aR);
+    transform_row_wide<M, N, false, true>(Pc + l * M * N, U, Wi, den.z, inv_den.z, aP);
+    sc.nnz += (uint32_t)(aL.nnz + aR.nnz + aP.nnz);
+    sc.nno += (uint32_t)(aL.nno + aR.nno + aP.nno);
+    sc.g2 += (sqrt(aL.sq) * sqrt(aR.sq)) * sqrt(aP.sq);
+  }
+  return sc;
+}
+template <int M, int K, int N, int MODE>
+__global__ void __launch_bounds__(kThreads) orbit_wide_kernel(int r, int3 den, double3 inv_den, int measure, unsigned long long seed, unsigned long long lo,
+                                                               unsigned long long hi, Key* __restrict__ block_best, uint32_t* __restrict__ tnnz,
+                                                               uint32_t* __restrict__ tnno, double* __restrict__ tg2) {
+  __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
+  __shared__ Key red[32];
+  const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+  Key best;
+  best.primary = ~0ull; best.index = ~0ull;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
+    const Score s = score_candidate_wide<M, K, N, MODE>(c_lrp, r, den, inv_den, seed, idx, scr + threadIdx.x, kThreads);
+    if (tnnz) tnnz[idx - lo] = s.nnz;
+    if (tnno) tnno[idx - lo] = s.nno;
+    if (tg2) tg2[idx - lo] = s.g2;
+    Key k;
+    k.primary = measure == PLO_MEASURE_G2 ? (unsigned long long)__double_as_longlong(s.g2) : (((unsigned long long)s.nnz << 32) | s.nno);
+    k.index = idx;
+    if (k.primary < best.primary) best = k;
+  }
+  best = block_min(best, red);
+  if (threadIdx.x == 0 && block_best) block_best[blockIdx.x] = best;
+}
+typedef void (*WideLaunch)(int mode, int grid, cudaStream_t st, int r, int3 den, double3 inv_den, int measure, unsigned long long seed,
+                           unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno, double* tg2);
+template <int M, int K, int N>
+static void wide_launch(int mode, int grid, cudaStream_t st, int r, int3 den, double3 inv_den, int measure, unsigned long long seed,
+                        unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno, double* tg2) {
+  if (mode == 0) orbit_wide_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2);
+  else orbit_wide_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2);
+}
+static WideLaunch find_wide(int m, int k, int n) {
+  if (m == 2 && k == 2 && n == 2) return &wide_launch<2, 2, 2>;
+  if (m == 3 && k == 3 && n == 3) return &wide_launch<3, 3, 3>;
+  if (m == 4 && k == 4 && n == 4) return &wide_launch<4, 4, 4>;
+  return nullptr;
+}
+
 typedef void (*ModpLaunch)(int mode, int grid, cudaStream_t st, int r, ModP mp, unsigned long long seed, unsigned long long lo,
                            unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno);
 template <int M, int K, int N>
@@ -706,6 +813,10 @@ struct plo_orbit_plan {
   int grid, lutn;
   bool lutfull, pack;
   size_t smem;
+  WideLaunch wide;      // non-null: 64-bit exact path (inputs beyond the int32 product bound)
+  double3 inv_den3;
+  uint32_t* d_wide_cnt;  // [2] nnz, nno of the winner
+  double* d_wide_g2;
 };
 
 // Z/pZ sweep: residues in, winner (and optional per-candidate table) out.  Synchronous.
@@ -815,8 +926,15 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   if (mode == 0 && plo_orbit_space(m, k, n) == 0) { set_error("orbit sweep: exhaustive space exceeds 64 bits"); return PLO_E_SHAPE; }
   long long smax = 0;
   bool lanes16 = false;
-  if (!magnitude_ok(m, k, n, r, L, R, P, &smax, &lanes16)) { set_error("orbit sweep: int32 magnitude bound exceeded"); return PLO_E_RANGE; }
+  WideLaunch wide = nullptr;
+  if (!magnitude_ok(m, k, n, r, L, R, P, &smax, &lanes16)) {
+    wide = find_wide(m, k, n);  // exact in 64 bits for every int32 input of these shapes
+    if (!wide) { set_error("orbit sweep: int32 magnitude bound exceeded and no 64-bit kernel for %dx%dx%d", m, k, n); return PLO_E_RANGE; }
+    smax = 0; lanes16 = false;
+  }
   plo_orbit_plan* pl = new plo_orbit_plan();
+  pl->wide = wide; pl->d_wide_cnt = nullptr; pl->d_wide_g2 = nullptr;
+  pl->inv_den3 = make_double3(1.0 / std::fabs((double)denL), 1.0 / std::fabs((double)denR), 1.0 / std::fabs((double)denP));
   pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->measure = measure; pl->mode = mode; pl->seed = seed;
   pl->inv_den = 1.0 / ((double)denL * (double)denR * (double)denP);
   if (pl->inv_den < 0) pl->inv_den = -pl->inv_den;
@@ -832,6 +950,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   pl->lutn = measure == PLO_MEASURE_G2 ? (int)(smax + 1 < 4096 ? smax + 1 : 4096) : 0;
   pl->lutfull = measure == PLO_MEASURE_G2 && smax + 1 <= 4096;
   pl->pack = lanes16 && getenv("PLO_ORBIT_NOPACK") == nullptr;
+  if (wide) { pl->lutn = 0; pl->lutfull = false; pl->pack = false; }
   int dmax = m > k ? (m > n ? m : n) : (k > n ? k : n);
   pl->smem = (size_t)pl->lutn * sizeof(double) + (dmax > 2 ? (size_t)dmax * dmax * kThreads * sizeof(int) : 0);
   if (pl->smem > 48 * 1024 && ops->allow_smem(pl->smem) != cudaSuccess) {
@@ -843,6 +962,11 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   pl->d_block_best = nullptr; pl->d_out = nullptr;
   if (pool_alloc(&pl->d_block_best, sizeof(Key) * pl->grid) != cudaSuccess || pool_alloc(&pl->d_out, sizeof(plo_orbit_best)) != cudaSuccess) {
     set_error("orbit sweep: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    plo_orbit_plan_destroy(pl);
+    return PLO_E_CUDA;
+  }
+  if (wide && (pool_alloc(&pl->d_wide_cnt, 8) != cudaSuccess || pool_alloc(&pl->d_wide_g2, 8) != cudaSuccess)) {
+    set_error("orbit sweep: device allocation failed");
     plo_orbit_plan_destroy(pl);
     return PLO_E_CUDA;
   }
@@ -863,6 +987,19 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   cudaStream_t st = (cudaStream_t)stream;
   int rc = orbit_upload(pl, st);
   if (rc) return rc;
+  if (pl->wide) {
+    Key none;
+    none.primary = ~0ull; none.index = ~0ull;
+    std::vector<Key> init((size_t)pl->grid, none);
+    PLO_CUDA(cudaMemcpyAsync(pl->d_block_best, init.data(), sizeof(Key) * pl->grid, cudaMemcpyHostToDevice, st));
+    if (hi > lo) {
+      const unsigned long long blocks = (hi - lo + kThreads - 1) / kThreads;
+      pl->wide(pl->mode, (int)std::min<unsigned long long>(blocks, (unsigned long long)pl->grid), st, pl->r, pl->den, pl->inv_den3, pl->measure, pl->seed, lo, hi,
+               pl->d_block_best, nullptr, nullptr, nullptr);
+    }
+    PLO_CUDA(cudaGetLastError());
+    return PLO_OK;
+  }
   pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());
@@ -874,6 +1011,26 @@ int plo_orbit_plan_launches(const plo_orbit_plan*) { return 2; }
 int plo_orbit_plan_result(plo_orbit_plan* pl, void* stream, plo_orbit_best* best) {
   if (!pl || !best) { set_error("plo_orbit_plan_result: bad argument"); return PLO_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (pl->wide) {  // host picks the winner among the block keys, one more 1-candidate launch returns all its measures
+    std::vector<Key> bb((size_t)pl->grid);
+    PLO_CUDA(cudaMemcpyAsync(bb.data(), pl->d_block_best, sizeof(Key) * pl->grid, cudaMemcpyDeviceToHost, st));
+    PLO_CUDA(cudaStreamSynchronize(st));
+    Key b = bb[0];
+    for (const Key& x : bb) if (key_less(x, b)) b = x;
+    best->index = b.index; best->nnz = 0; best->nno = 0; best->score = 0.0;
+    if (b.index == ~0ull) return PLO_OK;
+    int rc = orbit_upload(pl, st);
+    if (rc) return rc;
+    pl->wide(pl->mode, 1, st, pl->r, pl->den, pl->inv_den3, pl->measure, pl->seed, b.index, b.index + 1, nullptr, pl->d_wide_cnt, pl->d_wide_cnt + 1, pl->d_wide_g2);
+    uint32_t cnt[2];
+    double g2 = 0.0;
+    PLO_CUDA(cudaMemcpyAsync(cnt, pl->d_wide_cnt, 8, cudaMemcpyDeviceToHost, st));
+    PLO_CUDA(cudaMemcpyAsync(&g2, pl->d_wide_g2, 8, cudaMemcpyDeviceToHost, st));
+    PLO_CUDA(cudaStreamSynchronize(st));
+    best->nnz = cnt[0]; best->nno = cnt[1];
+    best->score = pl->measure == PLO_MEASURE_G2 ? g2 : (double)cnt[0];
+    return PLO_OK;
+  }
   PLO_CUDA(cudaMemcpyAsync(best, pl->d_out, sizeof(plo_orbit_best), cudaMemcpyDeviceToHost, st));
   PLO_CUDA(cudaStreamSynchronize(st));
   return PLO_OK;
@@ -884,6 +1041,7 @@ void plo_orbit_plan_destroy(plo_orbit_plan* pl) {
   for (int d = 0; d < kMaxDevices; ++d) if (g_const_owner_dev[d] == pl) g_const_owner_dev[d] = nullptr;
   if (pl->d_block_best) pool_free(pl->d_block_best);
   if (pl->d_out) pool_free(pl->d_out);
+  pool_free(pl->d_wide_cnt); pool_free(pl->d_wide_g2);
   delete pl;
 }
 
@@ -967,7 +1125,8 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
     if (!rc) {
       size_t blocks = (cnt + kThreads - 1) / kThreads;
       int grid = (int)(blocks < (size_t)pl->grid ? blocks : (size_t)pl->grid);
-      pl->ops->table(mode, grid, nullptr, r, pl->den, seed, lo, hi, pl->inv_den, d_nnz, d_nno, d_g2);
+      if (pl->wide) pl->wide(mode, grid, nullptr, r, pl->den, pl->inv_den3, PLO_MEASURE_G2, seed, lo, hi, nullptr, d_nnz, d_nno, d_g2);
+      else pl->ops->table(mode, grid, nullptr, r, pl->den, seed, lo, hi, pl->inv_den, d_nnz, d_nno, d_g2);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { set_error("plo_orbit_table: %s", cudaGetErrorString(e)); rc = PLO_E_CUDA; }
     }

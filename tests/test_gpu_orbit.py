@@ -98,8 +98,12 @@ def test_empty_range_and_errors(capi):
     with pytest.raises(capi.PloError) as e:
         capi.orbit_sweep((5, 5, 5), np.zeros((1, 25), np.int32), np.zeros((1, 25), np.int32), np.zeros((25, 1), np.int32), (1, 1, 1), 0, 1, 0, 0, 1)
     assert e.value.code == capi.E_SHAPE
+    # beyond the int32 product bound: 2x2x2 / 3x3x3 / 4x4x4 switch to the 64-bit exact kernels (same counts), other shapes refuse
+    big = capi.orbit_sweep(mkn, Li * 100000, Ri, Pi, (100000, 1, 1), 0, 1, SEED, 0, 2000)
+    assert (big["index"], big["nnz"], big["nno"]) == tuple(capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 0, 1, SEED, 0, 2000)[k] for k in ("index", "nnz", "nno"))
+    (_, _, _), mkn7, (L7, R7, P7), dens7 = ints("3x4x7_63_rational")
     with pytest.raises(capi.PloError) as e:
-        capi.orbit_sweep(mkn, Li * 100000, Ri, Pi, dens, 0, 1, 0, 0, 1)
+        capi.orbit_sweep(mkn7, L7 * 1000000, R7, P7, dens7, 0, 1, 0, 0, 1)
     assert e.value.code == capi.E_RANGE
 
 
@@ -154,3 +158,24 @@ def test_multi_device_sweep_in_one_process(capi):
             got = capi.orbit_sweep_devices(n, mkn, Li, Ri, Pi, dens, measure, 1, SEED, 5, 5 + 200000)
             assert got == one, (measure, n)
     assert capi.orbit_sweep_devices(2, mkn, Li, Ri, Pi, dens, 0, 1, SEED, 9, 9)["index"] is None
+
+
+def test_wide_exact_path_for_large_denominators(capi):
+    """2x2x2_7_DPS-integral-12.0662 (the reference's most accurate integral-coefficient variant, common denominators ~10^9): the
+    int32 product bound fails, the 64-bit exact kernels take over.  nnz / nno bit-exact, G2 within 1e-12 relative (entries become
+    doubles before squaring, growthfactor.cpp:25-28), the exhaustive orbit confirms 12.0662 as its minimum."""
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints("2x2x2_7_DPS-integral-12.0662")
+    assert max(dens) > 10 ** 9
+    space = capi.orbit_space(*mkn)
+    ref = O.orbit_sweep(L, R, P, 3, 0, 0, 0, space)
+    nnz, nno, g2 = capi.orbit_table(mkn, Li, Ri, Pi, dens, 0, 0, 0, space)
+    assert np.array_equal(nnz, ref["nnz"]) and np.array_equal(nno, ref["nno"])
+    assert np.allclose(g2, ref["g2"], rtol=RTOL, atol=0)
+    got = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 3, 0, 0, 0, space)
+    assert abs(got["score"] - 12.06616423) < 5e-9 and got["nnz"] == 63  # data/2x2x2_7_DPS-integral-12.0662_L.sms:1
+    assert abs(got["score"] - ref["best"][3]) <= RTOL * ref["best"][3]
+    refn = O.orbit_sweep(L, R, P, 0, 1, SEED, 0, 30000, table=False)["best"]
+    gotn = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 0, 1, SEED, 0, 30000)
+    assert (gotn["index"], gotn["nnz"], gotn["nno"]) == refn[:3]
+    halves = [capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 0, 1, SEED, 0, 11111), capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 0, 1, SEED, 11111, 30000)]
+    assert min(halves, key=lambda b: (b["nnz"], b["nno"], b["index"])) == gotn
