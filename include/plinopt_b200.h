@@ -143,6 +143,14 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
                     int32_t denR, int32_t denP, int mode, uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* nnz,
                     uint32_t* nno, double* g2);
 
+/* 64-bit inputs: entries and common denominators beyond the int32 C ABI above (2x2x2_7_DPS-intermediate-12.0695 has a common
+ * denominator of 1.0e11); |entries| < 2^46; shapes 2x2x2, 3x3x3, 4x4x4; same decode, same deterministic winner; G2 within 1e-12
+ * relative of growthfactor.cpp:117-125.  Synchronous. */
+int plo_orbit_sweep64(int m, int k, int n, int r, const int64_t* L, const int64_t* R, const int64_t* P, int64_t denL, int64_t denR,
+                      int64_t denP, int measure, int mode, uint64_t seed, uint64_t lo, uint64_t hi, plo_orbit_best* best);
+int plo_orbit_table64(int m, int k, int n, int r, const int64_t* L, const int64_t* R, const int64_t* P, int64_t denL, int64_t denR,
+                      int64_t denP, int mode, uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* nnz, uint32_t* nno, double* g2);
+
 /* The same table over Z/pZ (residues in, (nnz, nno) per candidate out). */
 int plo_orbit_table_modp(uint32_t p, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int mode,
                          uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* nnz, uint32_t* nno);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
-    "plo_orbit_table_modp", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
+    "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
     "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
@@ -226,6 +226,28 @@ def orbit_table(mkn, L, R, P, dens, mode, seed, lo, hi):
     nnz = np.zeros(cnt, dtype=np.uint32); nno = np.zeros(cnt, dtype=np.uint32); g2 = np.zeros(cnt, dtype=np.float64)
     f = lib().plo_orbit_table
     f.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 3
+    _check(f(m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), dens[0], dens[1], dens[2], mode, seed, lo, hi, _ptr(nnz), _ptr(nno), _ptr(g2)))
+    return nnz, nno, g2
+
+
+def orbit_sweep64(mkn, L, R, P, dens, measure, mode, seed, lo, hi):
+    """int64 entries / denominators (plo_orbit_sweep64)."""
+    m, k, n = mkn
+    L = _i64(L); R = _i64(R); P = _i64(P)
+    best = OrbitBest()
+    f = lib().plo_orbit_sweep64
+    f.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int64] * 3 + [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(OrbitBest)]
+    _check(f(m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), dens[0], dens[1], dens[2], measure, mode, seed, lo, hi, C.byref(best)))
+    return _best_tuple(best)
+
+
+def orbit_table64(mkn, L, R, P, dens, mode, seed, lo, hi):
+    m, k, n = mkn
+    L = _i64(L); R = _i64(R); P = _i64(P)
+    cnt = hi - lo
+    nnz = np.zeros(cnt, dtype=np.uint32); nno = np.zeros(cnt, dtype=np.uint32); g2 = np.zeros(cnt, dtype=np.float64)
+    f = lib().plo_orbit_table64
+    f.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int64] * 3 + [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 3
     _check(f(m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), dens[0], dens[1], dens[2], mode, seed, lo, hi, _ptr(nnz), _ptr(nno), _ptr(g2)))
     return nnz, nno, g2
 

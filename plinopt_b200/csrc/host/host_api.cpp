@@ -62,16 +62,29 @@ int run_sparsifier(const F& f, int rows, int cols, const int64_t* num, const int
   return PLO_OK;
 }
 
-int64_t lcd_of(const int64_t* den, size_t cnt) {
+int64_t lcd_of(const int64_t* den, size_t cnt, wide limit = (wide)INT32_MAX) {
   int64_t l = 1;
   for (size_t e = 0; e < cnt; ++e) {
     const int64_t d = den ? (den[e] < 0 ? -den[e] : den[e]) : 1;
     if (d == 0) throw RangeError("zero denominator");
     const wide v = (wide)l / wgcd(l, d) * d;
-    if (v > (wide)INT32_MAX) throw RangeError("common denominator exceeds 31 bits");
+    if (v > limit) throw RangeError("common denominator too large");
     l = (int64_t)v;
   }
   return l;
+}
+// scaled to 64-bit integers; `fits32` reports whether every entry (and the common denominator) also fits the int32 C ABI
+std::vector<int64_t> scale_int64(const int64_t* num, const int64_t* den, size_t cnt, int64_t lcd, bool& fits32) {
+  std::vector<int64_t> out(cnt);
+  if (lcd > (int64_t)INT32_MAX) fits32 = false;
+  for (size_t e = 0; e < cnt; ++e) {
+    const int64_t d = den ? den[e] : 1;
+    const wide v = (wide)num[e] * (lcd / d);
+    if (wabs(v) >= ((wide)1 << 46)) throw RangeError("scaled entry exceeds 46 bits");
+    if (wabs(v) > (wide)INT32_MAX) fits32 = false;
+    out[e] = (int64_t)v;
+  }
+  return out;
 }
 std::vector<int32_t> scale_int32(const int64_t* num, const int64_t* den, size_t cnt, int64_t lcd) {
   std::vector<int32_t> out(cnt);
@@ -402,15 +415,22 @@ int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int
     for (size_t e = 0; e < L.v.size(); ++e) { ln[e] = L.v[e].num; ld[e] = L.v[e].den; }
     for (size_t e = 0; e < R.v.size(); ++e) { rn[e] = R.v[e].num; rd[e] = R.v[e].den; }
     for (size_t e = 0; e < P.v.size(); ++e) { pn[e] = P.v[e].num; pd[e] = P.v[e].den; }
-    const int64_t dl = lcd_of(ld.data(), ld.size()), dr = lcd_of(rd.data(), rd.size()), dp = lcd_of(pd.data(), pd.size());
-    const std::vector<int32_t> Li = scale_int32(ln.data(), ld.data(), ln.size(), dl), Ri = scale_int32(rn.data(), rd.data(), rn.size(), dr),
-                               Pi = scale_int32(pn.data(), pd.data(), pn.size(), dp);
-    rc = plo_orbit_sweep_devices(g_sweep_devices, m, k, n, r, Li.data(), Ri.data(), Pi.data(), (int32_t)dl, (int32_t)dr, (int32_t)dp, measure, mode, seed, 0, loops, &rep->best);
+    const wide lim = (wide)1 << 46;
+    const int64_t dl = lcd_of(ld.data(), ld.size(), lim), dr = lcd_of(rd.data(), rd.size(), lim), dp = lcd_of(pd.data(), pd.size(), lim);
+    bool fits32 = true;
+    const std::vector<int64_t> L64 = scale_int64(ln.data(), ld.data(), ln.size(), dl, fits32), R64 = scale_int64(rn.data(), rd.data(), rn.size(), dr, fits32),
+                               P64 = scale_int64(pn.data(), pd.data(), pn.size(), dp, fits32);
+    if (fits32) {
+      const std::vector<int32_t> Li(L64.begin(), L64.end()), Ri(R64.begin(), R64.end()), Pi(P64.begin(), P64.end());
+      rc = plo_orbit_sweep_devices(g_sweep_devices, m, k, n, r, Li.data(), Ri.data(), Pi.data(), (int32_t)dl, (int32_t)dr, (int32_t)dp, measure, mode, seed, 0, loops, &rep->best);
+    } else {  // common denominators beyond 2^31 (2x2x2_7_DPS-intermediate-12.0695): the 64-bit input path
+      rc = plo_orbit_sweep64(m, k, n, r, L64.data(), R64.data(), P64.data(), dl, dr, dp, measure, mode, seed, 0, loops, &rep->best);
+    }
     if (rc) return rc;
     // acceptance against the input, src/orbiter.cpp:330-331
     bool improved = false;
     if (rep->best.index != PLO_NO_INDEX) {
-      if (measure == PLO_MEASURE_G2) improved = rep->best.score < rep->init_score;
+      if (measure == PLO_MEASURE_G2) improved = rep->best.score < rep->init_score * (1.0 - 1e-12);  // beyond the rounding of the two evaluations
       else improved = rep->best.nnz < rep->init_nnz || (rep->best.nnz == rep->init_nnz && rep->best.nno < rep->init_nno);
     }
     Dense<QField> Lj = L, Rg = R, hP = P;

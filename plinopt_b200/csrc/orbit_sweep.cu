@@ -25,7 +25,7 @@ namespace plo {
 
 constexpr int kMaxDim = 8;           // nibble-packed permutations
 constexpr int kConstInts = 15360;    // 60 KB of constant memory for L | R | P^T
-__constant__ int c_lrp[kConstInts];
+__constant__ __align__(16) int c_lrp[kConstInts];  // int32 entries, or int64 entries (two words each) for the 64-bit input path
 
 constexpr int MEASURE_BOTH = 4;  // internal: nnz, nno and G2 (tables, winner re-evaluation)
 
@@ -586,9 +586,9 @@ struct AccW {
   int nnz, nno;
   double sq;
 };
-template <int RA, int CA, bool TL, bool TR>
-__host__ __device__ __forceinline__ void transform_row_wide(const int* __restrict__ A, const int* Lm, const int* Rm, long long den, double inv_den, AccW& acc) {
-  int a[RA * CA];
+template <typename TA, int RA, int CA, bool TL, bool TR>
+__host__ __device__ __forceinline__ void transform_row_wide(const TA* __restrict__ A, const int* Lm, const int* Rm, long long den, double inv_den, AccW& acc) {
+  TA a[RA * CA];
 #pragma unroll
   for (int e = 0; e < RA * CA; ++e) a[e] = A[e];
 #pragma unroll
@@ -613,8 +613,11 @@ __host__ __device__ __forceinline__ void transform_row_wide(const int* __restric
     }
   }
 }
-template <int M, int K, int N, int MODE>
-__host__ __device__ __forceinline__ Score score_candidate_wide(const int* __restrict__ lrp, int r, int3 den, double3 inv_den, unsigned long long seed,
+struct Den3 {
+  long long x, y, z;
+};
+template <typename TA, int M, int K, int N, int MODE>
+__host__ __device__ __forceinline__ Score score_candidate_wide(const TA* __restrict__ lrp, int r, Den3 den, double3 inv_den, unsigned long long seed,
                                                                unsigned long long index, volatile int* scr, int stride) {
   Digits<MODE> ds(seed, index);
   const Zoi zu = decode_zoi<M, MODE>(ds);
@@ -627,26 +630,26 @@ __host__ __device__ __forceinline__ Score score_candidate_wide(const int* __rest
   expand_zoi<K, true>(zv, Vi, scr, stride);
   expand_zoi<N, false>(zw, W, scr, stride);
   expand_zoi<N, true>(zw, Wi, scr, stride);
-  const int* Lc = lrp;
-  const int* Rc = lrp + r * M * K;
-  const int* Pc = Rc + r * K * N;
+  const TA* Lc = lrp;
+  const TA* Rc = lrp + r * M * K;
+  const TA* Pc = Rc + r * K * N;
   Score sc;
   sc.nnz = 0; sc.nno = 0; sc.g2 = 0.0;
   for (int l = 0; l < r; ++l) {
     AccW aL, aR, aP;
     aL.nnz = aL.nno = 0; aL.sq = 0.0;
     aR = aL; aP = aL;
-    transform_row_wide<M, K, true, false>(Lc + l * M * K, Ui, V, den.x, inv_den.x, aL);
-    transform_row_wide<K, N, false, false>(Rc + l * K * N, Vi, W, den.y, inv_den.y, aR);
-    transform_row_wide<M, N, false, true>(Pc + l * M * N, U, Wi, den.z, inv_den.z, aP);
+    transform_row_wide<TA, M, K, true, false>(Lc + l * M * K, Ui, V, den.x, inv_den.x, aL);
+    transform_row_wide<TA, K, N, false, false>(Rc + l * K * N, Vi, W, den.y, inv_den.y, aR);
+    transform_row_wide<TA, M, N, false, true>(Pc + l * M * N, U, Wi, den.z, inv_den.z, aP);
     sc.nnz += (uint32_t)(aL.nnz + aR.nnz + aP.nnz);
     sc.nno += (uint32_t)(aL.nno + aR.nno + aP.nno);
     sc.g2 += (sqrt(aL.sq) * sqrt(aR.sq)) * sqrt(aP.sq);
   }
   return sc;
 }
-template <int M, int K, int N, int MODE>
-__global__ void __launch_bounds__(kThreads) orbit_wide_kernel(int r, int3 den, double3 inv_den, int measure, unsigned long long seed, unsigned long long lo,
+template <typename TA, int M, int K, int N, int MODE>
+__global__ void __launch_bounds__(kThreads) orbit_wide_kernel(int r, Den3 den, double3 inv_den, int measure, unsigned long long seed, unsigned long long lo,
                                                                unsigned long long hi, Key* __restrict__ block_best, uint32_t* __restrict__ tnnz,
                                                                uint32_t* __restrict__ tnno, double* __restrict__ tg2) {
   __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
@@ -655,7 +658,7 @@ __global__ void __launch_bounds__(kThreads) orbit_wide_kernel(int r, int3 den, d
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
-    const Score s = score_candidate_wide<M, K, N, MODE>(c_lrp, r, den, inv_den, seed, idx, scr + threadIdx.x, kThreads);
+    const Score s = score_candidate_wide<TA, M, K, N, MODE>(reinterpret_cast<const TA*>(c_lrp), r, den, inv_den, seed, idx, scr + threadIdx.x, kThreads);
     if (tnnz) tnnz[idx - lo] = s.nnz;
     if (tnno) tnno[idx - lo] = s.nno;
     if (tg2) tg2[idx - lo] = s.g2;
@@ -667,18 +670,19 @@ __global__ void __launch_bounds__(kThreads) orbit_wide_kernel(int r, int3 den, d
   best = block_min(best, red);
   if (threadIdx.x == 0 && block_best) block_best[blockIdx.x] = best;
 }
-typedef void (*WideLaunch)(int mode, int grid, cudaStream_t st, int r, int3 den, double3 inv_den, int measure, unsigned long long seed,
+typedef void (*WideLaunch)(int mode, int grid, cudaStream_t st, int r, Den3 den, double3 inv_den, int measure, unsigned long long seed,
                            unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno, double* tg2);
-template <int M, int K, int N>
-static void wide_launch(int mode, int grid, cudaStream_t st, int r, int3 den, double3 inv_den, int measure, unsigned long long seed,
+template <typename TA, int M, int K, int N>
+static void wide_launch(int mode, int grid, cudaStream_t st, int r, Den3 den, double3 inv_den, int measure, unsigned long long seed,
                         unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno, double* tg2) {
-  if (mode == 0) orbit_wide_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2);
-  else orbit_wide_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2);
+  if (mode == 0) orbit_wide_kernel<TA, M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2);
+  else orbit_wide_kernel<TA, M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2);
 }
+template <typename TA>
 static WideLaunch find_wide(int m, int k, int n) {
-  if (m == 2 && k == 2 && n == 2) return &wide_launch<2, 2, 2>;
-  if (m == 3 && k == 3 && n == 3) return &wide_launch<3, 3, 3>;
-  if (m == 4 && k == 4 && n == 4) return &wide_launch<4, 4, 4>;
+  if (m == 2 && k == 2 && n == 2) return &wide_launch<TA, 2, 2, 2>;
+  if (m == 3 && k == 3 && n == 3) return &wide_launch<TA, 3, 3, 3>;
+  if (m == 4 && k == 4 && n == 4) return &wide_launch<TA, 4, 4, 4>;
   return nullptr;
 }
 
@@ -928,7 +932,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   bool lanes16 = false;
   WideLaunch wide = nullptr;
   if (!magnitude_ok(m, k, n, r, L, R, P, &smax, &lanes16)) {
-    wide = find_wide(m, k, n);  // exact in 64 bits for every int32 input of these shapes
+    wide = find_wide<int>(m, k, n);  // exact in 64 bits for every int32 input of these shapes
     if (!wide) { set_error("orbit sweep: int32 magnitude bound exceeded and no 64-bit kernel for %dx%dx%d", m, k, n); return PLO_E_RANGE; }
     smax = 0; lanes16 = false;
   }
@@ -994,7 +998,7 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
     PLO_CUDA(cudaMemcpyAsync(pl->d_block_best, init.data(), sizeof(Key) * pl->grid, cudaMemcpyHostToDevice, st));
     if (hi > lo) {
       const unsigned long long blocks = (hi - lo + kThreads - 1) / kThreads;
-      pl->wide(pl->mode, (int)std::min<unsigned long long>(blocks, (unsigned long long)pl->grid), st, pl->r, pl->den, pl->inv_den3, pl->measure, pl->seed, lo, hi,
+      pl->wide(pl->mode, (int)std::min<unsigned long long>(blocks, (unsigned long long)pl->grid), st, pl->r, Den3{pl->den.x, pl->den.y, pl->den.z}, pl->inv_den3, pl->measure, pl->seed, lo, hi,
                pl->d_block_best, nullptr, nullptr, nullptr);
     }
     PLO_CUDA(cudaGetLastError());
@@ -1021,7 +1025,7 @@ int plo_orbit_plan_result(plo_orbit_plan* pl, void* stream, plo_orbit_best* best
     if (b.index == ~0ull) return PLO_OK;
     int rc = orbit_upload(pl, st);
     if (rc) return rc;
-    pl->wide(pl->mode, 1, st, pl->r, pl->den, pl->inv_den3, pl->measure, pl->seed, b.index, b.index + 1, nullptr, pl->d_wide_cnt, pl->d_wide_cnt + 1, pl->d_wide_g2);
+    pl->wide(pl->mode, 1, st, pl->r, Den3{pl->den.x, pl->den.y, pl->den.z}, pl->inv_den3, pl->measure, pl->seed, b.index, b.index + 1, nullptr, pl->d_wide_cnt, pl->d_wide_cnt + 1, pl->d_wide_g2);
     uint32_t cnt[2];
     double g2 = 0.0;
     PLO_CUDA(cudaMemcpyAsync(cnt, pl->d_wide_cnt, 8, cudaMemcpyDeviceToHost, st));
@@ -1125,7 +1129,7 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
     if (!rc) {
       size_t blocks = (cnt + kThreads - 1) / kThreads;
       int grid = (int)(blocks < (size_t)pl->grid ? blocks : (size_t)pl->grid);
-      if (pl->wide) pl->wide(mode, grid, nullptr, r, pl->den, pl->inv_den3, PLO_MEASURE_G2, seed, lo, hi, nullptr, d_nnz, d_nno, d_g2);
+      if (pl->wide) pl->wide(mode, grid, nullptr, r, Den3{pl->den.x, pl->den.y, pl->den.z}, pl->inv_den3, PLO_MEASURE_G2, seed, lo, hi, nullptr, d_nnz, d_nno, d_g2);
       else pl->ops->table(mode, grid, nullptr, r, pl->den, seed, lo, hi, pl->inv_den, d_nnz, d_nno, d_g2);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { set_error("plo_orbit_table: %s", cudaGetErrorString(e)); rc = PLO_E_CUDA; }
@@ -1138,6 +1142,84 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
   }
   cleanup();
   return rc;
+}
+
+// 64-bit inputs (common denominators beyond 2^31, e.g. 2x2x2_7_DPS-intermediate-12.0695): same exact 64-bit kernels, the constant
+// bank holds int64 entries.  |entries| < 2^46 keeps both product stages inside 64 bits.  Synchronous; winner and/or per-candidate table.
+static int orbit_wide64(int m, int k, int n, int r, const int64_t* L, const int64_t* R, const int64_t* P, int64_t denL, int64_t denR, int64_t denP,
+                        int measure, int mode, uint64_t seed, uint64_t lo, uint64_t hi, plo_orbit_best* best, uint32_t* tnnz, uint32_t* tnno, double* tg2) {
+  if (!L || !R || !P || r < 1 || denL == 0 || denR == 0 || denP == 0 || (measure != PLO_MEASURE_NNZ && measure != PLO_MEASURE_G2) ||
+      (mode != 0 && mode != 1) || hi < lo) { set_error("orbit sweep (64-bit inputs): bad argument"); return PLO_E_ARG; }
+  int rc = check_device();
+  if (rc) return rc;
+  const WideLaunch launch = find_wide<long long>(m, k, n);
+  if (!launch) { set_error("orbit sweep (64-bit inputs): shape %dx%dx%d not compiled in", m, k, n); return PLO_E_SHAPE; }
+  const size_t total = (size_t)r * (m * k + k * n + m * n);
+  if (2 * total > (size_t)kConstInts) { set_error("orbit sweep: L/R/P exceed constant memory"); return PLO_E_SHAPE; }
+  if (mode == 0 && plo_orbit_space(m, k, n) == 0) { set_error("orbit sweep: exhaustive space exceeds 64 bits"); return PLO_E_SHAPE; }
+  std::vector<long long> h(total);
+  long long* dst = h.data();
+  const long long lim = 1ll << 46;
+  bool ok = true;
+  auto put = [&](int64_t v) { if (v >= lim || v <= -lim) ok = false; *dst++ = v; };
+  for (int i = 0; i < r * m * k; ++i) put(L[i]);
+  for (int i = 0; i < r * k * n; ++i) put(R[i]);
+  for (int l = 0; l < r; ++l) for (int e = 0; e < m * n; ++e) put(P[(size_t)e * r + l]);
+  if (!ok) { set_error("orbit sweep (64-bit inputs): |entry| >= 2^46"); return PLO_E_RANGE; }
+  const Den3 den{denL < 0 ? -denL : denL, denR < 0 ? -denR : denR, denP < 0 ? -denP : denP};
+  const double3 inv = make_double3(1.0 / (double)den.x, 1.0 / (double)den.y, 1.0 / (double)den.z);
+  const uint64_t cnt = hi - lo;
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((cnt + kThreads - 1) / kThreads, (uint64_t)sm_count() * 4));
+  Key* d_bb = nullptr;
+  uint32_t *d_nnz = nullptr, *d_nno = nullptr;
+  double* d_g2 = nullptr;
+  auto cleanup = [&]() { pool_free(d_bb); pool_free(d_nnz); pool_free(d_nno); pool_free(d_g2); };
+  const_owner() = nullptr;
+  cudaError_t e = cudaMemcpyToSymbol(c_lrp, h.data(), total * sizeof(long long));
+  Key none;
+  none.primary = ~0ull; none.index = ~0ull;
+  std::vector<Key> bb((size_t)grid, none);
+  if (e == cudaSuccess) e = pool_alloc(&d_bb, sizeof(Key) * grid);
+  if (e == cudaSuccess) e = cudaMemcpy(d_bb, bb.data(), sizeof(Key) * grid, cudaMemcpyHostToDevice);
+  const bool want_tab = tnnz || tnno || tg2;
+  if (e == cudaSuccess && want_tab) e = pool_alloc(&d_nnz, (cnt ? cnt : 1) * 4);
+  if (e == cudaSuccess && want_tab) e = pool_alloc(&d_nno, (cnt ? cnt : 1) * 4);
+  if (e == cudaSuccess && want_tab) e = pool_alloc(&d_g2, (cnt ? cnt : 1) * 8);
+  if (e == cudaSuccess && cnt) { launch(mode, grid, nullptr, r, den, inv, measure, seed, lo, hi, d_bb, d_nnz, d_nno, d_g2); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpy(bb.data(), d_bb, sizeof(Key) * grid, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && tnnz && cnt) e = cudaMemcpy(tnnz, d_nnz, cnt * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && tnno && cnt) e = cudaMemcpy(tnno, d_nno, cnt * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && tg2 && cnt) e = cudaMemcpy(tg2, d_g2, cnt * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && best) {
+    Key b = bb[0];
+    for (const Key& x : bb) if (key_less(x, b)) b = x;
+    best->index = b.index; best->nnz = 0; best->nno = 0; best->score = 0.0;
+    if (b.index != ~0ull) {  // all measures of the winner: one 1-candidate launch
+      uint32_t* d_c = nullptr; double* d_g = nullptr;
+      if (pool_alloc(&d_c, 8) == cudaSuccess && pool_alloc(&d_g, 8) == cudaSuccess) {
+        launch(mode, 1, nullptr, r, den, inv, measure, seed, b.index, b.index + 1, nullptr, d_c, d_c + 1, d_g);
+        uint32_t c2[2] = {0, 0}; double g = 0.0;
+        e = cudaMemcpy(c2, d_c, 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(&g, d_g, 8, cudaMemcpyDeviceToHost);
+        best->nnz = c2[0]; best->nno = c2[1]; best->score = measure == PLO_MEASURE_G2 ? g : (double)c2[0];
+      } else e = cudaErrorMemoryAllocation;
+      pool_free(d_c); pool_free(d_g);
+    }
+  }
+  cleanup();
+  if (e != cudaSuccess) { set_error("orbit sweep (64-bit inputs): %s", cudaGetErrorString(e)); return PLO_E_CUDA; }
+  return PLO_OK;
+}
+
+int plo_orbit_sweep64(int m, int k, int n, int r, const int64_t* L, const int64_t* R, const int64_t* P, int64_t denL, int64_t denR, int64_t denP,
+                      int measure, int mode, uint64_t seed, uint64_t lo, uint64_t hi, plo_orbit_best* best) {
+  if (!best) { set_error("plo_orbit_sweep64: null output"); return PLO_E_ARG; }
+  return orbit_wide64(m, k, n, r, L, R, P, denL, denR, denP, measure, mode, seed, lo, hi, best, nullptr, nullptr, nullptr);
+}
+
+int plo_orbit_table64(int m, int k, int n, int r, const int64_t* L, const int64_t* R, const int64_t* P, int64_t denL, int64_t denR, int64_t denP,
+                      int mode, uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* nnz, uint32_t* nno, double* g2) {
+  return orbit_wide64(m, k, n, r, L, R, P, denL, denR, denP, PLO_MEASURE_G2, mode, seed, lo, hi, nullptr, nnz ? nnz : nullptr, nno, g2);
 }
 
 int plo_orbit_table_modp(uint32_t p, int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int mode,

@@ -179,3 +179,24 @@ def test_wide_exact_path_for_large_denominators(capi):
     assert (gotn["index"], gotn["nnz"], gotn["nno"]) == refn[:3]
     halves = [capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 0, 1, SEED, 0, 11111), capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 0, 1, SEED, 11111, 30000)]
     assert min(halves, key=lambda b: (b["nnz"], b["nno"], b["index"])) == gotn
+
+
+def test_int64_inputs_dps_intermediate(capi):
+    """2x2x2_7_DPS-intermediate-12.0695: common denominator 1.0e11 > 2^31, outside the int32 C ABI -> plo_orbit_sweep64 / table64.
+    Same exactness contract as the wide path: counts bit-exact, G2 within 1e-12; its own G2 (12.06954148,
+    data/2x2x2_7_DPS-intermediate-12.0695_L.sms:1) is the minimum of its orbit."""
+    L, R, P = O.triple("2x2x2_7_DPS-intermediate-12.0695")
+    mkn = O.LRP2MM(L, R, P)
+    (Li, dl), (Ri, dr), (Pi, dp) = O.scaled_int(L), O.scaled_int(R), O.scaled_int(P)
+    assert max(dl, dr, dp) > 2 ** 31
+    space = capi.orbit_space(*mkn)
+    ref = O.orbit_sweep(L, R, P, 3, 0, 0, 0, space)
+    nnz, nno, g2 = capi.orbit_table64(mkn, Li, Ri, Pi, (dl, dr, dp), 0, 0, 0, space)
+    assert np.array_equal(nnz, ref["nnz"]) and np.array_equal(nno, ref["nno"]) and np.allclose(g2, ref["g2"], rtol=RTOL, atol=0)
+    got = capi.orbit_sweep64(mkn, Li, Ri, Pi, (dl, dr, dp), 3, 0, 0, 0, space)
+    assert abs(got["score"] - 12.06954148) < 5e-9
+    gotn = capi.orbit_sweep64(mkn, Li, Ri, Pi, (dl, dr, dp), 0, 1, SEED, 0, 20000)
+    assert (gotn["index"], gotn["nnz"], gotn["nno"]) == O.orbit_sweep(L, R, P, 0, 1, SEED, 0, 20000, table=False)["best"][:3]
+    # host-level driver picks the 64-bit path by itself
+    rc = capi.orbiter(L, R, P, measure=capi.MEASURE_G2, mode=capi.MODE_EXHAUSTIVE, seed=0, loops=space)
+    assert rc[3]["mm_verdict"] == 0 and not rc[3]["improved"]

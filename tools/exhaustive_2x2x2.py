@@ -18,16 +18,15 @@ for stem in stems:
     L, R, P = hm.load_fixture(stem)
     mkn = hm.LRP2MM(L, R, P)
     (Li, dl), (Ri, dr), (Pi, dp) = (hm.scaled(M, np.int64) for M in (L, R, P))
-    if max(dl, dr, dp) >= 2 ** 31 or max(int(np.abs(A).max()) for A in (Li, Ri, Pi)) >= 2 ** 31:
-        print(f"{stem:36s} common denominators {dl}, {dr}, {dp}: outside the exact int32 path")
-        continue
     nnz0 = sum(1 for M in (L, R, P) for row in M for v in row if v != 0)
     g0 = capi.growth_G2(np.array([[float(v) for v in row] for row in L]), np.array([[float(v) for v in row] for row in R]),
                         np.array([[float(v) for v in row] for row in P]))[0]
     space = capi.orbit_space(*mkn)
+    wide = max(dl, dr, dp) >= 2 ** 31 or max(int(np.abs(A).max()) for A in (Li, Ri, Pi)) >= 2 ** 31  # beyond the int32 C ABI
+    sweep = (lambda *a: capi.orbit_sweep64(*a)) if wide else (lambda *a: capi.orbit_sweep(*a))
     try:
-        a = capi.orbit_sweep(mkn, Li, Ri, Pi, (dl, dr, dp), capi.MEASURE_NNZ, capi.MODE_EXHAUSTIVE, 0, 0, space)
-        b = capi.orbit_sweep(mkn, Li, Ri, Pi, (dl, dr, dp), capi.MEASURE_G2, capi.MODE_EXHAUSTIVE, 0, 0, space)
+        a = sweep(mkn, Li, Ri, Pi, (dl, dr, dp), capi.MEASURE_NNZ, capi.MODE_EXHAUSTIVE, 0, 0, space)
+        b = sweep(mkn, Li, Ri, Pi, (dl, dr, dp), capi.MEASURE_G2, capi.MODE_EXHAUSTIVE, 0, 0, space)
     except capi.PloError as e:  # common denominators of ~10^9: outside the exact int32 path (PLO_E_RANGE), reported, never wrapped
         print(f"{stem:36s} {nnz0:5d} {g0:10.6f} | {str(e)[:70]}")
         continue
