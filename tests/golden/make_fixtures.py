@@ -30,6 +30,7 @@ STEMS = [
 SINGLES = ["cyclic"]
 # straight-line programs the reference ships next to the .sms they were generated from (data/Makefile:31-32):
 # golden pairs for the SLP -> matrix builder
+ALL_OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "all_matrices.json")
 SLP_OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "slp_programs.json")
 SLP_STEMS = ["2x2x2_7_Winograd", "3x3x3_23_58", "3x4x7_63_rational", "3x4x7_63_rational-ALT", "3x4x7_63_rational-CoB",
              "4x4x4_48_rational", "4x4x4_48_rational-CoB", "4x4x4_48_accurate", "4x4x4_49_156"]
@@ -72,6 +73,18 @@ def main():
     with open(OUT, "w") as f:
         json.dump(out, f, separators=(",", ":"), sort_keys=True)
     print("wrote", OUT, len(out), "matrices", os.path.getsize(OUT), "bytes")
+    # every rational .sms of data/ (bin/FDT.sh and `make mmcheck` run over the whole directory); the three polynomial
+    # files *-X_{L,R,P}.sms are out of scope
+    allm = {}
+    for fn in sorted(os.listdir(os.path.join(REF, "data"))):
+        if fn.endswith(".sms"):
+            try:
+                allm[fn[:-4]] = read_sms(os.path.join(REF, "data", fn))
+            except ValueError:
+                pass
+    with open(ALL_OUT, "w") as f:
+        json.dump(allm, f, separators=(",", ":"), sort_keys=True)
+    print("wrote", ALL_OUT, len(allm), "matrices", os.path.getsize(ALL_OUT), "bytes")
     slp = {f"{stem}_{x}": open(os.path.join(REF, "data", f"{stem}_{x}.slp")).read() for stem in SLP_STEMS for x in "LRP"}
     with open(SLP_OUT, "w") as f:
         json.dump(slp, f, separators=(",", ":"), sort_keys=True)
