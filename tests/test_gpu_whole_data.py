@@ -85,3 +85,24 @@ def test_orbit_sweep_on_every_shipped_triple(capi):
                 assert got["index"] == ref[0] or abs(got["score"] - ref[3]) <= 1e-12 * ref[3], stem
             swept += 1
     assert swept >= 40 and refused <= 8
+
+
+def test_factorizer_on_every_shipped_matrix(capi):
+    """`factorizer -O 64 f` on every shipped matrix the device search covers (tall, at most 32 columns): the result is a consistent
+    factorisation never worse than the trivial one; rank-deficient inputs are refused (backSolver's precondition)."""
+    done = refused = 0
+    for name in sorted(ALL):
+        M = dense(name)
+        r, n = len(M), len(M[0])
+        if r <= n or n > 32:
+            continue
+        try:
+            rc, Alt, CoB, rep = capi.factorizer(M, loops=64, seed=3)
+        except capi.PloError as e:
+            assert "full column rank" in str(e), (name, str(e))
+            refused += 1
+            continue
+        assert rc == 0 and rep["consistent"] and rep["final"] <= rep["initial"], name
+        assert [[sum(Alt[i][t] * CoB[t][j] for t in range(n)) for j in range(n)] for i in range(r)] == M, name
+        done += 1
+    assert done >= 60 and refused <= 10
