@@ -307,6 +307,12 @@ int plo_orbiter_modp(uint64_t q, int mode, uint64_t seed, uint64_t loops, int r,
                      const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd, const int64_t* Pn,
                      const int64_t* Pd, int64_t* oL, int64_t* oR, int64_t* oP, plo_orbiter_report* rep);
 
+/* growthfactor  src/growthfactor.cpp:143-231: growth / error factors of one triple, in the reference's print order
+ * out[11] = Ginfinf, Ginf2, G2inf, G22, G2, Q0, Qkinfinf, Q1inf2, Q12inf, Qk2inf, Q122.  G2 (:117-125, the measure the orbit sweep
+ * minimises) is evaluated on the device; the other norms (:57-143) on the host. */
+int plo_growth_factors(int r, int Lcols, int Rcols, int Prows, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn,
+                       const int64_t* Rd, const int64_t* Pn, const int64_t* Pd, double* out);
+
 /* Factorizer  include/plinopt_sparsify.inl:924-990  (driver TFactorizer src/factorizer.cpp:28-97 without the
  * optional initial sparsification): M (rows x cols, full column rank) -> Alt (rows x k) . CoB (k x cols),
  * k = innerdim (0: cols), minimising (nnz(Alt), non-+-1 of Alt, nnz(CoB)) over `loops` random row orders

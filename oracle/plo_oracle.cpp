@@ -1411,3 +1411,40 @@ int orc_rotater(int right, int m, int k, int n, int r, const int64_t* Ln, const 
   return g_overflow ? -g_overflow : 0;
 }
 }  // extern "C"
+
+// =============================================================================
+// growthfactor (src/growthfactor.cpp:25-143): the eleven factors printed by its main (:199-229), restated literally on the
+// stored (non-zero) entries of each sparse row.
+// =============================================================================
+extern "C" int orc_growth_factors(int r, int a, int b, int c, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                                  const int64_t* Pn, const int64_t* Pd, double* out) {
+  g_overflow = 0;
+  QField f;
+  const Mat<QField> L = Loader<QField>::load(f, r, a, Ln, Ld), R = Loader<QField>::load(f, r, b, Rn, Rd), P = Loader<QField>::load(f, c, r, Pn, Pd);
+  size_t m, k, n;
+  LRP2MM(L.c, R.c, P.r, m, k, n);
+  auto n0 = [&](const Mat<QField>& M, size_t i) { return (double)rowSize(f, M, i); };                                                   // :32-34
+  auto n1 = [&](const Mat<QField>& M, size_t i) { double s = 0; for (size_t j = 0; j < M.c; ++j) if (!f.isZero(M(i, j))) s += std::fabs(toDouble(f, M(i, j))); return s; };
+  std::vector<double> GPinf(P.r, 0.), GP2(P.r, 0.);
+  for (size_t i = 0; i < P.c; ++i) {                                                                                                    // :57-67, 87-97
+    const double n1LRi = n1(L, i) * n1(R, i), n2LRi = norm2row(f, L, i) * norm2row(f, R, i);
+    for (size_t j = 0; j < P.r; ++j) { const double x = std::fabs(toDouble(f, P(j, i))); GPinf[j] += n1LRi * x; GP2[j] += n2LRi * x; }
+  }
+  auto vnorm2 = [](const std::vector<double>& v) { double s = 0; for (double x : v) s += x * x; return std::sqrt(s); };
+  const double ginfinf = *std::max_element(GPinf.begin(), GPinf.end()), ginf2 = *std::max_element(GP2.begin(), GP2.end());             // :70-75, 100-105
+  const double g2inf = vnorm2(GPinf), g22 = vnorm2(GP2), g2 = G2(f, L, R, P);                                                           // :78-83, 109-125
+  std::vector<double> n0LR(P.c);
+  for (size_t i = 0; i < P.c; ++i) n0LR[i] = n0(L, i) * n0(R, i);                                                                       // :128-143
+  double q0 = 0.;
+  for (size_t j = 0; j < P.r; ++j) {
+    double rj = 0.;
+    for (size_t i = 0; i < P.c; ++i) if (!f.isZero(P(j, i)) && n0LR[i] > rj) rj = n0LR[i];
+    rj += n0(P, j);
+    if (rj > q0) q0 = rj;
+  }
+  auto Qk = [](double q, double gamma, double kk) { return q * gamma / std::abs(gamma - kk); };                                         // :145
+  const double sqrtk = std::sqrt((double)k), kth = sqrtk * sqrtk * sqrtk;
+  const double v[11] = {ginfinf, ginf2, g2inf, g22, g2, q0, Qk(q0, ginfinf, (double)k), Qk(q0, ginf2, 1.), Qk(q0, g2inf, 1.), Qk(q0, g2inf, kth), Qk(q0, g22, 1.)};
+  for (int t = 0; t < 11; ++t) out[t] = v[t];
+  return g_overflow ? -g_overflow : 0;
+}

@@ -66,7 +66,7 @@ def build_library(force=False, verbose=False):
 
 CLI_DIR = os.path.join(HERE, "cli")
 BIN_DIR = os.path.join(os.path.dirname(HERE), "bin")
-CLIS = ["sparsifier", "orbiter", "MMchecker", "factorizer", "dependency", "negater", "rotater"]
+CLIS = ["sparsifier", "orbiter", "MMchecker", "factorizer", "dependency", "negater", "rotater", "growthfactor"]
 
 
 def build_clis(force=False):

@@ -31,7 +31,7 @@ SYMBOLS = [
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
     "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
     "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
-    "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender", "plo_negater", "plo_rotater",
+    "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender", "plo_negater", "plo_rotater", "plo_growth_factors",
 ]
 
 
@@ -618,3 +618,16 @@ def rotater(L, R, P, right=False):
     shapes = [(r, m * n), (r, m * k), (n * k, r)] if right else [(r, k * n), (r, m * n), (m * k, r)]
     rc, mats, _ = _triple_pass("plo_rotater", [1 if right else 0, r, len(L[0]), len(R[0]), len(P)], L, R, P, shapes)
     return rc, mats
+
+
+GROWTH_NAMES = ("Ginfinf", "Ginf2", "G2inf", "G22", "G2", "Q0", "Qkinfinf", "Q1inf2", "Qk12inf", "Qk2inf", "Q122")
+
+
+def growth_factors(L, R, P):
+    """plo_growth_factors: dict of the eleven factors of src/growthfactor.cpp:199-229."""
+    Ln, Ld = _numden(L); Rn, Rd = _numden(R); Pn, Pd = _numden(P)
+    out = np.zeros(11, dtype=np.float64)
+    f = lib().plo_growth_factors
+    f.argtypes = [C.c_int] * 4 + [C.c_void_p] * 7
+    _check(f(len(L), len(L[0]), len(R[0]), len(P), _ptr(Ln), _ptr(Ld), _ptr(Rn), _ptr(Rd), _ptr(Pn), _ptr(Pd), _ptr(out)))
+    return dict(zip(GROWTH_NAMES, out.tolist()))

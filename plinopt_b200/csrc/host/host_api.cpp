@@ -2,6 +2,7 @@
 // the GPU kernels (TSparsifier src/sparsifier.cpp:20-55, Orbiter src/orbiter.cpp:215-360,
 // fMMchecker src/MMchecker.cpp:48-81).  No CUDA code here; everything heavy goes through the
 // kernel-level C ABI (plo_lincomb_search, plo_orbit_*, plo_mmcheck_*).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -601,6 +602,50 @@ int plo_rotater(int right, int r, int Lcols, int Rcols, int Prows, const int64_t
 int plo_set_sweep_devices(int n) {
   if (n < 1) { plo::set_error("plo_set_sweep_devices: need n >= 1"); return PLO_E_ARG; }
   g_sweep_devices = n;
+  return PLO_OK;
+}
+
+// growthfactor  src/growthfactor.cpp:143-231: the growth / error factors of one triple.  G2 (:117-125) is the measure of the orbit
+// sweep and comes from the device (plo_growth_G2); the other norms are a few passes over the matrices on the host.
+// out[11] = Ginfinf, Ginf2, G2inf, G22, G2, Q0, Qkinfinf, Q1inf2, Q12inf, Qk2inf, Q122   (print order of :199-229)
+int plo_growth_factors(int r, int Lcols, int Rcols, int Prows, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                       const int64_t* Pn, const int64_t* Pd, double* out) {
+  if (!Ln || !Rn || !Pn || !out || r < 1 || Lcols < 1 || Rcols < 1 || Prows < 1) { plo::set_error("plo_growth_factors: bad argument"); return PLO_E_ARG; }
+  int m, k, n;
+  plo_LRP2MM(Lcols, Rcols, Prows, &m, &k, &n);
+  auto dbl = [](int64_t a, const int64_t* den, size_t e) { return (double)a / (double)(den ? den[e] : 1); };  // access(), :25-28
+  std::vector<double> L((size_t)r * Lcols), R((size_t)r * Rcols), P((size_t)Prows * r);
+  for (size_t e = 0; e < L.size(); ++e) L[e] = dbl(Ln[e], Ld, e);
+  for (size_t e = 0; e < R.size(); ++e) R[e] = dbl(Rn[e], Rd, e);
+  for (size_t e = 0; e < P.size(); ++e) P[e] = dbl(Pn[e], Pd, e);
+  auto row = [](const std::vector<double>& M, int cols, int i) { return M.data() + (size_t)i * cols; };
+  auto norm0 = [](const double* v, int c) { double s = 0; for (int j = 0; j < c; ++j) s += v[j] != 0.0; return s; };             // :32-34
+  auto norm1 = [](const double* v, int c) { double s = 0; for (int j = 0; j < c; ++j) s += std::fabs(v[j]); return s; };        // :36-39
+  auto norm2 = [](const double* v, int c) { double s = 0; for (int j = 0; j < c; ++j) s += v[j] * v[j]; return std::sqrt(s); };  // :41-44
+  std::vector<double> gpinf((size_t)Prows, 0.), gp2((size_t)Prows, 0.);                                                         // :57-67, 87-97
+  for (int i = 0; i < r; ++i) {
+    const double n1 = norm1(row(L, Lcols, i), Lcols) * norm1(row(R, Rcols, i), Rcols);
+    const double n2 = norm2(row(L, Lcols, i), Lcols) * norm2(row(R, Rcols, i), Rcols);
+    for (int j = 0; j < Prows; ++j) { const double a = std::fabs(P[(size_t)j * r + i]); gpinf[(size_t)j] += n1 * a; gp2[(size_t)j] += n2 * a; }
+  }
+  const double ginfinf = *std::max_element(gpinf.begin(), gpinf.end()), ginf2 = *std::max_element(gp2.begin(), gp2.end());
+  const double g2inf = norm2(gpinf.data(), Prows), g22 = norm2(gp2.data(), Prows);
+  double g2 = 0.;
+  const int rc = plo_growth_G2(1, r, Lcols, Rcols, Prows, L.data(), R.data(), P.data(), &g2);
+  if (rc) return rc;
+  std::vector<double> n0LR((size_t)r);                                                                                          // Q0 :128-143
+  for (int i = 0; i < r; ++i) n0LR[(size_t)i] = norm0(row(L, Lcols, i), Lcols) * norm0(row(R, Rcols, i), Rcols);
+  double q0 = 0.;
+  for (int j = 0; j < Prows; ++j) {
+    double rj = 0.;
+    for (int i = 0; i < r; ++i) if (P[(size_t)j * r + i] != 0.0 && n0LR[(size_t)i] > rj) rj = n0LR[(size_t)i];
+    rj += norm0(row(P, r, j), r);
+    if (rj > q0) q0 = rj;
+  }
+  auto Qk = [](double q, double gamma, double kk) { return q * gamma / std::fabs(gamma - kk); };                                // :145
+  const double sqrtk = std::sqrt((double)k), kth = sqrtk * sqrtk * sqrtk;
+  const double v[11] = {ginfinf, ginf2, g2inf, g22, g2, q0, Qk(q0, ginfinf, (double)k), Qk(q0, ginf2, 1.), Qk(q0, g2inf, 1.), Qk(q0, g2inf, kth), Qk(q0, g22, 1.)};
+  for (int t = 0; t < 11; ++t) out[t] = v[t];
   return PLO_OK;
 }
 

@@ -345,3 +345,15 @@ def rotater(L, R, P, right=False):
     r = len(L)
     shapes = [(r, m * n), (r, m * k), (n * k, r)] if right else [(r, k * n), (r, m * n), (m * k, r)]
     return _triple_call("orc_rotater", [1 if right else 0, m, k, n, r], L, R, P, shapes)[0]
+
+
+def growth_factors(L, R, P):
+    """src/growthfactor.cpp:199-229: the eleven printed factors, in print order."""
+    Ln, Ld = numden(L); Rn, Rd = numden(R); Pn, Pd = numden(P)
+    out = np.zeros(11, dtype=np.float64)
+    f = lib().orc_growth_factors
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 4 + [C.c_void_p] * 7
+    rc = f(len(L), len(L[0]), len(R[0]), len(P), *[a.ctypes.data for a in (Ln, Ld, Rn, Rd, Pn, Pd)], out.ctypes.data)
+    assert rc == 0
+    return out.tolist()

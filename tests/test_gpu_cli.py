@@ -137,3 +137,12 @@ def test_mmchecker_cli_on_the_regenerated_32x32x32(capi, tmp_path):
     bad.write_text("\n".join(lines) + "\n")
     q = run(["-m", "2147483647", files[0], files[1], str(bad)])
     assert q.returncode == 1 and "not a 32x32x32 MM algorithm" in q.stderr
+
+
+def test_growthfactor_cli(capi, tmp_path):
+    files = write_triple(tmp_path, "2x2x2_7_Strassen")
+    p = subprocess.run([os.path.join(BIN, "growthfactor")] + files, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "# Norms of 2x2x2 Matrix-Multiplication:" in p.stderr and "## Ginfinf:\t12.000000" in p.stderr and "## G2:\t\t14.828427" in p.stderr
+    bad = write_triple(tmp_path, "3x3x3_23_58")
+    assert subprocess.run([os.path.join(BIN, "growthfactor"), files[0], bad[1], files[2]], capture_output=True, text=True, timeout=300).returncode == 2

@@ -155,3 +155,18 @@ def test_modular_orbiter_driver(capi, stem, q):
         assert nnz == rep["best"]["nnz"]
     else:
         assert (Lj, Rg, hP) == (red(L), red(R), red(P))
+
+
+@pytest.mark.parametrize("stem", ["2x2x2_7_Strassen", "2x2x2_7_Winograd", "2x2x2_7_DPS-integral-12.0662", "3x3x3_23_58", "4x4x4_48_rational", "3x4x7_63_rational"])
+def test_growth_factors(capi, stem):
+    """growthfactor (src/growthfactor.cpp:148-231): the eleven printed factors against the oracle's literal restatement (1e-12), and
+    the classical values: Strassen gamma_inf,inf = 12, Winograd 18 (Ballard et al.), G2 as in the file names."""
+    L, R, P = O.triple(stem)
+    got = capi.growth_factors(L, R, P)
+    ref = O.growth_factors(L, R, P)
+    for name, e in zip(got, ref):
+        assert abs(got[name] - e) <= 1e-12 * abs(e), name
+    if stem == "2x2x2_7_Strassen":
+        assert got["Ginfinf"] == 12.0 and abs(got["G2"] - (12 + 2 * 2 ** 0.5)) < 1e-12 and got["Q0"] == 8.0
+    if stem == "2x2x2_7_Winograd":
+        assert got["Ginfinf"] == 18.0 and abs(got["G2"] - 17.8530) < 5e-5
