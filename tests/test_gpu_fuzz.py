@@ -1,0 +1,130 @@
+"""GPU: randomised differential tests against the oracle (seeded; ragged shapes, tiny and degenerate inputs).
+  * sparsifier search: random TM (n = 1..9 rows, m = 1..70 columns), random previous rows (sometimes dependent), every offset,
+    over Q and modulo small / large primes;
+  * batched MMchecker: random sparse "triples" (not algorithms: most samples must FAIL identically), few distinct values
+    (grouped format) or all distinct (plain format), operands wider than one slab."""
+import math
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from plinopt_b200 import hm
+
+pytestmark = pytest.mark.gpu
+
+
+def _residue(v, p):
+    return (v.numerator % p) * pow(v.denominator % p, -1, p) % p
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_lincomb_random_instances(capi, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 10)); m = int(rng.choice([1, 2, 5, 8, 9, 16, 17, 33, 48, 64, 65, 70]))
+    p = int(rng.choice([0, 0, 3, 7, 101, 2147483647]))
+    dens = [1, 1, 1, 2, 3, 4]
+    if p:
+        dens = [d for d in dens if d % p]
+    TM = [[Fraction(int(rng.choice([0, 0, 0, 1, -1, 2, -3])), int(rng.choice(dens))) for _ in range(m)] for _ in range(n)]
+    c = int(rng.choice([2, 3, 4, 5, 7]))
+    if p:
+        c = min(c, p)
+    nblocks = (n + 3) // 4
+    off = 4 * int(rng.integers(0, nblocks))
+    nprev = int(rng.integers(0, n))  # rows already chosen (may be linearly dependent: then nothing is admissible)
+    prev = [[Fraction(int(rng.integers(-2, 3))) for _ in range(n)] for _ in range(nprev)]
+    if nprev >= 2 and rng.random() < 0.3:
+        prev[-1] = [2 * v for v in prev[0]]
+    init = (-1, -1) if rng.random() < 0.6 else (int(rng.integers(0, m + 1)), int(rng.integers(0, n + 1)))
+    if p == 0:
+        tm_num, tm_den = O.numden(TM)
+        cf_num, cf_den = O.coeffs(TM, 0, c)
+        lc = 1
+        for d in cf_den:
+            lc = lc * int(d) // math.gcd(lc, int(d))
+        cf_int = np.array([int(a) * (lc // int(d)) for a, d in zip(cf_num, cf_den)], dtype=np.int64)
+        tm_int = np.zeros((n, m), dtype=np.int64)
+        for j in range(m):
+            l = 1
+            for i in range(n):
+                l = l * TM[i][j].denominator // math.gcd(l, TM[i][j].denominator)
+            for i in range(n):
+                tm_int[i, j] = int(TM[i][j] * l)
+        prev_int = np.array([[int(v) for v in row] for row in prev], dtype=np.int64).reshape(nprev, n)
+        lcob_num = np.zeros((n, n), dtype=np.int64); lcob_den = np.ones((n, n), dtype=np.int64)
+        lcob_num[:nprev] = prev_int
+    else:
+        tm_num = np.array([[_residue(v, p) for v in row] for row in TM], dtype=np.int64); tm_den = np.ones_like(tm_num)
+        cf_num, cf_den = O.coeffs(tm_num.tolist(), p, c)
+        cf_int = cf_num.copy(); tm_int = tm_num
+        prev_int = np.array([[int(v) % p for v in row] for row in prev], dtype=np.int64).reshape(nprev, n)
+        lcob_num = np.zeros((n, n), dtype=np.int64); lcob_den = np.ones((n, n), dtype=np.int64)
+        lcob_num[:nprev] = prev_int
+    num = nprev - off
+    if num < 0 or num > 3 or off + num >= n:
+        # the reference only ever searches row `off + num` with exactly the rows before it chosen: re-align the instance
+        nprev = min(off, n - 1); num = 0
+        prev_int = prev_int[:nprev] if nprev <= prev_int.shape[0] else np.vstack([prev_int, np.eye(n, dtype=np.int64)[prev_int.shape[0]:nprev]])
+        lcob_num = np.zeros((n, n), dtype=np.int64); lcob_num[:nprev] = prev_int
+    exp = O.lincomb_search(p, tm_num, tm_den, off, num, cf_num, cf_den, lcob_num, lcob_den, init[0], init[1])
+    got = capi.lincomb_search(p, tm_int, off, cf_int, prev_int if nprev else None, init[0], init[1])
+    assert (got[0], got[1], got[2]) == (exp[0], exp[1], None if exp[2] < 0 else exp[2]), (n, m, p, c, off, nprev, init)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_mmcheck_random_sparse_triples(capi, seed):
+    rng = np.random.default_rng(2000 + seed)
+    p = int(rng.choice([3, 101, 513083, 2147483647, 4294967291]))
+    m, k, n = (int(v) for v in rng.choice([(2, 2, 2), (3, 5, 2), (4, 4, 4), (40, 30, 2), (1, 1, 7), (2, 600, 2)]))
+    r = int(rng.integers(1, 40))
+    few = rng.random() < 0.5  # few distinct values -> grouped format; all distinct -> plain format
+    palette = rng.integers(1, p, 3)
+
+    def rand(rows, cols, dens):
+        M = []
+        for _ in range(rows):
+            row = [0] * cols
+            for j in rng.choice(cols, size=max(1, int(cols * dens)), replace=False):
+                row[int(j)] = int(rng.choice(palette)) if few else int(rng.integers(1, p))
+            M.append(row)
+        return M
+    L, R, P = rand(r, m * k, 0.3), rand(r, k * n, 0.3), rand(m * n, r, 0.5)
+    B = int(rng.choice([1, 31, 32, 33, 70]))
+    ua = rng.integers(0, p, (B, m * k)).astype(np.uint32); ub = rng.integers(0, p, (B, k * n)).astype(np.uint32)
+    fr = lambda M: [[Fraction(v) for v in row] for row in M]
+    v, ok = capi.mmcheck_batch(p, (m, k, n), r, hm.csr_modp(fr(L), p), hm.csr_modp(fr(R), p), hm.csr_modp(fr(P), p), batch=B, ua=ua, ub=ub)
+    exp = [O.mmcheck_modp(p, fr(L), fr(R), fr(P), ua[b].astype(np.int64), ub[b].astype(np.int64)) for b in range(B)]
+    assert ok.tolist() == [1 - e for e in exp] and v == (1 if any(exp) else 0)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_factor_sweep_random_matrices(capi, seed):
+    """Random tall matrices (possibly rank-deficient), every lane-group width (n = 1..32), inner dimensions n..r."""
+    rng = np.random.default_rng(3000 + seed)
+    n = int(rng.choice([1, 2, 3, 4, 5, 8, 9, 13, 16, 17, 24, 32])); r = n + int(rng.integers(1, 12))
+    k = n + int(rng.integers(0, r - n + 1))
+    p = int(rng.choice([3, 101, 2147483647]))
+    dens = [d for d in (1, 1, 2, 4) if d % p]
+    M = [[Fraction(int(rng.choice([0, 0, 1, -1, 2])), int(rng.choice(dens))) for _ in range(n)] for _ in range(r)]
+    if rng.random() < 0.2 and n > 1:
+        for row in M:
+            row[-1] = row[0]  # rank-deficient: no candidate can reach rank n
+    A = np.array([[_residue(v, p) for v in row] for row in M], dtype=np.uint32)
+    best, tab = capi.factor_sweep(p, A, k, 77, 3, 3 + 150, table=True)
+    ref = O.factor_sweep(M, k, 77, 3, 3 + 150, p=p)
+    assert np.array_equal(tab, ref["table"]) and best == ref["best"], (r, n, k, p)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_dependency_random_matrices(capi, seed):
+    rng = np.random.default_rng(4000 + seed)
+    r = int(rng.integers(2, 14)); n = int(rng.choice([1, 2, 3, 4, 7, 16, 17, 33, 64]))
+    q = int(rng.choice([0, 0, 7, 101]))
+    dens = [d for d in (1, 1, 2, 3) if not q or d % q]
+    M = [[Fraction(int(rng.choice([0, 0, 0, 1, -1, 2])), int(rng.choice(dens))) for _ in range(n)] for _ in range(r)]
+    level = int(rng.integers(1, 5)); c = int(rng.integers(1, 6))
+    got = capi.depender(M, level, c, q=q)
+    ref = O.depender(M, level, c, p=q)
+    assert got["coeffs"] == ref["coeffs"] and got["ncand"] == ref["ncand"] and got["hits"] == ref["hits"], (r, n, q, level, c)
