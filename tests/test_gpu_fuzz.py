@@ -128,3 +128,32 @@ def test_dependency_random_matrices(capi, seed):
     got = capi.depender(M, level, c, q=q)
     ref = O.depender(M, level, c, p=q)
     assert got["coeffs"] == ref["coeffs"] and got["ncand"] == ref["ncand"] and got["hits"] == ref["hits"], (r, n, q, level, c)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_orbit_random_triples(capi, seed):
+    """Random (L, R, P) of every compiled shape -- not algorithms, scoring does not care -- small or large entries (packed int32 /
+    plain int32 / 64-bit paths), with denominators, over Q and modulo p: per-candidate tables against the oracle."""
+    rng = np.random.default_rng(5000 + seed)
+    m, k, n = (int(v) for v in rng.choice([(2, 2, 2), (3, 3, 3), (4, 4, 4), (3, 4, 7), (3, 3, 6), (3, 6, 3), (6, 3, 3)]))
+    r = int(rng.integers(1, 9))
+    scale = int(rng.choice([1, 3, 1000, 40000]))  # 1000+: beyond the 16-bit lanes; 40000: beyond the int32 product bound
+    den = int(rng.choice([1, 2, 6]))
+    mat = lambda rows, cols: [[Fraction(int(rng.integers(-2, 3)) * scale, den) for _ in range(cols)] for _ in range(rows)]
+    L, R, P = mat(r, m * k), mat(r, k * n), mat(m * n, r)
+    (Li, dl), (Ri, dr), (Pi, dp) = O.scaled_int(L), O.scaled_int(R), O.scaled_int(P)
+    cnt = 400
+    ref = O.orbit_sweep(L, R, P, 3, 1, 9, 50, 50 + cnt)
+    try:
+        nnz, nno, g2 = capi.orbit_table((m, k, n), Li.astype(np.int32), Ri.astype(np.int32), Pi.astype(np.int32), (dl, dr, dp), 1, 9, 50, 50 + cnt)
+    except capi.PloError as e:
+        assert e.code == capi.E_RANGE and scale == 40000 and (m, k, n) not in ((2, 2, 2), (3, 3, 3), (4, 4, 4))
+        return
+    assert np.array_equal(nnz, ref["nnz"]) and np.array_equal(nno, ref["nno"])
+    assert np.allclose(g2, ref["g2"], rtol=1e-12, atol=0)
+    p = int(rng.choice([3, 101, 2147483647]))
+    if den % p and scale % p:
+        red = lambda M: np.array([[_residue(v, p) for v in row] for row in M], dtype=np.int32)
+        refp = O.orbit_sweep(L, R, P, 0, 1, 9, 50, 50 + cnt, p=p)
+        nz, no = capi.orbit_table_modp(p, (m, k, n), red(L), red(R), red(P), 1, 9, 50, 50 + cnt)
+        assert np.array_equal(nz, refp["nnz"]) and np.array_equal(no, refp["nno"])
