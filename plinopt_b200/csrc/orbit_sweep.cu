@@ -683,6 +683,10 @@ static WideLaunch find_wide(int m, int k, int n) {
   if (m == 2 && k == 2 && n == 2) return &wide_launch<TA, 2, 2, 2>;
   if (m == 3 && k == 3 && n == 3) return &wide_launch<TA, 3, 3, 3>;
   if (m == 4 && k == 4 && n == 4) return &wide_launch<TA, 4, 4, 4>;
+  if (m == 3 && k == 4 && n == 7) return &wide_launch<TA, 3, 4, 7>;
+  if (m == 3 && k == 3 && n == 6) return &wide_launch<TA, 3, 3, 6>;
+  if (m == 3 && k == 6 && n == 3) return &wide_launch<TA, 3, 6, 3>;
+  if (m == 6 && k == 3 && n == 3) return &wide_launch<TA, 6, 3, 3>;
   return nullptr;
 }
 
