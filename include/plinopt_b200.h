@@ -144,7 +144,7 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
                     uint32_t* nno, double* g2);
 
 /* 64-bit inputs: entries and common denominators beyond the int32 C ABI above (2x2x2_7_DPS-intermediate-12.0695 has a common
- * denominator of 1.0e11); |entries| < 2^46; shapes 2x2x2, 3x3x3, 4x4x4; same decode, same deterministic winner; G2 within 1e-12
+ * denominator of 1.0e11); |entries| < 2^46; every compiled shape; same decode, same deterministic winner; G2 within 1e-12
  * relative of growthfactor.cpp:117-125.  Synchronous. */
 int plo_orbit_sweep64(int m, int k, int n, int r, const int64_t* L, const int64_t* R, const int64_t* P, int64_t denL, int64_t denR,
                       int64_t denP, int measure, int mode, uint64_t seed, uint64_t lo, uint64_t hi, plo_orbit_best* best);
