@@ -279,7 +279,7 @@ def main():
                 "bound_note": "the contract's bound classes are hbm|tensor; this kernel is neither: it is bound by the INT32 (fma/alu) pipes, "
                               "so frac is against the live-measured IMAD peak (north_star); the hbm view shows how far it is from the memory roof"}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the contract times the CPU baseline on rank 0 at N = 1 only
             rate, cores, n, _ = cpu_reference_rate(fr, args.cpu_seconds)
             cpu = {"value": rate, "unit": "candidates/s", "cores": cores, "kind": "port", "sample": f"{n} Philox candidates of the same workload (oracle, OpenMP over candidates)"}
         line = {
