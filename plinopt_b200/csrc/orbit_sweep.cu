@@ -25,7 +25,9 @@ namespace plo {
 
 constexpr int kMaxDim = 8;           // nibble-packed permutations
 constexpr int kConstInts = 15360;    // 60 KB of constant memory for L | R | P^T
-__constant__ __align__(16) int c_lrp[kConstInts];  // int32 entries, or int64 entries (two words each) for the 64-bit input path
+__constant__ __align__(16) int c_lrp[kConstInts];
+constexpr int kConst2Ints = 1024;   // pairs of rows packed at 8-bit spacing for the four-lane growth-factor kernel
+__constant__ __align__(16) int c_lrp2[kConst2Ints];  // int32 entries, or int64 entries (two words each) for the 64-bit input path
 
 constexpr int MEASURE_BOTH = 4;  // internal: nnz, nno and G2 (tables, winner re-evaluation)
 
@@ -576,6 +578,99 @@ __global__ void __launch_bounds__(kThreads) orbit_modp_kernel(int r, ModP mp, un
 }
 
 // ---------------------------------------------------------------------------
+// Four-lane growth-factor path for small magnitudes (every transformed entry in [-127, 127]: integer-coefficient algorithms such as
+// Strassen / Winograd / Laderman).  Two rows x0,x1 of the left factor travel at 16-bit spacing (pack_left) AND two Hopcroft-Musinski
+// rows l,l+1 of the input at 8-bit spacing (host-packed c_lrp2), so one IMAD carries four products:
+//   (l0 + 2^16 l1)(a0 + 2^8 a1) = l0a0 + 2^8 l0a1 + 2^16 l1a0 + 2^24 l1a1   ->   lanes (x0,l) (x0,l+1) (x1,l) (x1,l+1).
+// v + 0x80808080 absorbs the borrows bottom-up, ^ 0x80808080 leaves four signed bytes; the squares of the two lanes that belong to
+// row l (bytes 0,2) and to row l+1 (bytes 1,3) are accumulated by one dp4a each.  Same doubles, same summation order as the other
+// paths: bit-identical G2.
+// ---------------------------------------------------------------------------
+template <int RA, int CA, bool TR>
+__device__ __forceinline__ void transform_pair_packed8(const int* __restrict__ A2, const int* LmP, const int* Rm, int& sq0, int& sq1) {
+  int a[RA * CA];
+#pragma unroll
+  for (int e = 0; e < RA * CA; ++e) a[e] = A2[e];
+  int both = 0, even = 0;  // squares of all four lanes / of the lanes of row l (bytes 0 and 2)
+#pragma unroll
+  for (int xp = 0; xp < (RA + 1) / 2; ++xp) {
+    int X[CA];
+#pragma unroll
+    for (int j = 0; j < CA; ++j) {
+      int s = 0;
+#pragma unroll
+      for (int i = 0; i < RA; ++i) s += LmP[xp * RA + i] * a[i * CA + j];
+      X[j] = s;
+    }
+#pragma unroll
+    for (int y = 0; y < CA; ++y) {
+      unsigned w = 0x80808080u;  // the bias rides in the accumulator of the first multiply-add
+#pragma unroll
+      for (int j = 0; j < CA; ++j) w += (unsigned)(X[j] * (TR ? Rm[y * CA + j] : Rm[j * CA + y]));
+      const int x = (int)(w ^ 0x80808080u);
+      const int xe = (int)((w ^ 0x80808080u) & 0x00FF00FFu);  // one LOP3, independent of x
+      both = __dp4a(x, x, both);
+      even = __dp4a(x, xe, even);
+    }
+  }
+  sq0 += even;
+  sq1 += both - even;
+}
+
+template <int M, int K, int N, int MODE, int RU>
+__global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned long long seed, unsigned long long lo, unsigned long long hi, int lutn,
+                                                                 Key* __restrict__ block_best) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  double* lut = reinterpret_cast<double*>(dyn_smem);
+  int* scr0 = reinterpret_cast<int*>(dyn_smem + (size_t)lutn * sizeof(double));
+  __shared__ Key red[32];
+  for (int e = threadIdx.x; e < lutn; e += kThreads) lut[e] = sqrt((double)e);
+  __syncthreads();
+  volatile int* scr = scr0 + threadIdx.x;
+  const int npair = RU > 0 ? (RU + 1) / 2 : (r + 1) / 2;
+  const int* L2 = c_lrp2;
+  const int* R2 = L2 + npair * M * K;
+  const int* P2 = R2 + npair * K * N;
+  const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+  Key best;
+  best.primary = ~0ull; best.index = ~0ull;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
+    Digits<MODE> ds(seed, idx);
+    const Zoi zu = decode_zoi<M, MODE>(ds);
+    const Zoi zv = decode_zoi<K, MODE>(ds);
+    const Zoi zw = decode_zoi<N, MODE>(ds);
+    int U[M * M], Ui[M * M], V[K * K], Vi[K * K], W[N * N], Wi[N * N];
+    expand_zoi<M, false>(zu, U, scr, kThreads);
+    expand_zoi<M, true>(zu, Ui, scr, kThreads);
+    expand_zoi<K, false>(zv, V, scr, kThreads);
+    expand_zoi<K, true>(zv, Vi, scr, kThreads);
+    expand_zoi<N, false>(zw, W, scr, kThreads);
+    expand_zoi<N, true>(zw, Wi, scr, kThreads);
+    int UiTP[((M + 1) / 2) * M], ViP[((K + 1) / 2) * K], UP[((M + 1) / 2) * M];
+    pack_left<M, true>(Ui, UiTP);
+    pack_left<K, false>(Vi, ViP);
+    pack_left<M, false>(U, UP);
+    double g2 = 0.0;
+#pragma unroll(RU > 0 ? (RU + 1) / 2 : 1)
+    for (int q = 0; q < npair; ++q) {
+      int sL0 = 0, sL1 = 0, sR0 = 0, sR1 = 0, sP0 = 0, sP1 = 0;
+      transform_pair_packed8<M, K, false>(L2 + q * M * K, UiTP, V, sL0, sL1);   // U^-T A V
+      transform_pair_packed8<K, N, false>(R2 + q * K * N, ViP, W, sR0, sR1);    // V^-1 B W
+      transform_pair_packed8<M, N, true>(P2 + q * M * N, UP, Wi, sP0, sP1);     // U C W^-T
+      // growthfactor.cpp:117-125, rows in order, no FMA contraction
+      g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(lut[sL0], lut[sR0]), lut[sP0]));
+      if (2 * q + 1 < (RU > 0 ? RU : r)) g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(lut[sL1], lut[sR1]), lut[sP1]));
+    }
+    Key k;
+    k.primary = (unsigned long long)__double_as_longlong(g2);
+    k.index = idx;
+    if (k.primary < best.primary) best = k;
+  }
+  best = block_min(best, red);
+  if (threadIdx.x == 0) block_best[blockIdx.x] = best;
+}
+
+// ---------------------------------------------------------------------------
 // Wide exact path: int32 inputs whose transforms (or squares) would leave 32 bits -- e.g. 2x2x2_7_DPS-integral-12.0662, common
 // denominators ~10^9.  Both stages of the product are accumulated exactly in 64 bits (|.| < 2^31 . 2^8 . 2^8, as in the modular
 // path); sparsity is classified on the exact integers; for the growth factor every entry becomes a double first
@@ -721,7 +816,10 @@ struct ShapeOps {
   void (*table)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
                 unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2);
   int (*blocks_per_sm)(size_t smem);
+  int (*blocks_per_sm8)(size_t smem);
   cudaError_t (*allow_smem)(size_t smem);
+  void (*sweep8)(int mode, int grid, size_t smem, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
+                 unsigned long long hi, int lutn, Key* bb);  // four-lane growth-factor kernel (small magnitudes)
 };
 
 template <int M, int K, int N, int RU>
@@ -752,6 +850,15 @@ struct Shape {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2, RU, false, false>, kThreads, smem);
     return nb > 0 ? nb : 1;
   }
+  static int blocks_per_sm8(size_t smem) {
+    int nb = 0;
+    if (smem > 48 * 1024) {
+      cudaFuncSetAttribute(orbit_sweep8_kernel<M, K, N, 0, RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(orbit_sweep8_kernel<M, K, N, 1, RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep8_kernel<M, K, N, 1, RU>, kThreads, smem);
+    return nb > 0 ? nb : 1;
+  }
   static cudaError_t allow_smem(size_t smem) {
     cudaError_t e = cudaSuccess;
 #define PLO_ALLOW(MODE_, MEAS_, LF_) \
@@ -762,7 +869,12 @@ struct Shape {
 #undef PLO_ALLOW
     return e;
   }
-  static ShapeOps ops() { return ShapeOps{M, K, N, RU, &sweep, &final, &table, &blocks_per_sm, &allow_smem}; }
+  static void sweep8(int mode, int grid, size_t smem, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
+                     unsigned long long hi, int lutn, Key* bb) {
+    if (mode == 0) orbit_sweep8_kernel<M, K, N, 0, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, bb);
+    else orbit_sweep8_kernel<M, K, N, 1, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, bb);
+  }
+  static ShapeOps ops() { return ShapeOps{M, K, N, RU, &sweep, &final, &table, &blocks_per_sm, &blocks_per_sm8, &allow_smem, &sweep8}; }
 };
 
 // (m, k, n, unrolled r); r-specialised entries come first, the generic (ru = 0) entry of a shape last
@@ -780,7 +892,7 @@ static const ShapeOps* find_shape(int m, int k, int n, int r) {
 // Worst-case magnitude bound of the transformed entries (host guard for the
 // int32 arithmetic): |T^-1| entries <= 2^(s-2), row/column abs sums <= 2^(s-1);
 // a {-1,0,1} factor contributes at most its dimension.
-static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, long long* smax, bool* lanes16) {
+static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, long long* smax, bool* lanes16, bool* lanes8 = nullptr) {
   auto maxabs = [](const int32_t* a, size_t cnt) { long long mx = 0; for (size_t i = 0; i < cnt; ++i) { long long v = a[i] < 0 ? -(long long)a[i] : a[i]; if (v > mx) mx = v; } return mx; };
   auto pw = [](int s) { return 1ll << (s > 1 ? s - 1 : 0); };
   const long long bl = maxabs(L, (size_t)r * m * k) * pw(m) * k;  // |U^-T A V| <= max|A| * colsum|U^-1| * colsum|V|
@@ -793,6 +905,7 @@ static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int
   if (bp * bp * m * n > s) s = bp * bp * m * n;
   *smax = s;
   *lanes16 = bl < 32768 && br < 32768 && bp < 32768;  // two-lane packing stays exact
+  if (lanes8) *lanes8 = bl < 128 && br < 128 && bp < 128;  // four-lane packing stays exact
   return true;
 }
 
@@ -821,6 +934,8 @@ struct plo_orbit_plan {
   int grid, lutn;
   bool lutfull, pack;
   size_t smem;
+  bool pack8;           // four-lane growth-factor kernel
+  std::vector<int> h_lrp2;
   WideLaunch wide;      // non-null: 64-bit exact path (inputs beyond the int32 product bound)
   double3 inv_den3;
   uint32_t* d_wide_cnt;  // [2] nnz, nno of the winner
@@ -933,12 +1048,12 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   if ((long long)r * (m * k + k * n + m * n) > kConstInts) { set_error("orbit sweep: L/R/P exceed constant memory"); return PLO_E_SHAPE; }
   if (mode == 0 && plo_orbit_space(m, k, n) == 0) { set_error("orbit sweep: exhaustive space exceeds 64 bits"); return PLO_E_SHAPE; }
   long long smax = 0;
-  bool lanes16 = false;
+  bool lanes16 = false, lanes8 = false;
   WideLaunch wide = nullptr;
-  if (!magnitude_ok(m, k, n, r, L, R, P, &smax, &lanes16)) {
+  if (!magnitude_ok(m, k, n, r, L, R, P, &smax, &lanes16, &lanes8)) {
     wide = find_wide<int>(m, k, n);  // exact in 64 bits for every int32 input of these shapes
     if (!wide) { set_error("orbit sweep: int32 magnitude bound exceeded and no 64-bit kernel for %dx%dx%d", m, k, n); return PLO_E_RANGE; }
-    smax = 0; lanes16 = false;
+    smax = 0; lanes16 = false; lanes8 = false;
   }
   plo_orbit_plan* pl = new plo_orbit_plan();
   pl->wide = wide; pl->d_wide_cnt = nullptr; pl->d_wide_g2 = nullptr;
@@ -959,6 +1074,25 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   pl->lutfull = measure == PLO_MEASURE_G2 && smax + 1 <= 4096;
   pl->pack = lanes16 && getenv("PLO_ORBIT_NOPACK") == nullptr;
   if (wide) { pl->lutn = 0; pl->lutfull = false; pl->pack = false; }
+  // four-lane kernel: growth factor only, every row norm^2 inside the sqrt table, pairs of rows packed at 8-bit spacing
+  const int npair = (r + 1) / 2;
+  pl->pack8 = !wide && measure == PLO_MEASURE_G2 && pl->lutfull && lanes8 && pl->pack && (long long)npair * (m * k + k * n + m * n) <= kConst2Ints &&
+              getenv("PLO_ORBIT_NOPACK8") == nullptr;
+  if (pl->pack8) {
+    pl->h_lrp2.assign((size_t)npair * (m * k + k * n + m * n), 0);
+    const int* src = pl->h_lrp.data();
+    int* d2 = pl->h_lrp2.data();
+    const int widths[3] = {m * k, k * n, m * n};
+    for (int t = 0; t < 3; ++t) {
+      for (int q = 0; q < npair; ++q)
+        for (int e = 0; e < widths[t]; ++e) {
+          const int a0 = src[(size_t)(2 * q) * widths[t] + e];
+          const int a1 = 2 * q + 1 < r ? src[(size_t)(2 * q + 1) * widths[t] + e] : 0;
+          *d2++ = a0 + 256 * a1;
+        }
+      src += (size_t)r * widths[t];
+    }
+  }
   int dmax = m > k ? (m > n ? m : n) : (k > n ? k : n);
   pl->smem = (size_t)pl->lutn * sizeof(double) + (dmax > 2 ? (size_t)dmax * dmax * kThreads * sizeof(int) : 0);
   if (pl->smem > 48 * 1024 && ops->allow_smem(pl->smem) != cudaSuccess) {
@@ -966,7 +1100,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
     delete pl;
     return PLO_E_CUDA;
   }
-  pl->grid = sm_count() * ops->blocks_per_sm(pl->smem);
+  pl->grid = sm_count() * (pl->pack8 ? ops->blocks_per_sm8(pl->smem) : ops->blocks_per_sm(pl->smem));
   pl->d_block_best = nullptr; pl->d_out = nullptr;
   if (pool_alloc(&pl->d_block_best, sizeof(Key) * pl->grid) != cudaSuccess || pool_alloc(&pl->d_out, sizeof(plo_orbit_best)) != cudaSuccess) {
     set_error("orbit sweep: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -985,6 +1119,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
 static int orbit_upload(plo_orbit_plan* pl, cudaStream_t st) {
   if (const_owner() != pl) {
     PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp, pl->h_lrp.data(), pl->h_lrp.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    if (pl->pack8) PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp2, pl->h_lrp2.data(), pl->h_lrp2.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
     const_owner() = pl;
   }
   return PLO_OK;
@@ -1008,7 +1143,8 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
     PLO_CUDA(cudaGetLastError());
     return PLO_OK;
   }
-  pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
+  if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->d_block_best);
+  else pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());
   return PLO_OK;

@@ -199,3 +199,21 @@ def test_int64_inputs_dps_intermediate(capi):
     # host-level driver picks the 64-bit path by itself
     rc = capi.orbiter(L, R, P, measure=capi.MEASURE_G2, mode=capi.MODE_EXHAUSTIVE, seed=0, loops=space)
     assert rc[3]["mm_verdict"] == 0 and not rc[3]["improved"]
+
+
+@pytest.mark.parametrize("stem", ["2x2x2_7_Winograd", "2x2x2_7_Strassen", "3x3x3_23_58", "4x4x4_49_156"])
+def test_four_lane_growth_kernel_is_bit_identical(capi, stem):
+    """Integer-coefficient algorithms take the four-lane (8-bit spacing, dp4a) growth-factor kernel in sweeps; the per-candidate table
+    comes from the plain kernel.  A sweep over a single candidate must return exactly the table's double, for every candidate tried;
+    and block / range splits do not change the winner."""
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints(stem)
+    assert dens == (1, 1, 1)
+    lo, cnt = 1000, 3000
+    _, _, g2 = capi.orbit_table(mkn, Li, Ri, Pi, dens, 1, SEED, lo, lo + cnt)
+    for i in list(range(0, 40)) + [cnt - 1, 1234, 2222]:
+        one = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 3, 1, SEED, lo + i, lo + i + 1)
+        assert one["index"] == lo + i and one["score"] == g2[i], (stem, i)
+    whole = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, 3, 1, SEED, lo, lo + cnt)
+    assert whole["score"] == g2.min() and whole["index"] == lo + int(np.argmin(g2))
+    ref = O.orbit_sweep(L, R, P, 3, 1, SEED, lo, lo + cnt, table=False)["best"]
+    assert (whole["index"], whole["score"]) == (ref[0], ref[3])
