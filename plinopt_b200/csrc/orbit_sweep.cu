@@ -70,6 +70,42 @@ struct Digits {
     R *= radix;
     return (uint32_t)(t >> 32);
   }
+  // All digits of one matrix at once, when the product `count` of its radices is small: successive multiply-high digits of one word
+  // are the mixed-radix digits (first drawn = most significant) of floor(x * count / 2^32); in mode 0 they are those of rem % count
+  // (first drawn = least significant).  RawDigits replays either numbering.
+  __host__ __device__ __forceinline__ uint32_t matrix_index(uint32_t count) {
+    if (MODE == 0) {
+      const uint32_t d = (uint32_t)(rem % count);
+      rem /= count;
+      return d;
+    }
+    new_word();
+#ifdef __CUDA_ARCH__
+    return __umulhi(x, count);
+#else
+    return (uint32_t)(((unsigned long long)x * count) >> 32);
+#endif
+  }
+};
+
+// Digit source that replays matrix number e of `count` (see Digits::matrix_index); no Philox behind it.
+template <int MODE>
+struct RawDigits {
+  unsigned long long rem;
+  uint32_t x;
+  __host__ __device__ __forceinline__ RawDigits(uint32_t e, uint32_t count)
+      : rem(e), x((uint32_t)((((unsigned long long)e << 32) + count - 1) / count)) {}
+  __host__ __device__ __forceinline__ void start_matrix() {}
+  __host__ __device__ __forceinline__ uint32_t digit(uint32_t radix) {
+    if (MODE == 0) {
+      const uint32_t d = (uint32_t)(rem % radix);
+      rem /= radix;
+      return d;
+    }
+    const unsigned long long t = (unsigned long long)x * radix;
+    x = (uint32_t)t;
+    return (uint32_t)(t >> 32);
+  }
 };
 
 // Compact form of one zoi matrix  M[P[i]][Q[j]] = T[i][j]  (src/orbiter.cpp:125-136):
@@ -87,8 +123,8 @@ __host__ __device__ __forceinline__ uint32_t nibble_swap(uint32_t perm, int i, u
   return perm ^ (xr << sh) ^ (xr << sh2);
 }
 
-template <int S, int MODE>
-__host__ __device__ __forceinline__ Zoi decode_zoi(Digits<MODE>& ds) {
+template <int S, int MODE, class DS = Digits<MODE>>
+__host__ __device__ __forceinline__ Zoi decode_zoi(DS& ds) {
   Zoi z;
   ds.start_matrix();
   z.pP = 0x76543210u;
@@ -254,6 +290,42 @@ __device__ __forceinline__ void pack_left(const int* Lm, int* LmP) {
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// 2x2 zoi matrices: the group has 2.2.2.2.3 = 48 elements, so decode + expansion + inverse + lane packing become one table in
+// shared memory, built by each block with the generic code above (same digits -> same matrices) and indexed by
+// Digits::matrix_index(48).  Entry layout (kZ2Stride = 20 words = 80 B: eight consecutive entries start in eight different
+// 16-byte bank groups):  M (4) | M^-1 (4) | pack_left<T>(M^-1) (2) | pack_left(M) (2) | pack_left(M^-1) (2).
+// ---------------------------------------------------------------------------
+constexpr int kZ2Count = 48, kZ2Stride = 20;
+#ifdef __CUDACC__
+template <int MODE>
+__device__ __forceinline__ void build_zoi2_table(int* tab) {
+  for (int e = threadIdx.x; e < kZ2Count; e += blockDim.x) {
+    RawDigits<MODE> ds((uint32_t)e, (uint32_t)kZ2Count);
+    const Zoi z = decode_zoi<2, MODE, RawDigits<MODE>>(ds);
+    int Mx[4], Mi[4], pit[2], pm[2], pi[2];
+    expand_zoi<2, false>(z, Mx, nullptr, 0);
+    expand_zoi<2, true>(z, Mi, nullptr, 0);
+    pack_left<2, true>(Mi, pit);
+    pack_left<2, false>(Mx, pm);
+    pack_left<2, false>(Mi, pi);
+    int* t = tab + e * kZ2Stride;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { t[q] = Mx[q]; t[4 + q] = Mi[q]; }
+    t[8] = pit[0]; t[9] = pit[1]; t[10] = pm[0]; t[11] = pm[1]; t[12] = pi[0]; t[13] = pi[1];
+  }
+}
+__device__ __forceinline__ void z2_load4(const int* t, int* out) {
+  const int4 v = *reinterpret_cast<const int4*>(t);
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+__device__ __forceinline__ void z2_load2(const int* t, int* out) {
+  const int2 v = *reinterpret_cast<const int2*>(t);
+  out[0] = v.x; out[1] = v.y;
+}
+#endif
+
 template <int RA, int CA, bool TR, int MEASURE>
 __device__ __forceinline__ void transform_row_packed(const int* __restrict__ A, const int* LmP, const int* Rm, int den, Acc& acc) {
   int a[RA * CA];
@@ -316,33 +388,50 @@ __host__ __device__ __forceinline__ double isqrt_lut(int s, const double* lut, i
 #endif
 }
 
-template <int M, int K, int N, int MODE, int MEASURE, int RU = 0, bool LF = false, bool PACK = false>
+template <int M, int K, int N, int MODE, int MEASURE, int RU = 0, bool LF = false, bool PACK = false, bool TAB = false>
 __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict__ lrp, int r, int3 den, unsigned long long seed,
                                                           unsigned long long index, volatile int* scr, int stride,
-                                                          const double* lut = nullptr, int lutn = 0) {
+                                                          const double* lut = nullptr, int lutn = 0, const int* z2tab = nullptr) {
+  static_assert(!TAB || (PACK && M == 2 && K == 2 && N == 2), "table path: packed 2x2x2 only");
   Digits<MODE> ds(seed, index);
-  const Zoi zu = decode_zoi<M, MODE>(ds);
-  const Zoi zv = decode_zoi<K, MODE>(ds);
-  const Zoi zw = decode_zoi<N, MODE>(ds);
   int U[M * M], Ui[M * M], V[K * K], Vi[K * K], W[N * N], Wi[N * N];
-  expand_zoi<M, false>(zu, U, scr, stride);
-  expand_zoi<M, true>(zu, Ui, scr, stride);
-  expand_zoi<K, false>(zv, V, scr, stride);
-  expand_zoi<K, true>(zv, Vi, scr, stride);
-  expand_zoi<N, false>(zw, W, scr, stride);
-  expand_zoi<N, true>(zw, Wi, scr, stride);
+#ifdef __CUDA_ARCH__
+  int UiTP[((M + 1) / 2) * M], ViP[((K + 1) / 2) * K], UP[((M + 1) / 2) * M];
+  if (TAB) {  // 2x2x2 with lane packing: everything the transforms need comes out of the 48-entry table
+    const int* tu = z2tab + ds.matrix_index(kZ2Count) * kZ2Stride;
+    const int* tv = z2tab + ds.matrix_index(kZ2Count) * kZ2Stride;
+    const int* tw = z2tab + ds.matrix_index(kZ2Count) * kZ2Stride;
+    int both[4];
+    z2_load4(tu + 8, both);
+    UiTP[0] = both[0]; UiTP[1] = both[1]; UP[0] = both[2]; UP[1] = both[3];
+    z2_load4(tv, V);
+    z2_load2(tv + 12, ViP);
+    z2_load4(tw, W);
+    z2_load4(tw + 4, Wi);
+  } else
+#endif
+  {
+    const Zoi zu = decode_zoi<M, MODE>(ds);
+    const Zoi zv = decode_zoi<K, MODE>(ds);
+    const Zoi zw = decode_zoi<N, MODE>(ds);
+    expand_zoi<M, false>(zu, U, scr, stride);
+    expand_zoi<M, true>(zu, Ui, scr, stride);
+    expand_zoi<K, false>(zv, V, scr, stride);
+    expand_zoi<K, true>(zv, Vi, scr, stride);
+    expand_zoi<N, false>(zw, W, scr, stride);
+    expand_zoi<N, true>(zw, Wi, scr, stride);
+#ifdef __CUDA_ARCH__
+    if (PACK) {
+      pack_left<M, true>(Ui, UiTP);
+      pack_left<K, false>(Vi, ViP);
+      pack_left<M, false>(U, UP);
+    }
+#endif
+  }
 
   const int* Lc = lrp;
   const int* Rc = lrp + r * M * K;
   const int* Pc = Rc + r * K * N;
-#ifdef __CUDA_ARCH__
-  int UiTP[((M + 1) / 2) * M], ViP[((K + 1) / 2) * K], UP[((M + 1) / 2) * M];
-  if (PACK) {
-    pack_left<M, true>(Ui, UiTP);
-    pack_left<K, false>(Vi, ViP);
-    pack_left<M, false>(U, UP);
-  }
-#endif
   Score sc;
   sc.nnz = 0; sc.nno = 0; sc.g2 = 0.0;
   int nnz = 0, nno = 0;
@@ -420,15 +509,18 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, int3 den, 
   double* lut = reinterpret_cast<double*>(dyn_smem);
   int* scr = reinterpret_cast<int*>(dyn_smem + (size_t)lutn * sizeof(double));
   __shared__ Key red[32];
+  constexpr bool TAB = PACK && M == 2 && K == 2 && N == 2;
+  __shared__ __align__(16) int z2tab[TAB ? kZ2Count * kZ2Stride : 4];
+  if (TAB) build_zoi2_table<MODE>(z2tab);
   if (MEASURE == PLO_MEASURE_G2) {
     for (int e = threadIdx.x; e < lutn; e += kThreads) lut[e] = sqrt((double)e);
-    __syncthreads();
   }
+  __syncthreads();
   const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
-    const Score s = score_candidate<M, K, N, MODE, MEASURE, RU, LF, PACK>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads, lut, lutn);
+    const Score s = score_candidate<M, K, N, MODE, MEASURE, RU, LF, PACK, TAB>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads, lut, lutn, z2tab);
     const Key k = make_key<MEASURE>(s, idx);
     if (k.primary < best.primary) best = k;  // indices visited in increasing order: strict '<' keeps the first
   }
@@ -591,7 +683,6 @@ __device__ __forceinline__ void transform_pair_packed8(const int* __restrict__ A
   int a[RA * CA];
 #pragma unroll
   for (int e = 0; e < RA * CA; ++e) a[e] = A2[e];
-  int both = 0, even = 0;  // squares of all four lanes / of the lanes of row l (bytes 0 and 2)
 #pragma unroll
   for (int xp = 0; xp < (RA + 1) / 2; ++xp) {
     int X[CA];
@@ -604,17 +695,14 @@ __device__ __forceinline__ void transform_pair_packed8(const int* __restrict__ A
     }
 #pragma unroll
     for (int y = 0; y < CA; ++y) {
-      unsigned w = 0x80808080u;  // the bias rides in the accumulator of the first multiply-add
+      int v = 0;
 #pragma unroll
-      for (int j = 0; j < CA; ++j) w += (unsigned)(X[j] * (TR ? Rm[y * CA + j] : Rm[j * CA + y]));
-      const int x = (int)(w ^ 0x80808080u);
-      const int xe = (int)((w ^ 0x80808080u) & 0x00FF00FFu);  // one LOP3, independent of x
-      both = __dp4a(x, x, both);
-      even = __dp4a(x, xe, even);
+      for (int j = 0; j < CA; ++j) v += X[j] * (TR ? Rm[y * CA + j] : Rm[j * CA + y]);
+      const unsigned x = ((unsigned)v + 0x80808080u) ^ 0x80808080u;  // ptxas folds the bias into the first multiply-add
+      sq0 = __dp4a((int)x, (int)(x & 0x00FF00FFu), sq0);
+      sq1 = __dp4a((int)x, (int)(x & 0xFF00FF00u), sq1);
     }
   }
-  sq0 += even;
-  sq1 += both - even;
 }
 
 template <int M, int K, int N, int MODE, int RU>
@@ -624,6 +712,9 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned 
   double* lut = reinterpret_cast<double*>(dyn_smem);
   int* scr0 = reinterpret_cast<int*>(dyn_smem + (size_t)lutn * sizeof(double));
   __shared__ Key red[32];
+  constexpr bool TAB = M == 2 && K == 2 && N == 2;
+  __shared__ __align__(16) int z2tab[TAB ? kZ2Count * kZ2Stride : 4];
+  if (TAB) build_zoi2_table<MODE>(z2tab);
   for (int e = threadIdx.x; e < lutn; e += kThreads) lut[e] = sqrt((double)e);
   __syncthreads();
   volatile int* scr = scr0 + threadIdx.x;
@@ -636,20 +727,34 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned 
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
     Digits<MODE> ds(seed, idx);
-    const Zoi zu = decode_zoi<M, MODE>(ds);
-    const Zoi zv = decode_zoi<K, MODE>(ds);
-    const Zoi zw = decode_zoi<N, MODE>(ds);
-    int U[M * M], Ui[M * M], V[K * K], Vi[K * K], W[N * N], Wi[N * N];
-    expand_zoi<M, false>(zu, U, scr, kThreads);
-    expand_zoi<M, true>(zu, Ui, scr, kThreads);
-    expand_zoi<K, false>(zv, V, scr, kThreads);
-    expand_zoi<K, true>(zv, Vi, scr, kThreads);
-    expand_zoi<N, false>(zw, W, scr, kThreads);
-    expand_zoi<N, true>(zw, Wi, scr, kThreads);
+    int V[K * K], W[N * N], Wi[N * N];
     int UiTP[((M + 1) / 2) * M], ViP[((K + 1) / 2) * K], UP[((M + 1) / 2) * M];
-    pack_left<M, true>(Ui, UiTP);
-    pack_left<K, false>(Vi, ViP);
-    pack_left<M, false>(U, UP);
+    if (TAB) {
+      const int* tu = z2tab + ds.matrix_index(kZ2Count) * kZ2Stride;
+      const int* tv = z2tab + ds.matrix_index(kZ2Count) * kZ2Stride;
+      const int* tw = z2tab + ds.matrix_index(kZ2Count) * kZ2Stride;
+      int both[4];
+      z2_load4(tu + 8, both);
+      UiTP[0] = both[0]; UiTP[1] = both[1]; UP[0] = both[2]; UP[1] = both[3];
+      z2_load4(tv, V);
+      z2_load2(tv + 12, ViP);
+      z2_load4(tw, W);
+      z2_load4(tw + 4, Wi);
+    } else {
+      const Zoi zu = decode_zoi<M, MODE>(ds);
+      const Zoi zv = decode_zoi<K, MODE>(ds);
+      const Zoi zw = decode_zoi<N, MODE>(ds);
+      int U[M * M], Ui[M * M], Vi[K * K];
+      expand_zoi<M, false>(zu, U, scr, kThreads);
+      expand_zoi<M, true>(zu, Ui, scr, kThreads);
+      expand_zoi<K, false>(zv, V, scr, kThreads);
+      expand_zoi<K, true>(zv, Vi, scr, kThreads);
+      expand_zoi<N, false>(zw, W, scr, kThreads);
+      expand_zoi<N, true>(zw, Wi, scr, kThreads);
+      pack_left<M, true>(Ui, UiTP);
+      pack_left<K, false>(Vi, ViP);
+      pack_left<M, false>(U, UP);
+    }
     double g2 = 0.0;
 #pragma unroll(RU > 0 ? (RU + 1) / 2 : 1)
     for (int q = 0; q < npair; ++q) {
