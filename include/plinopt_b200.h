@@ -257,6 +257,9 @@ int plo_dependency_explore(uint32_t p, int r, int n, int c, int level, const int
  * timed, best of `reps`.  Results in operations per second.
  * ------------------------------------------------------------------------ */
 int plo_measure_peaks(int reps, double* imad_per_s, double* dfma_per_s, double* ialu_per_s);
+/* Scheduler issue peak: IMAD (fma-heavy pipe) and LOP3 (alu pipe) chains interleaved one to one; thread instructions per
+ * second (= SMs x 4 schedulers x 32 lanes x clock when both pipes are kept full). */
+int plo_measure_issue_peak(int reps, double* inst_per_s);
 
 /* ---------------------------------------------------------------------------
  * Host-level entry points (C++ host orchestration around the kernels above;

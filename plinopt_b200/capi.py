@@ -28,7 +28,7 @@ SYMBOLS = [
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
     "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
-    "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks",
+    "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
     "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
     "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
     "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender", "plo_negater", "plo_rotater", "plo_growth_factors",
@@ -368,7 +368,11 @@ def measure_peaks(reps=10):
     f = lib().plo_measure_peaks
     f.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3
     _check(f(reps, C.byref(a), C.byref(b), C.byref(c)))
-    return dict(imad_per_s=a.value, dfma_per_s=b.value, ialu_pairs_per_s=c.value)
+    d = C.c_double()
+    g = lib().plo_measure_issue_peak
+    g.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    _check(g(reps, C.byref(d)))
+    return dict(imad_per_s=a.value, dfma_per_s=b.value, ialu_pairs_per_s=c.value, issue_inst_per_s=d.value)
 
 
 # --------------------------------------------------------------------------

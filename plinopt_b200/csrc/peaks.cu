@@ -69,6 +69,28 @@ __global__ void __launch_bounds__(kPeakThreads) peak_ialu_kernel(int* out, unsig
   if (s == 0x7fffffffu) out[0] = (int)s;
 }
 
+// Issue-rate peak: independent IMAD (fma-heavy pipe) and LOP3 (alu pipe) chains interleaved one to one; each pipe takes a warp
+// instruction every other cycle, so together they fill the scheduler's one instruction per cycle.
+__global__ void __launch_bounds__(kPeakThreads) peak_issue_kernel(int* out, int a, int b) {
+  int x[kPeakIlp];
+  unsigned int y[kPeakIlp];
+#pragma unroll
+  for (int i = 0; i < kPeakIlp; ++i) { x[i] = threadIdx.x + i; y[i] = threadIdx.x * 3u + i; }
+  for (int it = 0; it < kPeakIters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < kPeakIlp; ++i) {
+        x[i] = x[i] * a + b;                             // IMAD
+        y[i] = (y[i] & (unsigned)a) ^ (unsigned)(b + u);  // LOP3
+      }
+  }
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kPeakIlp; ++i) s += x[i] + (int)y[i];
+  if (s == 0x7fffffff) out[0] = s;
+}
+
 // One block per triple, one thread per row i; s = sum_i |L_i| |R_i| |Pt_i| (row order kept: serial final sum)
 __global__ void growth_g2_kernel(int r, int a, int b, int c, const double* __restrict__ L, const double* __restrict__ R,
                                  const double* __restrict__ P, double* __restrict__ out) {
@@ -132,6 +154,36 @@ int plo_measure_peaks(int reps, double* imad_per_s, double* dfma_per_s, double* 
   if (imad_per_s) *imad_per_s = best[0];
   if (dfma_per_s) *dfma_per_s = best[1];
   if (ialu_per_s) *ialu_per_s = best[2];  // compare+increment PAIRS per second
+  return PLO_OK;
+}
+
+int plo_measure_issue_peak(int reps, double* inst_per_s) {
+  int rc = check_device();
+  if (rc) return rc;
+  if (!inst_per_s) { set_error("plo_measure_issue_peak: null output"); return PLO_E_ARG; }
+  if (reps < 1) reps = 1;
+  const int grid = sm_count() * 8;
+  int* d_i = nullptr;
+  PLO_CUDA(cudaMalloc(&d_i, 64));
+  cudaEvent_t e0, e1;
+  PLO_CUDA(cudaEventCreate(&e0));
+  PLO_CUDA(cudaEventCreate(&e1));
+  const double inst = (double)grid * kPeakThreads * (double)kPeakIters * 4.0 * kPeakIlp * 2.0;  // thread instructions
+  double best = 0;
+  for (int rep = 0; rep < reps + 1; ++rep) {  // first repetition is the warm-up
+    cudaEventRecord(e0);
+    peak_issue_kernel<<<grid, kPeakThreads>>>(d_i, 0x7ffffff3, 1);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { set_error("peak kernel: %s", cudaGetErrorString(e)); cudaFree(d_i); return PLO_E_CUDA; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double rate = inst / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_i);
+  *inst_per_s = best;
   return PLO_OK;
 }
 
