@@ -163,6 +163,13 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
 int plo_orbit_plan_run(plo_orbit_plan* plan, uint64_t lo, uint64_t hi, void* stream);
 int plo_orbit_plan_result(plo_orbit_plan* plan, void* stream, plo_orbit_best* best);
 int plo_orbit_plan_launches(const plo_orbit_plan* plan);
+/* Survivor compaction (north_star: "surviving candidates are compacted through coalesced vectorised stores"): every candidate of
+ * [lo,hi) whose score does not exceed `threshold` -- sparsity plans: (nnz, nno) <= (threshold->nnz, threshold->nno)
+ * lexicographically (the order of src/orbiter.cpp:300-312); growth-factor plans: G2 <= threshold->score -- is returned with BOTH
+ * measures (nnz, nno, score = growth factor), sorted by index.  Synchronous.  *count = survivors found; if that exceeds `capacity`
+ * nothing is written and PLO_E_RANGE is returned (call again with room for *count records or a tighter threshold). */
+int plo_orbit_plan_survivors(plo_orbit_plan* plan, uint64_t lo, uint64_t hi, const plo_orbit_best* threshold, uint64_t capacity,
+                             plo_orbit_best* out, uint64_t* count);
 void plo_orbit_plan_destroy(plo_orbit_plan* plan);
 
 /* ---------------------------------------------------------------------------

@@ -26,7 +26,7 @@ SYMBOLS = [
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
-    "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_destroy",
+    "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_survivors", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
     "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
@@ -281,6 +281,23 @@ class OrbitPlan:
         best = OrbitBest()
         _check(lib().plo_orbit_plan_result(self._h, C.c_void_p(stream), C.byref(best)))
         return _best_tuple(best)
+
+    def survivors(self, lo, hi, nnz=0, nno=0, score=0.0, capacity=1 << 16):
+        """Candidates of [lo,hi) not worse than the threshold (sparsity plans: (nnz, nno); growth-factor plans: score), sorted by
+        index: list of dicts with index, nnz, nno, score (= growth factor).  Grows the buffer once if `capacity` was too small."""
+        f = lib().plo_orbit_plan_survivors
+        f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(OrbitBest), C.c_uint64, C.POINTER(OrbitBest), C.POINTER(C.c_uint64)]
+        thr = OrbitBest(score=score, nnz=nnz, nno=nno, index=0)
+        cnt = C.c_uint64(0)
+        for _ in range(2):
+            buf = (OrbitBest * max(1, capacity))()
+            rc = f(self._h, lo, hi, C.byref(thr), capacity, buf, C.byref(cnt))
+            if rc == E_RANGE and cnt.value > capacity:
+                capacity = cnt.value
+                continue
+            _check(rc)
+            return [_best_tuple(buf[i]) for i in range(cnt.value)]
+        _check(rc)
 
     def close(self):
         if self._h:

@@ -17,6 +17,7 @@
 #include <type_traits>
 
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "plo_device.cuh"
@@ -555,18 +556,57 @@ __global__ void __launch_bounds__(kThreads) orbit_final_kernel(int r, int3 den, 
   }
 }
 
+// Survivor compaction: every candidate whose score does not exceed a threshold is appended to a device buffer.  The survivors of a
+// warp take consecutive 32-byte records (one atomicAdd per warp, two 16-byte stores per survivor): coalesced, vectorised, in no
+// particular order -- the host sorts by index.  `count` keeps counting past `cap` so that the caller learns the size it needs.
+struct Sink {
+  uint4* rec;                 // {index lo, index hi, nnz, nno} {score bits lo, score bits hi, 0, 0}
+  unsigned long long* count;
+  unsigned long long cap;
+  unsigned long long thr_key;  // sparsity: (nnz << 32) | nno
+  double thr_score;            // growth factor
+  int measure;
+};
+__device__ __forceinline__ void sink_emit(const Sink& sk, bool valid, unsigned long long idx, uint32_t nnz, uint32_t nno, double score) {
+  // called by all 32 lanes of a warp (warp-uniform loops below)
+  const bool pass = valid && (sk.measure == PLO_MEASURE_G2 ? score <= sk.thr_score : ((((unsigned long long)nnz) << 32) | nno) <= sk.thr_key);
+  const unsigned mask = __ballot_sync(0xffffffffu, pass);
+  if (mask == 0u) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == __ffs(mask) - 1) base = atomicAdd(sk.count, (unsigned long long)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+  if (pass) {
+    const unsigned long long pos = base + __popc(mask & ((1u << lane) - 1u));
+    if (pos < sk.cap) {
+      const unsigned long long sb = (unsigned long long)__double_as_longlong(score);
+      sk.rec[2 * pos] = make_uint4((unsigned)idx, (unsigned)(idx >> 32), nnz, nno);
+      sk.rec[2 * pos + 1] = make_uint4((unsigned)sb, (unsigned)(sb >> 32), 0u, 0u);
+    }
+  }
+}
+
+// Per-candidate table and/or survivor compaction (both measures of every candidate; warp-uniform loop: whole warps step together).
 template <int M, int K, int N, int MODE>
 __global__ void __launch_bounds__(kThreads) orbit_table_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo,
                                                                 unsigned long long hi, double inv_den,
                                                                 uint32_t* __restrict__ nnz, uint32_t* __restrict__ nno,
-                                                                double* __restrict__ g2) {
+                                                                double* __restrict__ g2, Sink sink) {
   __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
   const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
-  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
-    const Score s = score_candidate<M, K, N, MODE, MEASURE_BOTH>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads);
-    if (nnz) nnz[idx - lo] = s.nnz;
-    if (nno) nno[idx - lo] = s.nno;
-    if (g2) g2[idx - lo] = s.g2 * inv_den;
+  const int lane = threadIdx.x & 31;
+  for (unsigned long long wb = lo + (unsigned long long)blockIdx.x * kThreads + (threadIdx.x - lane); wb < hi; wb += stride) {
+    const unsigned long long idx = wb + lane;
+    const bool valid = idx < hi;
+    Score s;
+    s.nnz = 0; s.nno = 0; s.g2 = 0.0;
+    if (valid) {
+      s = score_candidate<M, K, N, MODE, MEASURE_BOTH>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads);
+      if (nnz) nnz[idx - lo] = s.nnz;
+      if (nno) nno[idx - lo] = s.nno;
+      if (g2) g2[idx - lo] = s.g2 * inv_den;
+    }
+    if (sink.rec) sink_emit(sink, valid, idx, s.nnz, s.nno, s.g2 * inv_den);
   }
 }
 
@@ -851,32 +891,45 @@ __host__ __device__ __forceinline__ Score score_candidate_wide(const TA* __restr
 template <typename TA, int M, int K, int N, int MODE>
 __global__ void __launch_bounds__(kThreads) orbit_wide_kernel(int r, Den3 den, double3 inv_den, int measure, unsigned long long seed, unsigned long long lo,
                                                                unsigned long long hi, Key* __restrict__ block_best, uint32_t* __restrict__ tnnz,
-                                                               uint32_t* __restrict__ tnno, double* __restrict__ tg2) {
+                                                               uint32_t* __restrict__ tnno, double* __restrict__ tg2, Sink sink) {
   __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
   __shared__ Key red[32];
   const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+  const int lane = threadIdx.x & 31;
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
-  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
-    const Score s = score_candidate_wide<TA, M, K, N, MODE>(reinterpret_cast<const TA*>(c_lrp), r, den, inv_den, seed, idx, scr + threadIdx.x, kThreads);
-    if (tnnz) tnnz[idx - lo] = s.nnz;
-    if (tnno) tnno[idx - lo] = s.nno;
-    if (tg2) tg2[idx - lo] = s.g2;
-    Key k;
-    k.primary = measure == PLO_MEASURE_G2 ? (unsigned long long)__double_as_longlong(s.g2) : (((unsigned long long)s.nnz << 32) | s.nno);
-    k.index = idx;
-    if (k.primary < best.primary) best = k;
+  for (unsigned long long wb = lo + (unsigned long long)blockIdx.x * kThreads + (threadIdx.x - lane); wb < hi; wb += stride) {
+    const unsigned long long idx = wb + lane;
+    const bool valid = idx < hi;
+    Score s;
+    s.nnz = 0; s.nno = 0; s.g2 = 0.0;
+    if (valid) {
+      s = score_candidate_wide<TA, M, K, N, MODE>(reinterpret_cast<const TA*>(c_lrp), r, den, inv_den, seed, idx, scr + threadIdx.x, kThreads);
+      if (tnnz) tnnz[idx - lo] = s.nnz;
+      if (tnno) tnno[idx - lo] = s.nno;
+      if (tg2) tg2[idx - lo] = s.g2;
+      Key k;
+      k.primary = measure == PLO_MEASURE_G2 ? (unsigned long long)__double_as_longlong(s.g2) : (((unsigned long long)s.nnz << 32) | s.nno);
+      k.index = idx;
+      if (k.primary < best.primary) best = k;
+    }
+    if (sink.rec) sink_emit(sink, valid, idx, s.nnz, s.nno, s.g2);
   }
   best = block_min(best, red);
   if (threadIdx.x == 0 && block_best) block_best[blockIdx.x] = best;
 }
+static Sink no_sink() {
+  Sink sk;
+  sk.rec = nullptr; sk.count = nullptr; sk.cap = 0; sk.thr_key = 0; sk.thr_score = 0.0; sk.measure = PLO_MEASURE_NNZ;
+  return sk;
+}
 typedef void (*WideLaunch)(int mode, int grid, cudaStream_t st, int r, Den3 den, double3 inv_den, int measure, unsigned long long seed,
-                           unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno, double* tg2);
+                           unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno, double* tg2, Sink sink);
 template <typename TA, int M, int K, int N>
 static void wide_launch(int mode, int grid, cudaStream_t st, int r, Den3 den, double3 inv_den, int measure, unsigned long long seed,
-                        unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno, double* tg2) {
-  if (mode == 0) orbit_wide_kernel<TA, M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2);
-  else orbit_wide_kernel<TA, M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2);
+                        unsigned long long lo, unsigned long long hi, Key* bb, uint32_t* tnnz, uint32_t* tnno, double* tg2, Sink sink) {
+  if (mode == 0) orbit_wide_kernel<TA, M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2, sink);
+  else orbit_wide_kernel<TA, M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, inv_den, measure, seed, lo, hi, bb, tnnz, tnno, tg2, sink);
 }
 template <typename TA>
 static WideLaunch find_wide(int m, int k, int n) {
@@ -919,7 +972,7 @@ struct ShapeOps {
   void (*final)(int mode, cudaStream_t st, int r, int3 den, unsigned long long seed, int nblocks, int measure, double inv_den,
                 const Key* bb, plo_orbit_best* out);
   void (*table)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
-                unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2);
+                unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2, Sink sink);
   int (*blocks_per_sm)(size_t smem);
   int (*blocks_per_sm8)(size_t smem);
   cudaError_t (*allow_smem)(size_t smem);
@@ -946,9 +999,9 @@ struct Shape {
     else orbit_final_kernel<M, K, N, 1><<<1, kThreads, 0, st>>>(r, den, seed, nblocks, measure, inv_den, bb, out);
   }
   static void table(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
-                    unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2) {
-    if (mode == 0) orbit_table_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2);
-    else orbit_table_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2);
+                    unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2, Sink sink) {
+    if (mode == 0) orbit_table_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2, sink);
+    else orbit_table_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2, sink);
   }
   static int blocks_per_sm(size_t smem) {
     int nb = 0;
@@ -1243,7 +1296,7 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
     if (hi > lo) {
       const unsigned long long blocks = (hi - lo + kThreads - 1) / kThreads;
       pl->wide(pl->mode, (int)std::min<unsigned long long>(blocks, (unsigned long long)pl->grid), st, pl->r, Den3{pl->den.x, pl->den.y, pl->den.z}, pl->inv_den3, pl->measure, pl->seed, lo, hi,
-               pl->d_block_best, nullptr, nullptr, nullptr);
+               pl->d_block_best, nullptr, nullptr, nullptr, no_sink());
     }
     PLO_CUDA(cudaGetLastError());
     return PLO_OK;
@@ -1270,7 +1323,7 @@ int plo_orbit_plan_result(plo_orbit_plan* pl, void* stream, plo_orbit_best* best
     if (b.index == ~0ull) return PLO_OK;
     int rc = orbit_upload(pl, st);
     if (rc) return rc;
-    pl->wide(pl->mode, 1, st, pl->r, Den3{pl->den.x, pl->den.y, pl->den.z}, pl->inv_den3, pl->measure, pl->seed, b.index, b.index + 1, nullptr, pl->d_wide_cnt, pl->d_wide_cnt + 1, pl->d_wide_g2);
+    pl->wide(pl->mode, 1, st, pl->r, Den3{pl->den.x, pl->den.y, pl->den.z}, pl->inv_den3, pl->measure, pl->seed, b.index, b.index + 1, nullptr, pl->d_wide_cnt, pl->d_wide_cnt + 1, pl->d_wide_g2, no_sink());
     uint32_t cnt[2];
     double g2 = 0.0;
     PLO_CUDA(cudaMemcpyAsync(cnt, pl->d_wide_cnt, 8, cudaMemcpyDeviceToHost, st));
@@ -1374,8 +1427,8 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
     if (!rc) {
       size_t blocks = (cnt + kThreads - 1) / kThreads;
       int grid = (int)(blocks < (size_t)pl->grid ? blocks : (size_t)pl->grid);
-      if (pl->wide) pl->wide(mode, grid, nullptr, r, Den3{pl->den.x, pl->den.y, pl->den.z}, pl->inv_den3, PLO_MEASURE_G2, seed, lo, hi, nullptr, d_nnz, d_nno, d_g2);
-      else pl->ops->table(mode, grid, nullptr, r, pl->den, seed, lo, hi, pl->inv_den, d_nnz, d_nno, d_g2);
+      if (pl->wide) pl->wide(mode, grid, nullptr, r, Den3{pl->den.x, pl->den.y, pl->den.z}, pl->inv_den3, PLO_MEASURE_G2, seed, lo, hi, nullptr, d_nnz, d_nno, d_g2, no_sink());
+      else pl->ops->table(mode, grid, nullptr, r, pl->den, seed, lo, hi, pl->inv_den, d_nnz, d_nno, d_g2, no_sink());
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { set_error("plo_orbit_table: %s", cudaGetErrorString(e)); rc = PLO_E_CUDA; }
     }
@@ -1387,6 +1440,65 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
   }
   cleanup();
   return rc;
+}
+
+// Survivors of [lo,hi): every candidate whose score does not exceed `threshold` (sparsity plans: (nnz, nno) <= (threshold.nnz,
+// threshold.nno) lexicographically; growth-factor plans: score <= threshold.score), with both measures, sorted by index.
+// Synchronous.  *count = number found; more than `capacity` -> PLO_E_RANGE (nothing is written; retry with *count records).
+int plo_orbit_plan_survivors(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, const plo_orbit_best* threshold, uint64_t capacity,
+                             plo_orbit_best* out, uint64_t* count) {
+  if (!pl || !threshold || !count || hi < lo || (capacity && !out)) { set_error("plo_orbit_plan_survivors: bad argument"); return PLO_E_ARG; }
+  *count = 0;
+  if (hi == lo) return PLO_OK;
+  int rc = orbit_upload(pl, nullptr);
+  if (rc) return rc;
+  const uint64_t cap = capacity ? capacity : 1;
+  uint4* d_rec = nullptr;
+  unsigned long long* d_cnt = nullptr;
+  auto cleanup = [&]() { pool_free(d_rec); pool_free(d_cnt); };
+  if (pool_alloc(&d_rec, cap * 32) != cudaSuccess || pool_alloc(&d_cnt, 8) != cudaSuccess) {
+    set_error("plo_orbit_plan_survivors: device allocation of %llu records failed", (unsigned long long)cap);
+    cleanup();
+    return PLO_E_CUDA;
+  }
+  cudaError_t e = cudaMemset(d_cnt, 0, 8);
+  Sink sk;
+  sk.rec = d_rec; sk.count = d_cnt; sk.cap = capacity;
+  sk.thr_key = ((unsigned long long)threshold->nnz << 32) | threshold->nno;
+  sk.thr_score = threshold->score;
+  sk.measure = pl->measure;
+  const uint64_t blocks = (hi - lo + kThreads - 1) / kThreads;
+  const int grid = (int)std::min<uint64_t>(blocks, (uint64_t)pl->grid);
+  if (e == cudaSuccess) {
+    if (pl->wide) pl->wide(pl->mode, grid, nullptr, pl->r, Den3{pl->den.x, pl->den.y, pl->den.z}, pl->inv_den3, pl->measure, pl->seed, lo, hi, nullptr,
+                           nullptr, nullptr, nullptr, sk);
+    else pl->ops->table(pl->mode, grid, nullptr, pl->r, pl->den, pl->seed, lo, hi, pl->inv_den, nullptr, nullptr, nullptr, sk);
+    e = cudaGetLastError();
+  }
+  unsigned long long found = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&found, d_cnt, 8, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { set_error("plo_orbit_plan_survivors: %s", cudaGetErrorString(e)); cleanup(); return PLO_E_CUDA; }
+  *count = found;
+  if (found > capacity) {
+    set_error("plo_orbit_plan_survivors: %llu survivors, capacity %llu", found, (unsigned long long)capacity);
+    cleanup();
+    return PLO_E_RANGE;
+  }
+  std::vector<uint4> rec((size_t)found * 2);
+  if (found) e = cudaMemcpy(rec.data(), d_rec, (size_t)found * 32, cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) { set_error("plo_orbit_plan_survivors: %s", cudaGetErrorString(e)); return PLO_E_CUDA; }
+  for (size_t i = 0; i < (size_t)found; ++i) {
+    const uint4 a = rec[2 * i], b = rec[2 * i + 1];
+    out[i].index = ((uint64_t)a.y << 32) | a.x;
+    out[i].nnz = a.z; out[i].nno = a.w;
+    const unsigned long long sb = ((unsigned long long)b.y << 32) | b.x;
+    double sc;
+    std::memcpy(&sc, &sb, 8);
+    out[i].score = sc;
+  }
+  std::sort(out, out + found, [](const plo_orbit_best& x, const plo_orbit_best& y) { return x.index < y.index; });
+  return PLO_OK;
 }
 
 // 64-bit inputs (common denominators beyond 2^31, e.g. 2x2x2_7_DPS-intermediate-12.0695): same exact 64-bit kernels, the constant
@@ -1430,7 +1542,7 @@ static int orbit_wide64(int m, int k, int n, int r, const int64_t* L, const int6
   if (e == cudaSuccess && want_tab) e = pool_alloc(&d_nnz, (cnt ? cnt : 1) * 4);
   if (e == cudaSuccess && want_tab) e = pool_alloc(&d_nno, (cnt ? cnt : 1) * 4);
   if (e == cudaSuccess && want_tab) e = pool_alloc(&d_g2, (cnt ? cnt : 1) * 8);
-  if (e == cudaSuccess && cnt) { launch(mode, grid, nullptr, r, den, inv, measure, seed, lo, hi, d_bb, d_nnz, d_nno, d_g2); e = cudaGetLastError(); }
+  if (e == cudaSuccess && cnt) { launch(mode, grid, nullptr, r, den, inv, measure, seed, lo, hi, d_bb, d_nnz, d_nno, d_g2, no_sink()); e = cudaGetLastError(); }
   if (e == cudaSuccess) e = cudaMemcpy(bb.data(), d_bb, sizeof(Key) * grid, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && tnnz && cnt) e = cudaMemcpy(tnnz, d_nnz, cnt * 4, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && tnno && cnt) e = cudaMemcpy(tnno, d_nno, cnt * 4, cudaMemcpyDeviceToHost);
@@ -1442,7 +1554,7 @@ static int orbit_wide64(int m, int k, int n, int r, const int64_t* L, const int6
     if (b.index != ~0ull) {  // all measures of the winner: one 1-candidate launch
       uint32_t* d_c = nullptr; double* d_g = nullptr;
       if (pool_alloc(&d_c, 8) == cudaSuccess && pool_alloc(&d_g, 8) == cudaSuccess) {
-        launch(mode, 1, nullptr, r, den, inv, measure, seed, b.index, b.index + 1, nullptr, d_c, d_c + 1, d_g);
+        launch(mode, 1, nullptr, r, den, inv, measure, seed, b.index, b.index + 1, nullptr, d_c, d_c + 1, d_g, no_sink());
         uint32_t c2[2] = {0, 0}; double g = 0.0;
         e = cudaMemcpy(c2, d_c, 8, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess) e = cudaMemcpy(&g, d_g, 8, cudaMemcpyDeviceToHost);

@@ -217,3 +217,40 @@ def test_four_lane_growth_kernel_is_bit_identical(capi, stem):
     assert whole["score"] == g2.min() and whole["index"] == lo + int(np.argmin(g2))
     ref = O.orbit_sweep(L, R, P, 3, 1, SEED, lo, lo + cnt, table=False)["best"]
     assert (whole["index"], whole["score"]) == (ref[0], ref[3])
+
+
+@pytest.mark.parametrize("stem,count", [("2x2x2_7_Winograd", 30011), ("3x3x3_23_58", 5003), ("2x2x2_7_DPS-integral-12.0662", 4001)])
+def test_survivor_compaction_equals_filtered_oracle_table(capi, stem, count):
+    """plo_orbit_plan_survivors: exactly the candidates of the oracle's per-candidate table that pass the threshold, with both
+    measures, in index order -- for the sparsity order (nnz, nno) and for the growth factor; a ragged range (count not a multiple of
+    the warp), an empty range, the capacity protocol, and the 64-bit exact kernel (DPS-integral)."""
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints(stem)
+    lo = 12345
+    ref = O.orbit_sweep(L, R, P, 3, 1, SEED, lo, lo + count)
+    idx = np.arange(lo, lo + count, dtype=np.uint64)
+    # sparsity: a threshold in the lower part of the distribution
+    order = np.lexsort((ref["nno"], ref["nnz"]))
+    tn, to = int(ref["nnz"][order[count // 50]]), int(ref["nno"][order[count // 50]])
+    keep = (ref["nnz"] < tn) | ((ref["nnz"] == tn) & (ref["nno"] <= to))
+    plan = capi.OrbitPlan(mkn, Li, Ri, Pi, dens, capi.MEASURE_NNZ, 1, SEED)
+    got = plan.survivors(lo, lo + count, nnz=tn, nno=to, capacity=8)  # too small on purpose: the wrapper retries with *count
+    assert [g["index"] for g in got] == idx[keep].tolist()
+    assert [g["nnz"] for g in got] == ref["nnz"][keep].tolist() and [g["nno"] for g in got] == ref["nno"][keep].tolist()
+    np.testing.assert_allclose([g["score"] for g in got], ref["g2"][keep], rtol=RTOL, atol=0)
+    assert plan.survivors(lo, lo) == [] and plan.survivors(lo, lo + count, nnz=0, nno=0) == []
+    with pytest.raises(capi.PloError):  # capacity protocol at the C level: PLO_E_RANGE, count reported
+        import ctypes as C
+        cnt = C.c_uint64(0)
+        thr = capi.OrbitBest(score=0.0, nnz=tn, nno=to, index=0)
+        buf = (capi.OrbitBest * 1)()
+        rc = capi.lib().plo_orbit_plan_survivors(plan._h, lo, lo + count, C.byref(thr), 1, buf, C.byref(cnt))
+        assert rc == capi.E_RANGE and cnt.value == int(keep.sum())
+        capi._check(rc)
+    plan.close()
+    # growth factor
+    thr = float(np.sort(ref["g2"])[count // 100]) * (1 + 1e-9)
+    plan = capi.OrbitPlan(mkn, Li, Ri, Pi, dens, capi.MEASURE_G2, 1, SEED)
+    got = plan.survivors(lo, lo + count, score=thr)
+    want = idx[ref["g2"] <= thr].tolist()
+    assert [g["index"] for g in got] == want and len(want) >= count // 100
+    plan.close()

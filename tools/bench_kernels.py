@@ -130,6 +130,16 @@ def orbit_cases(peaks):
             print(json.dumps({"kernel": f"orbit_sweep_kernel<{m},{k},{n},philox,{name}>", "case": f"{stem}, 2^{lg} candidates", "ms": ms,
                               "candidates_per_s": B / ms * 1e3, "int32_ops_per_candidate": ops, "int32_ops_per_s": ops * B / ms * 1e3,
                               "frac_of_imad_peak": ops * B / ms * 1e3 / peaks["imad_per_s"], "best": best}))
+            if stem in ("2x2x2_7_Winograd", "3x3x3_23_58"):
+                # survivor compaction: every candidate at least as good as the winner of the first 2^16 (both measures per record)
+                plan.run(0, 1 << 16, 0)
+                thr = plan.result()
+                Bs = 1 << (lg - 2)
+                t0 = time.perf_counter()
+                sv = plan.survivors(0, Bs, nnz=thr["nnz"], nno=thr["nno"], score=thr["score"], capacity=1 << 20)
+                dt = time.perf_counter() - t0
+                print(json.dumps({"kernel": f"orbit_table_kernel<{m},{k},{n},philox> + survivor compaction ({name} threshold)", "case": f"{stem}, 2^{lg - 2} candidates",
+                                  "wall_ms_incl_host": dt * 1e3, "candidates_per_s": Bs / dt, "survivors": len(sv)}))
             plan.close()
 
 
