@@ -484,6 +484,58 @@ __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict_
   return sc;
 }
 
+// Sparsity score of one candidate in three phases (all rows of L, then of R, then of P): the counts are sums over the three products, so
+// only the matrices of ONE product are live at a time -- U^-T and V, then V^-1 and W, then U and W^-T -- instead of all six (3x4x7:
+// 134 registers of matrices).  The packed per-half counters run over all rows of a phase (r . lanes < 2^16, checked on the host).
+#ifdef __CUDACC__
+template <int M, int K, int N, int MODE>
+__device__ __forceinline__ Score score_candidate_nnz_split(const int* __restrict__ lrp, int r, int3 den, unsigned long long seed,
+                                                           unsigned long long index, volatile int* scr, int stride) {
+  Digits<MODE> ds(seed, index);
+  const Zoi zu = decode_zoi<M, MODE>(ds);
+  const Zoi zv = decode_zoi<K, MODE>(ds);
+  const Zoi zw = decode_zoi<N, MODE>(ds);
+  const int* Lc = lrp;
+  const int* Rc = lrp + r * M * K;
+  const int* Pc = Rc + r * K * N;
+  Acc aL, aR, aP;
+  aL.nnz = aL.nno = aL.sq = 0;
+  aR = aL; aP = aL;
+  {
+    int Ui[M * M], V[K * K], UiTP[((M + 1) / 2) * M];
+    expand_zoi<M, true>(zu, Ui, scr, stride);
+    pack_left<M, true>(Ui, UiTP);
+    expand_zoi<K, false>(zv, V, scr, stride);
+#pragma unroll 2
+    for (int l = 0; l < r; ++l) transform_row_packed<M, K, false, PLO_MEASURE_NNZ>(Lc + l * M * K, UiTP, V, den.x, aL);   // U^-T A V
+  }
+  {
+    int Vi[K * K], W[N * N], ViP[((K + 1) / 2) * K];
+    expand_zoi<K, true>(zv, Vi, scr, stride);
+    pack_left<K, false>(Vi, ViP);
+    expand_zoi<N, false>(zw, W, scr, stride);
+#pragma unroll 2
+    for (int l = 0; l < r; ++l) transform_row_packed<K, N, false, PLO_MEASURE_NNZ>(Rc + l * K * N, ViP, W, den.y, aR);    // V^-1 B W
+  }
+  {
+    int U[M * M], Wi[N * N], UP[((M + 1) / 2) * M];
+    expand_zoi<M, false>(zu, U, scr, stride);
+    pack_left<M, false>(U, UP);
+    expand_zoi<N, true>(zw, Wi, scr, stride);
+#pragma unroll 2
+    for (int l = 0; l < r; ++l) transform_row_packed<M, N, true, PLO_MEASURE_NNZ>(Pc + l * M * N, UP, Wi, den.z, aP);     // U C W^-T
+  }
+  constexpr int lanes = 2 * ((M + 1) / 2) * K + 2 * ((K + 1) / 2) * N + 2 * ((M + 1) / 2) * N;
+  const int z = (aL.nnz & 0xFFFF) + (aL.nnz >> 16) + (aR.nnz & 0xFFFF) + (aR.nnz >> 16) + (aP.nnz & 0xFFFF) + (aP.nnz >> 16);
+  const int d = (aL.nno & 0xFFFF) + (aL.nno >> 16) + (aR.nno & 0xFFFF) + (aR.nno >> 16) + (aP.nno & 0xFFFF) + (aP.nno >> 16);
+  Score sc;
+  sc.nnz = (uint32_t)z;
+  sc.nno = (uint32_t)(z - (r * lanes - d));
+  sc.g2 = 0.0;
+  return sc;
+}
+#endif
+
 template <int MEASURE>
 __device__ __forceinline__ Key make_key(const Score& s, unsigned long long index) {
   Key k;
@@ -504,7 +556,7 @@ struct MaxDim2 {
 // One candidate per thread, grid-stride over [lo,hi); per-block best to block_best[blockIdx.x].
 // Dynamic shared memory: lutn doubles (sqrt table, G2 only) then the expansion scratch.
 template <int M, int K, int N, int MODE, int MEASURE, int RU, bool LF, bool PACK>
-__global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo,
+__global__ void __launch_bounds__(kThreads, (PACK && MEASURE == PLO_MEASURE_NNZ && M * K * N >= 84) ? 4 : 0) orbit_sweep_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo,
                                                                 unsigned long long hi, int lutn, Key* __restrict__ block_best) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double* lut = reinterpret_cast<double*>(dyn_smem);
@@ -521,7 +573,10 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep_kernel(int r, int3 den, 
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
-    const Score s = score_candidate<M, K, N, MODE, MEASURE, RU, LF, PACK, TAB>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads, lut, lutn, z2tab);
+    constexpr bool SPLIT = PACK && !TAB && MEASURE == PLO_MEASURE_NNZ && RU == 0;
+    Score s;
+    if (SPLIT) s = score_candidate_nnz_split<M, K, N, MODE>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads);
+    else s = score_candidate<M, K, N, MODE, MEASURE, RU, LF, PACK, TAB>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads, lut, lutn, z2tab);
     const Key k = make_key<MEASURE>(s, idx);
     if (k.primary < best.primary) best = k;  // indices visited in increasing order: strict '<' keeps the first
   }
@@ -973,7 +1028,7 @@ struct ShapeOps {
                 const Key* bb, plo_orbit_best* out);
   void (*table)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo,
                 unsigned long long hi, double inv_den, uint32_t* nnz, uint32_t* nno, double* g2, Sink sink);
-  int (*blocks_per_sm)(size_t smem);
+  int (*blocks_per_sm)(int measure, bool lutfull, bool pack, size_t smem);
   int (*blocks_per_sm8)(size_t smem);
   cudaError_t (*allow_smem)(size_t smem);
   void (*sweep8)(int mode, int grid, size_t smem, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
@@ -1003,9 +1058,14 @@ struct Shape {
     if (mode == 0) orbit_table_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2, sink);
     else orbit_table_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, seed, lo, hi, inv_den, nnz, nno, g2, sink);
   }
-  static int blocks_per_sm(size_t smem) {
+  // occupancy of the kernel that `sweep` would launch for this configuration (register use differs a lot between them)
+  static int blocks_per_sm(int measure, bool lutfull, bool pack, size_t smem) {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep_kernel<M, K, N, 1, PLO_MEASURE_G2, RU, false, false>, kThreads, smem);
+#define PLO_OCC(MEAS_, LF_, PK_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep_kernel<M, K, N, 1, MEAS_, RU, LF_, PK_>, kThreads, smem)
+    if (measure == PLO_MEASURE_NNZ) { if (pack) PLO_OCC(PLO_MEASURE_NNZ, false, true); else PLO_OCC(PLO_MEASURE_NNZ, false, false); }
+    else if (lutfull) { if (pack) PLO_OCC(PLO_MEASURE_G2, true, true); else PLO_OCC(PLO_MEASURE_G2, true, false); }
+    else { if (pack) PLO_OCC(PLO_MEASURE_G2, false, true); else PLO_OCC(PLO_MEASURE_G2, false, false); }
+#undef PLO_OCC
     return nb > 0 ? nb : 1;
   }
   static int blocks_per_sm8(size_t smem) {
@@ -1258,7 +1318,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
     delete pl;
     return PLO_E_CUDA;
   }
-  pl->grid = sm_count() * (pl->pack8 ? ops->blocks_per_sm8(pl->smem) : ops->blocks_per_sm(pl->smem));
+  pl->grid = sm_count() * (pl->pack8 ? ops->blocks_per_sm8(pl->smem) : ops->blocks_per_sm(measure, pl->lutfull, pl->pack, pl->smem));
   pl->d_block_best = nullptr; pl->d_out = nullptr;
   if (pool_alloc(&pl->d_block_best, sizeof(Key) * pl->grid) != cudaSuccess || pool_alloc(&pl->d_out, sizeof(plo_orbit_best)) != cudaSuccess) {
     set_error("orbit sweep: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
