@@ -254,3 +254,27 @@ def test_survivor_compaction_equals_filtered_oracle_table(capi, stem, count):
     want = idx[ref["g2"] <= thr].tolist()
     assert [g["index"] for g in got] == want and len(want) >= count // 100
     plan.close()
+
+
+@pytest.mark.parametrize("measure", [0, 3])
+def test_full_size_sweep_reaches_the_exhaustive_optimum(capi, measure):
+    """BASELINE config 2 at bench.py's size (2^31 Philox candidates of 2x2x2_7_Winograd), through properties that do not need the
+    oracle at that size: the 48^3 orbit is sampled ~19000 times over, so the winner's score must be the optimum of the exhaustive
+    sweep; the result does not depend on how the range is cut; and the winner is the FIRST index that reaches the optimum (survivor
+    compaction below the winner returns exactly that one candidate)."""
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints("2x2x2_7_Winograd")
+    opt = capi.orbit_sweep(mkn, Li, Ri, Pi, dens, measure, 0, 0, 0, capi.orbit_space(*mkn))
+    N = 1 << 31
+    plan = capi.OrbitPlan(mkn, Li, Ri, Pi, dens, measure, 1, SEED)
+    plan.run(0, N); whole = plan.result()
+    assert (whole["score"], whole["nnz"], whole["nno"]) == (opt["score"], opt["nnz"], opt["nno"])
+    parts = []
+    for a, b in [(0, N // 7), (N // 7, N // 2 + 3), (N // 2 + 3, N)]:
+        plan.run(a, b); parts.append(plan.result())
+    key = (lambda d: (d["nnz"], d["nno"], d["index"])) if measure == 0 else (lambda d: (d["score"], d["index"]))
+    assert min(parts, key=key) == whole
+    first = plan.survivors(0, whole["index"] + 1, nnz=opt["nnz"], nno=opt["nno"], score=opt["score"])
+    assert [s["index"] for s in first] == [whole["index"]]
+    one = O.orbit_sweep(L, R, P, 3, 1, SEED, whole["index"], whole["index"] + 1)
+    assert (one["nnz"][0], one["nno"][0]) == (whole["nnz"], whole["nno"]) and (measure == 0 or one["g2"][0] == whole["score"])
+    plan.close()
