@@ -109,3 +109,41 @@ def allreduce_lincomb(results, device=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         keys = t.tolist()
     return [lincomb_unkey(k) for k in keys]
+
+
+def gather_survivors(local, device=None):
+    """Survivor lists (OrbitPlan.survivors: dicts with index, nnz, nno, score) of disjoint index ranges -> the global list on every
+    rank, sorted by index.  Two collectives: an all_gather of the counts and one of the padded (index, nnz<<32|nno, score bits)
+    triples; the ranges are disjoint and ascending with the rank, so concatenation in rank order is already sorted."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return list(local)
+    world = dist.get_world_size()
+    n = torch.tensor([len(local)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    width = max(max(counts), 1)
+    buf = torch.zeros((width, 3), dtype=torch.int64)
+    for i, sv in enumerate(local):
+        buf[i, 0] = _to_i64(sv["index"])
+        buf[i, 1] = _to_i64((sv["nnz"] << 32) | sv["nno"])
+        buf[i, 2] = struct.unpack("<q", struct.pack("<d", sv["score"]))[0]
+    buf = buf.to(device) if device is not None else buf
+    parts = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    out = []
+    for rk in range(world):
+        rows = parts[rk][:counts[rk]].cpu().tolist()
+        for idx, cnt, sb in rows:
+            cnt &= (1 << 64) - 1
+            out.append(dict(index=idx & ((1 << 64) - 1), nnz=cnt >> 32, nno=cnt & 0xFFFFFFFF, score=struct.unpack("<d", struct.pack("<q", sb))[0]))
+    out.sort(key=lambda d: d["index"])
+    return out
+
+
+def _to_i64(u):
+    """uint64 -> the int64 with the same bits (torch has no uint64 collectives)."""
+    u &= (1 << 64) - 1
+    return u - (1 << 64) if u >= (1 << 63) else u

@@ -54,7 +54,9 @@ def _worker(rank, world, port, q):
     f = S.allreduce_factor_best((196, 100, 168, 40 + rank) if rank == 1 else (196, 100, 168, 77))
     f0 = S.allreduce_factor_best((1, 2, 3, None))
     lc = S.allreduce_lincomb([(24, 2, 500 + rank), (10, 1, None) if rank == 0 else (10, 1, 7), (-1, -1, None)])
-    q.put((rank, g, e, f, f0, lc))
+    sv = S.gather_survivors([dict(index=(1 << 63) + 5 + 10 * rank + j, nnz=36 + j, nno=rank, score=14.5 + j) for j in range(2 - rank)])
+    sv0 = S.gather_survivors([])
+    q.put((rank, g, e, f, f0, lc, sv, sv0))
     dist.destroy_process_group()
 
 
@@ -66,7 +68,9 @@ def test_allreduce_min_with_index_gloo_world2():
     [p.start() for p in ps]
     out = [q.get(timeout=120) for _ in ps]
     [p.join(60) for p in ps]
-    for rank, g, e, f, f0, lc in out:
+    for rank, g, e, f, f0, lc, sv, sv0 in out:
+        assert sv0 == [] and [(d["index"], d["nnz"], d["nno"], d["score"]) for d in sv] == [
+            ((1 << 63) + 5, 36, 0, 14.5), ((1 << 63) + 6, 37, 0, 15.5), ((1 << 63) + 15, 36, 1, 14.5)]
         assert lc == [(24, 2, 500), (10, 1, 7), (-1, -1, None)]  # first maximiser in enumeration order; seed kept if nobody beat it
         assert g["index"] == 123 and g["rank"] == 0 and g["score"] == 12.0 and g["nnz"] == 40
         assert e["index"] == 999 and e["rank"] == 1
