@@ -437,6 +437,27 @@ __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict_
   sc.nnz = 0; sc.nno = 0; sc.g2 = 0.0;
   int nnz = 0, nno = 0;
   const int rows = RU > 0 ? RU : r;
+#ifdef __CUDA_ARCH__
+  if (PACK && MEASURE == PLO_MEASURE_NNZ) {
+    // packed per-half counters run over ALL rows (rows . lanes < 2^16) and are split once:
+    // nnz = sum of halves; nno = nnz - #(|y| == den) = nnz - (lanes - #(|y| != den))
+    Acc aL, aR, aP;
+    aL.nnz = aL.nno = aL.sq = 0;
+    aR = aL; aP = aL;
+#pragma unroll(RU > 0 ? RU : 1)
+    for (int l = 0; l < rows; ++l) {
+      transform_row_packed<M, K, false, MEASURE>(Lc + l * M * K, UiTP, V, den.x, aL);
+      transform_row_packed<K, N, false, MEASURE>(Rc + l * K * N, ViP, W, den.y, aR);
+      transform_row_packed<M, N, true, MEASURE>(Pc + l * M * N, UP, Wi, den.z, aP);
+    }
+    constexpr int lanes = 2 * ((M + 1) / 2) * K + 2 * ((K + 1) / 2) * N + 2 * ((M + 1) / 2) * N;
+    const int z = (aL.nnz & 0xFFFF) + (aL.nnz >> 16) + (aR.nnz & 0xFFFF) + (aR.nnz >> 16) + (aP.nnz & 0xFFFF) + (aP.nnz >> 16);
+    const int d = (aL.nno & 0xFFFF) + (aL.nno >> 16) + (aR.nno & 0xFFFF) + (aR.nno >> 16) + (aP.nno & 0xFFFF) + (aP.nno >> 16);
+    sc.nnz = (uint32_t)z;
+    sc.nno = (uint32_t)(z - (rows * lanes - d));
+    return sc;
+  }
+#endif
 #pragma unroll(RU > 0 ? RU : 1)
   for (int l = 0; l < rows; ++l) {
     Acc aL, aR, aP;
@@ -454,20 +475,8 @@ __host__ __device__ __forceinline__ Score score_candidate(const int* __restrict_
       transform_row<K, N, false, false, MEASURE>(Rc + l * K * N, Vi, W, den.y, aR);  // V^-1 B W
       transform_row<M, N, false, true, MEASURE>(Pc + l * M * N, U, Wi, den.z, aP);   // U C W^-T
     }
-#ifdef __CUDA_ARCH__
-    if (PACK && MEASURE == PLO_MEASURE_NNZ) {
-      // packed per-half counters: nnz = sum of halves; nno = nnz - #(|y| == den) = nnz - (lanes - #(|y| != den))
-      constexpr int lanesL = 2 * ((M + 1) / 2) * K, lanesR = 2 * ((K + 1) / 2) * N, lanesP = 2 * ((M + 1) / 2) * N;
-      const int zL = (aL.nnz & 0xFFFF) + (aL.nnz >> 16), zR = (aR.nnz & 0xFFFF) + (aR.nnz >> 16), zP = (aP.nnz & 0xFFFF) + (aP.nnz >> 16);
-      const int dL = (aL.nno & 0xFFFF) + (aL.nno >> 16), dR = (aR.nno & 0xFFFF) + (aR.nno >> 16), dP = (aP.nno & 0xFFFF) + (aP.nno >> 16);
-      nnz += zL + zR + zP;
-      nno += (zL + zR + zP) - (lanesL + lanesR + lanesP - dL - dR - dP);
-    } else
-#endif
-    {
-      nnz += aL.nnz + aR.nnz + aP.nnz;
-      nno += aL.nno + aR.nno + aP.nno;
-    }
+    nnz += aL.nnz + aR.nnz + aP.nnz;
+    nno += aL.nno + aR.nno + aP.nno;
     if (MEASURE == PLO_MEASURE_G2 || MEASURE == MEASURE_BOTH) {
       // growthfactor.cpp:117-125: s += norm2(L[i])*norm2(R[i])*norm2(Pt[i]); no FMA contraction
 #ifdef __CUDA_ARCH__
@@ -871,6 +880,106 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned 
 }
 
 // ---------------------------------------------------------------------------
+// 2x2x2, r = 7, four lanes, first product stage from tables.  With only 48 matrices per factor the whole first stage
+// X = pack(U^-T).A_l (resp. pack(V^-1).B_l, pack(U).C_l) depends on ONE matrix number, so each block tabulates it once:
+// entry e = 8 chunks of 16 bytes  [XL q0,q1 | XL q2,q3 | XP .. | XP .. | XR .. | XR .. | M | M^-1]  (XL/XP are read with the number of
+// U, XR and M with that of V, M and M^-1 with that of W).  Every chunk is stored in 8 replicas, replica c in 16-byte bank group c, and
+// lane t reads replica t mod 8: the eight lanes of a quarter warp never collide, whatever their matrix numbers (LDS.128 = 4
+// wavefronts, always).  The sqrt table is replicated 16 times the same way (lane t reads replica t mod 16: LDS.64 = 2 wavefronts).
+// A candidate then costs 9 + 21 loads and only the second product stage in IMADs (48 instead of 96).
+// ---------------------------------------------------------------------------
+constexpr int kXThreads = 512, kXChunks = 8, kXRep = 8, kXLutRep = 16;
+constexpr size_t kXTabBytes = (size_t)kZ2Count * kXChunks * kXRep * 16;
+
+__device__ __forceinline__ void ystage_pair8(int X0, int X1, int r0, int r1, int& sq0, int& sq1) {
+  const int v = X0 * r0 + X1 * r1;
+  const unsigned x = ((unsigned)v + 0x80808080u) ^ 0x80808080u;
+  sq0 = __dp4a((int)x, (int)(x & 0x00FF00FFu), sq0);
+  sq1 = __dp4a((int)x, (int)(x & 0xFF00FF00u), sq1);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kXThreads, 2) orbit_sweep8x_kernel(unsigned long long seed, unsigned long long lo, unsigned long long hi, int lutn,
+                                                                      Key* __restrict__ block_best) {
+  constexpr int RU = 7, NP = 4;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  int4* tab = reinterpret_cast<int4*>(dyn_smem);
+  double* lut = reinterpret_cast<double*>(dyn_smem + kXTabBytes);
+  __shared__ Key red[32];
+  const int* L2 = c_lrp2;
+  const int* R2 = L2 + NP * 4;
+  const int* P2 = R2 + NP * 4;
+  for (int t = threadIdx.x; t < kZ2Count * kXRep; t += kXThreads) {
+    const int e = t / kXRep, c = t % kXRep;
+    RawDigits<MODE> ds((uint32_t)e, (uint32_t)kZ2Count);
+    const Zoi z = decode_zoi<2, MODE, RawDigits<MODE>>(ds);
+    int Mx[4], Mi[4], pit[2], pm[2], pi[2];
+    expand_zoi<2, false>(z, Mx, nullptr, 0);
+    expand_zoi<2, true>(z, Mi, nullptr, 0);
+    pack_left<2, true>(Mi, pit);
+    pack_left<2, false>(Mx, pm);
+    pack_left<2, false>(Mi, pi);
+    int xl[2 * NP], xp[2 * NP], xr[2 * NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        xl[2 * q + j] = pit[0] * L2[q * 4 + j] + pit[1] * L2[q * 4 + 2 + j];
+        xp[2 * q + j] = pm[0] * P2[q * 4 + j] + pm[1] * P2[q * 4 + 2 + j];
+        xr[2 * q + j] = pi[0] * R2[q * 4 + j] + pi[1] * R2[q * 4 + 2 + j];
+      }
+    int4* ent = tab + (size_t)e * kXChunks * kXRep + c;
+    ent[0 * kXRep] = make_int4(xl[0], xl[1], xl[2], xl[3]);
+    ent[1 * kXRep] = make_int4(xl[4], xl[5], xl[6], xl[7]);
+    ent[2 * kXRep] = make_int4(xp[0], xp[1], xp[2], xp[3]);
+    ent[3 * kXRep] = make_int4(xp[4], xp[5], xp[6], xp[7]);
+    ent[4 * kXRep] = make_int4(xr[0], xr[1], xr[2], xr[3]);
+    ent[5 * kXRep] = make_int4(xr[4], xr[5], xr[6], xr[7]);
+    ent[6 * kXRep] = make_int4(Mx[0], Mx[1], Mx[2], Mx[3]);
+    ent[7 * kXRep] = make_int4(Mi[0], Mi[1], Mi[2], Mi[3]);
+  }
+  for (int e = threadIdx.x; e < lutn * kXLutRep; e += kXThreads) lut[e] = sqrt((double)(e / kXLutRep));
+  __syncthreads();
+  const int4* mytab = tab + (threadIdx.x % kXRep);
+  const double* mylut = lut + (threadIdx.x % kXLutRep);
+  const unsigned long long stride = (unsigned long long)gridDim.x * kXThreads;
+  Key best;
+  best.primary = ~0ull; best.index = ~0ull;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kXThreads + threadIdx.x; idx < hi; idx += stride) {
+    Digits<MODE> ds(seed, idx);
+    const int4* tu = mytab + ds.matrix_index(kZ2Count) * (kXChunks * kXRep);
+    const int4* tv = mytab + ds.matrix_index(kZ2Count) * (kXChunks * kXRep);
+    const int4* tw = mytab + ds.matrix_index(kZ2Count) * (kXChunks * kXRep);
+    const int4 xl0 = tu[0 * kXRep], xl1 = tu[1 * kXRep], xp0 = tu[2 * kXRep], xp1 = tu[3 * kXRep];
+    const int4 xr0 = tv[4 * kXRep], xr1 = tv[5 * kXRep], V = tv[6 * kXRep];
+    const int4 W = tw[6 * kXRep], Wi = tw[7 * kXRep];
+    const int XL[8] = {xl0.x, xl0.y, xl0.z, xl0.w, xl1.x, xl1.y, xl1.z, xl1.w};
+    const int XP[8] = {xp0.x, xp0.y, xp0.z, xp0.w, xp1.x, xp1.y, xp1.z, xp1.w};
+    const int XR[8] = {xr0.x, xr0.y, xr0.z, xr0.w, xr1.x, xr1.y, xr1.z, xr1.w};
+    double g2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      int sL0 = 0, sL1 = 0, sR0 = 0, sR1 = 0, sP0 = 0, sP1 = 0;
+      // second stage: y = X . Rm (Rm[j][y]) for L and R, y = X . Rm^T (Rm[y][j]) for P
+      ystage_pair8(XL[2 * q], XL[2 * q + 1], V.x, V.z, sL0, sL1);
+      ystage_pair8(XL[2 * q], XL[2 * q + 1], V.y, V.w, sL0, sL1);
+      ystage_pair8(XR[2 * q], XR[2 * q + 1], W.x, W.z, sR0, sR1);
+      ystage_pair8(XR[2 * q], XR[2 * q + 1], W.y, W.w, sR0, sR1);
+      ystage_pair8(XP[2 * q], XP[2 * q + 1], Wi.x, Wi.y, sP0, sP1);
+      ystage_pair8(XP[2 * q], XP[2 * q + 1], Wi.z, Wi.w, sP0, sP1);
+      g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(mylut[sL0 * kXLutRep], mylut[sR0 * kXLutRep]), mylut[sP0 * kXLutRep]));
+      if (2 * q + 1 < RU) g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(mylut[sL1 * kXLutRep], mylut[sR1 * kXLutRep]), mylut[sP1 * kXLutRep]));
+    }
+    Key k;
+    k.primary = (unsigned long long)__double_as_longlong(g2);
+    k.index = idx;
+    if (k.primary < best.primary) best = k;
+  }
+  best = block_min(best, red);
+  if (threadIdx.x == 0) block_best[blockIdx.x] = best;
+}
+
+// ---------------------------------------------------------------------------
 // Wide exact path: int32 inputs whose transforms (or squares) would leave 32 bits -- e.g. 2x2x2_7_DPS-integral-12.0662, common
 // denominators ~10^9.  Both stages of the product are accumulated exactly in 64 bits (|.| < 2^31 . 2^8 . 2^8, as in the modular
 // path); sparsity is classified on the exact integers; for the growth factor every entry becomes a double first
@@ -1153,6 +1262,8 @@ struct plo_orbit_plan {
   bool lutfull, pack;
   size_t smem;
   bool pack8;           // four-lane growth-factor kernel
+  bool xtab;            // ... with the first product stage from shared-memory tables (2x2x2, r = 7)
+  size_t xsmem;
   std::vector<int> h_lrp2;
   WideLaunch wide;      // non-null: 64-bit exact path (inputs beyond the int32 product bound)
   double3 inv_den3;
@@ -1319,6 +1430,19 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
     return PLO_E_CUDA;
   }
   pl->grid = sm_count() * (pl->pack8 ? ops->blocks_per_sm8(pl->smem) : ops->blocks_per_sm(measure, pl->lutfull, pl->pack, pl->smem));
+  pl->xtab = pl->pack8 && m == 2 && k == 2 && n == 2 && r == 7 && getenv("PLO_ORBIT_NOXTAB") == nullptr;
+  pl->xsmem = kXTabBytes + (size_t)pl->lutn * kXLutRep * sizeof(double);
+  if (pl->xtab) {
+    int nb = 0;
+    if (cudaFuncSetAttribute(orbit_sweep8x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->xsmem) != cudaSuccess ||
+        cudaFuncSetAttribute(orbit_sweep8x_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->xsmem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep8x_kernel<1>, kXThreads, pl->xsmem) != cudaSuccess || nb < 1) {
+      cudaGetLastError();
+      pl->xtab = false;  // the plain four-lane kernel still applies
+    } else {
+      pl->grid = sm_count() * nb;
+    }
+  }
   pl->d_block_best = nullptr; pl->d_out = nullptr;
   if (pool_alloc(&pl->d_block_best, sizeof(Key) * pl->grid) != cudaSuccess || pool_alloc(&pl->d_out, sizeof(plo_orbit_best)) != cudaSuccess) {
     set_error("orbit sweep: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1361,7 +1485,10 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
     PLO_CUDA(cudaGetLastError());
     return PLO_OK;
   }
-  if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->d_block_best);
+  if (pl->xtab) {
+    if (pl->mode == 0) orbit_sweep8x_kernel<0><<<pl->grid, kXThreads, pl->xsmem, st>>>(pl->seed, lo, hi, pl->lutn, pl->d_block_best);
+    else orbit_sweep8x_kernel<1><<<pl->grid, kXThreads, pl->xsmem, st>>>(pl->seed, lo, hi, pl->lutn, pl->d_block_best);
+  } else if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->d_block_best);
   else pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());
