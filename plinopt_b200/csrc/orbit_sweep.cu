@@ -892,10 +892,26 @@ constexpr int kXThreads = 512, kXChunks = 8, kXRep = 8, kXLutRep = 16;
 constexpr size_t kXTabBytes = (size_t)kZ2Count * kXChunks * kXRep * 16;
 
 __device__ __forceinline__ void ystage_pair8(int X0, int X1, int r0, int r1, int& sq0, int& sq1) {
-  const int v = X0 * r0 + X1 * r1;
-  const unsigned x = ((unsigned)v + 0x80808080u) ^ 0x80808080u;
+  // w = X0.r0 + X1.r1 + 0x80808080 with the bias as the addend of the first multiply-add (two IMAD, no separate add)
+  int t, w;
+  asm("mad.lo.s32 %0, %1, %2, 0x80808080;" : "=r"(t) : "r"(X0), "r"(r0));
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(w) : "r"(X1), "r"(r1), "r"(t));
+  const unsigned x = (unsigned)w ^ 0x80808080u;
   sq0 = __dp4a((int)x, (int)(x & 0x00FF00FFu), sq0);
   sq1 = __dp4a((int)x, (int)(x & 0xFF00FF00u), sq1);
+}
+
+// Shared-memory loads from a 32-bit shared-window address kept in a register: one address instruction per lookup (nvcc otherwise
+// re-adds the window base of the dynamic array to every data-dependent offset).
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t addr) {
+  int4 v;
+  asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 
 template <int MODE>
@@ -940,19 +956,20 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep8x_kernel(unsigned lo
   }
   for (int e = threadIdx.x; e < lutn * kXLutRep; e += kXThreads) lut[e] = sqrt((double)(e / kXLutRep));
   __syncthreads();
-  const int4* mytab = tab + (threadIdx.x % kXRep);
-  const double* mylut = lut + (threadIdx.x % kXLutRep);
+  const uint32_t mytab = (uint32_t)__cvta_generic_to_shared(tab + (threadIdx.x % kXRep));
+  const uint32_t mylut = (uint32_t)__cvta_generic_to_shared(lut + (threadIdx.x % kXLutRep));
+  constexpr uint32_t kEnt = kXChunks * kXRep * 16, kChunk = kXRep * 16, kLutStep = kXLutRep * 8;  // bytes
   const unsigned long long stride = (unsigned long long)gridDim.x * kXThreads;
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kXThreads + threadIdx.x; idx < hi; idx += stride) {
     Digits<MODE> ds(seed, idx);
-    const int4* tu = mytab + ds.matrix_index(kZ2Count) * (kXChunks * kXRep);
-    const int4* tv = mytab + ds.matrix_index(kZ2Count) * (kXChunks * kXRep);
-    const int4* tw = mytab + ds.matrix_index(kZ2Count) * (kXChunks * kXRep);
-    const int4 xl0 = tu[0 * kXRep], xl1 = tu[1 * kXRep], xp0 = tu[2 * kXRep], xp1 = tu[3 * kXRep];
-    const int4 xr0 = tv[4 * kXRep], xr1 = tv[5 * kXRep], V = tv[6 * kXRep];
-    const int4 W = tw[6 * kXRep], Wi = tw[7 * kXRep];
+    const uint32_t tu = mytab + ds.matrix_index(kZ2Count) * kEnt;
+    const uint32_t tv = mytab + ds.matrix_index(kZ2Count) * kEnt;
+    const uint32_t tw = mytab + ds.matrix_index(kZ2Count) * kEnt;
+    const int4 xl0 = lds_v4(tu), xl1 = lds_v4(tu + kChunk), xp0 = lds_v4(tu + 2 * kChunk), xp1 = lds_v4(tu + 3 * kChunk);
+    const int4 xr0 = lds_v4(tv + 4 * kChunk), xr1 = lds_v4(tv + 5 * kChunk), V = lds_v4(tv + 6 * kChunk);
+    const int4 W = lds_v4(tw + 6 * kChunk), Wi = lds_v4(tw + 7 * kChunk);
     const int XL[8] = {xl0.x, xl0.y, xl0.z, xl0.w, xl1.x, xl1.y, xl1.z, xl1.w};
     const int XP[8] = {xp0.x, xp0.y, xp0.z, xp0.w, xp1.x, xp1.y, xp1.z, xp1.w};
     const int XR[8] = {xr0.x, xr0.y, xr0.z, xr0.w, xr1.x, xr1.y, xr1.z, xr1.w};
@@ -967,8 +984,9 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep8x_kernel(unsigned lo
       ystage_pair8(XR[2 * q], XR[2 * q + 1], W.y, W.w, sR0, sR1);
       ystage_pair8(XP[2 * q], XP[2 * q + 1], Wi.x, Wi.y, sP0, sP1);
       ystage_pair8(XP[2 * q], XP[2 * q + 1], Wi.z, Wi.w, sP0, sP1);
-      g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(mylut[sL0 * kXLutRep], mylut[sR0 * kXLutRep]), mylut[sP0 * kXLutRep]));
-      if (2 * q + 1 < RU) g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(mylut[sL1 * kXLutRep], mylut[sR1 * kXLutRep]), mylut[sP1 * kXLutRep]));
+      g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(lds_f64(mylut + sL0 * kLutStep), lds_f64(mylut + sR0 * kLutStep)), lds_f64(mylut + sP0 * kLutStep)));
+      if (2 * q + 1 < RU)
+        g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(lds_f64(mylut + sL1 * kLutStep), lds_f64(mylut + sR1 * kLutStep)), lds_f64(mylut + sP1 * kLutStep)));
     }
     Key k;
     k.primary = (unsigned long long)__double_as_longlong(g2);
