@@ -28,10 +28,10 @@ WORKLOAD = "orbit sweep of 2x2x2_7_Winograd_{L,R,P}, measure G2 (growthfactor.cp
 INT_OPS_PER_CAND = 336 + 84
 FP64_OPS_PER_CAND = 21 + 14 + 7
 METRIC = "candidates scored/sec"
-NCU_DRAM_BYTES_PER_LAUNCH = 22528  # ncu --set full, profiles/ncu_r01_orbit_sweep.md: 22.5 KB read + 0 B written per launch
-# issued thread instructions per candidate of orbit_sweep8_kernel<2,2,2,philox,7>: smsp__inst_executed.sum x 32 / candidates of the
-# same capture (2 995 926 528 warp instructions for 2^28 candidates)
-NCU_INST_PER_CAND = 2995926528 * 32 / float(1 << 28)
+NCU_DRAM_BYTES_PER_LAUNCH = 23040  # ncu --set full, profiles/ncu_r01_orbit_sweep.md: 23.0 KB read + 0 B written per launch
+# issued thread instructions per candidate of orbit_sweep8x_kernel<philox>: smsp__inst_executed.sum x 32 / candidates of the
+# same capture (2 576 819 656 warp instructions for 2^28 candidates)
+NCU_INST_PER_CAND = 2576819656 * 32 / float(1 << 28)
 
 
 def env_int(name, default):
@@ -267,8 +267,8 @@ def main():
 
     if rank == 0:
         clocks = sampler.summary()
-        # The kernel carries four 8-bit lanes per IMAD and reads the 2x2 matrices from a table, so it does the 420 algorithmic int32
-        # operations of a candidate in ~357 issued instructions: the algorithmic rate is ABOVE the scalar IMAD peak, and the limit that
+        # The kernel carries four 8-bit lanes per IMAD and reads the 2x2 matrices and the first product stage from tables, so it does the
+        # 420 algorithmic int32 operations of a candidate in ~307 issued instructions: the algorithmic rate is ABOVE the scalar IMAD peak, and the limit that
         # binds is the scheduler's issue rate (IMAD/IDP on the fma-heavy pipe + LOP3 on the alu pipe).  frac = issued instructions per
         # second over the live-measured issue peak; the algorithmic view is kept beside it.
         cand_per_s = B / (kern_ms * 1e-3)
@@ -278,7 +278,7 @@ def main():
         roof = {"bound": "int32", "achieved": achieved, "peak": peak, "unit": "T thread-instructions/s (issue slots)", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/ncu_r01_orbit_sweep.md (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch; "
                 "independent of the candidate count: constants + one 16 B key per block)",
-                "kernel": "orbit_sweep8_kernel<2,2,2,philox,7>", "kernel_ms": kern_ms,
+                "kernel": "orbit_sweep8x_kernel<philox> (2x2x2, r = 7: four lanes per IMAD, first product stage from shared-memory tables)", "kernel_ms": kern_ms,
                 "instructions_per_candidate": NCU_INST_PER_CAND,
                 "instructions_source": "profiles/ncu_r01_orbit_sweep.md (smsp__inst_executed.sum x 32 / candidates of the captured launch)",
                 "peak_source": "plo_measure_issue_peak (IMAD and LOP3 chains interleaved 1:1, all SMs, best of 5, measured in this run); "
