@@ -75,8 +75,26 @@ __device__ __forceinline__ uint32_t fs_reduce(const FsAcc& a, const FsParams& P)
   const uint32_t u = (uint32_t)(((unsigned long long)s + (unsigned long long)m * P.p) >> 32);
   return u >= P.p ? u - P.p : u;
 }
-// a^-1 in the Montgomery domain: (aR)^(p-2) by square and multiply (p prime)
+// a^-1 in the Montgomery domain: (aR)^(p-2) (p prime).  For p = 2^31-1 (the prime every rational input is scored with) the exponent
+// 2^31-3 = 4.(2^29-1) + 1 has an addition chain of 30 squarings + 8 multiplications through a^(2^k-1), k = 1,2,4,8,16,24,28,29;
+// any other prime takes plain square and multiply (31 squarings + up to 30 multiplications).  The chain is serial: its length is
+// what the kernel waits for when a pivot is not +-1.
+__device__ __forceinline__ uint32_t mont_sqn(uint32_t a, int n, const FsParams& P) {
+#pragma unroll
+  for (int i = 0; i < n; ++i) a = mont_mul(a, a, P.p, P.pinv);
+  return a;
+}
 __device__ __forceinline__ uint32_t mont_inv(uint32_t a, const FsParams& P) {
+  if (P.p == 0x7FFFFFFFu) {
+    const uint32_t t2 = mont_mul(mont_sqn(a, 1, P), a, P.p, P.pinv);
+    const uint32_t t4 = mont_mul(mont_sqn(t2, 2, P), t2, P.p, P.pinv);
+    const uint32_t t8 = mont_mul(mont_sqn(t4, 4, P), t4, P.p, P.pinv);
+    const uint32_t t16 = mont_mul(mont_sqn(t8, 8, P), t8, P.p, P.pinv);
+    const uint32_t t24 = mont_mul(mont_sqn(t16, 8, P), t8, P.p, P.pinv);
+    const uint32_t t28 = mont_mul(mont_sqn(t24, 4, P), t4, P.p, P.pinv);
+    const uint32_t t29 = mont_mul(mont_sqn(t28, 1, P), a, P.p, P.pinv);
+    return mont_mul(mont_sqn(t29, 2, P), a, P.p, P.pinv);
+  }
   uint32_t result = P.one, base = a;
   uint32_t e = P.p - 2;
   while (e) {
