@@ -156,3 +156,45 @@ def test_orbit_random_triples(capi, seed):
         refp = O.orbit_sweep(L, R, P, 0, 1, 9, 50, 50 + cnt, p=p)
         nz, no = capi.orbit_table_modp(p, (m, k, n), red(L), red(R), red(P), 1, 9, 50, 50 + cnt)
         assert np.array_equal(nz, refp["nnz"]) and np.array_equal(no, refp["nno"])
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_orbit_sweep_kernels_against_the_table_kernel(capi, seed):
+    """The sweep kernels (two-lane / four-lane / table-driven / three-phase / 64-bit, chosen by shape, rank and magnitudes) against the
+    plain per-candidate table kernel on random triples: every 16-candidate window must elect the table's lexicographic minimum with the
+    lowest index, for both measures, and survivor compaction must return the table's sub-threshold set.  Seeds 0-5 force the
+    2x2x2, r = 7, small-integer case of the headline kernel."""
+    rng = np.random.default_rng(7000 + seed)
+    if seed < 6:
+        (m, k, n), r, scale, den = (2, 2, 2), 7, 1, 1
+    else:
+        m, k, n = (int(v) for v in rng.choice([(2, 2, 2), (3, 3, 3), (4, 4, 4), (3, 4, 7), (3, 3, 6), (3, 6, 3), (6, 3, 3)]))
+        r = int(rng.integers(1, 12)); scale = int(rng.choice([1, 1, 3, 1000, 40000])); den = int(rng.choice([1, 1, 2, 6]))
+    hi_v = 2 if seed % 2 else 3
+    mat = lambda rows, cols: [[Fraction(int(rng.integers(-hi_v + 1, hi_v)) * scale, den) for _ in range(cols)] for _ in range(rows)]
+    L, R, P = mat(r, m * k), mat(r, k * n), mat(m * n, r)
+    (Li, dl), (Ri, dr), (Pi, dp) = O.scaled_int(L), O.scaled_int(R), O.scaled_int(P)
+    Li, Ri, Pi = Li.astype(np.int32), Ri.astype(np.int32), Pi.astype(np.int32)
+    lo, cnt, win = 1 << 20, 320, 16
+    mode = int(seed % 3 != 2)  # mostly Philox, sometimes the mixed-radix enumeration (where the space fits 64 bits)
+    if mode == 0 and capi.orbit_space(m, k, n) <= (1 << 20) + 320:
+        mode = 1
+    nnz, nno, g2 = capi.orbit_table((m, k, n), Li, Ri, Pi, (dl, dr, dp), mode, 77, lo, lo + cnt)
+    for measure in (capi.MEASURE_NNZ, capi.MEASURE_G2):
+        plan = capi.OrbitPlan((m, k, n), Li, Ri, Pi, (dl, dr, dp), measure, mode, 77)
+        for a in range(0, cnt, win):
+            plan.run(lo + a, lo + a + win)
+            got = plan.result()
+            sl = slice(a, a + win)
+            if measure == capi.MEASURE_NNZ:
+                keys = [(int(x), int(y)) for x, y in zip(nnz[sl], nno[sl])]
+                j = keys.index(min(keys))
+                assert (got["index"], got["nnz"], got["nno"]) == (lo + a + j, keys[j][0], keys[j][1]), (m, k, n, r, scale, den, a)
+            else:
+                j = int(np.argmin(g2[sl]))
+                assert got["index"] == lo + a + j and got["score"] == g2[sl][j], (m, k, n, r, scale, den, a)
+        thr_n = int(np.sort(nnz)[cnt // 10]); thr_g = float(np.sort(g2)[cnt // 10])
+        sv = plan.survivors(lo, lo + cnt, nnz=thr_n, nno=0xFFFFFFFF, score=thr_g)
+        keep = (nnz <= thr_n) if measure == capi.MEASURE_NNZ else (g2 <= thr_g)
+        assert [s["index"] - lo for s in sv] == np.nonzero(keep)[0].tolist()
+        plan.close()
