@@ -565,7 +565,7 @@ struct MaxDim2 {
 // One candidate per thread, grid-stride over [lo,hi); per-block best to block_best[blockIdx.x].
 // Dynamic shared memory: lutn doubles (sqrt table, G2 only) then the expansion scratch.
 template <int M, int K, int N, int MODE, int MEASURE, int RU, bool LF, bool PACK>
-__global__ void __launch_bounds__(kThreads, (PACK && MEASURE == PLO_MEASURE_NNZ && M * K * N >= 84) ? 4 : 0) orbit_sweep_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo,
+__global__ void __launch_bounds__(kThreads, (PACK && M * K * N >= 84) ? (MEASURE == PLO_MEASURE_NNZ ? 4 : 3) : 0) orbit_sweep_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo,
                                                                 unsigned long long hi, int lutn, Key* __restrict__ block_best) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double* lut = reinterpret_cast<double*>(dyn_smem);
@@ -997,6 +997,105 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep8x_kernel(unsigned lo
   if (threadIdx.x == 0) block_best[blockIdx.x] = best;
 }
 
+// Sparsity twin of the table-driven kernel: 2x2x2, r = 7, two 16-bit lanes (any magnitudes the packed path takes, any denominators).
+// Entry = 14 chunks  [XL rows 0-1 | 2-3 | 4-5 | 6,- ] [XP ...] [XR ...] [M] [M^-1], one chunk = {X[l][0], X[l][1], X[l+1][0], X[l+1][1]};
+// same replicas, same addressing.  Classification as in transform_row_packed (DPX 16x2 minima on the biased lanes).
+constexpr int kX2Chunks = 14;
+constexpr size_t kX2TabBytes = (size_t)kZ2Count * kX2Chunks * kXRep * 16;
+
+__device__ __forceinline__ void ystage_count2(int X0, int X1, int r0, int r1, unsigned kz, unsigned kp, unsigned km, unsigned& accZ, unsigned& accD) {
+  int t, w;
+  asm("mad.lo.s32 %0, %1, %2, 0x80008000;" : "=r"(t) : "r"(X0), "r"(r0));
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(w) : "r"(X1), "r"(r1), "r"(t));
+  accZ += __vimin3_u16x2((unsigned)w ^ kz, 0x00010001u, 0x00010001u);
+  accD += __vimin3_u16x2((unsigned)w ^ kp, (unsigned)w ^ km, 0x00010001u);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kXThreads, 2) orbit_sweep2x_kernel(int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
+                                                                      Key* __restrict__ block_best) {
+  constexpr int RU = 7;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  int4* tab = reinterpret_cast<int4*>(dyn_smem);
+  __shared__ Key red[32];
+  const int* Lc = c_lrp;
+  const int* Rc = Lc + RU * 4;
+  const int* Pc = Rc + RU * 4;
+  for (int t = threadIdx.x; t < kZ2Count * kXRep; t += kXThreads) {
+    const int e = t / kXRep, c = t % kXRep;
+    RawDigits<MODE> ds((uint32_t)e, (uint32_t)kZ2Count);
+    const Zoi z = decode_zoi<2, MODE, RawDigits<MODE>>(ds);
+    int Mx[4], Mi[4], pit[2], pm[2], pi[2];
+    expand_zoi<2, false>(z, Mx, nullptr, 0);
+    expand_zoi<2, true>(z, Mi, nullptr, 0);
+    pack_left<2, true>(Mi, pit);
+    pack_left<2, false>(Mx, pm);
+    pack_left<2, false>(Mi, pi);
+    int4* ent = tab + (size_t)e * kX2Chunks * kXRep + c;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int xl[4], xp[4], xr[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int l = 2 * q + h;
+          xl[2 * h + j] = l < RU ? pit[0] * Lc[l * 4 + j] + pit[1] * Lc[l * 4 + 2 + j] : 0;
+          xp[2 * h + j] = l < RU ? pm[0] * Pc[l * 4 + j] + pm[1] * Pc[l * 4 + 2 + j] : 0;
+          xr[2 * h + j] = l < RU ? pi[0] * Rc[l * 4 + j] + pi[1] * Rc[l * 4 + 2 + j] : 0;
+        }
+      ent[(0 + q) * kXRep] = make_int4(xl[0], xl[1], xl[2], xl[3]);
+      ent[(4 + q) * kXRep] = make_int4(xp[0], xp[1], xp[2], xp[3]);
+      ent[(8 + q) * kXRep] = make_int4(xr[0], xr[1], xr[2], xr[3]);
+    }
+    ent[12 * kXRep] = make_int4(Mx[0], Mx[1], Mx[2], Mx[3]);
+    ent[13 * kXRep] = make_int4(Mi[0], Mi[1], Mi[2], Mi[3]);
+  }
+  __syncthreads();
+  const uint32_t mytab = (uint32_t)__cvta_generic_to_shared(tab + (threadIdx.x % kXRep));
+  constexpr uint32_t kEnt = kX2Chunks * kXRep * 16, kChunk = kXRep * 16;
+  const unsigned kz = 0x80008000u;
+  const unsigned dL = (unsigned)den.x * 0x00010001u, dR = (unsigned)den.y * 0x00010001u, dP = (unsigned)den.z * 0x00010001u;
+  const unsigned long long stride = (unsigned long long)gridDim.x * kXThreads;
+  Key best;
+  best.primary = ~0ull; best.index = ~0ull;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kXThreads + threadIdx.x; idx < hi; idx += stride) {
+    Digits<MODE> ds(seed, idx);
+    const uint32_t tu = mytab + ds.matrix_index(kZ2Count) * kEnt;
+    const uint32_t tv = mytab + ds.matrix_index(kZ2Count) * kEnt;
+    const uint32_t tw = mytab + ds.matrix_index(kZ2Count) * kEnt;
+    const int4 V = lds_v4(tv + 12 * kChunk), W = lds_v4(tw + 12 * kChunk), Wi = lds_v4(tw + 13 * kChunk);
+    unsigned accZ = 0, accD = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int4 xl = lds_v4(tu + q * kChunk), xp = lds_v4(tu + (4 + q) * kChunk), xr = lds_v4(tv + (8 + q) * kChunk);
+      // row 2q
+      ystage_count2(xl.x, xl.y, V.x, V.z, kz, kz + dL, kz - dL, accZ, accD);
+      ystage_count2(xl.x, xl.y, V.y, V.w, kz, kz + dL, kz - dL, accZ, accD);
+      ystage_count2(xr.x, xr.y, W.x, W.z, kz, kz + dR, kz - dR, accZ, accD);
+      ystage_count2(xr.x, xr.y, W.y, W.w, kz, kz + dR, kz - dR, accZ, accD);
+      ystage_count2(xp.x, xp.y, Wi.x, Wi.y, kz, kz + dP, kz - dP, accZ, accD);
+      ystage_count2(xp.x, xp.y, Wi.z, Wi.w, kz, kz + dP, kz - dP, accZ, accD);
+      if (2 * q + 1 < RU) {  // row 2q+1
+        ystage_count2(xl.z, xl.w, V.x, V.z, kz, kz + dL, kz - dL, accZ, accD);
+        ystage_count2(xl.z, xl.w, V.y, V.w, kz, kz + dL, kz - dL, accZ, accD);
+        ystage_count2(xr.z, xr.w, W.x, W.z, kz, kz + dR, kz - dR, accZ, accD);
+        ystage_count2(xr.z, xr.w, W.y, W.w, kz, kz + dR, kz - dR, accZ, accD);
+        ystage_count2(xp.z, xp.w, Wi.x, Wi.y, kz, kz + dP, kz - dP, accZ, accD);
+        ystage_count2(xp.z, xp.w, Wi.z, Wi.w, kz, kz + dP, kz - dP, accZ, accD);
+      }
+    }
+    // nnz = non-zero lanes; nno = nnz - #(|y| == den) = nnz - (lanes - #(|y| != den)), 12 lanes per row
+    const unsigned z = (accZ & 0xFFFFu) + (accZ >> 16), d = (accD & 0xFFFFu) + (accD >> 16);
+    Key k;
+    k.primary = ((unsigned long long)z << 32) | (unsigned long long)(z - (RU * 12u - d));
+    k.index = idx;
+    if (k.primary < best.primary) best = k;
+  }
+  best = block_min(best, red);
+  if (threadIdx.x == 0) block_best[blockIdx.x] = best;
+}
+
 // ---------------------------------------------------------------------------
 // Wide exact path: int32 inputs whose transforms (or squares) would leave 32 bits -- e.g. 2x2x2_7_DPS-integral-12.0662, common
 // denominators ~10^9.  Both stages of the product are accumulated exactly in 64 bits (|.| < 2^31 . 2^8 . 2^8, as in the modular
@@ -1281,6 +1380,7 @@ struct plo_orbit_plan {
   size_t smem;
   bool pack8;           // four-lane growth-factor kernel
   bool xtab;            // ... with the first product stage from shared-memory tables (2x2x2, r = 7)
+  bool xtab2;           // sparsity twin of it (two 16-bit lanes)
   size_t xsmem;
   std::vector<int> h_lrp2;
   WideLaunch wide;      // non-null: 64-bit exact path (inputs beyond the int32 product bound)
@@ -1450,6 +1550,18 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   pl->grid = sm_count() * (pl->pack8 ? ops->blocks_per_sm8(pl->smem) : ops->blocks_per_sm(measure, pl->lutfull, pl->pack, pl->smem));
   pl->xtab = pl->pack8 && m == 2 && k == 2 && n == 2 && r == 7 && getenv("PLO_ORBIT_NOXTAB") == nullptr;
   pl->xsmem = kXTabBytes + (size_t)pl->lutn * kXLutRep * sizeof(double);
+  pl->xtab2 = !wide && measure == PLO_MEASURE_NNZ && pl->pack && m == 2 && k == 2 && n == 2 && r == 7 && getenv("PLO_ORBIT_NOXTAB") == nullptr;
+  if (pl->xtab2) {
+    int nb = 0;
+    if (cudaFuncSetAttribute(orbit_sweep2x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kX2TabBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(orbit_sweep2x_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kX2TabBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweep2x_kernel<1>, kXThreads, kX2TabBytes) != cudaSuccess || nb < 1) {
+      cudaGetLastError();
+      pl->xtab2 = false;
+    } else {
+      pl->grid = sm_count() * nb;
+    }
+  }
   if (pl->xtab) {
     int nb = 0;
     if (cudaFuncSetAttribute(orbit_sweep8x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->xsmem) != cudaSuccess ||
@@ -1506,6 +1618,9 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   if (pl->xtab) {
     if (pl->mode == 0) orbit_sweep8x_kernel<0><<<pl->grid, kXThreads, pl->xsmem, st>>>(pl->seed, lo, hi, pl->lutn, pl->d_block_best);
     else orbit_sweep8x_kernel<1><<<pl->grid, kXThreads, pl->xsmem, st>>>(pl->seed, lo, hi, pl->lutn, pl->d_block_best);
+  } else if (pl->xtab2) {
+    if (pl->mode == 0) orbit_sweep2x_kernel<0><<<pl->grid, kXThreads, kX2TabBytes, st>>>(pl->den, pl->seed, lo, hi, pl->d_block_best);
+    else orbit_sweep2x_kernel<1><<<pl->grid, kXThreads, kX2TabBytes, st>>>(pl->den, pl->seed, lo, hi, pl->d_block_best);
   } else if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->d_block_best);
   else pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
