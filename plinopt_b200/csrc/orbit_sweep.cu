@@ -354,7 +354,8 @@ __device__ __forceinline__ void transform_row_packed(const int* __restrict__ A, 
         // (a phantom upper lane of an odd last pair is 0: it adds nothing to nnz and 1 to the second count, like every zero).
         const unsigned w = (unsigned)v + 0x80008000u;
         const unsigned d2 = (unsigned)den * 0x00010001u;
-        acc.nnz += (int)__vimin3_u16x2(w ^ 0x80008000u, 0x00010001u, 0x00010001u);
+        const unsigned wz = w ^ 0x80008000u;
+        acc.nnz += (int)__vimin3_u16x2(wz, wz, 0x00010001u);  // (x, x, 1): one immediate only, nothing to materialise
         acc.nno += (int)__vimin3_u16x2(w ^ (0x80008000u + d2), w ^ (0x80008000u - d2), 0x00010001u);
       } else {
         const int hi = (v + 0x8000) >> 16;
@@ -1007,7 +1008,8 @@ __device__ __forceinline__ void ystage_count2(int X0, int X1, int r0, int r1, un
   int t, w;
   asm("mad.lo.s32 %0, %1, %2, 0x80008000;" : "=r"(t) : "r"(X0), "r"(r0));
   asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(w) : "r"(X1), "r"(r1), "r"(t));
-  accZ += __vimin3_u16x2((unsigned)w ^ kz, 0x00010001u, 0x00010001u);
+  const unsigned wz = (unsigned)w ^ kz;
+  accZ += __vimin3_u16x2(wz, wz, 0x00010001u);
   accD += __vimin3_u16x2((unsigned)w ^ kp, (unsigned)w ^ km, 0x00010001u);
 }
 
