@@ -354,8 +354,10 @@ __device__ __forceinline__ void transform_row_packed(const int* __restrict__ A, 
         // (a phantom upper lane of an odd last pair is 0: it adds nothing to nnz and 1 to the second count, like every zero).
         const unsigned w = (unsigned)v + 0x80008000u;
         const unsigned d2 = (unsigned)den * 0x00010001u;
-        const unsigned wz = w ^ 0x80008000u;
-        acc.nnz += (int)__vimin3_u16x2(wz, wz, 0x00010001u);  // (x, x, 1): one immediate only, nothing to materialise
+        // a run-time spelling of 0x00010001 (den > 0): ptxas keeps it in ONE register instead of rematerialising an immediate
+        // for every value (the instruction takes a single immediate)
+        const unsigned k1 = 0x00010001u + ((unsigned)den >> 31);
+        acc.nnz += (int)__viaddmin_u16x2(w, 0x80008000u, k1);  // per-half (w + 0x8000) mod 2^16 = the lane itself; min(lane, 1)
         acc.nno += (int)__vimin3_u16x2(w ^ (0x80008000u + d2), w ^ (0x80008000u - d2), 0x00010001u);
       } else {
         const int hi = (v + 0x8000) >> 16;
@@ -1004,12 +1006,11 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep8x_kernel(unsigned lo
 constexpr int kX2Chunks = 14;
 constexpr size_t kX2TabBytes = (size_t)kZ2Count * kX2Chunks * kXRep * 16;
 
-__device__ __forceinline__ void ystage_count2(int X0, int X1, int r0, int r1, unsigned kz, unsigned kp, unsigned km, unsigned& accZ, unsigned& accD) {
+__device__ __forceinline__ void ystage_count2(int X0, int X1, int r0, int r1, unsigned k1, unsigned kp, unsigned km, unsigned& accZ, unsigned& accD) {
   int t, w;
   asm("mad.lo.s32 %0, %1, %2, 0x80008000;" : "=r"(t) : "r"(X0), "r"(r0));
   asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(w) : "r"(X1), "r"(r1), "r"(t));
-  const unsigned wz = (unsigned)w ^ kz;
-  accZ += __vimin3_u16x2(wz, wz, 0x00010001u);
+  accZ += __viaddmin_u16x2((unsigned)w, 0x80008000u, k1);  // per-half (w + 0x8000) mod 2^16 = the lane; min(lane, 1); k1 = 0x00010001 in a register
   accD += __vimin3_u16x2((unsigned)w ^ kp, (unsigned)w ^ km, 0x00010001u);
 }
 
@@ -1057,6 +1058,7 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep2x_kernel(int3 den, u
   const uint32_t mytab = (uint32_t)__cvta_generic_to_shared(tab + (threadIdx.x % kXRep));
   constexpr uint32_t kEnt = kX2Chunks * kXRep * 16, kChunk = kXRep * 16;
   const unsigned kz = 0x80008000u;
+  const unsigned k1 = 0x00010001u + ((unsigned)den.x >> 31);  // run-time spelling (den > 0): one register, not an immediate per use
   const unsigned dL = (unsigned)den.x * 0x00010001u, dR = (unsigned)den.y * 0x00010001u, dP = (unsigned)den.z * 0x00010001u;
   const unsigned long long stride = (unsigned long long)gridDim.x * kXThreads;
   Key best;
@@ -1072,19 +1074,19 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep2x_kernel(int3 den, u
     for (int q = 0; q < 4; ++q) {
       const int4 xl = lds_v4(tu + q * kChunk), xp = lds_v4(tu + (4 + q) * kChunk), xr = lds_v4(tv + (8 + q) * kChunk);
       // row 2q
-      ystage_count2(xl.x, xl.y, V.x, V.z, kz, kz + dL, kz - dL, accZ, accD);
-      ystage_count2(xl.x, xl.y, V.y, V.w, kz, kz + dL, kz - dL, accZ, accD);
-      ystage_count2(xr.x, xr.y, W.x, W.z, kz, kz + dR, kz - dR, accZ, accD);
-      ystage_count2(xr.x, xr.y, W.y, W.w, kz, kz + dR, kz - dR, accZ, accD);
-      ystage_count2(xp.x, xp.y, Wi.x, Wi.y, kz, kz + dP, kz - dP, accZ, accD);
-      ystage_count2(xp.x, xp.y, Wi.z, Wi.w, kz, kz + dP, kz - dP, accZ, accD);
+      ystage_count2(xl.x, xl.y, V.x, V.z, k1, kz + dL, kz - dL, accZ, accD);
+      ystage_count2(xl.x, xl.y, V.y, V.w, k1, kz + dL, kz - dL, accZ, accD);
+      ystage_count2(xr.x, xr.y, W.x, W.z, k1, kz + dR, kz - dR, accZ, accD);
+      ystage_count2(xr.x, xr.y, W.y, W.w, k1, kz + dR, kz - dR, accZ, accD);
+      ystage_count2(xp.x, xp.y, Wi.x, Wi.y, k1, kz + dP, kz - dP, accZ, accD);
+      ystage_count2(xp.x, xp.y, Wi.z, Wi.w, k1, kz + dP, kz - dP, accZ, accD);
       if (2 * q + 1 < RU) {  // row 2q+1
-        ystage_count2(xl.z, xl.w, V.x, V.z, kz, kz + dL, kz - dL, accZ, accD);
-        ystage_count2(xl.z, xl.w, V.y, V.w, kz, kz + dL, kz - dL, accZ, accD);
-        ystage_count2(xr.z, xr.w, W.x, W.z, kz, kz + dR, kz - dR, accZ, accD);
-        ystage_count2(xr.z, xr.w, W.y, W.w, kz, kz + dR, kz - dR, accZ, accD);
-        ystage_count2(xp.z, xp.w, Wi.x, Wi.y, kz, kz + dP, kz - dP, accZ, accD);
-        ystage_count2(xp.z, xp.w, Wi.z, Wi.w, kz, kz + dP, kz - dP, accZ, accD);
+        ystage_count2(xl.z, xl.w, V.x, V.z, k1, kz + dL, kz - dL, accZ, accD);
+        ystage_count2(xl.z, xl.w, V.y, V.w, k1, kz + dL, kz - dL, accZ, accD);
+        ystage_count2(xr.z, xr.w, W.x, W.z, k1, kz + dR, kz - dR, accZ, accD);
+        ystage_count2(xr.z, xr.w, W.y, W.w, k1, kz + dR, kz - dR, accZ, accD);
+        ystage_count2(xp.z, xp.w, Wi.x, Wi.y, k1, kz + dP, kz - dP, accZ, accD);
+        ystage_count2(xp.z, xp.w, Wi.z, Wi.w, k1, kz + dP, kz - dP, accZ, accD);
       }
     }
     // nnz = non-zero lanes; nno = nnz - #(|y| == den) = nnz - (lanes - #(|y| != den)), 12 lanes per row
