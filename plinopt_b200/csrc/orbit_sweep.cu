@@ -27,7 +27,10 @@ namespace plo {
 constexpr int kMaxDim = 8;           // nibble-packed permutations
 constexpr int kConstInts = 15360;    // 60 KB of constant memory for L | R | P^T
 __constant__ __align__(16) int c_lrp[kConstInts];
-constexpr int kConst2Ints = 1024;   // pairs of rows packed at 8-bit spacing for the four-lane growth-factor kernel
+// Philox round keys of the resident plan's seed (k0 + i.W0, k1 + i.W1, i < 10): loop-invariant, so the table-driven kernels read them
+// as constant-bank operands instead of re-deriving them per candidate.
+__constant__ uint32_t c_pkeys[20];
+constexpr int kConst2Ints = 1000;   // pairs of rows packed at 8-bit spacing for the four-lane growth-factor kernel
 __constant__ __align__(16) int c_lrp2[kConst2Ints];  // int32 entries, or int64 entries (two words each) for the 64-bit input path
 
 constexpr int MEASURE_BOTH = 4;  // internal: nnz, nno and G2 (tables, winner re-evaluation)
@@ -42,7 +45,21 @@ constexpr int MEASURE_BOTH = 4;  // internal: nnz, nno and G2 (tables, winner re
 //           taken from the current word would exceed 2^20.
 // All bookkeeping (R, nwords) is compile-time constant once the loops are unrolled.
 // ---------------------------------------------------------------------------
-template <int MODE>
+#ifdef __CUDACC__
+__device__ __forceinline__ void philox4x32_10_ck(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ c_pkeys[2 * r], n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ c_pkeys[2 * r + 1], n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+#endif
+
+template <int MODE, bool CK = false>
 struct Digits {
   unsigned long long index, seed, rem;
   uint32_t x, R, nwords;
@@ -50,8 +67,13 @@ struct Digits {
   __host__ __device__ __forceinline__ Digits(unsigned long long seed_, unsigned long long index_)
       : index(index_), seed(seed_), rem(index_), x(0), R(0), nwords(0) {}
   __host__ __device__ __forceinline__ void new_word() {
-    if ((nwords & 3u) == 0)
-      philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), nwords >> 2, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+    if ((nwords & 3u) == 0) {
+#ifdef __CUDA_ARCH__
+      if (CK) philox4x32_10_ck((uint32_t)index, (uint32_t)(index >> 32), nwords >> 2, 0u, buf);
+      else
+#endif
+        philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), nwords >> 2, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+    }
     x = buf[nwords & 3u];
     ++nwords;
     R = 1;
@@ -966,7 +988,7 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep8x_kernel(unsigned lo
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kXThreads + threadIdx.x; idx < hi; idx += stride) {
-    Digits<MODE> ds(seed, idx);
+    Digits<MODE, true> ds(seed, idx);
     const uint32_t tu = mytab + ds.matrix_index(kZ2Count) * kEnt;
     const uint32_t tv = mytab + ds.matrix_index(kZ2Count) * kEnt;
     const uint32_t tw = mytab + ds.matrix_index(kZ2Count) * kEnt;
@@ -1064,7 +1086,7 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep2x_kernel(int3 den, u
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kXThreads + threadIdx.x; idx < hi; idx += stride) {
-    Digits<MODE> ds(seed, idx);
+    Digits<MODE, true> ds(seed, idx);
     const uint32_t tu = mytab + ds.matrix_index(kZ2Count) * kEnt;
     const uint32_t tv = mytab + ds.matrix_index(kZ2Count) * kEnt;
     const uint32_t tw = mytab + ds.matrix_index(kZ2Count) * kEnt;
@@ -1385,6 +1407,7 @@ struct plo_orbit_plan {
   bool pack8;           // four-lane growth-factor kernel
   bool xtab;            // ... with the first product stage from shared-memory tables (2x2x2, r = 7)
   bool xtab2;           // sparsity twin of it (two 16-bit lanes)
+  uint32_t h_pkeys[20]; // Philox round keys of `seed`
   size_t xsmem;
   std::vector<int> h_lrp2;
   WideLaunch wide;      // non-null: 64-bit exact path (inputs beyond the int32 product bound)
@@ -1554,6 +1577,10 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   pl->grid = sm_count() * (pl->pack8 ? ops->blocks_per_sm8(pl->smem) : ops->blocks_per_sm(measure, pl->lutfull, pl->pack, pl->smem));
   pl->xtab = pl->pack8 && m == 2 && k == 2 && n == 2 && r == 7 && getenv("PLO_ORBIT_NOXTAB") == nullptr;
   pl->xsmem = kXTabBytes + (size_t)pl->lutn * kXLutRep * sizeof(double);
+  for (int i = 0; i < 10; ++i) {
+    pl->h_pkeys[2 * i] = (uint32_t)seed + (uint32_t)i * 0x9E3779B9u;
+    pl->h_pkeys[2 * i + 1] = (uint32_t)(seed >> 32) + (uint32_t)i * 0xBB67AE85u;
+  }
   pl->xtab2 = !wide && measure == PLO_MEASURE_NNZ && pl->pack && m == 2 && k == 2 && n == 2 && r == 7 && getenv("PLO_ORBIT_NOXTAB") == nullptr;
   if (pl->xtab2) {
     int nb = 0;
@@ -1596,6 +1623,7 @@ static int orbit_upload(plo_orbit_plan* pl, cudaStream_t st) {
   if (const_owner() != pl) {
     PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp, pl->h_lrp.data(), pl->h_lrp.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
     if (pl->pack8) PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp2, pl->h_lrp2.data(), pl->h_lrp2.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    PLO_CUDA(cudaMemcpyToSymbolAsync(c_pkeys, pl->h_pkeys, sizeof(pl->h_pkeys), 0, cudaMemcpyHostToDevice, st));
     const_owner() = pl;
   }
   return PLO_OK;
