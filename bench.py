@@ -28,10 +28,10 @@ WORKLOAD = "orbit sweep of 2x2x2_7_Winograd_{L,R,P}, measure G2 (growthfactor.cp
 INT_OPS_PER_CAND = 336 + 84
 FP64_OPS_PER_CAND = 21 + 14 + 7
 METRIC = "candidates scored/sec"
-NCU_DRAM_BYTES_PER_LAUNCH = 23040  # ncu --set full, profiles/ncu_r01_orbit_sweep.md: 23.0 KB read + 0 B written per launch
+NCU_DRAM_BYTES_PER_LAUNCH = 22784  # ncu --set full, profiles/ncu_r01_orbit_sweep.md: 22.8 KB read + 0 B written per launch
 # issued thread instructions per candidate of orbit_sweep8x_kernel<philox>: smsp__inst_executed.sum x 32 / candidates of the
-# same capture (2 576 819 656 warp instructions for 2^28 candidates)
-NCU_INST_PER_CAND = 2576819656 * 32 / float(1 << 28)
+# same capture (2 434 142 576 warp instructions for 2^28 candidates)
+NCU_INST_PER_CAND = 2434142576 * 32 / float(1 << 28)
 
 
 def env_int(name, default):
@@ -268,7 +268,7 @@ def main():
     if rank == 0:
         clocks = sampler.summary()
         # The kernel carries four 8-bit lanes per IMAD and reads the 2x2 matrices and the first product stage from tables, so it does the
-        # 420 algorithmic int32 operations of a candidate in ~307 issued instructions: the algorithmic rate is ABOVE the scalar IMAD peak, and the limit that
+        # 420 algorithmic int32 operations of a candidate in ~290 issued instructions: the algorithmic rate is ABOVE the scalar IMAD peak, and the limit that
         # binds is the scheduler's issue rate (IMAD/IDP on the fma-heavy pipe + LOP3 on the alu pipe).  frac = issued instructions per
         # second over the live-measured issue peak; the algorithmic view is kept beside it.
         cand_per_s = B / (kern_ms * 1e-3)
@@ -286,6 +286,8 @@ def main():
                 "algorithmic": {"ops_per_candidate": {"int32": INT_OPS_PER_CAND, "fp64": FP64_OPS_PER_CAND}, "achieved_tiops": alg,
                                 "scalar_imad_peak_tiops": peaks["imad_per_s"] / 1e12, "vs_scalar_imad_peak": alg / (peaks["imad_per_s"] / 1e12),
                                 "note": "above 1: one IMAD carries four 8-bit lanes (two rows of the left factor x two Hopcroft-Musinski rows)"},
+                "shared_memory": {"wavefronts_per_warp_candidate": 78, "ncu_pct_of_peak": 78.9,
+                                  "note": "9 LDS.128 + 21 LDS.64 per candidate, bank-conflict free (profiles/ncu_r01_orbit_sweep.md): the busiest unit after the schedulers"},
                 "fp64": {"achieved_tflop": FP64_OPS_PER_CAND * cand_per_s / 1e12, "peak_dfma_tflop": 2 * peaks["dfma_per_s"] / 1e12},
                 "hbm_bytes_per_candidate": 16.0 * plan_grid_bytes(B),
                 "hbm": hbm_view(kern_ms),
