@@ -905,6 +905,94 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned 
 }
 
 // ---------------------------------------------------------------------------
+// Four-lane SPARSITY kernel (same packing as orbit_sweep8_kernel: every transformed entry in [-127, 127], denominators < 128).
+// A word w = v + 0x80808080 holds four biased lanes; VABSDIFF4.U8(w, 0x80808080) is |lane| per byte (<= 127), and for a word a of
+// bytes <= 127 the bytes that differ from a constant c are the bit-7 positions of ((a ^ c) + 0x7f7f7f7f): non-zero lanes with c = 0,
+// lanes with |y| != den with c = den.  The marks are summed as byte counters (LEA.HI: acc + (mask >> 7)), flushed into 32-bit
+// totals by one dp4a per pair of rows (at most 3.ceil(RA/2).CA <= 63 marks per byte between flushes).  Phantom lanes (odd RA, odd r) are
+// zero: they add nothing to nnz and count as "!= den".   nno = nnz - #(|y| == den) = nnz - (lanes - #(|y| != den)).
+// Half the IMADs of the two-lane kernels at the same number of classification instructions per lane.
+// ---------------------------------------------------------------------------
+template <int RA, int CA, bool TR>
+__device__ __forceinline__ void transform_pair_count8(const int* __restrict__ A2, const int* LmP, const int* Rm, unsigned dd, unsigned& cz, unsigned& cd) {
+  int a[RA * CA];
+#pragma unroll
+  for (int e = 0; e < RA * CA; ++e) a[e] = A2[e];
+#pragma unroll
+  for (int xp = 0; xp < (RA + 1) / 2; ++xp) {
+    int X[CA];
+#pragma unroll
+    for (int j = 0; j < CA; ++j) {
+      int s = 0;
+#pragma unroll
+      for (int i = 0; i < RA; ++i) s += LmP[xp * RA + i] * a[i * CA + j];
+      X[j] = s;
+    }
+#pragma unroll
+    for (int y = 0; y < CA; ++y) {
+      int v = 0;
+#pragma unroll
+      for (int j = 0; j < CA; ++j) v += X[j] * (TR ? Rm[y * CA + j] : Rm[j * CA + y]);
+      const unsigned ab = __vabsdiffu4((unsigned)v + 0x80808080u, 0x80808080u);
+      // acc + (mask >> 7) as ONE multiply-high-add (mask . 2^25 >> 32): the fma-heavy pipe has room here, the alu pipe does not
+      asm("mad.hi.u32 %0, %1, 0x02000000, %0;" : "+r"(cz) : "r"((ab + 0x7F7F7F7Fu) & 0x80808080u));
+      asm("mad.hi.u32 %0, %1, 0x02000000, %0;" : "+r"(cd) : "r"(((ab ^ dd) + 0x7F7F7F7Fu) & 0x80808080u));
+    }
+  }
+}
+
+template <int M, int K, int N, int MODE>
+__global__ void __launch_bounds__(kThreads) orbit_sweepn8_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
+                                                                  Key* __restrict__ block_best) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  int* scr0 = reinterpret_cast<int*>(dyn_smem);
+  __shared__ Key red[32];
+  volatile int* scr = scr0 + threadIdx.x;
+  const int npair = (r + 1) / 2;
+  const int* L2 = c_lrp2;
+  const int* R2 = L2 + npair * M * K;
+  const int* P2 = R2 + npair * K * N;
+  const unsigned dL = (unsigned)den.x * 0x01010101u, dR = (unsigned)den.y * 0x01010101u, dP = (unsigned)den.z * 0x01010101u;
+  constexpr int lanes = 4 * (((M + 1) / 2) * K + ((K + 1) / 2) * N + ((M + 1) / 2) * N);  // per pair of rows, phantom lanes included
+  const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+  Key best;
+  best.primary = ~0ull; best.index = ~0ull;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
+    Digits<MODE> ds(seed, idx);
+    const Zoi zu = decode_zoi<M, MODE>(ds);
+    const Zoi zv = decode_zoi<K, MODE>(ds);
+    const Zoi zw = decode_zoi<N, MODE>(ds);
+    int U[M * M], Ui[M * M], V[K * K], Vi[K * K], W[N * N], Wi[N * N];
+    expand_zoi<M, false>(zu, U, scr, kThreads);
+    expand_zoi<M, true>(zu, Ui, scr, kThreads);
+    expand_zoi<K, false>(zv, V, scr, kThreads);
+    expand_zoi<K, true>(zv, Vi, scr, kThreads);
+    expand_zoi<N, false>(zw, W, scr, kThreads);
+    expand_zoi<N, true>(zw, Wi, scr, kThreads);
+    int UiTP[((M + 1) / 2) * M], ViP[((K + 1) / 2) * K], UP[((M + 1) / 2) * M];
+    pack_left<M, true>(Ui, UiTP);
+    pack_left<K, false>(Vi, ViP);
+    pack_left<M, false>(U, UP);
+    unsigned z = 0, d = 0;
+#pragma unroll 1
+    for (int q = 0; q < npair; ++q) {
+      unsigned cz = 0, cd = 0;  // byte counters of this pair of rows
+      transform_pair_count8<M, K, false>(L2 + q * M * K, UiTP, V, dL, cz, cd);   // U^-T A V
+      transform_pair_count8<K, N, false>(R2 + q * K * N, ViP, W, dR, cz, cd);    // V^-1 B W
+      transform_pair_count8<M, N, true>(P2 + q * M * N, UP, Wi, dP, cz, cd);     // U C W^-T
+      z = __dp4a(cz, 0x01010101u, z);
+      d = __dp4a(cd, 0x01010101u, d);
+    }
+    Key k;
+    k.primary = ((unsigned long long)z << 32) | (unsigned long long)(z - ((unsigned)(npair * lanes) - d));
+    k.index = idx;
+    if (k.primary < best.primary) best = k;
+  }
+  best = block_min(best, red);
+  if (threadIdx.x == 0) block_best[blockIdx.x] = best;
+}
+
+// ---------------------------------------------------------------------------
 // 2x2x2, r = 7, four lanes, first product stage from tables.  With only 48 matrices per factor the whole first stage
 // X = pack(U^-T).A_l (resp. pack(V^-1).B_l, pack(U).C_l) depends on ONE matrix number, so each block tabulates it once:
 // entry e = 8 chunks of 16 bytes  [XL q0,q1 | XL q2,q3 | XP .. | XP .. | XR .. | XR .. | M | M^-1]  (XL/XP are read with the number of
@@ -1285,6 +1373,8 @@ struct ShapeOps {
   cudaError_t (*allow_smem)(size_t smem);
   void (*sweep8)(int mode, int grid, size_t smem, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
                  unsigned long long hi, int lutn, Key* bb);  // four-lane growth-factor kernel (small magnitudes)
+  int (*sweepn8)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
+                 Key* bb, bool launch);                      // four-lane sparsity kernel; launch = false: blocks per SM
 };
 
 template <int M, int K, int N, int RU>
@@ -1344,7 +1434,25 @@ struct Shape {
     if (mode == 0) orbit_sweep8_kernel<M, K, N, 0, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, bb);
     else orbit_sweep8_kernel<M, K, N, 1, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, bb);
   }
-  static ShapeOps ops() { return ShapeOps{M, K, N, RU, &sweep, &final, &table, &blocks_per_sm, &blocks_per_sm8, &allow_smem, &sweep8}; }
+  static int sweepn8(int mode, int sms, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
+                     Key* bb, bool launch) {
+    constexpr int d = MaxDim2<M, K, N>::d;
+    const size_t smem = d > 2 ? scratch_bytes : 0;
+    if (!launch) {  // occupancy query: blocks per SM (0 = cannot run)
+      int nb = 0;
+      if (smem > 48 * 1024 && (cudaFuncSetAttribute(orbit_sweepn8_kernel<M, K, N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                               cudaFuncSetAttribute(orbit_sweepn8_kernel<M, K, N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)) {
+        cudaGetLastError();
+        return 0;
+      }
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweepn8_kernel<M, K, N, 1>, kThreads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+      return nb;
+    }
+    if (mode == 0) orbit_sweepn8_kernel<M, K, N, 0><<<sms, kThreads, smem, st>>>(r, den, seed, lo, hi, bb);
+    else orbit_sweepn8_kernel<M, K, N, 1><<<sms, kThreads, smem, st>>>(r, den, seed, lo, hi, bb);
+    return 1;
+  }
+  static ShapeOps ops() { return ShapeOps{M, K, N, RU, &sweep, &final, &table, &blocks_per_sm, &blocks_per_sm8, &allow_smem, &sweep8, &sweepn8}; }
 };
 
 // (m, k, n, unrolled r); r-specialised entries come first, the generic (ru = 0) entry of a shape last
@@ -1407,6 +1515,7 @@ struct plo_orbit_plan {
   bool pack8;           // four-lane growth-factor kernel
   bool xtab;            // ... with the first product stage from shared-memory tables (2x2x2, r = 7)
   bool xtab2;           // sparsity twin of it (two 16-bit lanes)
+  bool packn8;          // four-lane sparsity kernel (small magnitudes, denominators < 128)
   uint32_t h_pkeys[20]; // Philox round keys of `seed`
   size_t xsmem;
   std::vector<int> h_lrp2;
@@ -1552,7 +1661,9 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   const int npair = (r + 1) / 2;
   pl->pack8 = !wide && measure == PLO_MEASURE_G2 && pl->lutfull && lanes8 && pl->pack && (long long)npair * (m * k + k * n + m * n) <= kConst2Ints &&
               getenv("PLO_ORBIT_NOPACK8") == nullptr;
-  if (pl->pack8) {
+  pl->packn8 = !wide && measure == PLO_MEASURE_NNZ && lanes8 && pl->pack && (long long)npair * (m * k + k * n + m * n) <= kConst2Ints &&
+               pl->den.x < 128 && pl->den.y < 128 && pl->den.z < 128 && !(m == 2 && k == 2 && n == 2 && r == 7) && getenv("PLO_ORBIT_NOPACK8") == nullptr;
+  if (pl->pack8 || pl->packn8) {
     pl->h_lrp2.assign((size_t)npair * (m * k + k * n + m * n), 0);
     const int* src = pl->h_lrp.data();
     int* d2 = pl->h_lrp2.data();
@@ -1580,6 +1691,11 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   for (int i = 0; i < 10; ++i) {
     pl->h_pkeys[2 * i] = (uint32_t)seed + (uint32_t)i * 0x9E3779B9u;
     pl->h_pkeys[2 * i + 1] = (uint32_t)(seed >> 32) + (uint32_t)i * 0xBB67AE85u;
+  }
+  if (pl->packn8) {
+    const int nb = ops->sweepn8(mode, 0, nullptr, r, pl->den, seed, 0, 0, nullptr, false);
+    if (nb < 1) pl->packn8 = false;
+    else pl->grid = sm_count() * nb;
   }
   pl->xtab2 = !wide && measure == PLO_MEASURE_NNZ && pl->pack && m == 2 && k == 2 && n == 2 && r == 7 && getenv("PLO_ORBIT_NOXTAB") == nullptr;
   if (pl->xtab2) {
@@ -1622,7 +1738,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
 static int orbit_upload(plo_orbit_plan* pl, cudaStream_t st) {
   if (const_owner() != pl) {
     PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp, pl->h_lrp.data(), pl->h_lrp.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    if (pl->pack8) PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp2, pl->h_lrp2.data(), pl->h_lrp2.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    if (pl->pack8 || pl->packn8) PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp2, pl->h_lrp2.data(), pl->h_lrp2.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
     PLO_CUDA(cudaMemcpyToSymbolAsync(c_pkeys, pl->h_pkeys, sizeof(pl->h_pkeys), 0, cudaMemcpyHostToDevice, st));
     const_owner() = pl;
   }
@@ -1653,7 +1769,8 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   } else if (pl->xtab2) {
     if (pl->mode == 0) orbit_sweep2x_kernel<0><<<pl->grid, kXThreads, kX2TabBytes, st>>>(pl->den, pl->seed, lo, hi, pl->d_block_best);
     else orbit_sweep2x_kernel<1><<<pl->grid, kXThreads, kX2TabBytes, st>>>(pl->den, pl->seed, lo, hi, pl->d_block_best);
-  } else if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->d_block_best);
+  } else if (pl->packn8) pl->ops->sweepn8(pl->mode, pl->grid, st, pl->r, pl->den, pl->seed, lo, hi, pl->d_block_best, true);
+  else if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->d_block_best);
   else pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());
