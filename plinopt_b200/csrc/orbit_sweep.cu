@@ -25,12 +25,12 @@
 namespace plo {
 
 constexpr int kMaxDim = 8;           // nibble-packed permutations
-constexpr int kConstInts = 15360;    // 60 KB of constant memory for L | R | P^T
+constexpr int kConstInts = 12000;    // 48 KB of constant memory for L | R | P^T (shipped maximum: 3843 ints, 7686 as int64)
 __constant__ __align__(16) int c_lrp[kConstInts];
 // Philox round keys of the resident plan's seed (k0 + i.W0, k1 + i.W1, i < 10): loop-invariant, so the table-driven kernels read them
 // as constant-bank operands instead of re-deriving them per candidate.
 __constant__ uint32_t c_pkeys[20];
-constexpr int kConst2Ints = 1000;   // pairs of rows packed at 8-bit spacing for the four-lane growth-factor kernel
+constexpr int kConst2Ints = 4300;   // 17 KB: pairs of rows packed at 8-bit spacing for the four-lane kernels
 __constant__ __align__(16) int c_lrp2[kConst2Ints];  // int32 entries, or int64 entries (two words each) for the 64-bit input path
 
 constexpr int MEASURE_BOTH = 4;  // internal: nnz, nno and G2 (tables, winner re-evaluation)
@@ -834,23 +834,9 @@ __device__ __forceinline__ void transform_pair_packed8(const int* __restrict__ A
   }
 }
 
-template <int M, int K, int N, int MODE, int RU>
-__global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned long long seed, unsigned long long lo, unsigned long long hi, int lutn,
-                                                                 Key* __restrict__ block_best) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  double* lut = reinterpret_cast<double*>(dyn_smem);
-  int* scr0 = reinterpret_cast<int*>(dyn_smem + (size_t)lutn * sizeof(double));
-  __shared__ Key red[32];
-  constexpr bool TAB = M == 2 && K == 2 && N == 2;
-  __shared__ __align__(16) int z2tab[TAB ? kZ2Count * kZ2Stride : 4];
-  if (TAB) build_zoi2_table<MODE>(z2tab);
-  for (int e = threadIdx.x; e < lutn; e += kThreads) lut[e] = sqrt((double)e);
-  __syncthreads();
-  volatile int* scr = scr0 + threadIdx.x;
-  const int npair = RU > 0 ? (RU + 1) / 2 : (r + 1) / 2;
-  const int* L2 = c_lrp2;
-  const int* R2 = L2 + npair * M * K;
-  const int* P2 = R2 + npair * K * N;
+template <int M, int K, int N, int MODE, int RU, bool LF, bool TAB>
+__device__ __forceinline__ Key sweep8_loop(int r, unsigned long long seed, unsigned long long lo, unsigned long long hi, int lutn, const double* lut,
+                                           volatile int* scr, const int* z2tab, int npair, const int* L2, const int* R2, const int* P2) {
   const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
@@ -892,14 +878,39 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned 
       transform_pair_packed8<K, N, false>(R2 + q * K * N, ViP, W, sR0, sR1);    // V^-1 B W
       transform_pair_packed8<M, N, true>(P2 + q * M * N, UP, Wi, sP0, sP1);     // U C W^-T
       // growthfactor.cpp:117-125, rows in order, no FMA contraction
-      g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(lut[sL0], lut[sR0]), lut[sP0]));
-      if (2 * q + 1 < (RU > 0 ? RU : r)) g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(lut[sL1], lut[sR1]), lut[sP1]));
+      // table lookup; a row norm^2 beyond the table (worst-case bound larger than the 4096 entries kept) takes the out-of-line sqrt
+      auto root = [&](int sq) { return (LF || sq < lutn) ? lut[sq] : slow_isqrt(sq); };
+      g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(root(sL0), root(sR0)), root(sP0)));
+      if (2 * q + 1 < (RU > 0 ? RU : r)) g2 = __dadd_rn(g2, __dmul_rn(__dmul_rn(root(sL1), root(sR1)), root(sP1)));
     }
     Key k;
     k.primary = (unsigned long long)__double_as_longlong(g2);
     k.index = idx;
     if (k.primary < best.primary) best = k;
   }
+  return best;
+}
+
+template <int M, int K, int N, int MODE, int RU>
+__global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned long long seed, unsigned long long lo, unsigned long long hi, int lutn, int lutfull,
+                                                                 Key* __restrict__ block_best) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  double* lut = reinterpret_cast<double*>(dyn_smem);
+  int* scr0 = reinterpret_cast<int*>(dyn_smem + (size_t)lutn * sizeof(double));
+  __shared__ Key red[32];
+  constexpr bool TAB = M == 2 && K == 2 && N == 2;
+  __shared__ __align__(16) int z2tab[TAB ? kZ2Count * kZ2Stride : 4];
+  if (TAB) build_zoi2_table<MODE>(z2tab);
+  for (int e = threadIdx.x; e < lutn; e += kThreads) lut[e] = sqrt((double)e);
+  __syncthreads();
+  volatile int* scr = scr0 + threadIdx.x;
+  const int npair = RU > 0 ? (RU + 1) / 2 : (r + 1) / 2;
+  const int* L2 = c_lrp2;
+  const int* R2 = L2 + npair * M * K;
+  const int* P2 = R2 + npair * K * N;
+  Key best;
+  if (lutfull) best = sweep8_loop<M, K, N, MODE, RU, true, TAB>(r, seed, lo, hi, lutn, lut, scr, z2tab, npair, L2, R2, P2);
+  else best = sweep8_loop<M, K, N, MODE, RU, false, TAB>(r, seed, lo, hi, lutn, lut, scr, z2tab, npair, L2, R2, P2);
   best = block_min(best, red);
   if (threadIdx.x == 0) block_best[blockIdx.x] = best;
 }
@@ -1372,7 +1383,7 @@ struct ShapeOps {
   int (*blocks_per_sm8)(size_t smem);
   cudaError_t (*allow_smem)(size_t smem);
   void (*sweep8)(int mode, int grid, size_t smem, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
-                 unsigned long long hi, int lutn, Key* bb);  // four-lane growth-factor kernel (small magnitudes)
+                 unsigned long long hi, int lutn, bool lutfull, Key* bb);  // four-lane growth-factor kernel (small magnitudes)
   int (*sweepn8)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
                  Key* bb, bool launch);                      // four-lane sparsity kernel; launch = false: blocks per SM
 };
@@ -1430,9 +1441,9 @@ struct Shape {
     return e;
   }
   static void sweep8(int mode, int grid, size_t smem, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
-                     unsigned long long hi, int lutn, Key* bb) {
-    if (mode == 0) orbit_sweep8_kernel<M, K, N, 0, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, bb);
-    else orbit_sweep8_kernel<M, K, N, 1, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, bb);
+                     unsigned long long hi, int lutn, bool lutfull, Key* bb) {
+    if (mode == 0) orbit_sweep8_kernel<M, K, N, 0, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, (int)lutfull, bb);
+    else orbit_sweep8_kernel<M, K, N, 1, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, (int)lutfull, bb);
   }
   static int sweepn8(int mode, int sms, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
                      Key* bb, bool launch) {
@@ -1659,7 +1670,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
   if (wide) { pl->lutn = 0; pl->lutfull = false; pl->pack = false; }
   // four-lane kernel: growth factor only, every row norm^2 inside the sqrt table, pairs of rows packed at 8-bit spacing
   const int npair = (r + 1) / 2;
-  pl->pack8 = !wide && measure == PLO_MEASURE_G2 && pl->lutfull && lanes8 && pl->pack && (long long)npair * (m * k + k * n + m * n) <= kConst2Ints &&
+  pl->pack8 = !wide && measure == PLO_MEASURE_G2 && lanes8 && pl->pack && (long long)npair * (m * k + k * n + m * n) <= kConst2Ints &&
               getenv("PLO_ORBIT_NOPACK8") == nullptr;
   pl->packn8 = !wide && measure == PLO_MEASURE_NNZ && lanes8 && pl->pack && (long long)npair * (m * k + k * n + m * n) <= kConst2Ints &&
                pl->den.x < 128 && pl->den.y < 128 && pl->den.z < 128 && !(m == 2 && k == 2 && n == 2 && r == 7) && getenv("PLO_ORBIT_NOPACK8") == nullptr;
@@ -1686,7 +1697,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
     return PLO_E_CUDA;
   }
   pl->grid = sm_count() * (pl->pack8 ? ops->blocks_per_sm8(pl->smem) : ops->blocks_per_sm(measure, pl->lutfull, pl->pack, pl->smem));
-  pl->xtab = pl->pack8 && m == 2 && k == 2 && n == 2 && r == 7 && getenv("PLO_ORBIT_NOXTAB") == nullptr;
+  pl->xtab = pl->pack8 && pl->lutfull && m == 2 && k == 2 && n == 2 && r == 7 && getenv("PLO_ORBIT_NOXTAB") == nullptr;
   pl->xsmem = kXTabBytes + (size_t)pl->lutn * kXLutRep * sizeof(double);
   for (int i = 0; i < 10; ++i) {
     pl->h_pkeys[2 * i] = (uint32_t)seed + (uint32_t)i * 0x9E3779B9u;
@@ -1770,7 +1781,7 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
     if (pl->mode == 0) orbit_sweep2x_kernel<0><<<pl->grid, kXThreads, kX2TabBytes, st>>>(pl->den, pl->seed, lo, hi, pl->d_block_best);
     else orbit_sweep2x_kernel<1><<<pl->grid, kXThreads, kX2TabBytes, st>>>(pl->den, pl->seed, lo, hi, pl->d_block_best);
   } else if (pl->packn8) pl->ops->sweepn8(pl->mode, pl->grid, st, pl->r, pl->den, pl->seed, lo, hi, pl->d_block_best, true);
-  else if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->d_block_best);
+  else if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->d_block_best);
   else pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());

@@ -110,7 +110,7 @@ def lincomb_c5_case(peaks):
 
 def orbit_cases(peaks):
     """Orbit sweep (src/orbiter.cpp:272-324) on every instantiated shape, both measures; ops per candidate as in SURVEY.md 8d."""
-    cases = [("2x2x2_7_Winograd", 28), ("3x3x3_23_58", 24), ("4x4x4_48_rational", 22), ("3x4x7_63_rational", 21)]
+    cases = [("2x2x2_7_Winograd", 28), ("3x3x3_23_58", 24), ("4x4x4_49_156", 22), ("4x4x4_48_rational", 22), ("3x4x7_63_rational", 21)]
     for stem, lg in cases:
         L, R, P = hm.load_fixture(stem)
         mkn = hm.LRP2MM(L, R, P)
