@@ -163,6 +163,9 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
 int plo_orbit_plan_run(plo_orbit_plan* plan, uint64_t lo, uint64_t hi, void* stream);
 int plo_orbit_plan_result(plo_orbit_plan* plan, void* stream, plo_orbit_best* best);
 int plo_orbit_plan_launches(const plo_orbit_plan* plan);
+/* Host-only self-test (no device needed) of the whole-matrix decode behind the table-driven 2x2x2 kernels: number of mismatches
+ * between digit-by-digit decoding and replaying matrix number floor(x.count/2^32) resp. rem mod count; 0 = consistent. */
+int plo_selftest_matrix_index(void);
 /* Survivor compaction (north_star: "surviving candidates are compacted through coalesced vectorised stores"): every candidate of
  * [lo,hi) whose score does not exceed `threshold` -- sparsity plans: (nnz, nno) <= (threshold->nnz, threshold->nno)
  * lexicographically (the order of src/orbiter.cpp:300-312); growth-factor plans: G2 <= threshold->score -- is returned with BOTH

@@ -26,7 +26,7 @@ SYMBOLS = [
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
-    "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_survivors", "plo_orbit_plan_destroy",
+    "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_survivors", "plo_selftest_matrix_index", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
     "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",

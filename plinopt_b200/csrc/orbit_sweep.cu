@@ -1507,6 +1507,34 @@ static const void*& const_owner() {
   return g_const_owner_dev[(d >= 0 && d < kMaxDevices) ? d : 0];
 }
 
+// Host-only self-test of the "whole matrix from one number" decode the table-driven kernels rely on (no device needed): for S = 2
+// (48 matrices) and S = 3 (7776), drawing the digits of a matrix one by one from a word x gives the same matrix as replaying matrix
+// number floor(x . count / 2^32) (Philox mode) resp. rem mod count (exhaustive mode).  Returns the number of mismatches.
+template <int S, int COUNT>
+static int matrix_index_mismatches() {
+  int bad = 0;
+  auto same = [](const Zoi& a, const Zoi& b) { return a.pP == b.pP && a.pQ == b.pQ && a.D == b.D && a.T == b.T; };
+  for (uint32_t e = 0; e < (uint32_t)COUNT; ++e) {
+    // the first, the last and a middle word of the slice of 2^32 that maps to e
+    const uint32_t x0 = (uint32_t)((((unsigned long long)e << 32) + COUNT - 1) / COUNT);
+    const uint32_t x1 = (uint32_t)(((((unsigned long long)e + 1) << 32) + COUNT - 1) / COUNT - 1);
+    const uint32_t xs[3] = {x0, x1, x0 + (x1 - x0) / 2};
+    RawDigits<1> ref(e, COUNT);
+    const Zoi zr = decode_zoi<S, 1, RawDigits<1>>(ref);
+    for (uint32_t x : xs) {
+      if ((uint32_t)(((unsigned long long)x * COUNT) >> 32) != e) { ++bad; continue; }
+      RawDigits<1> d(0, COUNT);
+      d.x = x;
+      if (!same(decode_zoi<S, 1, RawDigits<1>>(d), zr)) ++bad;
+    }
+    RawDigits<0> ref0(e, COUNT);
+    const Zoi z0 = decode_zoi<S, 0, RawDigits<0>>(ref0);
+    RawDigits<0> d0(0, COUNT);
+    d0.rem = (unsigned long long)e + 5ull * COUNT;  // a larger running remainder: only rem mod count may matter
+    if (!same(decode_zoi<S, 0, RawDigits<0>>(d0), z0)) ++bad;
+  }
+  return bad;
+}
 }  // namespace plo
 
 using namespace plo;
@@ -1787,6 +1815,8 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   PLO_CUDA(cudaGetLastError());
   return PLO_OK;
 }
+
+int plo_selftest_matrix_index(void) { return matrix_index_mismatches<2, 48>() + matrix_index_mismatches<3, 7776>(); }
 
 int plo_orbit_plan_launches(const plo_orbit_plan*) { return 2; }
 

@@ -78,3 +78,13 @@ def test_argument_errors():
     with pytest.raises(capi.PloError) as e:
         capi.orbit_decode(9, 2, 2, 1, 0, 0)
     assert e.value.code == capi.E_ARG
+
+
+def test_whole_matrix_decode_selftest():
+    """Host-only: the table-driven kernels index a 2x2 (48) or 3x3 (7776) zoi matrix by ONE number per factor; the library checks that
+    this numbering reproduces the digit-by-digit decode in both enumeration modes (no device needed)."""
+    import ctypes
+    from plinopt_b200 import capi
+    f = capi.lib().plo_selftest_matrix_index
+    f.restype = ctypes.c_int
+    assert f() == 0
