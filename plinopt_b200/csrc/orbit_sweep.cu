@@ -834,9 +834,57 @@ __device__ __forceinline__ void transform_pair_packed8(const int* __restrict__ A
   }
 }
 
+// 3x3 zoi matrices: 6.6.8.27 = 7776 per factor -- too many for shared memory, but one table per plan in global memory (1.5 MB,
+// L2-resident) still replaces decode + expansion + inverse + packing (~450 instructions per candidate) by 15 128-bit loads.
+// Entry = 12 chunks of 16 bytes: M (9 ints, 3 chunks) | M^-1 (3) | pack_left<T>(M^-1) (6 ints, 2) | pack_left(M) (2) | pack_left(M^-1) (2).
+constexpr int kZ3Count = 7776, kZ3Chunks = 12;
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) zoi3_table_kernel(int4* __restrict__ tab) {
+  __shared__ int scr0[9 * kThreads];
+  const int e = blockIdx.x * kThreads + threadIdx.x;
+  if (e >= kZ3Count) return;
+  volatile int* scr = scr0 + threadIdx.x;
+  RawDigits<MODE> ds((uint32_t)e, (uint32_t)kZ3Count);
+  const Zoi z = decode_zoi<3, MODE, RawDigits<MODE>>(ds);
+  int Mx[9], Mi[9], pit[6], pm[6], pi[6];
+  expand_zoi<3, false>(z, Mx, scr, kThreads);
+  expand_zoi<3, true>(z, Mi, scr, kThreads);
+  pack_left<3, true>(Mi, pit);
+  pack_left<3, false>(Mx, pm);
+  pack_left<3, false>(Mi, pi);
+  int4* t = tab + (size_t)e * kZ3Chunks;
+  t[0] = make_int4(Mx[0], Mx[1], Mx[2], Mx[3]); t[1] = make_int4(Mx[4], Mx[5], Mx[6], Mx[7]); t[2] = make_int4(Mx[8], 0, 0, 0);
+  t[3] = make_int4(Mi[0], Mi[1], Mi[2], Mi[3]); t[4] = make_int4(Mi[4], Mi[5], Mi[6], Mi[7]); t[5] = make_int4(Mi[8], 0, 0, 0);
+  t[6] = make_int4(pit[0], pit[1], pit[2], pit[3]); t[7] = make_int4(pit[4], pit[5], 0, 0);
+  t[8] = make_int4(pm[0], pm[1], pm[2], pm[3]); t[9] = make_int4(pm[4], pm[5], 0, 0);
+  t[10] = make_int4(pi[0], pi[1], pi[2], pi[3]); t[11] = make_int4(pi[4], pi[5], 0, 0);
+}
+__device__ __forceinline__ void z3_load9(const int4* t, int* out) {
+  const int4 a = __ldg(t), b = __ldg(t + 1), c = __ldg(t + 2);
+  out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w; out[8] = c.x;
+}
+__device__ __forceinline__ void z3_load6(const int4* t, int* out) {
+  const int4 a = __ldg(t), b = __ldg(t + 1);
+  out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y;
+}
+// all a candidate of a 3x3x3 sweep needs from the table: pack(U^-T), pack(U), V, pack(V^-1), W, W^-1
+template <int MODE>
+__device__ __forceinline__ void z3_candidate(const int4* __restrict__ z3tab, Digits<MODE>& ds, int* UiTP, int* UP, int* V, int* ViP, int* W, int* Wi) {
+  const int4* tu = z3tab + (size_t)ds.matrix_index(kZ3Count) * kZ3Chunks;
+  const int4* tv = z3tab + (size_t)ds.matrix_index(kZ3Count) * kZ3Chunks;
+  const int4* tw = z3tab + (size_t)ds.matrix_index(kZ3Count) * kZ3Chunks;
+  z3_load6(tu + 6, UiTP);
+  z3_load6(tu + 8, UP);
+  z3_load9(tv, V);
+  z3_load6(tv + 10, ViP);
+  z3_load9(tw, W);
+  z3_load9(tw + 3, Wi);
+}
+
 template <int M, int K, int N, int MODE, int RU, bool LF, bool TAB>
 __device__ __forceinline__ Key sweep8_loop(int r, unsigned long long seed, unsigned long long lo, unsigned long long hi, int lutn, const double* lut,
-                                           volatile int* scr, const int* z2tab, int npair, const int* L2, const int* R2, const int* P2) {
+                                           volatile int* scr, const int* z2tab, int npair, const int* L2, const int* R2, const int* P2,
+                                           const int4* __restrict__ z3tab) {
   const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
@@ -855,6 +903,8 @@ __device__ __forceinline__ Key sweep8_loop(int r, unsigned long long seed, unsig
       z2_load2(tv + 12, ViP);
       z2_load4(tw, W);
       z2_load4(tw + 4, Wi);
+    } else if (M == 3 && K == 3 && N == 3 && z3tab != nullptr) {
+      z3_candidate<MODE>(z3tab, ds, UiTP, UP, V, ViP, W, Wi);
     } else {
       const Zoi zu = decode_zoi<M, MODE>(ds);
       const Zoi zv = decode_zoi<K, MODE>(ds);
@@ -893,7 +943,7 @@ __device__ __forceinline__ Key sweep8_loop(int r, unsigned long long seed, unsig
 
 template <int M, int K, int N, int MODE, int RU>
 __global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned long long seed, unsigned long long lo, unsigned long long hi, int lutn, int lutfull,
-                                                                 Key* __restrict__ block_best) {
+                                                                 Key* __restrict__ block_best, const int4* __restrict__ z3tab) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double* lut = reinterpret_cast<double*>(dyn_smem);
   int* scr0 = reinterpret_cast<int*>(dyn_smem + (size_t)lutn * sizeof(double));
@@ -909,8 +959,8 @@ __global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned 
   const int* R2 = L2 + npair * M * K;
   const int* P2 = R2 + npair * K * N;
   Key best;
-  if (lutfull) best = sweep8_loop<M, K, N, MODE, RU, true, TAB>(r, seed, lo, hi, lutn, lut, scr, z2tab, npair, L2, R2, P2);
-  else best = sweep8_loop<M, K, N, MODE, RU, false, TAB>(r, seed, lo, hi, lutn, lut, scr, z2tab, npair, L2, R2, P2);
+  if (lutfull) best = sweep8_loop<M, K, N, MODE, RU, true, TAB>(r, seed, lo, hi, lutn, lut, scr, z2tab, npair, L2, R2, P2, z3tab);
+  else best = sweep8_loop<M, K, N, MODE, RU, false, TAB>(r, seed, lo, hi, lutn, lut, scr, z2tab, npair, L2, R2, P2, z3tab);
   best = block_min(best, red);
   if (threadIdx.x == 0) block_best[blockIdx.x] = best;
 }
@@ -954,7 +1004,7 @@ __device__ __forceinline__ void transform_pair_count8(const int* __restrict__ A2
 
 template <int M, int K, int N, int MODE>
 __global__ void __launch_bounds__(kThreads) orbit_sweepn8_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
-                                                                  Key* __restrict__ block_best) {
+                                                                  Key* __restrict__ block_best, const int4* __restrict__ z3tab) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   int* scr0 = reinterpret_cast<int*>(dyn_smem);
   __shared__ Key red[32];
@@ -970,20 +1020,25 @@ __global__ void __launch_bounds__(kThreads) orbit_sweepn8_kernel(int r, int3 den
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
     Digits<MODE> ds(seed, idx);
-    const Zoi zu = decode_zoi<M, MODE>(ds);
-    const Zoi zv = decode_zoi<K, MODE>(ds);
-    const Zoi zw = decode_zoi<N, MODE>(ds);
-    int U[M * M], Ui[M * M], V[K * K], Vi[K * K], W[N * N], Wi[N * N];
-    expand_zoi<M, false>(zu, U, scr, kThreads);
-    expand_zoi<M, true>(zu, Ui, scr, kThreads);
-    expand_zoi<K, false>(zv, V, scr, kThreads);
-    expand_zoi<K, true>(zv, Vi, scr, kThreads);
-    expand_zoi<N, false>(zw, W, scr, kThreads);
-    expand_zoi<N, true>(zw, Wi, scr, kThreads);
+    int V[K * K], W[N * N], Wi[N * N];
     int UiTP[((M + 1) / 2) * M], ViP[((K + 1) / 2) * K], UP[((M + 1) / 2) * M];
-    pack_left<M, true>(Ui, UiTP);
-    pack_left<K, false>(Vi, ViP);
-    pack_left<M, false>(U, UP);
+    if (M == 3 && K == 3 && N == 3 && z3tab != nullptr) {
+      z3_candidate<MODE>(z3tab, ds, UiTP, UP, V, ViP, W, Wi);
+    } else {
+      const Zoi zu = decode_zoi<M, MODE>(ds);
+      const Zoi zv = decode_zoi<K, MODE>(ds);
+      const Zoi zw = decode_zoi<N, MODE>(ds);
+      int U[M * M], Ui[M * M], Vi[K * K];
+      expand_zoi<M, false>(zu, U, scr, kThreads);
+      expand_zoi<M, true>(zu, Ui, scr, kThreads);
+      expand_zoi<K, false>(zv, V, scr, kThreads);
+      expand_zoi<K, true>(zv, Vi, scr, kThreads);
+      expand_zoi<N, false>(zw, W, scr, kThreads);
+      expand_zoi<N, true>(zw, Wi, scr, kThreads);
+      pack_left<M, true>(Ui, UiTP);
+      pack_left<K, false>(Vi, ViP);
+      pack_left<M, false>(U, UP);
+    }
     unsigned z = 0, d = 0;
 #pragma unroll 1
     for (int q = 0; q < npair; ++q) {
@@ -1383,9 +1438,9 @@ struct ShapeOps {
   int (*blocks_per_sm8)(size_t smem);
   cudaError_t (*allow_smem)(size_t smem);
   void (*sweep8)(int mode, int grid, size_t smem, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
-                 unsigned long long hi, int lutn, bool lutfull, Key* bb);  // four-lane growth-factor kernel (small magnitudes)
+                 unsigned long long hi, int lutn, bool lutfull, Key* bb, const int4* z3tab);  // four-lane growth-factor kernel (small magnitudes)
   int (*sweepn8)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
-                 Key* bb, bool launch);                      // four-lane sparsity kernel; launch = false: blocks per SM
+                 Key* bb, const int4* z3tab, bool launch);                      // four-lane sparsity kernel; launch = false: blocks per SM
 };
 
 template <int M, int K, int N, int RU>
@@ -1441,12 +1496,12 @@ struct Shape {
     return e;
   }
   static void sweep8(int mode, int grid, size_t smem, cudaStream_t st, int r, unsigned long long seed, unsigned long long lo,
-                     unsigned long long hi, int lutn, bool lutfull, Key* bb) {
-    if (mode == 0) orbit_sweep8_kernel<M, K, N, 0, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, (int)lutfull, bb);
-    else orbit_sweep8_kernel<M, K, N, 1, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, (int)lutfull, bb);
+                     unsigned long long hi, int lutn, bool lutfull, Key* bb, const int4* z3tab) {
+    if (mode == 0) orbit_sweep8_kernel<M, K, N, 0, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, (int)lutfull, bb, z3tab);
+    else orbit_sweep8_kernel<M, K, N, 1, RU><<<grid, kThreads, smem, st>>>(r, seed, lo, hi, lutn, (int)lutfull, bb, z3tab);
   }
   static int sweepn8(int mode, int sms, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
-                     Key* bb, bool launch) {
+                     Key* bb, const int4* z3tab, bool launch) {
     constexpr int d = MaxDim2<M, K, N>::d;
     const size_t smem = d > 2 ? scratch_bytes : 0;
     if (!launch) {  // occupancy query: blocks per SM (0 = cannot run)
@@ -1459,8 +1514,8 @@ struct Shape {
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, orbit_sweepn8_kernel<M, K, N, 1>, kThreads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
       return nb;
     }
-    if (mode == 0) orbit_sweepn8_kernel<M, K, N, 0><<<sms, kThreads, smem, st>>>(r, den, seed, lo, hi, bb);
-    else orbit_sweepn8_kernel<M, K, N, 1><<<sms, kThreads, smem, st>>>(r, den, seed, lo, hi, bb);
+    if (mode == 0) orbit_sweepn8_kernel<M, K, N, 0><<<sms, kThreads, smem, st>>>(r, den, seed, lo, hi, bb, z3tab);
+    else orbit_sweepn8_kernel<M, K, N, 1><<<sms, kThreads, smem, st>>>(r, den, seed, lo, hi, bb, z3tab);
     return 1;
   }
   static ShapeOps ops() { return ShapeOps{M, K, N, RU, &sweep, &final, &table, &blocks_per_sm, &blocks_per_sm8, &allow_smem, &sweep8, &sweepn8}; }
@@ -1555,6 +1610,7 @@ struct plo_orbit_plan {
   bool xtab;            // ... with the first product stage from shared-memory tables (2x2x2, r = 7)
   bool xtab2;           // sparsity twin of it (two 16-bit lanes)
   bool packn8;          // four-lane sparsity kernel (small magnitudes, denominators < 128)
+  int4* d_z3tab;        // 3x3x3 with a four-lane kernel: the 7776 zoi matrices of a factor, ready to use (1.5 MB, L2-resident)
   uint32_t h_pkeys[20]; // Philox round keys of `seed`
   size_t xsmem;
   std::vector<int> h_lrp2;
@@ -1678,7 +1734,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
     smax = 0; lanes16 = false; lanes8 = false;
   }
   plo_orbit_plan* pl = new plo_orbit_plan();
-  pl->wide = wide; pl->d_wide_cnt = nullptr; pl->d_wide_g2 = nullptr;
+  pl->wide = wide; pl->d_wide_cnt = nullptr; pl->d_wide_g2 = nullptr; pl->d_z3tab = nullptr;
   pl->inv_den3 = make_double3(1.0 / std::fabs((double)denL), 1.0 / std::fabs((double)denR), 1.0 / std::fabs((double)denP));
   pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->measure = measure; pl->mode = mode; pl->seed = seed;
   pl->inv_den = 1.0 / ((double)denL * (double)denR * (double)denP);
@@ -1732,7 +1788,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
     pl->h_pkeys[2 * i + 1] = (uint32_t)(seed >> 32) + (uint32_t)i * 0xBB67AE85u;
   }
   if (pl->packn8) {
-    const int nb = ops->sweepn8(mode, 0, nullptr, r, pl->den, seed, 0, 0, nullptr, false);
+    const int nb = ops->sweepn8(mode, 0, nullptr, r, pl->den, seed, 0, 0, nullptr, nullptr, false);
     if (nb < 1) pl->packn8 = false;
     else pl->grid = sm_count() * nb;
   }
@@ -1764,6 +1820,18 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
     set_error("orbit sweep: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     plo_orbit_plan_destroy(pl);
     return PLO_E_CUDA;
+  }
+  if ((pl->pack8 || pl->packn8) && m == 3 && k == 3 && n == 3 && getenv("PLO_ORBIT_NOTAB3") == nullptr) {
+    // built once per plan, on the default stream (plan creation is synchronous); without it the kernels decode per candidate
+    if (pool_alloc(&pl->d_z3tab, (size_t)kZ3Count * kZ3Chunks * sizeof(int4)) == cudaSuccess) {
+      const int nb = (kZ3Count + kThreads - 1) / kThreads;
+      if (mode == 0) zoi3_table_kernel<0><<<nb, kThreads>>>(pl->d_z3tab);
+      else zoi3_table_kernel<1><<<nb, kThreads>>>(pl->d_z3tab);
+      if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); pool_free(pl->d_z3tab); pl->d_z3tab = nullptr; }
+    } else {
+      cudaGetLastError();
+      pl->d_z3tab = nullptr;
+    }
   }
   if (wide && (pool_alloc(&pl->d_wide_cnt, 8) != cudaSuccess || pool_alloc(&pl->d_wide_g2, 8) != cudaSuccess)) {
     set_error("orbit sweep: device allocation failed");
@@ -1808,8 +1876,8 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   } else if (pl->xtab2) {
     if (pl->mode == 0) orbit_sweep2x_kernel<0><<<pl->grid, kXThreads, kX2TabBytes, st>>>(pl->den, pl->seed, lo, hi, pl->d_block_best);
     else orbit_sweep2x_kernel<1><<<pl->grid, kXThreads, kX2TabBytes, st>>>(pl->den, pl->seed, lo, hi, pl->d_block_best);
-  } else if (pl->packn8) pl->ops->sweepn8(pl->mode, pl->grid, st, pl->r, pl->den, pl->seed, lo, hi, pl->d_block_best, true);
-  else if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->d_block_best);
+  } else if (pl->packn8) pl->ops->sweepn8(pl->mode, pl->grid, st, pl->r, pl->den, pl->seed, lo, hi, pl->d_block_best, pl->d_z3tab, true);
+  else if (pl->pack8) pl->ops->sweep8(pl->mode, pl->grid, pl->smem, st, pl->r, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->d_block_best, pl->d_z3tab);
   else pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());
@@ -1853,7 +1921,7 @@ void plo_orbit_plan_destroy(plo_orbit_plan* pl) {
   for (int d = 0; d < kMaxDevices; ++d) if (g_const_owner_dev[d] == pl) g_const_owner_dev[d] = nullptr;
   if (pl->d_block_best) pool_free(pl->d_block_best);
   if (pl->d_out) pool_free(pl->d_out);
-  pool_free(pl->d_wide_cnt); pool_free(pl->d_wide_g2);
+  pool_free(pl->d_wide_cnt); pool_free(pl->d_wide_g2); pool_free(pl->d_z3tab);
   delete pl;
 }
 

@@ -278,3 +278,29 @@ def test_full_size_sweep_reaches_the_exhaustive_optimum(capi, measure):
     one = O.orbit_sweep(L, R, P, 3, 1, SEED, whole["index"], whole["index"] + 1)
     assert (one["nnz"][0], one["nno"][0]) == (whole["nnz"], whole["nno"]) and (measure == 0 or one["g2"][0] == whole["score"])
     plan.close()
+
+
+@pytest.mark.parametrize("stem,lo", [("3x3x3_23_58", 7776 * 7776 * 5 + 12345), ("2x2x2_7_Winograd", 48 * 48 * 7 + 11)])
+def test_table_driven_decode_in_exhaustive_mode(capi, stem, lo):
+    """The kernels that read whole zoi matrices from a table (2x2: shared memory, 3x3: one global table per plan) index them by
+    `index mod count` in exhaustive mode: windows of the mixed-radix enumeration must elect the per-candidate table's minimum (first
+    index among ties), for both measures; the table itself equals the oracle's."""
+    (L, R, P), mkn, (Li, Ri, Pi), dens = ints(stem)
+    cnt, win = 2000, 50
+    ref = O.orbit_sweep(L, R, P, 3, 0, 0, lo, lo + cnt)
+    nnz, nno, g2 = capi.orbit_table(mkn, Li, Ri, Pi, dens, 0, 0, lo, lo + cnt)
+    assert np.array_equal(nnz, ref["nnz"]) and np.array_equal(nno, ref["nno"]) and np.array_equal(g2, ref["g2"])
+    for measure in (capi.MEASURE_NNZ, capi.MEASURE_G2):
+        plan = capi.OrbitPlan(mkn, Li, Ri, Pi, dens, measure, 0, 0)
+        for a in range(0, cnt, win):
+            plan.run(lo + a, lo + a + win)
+            got = plan.result()
+            sl = slice(a, a + win)
+            if measure == capi.MEASURE_NNZ:
+                keys = [(int(x), int(y)) for x, y in zip(nnz[sl], nno[sl])]
+                j = keys.index(min(keys))
+                assert (got["index"], got["nnz"], got["nno"]) == (lo + a + j, keys[j][0], keys[j][1])
+            else:
+                j = int(np.argmin(g2[sl]))
+                assert got["index"] == lo + a + j and got["score"] == g2[sl][j]
+        plan.close()
