@@ -10,6 +10,12 @@
  *
  * Return codes: 0 success; PLO_E_* (< 0) on argument / CUDA errors (message via
  * plo_last_error()).  Verdict-returning calls document their positive codes.
+ *
+ * Threading (as in the reference, include/plinopt_sparsify.inl / src/orbiter.cpp: the search entry points are called from ONE host
+ * thread, the parallelism is inside): calls are serialised per device by the caller.  The orbit kernels keep L|R|P and the Philox
+ * round keys of the plan that ran last in the device's constant memory (re-uploaded when another plan runs), and the workspace
+ * pool is per device, so two host threads must not drive the same device at the same time; different devices are independent
+ * (plo_orbit_sweep_devices drives several from one thread).  The last-error message is thread-local.
  * ========================================================================== */
 #ifndef PLINOPT_B200_H
 #define PLINOPT_B200_H
