@@ -273,7 +273,16 @@ def main():
         # second over the live-measured issue peak; the algorithmic view is kept beside it.
         cand_per_s = B / (kern_ms * 1e-3)
         achieved = NCU_INST_PER_CAND * cand_per_s / 1e12
-        peak = peaks["issue_inst_per_s"] / 1e12
+        peak_measured = peaks["issue_inst_per_s"] / 1e12
+        # the microbenchmark reaches 88-96 % of the schedulers' nominal rate depending on the box; the denominator is the LARGER of
+        # it and SMs x 4 schedulers x 32 lanes x the SM clock sampled under load, so that frac never flatters the kernel
+        peak_clock = None
+        try:
+            if clocks.get("sm_mhz"):
+                peak_clock = torch.cuda.get_device_properties(dev).multi_processor_count * 4 * 32 * float(clocks["sm_mhz"]) * 1e6 / 1e12
+        except Exception:
+            peak_clock = None
+        peak = max(peak_measured, peak_clock) if peak_clock else peak_measured
         alg = INT_OPS_PER_CAND * cand_per_s / 1e12
         roof = {"bound": "int32", "achieved": achieved, "peak": peak, "unit": "T thread-instructions/s (issue slots)", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/ncu_r01_orbit_sweep.md (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch; "
@@ -281,8 +290,9 @@ def main():
                 "kernel": "orbit_sweep8x_kernel<philox> (2x2x2, r = 7: four lanes per IMAD, first product stage from shared-memory tables)", "kernel_ms": kern_ms,
                 "instructions_per_candidate": NCU_INST_PER_CAND,
                 "instructions_source": "profiles/ncu_r01_orbit_sweep.md (smsp__inst_executed.sum x 32 / candidates of the captured launch)",
-                "peak_source": "plo_measure_issue_peak (IMAD and LOP3 chains interleaved 1:1, all SMs, best of 5, measured in this run); "
-                               "MEASURED_PEAKS.json has no int32/fp64 entry",
+                "peak_measured": peak_measured, "peak_from_clock": peak_clock,
+                "peak_source": "max(plo_measure_issue_peak: IMAD and LOP3 chains interleaved 1:1, all SMs, best of 5, measured in this run; "
+                               "SMs x 4 schedulers x 32 lanes x SM clock sampled under load); MEASURED_PEAKS.json has no int32/fp64 entry",
                 "algorithmic": {"ops_per_candidate": {"int32": INT_OPS_PER_CAND, "fp64": FP64_OPS_PER_CAND}, "achieved_tiops": alg,
                                 "scalar_imad_peak_tiops": peaks["imad_per_s"] / 1e12, "vs_scalar_imad_peak": alg / (peaks["imad_per_s"] / 1e12),
                                 "note": "above 1: one IMAD carries four 8-bit lanes (two rows of the left factor x two Hopcroft-Musinski rows)"},
