@@ -169,6 +169,14 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
 int plo_orbit_plan_run(plo_orbit_plan* plan, uint64_t lo, uint64_t hi, void* stream);
 int plo_orbit_plan_result(plo_orbit_plan* plan, void* stream, plo_orbit_best* best);
 int plo_orbit_plan_launches(const plo_orbit_plan* plan);
+/* Name of the sweep kernel plo_orbit_plan_run launches for this plan and the number of candidate-matrix entries one 32-bit
+ * multiply-add carries in it (1 scalar, 2 sixteen-bit lanes, 4 eight-bit lanes): the roofline of a sweep is stated against
+ * lanes x the measured IMAD peak, and a profile is only quoted for the kernel it was taken from. */
+int plo_orbit_plan_kernel(const plo_orbit_plan* plan, char* name, int cap, int* lanes);
+/* Host-only (no device needed): the worst-case magnitudes of the transformed entries of L.(U^-1 (x) V), R.(V^-T (x) W),
+ * (U (x) W^-1).P over the whole orbit, bounds[3], that select the lane packing.  Returns 4 / 2 / 1 (eight-bit lanes, sixteen-bit
+ * lanes, scalar int32 kernel) or 0 (beyond the int32 product bound: 64-bit kernels), PLO_E_ARG on bad arguments. */
+int plo_orbit_magnitude_bounds(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int64_t* bounds);
 /* Host-only self-test (no device needed) of the whole-matrix decode behind the table-driven 2x2x2 kernels: number of mismatches
  * between digit-by-digit decoding and replaying matrix number floor(x.count/2^32) resp. rem mod count; 0 = consistent. */
 int plo_selftest_matrix_index(void);

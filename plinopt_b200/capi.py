@@ -26,7 +26,7 @@ SYMBOLS = [
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
-    "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_survivors", "plo_selftest_matrix_index", "plo_orbit_plan_destroy",
+    "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_kernel", "plo_orbit_magnitude_bounds", "plo_orbit_plan_survivors", "plo_selftest_matrix_index", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
     "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
@@ -273,6 +273,10 @@ class OrbitPlan:
         f.argtypes = [C.POINTER(C.c_void_p)] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_int, C.c_int, C.c_uint64]
         _check(f(C.byref(self._h), m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), dens[0], dens[1], dens[2], measure, mode, seed))
         self.launches = lib().plo_orbit_plan_launches(self._h)
+        name = C.create_string_buffer(64)
+        lanes = C.c_int(0)
+        _check(lib().plo_orbit_plan_kernel(self._h, name, 64, C.byref(lanes)))
+        self.kernel, self.lanes = name.value.decode(), lanes.value
 
     def run(self, lo, hi, stream=0):
         _check(lib().plo_orbit_plan_run(self._h, lo, hi, C.c_void_p(stream)))
@@ -309,6 +313,19 @@ class OrbitPlan:
             self.close()
         except Exception:
             pass
+
+
+def orbit_magnitude_bounds(mkn, L, R, P):
+    """(lanes, (bL, bR, bP)): host-only worst-case magnitudes of the transformed entries over the whole orbit."""
+    m, k, n = mkn
+    L = _i32(L); R = _i32(R); P = _i32(P)
+    b = np.zeros(3, dtype=np.int64)
+    f = lib().plo_orbit_magnitude_bounds
+    f.argtypes = [C.c_int] * 4 + [C.c_void_p] * 4
+    rc = f(m, k, n, L.shape[0], _ptr(L), _ptr(R), _ptr(P), _ptr(b))
+    if rc < 0:
+        _check(rc)
+    return rc, tuple(int(x) for x in b)
 
 
 def growth_G2(L, R, P):

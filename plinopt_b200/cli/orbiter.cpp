@@ -47,8 +47,12 @@ int main(int argc, char** argv) {
   plo::host::QField Q;
   plo::host::Dense<plo::host::QField> L, R, P;
   if (!cli::read_file(files[0], L) || !cli::read_file(files[1], R) || !cli::read_file(files[2], P)) return -1;
-  if (L.rows != R.rows || L.rows != P.cols)  // warning only, src/orbiter.cpp:236-242
+  if (L.rows != R.rows || L.rows != P.cols) {
+    // The reference only warns here (its `return 2` is commented out, src/orbiter.cpp:236-242) and then fails inside LinBox; this
+    // engine takes flat r x cols buffers, so a mismatched triple is rejected with fMMchecker's code (src/MMchecker.cpp:65-71).
     std::cerr << "# \033[1;31m****** ERROR, inner dimension mismatch: " << L.rows << "(.)" << R.rows << '|' << P.cols << " ******\033[0m" << std::endl;
+    return 2;
+  }
   const cli::NumDen l = cli::flatten(L), r = cli::flatten(R), p = cli::flatten(P);
   uint32_t cnt[2];
   const int v0 = plo_mmchecker(modulus, seed, 32, l.rows, l.cols, r.rows, r.cols, p.rows, p.cols, l.num.data(), l.den.data(), r.num.data(), r.den.data(),

@@ -1533,15 +1533,47 @@ static const ShapeOps* find_shape(int m, int k, int n, int r) {
   return nullptr;
 }
 
-// Worst-case magnitude bound of the transformed entries (host guard for the
-// int32 arithmetic): |T^-1| entries <= 2^(s-2), row/column abs sums <= 2^(s-1);
-// a {-1,0,1} factor contributes at most its dimension.
-static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, long long* smax, bool* lanes16, bool* lanes8 = nullptr) {
-  auto maxabs = [](const int32_t* a, size_t cnt) { long long mx = 0; for (size_t i = 0; i < cnt; ++i) { long long v = a[i] < 0 ? -(long long)a[i] : a[i]; if (v > mx) mx = v; } return mx; };
-  auto pw = [](int s) { return 1ll << (s > 1 ? s - 1 : 0); };
-  const long long bl = maxabs(L, (size_t)r * m * k) * pw(m) * k;  // |U^-T A V| <= max|A| * colsum|U^-1| * colsum|V|
-  const long long br = maxabs(R, (size_t)r * k * n) * pw(k) * n;
-  const long long bp = maxabs(P, (size_t)r * m * n) * pw(n) * m;
+// Worst-case magnitude bound of the transformed entries (host guard for the int32 arithmetic and for the lane packings).
+// Only the FINAL entries matter: the packed multiply-adds are plain arithmetic modulo 2^32, so an intermediate lane may spill as
+// long as every final lane is inside its range.  A row (or column) of the inverse of a zoi matrix is a permuted row of T^-1 with
+// |T^-1[i][j]| <= 2^(j-i-1) (j > i), 1 on the diagonal, so its magnitudes sorted in decreasing order are dominated by
+// g(s) = (2^(s-2), .., 2, 1, 1); the {-1,0,1} factor on the other side contributes at most 1 per term.  Hence, per row l,
+//   |U^-T A_l V| <= sum_t g(m)_t . (row sums of |A_l|, decreasing)_t      (rearrangement inequality)
+//   |V^-1 B_l W| <= sum_t g(k)_t . (row sums of |B_l|, decreasing)_t
+//   |U C_l W^-T| <= sum_t g(n)_t . (column sums of |C_l|, decreasing)_t
+// which follows the actual sparsity of the Hopcroft-Musinski rows instead of max|entry| . 2^(s-1) . dimension
+// (3x4x7_63_rational: 6 / 56 / 96 instead of 16 / 112 / 192, which admits the four-lane kernels).
+static long long tight_bound(const int32_t* A, int r, int ra, int ca, size_t row_stride, size_t elt_stride, bool by_rows) {
+  const int s = by_rows ? ra : ca, other = by_rows ? ca : ra;
+  long long g[kMaxDim], sums[kMaxDim], worst = 0;
+  g[0] = 1;
+  for (int t = 1; t < s; ++t) g[t] = 1ll << (t - 1);
+  std::sort(g, g + s, [](long long a, long long b) { return a > b; });
+  for (int l = 0; l < r; ++l) {
+    for (int t = 0; t < s; ++t) {
+      long long acc = 0;
+      for (int o = 0; o < other; ++o) {
+        const int i = by_rows ? t : o, j = by_rows ? o : t;
+        const long long v = A[(size_t)l * row_stride + (size_t)(i * ca + j) * elt_stride];
+        acc += v < 0 ? -v : v;
+      }
+      sums[t] = acc;
+    }
+    std::sort(sums, sums + s, [](long long a, long long b) { return a > b; });
+    long long b = 0;
+    for (int t = 0; t < s; ++t) b += g[t] * sums[t];
+    if (b > worst) worst = b;
+  }
+  return worst;
+}
+
+static bool magnitude_ok(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, long long* smax, bool* lanes16, bool* lanes8 = nullptr,
+                         long long* bounds = nullptr) {
+  if (m > kMaxDim || k > kMaxDim || n > kMaxDim) return false;
+  const long long bl = tight_bound(L, r, m, k, (size_t)m * k, 1, true);   // L: r x (m*k), row l = vec(A_l)
+  const long long br = tight_bound(R, r, k, n, (size_t)k * n, 1, true);   // R: r x (k*n)
+  const long long bp = tight_bound(P, r, m, n, 1, (size_t)r, false);      // P: (m*n) x r, column l = vec(C_l)
+  if (bounds) { bounds[0] = bl; bounds[1] = br; bounds[2] = bp; }
   auto ok = [](long long b, int cnt) { return b < 46340 && b * b * cnt < 2147483647ll; };
   if (!(ok(bl, m * k) && ok(br, k * n) && ok(bp, m * n))) return false;
   long long s = bl * bl * m * k;
@@ -1887,6 +1919,34 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
 int plo_selftest_matrix_index(void) { return matrix_index_mismatches<2, 48>() + matrix_index_mismatches<3, 7776>(); }
 
 int plo_orbit_plan_launches(const plo_orbit_plan*) { return 2; }
+
+int plo_orbit_magnitude_bounds(int m, int k, int n, int r, const int32_t* L, const int32_t* R, const int32_t* P, int64_t* bounds) {
+  if (!L || !R || !P || !bounds || r < 1 || m < 1 || k < 1 || n < 1 || m > kMaxDim || k > kMaxDim || n > kMaxDim) {
+    set_error("plo_orbit_magnitude_bounds: bad argument");
+    return PLO_E_ARG;
+  }
+  long long smax = 0, b[3] = {0, 0, 0};
+  bool l16 = false, l8 = false;
+  const bool ok = magnitude_ok(m, k, n, r, L, R, P, &smax, &l16, &l8, b);
+  bounds[0] = b[0]; bounds[1] = b[1]; bounds[2] = b[2];
+  return ok ? (l8 ? 4 : (l16 ? 2 : 1)) : 0;
+}
+
+// which sweep kernel plo_orbit_plan_run launches, and how many candidate-matrix entries one 32-bit multiply-add carries in it
+int plo_orbit_plan_kernel(const plo_orbit_plan* pl, char* name, int cap, int* lanes) {
+  if (!pl) { set_error("plo_orbit_plan_kernel: null plan"); return PLO_E_ARG; }
+  const char* nm;
+  int ln;
+  if (pl->wide) { nm = "orbit_wide_kernel"; ln = 1; }
+  else if (pl->xtab) { nm = "orbit_sweep8x_kernel"; ln = 4; }
+  else if (pl->xtab2) { nm = "orbit_sweep2x_kernel"; ln = 2; }
+  else if (pl->packn8) { nm = "orbit_sweepn8_kernel"; ln = 4; }
+  else if (pl->pack8) { nm = "orbit_sweep8_kernel"; ln = 4; }
+  else { nm = "orbit_sweep_kernel"; ln = pl->pack ? 2 : 1; }
+  if (name && cap > 0) { strncpy(name, nm, (size_t)cap - 1); name[cap - 1] = 0; }
+  if (lanes) *lanes = ln;
+  return PLO_OK;
+}
 
 int plo_orbit_plan_result(plo_orbit_plan* pl, void* stream, plo_orbit_best* best) {
   if (!pl || !best) { set_error("plo_orbit_plan_result: bad argument"); return PLO_E_ARG; }

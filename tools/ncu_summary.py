@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Condenses an Nsight Compute report (.ncu-rep, `ncu --set full`) into the small text summary that is
-committed under profiles/:  python tools/ncu_summary.py REPORT.ncu-rep [OUT.md]
+"""Condenses an Nsight Compute report (.ncu-rep, `ncu --set full`, or its `--page raw --csv` export) into the small text
+summary that is committed under profiles/:  python tools/ncu_summary.py REPORT.ncu-rep|REPORT.raw.csv [OUT.md]
 Reads the report with `ncu -i ... --page raw --csv` (no GPU needed)."""
 import csv
 import io
@@ -28,7 +28,10 @@ KEYS = [
 
 def main():
     rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # already converted on the GPU box (tools/ncu_capture.sh)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     out = [f"# ncu --set full summary of `{rep.split('/')[-1]}` ({len(rows) - 2} captured launches)", ""]
