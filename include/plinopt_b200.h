@@ -66,7 +66,8 @@ int plo_set_sweep_devices(int n);     /* host-level orbit sweeps (plo_orbiter) a
  * TM       n x m row-major (n = TM.rowdim() = width of the CoB block).
  * off      4*block ; the candidate w has coeffs[i],[j],[k],[l] at positions
  *          off..off+3 (positions >= n are truncated, reference quirk Q4).
- * coeffs   c values in the reference's enumeration order (c <= 512).
+ * coeffs   c values in the reference's enumeration order (c <= 511: every index < c^4 has its own 36-bit key field below the
+ *          seed's).
  * prev_rows nprev x n : the rows of LCoB chosen so far (Cand rows 0..num-1,
  *          plinopt_sparsify.inl:289,172); a candidate is admissible iff it is
  *          linearly independent of them (rank(Cand) > num, :173-175).
@@ -85,6 +86,46 @@ int plo_lincomb_search(uint32_t p, int n, int m, const int64_t* TM, int off, int
 int plo_lincomb_search_batch(uint32_t p, int nbatch, int n, int m, const int64_t* TM, int off, int c,
                              const int64_t* coeffs, int nprev, const int64_t* prev_rows, const int* init_rl,
                              const int* init_cl, int* best_rl, int* best_cl, uint64_t* best_index);
+
+/* ALL the rows of one inner block in one launch sequence ("score once, filter four times").
+ * In include/plinopt_sparsify.inl:282-326 the quad loop runs once per row num = 0..3 of an inner block, but the score
+ * (rlHw, clHw) of a candidate (:176-180) does not depend on num; only the independence filter (:172-175) and the weight seed
+ * (:290-295) do.  plo_lincomb_quad scores every candidate ONCE on the device and then picks the rows one after the other, the
+ * filter of row num being derived on the device from the winners of rows 0..num-1: one host->device copy, six kernel launches
+ * and one device->host copy for any number of independent problems (the column blocks of blockSparsifier, :710-723).
+ * The rows are exactly those of successive plo_lincomb_search calls for the rows nprev .. off+3 of the block (min(4, n - off)
+ * rows when nprev <= off; fewer when the call resumes inside a block), each with the previous winners appended to prev_rows
+ * and, after the first, the weight seed (-1, -1).
+ *
+ * Per problem (m, the number of columns of TM, is common to the call, m <= 64; sum of c^4 <= PLO_QUAD_MAX_COUNT_BYTES):
+ *   n, off, c, nprev, TM, coeffs, prev_rows, init_rl, init_cl   as in plo_lincomb_search (seed of the FIRST row);
+ *   seed_vec  (n entries, scaled like prev_rows, or NULL) the vector that holds the seed weight -- the nullspace vector of
+ *             :227-252; when it keeps row 0 and lives on the positions off..off+3 the device goes on with it as a previous row.
+ * Outputs: rl/cl/index[t] for the rows t < nrows that were decided (index == PLO_NO_INDEX: the seed vector kept row 0), and
+ *   status  PLO_QUAD_DONE   all the rows of the block decided;
+ *           PLO_QUAD_MISS   row `nrows` has no admissible candidate: the caller applies the canonical fallback (:317-326)
+ *                           and calls again for the remaining rows;
+ *           PLO_QUAD_SEED   the seed vector kept row 0 and the device could not go on with it (seed_vec NULL or not on the
+ *                           live positions): nrows == 1, call again with it among prev_rows;
+ *           PLO_QUAD_RANGE  the exact-integer guard of the device-side filter tripped at row `nrows`: go on with
+ *                           plo_lincomb_search for that row (never a silent wrap-around). */
+#define PLO_QUAD_DONE 0
+#define PLO_QUAD_MISS 1
+#define PLO_QUAD_SEED 2
+#define PLO_QUAD_RANGE 3
+#define PLO_QUAD_MAX_COUNT_BYTES (1ull << 31)
+typedef struct plo_quad_problem {
+  int n, off, c, nprev;
+  const int64_t* TM;        /* n x m */
+  const int64_t* coeffs;    /* c */
+  const int64_t* prev_rows; /* nprev x n */
+  const int64_t* seed_vec;  /* n, may be NULL */
+  int init_rl, init_cl;
+  int nrows, status;        /* out */
+  int rl[4], cl[4];         /* out */
+  uint64_t index[4];        /* out */
+} plo_quad_problem;
+int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* problems);
 
 /* Device-resident variant used for throughput measurement: inputs are uploaded
  * once, every plo_lincomb_plan_run() enqueues one full search on `stream`

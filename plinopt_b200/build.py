@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libplinopt_b200.so")
-SOURCES = ["common.cu", "orbit_sweep.cu", "lincomb_search.cu", "mmcheck.cu", "factor_sweep.cu", "dependency_explore.cu", "peaks.cu", "host/host_api.cpp"]
+SOURCES = ["common.cu", "orbit_sweep.cu", "lincomb_search.cu", "lincomb_quad.cu", "mmcheck.cu", "factor_sweep.cu", "dependency_explore.cu", "peaks.cu", "host/host_api.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v",
               "-split-compile", "0"]  # ptxas of the many template instantiations in parallel (orbit_sweep.cu: 180 s -> 60 s)
@@ -24,9 +24,20 @@ def _nvcc():
     return nv
 
 
+HOST_HEADERS = ["exact.hpp", "sparsify_host.hpp", "matrix_io.hpp", "slp.hpp", "factor_host.hpp", "dependency_host.hpp", "negate_host.hpp"]
+# headers each source really includes (a change to the host layer does not recompile the 2000-line orbit kernels)
+EXTRA_DEPS = {
+    "lincomb_search.cu": ["lincomb_common.cuh", "host/exact.hpp"],
+    "lincomb_quad.cu": ["lincomb_common.cuh", "host/exact.hpp"],
+    "factor_sweep.cu": ["host/exact.hpp"],
+    "dependency_explore.cu": ["host/exact.hpp"],
+    "host/host_api.cpp": ["host/" + h for h in HOST_HEADERS],
+}
+
+
 def _deps(src):
-    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "plo_device.cuh"), os.path.join(CSRC, "host", "exact.hpp"), os.path.join(CSRC, "host", "sparsify_host.hpp"), os.path.join(CSRC, "host", "matrix_io.hpp"), os.path.join(CSRC, "host", "slp.hpp"), os.path.join(CSRC, "host", "factor_host.hpp"), os.path.join(CSRC, "host", "dependency_host.hpp"), os.path.join(CSRC, "host", "negate_host.hpp"),
-            os.path.join(os.path.dirname(HERE), "include", "plinopt_b200.h"), os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "plo_device.cuh"), os.path.join(os.path.dirname(HERE), "include", "plinopt_b200.h"), os.path.abspath(__file__)]
+    deps += [os.path.join(CSRC, h) for h in EXTRA_DEPS.get(src, [])]
     return max(os.path.getmtime(d) for d in deps if os.path.exists(d))
 
 

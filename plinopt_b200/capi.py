@@ -23,7 +23,7 @@ NO_INDEX = 2 ** 64 - 1
 SYMBOLS = [
     "plo_release_workspace", "plo_set_sweep_devices", "plo_orbit_sweep_devices",
     "plo_version", "plo_device_count", "plo_set_device", "plo_last_error",
-    "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
+    "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_quad", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
     "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_kernel", "plo_orbit_magnitude_bounds", "plo_orbit_plan_survivors", "plo_selftest_matrix_index", "plo_orbit_plan_destroy",
@@ -122,6 +122,43 @@ def lincomb_search(p, TM, off, coeffs, prev_rows=None, init_rl=-1, init_cl=-1):
     _check(f(int(p), n, m, _ptr(TM), int(off), len(coeffs), _ptr(coeffs), nprev, _ptr(prev), int(init_rl), int(init_cl),
              C.byref(rl), C.byref(cl), C.byref(idx)))
     return rl.value, cl.value, (None if idx.value == NO_INDEX else idx.value)
+
+
+class QuadProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("off", C.c_int), ("c", C.c_int), ("nprev", C.c_int), ("TM", C.c_void_p), ("coeffs", C.c_void_p),
+                ("prev_rows", C.c_void_p), ("seed_vec", C.c_void_p), ("init_rl", C.c_int), ("init_cl", C.c_int), ("nrows", C.c_int),
+                ("status", C.c_int), ("rl", C.c_int * 4), ("cl", C.c_int * 4), ("index", C.c_uint64 * 4)]
+
+
+QUAD_DONE, QUAD_MISS, QUAD_SEED, QUAD_RANGE = 0, 1, 2, 3
+
+
+def lincomb_quad(p, problems):
+    """All rows of one inner block for a list of independent problems (plo_lincomb_quad).  Each problem is a dict with TM (n x m),
+    off, coeffs and optionally prev_rows, init_rl, init_cl, seed_vec.  Returns per problem (status, [(rl, cl, index or None), ...])."""
+    arr = (QuadProblem * len(problems))()
+    keep = []
+    m = None
+    for q, pr in zip(arr, problems):
+        TM = _i64(pr["TM"]); cf = _i64(pr["coeffs"])
+        prev = pr.get("prev_rows")
+        prev = _i64(prev) if prev is not None and len(prev) else None
+        sv = pr.get("seed_vec")
+        sv = _i64(sv) if sv is not None else None
+        keep += [TM, cf, prev, sv]
+        if m is None:
+            m = TM.shape[1]
+        assert TM.shape[1] == m
+        q.n, q.off, q.c, q.nprev = TM.shape[0], int(pr.get("off", 0)), len(cf), (0 if prev is None else prev.shape[0])
+        q.TM, q.coeffs, q.prev_rows, q.seed_vec = _ptr(TM), _ptr(cf), _ptr(prev), _ptr(sv)
+        q.init_rl, q.init_cl = int(pr.get("init_rl", -1)), int(pr.get("init_cl", -1))
+    f = lib().plo_lincomb_quad
+    f.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+    _check(f(int(p), int(m), len(problems), C.cast(arr, C.c_void_p)))
+    out = []
+    for q in arr:
+        out.append((q.status, [(q.rl[t], q.cl[t], (None if q.index[t] == NO_INDEX else q.index[t])) for t in range(q.nrows)]))
+    return out
 
 
 class LincombPlan:

@@ -100,6 +100,7 @@ void pool_free(void* p) {
 extern "C" {
 
 void plo_release_workspace(void) {
+  plo::quad_release_all();
   plo::Pool& P = plo::pool();
   std::lock_guard<std::mutex> g(P.mu);
   for (auto& kv : P.free_blocks)

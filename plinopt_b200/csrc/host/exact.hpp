@@ -22,8 +22,21 @@ struct RangeError : std::runtime_error {
 typedef __int128 wide;
 
 inline wide wabs(wide a) { return a < 0 ? -a : a; }
+inline uint64_t gcd64(uint64_t a, uint64_t b) {  // binary gcd: shifts and subtractions only
+  if (a == 0) return b;
+  if (b == 0) return a;
+  const int sh = __builtin_ctzll(a | b);
+  a >>= __builtin_ctzll(a);
+  do {
+    b >>= __builtin_ctzll(b);
+    if (a > b) { const uint64_t t = a; a = b; b = t; }
+    b -= a;
+  } while (b != 0);
+  return a << sh;
+}
 inline wide wgcd(wide a, wide b) {
   a = wabs(a); b = wabs(b);
+  if ((a >> 64) == 0 && (b >> 64) == 0) return (wide)gcd64((uint64_t)a, (uint64_t)b);  // the usual case: no 128-bit division
   while (b != 0) { wide t = a % b; a = b; b = t; }
   return a;
 }
@@ -38,6 +51,14 @@ struct Rat {
     if (d < 0) { n = -n; d = -d; }
     Rat r;
     if (n == 0) return r;
+    const wide an = wabs(n);
+    if ((an >> 63) == 0 && (d >> 63) == 0) {  // both fit 63 bits: 64-bit arithmetic throughout
+      const uint64_t g = gcd64((uint64_t)an, (uint64_t)d);
+      const int64_t q = (int64_t)((uint64_t)an / g);
+      r.num = n < 0 ? -q : q;
+      r.den = (int64_t)((uint64_t)d / g);
+      return r;
+    }
     const wide g = wgcd(n, d);
     n /= g; d /= g;
     if (wabs(n) > (wide)INT64_MAX || d > (wide)INT64_MAX) throw RangeError("rational exceeds 64 bits");
@@ -59,9 +80,22 @@ struct QField {
   Elt mone() const { return Rat(-1); }
   Elt from_int(int64_t i) const { return Rat(i); }
   Elt from_ratio(int64_t n, int64_t d) const { return Rat::make(n, d); }
-  Elt add(const Elt& a, const Elt& b) const { return Rat::make((wide)a.num * b.den + (wide)b.num * a.den, (wide)a.den * b.den); }
-  Elt sub(const Elt& a, const Elt& b) const { return Rat::make((wide)a.num * b.den - (wide)b.num * a.den, (wide)a.den * b.den); }
-  Elt mul(const Elt& a, const Elt& b) const { return Rat::make((wide)a.num * b.num, (wide)a.den * b.den); }
+  static Elt integer(wide v) {
+    if (wabs(v) > (wide)INT64_MAX) throw RangeError("rational exceeds 64 bits");
+    Rat r; r.num = (int64_t)v; return r;
+  }
+  Elt add(const Elt& a, const Elt& b) const {
+    if (a.den == 1 && b.den == 1) return integer((wide)a.num + b.num);
+    return Rat::make((wide)a.num * b.den + (wide)b.num * a.den, (wide)a.den * b.den);
+  }
+  Elt sub(const Elt& a, const Elt& b) const {
+    if (a.den == 1 && b.den == 1) return integer((wide)a.num - b.num);
+    return Rat::make((wide)a.num * b.den - (wide)b.num * a.den, (wide)a.den * b.den);
+  }
+  Elt mul(const Elt& a, const Elt& b) const {
+    if (a.den == 1 && b.den == 1) return integer((wide)a.num * b.num);
+    return Rat::make((wide)a.num * b.num, (wide)a.den * b.den);
+  }
   Elt div(const Elt& a, const Elt& b) const { return Rat::make((wide)a.num * b.den, (wide)a.den * b.num); }
   Elt neg(const Elt& a) const { Rat r; r.num = -a.num; r.den = a.den; return r; }
   Elt raw_neg(const Elt& a) const { return neg(a); }
@@ -83,15 +117,23 @@ struct ZpField {
   int64_t p;
   explicit ZpField(int64_t p_) : p(p_) {}
   uint64_t characteristic() const { return (uint64_t)p; }
-  Elt canon(Elt a) const { a %= p; return a < 0 ? a + p : a; }
+  Elt canon(Elt a) const {
+    if ((uint64_t)a < (uint64_t)p) return a;  // already the canonical representative (the usual case)
+    a %= p;
+    return a < 0 ? a + p : a;
+  }
   Elt zero() const { return 0; }
   Elt one() const { return 1 % p; }
   Elt mone() const { return canon(-1); }
   Elt from_int(int64_t i) const { return i; }
   Elt from_ratio(int64_t n, int64_t d) const { return div(canon(n), canon(d)); }
-  Elt add(Elt a, Elt b) const { return (Elt)(((wide)canon(a) + canon(b)) % p); }
-  Elt sub(Elt a, Elt b) const { return (Elt)(((wide)canon(a) + p - canon(b)) % p); }
-  Elt mul(Elt a, Elt b) const { return (Elt)(((wide)canon(a) * canon(b)) % p); }
+  Elt add(Elt a, Elt b) const { const uint64_t s = (uint64_t)canon(a) + (uint64_t)canon(b); return (Elt)(s >= (uint64_t)p ? s - (uint64_t)p : s); }  // p < 2^63
+  Elt sub(Elt a, Elt b) const { const uint64_t x = (uint64_t)canon(a), y = (uint64_t)canon(b); return (Elt)(x >= y ? x - y : x + (uint64_t)p - y); }
+  Elt mul(Elt a, Elt b) const {
+    const uint64_t x = (uint64_t)canon(a), y = (uint64_t)canon(b);
+    if ((uint64_t)p <= 0xFFFFFFFFull) return (Elt)((x * y) % (uint64_t)p);  // word-size moduli: one 64-bit division
+    return (Elt)(((unsigned __int128)x * y) % (uint64_t)p);
+  }
   Elt neg(Elt a) const { a = canon(a); return a ? p - a : 0; }
   Elt raw_neg(Elt a) const { return -a; }
   Elt inv(Elt a) const {

@@ -60,6 +60,7 @@ int run_sparsifier(const F& f, int rows, int cols, const int64_t* num, const int
   store(Res, res_num, res_den);
   if (consistent) *consistent = sp.consistency(M, Res, CoB) ? 1 : 0;
   if (stats) { stats[0] = sp.stats.candidates; stats[1] = sp.stats.searches; stats[2] = sp.stats.fallbacks; }
+  if (getenv("PLO_TIMING")) fprintf(stderr, "# [B200] plo_sparsifier: %.1f us inside %llu device round trips; host: begin_alternate %.1f us (incl. first begin_local), begin_local %.1f us, finish_local %.1f us (incl. nested begin_local)\n", sp.stats.device_seconds * 1e6, sp.stats.searches, sp.stats.t_begin_alt * 1e6, sp.stats.t_begin_local * 1e6, sp.stats.t_finish_local * 1e6);
   return PLO_OK;
 }
 

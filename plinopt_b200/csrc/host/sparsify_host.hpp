@@ -1,21 +1,29 @@
-// sparsify_host.hpp -- host orchestration of the alternate-basis sparsifier around the GPU
-// candidate search.  Mirrors the reference's entry points (names, argument meaning, log
-// prefixes) of include/plinopt_sparsify.inl so that a reference maintainer can map one onto
-// the other:
-//   augment :20-35 · rank :38-45 · localSparsifier :205-347 · FactorDiagonals :354-375 ·
-//   inverse/inverseTranspose :380-465 · SparseFactor :473-513 · sparseLU :523-568 ·
-//   sparseILU :576-604 · sparseAlternate :609-661 · blockSparsifier :666-748 · consistency :871-907
-// The quad loop + testLinComb (:299-314, :166-197) is NOT here: it runs on the GPU through
-// plo_lincomb_search (lincomb_search.cu).  Everything in this file is O(n^3) glue on
-// matrices of a few dozen entries.
+// sparsify_host.hpp -- host orchestration of the alternate-basis sparsifier around the GPU candidate search.
+// Mirrors the reference's entry points of include/plinopt_sparsify.inl (names, argument meaning, log prefixes):
+//   augment :20-35 · rank :38-45 · localSparsifier :205-347 · FactorDiagonals :354-375 · inverse/inverseTranspose :380-465 ·
+//   SparseFactor :473-513 · sparseLU :523-568 · sparseILU :576-604 · sparseAlternate :609-661 · blockSparsifier :666-748 ·
+//   consistency :871-907
 //
-// LinBox's GaussDomain::QLUPin / nullspacebasisin are not in the reference tree; the pivot
-// rule used instead is documented in DESIGN.md ("pivot rule") -- parity unpinned upstream.
+// How the work is organised here (the reference is strictly sequential):
+//   * the quad loop + testLinComb (:299-314, :166-197) runs on the GPU -- all the rows of an inner block in ONE launch sequence
+//     (plo_lincomb_quad, lincomb_quad.cu); wide outputs (m > 64) keep the one-row entry point plo_lincomb_search;
+//   * the independent column blocks of blockSparsifier (:710-723) advance in LOCK STEP: sparseAlternate is a resumable state
+//     machine (AlternateRun) that stops whenever it needs a search; the driver collects the pending searches of every block and
+//     submits them as one batch, so a whole run costs a handful of device round trips instead of one per (block, num) step;
+//   * eliminations work on sparse rows (column-sorted entry lists with running column counts), so the initial LU of
+//     blockSparsifier scales to wide inputs (32x32x32_15096: 1024 x 15096).
+// Progress lines of a column block are buffered and emitted in block order: the log reads like the reference's.
+//
+// LinBox's GaussDomain::QLUPin / nullspacebasisin are not in the reference tree; the pivot rule used instead is documented in
+// DESIGN.md ("pivot rule") -- parity unpinned upstream.
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <map>
+#include <memory>
 #include <numeric>
 #include <ostream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -34,15 +42,19 @@ struct EngineError : std::runtime_error {
   EngineError(int c, const std::string& s) : std::runtime_error(s), code(c) {}
 };
 
-// statistics of the GPU part of a run (candidates scored, kernel calls)
+// statistics of the GPU part of a run: candidate evaluations of the reference loop covered (c^4 per row decided),
+// device round trips (batched quad calls + single-row searches), canonical fallbacks
 struct SearchStats {
   unsigned long long candidates = 0, searches = 0, fallbacks = 0;
+  double device_seconds = 0;  // wall time inside the device calls (copies, launches, synchronisation)
+  double t_begin_local = 0, t_finish_local = 0, t_begin_alt = 0;  // host phases (PLO_TIMING)
 };
 
 template <class F>
 struct Sparsifier {
   typedef typename F::Elt Elt;
   typedef Dense<F> Mat;
+  typedef std::vector<std::pair<size_t, Elt>> SRow;  // one sparse row: (column, value), columns increasing
   const F& f;
   std::ostream* log;  // may be null
   SearchStats stats;
@@ -57,7 +69,7 @@ struct Sparsifier {
   }
   size_t density(const Mat& M) const {  // plinopt_library.inl:238-245
     size_t s = 0;
-    for (size_t i = 0; i < M.rows; ++i) s += rowSize(M, i);
+    for (const Elt& e : M.v) s += !f.is_zero(e);
     return s;
   }
   Mat transpose(const Mat& A) const {
@@ -72,13 +84,20 @@ struct Sparsifier {
   }
   Mat mul(const Mat& A, const Mat& B) const {
     Mat C(f, A.rows, B.cols);
+    std::vector<SRow> Bs(B.rows);
+    for (size_t t = 0; t < B.rows; ++t) Bs[t] = sparse_row(B, t);
     for (size_t i = 0; i < A.rows; ++i)
       for (size_t t = 0; t < A.cols; ++t) {
-        if (f.is_zero(A.at(i, t))) continue;
-        for (size_t j = 0; j < B.cols; ++j)
-          if (!f.is_zero(B.at(t, j))) C.at(i, j) = f.add(C.at(i, j), f.mul(A.at(i, t), B.at(t, j)));
+        const Elt& a = A.at(i, t);
+        if (f.is_zero(a)) continue;
+        for (const auto& e : Bs[t]) C.at(i, e.first) = f.add(C.at(i, e.first), f.mul(a, e.second));
       }
     return C;
+  }
+  SRow sparse_row(const Mat& M, size_t i) const {
+    SRow r;
+    for (size_t j = 0; j < M.cols; ++j) if (!f.is_zero(M.at(i, j))) r.emplace_back(j, M.at(i, j));
+    return r;
   }
   size_t rank(const Mat& A) const {  // :38-45
     Mat U = A;
@@ -105,63 +124,93 @@ struct Sparsifier {
     return out << '=' << ss;
   }
 
-  // ---- elimination with the documented pivot rule (stand-in for QLUPin) ----------------
+  // ---- elimination with the documented pivot rule (stand-in for QLUPin), on sparse rows -----------------------------------
+  // Step k: the sparsest non-empty remaining row comes first (lowest position among ties); its pivot is the entry whose column
+  // holds the fewest non-zeroes among the remaining rows (leftmost among ties); rows below are reduced.  A = Pr^T . L . U with L
+  // unit lower triangular (strict part in `L`, row-wise) and Pr the row order `rowperm`.
   struct Elim {
-    size_t rank;
+    size_t rank = 0, rows = 0, cols = 0;
     std::vector<size_t> rowperm, pivcol;
-    Mat U, L;
+    std::vector<SRow> U, L;
   };
+  // r <- r - mult . piv   (both column-sorted); `colcnt` follows the fill-in and the cancellations
+  void axpy_row(SRow& r, const Elt& mult, const SRow& piv, std::vector<size_t>& colcnt) const {
+    SRow out;
+    out.reserve(r.size() + piv.size());
+    size_t a = 0, b = 0;
+    while (a < r.size() || b < piv.size()) {
+      if (b == piv.size() || (a < r.size() && r[a].first < piv[b].first)) { out.push_back(r[a++]); continue; }
+      if (a == r.size() || piv[b].first < r[a].first) {
+        out.emplace_back(piv[b].first, f.neg(f.mul(mult, piv[b].second)));
+        ++colcnt[piv[b].first];
+        ++b;
+        continue;
+      }
+      const Elt v = f.sub(r[a].second, f.mul(mult, piv[b].second));
+      if (f.is_zero(v)) --colcnt[r[a].first]; else out.emplace_back(r[a].first, v);
+      ++a; ++b;
+    }
+    r.swap(out);
+  }
   Elim eliminate(const Mat& A) const {
-    const size_t m = A.rows, n = A.cols;
     Elim e;
-    e.U = A; e.L = identity(m); e.rank = 0;
+    const size_t m = A.rows, n = A.cols;
+    e.rows = m; e.cols = n;
+    e.U.resize(m); e.L.resize(m);
     e.rowperm.resize(m);
     std::iota(e.rowperm.begin(), e.rowperm.end(), 0);
+    std::vector<size_t> colcnt(n, 0);
+    for (size_t i = 0; i < m; ++i) {
+      e.U[i] = sparse_row(A, i);
+      for (const auto& x : e.U[i]) ++colcnt[x.first];
+    }
     for (size_t k = 0; k < m; ++k) {
-      size_t best = m, bestsz = n + 1;  // sparsest non-empty remaining row, first among ties
-      for (size_t i = k; i < m; ++i) { const size_t s = rowSize(e.U, i); if (s > 0 && s < bestsz) { bestsz = s; best = i; } }
+      size_t best = m, bestsz = n + 1;
+      for (size_t i = k; i < m; ++i) { const size_t s = e.U[i].size(); if (s > 0 && s < bestsz) { bestsz = s; best = i; } }
       if (best == m) break;
-      if (best != k) {
-        for (size_t j = 0; j < n; ++j) std::swap(e.U.at(k, j), e.U.at(best, j));
-        for (size_t j = 0; j < k; ++j) std::swap(e.L.at(k, j), e.L.at(best, j));
-        std::swap(e.rowperm[k], e.rowperm[best]);
-      }
-      size_t pc = n, pcsz = m + 1;  // pivot: entry of that row whose column is sparsest below, first among ties
-      for (size_t j = 0; j < n; ++j) {
-        if (f.is_zero(e.U.at(k, j))) continue;
-        size_t s = 0;
-        for (size_t i = k; i < m; ++i) s += !f.is_zero(e.U.at(i, j));
-        if (s < pcsz) { pcsz = s; pc = j; }
-      }
+      if (best != k) { e.U[k].swap(e.U[best]); e.L[k].swap(e.L[best]); std::swap(e.rowperm[k], e.rowperm[best]); }
+      const SRow& prow = e.U[k];
+      size_t pidx = 0, pcsz = m + 1;
+      for (size_t t = 0; t < prow.size(); ++t) if (colcnt[prow[t].first] < pcsz) { pcsz = colcnt[prow[t].first]; pidx = t; }
+      const size_t pc = prow[pidx].first;
       e.pivcol.push_back(pc);
-      const Elt ip = f.inv(e.U.at(k, pc));
+      const Elt ip = f.inv(prow[pidx].second);
       for (size_t i = k + 1; i < m; ++i) {
-        if (f.is_zero(e.U.at(i, pc))) continue;
-        const Elt mult = f.mul(e.U.at(i, pc), ip);
-        e.L.at(i, k) = mult;
-        for (size_t j = 0; j < n; ++j)
-          if (!f.is_zero(e.U.at(k, j))) e.U.at(i, j) = f.sub(e.U.at(i, j), f.mul(mult, e.U.at(k, j)));
+        SRow& r = e.U[i];
+        auto it = std::lower_bound(r.begin(), r.end(), pc, [](const std::pair<size_t, Elt>& x, size_t c) { return x.first < c; });
+        if (it == r.end() || it->first != pc) continue;
+        const Elt mult = f.mul(it->second, ip);
+        e.L[i].emplace_back(k, mult);
+        axpy_row(r, mult, e.U[k], colcnt);
       }
+      for (const auto& x : e.U[k]) --colcnt[x.first];  // row k leaves the remaining set
       ++e.rank;
     }
     return e;
   }
-  // first nullspace vector (stand-in for nullspacebasisin column 0, :235-239)
+  Mat dense_of(const std::vector<SRow>& R, size_t rows, size_t cols) const {
+    Mat M(f, rows, cols);
+    for (size_t i = 0; i < rows; ++i) for (const auto& x : R[i]) M.at(i, x.first) = x.second;
+    return M;
+  }
+  // first nullspace vector (stand-in for nullspacebasisin column 0, :235-239): the leftmost non-pivot column is set to one, the
+  // pivot coordinates follow by back substitution through U
   bool nullspaceVector(const Mat& N, std::vector<Elt>& x) const {
     const size_t n = N.cols;
     const Elim e = eliminate(N);
     std::vector<char> isp(n, 0);
-    for (size_t k = 0; k < e.rank; ++k) isp[e.pivcol[k]] = 1;
-    size_t fc = n;
-    for (size_t j = 0; j < n; ++j) if (!isp[j]) { fc = j; break; }
+    for (size_t c : e.pivcol) isp[c] = 1;
     x.assign(n, f.zero());
+    const size_t fc = (size_t)(std::find(isp.begin(), isp.end(), 0) - isp.begin());
     if (fc == n) return false;
     x[fc] = f.one();
     for (size_t kk = e.rank; kk-- > 0;) {
-      Elt s = f.zero();
-      for (size_t j = 0; j < n; ++j)
-        if (j != e.pivcol[kk] && !f.is_zero(e.U.at(kk, j)) && !f.is_zero(x[j])) s = f.add(s, f.mul(e.U.at(kk, j), x[j]));
-      x[e.pivcol[kk]] = f.neg(f.div(s, e.U.at(kk, e.pivcol[kk])));
+      Elt s = f.zero(), pv = f.one();
+      for (const auto& t : e.U[kk]) {
+        if (t.first == e.pivcol[kk]) pv = t.second;
+        else if (!f.is_zero(x[t.first])) s = f.add(s, f.mul(t.second, x[t.first]));
+      }
+      x[e.pivcol[kk]] = f.neg(f.div(s, pv));
     }
     return true;
   }
@@ -240,91 +289,6 @@ struct Sparsifier {
     return false;
   }
 
-  // ---- localSparsifier (:205-347): GPU quad loop ------------------------------------------
-  void localSparsifier(Mat& TCoB, Mat& TM, size_t maxnumcoeff) {
-    const size_t n = TCoB.rows;
-    Mat LCoB(f, n, n);
-    int cnHw = -1, rnHw = -1;
-    if (TM.rows > 1) {  // nullspace prelude :227-252
-      Mat N = transpose(TM);
-      {  // std::sort(N.rowBegin(), N.rowEnd(), sizeSup) :229
-        std::vector<std::vector<std::pair<size_t, Elt>>> rows(N.rows);
-        for (size_t i = 0; i < N.rows; ++i)
-          for (size_t j = 0; j < N.cols; ++j)
-            if (!f.is_zero(N.at(i, j))) rows[i].emplace_back(j, N.at(i, j));
-        std::sort(rows.begin(), rows.end(), [](const auto& a, const auto& b) { return a.size() > b.size(); });
-        Mat S(f, N.rows, N.cols);
-        for (size_t i = 0; i < N.rows; ++i) for (const auto& e : rows[i]) S.at(i, e.first) = e.second;
-        N = S;
-      }
-      while (N.rows > 0 && rank(N) == N.cols) { N.v.resize((N.rows - 1) * N.cols); N.rows -= 1; }
-      if (N.rows > 0) {
-        std::vector<Elt> x;
-        nullspaceVector(N, x);
-        for (size_t i = 0; i < n; ++i) if (!f.is_zero(x[i])) LCoB.at(0, i) = x[i];
-        cnHw = (int)rowSize(LCoB, 0);  // number of NON-zeroes (sic, :242)
-        rnHw = 0;
-        for (size_t j = 0; j < TM.cols; ++j) {
-          Elt s = f.zero();
-          for (size_t i = 0; i < TM.rows; ++i)
-            if (!f.is_zero(LCoB.at(0, i)) && !f.is_zero(TM.at(i, j))) s = f.add(s, f.mul(LCoB.at(0, i), TM.at(i, j)));
-          rnHw += f.is_zero(s);
-        }
-      }
-    }
-    const std::vector<Elt> Coeffs = coefficients(TM, maxnumcoeff);
-    if (log) {
-      *log << "# [SPRF] linear combination coefficients: [";
-      for (size_t i = 0; i < Coeffs.size(); ++i) { if (i) *log << ' '; print(*log, Coeffs[i]); }
-      *log << ']' << std::endl;
-    }
-    std::vector<int64_t> tm_int, cf_int(Coeffs.size());
-    to_int_columns(TM, tm_int);
-    to_int_vector(f, Coeffs.data(), Coeffs.size(), cf_int.data());
-
-    const size_t numblocks = (TM.rows + 3) >> 2;
-    const uint32_t p = (uint32_t)f.characteristic();
-    std::vector<int64_t> prev;
-    for (size_t block = 0; block < numblocks; ++block) {
-      const size_t off = block << 2;
-      const size_t firstcolumns = std::min<size_t>(4u, LCoB.rows - off);
-      for (size_t num = 0; num < firstcolumns; ++num) {
-        Mat A = LCoB;  // :289
-        std::pair<int, int> weight{-1, -1};
-        bool found = (block == 0) && (num == 0);  // :291
-        if (found) weight = {rnHw, cnHw};
-        const size_t nprev = off + num;
-        prev.assign(nprev * n, 0);
-        for (size_t i = 0; i < nprev; ++i) to_int_vector(f, &LCoB.at(i, 0), n, &prev[i * n]);
-        int brl = -1, bcl = -1;
-        uint64_t bidx = PLO_NO_INDEX;
-        const int rc = plo_lincomb_search(p, (int)n, (int)TM.cols, tm_int.data(), (int)off, (int)Coeffs.size(), cf_int.data(), (int)nprev,
-                                          nprev ? prev.data() : nullptr, weight.first, weight.second, &brl, &bcl, &bidx);
-        if (rc != PLO_OK) throw EngineError(rc, plo_last_error());
-        ++stats.searches;
-        stats.candidates += (unsigned long long)Coeffs.size() * Coeffs.size() * Coeffs.size() * Coeffs.size();
-        if (bidx != PLO_NO_INDEX) {
-          const size_t c = Coeffs.size();
-          const size_t ids[4] = {(size_t)(bidx / (c * c * c)), (size_t)((bidx / (c * c)) % c), (size_t)((bidx / c) % c), (size_t)(bidx % c)};
-          for (size_t j = 0; j < n; ++j) LCoB.at(nprev, j) = f.zero();
-          for (size_t t = 0; t < 4; ++t) if (off + t < n) LCoB.at(nprev, off + t) = Coeffs[ids[t]];
-          weight = {brl, bcl};
-          found = true;
-        }
-        for (size_t q = 0; !found; ++q) {  // canonical fallback :317-326
-          if (q >= TM.rows) throw RangeError("localSparsifier: no independent canonical vector");
-          weight = {-1, -1};
-          std::vector<Elt> w(TM.rows, f.zero());
-          w[q] = f.one();
-          found |= testLinComb(weight, LCoB, A, nprev, w, TM);
-          if (found) ++stats.fallbacks;
-        }
-      }
-    }
-    TM = mul(LCoB, TM);      // :339,343
-    TCoB = mul(LCoB, TCoB);  // :340,344
-  }
-
   // ---- FactorDiagonals (:354-375; Q18: first maximum in std::map order) -----------------
   void FactorDiagonals(Mat& TCoB, Mat& TM) const {
     for (size_t i = 0; i < TM.rows; ++i) {
@@ -345,14 +309,17 @@ struct Sparsifier {
   // ---- sparseLU (:523-568) / sparseILU (:576-604) -----------------------------------------
   bool sparseLU(Mat& QL, Mat& A, size_t sparsity) const {
     const Elim e = eliminate(A);
-    const bool sparser = density(e.U) < sparsity;
-    if (sparser) {
-      Mat C(f, A.rows, A.rows);
-      for (size_t k = 0; k < A.rows; ++k) for (size_t j = 0; j < A.rows; ++j) C.at(e.rowperm[k], j) = e.L.at(k, j);
-      A = e.U;
-      QL = C;
+    size_t du = 0;
+    for (const SRow& r : e.U) du += r.size();
+    if (du >= sparsity) return false;
+    Mat C(f, A.rows, A.rows);  // Pr^T . L
+    for (size_t k = 0; k < A.rows; ++k) {
+      C.at(e.rowperm[k], k) = f.one();
+      for (const auto& x : e.L[k]) C.at(e.rowperm[k], x.first) = x.second;
     }
-    return sparser;
+    A = dense_of(e.U, A.rows, A.cols);
+    QL = C;
+    return true;
   }
   bool sparseILU(Mat& TC, Mat& A, size_t sparsity) const {
     Mat QL = identity(A.rows);
@@ -361,44 +328,276 @@ struct Sparsifier {
     return sparser;
   }
 
-  // ---- SparseFactor (:473-513) ---------------------------------------------------------------
-  size_t SparseFactor(Mat& TICoB, Mat& TM, size_t start = 3u, size_t increment = 4u, size_t threshold = COEFFICIENT_SEARCH) {
-    size_t s2;
-    if (log) densityProfile(*log << "# [SpFc] Columns profile: ", s2, TM) << std::endl; else s2 = density(TM);
-    size_t numcoeffs = start, ss;
-    do {
-      ss = s2;
-      localSparsifier(TICoB, TM, numcoeffs);
-      FactorDiagonals(TICoB, TM);
-      if (log) densityProfile(*log << "# [SpFc] Density profile: ", s2, TM) << std::endl; else s2 = density(TM);
-      if (numcoeffs < threshold) numcoeffs += increment;
-    } while (s2 < ss);
-    return s2;
+  // =====================================================================================================================
+  // sparseAlternate (:609-661) as a resumable state machine.  One AlternateRun owns the transposed block TM, the accumulated
+  // inverse change of basis TICoB and the position inside
+  //   SparseFactor(3, +4, COEFFICIENT_SEARCH) ; SparseFactor(maxnumcoeff, +1, maxnumcoeff)      (:640-642, loops :497-510)
+  //     localSparsifier (:205-347): prelude -> for every inner block: rows via the GPU (+ canonical fallbacks) -> apply
+  // advance() runs host work until a device search is needed (returns true, `pending` filled) or the block is finished.
+  // =====================================================================================================================
+  struct Pending {  // one inner-block search waiting for the device
+    size_t off = 0, nprev = 0, c = 0;
+    std::vector<int64_t> prev, seed;
+    bool has_seed = false;
+    int init_rl = -1, init_cl = -1;
+  };
+  struct AlternateRun {
+    Mat TM, TICoB, LCoB;
+    std::ostringstream text;  // progress lines of this block
+    bool logging = false;
+    int phase = -1;           // -1 not started, 0/1 the two SparseFactor calls, 2 finished
+    size_t numcoeffs = 0, increment = 0, threshold = 0, ss = 0, s2 = 0, maxnumcoeff = 0;
+    // localSparsifier in flight
+    std::vector<Elt> Coeffs;
+    std::vector<int64_t> tm_int, cf_int;
+    int rnHw = -1, cnHw = -1;
+    size_t inner = 0, numblocks = 0, rows_done = 0;  // rows_done: rows of the current inner block already decided
+    Pending pending;
+  };
+
+  std::ostream* out_of(AlternateRun& R) { return R.logging ? &R.text : nullptr; }
+
+  void begin_alternate(AlternateRun& R, const Mat& M, size_t maxnumcoeff) {
+    Tick tick(stats.t_begin_alt);
+    R.logging = log != nullptr;
+    R.maxnumcoeff = maxnumcoeff;
+    R.TM = transpose(M);
+    R.TICoB = identity(M.cols);
+    FactorDiagonals(R.TICoB, R.TM);
+    const bool reduced = sparseILU(R.TICoB, R.TM, density(R.TM));
+    if (reduced && R.logging) {
+      size_t sl, su;
+      densityProfile(R.text << "# [sALT] GaussLo profile: ", sl, R.TICoB) << std::endl;
+      densityProfile(R.text << "# [sALT] GaussUp profile: ", su, R.TM) << std::endl;
+    }
+    begin_factor(R, 0);
+  }
+  void begin_factor(AlternateRun& R, int phase) {  // SparseFactor entry (:473-496)
+    R.phase = phase;
+    if (phase == 0) { R.numcoeffs = 3u; R.increment = 4u; R.threshold = COEFFICIENT_SEARCH; }
+    else { R.numcoeffs = R.maxnumcoeff; R.increment = 1u; R.threshold = R.maxnumcoeff; }
+    if (R.logging) densityProfile(R.text << "# [SpFc] Columns profile: ", R.s2, R.TM) << std::endl; else R.s2 = density(R.TM);
+    begin_local(R);
+  }
+  // localSparsifier up to the first search: nullspace prelude (:227-252), Coeffs (:256-270), integer images
+  struct Tick {
+    double& acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit Tick(double& a) : acc(a) {}
+    ~Tick() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  };
+  void begin_local(AlternateRun& R) {
+    Tick tick(stats.t_begin_local);
+    R.ss = R.s2;  // do { ss = s2; localSparsifier(...)
+    const Mat& TM = R.TM;
+    const size_t n = TM.rows;
+    R.LCoB = Mat(f, n, n);
+    R.cnHw = -1; R.rnHw = -1;
+    if (TM.rows > 1) {
+      // rows of TM^T by decreasing size -- the same std::sort call on (size, row) objects as the reference's on its rows (Q7);
+      // then the longest prefix of rank n-1: the prefix is extended row by row and an echelon basis tells when rank n is reached
+      struct Line { size_t size, row; };
+      std::vector<Line> order(TM.cols);
+      for (size_t j = 0; j < TM.cols; ++j) { size_t s = 0; for (size_t i = 0; i < n; ++i) s += !f.is_zero(TM.at(i, j)); order[j] = Line{s, j}; }
+      std::sort(order.begin(), order.end(), [](const Line& a, const Line& b) { return a.size > b.size; });
+      Mat basis(f, n, n);
+      std::vector<size_t> lead;  // pivot column of each basis row
+      size_t keep = order.size();
+      for (size_t t = 0; t < order.size(); ++t) {
+        std::vector<Elt> v(n);
+        for (size_t i = 0; i < n; ++i) v[i] = TM.at(i, order[t].row);
+        for (size_t b = 0; b < lead.size(); ++b)
+          if (!f.is_zero(v[lead[b]])) {
+            const Elt mlt = v[lead[b]];
+            for (size_t i = 0; i < n; ++i) v[i] = f.sub(v[i], f.mul(mlt, basis.at(b, i)));
+          }
+        size_t pc = n;
+        for (size_t i = 0; i < n; ++i) if (!f.is_zero(v[i])) { pc = i; break; }
+        if (pc == n) continue;
+        if (lead.size() + 1 == n) { keep = t; break; }  // this row would complete rank n: the prefix stops before it
+        const Elt ip = f.inv(v[pc]);
+        for (size_t i = 0; i < n; ++i) basis.at(lead.size(), i) = f.mul(v[i], ip);
+        lead.push_back(pc);
+      }
+      if (keep > 0) {
+        Mat N(f, keep, n);
+        for (size_t t = 0; t < keep; ++t) for (size_t i = 0; i < n; ++i) N.at(t, i) = TM.at(i, order[t].row);
+        std::vector<Elt> x;
+        nullspaceVector(N, x);
+        for (size_t i = 0; i < n; ++i) if (!f.is_zero(x[i])) R.LCoB.at(0, i) = x[i];
+        R.cnHw = (int)rowSize(R.LCoB, 0);  // number of NON-zeroes (sic, :242)
+        R.rnHw = 0;
+        for (size_t j = 0; j < TM.cols; ++j) {
+          Elt s = f.zero();
+          for (size_t i = 0; i < n; ++i)
+            if (!f.is_zero(R.LCoB.at(0, i)) && !f.is_zero(TM.at(i, j))) s = f.add(s, f.mul(R.LCoB.at(0, i), TM.at(i, j)));
+          R.rnHw += f.is_zero(s);
+        }
+      }
+    }
+    R.Coeffs = coefficients(TM, R.numcoeffs);
+    if (R.logging) {
+      R.text << "# [SPRF] linear combination coefficients: [";
+      for (size_t i = 0; i < R.Coeffs.size(); ++i) { if (i) R.text << ' '; print(R.text, R.Coeffs[i]); }
+      R.text << ']' << std::endl;
+    }
+    R.cf_int.resize(R.Coeffs.size());
+    to_int_columns(TM, R.tm_int);
+    to_int_vector(f, R.Coeffs.data(), R.Coeffs.size(), R.cf_int.data());
+    R.numblocks = (TM.rows + 3) >> 2;
+    R.inner = 0;
+    R.rows_done = 0;
+    post_search(R);
+  }
+  // the search for the undecided rows of the current inner block
+  void post_search(AlternateRun& R) {
+    const size_t n = R.TM.rows, off = R.inner << 2;
+    Pending& P = R.pending;
+    P = Pending();
+    P.off = off;
+    P.nprev = off + R.rows_done;
+    P.c = R.Coeffs.size();
+    P.prev.assign(P.nprev * n, 0);
+    for (size_t i = 0; i < P.nprev; ++i) to_int_vector(f, &R.LCoB.at(i, 0), n, &P.prev[i * n]);
+    if (R.inner == 0 && R.rows_done == 0) {  // found starts true with the nullspace weight (:290-295)
+      P.init_rl = R.rnHw; P.init_cl = R.cnHw;
+      P.has_seed = true;
+      P.seed.resize(n);
+      to_int_vector(f, &R.LCoB.at(0, 0), n, P.seed.data());
+    }
+  }
+  void set_row(AlternateRun& R, size_t row, uint64_t idx) {
+    const size_t n = R.TM.rows, off = R.inner << 2, c = R.Coeffs.size();
+    const size_t ids[4] = {(size_t)(idx / (c * c * c)), (size_t)((idx / (c * c)) % c), (size_t)((idx / c) % c), (size_t)(idx % c)};
+    for (size_t j = 0; j < n; ++j) R.LCoB.at(row, j) = f.zero();
+    for (size_t t = 0; t < 4; ++t) if (off + t < n) R.LCoB.at(row, off + t) = R.Coeffs[ids[t]];
+  }
+  void canonical_fallback(AlternateRun& R, size_t row) {  // :317-326
+    Mat A = R.LCoB;
+    std::pair<int, int> weight;
+    bool found = false;
+    for (size_t q = 0; !found; ++q) {
+      if (q >= R.TM.rows) throw RangeError("localSparsifier: no independent canonical vector");
+      weight = {-1, -1};
+      std::vector<Elt> w(R.TM.rows, f.zero());
+      w[q] = f.one();
+      found = testLinComb(weight, R.LCoB, A, row, w, R.TM);
+    }
+    ++stats.fallbacks;
+  }
+  // Results of the pending search: `nrows` decided rows (index PLO_NO_INDEX: the seed vector keeps row 0) and the quad status.
+  // Returns true when another search is pending, false when the block has finished.
+  bool consume(AlternateRun& R, int nrows, int status, const uint64_t* index) {
+    const size_t n = R.TM.rows, off = R.inner << 2;
+    const size_t nact = std::min<size_t>(4u, n - off);
+    const unsigned long long c4 = (unsigned long long)R.Coeffs.size() * R.Coeffs.size() * R.Coeffs.size() * R.Coeffs.size();
+    for (int t = 0; t < nrows; ++t) {
+      if (index[t] != PLO_NO_INDEX) set_row(R, off + R.rows_done, index[t]);
+      ++R.rows_done;
+      stats.candidates += c4;
+    }
+    if (status == PLO_QUAD_MISS) {
+      stats.candidates += c4;
+      // (block 0, num 0) starts with found == true even when the prelude produced no vector (weight (-1,-1), quirk Q5): the row
+      // then stays as the prelude left it; every other row without an admissible candidate takes a canonical vector
+      if (!(R.pending.has_seed && R.rows_done == 0)) canonical_fallback(R, off + R.rows_done);
+      ++R.rows_done;
+    } else if (status == PLO_QUAD_RANGE) {  // the device-side filter could not stay exact: this row through the one-row entry point
+      single_row(R);
+    }
+    if (R.rows_done < nact) { post_search(R); return true; }
+    R.rows_done = 0;
+    if (++R.inner < R.numblocks) { post_search(R); return true; }
+    return finish_local(R);
+  }
+  // one row through plo_lincomb_search (host-computed filter; wide outputs and the RANGE fallback)
+  void single_row(AlternateRun& R) {
+    const size_t n = R.TM.rows, off = R.inner << 2, nprev = off + R.rows_done;
+    post_search(R);
+    const Pending& P = R.pending;
+    int brl = -1, bcl = -1;
+    uint64_t bidx = PLO_NO_INDEX;
+    const int rc = plo_lincomb_search((uint32_t)f.characteristic(), (int)n, (int)R.TM.cols, R.tm_int.data(), (int)off, (int)P.c, R.cf_int.data(), (int)nprev,
+                                      nprev ? P.prev.data() : nullptr, P.init_rl, P.init_cl, &brl, &bcl, &bidx);
+    if (rc != PLO_OK) throw EngineError(rc, plo_last_error());
+    ++stats.searches;
+    stats.candidates += (unsigned long long)P.c * P.c * P.c * P.c;
+    if (bidx != PLO_NO_INDEX) set_row(R, nprev, bidx);
+    else if (!P.has_seed) canonical_fallback(R, nprev);
+    ++R.rows_done;
+  }
+  // end of localSparsifier (:335-346) and the do-while of SparseFactor (:497-510)
+  bool finish_local(AlternateRun& R) {
+    Tick tick(stats.t_finish_local);
+    R.TM = mul(R.LCoB, R.TM);
+    R.TICoB = mul(R.LCoB, R.TICoB);
+    FactorDiagonals(R.TICoB, R.TM);
+    if (R.logging) densityProfile(R.text << "# [SpFc] Density profile: ", R.s2, R.TM) << std::endl; else R.s2 = density(R.TM);
+    if (R.numcoeffs < R.threshold) R.numcoeffs += R.increment;
+    if (R.s2 < R.ss) { begin_local(R); return true; }
+    if (R.phase == 0) { begin_factor(R, 1); return true; }
+    R.phase = 2;
+    return false;
+  }
+  void finish_alternate(AlternateRun& R, Mat& CoB, Mat& Res) {
+    CoB = inverseTranspose(R.TICoB);
+    if (R.logging) { size_t sc; densityProfile(R.text << "# [sALT] CoBasis profile: ", sc, CoB) << std::endl; }
+    Res = transpose(R.TM);
+    if (log) *log << R.text.str() << std::flush;
+  }
+
+  // ---- lock-step driver over any number of independent blocks ------------------------------------------------------------
+  void run_blocks(std::vector<std::unique_ptr<AlternateRun>>& runs) {
+    const uint32_t p = (uint32_t)f.characteristic();
+    std::vector<AlternateRun*> active;
+    for (auto& r : runs) if (r->phase != 2) active.push_back(r.get());
+    while (!active.empty()) {
+      const int m = (int)active[0]->TM.cols;
+      std::vector<AlternateRun*> next;
+      if (m > 64) {  // wide outputs: tiled kernels behind the one-row entry point
+        for (AlternateRun* R : active) {
+          single_row(*R);
+          const uint64_t none = PLO_NO_INDEX;
+          if (consume(*R, 0, PLO_QUAD_DONE, &none)) next.push_back(R);
+        }
+        active.swap(next);
+        continue;
+      }
+      std::vector<plo_quad_problem> probs(active.size());
+      for (size_t b = 0; b < active.size(); ++b) {
+        AlternateRun& R = *active[b];
+        const Pending& P = R.pending;
+        plo_quad_problem& q = probs[b];
+        q.n = (int)R.TM.rows; q.off = (int)P.off; q.c = (int)P.c; q.nprev = (int)P.nprev;
+        q.TM = R.tm_int.data(); q.coeffs = R.cf_int.data();
+        q.prev_rows = P.nprev ? P.prev.data() : nullptr;
+        q.seed_vec = P.has_seed ? P.seed.data() : nullptr;
+        q.init_rl = P.init_rl; q.init_cl = P.init_cl;
+      }
+      const auto t0 = std::chrono::steady_clock::now();
+      const int rc = plo_lincomb_quad(p, m, (int)probs.size(), probs.data());
+      stats.device_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (rc != PLO_OK) throw EngineError(rc, plo_last_error());
+      ++stats.searches;
+      for (size_t b = 0; b < active.size(); ++b)
+        if (consume(*active[b], probs[b].nrows, probs[b].status, probs[b].index)) next.push_back(active[b]);
+      active.swap(next);
+    }
   }
 
   // ---- sparseAlternate (:609-661) -------------------------------------------------------------
   void sparseAlternate(Mat& CoB, Mat& Res, const Mat& M, size_t maxnumcoeff) {
-    Mat TM = transpose(M);
-    Mat TICoB = identity(M.cols);
-    FactorDiagonals(TICoB, TM);
-    const bool reduced = sparseILU(TICoB, TM, density(TM));
-    if (reduced && log) {
-      size_t sl, su;
-      densityProfile(*log << "# [sALT] GaussLo profile: ", sl, TICoB) << std::endl;
-      densityProfile(*log << "# [sALT] GaussUp profile: ", su, TM) << std::endl;
-    }
-    SparseFactor(TICoB, TM);                                   // :640
-    SparseFactor(TICoB, TM, maxnumcoeff, 1u, maxnumcoeff);      // :642
-    CoB = inverseTranspose(TICoB);
-    if (log) { size_t sc; densityProfile(*log << "# [sALT] CoBasis profile: ", sc, CoB) << std::endl; }
-    Res = transpose(TM);
+    std::vector<std::unique_ptr<AlternateRun>> runs;
+    runs.emplace_back(new AlternateRun());
+    begin_alternate(*runs[0], M, maxnumcoeff);
+    run_blocks(runs);
+    finish_alternate(*runs[0], CoB, Res);
   }
 
   // ---- blockSparsifier (:666-748) --------------------------------------------------------------
   int blockSparsifier(Mat& CoB, Mat& Res, const Mat& M, size_t blocksize, size_t maxnumcoeff, bool initialElimination) {
     if (blocksize <= 1) { sparseAlternate(CoB, Res, M, maxnumcoeff); return 0; }
     const size_t m = M.rows, n = M.cols;
-    Mat U(f, n, m), L = identity(n);
+    Mat U(f, 0, 0), L = identity(n);
     bool reduced = initialElimination;
     if (initialElimination) {
       U = transpose(M);
@@ -410,30 +609,34 @@ struct Sparsifier {
       }
     }
     const Mat A = reduced ? transpose(U) : M;
-    std::vector<Mat> vC, vR;
-    for (size_t c0 = 0; c0 < n; c0 += blocksize) {  // separateColumnBlocks :88-114
+    // separateColumnBlocks :88-114 ; every block is an independent sparseAlternate (:710-723): they advance in lock step
+    std::vector<std::unique_ptr<AlternateRun>> runs;
+    std::vector<size_t> widths;
+    for (size_t c0 = 0; c0 < n; c0 += blocksize) {
       const size_t w = std::min(blocksize, n - c0);
       Mat B(f, m, w);
       for (size_t i = 0; i < m; ++i) for (size_t j = 0; j < w; ++j) B.at(i, j) = A.at(i, c0 + j);
-      Mat C(f, w, w), R(f, m, w);
-      sparseAlternate(C, R, B, maxnumcoeff);
-      vC.push_back(C);
-      vR.push_back(R);
+      runs.emplace_back(new AlternateRun());
+      begin_alternate(*runs.back(), B, maxnumcoeff);
+      widths.push_back(w);
     }
+    run_blocks(runs);
     Res = Mat(f, m, n);
     CoB = Mat(f, n, n);
-    size_t c0 = 0;
     Mat TCoB(f, n, n);
-    for (size_t b = 0; b < vC.size(); ++b) {
-      const size_t w = vC[b].cols;
-      for (size_t i = 0; i < m; ++i) for (size_t j = 0; j < w; ++j) Res.at(i, c0 + j) = vR[b].at(i, j);  // augmentedMatrix :726
+    size_t c0 = 0;
+    for (size_t b = 0; b < runs.size(); ++b) {
+      const size_t w = widths[b];
+      Mat C(f, w, w), R(f, m, w);
+      finish_alternate(*runs[b], C, R);
+      for (size_t i = 0; i < m; ++i) for (size_t j = 0; j < w; ++j) Res.at(i, c0 + j) = R.at(i, j);  // augmentedMatrix :726
       if (reduced) {  // :728-741
         Mat Lb(f, n, w);
         for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < w; ++j) Lb.at(i, j) = L.at(i, c0 + j);
-        const Mat B = mul(Lb, transpose(vC[b]));
+        const Mat B = mul(Lb, transpose(C));
         for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < w; ++j) TCoB.at(i, c0 + j) = B.at(i, j);
       } else {  // diagonalMatrix :743
-        for (size_t i = 0; i < w; ++i) for (size_t j = 0; j < w; ++j) CoB.at(c0 + i, c0 + j) = vC[b].at(i, j);
+        for (size_t i = 0; i < w; ++i) for (size_t j = 0; j < w; ++j) CoB.at(c0 + i, c0 + j) = C.at(i, j);
       }
       c0 += w;
     }

@@ -24,19 +24,9 @@
 #include <type_traits>
 #include <vector>
 
-#include "host/exact.hpp"
-#include "plo_device.cuh"
+#include "lincomb_common.cuh"
 
 namespace plo {
-
-constexpr int kLcThreads = 128;
-constexpr int kIdxBits = 36;
-constexpr unsigned long long kIdxMask = (1ull << kIdxBits) - 1ull;
-
-// key = (rl+1) << 48 | (cl+1) << 36 | (2^36 - 2 - index); the weight seed uses low bits 2^36-1
-__host__ __device__ __forceinline__ unsigned long long pack_key(int rl, int cl, unsigned long long low) {
-  return ((unsigned long long)(rl + 1) << 48) | ((unsigned long long)(cl + 1) << kIdxBits) | low;
-}
 
 template <typename T>
 struct LcParams {
@@ -56,26 +46,6 @@ struct LcParams {
   const unsigned long long* seed;   // [b]
   unsigned long long* result;       // [b]
 };
-
-template <bool MODP>
-__device__ __forceinline__ bool independent(const long long* __restrict__ phi, int nphi, const long long* __restrict__ coef,
-                                            unsigned int p, int i, int j, int k, int l) {
-  const long long w[4] = {coef[i], coef[j], coef[k], coef[l]};
-  for (int q = 0; q < nphi; ++q) {
-    if (MODP) {
-      unsigned long long s = 0;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) s += ((unsigned long long)phi[q * 4 + t] * (unsigned long long)w[t]) % p;
-      if (s % p) return true;
-    } else {
-      long long s = 0;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) s += phi[q * 4 + t] * w[t];
-      if (s) return true;
-    }
-  }
-  return false;
-}
 
 template <typename T, int MPAD, bool MODP>
 __global__ void __launch_bounds__(kLcThreads) lincomb_kernel(const LcParams<T> prm) {
@@ -346,52 +316,6 @@ struct plo_lincomb_plan {
 
 namespace {
 
-inline int pad_m(int m) {
-  const int opts[] = {8, 16, 32, 48, 64};
-  for (int o : opts) if (m <= o) return o;
-  return -1;
-}
-
-// One reduced functional -> integers: clear denominators over Q; residues are used as they are mod p.
-inline void phi_row(const plo::host::QField&, const plo::host::Rat* row, long long* out) {
-  long long lcd = 1;
-  for (int t = 0; t < 4; ++t) { const long long g = (long long)plo::host::wgcd(lcd, row[t].den); lcd = lcd / g * row[t].den; }
-  for (int t = 0; t < 4; ++t) out[t] = row[t].num * (lcd / row[t].den);
-}
-inline void phi_row(const plo::host::ZpField&, const int64_t* row, long long* out) {
-  for (int t = 0; t < 4; ++t) out[t] = row[t];
-}
-
-// Annihilator functionals of span(prev rows) restricted to the live positions off..off+nact-1,
-// reduced to an independent set (<= 4 vectors of 4 entries).  Returns false if the previous rows
-// are linearly dependent (then rank(Cand) can never exceed num: plinopt_sparsify.inl:173-175).
-template <class F>
-bool annihilators(const F& f, int n, int nprev, const int64_t* prev, int off, int nact, std::vector<long long>& phi, int& nphi) {
-  using namespace plo::host;
-  phi.assign(16, 0);
-  nphi = 0;
-  std::vector<std::vector<typename F::Elt>> basis;
-  if (nprev == 0) {
-    for (int t = 0; t < nact; ++t) { phi[nphi * 4 + t] = 1; ++nphi; }  // everything non-zero is independent
-    return true;
-  }
-  Dense<F> A(f, (size_t)nprev, (size_t)n);
-  for (int i = 0; i < nprev; ++i)
-    for (int j = 0; j < n; ++j) A.at(i, j) = f.modular ? f.from_ratio(prev[(size_t)i * n + j], 1) : f.from_int(prev[(size_t)i * n + j]);
-  size_t rk = 0;
-  basis = nullspace(f, A, &rk);
-  if ((int)rk < nprev) return false;
-  Dense<F> R(f, basis.size(), 4);
-  for (size_t q = 0; q < basis.size(); ++q)
-    for (int t = 0; t < nact; ++t) R.at(q, t) = basis[q][off + t];
-  const std::vector<size_t> piv = rref(f, R);
-  for (size_t q = 0; q < piv.size(); ++q) {
-    phi_row(f, &R.at(q, 0), &phi[(size_t)nphi * 4]);
-    ++nphi;
-  }
-  return true;
-}
-
 template <typename T>
 void fill_tables(uint32_t p, int n, int m, int off, int nact, int c, int mpad, const int64_t* TM, const int64_t* coef,
                  T* t0, T* t1, T* t2, T* t3) {
@@ -426,7 +350,7 @@ void plo_lincomb_plan_destroy(plo_lincomb_plan* pl) {
 int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int n, int m, const int64_t* TM, int off,
                             int c, const int64_t* coeffs, int nprev, const int64_t* prev_rows, const int* init_rl,
                             const int* init_cl) {
-  if (!plan || !TM || !coeffs || nbatch < 1 || n < 1 || m < 1 || c < 1 || c > 512 || off < 0 || off >= n || (off & 3) ||
+  if (!plan || !TM || !coeffs || nbatch < 1 || n < 1 || m < 1 || c < 1 || c > 511 || off < 0 || off >= n || (off & 3) ||
       nprev < 0 || nprev > n || (nprev > 0 && !prev_rows) || n > 4000 || m > 65000) {
     set_error("plo_lincomb_plan_create: bad argument");
     return PLO_E_ARG;
@@ -520,6 +444,12 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
       if (p) { plo::host::ZpField f((int64_t)p); ok = annihilators(f, n, nprev, pv.data() + (size_t)b * nprev * n, off, nact, ph, np); }
       else { plo::host::QField f; ok = annihilators(f, n, nprev, pv.data() + (size_t)b * nprev * n, off, nact, ph, np); }
       if (!ok) { pl->trivially_none[b] = 1; np = 0; ph.assign(16, 0); }
+      if (!p) {  // the device evaluates phi . w in int64: 4 . |phi| . |coef| must stay below 2^63
+        unsigned __int128 mp = 0, mc = 0;
+        for (long long v : ph) { const unsigned __int128 a = v < 0 ? -(__int128)v : v; if (a > mp) mp = a; }
+        for (int l = 0; l < c; ++l) { const unsigned __int128 a = cfb[l] < 0 ? -(__int128)cfb[l] : cfb[l]; if (a > mc) mc = a; }
+        if (mp * mc * 4 >= ((unsigned __int128)1 << 63)) throw plo::host::RangeError("annihilator functional times coefficient exceeds 63 bits");
+      }
       std::copy(ph.begin(), ph.end(), phi.begin() + (size_t)b * 16);
       nphi[b] = np;
       pl->h_seed[b] = pack_key(pl->h_init_rl[b], pl->h_init_cl[b], kIdxMask);

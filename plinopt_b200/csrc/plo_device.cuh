@@ -31,6 +31,7 @@ int sm_count();
 // (plo_release_workspace() returns them to the driver).  pool_free() synchronises the device first, like cudaFree.
 cudaError_t pool_alloc_bytes(void** p, size_t bytes);
 void pool_free(void* p);
+void quad_release_all();  // lincomb_quad.cu: per-device staging buffers and stream (called by plo_release_workspace)
 template <class T>
 inline cudaError_t pool_alloc(T** p, size_t bytes) { return pool_alloc_bytes(reinterpret_cast<void**>(p), bytes); }
 

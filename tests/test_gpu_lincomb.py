@@ -50,11 +50,14 @@ def run_steps(capi, TM, p, c, nsteps_blocks=None):
     checked = 0
     for block in range(nblocks):
         off = 4 * block
+        prev0 = lcob_int[:off].copy()
+        trace = []
         for num in range(min(4, n - off)):
             exp = O.lincomb_search(p, tm_num, tm_den, off, num, cf_num, cf_den, lcob_num, lcob_den)
             got = capi.lincomb_search(p, tm_int, off, cf_int, lcob_int[:off + num] if off + num else None)
             exp_idx = None if exp[2] < 0 else exp[2]
             assert (got[0], got[1], got[2]) == (exp[0], exp[1], exp_idx), (block, num, got, exp)
+            trace.append((exp[0], exp[1], exp_idx))
             checked += 1
             cc = len(cf_num)
             if exp_idx is None:  # reference fallback: canonical vector (plinopt_sparsify.inl:317-326)
@@ -70,7 +73,24 @@ def run_steps(capi, TM, p, c, nsteps_blocks=None):
                 if off + t < n:
                     lcob_num[off + num, off + t] = cf_num[ids[t]]; lcob_den[off + num, off + t] = cf_den[ids[t]]
                     lcob_int[off + num, off + t] = cf_int[ids[t]]
+        check_quad(capi, p, tm_int, off, cf_int, prev0, trace)
     return checked
+
+
+def check_quad(capi, p, tm_int, off, cf_int, prev0, trace):
+    """The same inner block through plo_lincomb_quad (one launch sequence for all its rows): identical rows up to the first row
+    without an admissible candidate, where the call stops with PLO_QUAD_MISS (the canonical fallback is the host's)."""
+    if tm_int.shape[1] > 64:  # wide outputs keep the one-step entry point (tiled count + pick kernels): reported, not silently handled
+        with pytest.raises(capi.PloError) as e:
+            capi.lincomb_quad(p, [dict(TM=tm_int, off=off, coeffs=cf_int)])
+        assert e.value.code == capi.E_SHAPE
+        return
+    (status, rows), = capi.lincomb_quad(p, [dict(TM=tm_int, off=off, coeffs=cf_int, prev_rows=prev0 if len(prev0) else None)])
+    miss = next((t for t, r in enumerate(trace) if r[2] is None), None)
+    if miss is None:
+        assert status == capi.QUAD_DONE and rows == trace, (status, rows, trace)
+    else:
+        assert status == capi.QUAD_MISS and rows == trace[:miss], (status, rows, trace)
 
 
 def transpose(M):
@@ -255,3 +275,83 @@ def test_c5_first_block_of_32x32x32(capi):
         parts.append([(int(a), int(b), None if int(i) == capi.NO_INDEX else int(i)) for a, b, i in zip(*plan.result())])
     assert [S.lincomb_unkey(max(S.lincomb_key(*parts[r][0]) for r in range(3)))] == full
     plan.close()
+
+
+def sequential_rows(capi, p, tm_int, off, cf_int, prev0, init, seed_vec):
+    """Reference behaviour through the one-step entry point: four successive searches, the winner (or the seed vector when it keeps
+    row 0, plinopt_sparsify.inl:290-295) appended to the previous rows."""
+    n = tm_int.shape[0]
+    prev = [list(r) for r in prev0]
+    rows = []
+    cc = len(cf_int)
+    for num in range(min(4, n - off) - max(0, len(prev) - off)):
+        irl, icl = init if num == 0 else (-1, -1)
+        rl, cl, idx = capi.lincomb_search(p, tm_int, off, cf_int, np.array(prev, dtype=np.int64) if prev else None, irl, icl)
+        if idx is None:
+            if num == 0 and init != (-1, -1) and seed_vec is not None:
+                rows.append((rl, cl, None)); prev.append(list(seed_vec)); continue
+            break
+        rows.append((rl, cl, idx))
+        w = [0] * n
+        ids = [idx // cc ** 3, (idx // cc ** 2) % cc, (idx // cc) % cc, idx % cc]
+        for t in range(4):
+            if off + t < n:
+                w[off + t] = int(cf_int[ids[t]])
+        prev.append(w)
+    return rows
+
+
+@pytest.mark.parametrize("p", [0, 101, P31])
+def test_quad_batch_with_seeds_matches_sequential_searches(capi, p):
+    """Several problems with different c in ONE call; weight seeds that lose, win (device goes on with the seed vector) and a
+    seed without vector (PLO_QUAD_SEED)."""
+    M = O.dense_fractions("4x4x4_48_rational_L")
+    probs, expect = [], []
+    for blk, c, init, with_vec in [(0, 5, (-1, -1), False), (1, 7, (3, 1), True), (2, 9, (47, 2), True), (3, 4, (47, 2), False), (0, 11, (30, 0), True)]:
+        TM = transpose([row[4 * blk:4 * blk + 4] for row in M])
+        if p == 0:
+            tm_int = col_scaled(TM)
+            cf_num, cf_den = O.coeffs(TM, 0, c)
+            lc = 1
+            for d in cf_den:
+                lc = lc * int(d) // math.gcd(lc, int(d))
+            cf_int = np.array([int(a) * (lc // int(d)) for a, d in zip(cf_num, cf_den)], dtype=np.int64)
+        else:
+            tm_int = np.array([[(v.numerator % p) * pow(v.denominator % p, -1, p) % p for v in row] for row in TM], dtype=np.int64)
+            cf_int = O.coeffs(tm_int.tolist(), p, c)[0].copy()
+        seed_vec = np.array([1, 2, 0, 1 if p == 0 else p - 1], dtype=np.int64) if with_vec else None
+        probs.append(dict(TM=tm_int, off=0, coeffs=cf_int, init_rl=init[0], init_cl=init[1], seed_vec=seed_vec))
+        expect.append(sequential_rows(capi, p, tm_int, 0, cf_int, [], init, seed_vec))
+    got = capi.lincomb_quad(p, probs)
+    for (status, rows), exp, pr in zip(got, expect, probs):
+        seed_kept_without_vector = len(exp) == 0 and (pr["init_rl"], pr["init_cl"]) != (-1, -1)
+        if seed_kept_without_vector:
+            assert status == capi.QUAD_SEED and rows == [(pr["init_rl"], pr["init_cl"], None)]
+        else:
+            assert rows == exp, (rows, exp)
+            assert status == (capi.QUAD_DONE if len(rows) == 4 else capi.QUAD_MISS)
+    assert any(r and r[0][2] is None for _, r in got), "no case exercised a winning seed"
+
+
+def test_quad_with_dependent_canonical_previous_row(capi):
+    """Resuming inside a block after a canonical fallback row (e_1): the three remaining rows, independent of it."""
+    M = O.dense_fractions("3x4x7_63_rational_R")
+    TM = transpose([row[:4] for row in M])
+    tm_int = col_scaled(TM)
+    cf_int = np.array([0, 1, -1, 2, -2], dtype=np.int64)
+    prev0 = np.array([[0, 1, 0, 0]], dtype=np.int64)
+    (status, rows), = capi.lincomb_quad(0, [dict(TM=tm_int, off=0, coeffs=cf_int, prev_rows=prev0)])
+    exp = sequential_rows(capi, 0, tm_int, 0, cf_int, prev0, (-1, -1), None)
+    assert rows == exp and len(rows) == 3 and status == capi.QUAD_DONE
+
+
+@pytest.mark.parametrize("p,c", [(0, 7), (P31, 11), (P31, 24), (0, 23)])
+def test_quad_multi_kernel_path(capi, monkeypatch, p, c):
+    """Searches too large for the one-launch kernel (c^4 bytes of counts beyond one SM's shared memory: c >= 22) run as tables +
+    count + four pick kernels; PLO_QUAD_NOSMALL=1 forces that path for small c too.  Same rows either way."""
+    monkeypatch.setenv("PLO_QUAD_NOSMALL", "1")
+    M = O.dense_fractions("4x4x4_48_rational_L")
+    TM = transpose([row[4:8] for row in M])
+    assert run_steps(capi, TM, p, c) == 4
+    monkeypatch.delenv("PLO_QUAD_NOSMALL")
+    assert run_steps(capi, TM, p, c) == 4
