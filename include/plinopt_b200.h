@@ -210,6 +210,11 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
 int plo_orbit_plan_run(plo_orbit_plan* plan, uint64_t lo, uint64_t hi, void* stream);
 int plo_orbit_plan_result(plo_orbit_plan* plan, void* stream, plo_orbit_best* best);
 int plo_orbit_plan_launches(const plo_orbit_plan* plan);
+/* Multi-GPU plumbing without a host hop (the reference analogue is the `omp critical` of src/orbiter.cpp:298): writes the winner of
+ * the last run on `stream` into slot `rank` of a DEVICE table of world x 4 int64 words (order-preserving bits of the score, index,
+ * nnz, nno; INT64_MAX elsewhere).  One all-reduce(MIN) over the table (ncclAllReduce / torch.distributed on the same buffer)
+ * then leaves every local winner on every rank; the global one is the lexicographic minimum of (score[, nno], index). */
+int plo_orbit_plan_pack(plo_orbit_plan* plan, int64_t* slots_device, int rank, int world, void* stream);
 /* Name of the sweep kernel plo_orbit_plan_run launches for this plan and the number of candidate-matrix entries one 32-bit
  * multiply-add carries in it (1 scalar, 2 sixteen-bit lanes, 4 eight-bit lanes): the roofline of a sweep is stated against
  * lanes x the measured IMAD peak, and a profile is only quoted for the kernel it was taken from. */

@@ -26,7 +26,7 @@ SYMBOLS = [
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_quad", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
-    "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_kernel", "plo_orbit_magnitude_bounds", "plo_orbit_plan_survivors", "plo_selftest_matrix_index", "plo_orbit_plan_destroy",
+    "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_pack", "plo_orbit_plan_kernel", "plo_orbit_magnitude_bounds", "plo_orbit_plan_survivors", "plo_selftest_matrix_index", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
     "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
@@ -322,6 +322,12 @@ class OrbitPlan:
         best = OrbitBest()
         _check(lib().plo_orbit_plan_result(self._h, C.c_void_p(stream), C.byref(best)))
         return _best_tuple(best)
+
+    def pack(self, slots_ptr, rank, world, stream=0):
+        """Winner of the last run -> slot `rank` of a device table of world x 4 int64 words (see plo_orbit_plan_pack)."""
+        f = lib().plo_orbit_plan_pack
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _check(f(self._h, C.c_void_p(slots_ptr), rank, world, C.c_void_p(stream)))
 
     def survivors(self, lo, hi, nnz=0, nno=0, score=0.0, capacity=1 << 16):
         """Candidates of [lo,hi) not worse than the threshold (sparsity plans: (nnz, nno); growth-factor plans: score), sorted by

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kSmallThreads) quad_small_kernel(const QuadDes
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long sh_phi[4 * kMaxPhi];
   __shared__ int sh_nphi, sh_stop;
-  __shared__ unsigned long long red[32], sh_res[4];
+  __shared__ unsigned long long red[32], sh_res[4], sh_best;
   __shared__ __align__(16) typename QuadRing<MODP>::V sh_ws[kPrepWords];
   constexpr int VEC = 16 / sizeof(T);
   const int b = blockIdx.x;
@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(kSmallThreads) quad_small_kernel(const QuadDes
     const T* t0 = tabs; const T* t1 = t0 + tab; const T* t2 = t1 + tab; const T* t3 = t2 + tab;
     const T SENT = (T)(~(T)0) >> (MODP ? 0 : 1);
     const unsigned nprefix = (unsigned)c * c * c;
+    const bool small_p = MODP && p <= 0x80000000u;
     for (unsigned q = threadIdx.x; q < nprefix; q += kSmallThreads) {
       const int k = (int)(q % (unsigned)c);
       const unsigned qq = q / (unsigned)c;
@@ -457,10 +458,18 @@ __global__ void __launch_bounds__(kSmallThreads) quad_small_kernel(const QuadDes
       for (int e = 0; e < MPAD; ++e) {
         const T a0 = t0[(size_t)i * MPAD + e], a1 = t1[(size_t)j * MPAD + e], a2 = t2[(size_t)k * MPAD + e];
         if (MODP) {
-          unsigned long long sum = (unsigned long long)a0 + a1 + a2;
-          sum -= sum >= p ? p : 0u;
-          sum -= sum >= p ? p : 0u;
-          nb[e] = (T)(sum ? p - sum : 0ull);
+          if (small_p) {  // p <= 2^31: the sum of two residues fits 32 bits -- a third of the instructions of the 64-bit form
+            unsigned t32 = (unsigned)a0 + (unsigned)a1;
+            t32 -= t32 >= p ? p : 0u;
+            t32 += (unsigned)a2;
+            t32 -= t32 >= p ? p : 0u;
+            nb[e] = (T)(t32 ? p - t32 : 0u);
+          } else {
+            unsigned long long sum = (unsigned long long)a0 + a1 + a2;
+            sum -= sum >= p ? p : 0u;
+            sum -= sum >= p ? p : 0u;
+            nb[e] = (T)(sum ? p - sum : 0ull);
+          }
         } else {
           nb[e] = (T)0 - (a0 + a1 + a2);
         }
@@ -493,7 +502,7 @@ __global__ void __launch_bounds__(kSmallThreads) quad_small_kernel(const QuadDes
   for (int num = 0; num < d.npick; ++num) {
     if (threadIdx.x < 32) {
       const int rc = quad_prepare<MODP>(d, coef, sh_res, num, sh_phi, &sh_nphi, sh_ws);
-      if (threadIdx.x == 0) sh_stop = rc;
+      if (threadIdx.x == 0) { sh_stop = rc; sh_best = sh_res[num]; }
     }
     __syncthreads();
     if (sh_stop) break;
@@ -502,9 +511,11 @@ __global__ void __launch_bounds__(kSmallThreads) quad_small_kernel(const QuadDes
     unsigned long long best = seed;
     // A thread owns ~c^4/512 candidates: too few for a running best to filter anything.  Instead it walks ITS candidates in
     // decreasing key order -- the largest key below `limit`, then the filter for that one candidate only -- until one passes.
+    // sh_best carries the best admissible key anyone has found so far: a thread stops as soon as its remaining keys fall below it.
     unsigned long long limit = ~0ull;
     for (;;) {
-      unsigned long long loc = seed;
+      const unsigned long long floor_key = *reinterpret_cast<volatile unsigned long long*>(&sh_best);
+      unsigned long long loc = floor_key;
       int loc_rl1 = (int)(loc >> 48), wi = 0, wj = 0, wk = 0, wl = 0;
       for (unsigned g = threadIdx.x; g < nchunks; g += kSmallThreads) {
         unsigned idx = g * 16u;
@@ -524,8 +535,8 @@ __global__ void __launch_bounds__(kSmallThreads) quad_small_kernel(const QuadDes
           if (++l == c) { l = 0; if (++k == c) { k = 0; if (++j == c) { j = 0; ++i; } } }
         }
       }
-      if (loc == seed) break;  // nothing of this thread beats the seed
-      if (quad_independent<MODP>(sh_phi, nphi, coef, p, d.m64, wi, wj, wk, wl)) { best = loc; break; }
+      if (loc == floor_key) break;  // nothing left in this thread that beats the best known key
+      if (quad_independent<MODP>(sh_phi, nphi, coef, p, d.m64, wi, wj, wk, wl)) { best = loc; atomicMax(&sh_best, loc); break; }
       limit = loc;
     }
 #pragma unroll
@@ -774,7 +785,11 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
   }
 
   cudaStream_t st = Q.st;
+  const bool timing = getenv("PLO_TIMING") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (timing) { for (auto& x : ev) cudaEventCreate(&x); cudaEventRecord(ev[0], st); }
   PLO_CUDA(cudaMemcpyAsync(Q.d_stage, Q.h_stage, h2d_bytes, cudaMemcpyHostToDevice, st));
+  if (timing) cudaEventRecord(ev[1], st);
   const QuadDesc* dd = reinterpret_cast<const QuadDesc*>(Q.d_stage);
   const long long* dstage = reinterpret_cast<const long long*>(Q.d_stage + desc_bytes);
   unsigned char* dzf = Q.d_stage + zf_off0;
@@ -817,8 +832,17 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
     PLO_CUDA(cudaGetLastError());
   }
   }
+  if (timing) cudaEventRecord(ev[2], st);
   PLO_CUDA(cudaMemcpyAsync(Q.h_res, dres, res_bytes, cudaMemcpyDeviceToHost, st));  // keys and status words are contiguous
+  if (timing) cudaEventRecord(ev[3], st);
   PLO_CUDA(cudaStreamSynchronize(st));
+  if (timing) {
+    float a = 0, b2 = 0, c2 = 0;
+    cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b2, ev[1], ev[2]); cudaEventElapsedTime(&c2, ev[2], ev[3]);
+    fprintf(stderr, "# [B200] plo_lincomb_quad: %d problems, c <= %d, %s path: h2d %.1f us (%zu B), kernels %.1f us, d2h %.1f us\n", nproblems, cmaxall,
+            small ? "one-launch" : "multi-kernel", a * 1e3, h2d_bytes, b2 * 1e3, c2 * 1e3);
+    for (auto& x : ev) cudaEventDestroy(x);
+  }
 
   const int* hstatus = reinterpret_cast<const int*>(Q.h_res + (size_t)nproblems * 4);
   for (int b = 0; b < nproblems; ++b) {

@@ -1916,6 +1916,28 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   return PLO_OK;
 }
 
+// The winner of the last run as one slot of a world x 4 table of int64 words (order-preserving bits of the score, index, nnz,
+// nno; INT64_MAX everywhere else): after an all-reduce(MIN) over the table every rank holds every local winner, and the global
+// one is the lexicographic minimum -- no host round trip between the sweep and the collective.
+__global__ void orbit_pack_slot_kernel(const plo_orbit_best* __restrict__ out, long long* __restrict__ slots, int rank, int world) {
+  for (int w = threadIdx.x; w < world * 4; w += blockDim.x) slots[w] = 0x7fffffffffffffffll;
+  __syncthreads();
+  if (threadIdx.x == 0 && out->index != ~0ull && out->index <= 0x7fffffffffffffffull) {
+    slots[rank * 4 + 0] = __double_as_longlong(out->score);  // score >= 0: IEEE bits order like integers
+    slots[rank * 4 + 1] = (long long)out->index;
+    slots[rank * 4 + 2] = out->nnz;
+    slots[rank * 4 + 3] = out->nno;
+  }
+}
+
+int plo_orbit_plan_pack(plo_orbit_plan* pl, int64_t* slots, int rank, int world, void* stream) {
+  if (!pl || !slots || world < 1 || rank < 0 || rank >= world) { set_error("plo_orbit_plan_pack: bad argument"); return PLO_E_ARG; }
+  if (pl->wide) { set_error("plo_orbit_plan_pack: the 64-bit path picks its winner on the host (use plo_orbit_plan_result)"); return PLO_E_SHAPE; }
+  orbit_pack_slot_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(pl->d_out, reinterpret_cast<long long*>(slots), rank, world);
+  PLO_CUDA(cudaGetLastError());
+  return PLO_OK;
+}
+
 int plo_selftest_matrix_index(void) { return matrix_index_mismatches<2, 48>() + matrix_index_mismatches<3, 7776>(); }
 
 int plo_orbit_plan_launches(const plo_orbit_plan*) { return 2; }

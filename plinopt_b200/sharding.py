@@ -89,6 +89,8 @@ def lincomb_key(rl, cl, idx):
     """Order-preserving int64 image of a sparsifier search result: maximum of (rl, cl, -index)
     (strict '>' acceptance of plinopt_sparsify.inl:183-184 = first maximiser in enumeration order).
     idx None (no candidate beat the seed) maps below every real candidate of the same weight."""
+    if idx is not None and int(idx) >= (1 << LC_IDX_BITS) - 1:
+        raise ValueError("candidate index does not fit the 36-bit key field (c <= 511)")
     low = 0 if idx is None else (1 << LC_IDX_BITS) - 1 - int(idx)
     return ((int(rl) + 1) << 48) | ((int(cl) + 1) << LC_IDX_BITS) | low
 

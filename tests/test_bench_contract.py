@@ -26,6 +26,11 @@ def test_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "candidates_per_gpu_per_step" in d["config"]  # same key names as the engine arm's config
+    cfg = d["configs"]  # the other BASELINE configs, CPU oracle on the same inputs
+    assert cfg["C4_orbit_3x4x7_nnz"]["value"] > 0 and cfg["C4_orbit_3x4x7_G2"]["value"] > 0
+    assert cfg["C3_sparsifier_4x4x4"]["search_1core"]["cores"] == 1 and cfg["C3_sparsifier_4x4x4"]["pipeline_c11"]["value"] > 0
+    assert cfg["C5_mmcheck_32x32x32"]["all_correct"] and cfg["C5_mmcheck_32x32x32"]["unit"] == "samples/s"
 
 
 @pytest.mark.gpu
@@ -33,9 +38,20 @@ def test_engine_arm_line(capi):
     d = run_bench(["--steps", "2", "--warmup", "3", "--batch-log2", "26", "--cpu-seconds", "1"])
     assert BASE_KEYS <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["value"] > 1e9 and d["scaling"] == "weak"
-    assert d["gpu_launches"] == 2 * 2  # sweep + final kernel per step
+    assert d["gpu_launches"] == 2 * 3  # sweep + final + slot-pack kernel per step
     r = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and 0 < r["frac"] < 2 and r["peak"] > 1
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and 0 < r["frac"] < 1 and r["peak"] > 1
+    assert r["kernel"] == "orbit_sweep8x_kernel" and r["lanes_per_imad"] == 4  # frac is stated against lanes x the measured IMAD peak
+    cfg = d["configs"]
+    for key in ("C4_orbit_3x4x7_nnz", "C4_orbit_3x4x7_G2"):
+        e = cfg[key]
+        assert e["value"] > 1e8 and e["roofline"]["lanes_per_imad"] == 4 and 0 < e["roofline"]["frac"] < 1 and e["e2e"]["value"] > 0 and e["cpu_baseline"]["value"] > 0
+    c3 = cfg["C3_sparsifier_4x4x4"]
+    assert c3["search_c128"]["value"] > 1e10 and c3["search_c128"]["e2e"]["value"] > 1e10 and c3["pipeline_c11"]["consistent"]
+    assert c3["pipeline_c11"]["value"] > 10 * c3["pipeline_c11"]["round1_value"] / 2
+    c5 = cfg["C5_mmcheck_32x32x32"]
+    assert c5["batch_4096"]["all_samples_agree"] and c5["batch_32"]["all_samples_agree"] and c5["batch_4096"]["value"] > 1e5
+    assert cfg["C2_strong"]["scaling"] == "strong" and cfg["C2_strong"]["value"] > 1e9
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 336 and e["d2h_bytes_per_step"] == 24
     c = d["clocks"]
