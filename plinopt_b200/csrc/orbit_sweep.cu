@@ -33,6 +33,12 @@ __constant__ uint32_t c_pkeys[20];
 constexpr int kConst2Ints = 4300;   // 17 KB: pairs of rows packed at 8-bit spacing for the four-lane kernels
 __constant__ __align__(16) int c_lrp2[kConst2Ints];  // int32 entries, or int64 entries (two words each) for the 64-bit input path
 
+#ifndef PLO_SWEEP8_MINB
+#define PLO_SWEEP8_MINB 3
+#endif
+#ifndef PLO_SWEEPN8_MINB
+#define PLO_SWEEPN8_MINB 4
+#endif
 constexpr int MEASURE_BOTH = 4;  // internal: nnz, nno and G2 (tables, winner re-evaluation)
 
 // ---------------------------------------------------------------------------
@@ -942,7 +948,7 @@ __device__ __forceinline__ Key sweep8_loop(int r, unsigned long long seed, unsig
 }
 
 template <int M, int K, int N, int MODE, int RU>
-__global__ void __launch_bounds__(kThreads) orbit_sweep8_kernel(int r, unsigned long long seed, unsigned long long lo, unsigned long long hi, int lutn, int lutfull,
+__global__ void __launch_bounds__(kThreads, (M * K * N >= 84) ? PLO_SWEEP8_MINB : 1) orbit_sweep8_kernel(int r, unsigned long long seed, unsigned long long lo, unsigned long long hi, int lutn, int lutfull,
                                                                  Key* __restrict__ block_best, const int4* __restrict__ z3tab) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double* lut = reinterpret_cast<double*>(dyn_smem);
@@ -1003,7 +1009,7 @@ __device__ __forceinline__ void transform_pair_count8(const int* __restrict__ A2
 }
 
 template <int M, int K, int N, int MODE>
-__global__ void __launch_bounds__(kThreads) orbit_sweepn8_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
+__global__ void __launch_bounds__(kThreads, (M * K * N >= 84) ? PLO_SWEEPN8_MINB : 1) orbit_sweepn8_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
                                                                   Key* __restrict__ block_best, const int4* __restrict__ z3tab) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   int* scr0 = reinterpret_cast<int*>(dyn_smem);
@@ -1020,6 +1026,59 @@ __global__ void __launch_bounds__(kThreads) orbit_sweepn8_kernel(int r, int3 den
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
     Digits<MODE> ds(seed, idx);
+    if (M * K * N >= 84) {
+      // Large shapes (3x4x7: W and W^-T alone are 98 registers): the counts are sums over the three products, so the rows of L, then
+      // of R, then of P are swept with only the two matrices of that product live -- 222 -> 128 registers, 2 -> 4 blocks per SM.
+      // The byte counters are flushed per pair of rows and phase (at most ceil(RA/2).CA <= 14 marks per byte in between).
+      const Zoi zu = decode_zoi<M, MODE>(ds);
+      const Zoi zv = decode_zoi<K, MODE>(ds);
+      const Zoi zw = decode_zoi<N, MODE>(ds);
+      unsigned z = 0, d = 0;
+      {
+        int Ui[M * M], V[K * K], UiTP[((M + 1) / 2) * M];
+        expand_zoi<M, true>(zu, Ui, scr, kThreads);
+        pack_left<M, true>(Ui, UiTP);
+        expand_zoi<K, false>(zv, V, scr, kThreads);
+#pragma unroll 1
+        for (int q = 0; q < npair; ++q) {
+          unsigned cz = 0, cd = 0;
+          transform_pair_count8<M, K, false>(L2 + q * M * K, UiTP, V, dL, cz, cd);   // U^-T A V
+          z = __dp4a(cz, 0x01010101u, z);
+          d = __dp4a(cd, 0x01010101u, d);
+        }
+      }
+      {
+        int Vi[K * K], W[N * N], ViP[((K + 1) / 2) * K];
+        expand_zoi<K, true>(zv, Vi, scr, kThreads);
+        pack_left<K, false>(Vi, ViP);
+        expand_zoi<N, false>(zw, W, scr, kThreads);
+#pragma unroll 1
+        for (int q = 0; q < npair; ++q) {
+          unsigned cz = 0, cd = 0;
+          transform_pair_count8<K, N, false>(R2 + q * K * N, ViP, W, dR, cz, cd);    // V^-1 B W
+          z = __dp4a(cz, 0x01010101u, z);
+          d = __dp4a(cd, 0x01010101u, d);
+        }
+      }
+      {
+        int U[M * M], Wi[N * N], UP[((M + 1) / 2) * M];
+        expand_zoi<M, false>(zu, U, scr, kThreads);
+        pack_left<M, false>(U, UP);
+        expand_zoi<N, true>(zw, Wi, scr, kThreads);
+#pragma unroll 1
+        for (int q = 0; q < npair; ++q) {
+          unsigned cz = 0, cd = 0;
+          transform_pair_count8<M, N, true>(P2 + q * M * N, UP, Wi, dP, cz, cd);     // U C W^-T
+          z = __dp4a(cz, 0x01010101u, z);
+          d = __dp4a(cd, 0x01010101u, d);
+        }
+      }
+      Key k;
+      k.primary = ((unsigned long long)z << 32) | (unsigned long long)(z - ((unsigned)(npair * lanes) - d));
+      k.index = idx;
+      if (k.primary < best.primary) best = k;
+      continue;
+    }
     int V[K * K], W[N * N], Wi[N * N];
     int UiTP[((M + 1) / 2) * M], ViP[((K + 1) / 2) * K], UP[((M + 1) / 2) * M];
     if (M == 3 && K == 3 && N == 3 && z3tab != nullptr) {
