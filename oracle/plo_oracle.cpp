@@ -553,8 +553,6 @@ static bool sparseILU(const F& f, Mat<F>& TC, Mat<F>& A, size_t sparsity) {
   return sparser;
 }
 
-static inline size_t totalDensity(const std::vector<size_t>&) { return 0; }
-
 // include/plinopt_sparsify.inl:473-513  SparseFactor
 template <class F>
 static size_t SparseFactor(const F& f, Mat<F>& TICoB, Mat<F>& TM, size_t start, size_t increment, size_t threshold) {
@@ -937,6 +935,17 @@ int orc_sparsifier(int64_t p, int rows, int cols, const int64_t* num, const int6
   if (p == 0) { QField f; return sparsifier_impl(f, rows, cols, num, den, blocksize, maxnumcoeff, initialElimination, cob_num, cob_den, res_num, res_den, consistent); }
   ZpField f{p};
   return sparsifier_impl(f, rows, cols, num, den, blocksize, maxnumcoeff, initialElimination, cob_num, cob_den, res_num, res_den, consistent);
+}
+
+// libstdc++'s std::sort on (size, index) objects with the size-only comparator of plinopt_sparsify.inl:229 (sizeSup): the
+// permutation it produces (ties follow the introsort, quirk Q7).  tests/py_sparsifier.py restates the algorithm in Python and is
+// checked against this.
+void orc_std_sort_by_size(int n, const int32_t* sizes, int32_t* perm) {
+  struct Line { int size, idx; };
+  std::vector<Line> v((size_t)n);
+  for (int i = 0; i < n; ++i) v[(size_t)i] = Line{sizes[i], i};
+  std::sort(v.begin(), v.end(), [](const Line& a, const Line& b) { return a.size > b.size; });
+  for (int i = 0; i < n; ++i) perm[i] = v[(size_t)i].idx;
 }
 
 // Trace of every (block,num) step of the last orc_sparsifier call when tracing is on.
