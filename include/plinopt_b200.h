@@ -364,6 +364,14 @@ int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int
                 const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd, int64_t* oPn, int64_t* oPd,
                 plo_orbiter_report* report);
 
+/* The '# Found opt:' records of src/orbiter.cpp:300-318, deterministic: the reference prints every candidate that improves on the
+ * best so far as its OpenMP threads meet them; in index order those are the successive minima of the prefixes [0, i] that also
+ * improve on the input triple (acceptance :300-302).  records[0..*count) in increasing index order, the last one being the winner
+ * plo_orbiter returns; PLO_E_RANGE (with *count set) when `capacity` is too small.  Costs about one more sweep. */
+int plo_orbiter_progress(int measure, int mode, uint64_t seed, uint64_t loops, int r, int Lcols, int Rcols, int Prows,
+                         const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd, const int64_t* Pn,
+                         const int64_t* Pd, uint64_t capacity, plo_orbit_best* records, uint64_t* count);
+
 /* fMMchecker + MMchecker  src/MMchecker.cpp:48-81, include/plinopt_library.inl:472-558 on dense
  * rational inputs.  modulus == 0: the reference checks over Q with `bitsize`-bit random inputs; this
  * engine checks modulo the word-size prime 2^31-1 (next prime below if a denominator vanishes),

@@ -29,7 +29,7 @@ SYMBOLS = [
     "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_pack", "plo_orbit_plan_kernel", "plo_orbit_magnitude_bounds", "plo_orbit_plan_survivors", "plo_selftest_matrix_index", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
     "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
-    "plo_sparsifier", "plo_orbiter", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
+    "plo_sparsifier", "plo_orbiter", "plo_orbiter_progress", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
     "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
     "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender", "plo_negater", "plo_rotater", "plo_growth_factors",
 ]
@@ -507,6 +507,17 @@ def orbiter(L, R, P, measure=MEASURE_NNZ, mode=MODE_PHILOX, seed=0, loops=100):
     report = dict(init_nnz=rep.init_nnz, init_nno=rep.init_nno, init_score=rep.init_score, best=_best_tuple(rep.best),
                   improved=bool(rep.improved), mm_verdict=rep.mm_verdict, mkn=(rep.m, rep.k, rep.n))
     return _fractions(outs[0], outs[1]), _fractions(outs[2], outs[3]), _fractions(outs[4], outs[5]), report
+
+
+def orbiter_progress(L, R, P, measure=MEASURE_NNZ, mode=MODE_PHILOX, seed=0, loops=100, capacity=256):
+    """The deterministic '# Found opt:' records (plo_orbiter_progress): list of dicts in increasing index order."""
+    Ln, Ld = _numden(L); Rn, Rd = _numden(R); Pn, Pd = _numden(P)
+    buf = (OrbitBest * capacity)()
+    cnt = C.c_uint64(0)
+    f = lib().plo_orbiter_progress
+    f.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 6 + [C.c_uint64, C.POINTER(OrbitBest), C.POINTER(C.c_uint64)]
+    _check(f(measure, mode, seed, loops, len(L), len(L[0]), len(R[0]), len(P), _ptr(Ln), _ptr(Ld), _ptr(Rn), _ptr(Rd), _ptr(Pn), _ptr(Pd), capacity, buf, C.byref(cnt)))
+    return [_best_tuple(buf[i]) for i in range(cnt.value)]
 
 
 def orbiter_modp(L, R, P, q, mode=MODE_PHILOX, seed=0, loops=100):

@@ -10,7 +10,7 @@
 
 static void usage(const char* prg, size_t loops) {
   std::clog << "Usage: " << prg << "  [-h|-O/-b #|-m/-q #|-r # # #|-s|-g] L.sms R.sms P.sms\n"
-            << "  [-b b]: random check with values of size 'bitsize'\n"
+            << "  [-b b]: random check with values of size 'bitsize' (here: b samples modulo a word-size prime)\n"
             << "  [-m/-q m]: check is modulo (mod) or (mod/2^k) (default no)\n"
             << "  [-r r e s]: check is modulo (r^e-s) or ((r^e-s)/2^k) (default no)\n"
             << "  [-s|-g]: search sparser|lower growth factor (default is sparser)\n"
@@ -21,7 +21,7 @@ static void usage(const char* prg, size_t loops) {
 }
 
 int main(int argc, char** argv) {
-  unsigned long long loops = 100, modulus = 0, seed = 0x504C494E4F505431ull;  // DEFAULT_RANDOM_LOOPS, plinopt_library.h:37-39
+  unsigned long long loops = 100, modulus = 0, seed = 0x504C494E4F505431ull, bitsize = 32;  // DEFAULT_RANDOM_LOOPS, plinopt_library.h:37-39
   int measure = PLO_MEASURE_NNZ, mode = PLO_MODE_PHILOX;
   std::vector<std::string> files;
   for (int i = 1; i < argc; ++i) {
@@ -31,7 +31,13 @@ int main(int argc, char** argv) {
     else if (a == "--exhaustive") mode = PLO_MODE_EXHAUSTIVE;
     else if (a[0] == '-' && a.size() > 1) {
       if (a[1] == 'h') usage(argv[0], loops);
-      else if (a[1] == 'b' && i + 1 < argc) ++i;  // bitsize only matters over Q in the reference
+      else if (a[1] == 'b' && i + 1 < argc) {
+        // -b is the bit size of the random rational inputs of the reference's over-Q check (plinopt_library.inl:497-500).  This
+        // engine checks modulo a word-size prime on counter-based residues, so the value is used the way bin/MMchecker uses it:
+        // as the number of independent samples of the check (confidence grows with it, as with the bit size) -- and that is said.
+        bitsize = strtoull(argv[++i], nullptr, 10);
+        std::cerr << "# \033[1;33mNOTE: -b " << bitsize << ": the MMchecker runs modulo 2^31-1 (or -m/-q/-r) and uses b as its number of samples\033[0m" << std::endl;
+      }
       else if ((a[1] == 'm' || a[1] == 'q') && i + 1 < argc) modulus = strtoull(argv[++i], nullptr, 10);
       else if (a[1] == 'r' && i + 3 < argc) {
         const unsigned long long r = strtoull(argv[++i], nullptr, 10); const int e = atoi(argv[++i]); const unsigned long long s = strtoull(argv[++i], nullptr, 10);
@@ -55,7 +61,7 @@ int main(int argc, char** argv) {
   }
   const cli::NumDen l = cli::flatten(L), r = cli::flatten(R), p = cli::flatten(P);
   uint32_t cnt[2];
-  const int v0 = plo_mmchecker(modulus, seed, 32, l.rows, l.cols, r.rows, r.cols, p.rows, p.cols, l.num.data(), l.den.data(), r.num.data(), r.den.data(),
+  const int v0 = plo_mmchecker(modulus, seed, (int)(bitsize < 1 ? 1 : (bitsize > 4096 ? 4096 : bitsize)), l.rows, l.cols, r.rows, r.cols, p.rows, p.cols, l.num.data(), l.den.data(), r.num.data(), r.den.data(),
                                p.num.data(), p.den.data(), cnt);  // :251 (result ignored by the reference)
   int m, k, n;
   plo_LRP2MM(l.cols, r.cols, p.rows, &m, &k, &n);
@@ -75,6 +81,20 @@ int main(int argc, char** argv) {
                      p.den.data(), oLn.data(), oLd.data(), oRn.data(), oRd.data(), oPn.data(), oPd.data(), &rep);
   if (rc != PLO_OK) { std::cerr << "# \033[1;31m****** ERROR " << rc << ": " << plo_last_error() << " ******\033[0m" << std::endl; return rc; }
   std::clog << "# Init. ops: " << rep.init_score << ", {" << rep.init_nnz << ',' << rep.init_nno << '}' << std::endl;
+  if (modulus == 0 && rep.improved) {  // '# Found opt:' lines of src/orbiter.cpp:312-315, in index order (deterministic)
+    std::vector<plo_orbit_best> recs(256);
+    uint64_t nrec = 0;
+    if (plo_orbiter_progress(measure, mode, seed, loops, l.rows, l.cols, r.cols, p.rows, l.num.data(), l.den.data(), r.num.data(), r.den.data(), p.num.data(),
+                             p.den.data(), recs.size(), recs.data(), &nrec) == PLO_OK) {
+      double bestopt = rep.init_score;
+      uint32_t bnnz = rep.init_nnz, bnno = rep.init_nno;
+      for (uint64_t t = 0; t < nrec; ++t) {
+        std::clog << "# Found opt: " << recs[t].score << (recs[t].score < bestopt ? '<' : '=') << bestopt << "\t{" << recs[t].nnz << ',' << recs[t].nno << "}&{" << bnnz << ','
+                  << bnno << "}\t[" << recs[t].index << "/gpu]" << std::endl;
+        bestopt = recs[t].score; bnnz = recs[t].nnz; bnno = recs[t].nno;
+      }
+    }
+  }
   std::clog << "# Search(" << loops << "): " << timer.seconds() << "s" << std::endl;
   if (rep.improved) {
     std::clog << "# \033[1;36mRdcd. opt: " << rep.best.score << '<' << rep.init_score << "\t{" << rep.best.nnz << ',' << rep.best.nno << "}\033[0m\t[" << rep.best.index << ']' << std::endl;

@@ -392,6 +392,81 @@ int plo_sparsifier(uint64_t q, int rows, int cols, const int64_t* num, const int
   }
 }
 
+namespace {
+// integer images of a rational triple (every entry times the matrix' common LCD) and the sweep entry point that fits them
+struct OrbitImages {
+  std::vector<int64_t> L64, R64, P64;
+  int64_t dl = 1, dr = 1, dp = 1;
+  bool fits32 = true;
+  OrbitImages(const Dense<QField>& L, const Dense<QField>& R, const Dense<QField>& P) {
+    auto split = [](const Dense<QField>& M, std::vector<int64_t>& n, std::vector<int64_t>& d) {
+      n.resize(M.v.size()); d.resize(M.v.size());
+      for (size_t e = 0; e < M.v.size(); ++e) { n[e] = M.v[e].num; d[e] = M.v[e].den; }
+    };
+    std::vector<int64_t> ln, ld, rn, rd, pn, pd;
+    split(L, ln, ld); split(R, rn, rd); split(P, pn, pd);
+    const wide lim = (wide)1 << 46;
+    dl = lcd_of(ld.data(), ld.size(), lim); dr = lcd_of(rd.data(), rd.size(), lim); dp = lcd_of(pd.data(), pd.size(), lim);
+    L64 = scale_int64(ln.data(), ld.data(), ln.size(), dl, fits32);
+    R64 = scale_int64(rn.data(), rd.data(), rn.size(), dr, fits32);
+    P64 = scale_int64(pn.data(), pd.data(), pn.size(), dp, fits32);
+  }
+  int sweep(int m, int k, int n, int r, int measure, int mode, uint64_t seed, uint64_t lo, uint64_t hi, plo_orbit_best* best) const {
+    if (fits32) {
+      const std::vector<int32_t> Li(L64.begin(), L64.end()), Ri(R64.begin(), R64.end()), Pi(P64.begin(), P64.end());
+      return plo_orbit_sweep_devices(g_sweep_devices, m, k, n, r, Li.data(), Ri.data(), Pi.data(), (int32_t)dl, (int32_t)dr, (int32_t)dp, measure, mode, seed, lo, hi, best);
+    }
+    // common denominators beyond 2^31 (2x2x2_7_DPS-intermediate-12.0695): the 64-bit input path
+    return plo_orbit_sweep64(m, k, n, r, L64.data(), R64.data(), P64.data(), dl, dr, dp, measure, mode, seed, lo, hi, best);
+  }
+};
+bool orbit_improves(int measure, const plo_orbit_best& b, double init_score, uint32_t init_nnz, uint32_t init_nno) {  // src/orbiter.cpp:300-302, 330-331
+  if (b.index == PLO_NO_INDEX) return false;
+  if (measure == PLO_MEASURE_G2) return b.score < init_score * (1.0 - 1e-12);  // beyond the rounding of the two evaluations
+  return b.nnz < init_nnz || (b.nnz == init_nnz && b.nno < init_nno);
+}
+}  // namespace
+
+// The '# Found opt:' records of src/orbiter.cpp:300-318 made deterministic: the reference prints every candidate that improves
+// on the best so far as its threads meet them; in index order those are the successive minima of the prefixes [0, i] that also
+// improve on the input.  They are found backwards: the winner of [0, loops), then the winner of [0, its index), and so on
+// (each sweep is shorter; about twice the cost of one sweep in total).  records come back in increasing index order.
+int plo_orbiter_progress(int measure, int mode, uint64_t seed, uint64_t loops, int r, int Lcols, int Rcols, int Prows,
+                         const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd, const int64_t* Pn,
+                         const int64_t* Pd, uint64_t capacity, plo_orbit_best* records, uint64_t* count) {
+  if (!Ln || !Rn || !Pn || !records || !count || r < 1 || Lcols < 1 || Rcols < 1 || Prows < 1) { plo::set_error("plo_orbiter_progress: bad argument"); return PLO_E_ARG; }
+  int rc = plo::check_device();
+  if (rc) return rc;
+  try {
+    QField Q;
+    int m, k, n;
+    plo_LRP2MM(Lcols, Rcols, Prows, &m, &k, &n);
+    if (Lcols != m * k || Rcols != k * n || Prows != m * n) { plo::set_error("plo_orbiter_progress: outer dimension mismatch"); return 3; }
+    const Dense<QField> L = load(Q, (size_t)r, (size_t)Lcols, Ln, Ld), R = load(Q, (size_t)r, (size_t)Rcols, Rn, Rd), P = load(Q, (size_t)Prows, (size_t)r, Pn, Pd);
+    uint32_t init_nnz = 0, init_nno = 0;
+    count_nonzeroes(L, init_nnz, init_nno); count_nonzeroes(R, init_nnz, init_nno); count_nonzeroes(P, init_nnz, init_nno);
+    const double init_score = measure == PLO_MEASURE_G2 ? growth_G2(L, R, P) : (double)init_nnz;
+    const OrbitImages img(L, R, P);
+    std::vector<plo_orbit_best> rev;
+    uint64_t hi = loops;
+    while (hi > 0 && rev.size() < 256) {
+      plo_orbit_best b;
+      rc = img.sweep(m, k, n, r, measure, mode, seed, 0, hi, &b);
+      if (rc) return rc;
+      if (!orbit_improves(measure, b, init_score, init_nnz, init_nno)) break;
+      rev.push_back(b);
+      hi = b.index;
+    }
+    *count = rev.size();
+    if (rev.size() > capacity) { plo::set_error("plo_orbiter_progress: %zu records, room for %llu", rev.size(), (unsigned long long)capacity); return PLO_E_RANGE; }
+    for (size_t t = 0; t < rev.size(); ++t) records[t] = rev[rev.size() - 1 - t];
+    return PLO_OK;
+  } catch (const RangeError& e) {
+    plo::set_error("plo_orbiter_progress: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
 int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int Lcols, int Rcols, int Prows,
                 const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd, const int64_t* Pn,
                 const int64_t* Pd, int64_t* oLn, int64_t* oLd, int64_t* oRn, int64_t* oRd, int64_t* oPn, int64_t* oPd,
@@ -412,29 +487,11 @@ int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int
     rep->m = m; rep->k = k; rep->n = n;
     count_nonzeroes(L, rep->init_nnz, rep->init_nno); count_nonzeroes(R, rep->init_nnz, rep->init_nno); count_nonzeroes(P, rep->init_nnz, rep->init_nno);
     rep->init_score = measure == PLO_MEASURE_G2 ? growth_G2(L, R, P) : (double)rep->init_nnz;
-    // integer images
-    std::vector<int64_t> ld(L.v.size()), rd(R.v.size()), pd(P.v.size()), ln(L.v.size()), rn(R.v.size()), pn(P.v.size());
-    for (size_t e = 0; e < L.v.size(); ++e) { ln[e] = L.v[e].num; ld[e] = L.v[e].den; }
-    for (size_t e = 0; e < R.v.size(); ++e) { rn[e] = R.v[e].num; rd[e] = R.v[e].den; }
-    for (size_t e = 0; e < P.v.size(); ++e) { pn[e] = P.v[e].num; pd[e] = P.v[e].den; }
-    const wide lim = (wide)1 << 46;
-    const int64_t dl = lcd_of(ld.data(), ld.size(), lim), dr = lcd_of(rd.data(), rd.size(), lim), dp = lcd_of(pd.data(), pd.size(), lim);
-    bool fits32 = true;
-    const std::vector<int64_t> L64 = scale_int64(ln.data(), ld.data(), ln.size(), dl, fits32), R64 = scale_int64(rn.data(), rd.data(), rn.size(), dr, fits32),
-                               P64 = scale_int64(pn.data(), pd.data(), pn.size(), dp, fits32);
-    if (fits32) {
-      const std::vector<int32_t> Li(L64.begin(), L64.end()), Ri(R64.begin(), R64.end()), Pi(P64.begin(), P64.end());
-      rc = plo_orbit_sweep_devices(g_sweep_devices, m, k, n, r, Li.data(), Ri.data(), Pi.data(), (int32_t)dl, (int32_t)dr, (int32_t)dp, measure, mode, seed, 0, loops, &rep->best);
-    } else {  // common denominators beyond 2^31 (2x2x2_7_DPS-intermediate-12.0695): the 64-bit input path
-      rc = plo_orbit_sweep64(m, k, n, r, L64.data(), R64.data(), P64.data(), dl, dr, dp, measure, mode, seed, 0, loops, &rep->best);
-    }
+    const OrbitImages img(L, R, P);
+    rc = img.sweep(m, k, n, r, measure, mode, seed, 0, loops, &rep->best);
     if (rc) return rc;
     // acceptance against the input, src/orbiter.cpp:330-331
-    bool improved = false;
-    if (rep->best.index != PLO_NO_INDEX) {
-      if (measure == PLO_MEASURE_G2) improved = rep->best.score < rep->init_score * (1.0 - 1e-12);  // beyond the rounding of the two evaluations
-      else improved = rep->best.nnz < rep->init_nnz || (rep->best.nnz == rep->init_nnz && rep->best.nno < rep->init_nno);
-    }
+    const bool improved = orbit_improves(measure, rep->best, rep->init_score, rep->init_nnz, rep->init_nno);
     Dense<QField> Lj = L, Rg = R, hP = P;
     if (improved) {
       std::vector<int32_t> U((size_t)m * m), V((size_t)k * k), W((size_t)n * n);

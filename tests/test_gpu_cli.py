@@ -146,3 +146,35 @@ def test_growthfactor_cli(capi, tmp_path):
     assert "# Norms of 2x2x2 Matrix-Multiplication:" in p.stderr and "## Ginfinf:\t12.000000" in p.stderr and "## G2:\t\t14.828427" in p.stderr
     bad = write_triple(tmp_path, "3x3x3_23_58")
     assert subprocess.run([os.path.join(BIN, "growthfactor"), files[0], bad[1], files[2]], capture_output=True, text=True, timeout=300).returncode == 2
+
+
+def test_orbiter_cli_progress_lines_and_bitsize(capi, tmp_path):
+    """'# Found opt:' records (src/orbiter.cpp:312-315), deterministic: the successive prefix minima in index order; the last one is the
+    winner of the 'Rdcd. opt' line, every record improves on the one before, and they equal plo_orbiter_progress.  -b is used as the
+    number of samples of the MMchecker and says so."""
+    import re
+    files = write_triple(tmp_path, "3x3x3_23_58")
+    p = subprocess.run([os.path.join(BIN, "orbiter"), "-b", "8", "-O", "300000", "--seed", "5"] + files, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "NOTE: -b 8" in p.stderr
+    recs = [(float(a), int(b), int(c), int(i)) for a, b, c, i in re.findall(r"# Found opt: ([0-9.]+)[<=][0-9.]+\t\{(\d+),(\d+)\}&\{\d+,\d+\}\t\[(\d+)/gpu\]", p.stderr)]
+    assert len(recs) >= 2
+    assert all(x[3] < y[3] and (x[1], x[2]) > (y[1], y[2]) for x, y in zip(recs, recs[1:]))
+    win = re.search(r"Rdcd\. opt: ([0-9.]+)<[0-9.]+\t\{(\d+),(\d+)\}.*\[(\d+)\]", p.stderr)
+    assert (int(win.group(2)), int(win.group(3)), int(win.group(4))) == recs[-1][1:]
+    L, R, P = O.triple("3x3x3_23_58")
+    api = capi.orbiter_progress(L, R, P, capi.MEASURE_NNZ, capi.MODE_PHILOX, 5, 300000)
+    assert [(r["nnz"], r["nno"], r["index"]) for r in api] == [x[1:] for x in recs]
+    # every record really is the minimum of its prefix: check the first two against the oracle's table of the prefix
+    tab = O.orbit_sweep(L, R, P, 0, 1, 5, 0, api[1]["index"] + 1)
+    keys = list(zip(tab["nnz"].tolist(), tab["nno"].tolist()))
+    assert min(range(len(keys)), key=lambda i: (keys[i], i)) == api[1]["index"] and min(range(api[1]["index"]), key=lambda i: (keys[i], i)) == api[0]["index"]
+
+
+def test_orbiter_cli_rejects_inner_dimension_mismatch(capi, tmp_path):
+    """The reference only warns (src/orbiter.cpp:236-242) and then fails inside LinBox; the engine takes flat buffers, so it rejects
+    the triple with fMMchecker's code 2 instead of reading past them."""
+    s = write_triple(tmp_path, "2x2x2_7_Strassen")
+    w = write_triple(tmp_path, "3x3x3_23_58")
+    p = subprocess.run([os.path.join(BIN, "orbiter"), "-O", "10", s[0], w[1], s[2]], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 2 and "inner dimension mismatch" in p.stderr
