@@ -322,6 +322,22 @@ int plo_dependency_explore(uint32_t p, int r, int n, int c, int level, const int
                            uint64_t max_hits, plo_dep_hit* hits, uint64_t* nhits, uint64_t* ncand);
 
 /* ---------------------------------------------------------------------------
+ * The other sweeps sharded over the first `ndev` CUDA devices of the calling process (clamped to the devices present), like
+ * plo_orbit_sweep_devices: one host thread, asynchronous launches, results merged in device order -- same answers as the
+ * single-device calls.  Reference analogues: the omp loops of include/plinopt_sparsify.inl:962,968 and src/orbiter.cpp:272.
+ *   plo_lincomb_search_devices  one (batched) sparsifier search, the prefix range (i*c+j)*c+k split over the devices
+ *   plo_mmcheck_batch_devices   `batch` Philox samples split over the devices (ok[s] as in plo_mmcheck_batch; returns its verdict)
+ *   plo_factor_sweep_devices    Factorizer random restarts [lo,hi) split over the devices
+ * ------------------------------------------------------------------------ */
+int plo_lincomb_search_devices(int ndev, uint32_t p, int nbatch, int n, int m, const int64_t* TM, int off, int c, const int64_t* coeffs,
+                               int nprev, const int64_t* prev_rows, const int* init_rl, const int* init_cl, int* best_rl, int* best_cl,
+                               uint64_t* best_index);
+int plo_mmcheck_batch_devices(int ndev, uint32_t p, int m, int k, int n, int r, const plo_csr* L, const plo_csr* R, const plo_csr* P,
+                              uint64_t seed, int batch, uint8_t* ok);
+int plo_factor_sweep_devices(int ndev, uint32_t p, int r, int n, int k, const uint32_t* M, uint64_t seed, uint64_t lo, uint64_t hi,
+                             plo_factor_best* best);
+
+/* ---------------------------------------------------------------------------
  * Roofline denominators that MEASURED_PEAKS.json does not hold: register-
  * resident unrolled IMAD / DFMA / (ISETP+IADD) loops over all SMs, CUDA-event
  * timed, best of `reps`.  Results in operations per second.

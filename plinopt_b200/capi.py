@@ -21,7 +21,7 @@ NO_INDEX = 2 ** 64 - 1
 
 # every symbol include/plinopt_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "plo_release_workspace", "plo_set_sweep_devices", "plo_orbit_sweep_devices",
+    "plo_release_workspace", "plo_set_sweep_devices", "plo_orbit_sweep_devices", "plo_lincomb_search_devices", "plo_mmcheck_batch_devices", "plo_factor_sweep_devices",
     "plo_version", "plo_device_count", "plo_set_device", "plo_last_error",
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_quad", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
@@ -120,6 +120,22 @@ def lincomb_search(p, TM, off, coeffs, prev_rows=None, init_rl=-1, init_cl=-1):
     f.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                   C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     _check(f(int(p), n, m, _ptr(TM), int(off), len(coeffs), _ptr(coeffs), nprev, _ptr(prev), int(init_rl), int(init_cl),
+             C.byref(rl), C.byref(cl), C.byref(idx)))
+    return rl.value, cl.value, (None if idx.value == NO_INDEX else idx.value)
+
+
+def lincomb_search_devices(ndev, p, TM, off, coeffs, prev_rows=None, init_rl=-1, init_cl=-1):
+    """plo_lincomb_search_devices on one problem: (best_rl, best_cl, best_index or None)."""
+    TM = _i64(TM); coeffs = _i64(coeffs)
+    n, m = TM.shape
+    prev = _i64(prev_rows) if prev_rows is not None and len(prev_rows) else None
+    nprev = 0 if prev is None else prev.shape[0]
+    rl, cl, idx = C.c_int(), C.c_int(), C.c_uint64()
+    irl, icl = C.c_int(int(init_rl)), C.c_int(int(init_cl))
+    f = lib().plo_lincomb_search_devices
+    f.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int),
+                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    _check(f(int(ndev), int(p), 1, n, m, _ptr(TM), int(off), len(coeffs), _ptr(coeffs), nprev, _ptr(prev), C.byref(irl), C.byref(icl),
              C.byref(rl), C.byref(cl), C.byref(idx)))
     return rl.value, cl.value, (None if idx.value == NO_INDEX else idx.value)
 
@@ -346,6 +362,17 @@ class OrbitPlan:
             return [_best_tuple(buf[i]) for i in range(cnt.value)]
         _check(rc)
 
+    def survivors_array(self, lo, hi, nnz=0, nno=0, score=0.0, capacity=1 << 16):
+        """The same as `survivors` without the per-record Python objects: (count, structured numpy array score/nnz/nno/index).
+        Raises PloError(E_RANGE) when `capacity` is too small (the message carries the count)."""
+        f = lib().plo_orbit_plan_survivors
+        f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(OrbitBest), C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+        thr = OrbitBest(score=score, nnz=nnz, nno=nno, index=0)
+        buf = np.zeros(max(1, capacity), dtype=np.dtype([("score", "<f8"), ("nnz", "<u4"), ("nno", "<u4"), ("index", "<u8")]))
+        cnt = C.c_uint64(0)
+        _check(f(self._h, lo, hi, C.byref(thr), capacity, _ptr(buf), C.byref(cnt)))
+        return cnt.value, buf[:cnt.value]
+
     def close(self):
         if self._h:
             lib().plo_orbit_plan_destroy(self._h)
@@ -403,6 +430,17 @@ def mmcheck_batch(p, mkn, r, L, R, P, seed=0, batch=1, ua=None, ub=None):
     f = lib().plo_mmcheck_batch
     f.argtypes = [C.c_uint32] + [C.c_int] * 4 + [C.POINTER(Csr)] * 3 + [C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     rc = _check(f(p, m, k, n, r, C.byref(hl.c), C.byref(hr.c), C.byref(hp.c), seed, batch, _ptr(a), _ptr(b), _ptr(ok)), allow=(1, 2, 3))
+    return rc, ok
+
+
+def mmcheck_batch_devices(ndev, p, mkn, r, L, R, P, seed=0, batch=1):
+    """plo_mmcheck_batch_devices: the batch split over the first ndev devices.  Returns (verdict, ok[batch])."""
+    m, k, n = mkn
+    hl, hr, hp = _CsrHolder(*L), _CsrHolder(*R), _CsrHolder(*P)
+    ok = np.zeros(batch, dtype=np.uint8)
+    f = lib().plo_mmcheck_batch_devices
+    f.argtypes = [C.c_int, C.c_uint32] + [C.c_int] * 4 + [C.POINTER(Csr)] * 3 + [C.c_uint64, C.c_int, C.c_void_p]
+    rc = _check(f(int(ndev), p, m, k, n, r, C.byref(hl.c), C.byref(hr.c), C.byref(hp.c), seed, batch, _ptr(ok)), allow=(1, 2, 3))
     return rc, ok
 
 
@@ -586,6 +624,17 @@ def factor_sweep(p, M, k, seed, lo, hi, table=False):
     f.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(FactorBest), C.c_void_p]
     _check(f(p, r, n, k, _ptr(M), seed, lo, hi, C.byref(best), _ptr(tab) if table else None))
     return (_factor_tuple(best), tab) if table else _factor_tuple(best)
+
+
+def factor_sweep_devices(ndev, p, M, k, seed, lo, hi):
+    """plo_factor_sweep_devices: the index range split over the first ndev devices; (nnz_alt, nno_alt, nnz_cob, index)."""
+    M = np.ascontiguousarray(M, dtype=np.uint32)
+    r, n = M.shape
+    best = FactorBest()
+    f = lib().plo_factor_sweep_devices
+    f.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(FactorBest)]
+    _check(f(int(ndev), p, r, n, k, _ptr(M), seed, lo, hi, C.byref(best)))
+    return _factor_tuple(best)
 
 
 def factor_decode(r, seed, index):

@@ -20,6 +20,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "plo_device.cuh"
 
 namespace plo {
@@ -39,7 +41,20 @@ __constant__ __align__(16) int c_lrp2[kConst2Ints];  // int32 entries, or int64 
 #ifndef PLO_SWEEPN8_MINB
 #define PLO_SWEEPN8_MINB 4
 #endif
-constexpr int MEASURE_BOTH = 4;  // internal: nnz, nno and G2 (tables, winner re-evaluation)
+constexpr int MEASURE_BOTH = 4;
+
+// Survivor compaction inside the sweep kernels (north_star: "surviving candidates are compacted through coalesced vectorised
+// stores"; reference analogue: the per-improvement report of src/orbiter.cpp:300-318).  While a survivors call runs, the constant
+// bank holds a threshold on the sweep's own key and an index buffer: every kernel of the family appends the index of a candidate
+// whose key does not exceed the threshold (warp-aggregated: one atomicAdd per warp with survivors, consecutive 8-byte slots).
+// idx == nullptr (the normal state) disables it at the cost of one uniform compare per candidate.
+struct Surv {
+  unsigned long long thr;
+  unsigned long long* idx;
+  unsigned long long* count;
+  unsigned long long cap;
+};
+__constant__ Surv c_surv;  // internal: nnz, nno and G2 (tables, winner re-evaluation)
 
 // ---------------------------------------------------------------------------
 // Digit stream: a pure function of (mode, seed, index).
@@ -252,6 +267,67 @@ __host__ __device__ __forceinline__ void expand_zoi(const Zoi& z, int* out, vola
   }
 #pragma unroll
   for (int e = 0; e < S * S; ++e) out[e] = scr[e * stride];
+}
+
+// ---------------------------------------------------------------------------
+// Triangular right factors.  A zoi matrix is M = Pi_P T Pi_Q^T with T upper triangular, diagonal d_i = +-1 (src/orbiter.cpp:
+// 125-136).  As the RIGHT factor of a product X.M (or X.M^-T) the outer permutation Pi_Q and the diagonal signs only permute the
+// output entries and flip their signs -- every measure (zero count, +-1 count, sum of squares) is blind to both -- and the inner
+// permutation Pi_P permutes the entries of X:
+//     (X.M)[Q[j]]    = d_j  ( X'[j] + sum_{i<j} X'[i] . T[i][j] d_j )           X'[i] = X[P[i]]
+//     (X.M^-T)[Q[i]] = d_i  ( X'[i] + sum_{j>i} X'[j] . d_i T^-1[i][j] )
+// so the second product stage costs S(S-1)/2 multiply-adds per row of X instead of S^2 (7x7: 21 instead of 49), the unit diagonal
+// is the accumulator's start value, and the factor occupies S(S-1)/2 registers instead of S^2.  X is permuted through the
+// thread-private column of the expansion scratch (S stores, S loads, bank-conflict free).
+// tri[i*S - i(i+1)/2 + (j-i-1)] for i < j:   INV = false: T[i][j].d_j     INV = true: d_i.T^-1[i][j]
+// ---------------------------------------------------------------------------
+template <int S>
+__host__ __device__ constexpr int tri_index(int i, int j) { return i * S - i * (i + 1) / 2 + (j - i - 1); }
+
+template <int S, bool INV>
+__host__ __device__ __forceinline__ void zoi_tri(const Zoi& z, int* tri) {
+  int t[S][S];
+  {
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      t[i][i] = ((z.D >> i) & 1u) ? 1 : -1;
+#pragma unroll
+      for (int j = i + 1; j < S; ++j) {
+        t[i][j] = (int)((z.T >> (2 * idx)) & 3ull) - 1;
+        ++idx;
+      }
+    }
+  }
+  if (!INV) {
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+#pragma unroll
+      for (int j = i + 1; j < S; ++j) tri[tri_index<S>(i, j)] = t[i][j] * t[j][j];
+  } else {
+    int xinv[S][S];  // back substitution, as in expand_zoi
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      xinv[j][j] = t[j][j];
+#pragma unroll
+      for (int i = j - 1; i >= 0; --i) {
+        int acc = 0;
+#pragma unroll
+        for (int k = i + 1; k <= j; ++k) acc += t[i][k] * xinv[k][j];
+        xinv[i][j] = -t[i][i] * acc;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+#pragma unroll
+      for (int j = i + 1; j < S; ++j) tri[tri_index<S>(i, j)] = t[i][i] * xinv[i][j];
+  }
+}
+// scratch offsets (in ints, thread-private column with stride kThreads) of X[P[i]]
+template <int S>
+__device__ __forceinline__ void zoi_perm_offsets(const Zoi& z, int stride, int* poff) {
+#pragma unroll
+  for (int i = 0; i < S; ++i) poff[i] = (int)((z.pP >> (4 * i)) & 15u) * stride;
 }
 
 // ---------------------------------------------------------------------------
@@ -576,6 +652,20 @@ __device__ __forceinline__ Score score_candidate_nnz_split(const int* __restrict
 }
 #endif
 
+#ifdef __CUDACC__
+__device__ __forceinline__ void surv_emit(const Key& k) {
+  if (c_surv.idx != nullptr && k.primary <= c_surv.thr) {
+    const unsigned act = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(act) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(c_surv.count, (unsigned long long)__popc(act));
+    base = __shfl_sync(act, base, leader);
+    const unsigned long long pos = base + __popc(act & ((1u << lane) - 1u));
+    if (pos < c_surv.cap) c_surv.idx[pos] = k.index;
+  }
+}
+#endif
+
 template <int MEASURE>
 __device__ __forceinline__ Key make_key(const Score& s, unsigned long long index) {
   Key k;
@@ -619,6 +709,7 @@ __global__ void __launch_bounds__(kThreads, (PACK && M * K * N >= 84) ? (MEASURE
     else s = score_candidate<M, K, N, MODE, MEASURE, RU, LF, PACK, TAB>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads, lut, lutn, z2tab);
     const Key k = make_key<MEASURE>(s, idx);
     if (k.primary < best.primary) best = k;  // indices visited in increasing order: strict '<' keeps the first
+    surv_emit(k);
   }
   best = block_min(best, red);
   if (threadIdx.x == 0) block_best[blockIdx.x] = best;
@@ -702,6 +793,20 @@ __global__ void __launch_bounds__(kThreads) orbit_table_kernel(int r, int3 den, 
       if (g2) g2[idx - lo] = s.g2 * inv_den;
     }
     if (sink.rec) sink_emit(sink, valid, idx, s.nnz, s.nno, s.g2 * inv_den);
+  }
+}
+
+// Both measures of a LIST of candidates (the survivors of a sweep, sorted by index): one record of 32 bytes each, two 16-byte stores.
+template <int M, int K, int N, int MODE>
+__global__ void __launch_bounds__(kThreads) orbit_gather_kernel(int r, int3 den, unsigned long long seed, const unsigned long long* __restrict__ list,
+                                                                 unsigned long long count, double inv_den, uint4* __restrict__ rec) {
+  __shared__ int scr[MaxDim2<M, K, N>::value * kThreads];
+  for (unsigned long long t = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; t < count; t += (unsigned long long)gridDim.x * kThreads) {
+    const unsigned long long idx = list[t];
+    const Score sc = score_candidate<M, K, N, MODE, MEASURE_BOTH>(c_lrp, r, den, seed, idx, scr + threadIdx.x, kThreads);
+    const unsigned long long sb = (unsigned long long)__double_as_longlong(sc.g2 * inv_den);
+    rec[2 * t] = make_uint4((unsigned)idx, (unsigned)(idx >> 32), sc.nnz, sc.nno);
+    rec[2 * t + 1] = make_uint4((unsigned)sb, (unsigned)(sb >> 32), 0u, 0u);
   }
 }
 
@@ -840,6 +945,43 @@ __device__ __forceinline__ void transform_pair_packed8(const int* __restrict__ A
   }
 }
 
+// The same with a triangular right factor (see "Triangular right factors"): LOWER = false for X.M (sum over i < y), true for X.M^-T
+// (sum over j > y).  scr = this thread's scratch column, poff[i] = offset of X[P[i]] in it.
+template <int RA, int CA, bool LOWER>
+__device__ __forceinline__ void transform_pair_packed8_tri(const int* __restrict__ A2, const int* LmP, const int* tri, const int* poff, volatile int* scr,
+                                                           int& sq0, int& sq1) {
+  int a[RA * CA];
+#pragma unroll
+  for (int e = 0; e < RA * CA; ++e) a[e] = A2[e];
+#pragma unroll
+  for (int xp = 0; xp < (RA + 1) / 2; ++xp) {
+    int X[CA];
+#pragma unroll
+    for (int j = 0; j < CA; ++j) {
+      int acc = 0;
+#pragma unroll
+      for (int i = 0; i < RA; ++i) acc += LmP[xp * RA + i] * a[i * CA + j];
+      scr[j * kThreads] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < CA; ++i) X[i] = scr[poff[i]];
+#pragma unroll
+    for (int y = 0; y < CA; ++y) {
+      int v = X[y];
+      if (!LOWER) {
+#pragma unroll
+        for (int i = 0; i < y; ++i) v += X[i] * tri[tri_index<CA>(i, y)];
+      } else {
+#pragma unroll
+        for (int j = y + 1; j < CA; ++j) v += X[j] * tri[tri_index<CA>(y, j)];
+      }
+      const unsigned x = ((unsigned)v + 0x80808080u) ^ 0x80808080u;
+      sq0 = __dp4a((int)x, (int)(x & 0x00FF00FFu), sq0);
+      sq1 = __dp4a((int)x, (int)(x & 0xFF00FF00u), sq1);
+    }
+  }
+}
+
 // 3x3 zoi matrices: 6.6.8.27 = 7776 per factor -- too many for shared memory, but one table per plan in global memory (1.5 MB,
 // L2-resident) still replaces decode + expansion + inverse + packing (~450 instructions per candidate) by 15 128-bit loads.
 // Entry = 12 chunks of 16 bytes: M (9 ints, 3 chunks) | M^-1 (3) | pack_left<T>(M^-1) (6 ints, 2) | pack_left(M) (2) | pack_left(M^-1) (2).
@@ -896,7 +1038,8 @@ __device__ __forceinline__ Key sweep8_loop(int r, unsigned long long seed, unsig
   best.primary = ~0ull; best.index = ~0ull;
   for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * kThreads + threadIdx.x; idx < hi; idx += stride) {
     Digits<MODE> ds(seed, idx);
-    int V[K * K], W[N * N], Wi[N * N];
+    constexpr bool TRIW = N >= 5 && !TAB;  // large right factor: triangular form (only S(S-1)/2 of the N*N slots below are used then)
+    int V[K * K], W[TRIW ? N * (N - 1) / 2 : N * N], Wi[TRIW ? N * (N - 1) / 2 : N * N], wpoff[TRIW ? N : 1];
     int UiTP[((M + 1) / 2) * M], ViP[((K + 1) / 2) * K], UP[((M + 1) / 2) * M];
     if (TAB) {
       const int* tu = z2tab + ds.matrix_index(kZ2Count) * kZ2Stride;
@@ -920,8 +1063,14 @@ __device__ __forceinline__ Key sweep8_loop(int r, unsigned long long seed, unsig
       expand_zoi<M, true>(zu, Ui, scr, kThreads);
       expand_zoi<K, false>(zv, V, scr, kThreads);
       expand_zoi<K, true>(zv, Vi, scr, kThreads);
-      expand_zoi<N, false>(zw, W, scr, kThreads);
-      expand_zoi<N, true>(zw, Wi, scr, kThreads);
+      if (TRIW) {  // W and W^-T as triangular right factors: 2 x 21 registers instead of 2 x 49 for a 7x7 factor
+        zoi_tri<N, false>(zw, W);
+        zoi_tri<N, true>(zw, Wi);
+        zoi_perm_offsets<N>(zw, kThreads, wpoff);
+      } else {
+        expand_zoi<N, false>(zw, W, scr, kThreads);
+        expand_zoi<N, true>(zw, Wi, scr, kThreads);
+      }
       pack_left<M, true>(Ui, UiTP);
       pack_left<K, false>(Vi, ViP);
       pack_left<M, false>(U, UP);
@@ -931,8 +1080,13 @@ __device__ __forceinline__ Key sweep8_loop(int r, unsigned long long seed, unsig
     for (int q = 0; q < npair; ++q) {
       int sL0 = 0, sL1 = 0, sR0 = 0, sR1 = 0, sP0 = 0, sP1 = 0;
       transform_pair_packed8<M, K, false>(L2 + q * M * K, UiTP, V, sL0, sL1);   // U^-T A V
+      if (TRIW) {
+        transform_pair_packed8_tri<K, N, false>(R2 + q * K * N, ViP, W, wpoff, scr, sR0, sR1);    // V^-1 B W
+        transform_pair_packed8_tri<M, N, true>(P2 + q * M * N, UP, Wi, wpoff, scr, sP0, sP1);     // U C W^-T
+      } else {
       transform_pair_packed8<K, N, false>(R2 + q * K * N, ViP, W, sR0, sR1);    // V^-1 B W
       transform_pair_packed8<M, N, true>(P2 + q * M * N, UP, Wi, sP0, sP1);     // U C W^-T
+      }
       // growthfactor.cpp:117-125, rows in order, no FMA contraction
       // table lookup; a row norm^2 beyond the table (worst-case bound larger than the 4096 entries kept) takes the out-of-line sqrt
       auto root = [&](int sq) { return (LF || sq < lutn) ? lut[sq] : slow_isqrt(sq); };
@@ -943,6 +1097,7 @@ __device__ __forceinline__ Key sweep8_loop(int r, unsigned long long seed, unsig
     k.primary = (unsigned long long)__double_as_longlong(g2);
     k.index = idx;
     if (k.primary < best.primary) best = k;
+    surv_emit(k);
   }
   return best;
 }
@@ -1008,6 +1163,41 @@ __device__ __forceinline__ void transform_pair_count8(const int* __restrict__ A2
   }
 }
 
+template <int RA, int CA, bool LOWER>
+__device__ __forceinline__ void transform_pair_count8_tri(const int* __restrict__ A2, const int* LmP, const int* tri, const int* poff, volatile int* scr,
+                                                          unsigned dd, unsigned& cz, unsigned& cd) {
+  int a[RA * CA];
+#pragma unroll
+  for (int e = 0; e < RA * CA; ++e) a[e] = A2[e];
+#pragma unroll
+  for (int xp = 0; xp < (RA + 1) / 2; ++xp) {
+    int X[CA];
+#pragma unroll
+    for (int j = 0; j < CA; ++j) {
+      int acc = 0;
+#pragma unroll
+      for (int i = 0; i < RA; ++i) acc += LmP[xp * RA + i] * a[i * CA + j];
+      scr[j * kThreads] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < CA; ++i) X[i] = scr[poff[i]];
+#pragma unroll
+    for (int y = 0; y < CA; ++y) {
+      int v = X[y];
+      if (!LOWER) {
+#pragma unroll
+        for (int i = 0; i < y; ++i) v += X[i] * tri[tri_index<CA>(i, y)];
+      } else {
+#pragma unroll
+        for (int j = y + 1; j < CA; ++j) v += X[j] * tri[tri_index<CA>(y, j)];
+      }
+      const unsigned ab = __vabsdiffu4((unsigned)v + 0x80808080u, 0x80808080u);
+      asm("mad.hi.u32 %0, %1, 0x02000000, %0;" : "+r"(cz) : "r"((ab + 0x7F7F7F7Fu) & 0x80808080u));
+      asm("mad.hi.u32 %0, %1, 0x02000000, %0;" : "+r"(cd) : "r"(((ab ^ dd) + 0x7F7F7F7Fu) & 0x80808080u));
+    }
+  }
+}
+
 template <int M, int K, int N, int MODE>
 __global__ void __launch_bounds__(kThreads, (M * K * N >= 84) ? PLO_SWEEPN8_MINB : 1) orbit_sweepn8_kernel(int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
                                                                   Key* __restrict__ block_best, const int4* __restrict__ z3tab) {
@@ -1047,28 +1237,30 @@ __global__ void __launch_bounds__(kThreads, (M * K * N >= 84) ? PLO_SWEEPN8_MINB
           d = __dp4a(cd, 0x01010101u, d);
         }
       }
+      int wpoff[N];
+      zoi_perm_offsets<N>(zw, kThreads, wpoff);
       {
-        int Vi[K * K], W[N * N], ViP[((K + 1) / 2) * K];
+        int Vi[K * K], Wt[N * (N - 1) / 2], ViP[((K + 1) / 2) * K];
         expand_zoi<K, true>(zv, Vi, scr, kThreads);
         pack_left<K, false>(Vi, ViP);
-        expand_zoi<N, false>(zw, W, scr, kThreads);
+        zoi_tri<N, false>(zw, Wt);
 #pragma unroll 1
         for (int q = 0; q < npair; ++q) {
           unsigned cz = 0, cd = 0;
-          transform_pair_count8<K, N, false>(R2 + q * K * N, ViP, W, dR, cz, cd);    // V^-1 B W
+          transform_pair_count8_tri<K, N, false>(R2 + q * K * N, ViP, Wt, wpoff, scr, dR, cz, cd);    // V^-1 B W, W as a triangular factor
           z = __dp4a(cz, 0x01010101u, z);
           d = __dp4a(cd, 0x01010101u, d);
         }
       }
       {
-        int U[M * M], Wi[N * N], UP[((M + 1) / 2) * M];
+        int U[M * M], Wit[N * (N - 1) / 2], UP[((M + 1) / 2) * M];
         expand_zoi<M, false>(zu, U, scr, kThreads);
         pack_left<M, false>(U, UP);
-        expand_zoi<N, true>(zw, Wi, scr, kThreads);
+        zoi_tri<N, true>(zw, Wit);
 #pragma unroll 1
         for (int q = 0; q < npair; ++q) {
           unsigned cz = 0, cd = 0;
-          transform_pair_count8<M, N, true>(P2 + q * M * N, UP, Wi, dP, cz, cd);     // U C W^-T
+          transform_pair_count8_tri<M, N, true>(P2 + q * M * N, UP, Wit, wpoff, scr, dP, cz, cd);     // U C W^-T, W^-T as a triangular factor
           z = __dp4a(cz, 0x01010101u, z);
           d = __dp4a(cd, 0x01010101u, d);
         }
@@ -1077,6 +1269,7 @@ __global__ void __launch_bounds__(kThreads, (M * K * N >= 84) ? PLO_SWEEPN8_MINB
       k.primary = ((unsigned long long)z << 32) | (unsigned long long)(z - ((unsigned)(npair * lanes) - d));
       k.index = idx;
       if (k.primary < best.primary) best = k;
+      surv_emit(k);
       continue;
     }
     int V[K * K], W[N * N], Wi[N * N];
@@ -1112,6 +1305,7 @@ __global__ void __launch_bounds__(kThreads, (M * K * N >= 84) ? PLO_SWEEPN8_MINB
     k.primary = ((unsigned long long)z << 32) | (unsigned long long)(z - ((unsigned)(npair * lanes) - d));
     k.index = idx;
     if (k.primary < best.primary) best = k;
+    surv_emit(k);
   }
   best = block_min(best, red);
   if (threadIdx.x == 0) block_best[blockIdx.x] = best;
@@ -1230,6 +1424,7 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep8x_kernel(unsigned lo
     k.primary = (unsigned long long)__double_as_longlong(g2);
     k.index = idx;
     if (k.primary < best.primary) best = k;
+    surv_emit(k);
   }
   best = block_min(best, red);
   if (threadIdx.x == 0) block_best[blockIdx.x] = best;
@@ -1330,6 +1525,7 @@ __global__ void __launch_bounds__(kXThreads, 2) orbit_sweep2x_kernel(int3 den, u
     k.primary = ((unsigned long long)z << 32) | (unsigned long long)(z - (RU * 12u - d));
     k.index = idx;
     if (k.primary < best.primary) best = k;
+    surv_emit(k);
   }
   best = block_min(best, red);
   if (threadIdx.x == 0) block_best[blockIdx.x] = best;
@@ -1500,6 +1696,8 @@ struct ShapeOps {
                  unsigned long long hi, int lutn, bool lutfull, Key* bb, const int4* z3tab);  // four-lane growth-factor kernel (small magnitudes)
   int (*sweepn8)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, unsigned long long lo, unsigned long long hi,
                  Key* bb, const int4* z3tab, bool launch);                      // four-lane sparsity kernel; launch = false: blocks per SM
+  void (*gather)(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, const unsigned long long* list, unsigned long long count,
+                 double inv_den, uint4* rec);                                   // both measures of a list of candidates
 };
 
 template <int M, int K, int N, int RU>
@@ -1577,7 +1775,12 @@ struct Shape {
     else orbit_sweepn8_kernel<M, K, N, 1><<<sms, kThreads, smem, st>>>(r, den, seed, lo, hi, bb, z3tab);
     return 1;
   }
-  static ShapeOps ops() { return ShapeOps{M, K, N, RU, &sweep, &final, &table, &blocks_per_sm, &blocks_per_sm8, &allow_smem, &sweep8, &sweepn8}; }
+  static void gather(int mode, int grid, cudaStream_t st, int r, int3 den, unsigned long long seed, const unsigned long long* list, unsigned long long count,
+                     double inv_den, uint4* rec) {
+    if (mode == 0) orbit_gather_kernel<M, K, N, 0><<<grid, kThreads, 0, st>>>(r, den, seed, list, count, inv_den, rec);
+    else orbit_gather_kernel<M, K, N, 1><<<grid, kThreads, 0, st>>>(r, den, seed, list, count, inv_den, rec);
+  }
+  static ShapeOps ops() { return ShapeOps{M, K, N, RU, &sweep, &final, &table, &blocks_per_sm, &blocks_per_sm8, &allow_smem, &sweep8, &sweepn8, &gather}; }
 };
 
 // (m, k, n, unrolled r); r-specialised entries come first, the generic (ru = 0) entry of a shape last
@@ -2164,6 +2367,81 @@ int plo_orbit_table(int m, int k, int n, int r, const int32_t* L, const int32_t*
 // Survivors of [lo,hi): every candidate whose score does not exceed `threshold` (sparsity plans: (nnz, nno) <= (threshold.nnz,
 // threshold.nno) lexicographically; growth-factor plans: score <= threshold.score), with both measures, sorted by index.
 // Synchronous.  *count = number found; more than `capacity` -> PLO_E_RANGE (nothing is written; retry with *count records).
+// Survivors through the plan's own (packed, table-driven, ...) sweep kernel: pass 1 = the sweep with the constant-bank sink armed
+// (indices only, 8 bytes per survivor), device radix sort of the indices, pass 2 = both measures of the survivors in index order.
+// The growth-factor threshold is applied to the kernel's unscaled key with two ulps of slack and exactly on the records afterwards.
+static int survivors_from_the_sweep(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, const plo_orbit_best* threshold, uint64_t capacity,
+                                    plo_orbit_best* out, uint64_t* count) {
+  const uint64_t cap = capacity ? capacity : 1;
+  unsigned long long *d_idx = nullptr, *d_sorted = nullptr, *d_cnt = nullptr;
+  uint4* d_rec = nullptr;
+  void* d_temp = nullptr;
+  size_t temp_bytes = 0;
+  auto cleanup = [&]() { pool_free(d_idx); pool_free(d_sorted); pool_free(d_cnt); pool_free(d_rec); pool_free(d_temp); };
+  cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, d_idx, d_sorted, (int)std::min<uint64_t>(cap, 0x7fffffffull));
+  if (cap > 0x7fffffffull || pool_alloc(&d_idx, cap * 8) != cudaSuccess || pool_alloc(&d_sorted, cap * 8) != cudaSuccess || pool_alloc(&d_cnt, 8) != cudaSuccess ||
+      pool_alloc(&d_rec, cap * 32) != cudaSuccess || pool_alloc(&d_temp, temp_bytes ? temp_bytes : 1) != cudaSuccess) {
+    set_error("plo_orbit_plan_survivors: device allocation for %llu records failed", (unsigned long long)cap);
+    cleanup();
+    return PLO_E_CUDA;
+  }
+  Surv sv;
+  if (pl->measure == PLO_MEASURE_G2) {
+    double raw = threshold->score / pl->inv_den;
+    raw = std::nextafter(std::nextafter(raw, INFINITY), INFINITY);
+    if (!(raw >= 0.0)) raw = 0.0;
+    std::memcpy(&sv.thr, &raw, 8);
+  } else {
+    sv.thr = ((unsigned long long)threshold->nnz << 32) | threshold->nno;
+  }
+  sv.idx = d_idx; sv.count = d_cnt; sv.cap = capacity;
+  const Surv off{0ull, nullptr, nullptr, 0ull};
+  cudaError_t e = cudaMemset(d_cnt, 0, 8);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_surv, &sv, sizeof(sv));
+  int rc = PLO_OK;
+  if (e == cudaSuccess) rc = plo_orbit_plan_run(pl, lo, hi, nullptr);
+  cudaError_t e2 = cudaMemcpyToSymbol(c_surv, &off, sizeof(off));  // always disarm (synchronises with the sweep)
+  if (e == cudaSuccess) e = e2;
+  unsigned long long found = 0;
+  if (e == cudaSuccess && rc == PLO_OK) e = cudaMemcpy(&found, d_cnt, 8, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess || rc != PLO_OK) {
+    if (e != cudaSuccess) { set_error("plo_orbit_plan_survivors: %s", cudaGetErrorString(e)); rc = PLO_E_CUDA; }
+    cleanup();
+    return rc;
+  }
+  *count = found;
+  if (found > capacity) {
+    set_error("plo_orbit_plan_survivors: %llu survivors, capacity %llu", found, (unsigned long long)capacity);
+    cleanup();
+    return PLO_E_RANGE;
+  }
+  std::vector<uint4> rec((size_t)found * 2);
+  if (found) {
+    e = cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, d_idx, d_sorted, (int)found);
+    if (e == cudaSuccess) {
+      const int grid = (int)std::min<uint64_t>((found + kThreads - 1) / kThreads, (uint64_t)sm_count() * 8);
+      pl->ops->gather(pl->mode, grid, nullptr, pl->r, pl->den, pl->seed, d_sorted, found, pl->inv_den, d_rec);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(rec.data(), d_rec, (size_t)found * 32, cudaMemcpyDeviceToHost);
+  }
+  cleanup();
+  if (e != cudaSuccess) { set_error("plo_orbit_plan_survivors: %s", cudaGetErrorString(e)); return PLO_E_CUDA; }
+  uint64_t kept = 0;
+  for (size_t i = 0; i < (size_t)found; ++i) {
+    const uint4 a = rec[2 * i], b = rec[2 * i + 1];
+    const unsigned long long sb = ((unsigned long long)b.y << 32) | b.x;
+    double sc;
+    std::memcpy(&sc, &sb, 8);
+    if (pl->measure == PLO_MEASURE_G2 && !(sc <= threshold->score)) continue;  // the two ulps of slack of pass 1
+    out[kept].index = ((uint64_t)a.y << 32) | a.x;
+    out[kept].nnz = a.z; out[kept].nno = a.w; out[kept].score = sc;
+    ++kept;
+  }
+  *count = kept;
+  return PLO_OK;
+}
+
 int plo_orbit_plan_survivors(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, const plo_orbit_best* threshold, uint64_t capacity,
                              plo_orbit_best* out, uint64_t* count) {
   if (!pl || !threshold || !count || hi < lo || (capacity && !out)) { set_error("plo_orbit_plan_survivors: bad argument"); return PLO_E_ARG; }
@@ -2171,6 +2449,8 @@ int plo_orbit_plan_survivors(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, const
   if (hi == lo) return PLO_OK;
   int rc = orbit_upload(pl, nullptr);
   if (rc) return rc;
+  if (!pl->wide && getenv("PLO_ORBIT_TABLE_SURVIVORS") == nullptr)
+    return survivors_from_the_sweep(pl, lo, hi, threshold, capacity, out, count);
   const uint64_t cap = capacity ? capacity : 1;
   uint4* d_rec = nullptr;
   unsigned long long* d_cnt = nullptr;
