@@ -15,7 +15,9 @@
  * thread, the parallelism is inside): calls are serialised per device by the caller.  The orbit kernels keep L|R|P and the Philox
  * round keys of the plan that ran last in the device's constant memory (re-uploaded when another plan runs), and the workspace
  * pool is per device, so two host threads must not drive the same device at the same time; different devices are independent
- * (plo_orbit_sweep_devices drives several from one thread).  The last-error message is thread-local.
+ * (plo_orbit_sweep_devices drives several from one thread).  ONE thread may use several streams and alternate plans freely: the bank
+ * is guarded by an event (a stream that re-writes it, or reads it after another stream wrote it, waits for its last use).
+ * The last-error message is thread-local.
  * ========================================================================== */
 #ifndef PLINOPT_B200_H
 #define PLINOPT_B200_H
@@ -308,8 +310,9 @@ void plo_factor_plan_destroy(plo_factor_plan* plan);
  * exactly one non-zero coordinate (pos = that coordinate).  base (r x n) = the rows of M, prod
  * (r x c x n) = C[v].M[q], both in the field: residues mod p (p > 0) or integers scaled by a common
  * denominator (p == 0, |entries| <= 2^60).  Hits come back in the reference's depth-first order
- * (a combination before its extensions); at most max_hits are stored, *nhits is the total found,
- * *ncand the number of combinations tested.
+ * (a combination before its extensions); *nhits is the total found, *ncand the number of combinations tested.  When more hits
+ * exist than max_hits the call returns PLO_E_RANGE with *nhits set (call again with room for all of them): the records stored in
+ * that case are an arbitrary subset, not the first lines of the reference's output.
  * ------------------------------------------------------------------------ */
 typedef struct plo_dep_hit {
   int32_t depth;    /* number of added rows d */

@@ -720,8 +720,11 @@ def depender(M, level, maxnumcoeff=11, q=0, user=(), max_hits=1 << 20, text_cap=
     f = lib().plo_depender
     f.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p,
                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
-    _check(f(q, r, n, _ptr(num), _ptr(den), len(user), _ptr(un) if len(user) else None, _ptr(ud) if len(user) else None, maxnumcoeff, level,
-             max_hits, C.cast(hits, C.c_void_p), C.byref(nh), C.byref(nc), text, text_cap, C.byref(tl), _ptr(cn), _ptr(cd), C.byref(ncoef)))
+    rc = f(q, r, n, _ptr(num), _ptr(den), len(user), _ptr(un) if len(user) else None, _ptr(ud) if len(user) else None, maxnumcoeff, level,
+           max_hits, C.cast(hits, C.c_void_p), C.byref(nh), C.byref(nc), text, text_cap, C.byref(tl), _ptr(cn), _ptr(cd), C.byref(ncoef))
+    if rc == E_RANGE and nh.value > max_hits:  # more hits than room: the library reports the total, come back with room for all
+        return depender(M, level, maxnumcoeff, q, user, max_hits=nh.value, text_cap=max(text_cap, 80 * nh.value))
+    _check(rc)
     k = min(nh.value, max_hits)
     out = [(h.depth, h.pos, tuple(h.rows), tuple(h.coefs)) for h in hits[:k]]
     coeffs = [Fraction(int(a), int(b)) for a, b in zip(cn[:ncoef.value], cd[:ncoef.value])]

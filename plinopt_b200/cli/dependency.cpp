@@ -45,13 +45,13 @@ int main(int argc, char** argv) {
   std::vector<char> text;
   std::vector<int64_t> cn(maxnumcoeff), cd(maxnumcoeff, 1);
   int ncoef = 0, rc = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {  // second pass only if the hit list was larger than the first guess
+  for (int attempt = 0; attempt < 3; ++attempt) {  // further passes only if the hit list or its text was larger than the first guess
     hits.resize(max_hits);
     text.resize(max_hits * 64 + 64);
     rc = plo_depender(q, in.rows, in.cols, in.num.data(), in.den.data(), (int)un.size(), un.data(), ud.data(), (int)maxnumcoeff, (int)level,
                       max_hits, hits.data(), &nhits, &ncand, text.data(), text.size(), &tlen, cn.data(), cd.data(), &ncoef);
-    if (rc != PLO_OK || (nhits <= max_hits && tlen < text.size())) break;
-    max_hits = nhits;
+    if (rc == PLO_E_RANGE && nhits > max_hits) { max_hits = nhits; continue; }  // more hits than room: come back with room for all of them
+    if (rc != PLO_OK || tlen < text.size()) break;
   }
   if (rc != PLO_OK) { std::cerr << "# \033[1;31m****** ERROR " << rc << ": " << plo_last_error() << " ******\033[0m" << std::endl; return rc; }
   std::clog << "# [DEPND] level " << level << ", coefficients: [";

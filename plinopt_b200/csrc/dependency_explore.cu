@@ -263,6 +263,12 @@ static int dep_run(uint32_t p, int r, int n, int c, int level, const int64_t* ba
   });
   if (nhits) *nhits = total_hits;
   if (ncand) *ncand = total_cand;
+  if (total_hits > max_hits) {
+    // The stored subset was filled depth by depth in arrival order: it is NOT the first max_hits lines of the reference's
+    // depth-first output.  Same protocol as plo_orbit_plan_survivors: report the total and let the caller come back with room.
+    set_error("plo_dependency_explore: %llu hits, room for %llu", total_hits, (unsigned long long)max_hits);
+    return PLO_E_RANGE;
+  }
   return PLO_OK;
 }
 

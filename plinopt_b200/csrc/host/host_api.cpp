@@ -312,8 +312,8 @@ static int run_depender(const F& f, const Dense<QField>& B, const std::vector<Ra
   }
   uint64_t found = 0;
   const int rc = plo_dependency_explore(p, (int)r, (int)n, (int)c, level, base.data(), prod.data(), max_hits, hits, &found, ncand);
+  if (nhits) *nhits = found;  // also set with PLO_E_RANGE: the number of records the caller has to make room for
   if (rc) return rc;
-  if (nhits) *nhits = found;
   if (text) {
     DependencyHost<F> dh(f);
     std::string all;

@@ -1855,6 +1855,30 @@ static const void*& const_owner() {
   cudaGetDevice(&d);
   return g_const_owner_dev[(d >= 0 && d < kMaxDevices) ? d : 0];
 }
+// The constant bank is shared by every plan of a device, and plan_run is asynchronous: before the bank is re-written, or read from
+// another stream than the one that wrote it, that stream waits for an event recorded after the bank's last use.  This makes one host
+// thread driving several streams (or alternating plans) safe; two host threads on one device are still excluded (plinopt_b200.h).
+static cudaEvent_t g_bank_event[kMaxDevices] = {nullptr};
+static cudaStream_t g_bank_stream[kMaxDevices] = {nullptr};
+static bool g_bank_used[kMaxDevices] = {false};
+static int bank_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+// call before uploading to the bank or launching a kernel that reads it on stream `st`
+static void bank_acquire(cudaStream_t st, bool rewriting) {
+  const int d = bank_device();
+  if (g_bank_used[d] && g_bank_event[d] && (rewriting || g_bank_stream[d] != st)) cudaStreamWaitEvent(st, g_bank_event[d], 0);
+}
+// call after the last launch of a sequence that reads the bank on stream `st`
+static void bank_release(cudaStream_t st) {
+  const int d = bank_device();
+  if (!g_bank_event[d] && cudaEventCreateWithFlags(&g_bank_event[d], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); g_bank_event[d] = nullptr; return; }
+  cudaEventRecord(g_bank_event[d], st);
+  g_bank_stream[d] = st;
+  g_bank_used[d] = true;
+}
 
 // Host-only self-test of the "whole matrix from one number" decode the table-driven kernels rely on (no device needed): for S = 2
 // (48 matrices) and S = 3 (7776), drawing the digits of a matrix one by one from a word x gives the same matrix as replaying matrix
@@ -1945,6 +1969,7 @@ static int orbit_modp(uint32_t p, int m, int k, int n, int r, const int32_t* L, 
   uint32_t *d_nnz = nullptr, *d_nno = nullptr;
   auto cleanup = [&]() { pool_free(d_bb); pool_free(d_nnz); pool_free(d_nno); };
   const_owner() = nullptr;
+  bank_acquire(nullptr, true);
   cudaError_t e = cudaMemcpyToSymbol(c_lrp, h.data(), total * sizeof(int));
   if (e == cudaSuccess) e = pool_alloc(&d_bb, sizeof(Key) * grid);
   if (e == cudaSuccess && tnnz && cnt) e = pool_alloc(&d_nnz, cnt * 4);
@@ -2137,6 +2162,7 @@ int plo_orbit_plan_create(plo_orbit_plan** plan, int m, int k, int n, int r, con
 }
 
 static int orbit_upload(plo_orbit_plan* pl, cudaStream_t st) {
+  bank_acquire(st, const_owner() != pl);
   if (const_owner() != pl) {
     PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp, pl->h_lrp.data(), pl->h_lrp.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
     if (pl->pack8 || pl->packn8) PLO_CUDA(cudaMemcpyToSymbolAsync(c_lrp2, pl->h_lrp2.data(), pl->h_lrp2.size() * sizeof(int), 0, cudaMemcpyHostToDevice, st));
@@ -2162,6 +2188,7 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
                pl->d_block_best, nullptr, nullptr, nullptr, no_sink());
     }
     PLO_CUDA(cudaGetLastError());
+    bank_release(st);
     return PLO_OK;
   }
   if (pl->xtab) {
@@ -2175,6 +2202,7 @@ int plo_orbit_plan_run(plo_orbit_plan* pl, uint64_t lo, uint64_t hi, void* strea
   else pl->ops->sweep(pl->measure, pl->mode, pl->grid, pl->smem, st, pl->r, pl->den, pl->seed, lo, hi, pl->lutn, pl->lutfull, pl->pack, pl->d_block_best);
   pl->ops->final(pl->mode, st, pl->r, pl->den, pl->seed, pl->grid, pl->measure, pl->inv_den, pl->d_block_best, pl->d_out);
   PLO_CUDA(cudaGetLastError());
+  bank_release(st);
   return PLO_OK;
 }
 
@@ -2224,8 +2252,9 @@ int plo_orbit_plan_kernel(const plo_orbit_plan* pl, char* name, int cap, int* la
   if (pl->wide) { nm = "orbit_wide_kernel"; ln = 1; }
   else if (pl->xtab) { nm = "orbit_sweep8x_kernel"; ln = 4; }
   else if (pl->xtab2) { nm = "orbit_sweep2x_kernel"; ln = 2; }
-  else if (pl->packn8) { nm = "orbit_sweepn8_kernel"; ln = 4; }
-  else if (pl->pack8) { nm = "orbit_sweep8_kernel"; ln = 4; }
+  // the suffix names the code variant the templates select for this shape, so that a profile is never quoted for another variant
+  else if (pl->packn8) { nm = pl->m * pl->k * pl->n >= 84 ? (pl->n >= 5 ? "orbit_sweepn8_kernel+3phase+tri" : "orbit_sweepn8_kernel+3phase") : "orbit_sweepn8_kernel"; ln = 4; }
+  else if (pl->pack8) { nm = pl->n >= 5 && !(pl->m == 2 && pl->k == 2 && pl->n == 2) ? "orbit_sweep8_kernel+tri" : "orbit_sweep8_kernel"; ln = 4; }
   else { nm = "orbit_sweep_kernel"; ln = pl->pack ? 2 : 1; }
   if (name && cap > 0) { strncpy(name, nm, (size_t)cap - 1); name[cap - 1] = 0; }
   if (lanes) *lanes = ln;
@@ -2396,6 +2425,7 @@ static int survivors_from_the_sweep(plo_orbit_plan* pl, uint64_t lo, uint64_t hi
   }
   sv.idx = d_idx; sv.count = d_cnt; sv.cap = capacity;
   const Surv off{0ull, nullptr, nullptr, 0ull};
+  bank_acquire(nullptr, true);  // nothing that still reads the bank may see the sink armed
   cudaError_t e = cudaMemset(d_cnt, 0, 8);
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_surv, &sv, sizeof(sv));
   int rc = PLO_OK;
@@ -2531,6 +2561,7 @@ static int orbit_wide64(int m, int k, int n, int r, const int64_t* L, const int6
   double* d_g2 = nullptr;
   auto cleanup = [&]() { pool_free(d_bb); pool_free(d_nnz); pool_free(d_nno); pool_free(d_g2); };
   const_owner() = nullptr;
+  bank_acquire(nullptr, true);
   cudaError_t e = cudaMemcpyToSymbol(c_lrp, h.data(), total * sizeof(long long));
   Key none;
   none.primary = ~0ull; none.index = ~0ull;

@@ -3,6 +3,7 @@ recursion: same coefficient list, same hits, same (depth-first) order, same coun
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 import oracle_lib as O
@@ -48,8 +49,19 @@ def test_user_coefficients_and_text(capi):
 def test_hit_list_truncation_and_errors(capi):
     M = O.dense_fractions("2x2x2_7_Winograd_L")
     full = capi.depender(M, 4, 5)
+    # too little room: the C call reports PLO_E_RANGE with the total (a truncated list would be an arbitrary subset, not the first lines of the
+    # reference's depth-first output); the binding comes back with room and returns the complete list
+    import ctypes as C
+    num, den = capi._numden(M)
+    hits = (capi.DepHit * 7)()
+    nh, nc, tl, ncoef = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+    cn = np.zeros(5, dtype=np.int64); cd = np.ones(5, dtype=np.int64)
+    f = capi.lib().plo_depender
+    rc = f(0, len(M), len(M[0]), capi._ptr(num), capi._ptr(den), 0, None, None, 5, 4, 7, C.cast(hits, C.c_void_p), C.byref(nh), C.byref(nc), None, 0, C.byref(tl),
+           capi._ptr(cn), capi._ptr(cd), C.byref(ncoef))
+    assert rc == capi.E_RANGE and nh.value == full["nhits"] > 7
     part = capi.depender(M, 4, 5, max_hits=7)
-    assert part["nhits"] == full["nhits"] and len(part["hits"]) == 7
+    assert part["nhits"] == full["nhits"] and part["hits"] == full["hits"] and part["text"] == full["text"]
     assert capi.depender(M, 1, 5)["ncand"] == 0  # level 1: nothing to add (:153-160)
     with pytest.raises(capi.PloError):
         capi.depender(M, 7, 5)  # more than 4 added rows is not supported

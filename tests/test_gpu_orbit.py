@@ -304,3 +304,29 @@ def test_table_driven_decode_in_exhaustive_mode(capi, stem, lo):
                 j = int(np.argmin(g2[sl]))
                 assert got["index"] == lo + a + j and got["score"] == g2[sl][j]
         plan.close()
+
+
+def test_two_plans_on_two_streams_share_the_constant_bank_safely(capi):
+    """plo_orbit_plan_run is asynchronous and every plan of a device uses the same constant bank: alternating two plans on two
+    non-blocking streams without any synchronisation in between must give the single-stream answers (the bank is guarded by an
+    event: a stream that re-writes it waits for its last use)."""
+    import torch
+    from plinopt_b200 import hm
+    torch.cuda.set_device(0)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    plans, ranges = [], [(0, 1 << 22), (5, (1 << 18) + 5)]
+    for stem, measure in (("2x2x2_7_Winograd", capi.MEASURE_G2), ("3x3x3_23_58", capi.MEASURE_NNZ)):
+        L, R, P = hm.load_fixture(stem)
+        (Li, dl), (Ri, dr), (Pi, dp) = (hm.scaled(M, np.int32) for M in (L, R, P))
+        plans.append(capi.OrbitPlan(hm.LRP2MM(L, R, P), Li, Ri, Pi, (dl, dr, dp), measure, capi.MODE_PHILOX, SEED))
+    expect = []
+    for pl, (lo, hi) in zip(plans, ranges):
+        pl.run(lo, hi, 0)
+        expect.append(pl.result(0))
+    for _ in range(25):
+        plans[0].run(*ranges[0], s1.cuda_stream)
+        plans[1].run(*ranges[1], s2.cuda_stream)
+    got = [plans[0].result(s1.cuda_stream), plans[1].result(s2.cuda_stream)]
+    assert got == expect
+    for pl in plans:
+        pl.close()

@@ -24,7 +24,7 @@ def main():
     rd, ru = get("dram__bytes_read.sum")
     wr, wu = get("dram__bytes_write.sum")
     name = r[hdr.index("Kernel Name")]
-    assert key.split("|")[0] in name, (key, name)
+    assert key.split("|")[0].split("+")[0] in name, (key, name)
     try:
         table = json.load(open(OUT))
     except Exception:
