@@ -361,8 +361,8 @@ def bench_orbit(ctx, stem, measure, batch_log2, steps, warmup, cpu_seconds, head
         plan.run(lo, lo + B, ctx.sp)
         row = slots[s % slots.shape[0]]
         plan.pack(row.data_ptr(), ctx.rank, ctx.world, ctx.sp)
-        if ctx.world > 1:
-            ctx.dist.all_reduce(row, op=ctx.dist.ReduceOp.MIN)
+        if ctx.world > 1:  # the engine's own NCCL all-reduce on the device table, same stream: no host hop, no torch on the data path
+            ctx.comm.allreduce_i64(row.data_ptr(), ctx.world * 4, capi.REDUCE_MIN, ctx.sp)
 
     sampler = ClockSampler(ctx.local) if headline else None
     if sampler:
@@ -453,7 +453,7 @@ def bench_orbit_strong(ctx, stem, measure, total_log2, steps):
         plan.run(lo, hi, ctx.sp)
         plan.pack(slots.data_ptr(), ctx.rank, ctx.world, ctx.sp)
         if ctx.world > 1:
-            ctx.dist.all_reduce(slots, op=ctx.dist.ReduceOp.MIN)
+            ctx.comm.allreduce_i64(slots.data_ptr(), ctx.world * 4, capi.REDUCE_MIN, ctx.sp)
     ms = timed_steps(ctx, step, steps, 1)
     g = sharding.pick_global(slots.cpu().tolist(), ctx.world, measure_nnz=(measure == capi.MEASURE_NNZ))
     plan.close()
@@ -617,8 +617,15 @@ def main():
     capi.set_device(ctx.local)
     ctx.dev = torch.device("cuda", ctx.local)
     ctx.dist = dist
+    ctx.comm = None
     if ctx.world > 1:
-        dist.init_process_group("nccl", device_id=ctx.dev)
+        dist.init_process_group("nccl", device_id=ctx.dev)  # launch plumbing: barriers, max-over-ranks of the timings, the id exchange below
+
+        def exchange(ident):
+            box = [ident]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        ctx.comm = capi.Comm(ctx.rank, ctx.world, exchange)  # the data-path collective is the engine's own (plo_comm_*, NCCL via dlopen)
     ctx.stream = torch.cuda.current_stream()
     ctx.sp = ctx.stream.cuda_stream
     ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device=ctx.dev)  # > 126 MB L2
@@ -643,7 +650,7 @@ def main():
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 + f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "candidates_per_gpu_per_step": 1 << args.batch_log2, "seed": hex(SEED),
-                       "parallelism": f"index-range sharding x{ctx.world} + one min-allreduce on the device buffer",
+                       "parallelism": f"index-range sharding x{ctx.world} + one min-allreduce (plo_comm_allreduce_i64: NCCL issued by the engine on the device table)",
                        "l2": "256 MiB buffer rewritten between timed iterations (outside the event pairs); the path reads 84 ints from constant memory"},
             "clocks": ctx.clocks,
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"],
@@ -652,6 +659,7 @@ def main():
         }
         print(json.dumps(line))
     if ctx.world > 1:
+        ctx.comm.close()
         dist.destroy_process_group()
     return 0
 

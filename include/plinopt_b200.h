@@ -325,6 +325,26 @@ int plo_dependency_explore(uint32_t p, int r, int n, int c, int level, const int
                            uint64_t max_hits, plo_dep_hit* hits, uint64_t* nhits, uint64_t* ncand);
 
 /* ---------------------------------------------------------------------------
+ * The one collective of the path, issued by the engine: an all-reduce (min / max) over a few int64 words of device memory through
+ * NCCL (one rank per GPU and process).  north_star: "a single tiny NCCL allreduce(min-with-index) picks the global best"; reference
+ * analogue: the `omp critical` of src/orbiter.cpp:298.  NCCL is bound at run time (dlopen of libnccl.so.2), so single-GPU users
+ * never need it.  Rank 0 calls plo_comm_unique_id and hands the 128 bytes to the other ranks through whatever launched them
+ * (bench.py: torch.distributed broadcast); every rank then calls plo_comm_create on its own device.  A sweep step on N GPUs is
+ *   plo_orbit_plan_run -> plo_orbit_plan_pack(slots) -> plo_comm_allreduce_i64(slots, 4*N, PLO_REDUCE_MIN)   all on one stream,
+ * the sparsifier search merges its packed (rl, cl, -index) keys with PLO_REDUCE_MAX.
+ * ------------------------------------------------------------------------ */
+#define PLO_REDUCE_MIN 0
+#define PLO_REDUCE_MAX 1
+typedef struct plo_comm plo_comm;
+int plo_comm_nccl_version(void);                 /* 0 when libnccl.so.2 cannot be loaded */
+int plo_comm_unique_id(uint8_t* id128);          /* 128 bytes, rank 0 */
+int plo_comm_create(plo_comm** comm, int rank, int world, const uint8_t* id128);
+int plo_comm_rank(const plo_comm* comm);
+int plo_comm_size(const plo_comm* comm);
+int plo_comm_allreduce_i64(plo_comm* comm, int64_t* buf_device, uint64_t count, int op, void* stream);  /* in place, asynchronous on `stream` */
+void plo_comm_destroy(plo_comm* comm);
+
+/* ---------------------------------------------------------------------------
  * The other sweeps sharded over the first `ndev` CUDA devices of the calling process (clamped to the devices present), like
  * plo_orbit_sweep_devices: one host thread, asynchronous launches, results merged in device order -- same answers as the
  * single-device calls.  Reference analogues: the omp loops of include/plinopt_sparsify.inl:962,968 and src/orbiter.cpp:272.

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libplinopt_b200.so")
-SOURCES = ["common.cu", "orbit_sweep.cu", "lincomb_search.cu", "lincomb_quad.cu", "mmcheck.cu", "factor_sweep.cu", "dependency_explore.cu", "multi_device.cu", "peaks.cu", "host/host_api.cpp"]
+SOURCES = ["common.cu", "orbit_sweep.cu", "lincomb_search.cu", "lincomb_quad.cu", "mmcheck.cu", "factor_sweep.cu", "dependency_explore.cu", "multi_device.cu", "nccl_comm.cu", "peaks.cu", "host/host_api.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v",
               "-split-compile", "0"]  # ptxas of the many template instantiations in parallel (orbit_sweep.cu: 180 s -> 60 s)
@@ -69,7 +69,7 @@ def build_library(force=False, verbose=False):
                 if verbose:
                     print("compiled", s, file=sys.stderr)
     if jobs or force or not os.path.exists(LIB):
-        cmd = [nvcc] + ccbin + ["-shared", "-cudart", "static", "-o", LIB] + objs
+        cmd = [nvcc] + ccbin + ["-shared", "-cudart", "static", "-o", LIB] + objs + ["-ldl"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")

@@ -21,7 +21,7 @@ NO_INDEX = 2 ** 64 - 1
 
 # every symbol include/plinopt_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "plo_release_workspace", "plo_set_sweep_devices", "plo_orbit_sweep_devices", "plo_lincomb_search_devices", "plo_mmcheck_batch_devices", "plo_factor_sweep_devices",
+    "plo_release_workspace", "plo_comm_nccl_version", "plo_comm_unique_id", "plo_comm_create", "plo_comm_rank", "plo_comm_size", "plo_comm_allreduce_i64", "plo_comm_destroy", "plo_set_sweep_devices", "plo_orbit_sweep_devices", "plo_lincomb_search_devices", "plo_mmcheck_batch_devices", "plo_factor_sweep_devices",
     "plo_version", "plo_device_count", "plo_set_device", "plo_last_error",
     "plo_lincomb_search", "plo_lincomb_search_batch", "plo_lincomb_quad", "plo_lincomb_plan_create", "plo_lincomb_plan_run", "plo_lincomb_plan_run_range",
     "plo_lincomb_plan_result", "plo_lincomb_plan_candidates", "plo_lincomb_plan_launches", "plo_lincomb_plan_destroy",
@@ -122,6 +122,37 @@ def lincomb_search(p, TM, off, coeffs, prev_rows=None, init_rl=-1, init_cl=-1):
     _check(f(int(p), n, m, _ptr(TM), int(off), len(coeffs), _ptr(coeffs), nprev, _ptr(prev), int(init_rl), int(init_cl),
              C.byref(rl), C.byref(cl), C.byref(idx)))
     return rl.value, cl.value, (None if idx.value == NO_INDEX else idx.value)
+
+
+REDUCE_MIN, REDUCE_MAX = 0, 1
+
+
+class Comm:
+    """The engine's own NCCL communicator (plo_comm_*): one rank per GPU and process.  `exchange(id_or_None)` is whatever hands rank 0's
+    128-byte unique id to the other ranks (bench.py: a torch.distributed broadcast) -- the engine does the collective itself."""
+
+    def __init__(self, rank, world, exchange):
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _check(lib().plo_comm_unique_id(_ptr(ident)))
+        ident = np.frombuffer(bytes(exchange(ident.tobytes() if rank == 0 else None)), dtype=np.uint8).copy()
+        self._h = C.c_void_p()
+        f = lib().plo_comm_create
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
+        _check(f(C.byref(self._h), rank, world, _ptr(ident)))
+        self.rank, self.world = rank, world
+
+    def allreduce_i64(self, device_ptr, count, op=REDUCE_MIN, stream=0):
+        f = lib().plo_comm_allreduce_i64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        _check(f(self._h, C.c_void_p(device_ptr), count, op, C.c_void_p(stream)))
+
+    def close(self):
+        if self._h:
+            f = lib().plo_comm_destroy
+            f.argtypes = [C.c_void_p]
+            f(self._h)
+            self._h = C.c_void_p()
 
 
 def lincomb_search_devices(ndev, p, TM, off, coeffs, prev_rows=None, init_rl=-1, init_cl=-1):

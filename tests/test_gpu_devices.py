@@ -46,3 +46,16 @@ def test_factor_sweep_devices(capi, ndev):
     A = np.array([[(x.numerator % P31) * pow(x.denominator % P31, -1, P31) % P31 for x in row] for row in M], dtype=np.uint32)
     assert capi.factor_sweep_devices(ndev, P31, A, 12, SEED, 0, 5000) == capi.factor_sweep(P31, A, 12, SEED, 0, 5000)
     assert capi.factor_sweep_devices(ndev, P31, A, 12, SEED, 7, 7)[3] is None
+
+
+def test_engine_comm_single_rank(capi):
+    """plo_comm_* (NCCL bound at run time): a one-rank communicator reduces a device table to itself; the N-rank case runs in
+    bench.py under torchrun."""
+    import torch
+    assert capi.lib().plo_comm_nccl_version() >= 20000
+    comm = capi.Comm(0, 1, lambda ident: ident)
+    t = torch.tensor([5, -7, 2 ** 62, 0], dtype=torch.int64, device="cuda:0")
+    comm.allreduce_i64(t.data_ptr(), 4, capi.REDUCE_MIN, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert t.tolist() == [5, -7, 2 ** 62, 0]
+    comm.close()

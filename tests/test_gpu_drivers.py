@@ -172,3 +172,31 @@ def test_growth_factors(capi, stem):
         assert got["Ginfinf"] == 12.0 and abs(got["G2"] - (12 + 2 * 2 ** 0.5)) < 1e-12 and got["Q0"] == 8.0
     if stem == "2x2x2_7_Winograd":
         assert got["Ginfinf"] == 18.0 and abs(got["G2"] - 17.8530) < 5e-5
+
+
+def test_blocksparsifier_on_c5_width_blocks(capi):
+    """BASELINE config 5 size: column blocks of 32x32x32_15096_L (TM = 4 x 15096 per block: the tiled wide search kernels behind the
+    one-row entry point, sparse-row eliminations on the host).  The reference's own check (bin/FDT.sh): consistent factorisation
+    M == Res.CoB, and the residue is sparser.  (The whole 15096 x 1024 matrix takes 3.2 s: profiles/sparsifier_c5_r02.jsonl.)"""
+    import ctypes as C
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "large", "32x32x32_15096.npz")
+    if not os.path.exists(path):
+        pytest.skip("large fixture absent")
+    z = np.load(path)
+    rows, cols = (int(v) for v in z["L_shape"])
+    ncols = 12
+    num = np.zeros((rows, ncols), dtype=np.int64); den = np.ones((rows, ncols), dtype=np.int64)
+    ri = np.repeat(np.arange(rows), np.diff(z["L_ptr"]))
+    sel = z["L_col"] < ncols
+    num[ri[sel], z["L_col"][sel]] = z["L_num"][sel]; den[ri[sel], z["L_col"][sel]] = z["L_den"][sel]
+    for q in (2147483647, 0):
+        cn = np.zeros((ncols, ncols), dtype=np.int64); cd = np.ones((ncols, ncols), dtype=np.int64)
+        rn = np.zeros((rows, ncols), dtype=np.int64); rd = np.ones((rows, ncols), dtype=np.int64)
+        ok = C.c_int(0)
+        stats = np.zeros(3, dtype=np.uint64)
+        f = capi.lib().plo_sparsifier
+        f.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_int), C.c_void_p, C.c_int]
+        rc = f(q, rows, ncols, capi._ptr(num), capi._ptr(den), 4, 5, 1, capi._ptr(cn), capi._ptr(cd), capi._ptr(rn), capi._ptr(rd), C.byref(ok), capi._ptr(stats), -1)
+        assert rc == 0, capi.lib().plo_last_error()
+        assert ok.value == 1 and np.count_nonzero(rn) < np.count_nonzero(num) and stats[0] > 0

@@ -355,3 +355,44 @@ def test_quad_multi_kernel_path(capi, monkeypatch, p, c):
     assert run_steps(capi, TM, p, c) == 4
     monkeypatch.delenv("PLO_QUAD_NOSMALL")
     assert run_steps(capi, TM, p, c) == 4
+
+
+@pytest.mark.parametrize("n,c,p", [(1, 3, 0), (2, 4, 0), (3, 5, 7), (4, 1, 0), (4, 2, P31), (5, 3, 0)])
+def test_quad_edge_shapes(capi, n, c, p):
+    """One-row and two-row blocks (positions beyond n are truncated, Q4), a coefficient list that is just {0} (no admissible
+    candidate at all: PLO_QUAD_MISS at row 0) or {0, 1}, a last block with one live position (n = 5): the rows equal the one-step
+    entry point's."""
+    M = O.dense_fractions("3x4x7_63_rational_L")  # 63 x 12
+    TM = transpose([row[:n] for row in M])
+    if p == 0:
+        tm_int = col_scaled(TM)
+        cf_int = np.array([0, 1, -1, 2, -2][:c], dtype=np.int64)
+    else:
+        tm_int = np.array([[(v.numerator % p) * pow(v.denominator % p, -1, p) % p for v in row] for row in TM], dtype=np.int64)
+        cf_int = np.array([0, 1, p - 1, 2, p - 2][:c], dtype=np.int64)
+    for off in range(0, n, 4):
+        prev0 = np.zeros((off, n), dtype=np.int64)
+        for t in range(off):
+            prev0[t, t] = 1  # earlier blocks: canonical rows on their own positions
+        exp = sequential_rows(capi, p, tm_int, off, cf_int, prev0, (-1, -1), None)
+        (status, rows), = capi.lincomb_quad(p, [dict(TM=tm_int, off=off, coeffs=cf_int, prev_rows=prev0 if off else None)])
+        assert rows == exp, (off, rows, exp)
+        assert status == (capi.QUAD_DONE if len(rows) == min(4, n - off) else capi.QUAD_MISS)
+
+
+def test_coefficient_count_limit(capi):
+    """c <= 511: every index below c^4 keeps its own 36-bit field under the seed's in the packed (rl, cl, -index) key; c = 512 would
+    let the last candidate collide with it, so it is rejected (PLO_E_ARG) by every entry point."""
+    from plinopt_b200 import sharding
+    tm = np.ones((4, 8), dtype=np.int64)
+    cf = np.arange(512, dtype=np.int64)
+    for call in (lambda: capi.lincomb_search(P31, tm, 0, cf), lambda: capi.lincomb_quad(P31, [dict(TM=tm, off=0, coeffs=cf)]),
+                 lambda: capi.lincomb_search_devices(2, P31, tm, 0, cf)):
+        with pytest.raises(capi.PloError) as e:
+            call()
+        assert e.value.code == capi.E_ARG
+    last = 511 ** 4 - 1
+    k = sharding.lincomb_key(3, 1, last)
+    assert sharding.lincomb_unkey(k) == (3, 1, last) and k > sharding.lincomb_key(3, 1, None)
+    with pytest.raises(ValueError):
+        sharding.lincomb_key(3, 1, 2 ** 36 - 1)
