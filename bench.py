@@ -60,6 +60,10 @@ class ClockSampler(threading.Thread):
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")  # NVML numbers the physical devices: map the CUDA ordinal through the mask
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if ids and all(v.isdigit() for v in ids) and index < len(ids):
+                index = int(ids[index])
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.ok = True
         except Exception:
