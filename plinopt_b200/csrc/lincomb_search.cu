@@ -21,6 +21,7 @@
 // strict-'>' first-maximiser rule and is associative, so the warp-shuffle /
 // block / atomicMax reduction is deterministic for any launch geometry.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -151,6 +152,140 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_kernel(const LcParams<T> p
     }
     if (threadIdx.x == 0) atomicMax(prm.result + b, v);
   }
+}
+
+// ---------------------------------------------------------------------------
+// Many coefficients mod p (c >= 32): inverse lookup instead of c compares per coordinate (lincomb_common.cuh, "inverse lookup").
+// Thread <-> prefix; per coordinate one Barrett multiplication and one hash probe; the hits go into c byte counters of the
+// thread (shared memory, padded rows); then the usual keep-best over l, skipping four empty counters at a time.
+// Same key, same lazy independence test, same winner as lincomb_kernel.
+// ---------------------------------------------------------------------------
+struct LcInvParams {
+  const unsigned int* inv;   // [b][InvTables::words]
+  int hbits, cpad;           // hash bits; c rounded up to a multiple of 4
+  unsigned long long m64;    // floor((2^64-1)/p)
+};
+
+template <int MPAD>
+__global__ void __launch_bounds__(kLcThreads) lincomb_inv_kernel(const LcParams<unsigned int> prm, const LcInvParams ip) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned long long red[32];
+  const int b = blockIdx.y, c = prm.c, hsize = 1 << ip.hbits;
+  const unsigned int p = prm.p;
+  unsigned int* ninv = reinterpret_cast<unsigned int*>(smem_raw);
+  uint2* htab = reinterpret_cast<uint2*>(ninv + MPAD);
+  unsigned int* nextdup = reinterpret_cast<unsigned int*>(htab + hsize);
+  unsigned char* hist0 = reinterpret_cast<unsigned char*>(nextdup + c);
+  const int hstride = ip.cpad + 4;  // bytes per thread: consecutive threads start in different banks
+  unsigned char* hist = hist0 + (size_t)threadIdx.x * hstride;
+  {
+    const unsigned int* src = ip.inv + (size_t)b * InvTables::words(MPAD, hsize, c);
+    const int nw = (int)InvTables::words(MPAD, hsize, c);
+    for (int e = threadIdx.x; e < nw; e += kLcThreads) ninv[e] = src[e];  // ninv | htab | nextdup are contiguous
+  }
+  __syncthreads();
+  const size_t tab = (size_t)c * MPAD;
+  const unsigned int* __restrict__ t0 = prm.t0 + b * tab;
+  const unsigned int* __restrict__ t1 = prm.t1 + b * tab;
+  const unsigned int* __restrict__ t2 = prm.t2 + b * tab;
+  const unsigned char* __restrict__ zf = prm.zflag + (size_t)b * 4 * c;
+  const long long* __restrict__ phi = prm.phi + b * 16;
+  const long long* __restrict__ coef = prm.coef + (size_t)b * c;
+  const int nphi = prm.nphi[b];
+  unsigned long long best = prm.seed[b];
+  const unsigned long long nthreads = (unsigned long long)gridDim.x * kLcThreads;
+  for (unsigned long long q = prm.qlo + (unsigned long long)blockIdx.x * kLcThreads + threadIdx.x; q < prm.qhi; q += nthreads) {
+    const int k = (int)(q % (unsigned)c);
+    const unsigned long long qq = q / (unsigned)c;
+    const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
+    for (int w = 0; w < ip.cpad; w += 4) *reinterpret_cast<unsigned int*>(hist + w) = 0u;
+    int base = 0;  // coordinates that vanish whatever l is
+#pragma unroll
+    for (int e = 0; e < MPAD; ++e) {
+      if (e < prm.m) {
+        unsigned int sum = t0[(size_t)i * MPAD + e] + t1[(size_t)j * MPAD + e];  // p <= 2^31: no overflow
+        sum -= sum >= p ? p : 0u;
+        sum += t2[(size_t)e * c + k];
+        sum -= sum >= p ? p : 0u;
+        const unsigned int ni = ninv[e];
+        if (ni == InvTables::kEmpty) {
+          base += (sum == 0u);
+        } else {
+          const unsigned long long prod = (unsigned long long)sum * ni;
+          unsigned long long r = prod - __umul64hi(prod, ip.m64) * p;
+          r -= r >= p ? p : 0;
+          r -= r >= p ? p : 0;
+          const unsigned int x = (unsigned int)r;  // the value C_l must have
+          unsigned h = inv_hash(x, ip.hbits);
+          for (;;) {
+            const uint2 ent = htab[h];
+            if (ent.y == InvTables::kEmpty) break;
+            if (ent.x == x) {
+              for (unsigned l = ent.y; l != InvTables::kEmpty; l = nextdup[l]) ++hist[l];
+              break;
+            }
+            h = (h + 1) & (unsigned)(hsize - 1);
+          }
+        }
+      }
+    }
+    const int zc = prm.cl_const + zf[i] + zf[c + j] + zf[2 * c + k];
+    int best_rl1 = (int)(best >> 48);
+    for (int l0 = 0; l0 < c; l0 += 4) {
+      const unsigned int w = *reinterpret_cast<const unsigned int*>(hist + l0);
+      if (w == 0u && base + 1 < best_rl1) continue;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int l = l0 + t;
+        if (l >= c) break;
+        const int rl = base + (int)((w >> (8 * t)) & 0xFFu);
+        if (rl + 1 >= best_rl1) {
+          const int cl = zc + zf[3 * c + l];
+          const unsigned long long idx = q * (unsigned)c + (unsigned)l;
+          const unsigned long long key = pack_key(rl, cl, kIdxMask - 1ull - idx);
+          if (key > best && independent<true>(phi, nphi, coef, p, i, j, k, l)) {
+            best = key;
+            best_rl1 = rl + 1;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+    best = o > best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long v = threadIdx.x < (kLcThreads >> 5) ? red[threadIdx.x] : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
+      v = o > v ? o : v;
+    }
+    if (threadIdx.x == 0) atomicMax(prm.result + b, v);
+  }
+}
+
+static cudaError_t launch_lincomb_inv(int mpad, dim3 grid, size_t smem, cudaStream_t st, const LcParams<unsigned int>& prm, const LcInvParams& ip) {
+#define PLO_LI_CASE(MP)                                                                                       \
+  case MP: {                                                                                                  \
+    auto kern = lincomb_inv_kernel<MP>;                                                                       \
+    if (smem > 48 * 1024) {                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      if (e != cudaSuccess) return e;                                                                         \
+    }                                                                                                         \
+    kern<<<grid, kLcThreads, smem, st>>>(prm, ip);                                                            \
+    break;                                                                                                    \
+  }
+  switch (mpad) {
+    PLO_LI_CASE(8) PLO_LI_CASE(16) PLO_LI_CASE(32) PLO_LI_CASE(48) PLO_LI_CASE(64)
+    default: return cudaErrorInvalidValue;
+  }
+#undef PLO_LI_CASE
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
@@ -312,6 +447,10 @@ struct plo_lincomb_plan {
   unsigned int* d_counts;  // [nbatch][c^4] zero counts (big path)
   int tiles_per_group, tile_groups;
   int m_eff, rl_const;     // wide path: columns kept after dropping those that vanish on the live rows
+  bool use_inv;            // mod p, c >= 32: inverse-lookup kernel
+  unsigned int* d_inv;
+  int hbits;
+  size_t inv_smem;
 };
 
 namespace {
@@ -343,7 +482,7 @@ extern "C" {
 void plo_lincomb_plan_destroy(plo_lincomb_plan* pl) {
   if (!pl) return;
   pool_free(pl->d_tables); pool_free(pl->d_zflag); pool_free(pl->d_phi); pool_free(pl->d_nphi);
-  pool_free(pl->d_coef); pool_free(pl->d_seed); pool_free(pl->d_result); pool_free(pl->d_counts);
+  pool_free(pl->d_coef); pool_free(pl->d_seed); pool_free(pl->d_result); pool_free(pl->d_counts); pool_free(pl->d_inv);
   delete pl;
 }
 
@@ -409,6 +548,7 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
   plo_lincomb_plan* pl = new plo_lincomb_plan();
   pl->p = p; pl->nbatch = nbatch; pl->n = n; pl->m = m; pl->off = off; pl->c = c; pl->nprev = nprev; pl->mpad = mpad; pl->width = width;
   pl->big = big; pl->m_eff = m_eff; pl->rl_const = rl_const; pl->d_counts = nullptr; pl->tiles_per_group = 1; pl->tile_groups = 1;
+  pl->use_inv = false; pl->d_inv = nullptr; pl->hbits = 0; pl->inv_smem = 0;
   pl->d_tables = nullptr; pl->d_zflag = nullptr; pl->d_phi = nullptr; pl->d_nphi = nullptr; pl->d_coef = nullptr; pl->d_seed = nullptr; pl->d_result = nullptr;
   pl->h_init_rl.assign(init_rl ? init_rl : nullptr, init_rl ? init_rl + nbatch : nullptr);
   pl->h_init_cl.assign(init_cl ? init_cl : nullptr, init_cl ? init_cl + nbatch : nullptr);
@@ -494,6 +634,24 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
     if (pool_alloc(dst, bytes ? bytes : 1) != cudaSuccess) return false;
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
+  // inverse lookup: residues mod p <= 2^31, many coefficients, register-resident path
+  if (p && p <= 0x80000000u && !big && width == 4 && c >= (getenv("PLO_LINCOMB_INV_MINC") ? atoi(getenv("PLO_LINCOMB_INV_MINC")) : 32) &&
+      getenv("PLO_LINCOMB_NOINV") == nullptr) {
+    pl->hbits = inv_hash_bits(c);
+    const size_t words = InvTables::words(mpad, 1 << pl->hbits, c);
+    std::vector<uint32_t> inv((size_t)nbatch * words);
+    bool good = true;
+    for (int b = 0; b < nbatch && good; ++b)
+      good = build_inv_tables(p, m, mpad, c, pl->hbits, nact == 4 ? tm.data() + ((size_t)b * n + off + 3) * m : nullptr, cf.data() + (size_t)b * c,
+                              inv.data() + (size_t)b * words);
+    const int cpad = (c + 3) & ~3;
+    pl->inv_smem = words * 4 + (size_t)kLcThreads * (cpad + 4);
+    if (good && pl->inv_smem <= 200 * 1024 && up((void**)&pl->d_inv, inv.data(), inv.size() * 4)) {
+      pl->use_inv = true;
+      const unsigned long long blocks = (nprefix + kLcThreads - 1) / kLcThreads;
+      pl->grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(blocks, (unsigned long long)sms * 8ull));
+    }
+  }
   bool ok = up(&pl->d_tables, tables.data(), tables.size()) && up((void**)&pl->d_zflag, zflag.data(), zflag.size()) &&
             up((void**)&pl->d_phi, phi.data(), phi.size() * 8) && up((void**)&pl->d_nphi, nphi.data(), nphi.size() * 4) &&
             up((void**)&pl->d_coef, cf.data(), cf.size() * 8) && up((void**)&pl->d_seed, pl->h_seed.data(), pl->h_seed.size() * 8) &&
@@ -554,6 +712,11 @@ int plo_lincomb_plan_run_range(plo_lincomb_plan* pl, uint64_t prefix_lo, uint64_
       go(fill((uint64_t*)pl->d_tables), std::false_type());
     }
     e = cudaGetLastError();
+  } else if (pl->use_inv) {
+    auto prm = fill((uint32_t*)pl->d_tables);
+    LcInvParams ip;
+    ip.inv = pl->d_inv; ip.hbits = pl->hbits; ip.cpad = (pl->c + 3) & ~3; ip.m64 = ~0ull / pl->p;
+    e = launch_lincomb_inv(pl->mpad, grid, pl->inv_smem, st, prm, ip);
   } else if (pl->width == 4) {
     auto prm = fill((uint32_t*)pl->d_tables);
     e = pl->p ? launch_lincomb<uint32_t, true>(pl->mpad, grid, pl->smem, st, prm) : launch_lincomb<uint32_t, false>(pl->mpad, grid, pl->smem, st, prm);

@@ -396,3 +396,44 @@ def test_coefficient_count_limit(capi):
     assert sharding.lincomb_unkey(k) == (3, 1, last) and k > sharding.lincomb_key(3, 1, None)
     with pytest.raises(ValueError):
         sharding.lincomb_key(3, 1, 2 ** 36 - 1)
+
+
+def _c3_block(blk, c):
+    M = O.dense_fractions("4x4x4_48_rational_L")
+    TM = transpose([row[4 * blk:4 * blk + 4] for row in M])
+    tm = np.array([[(v.numerator % P31) * pow(v.denominator % P31, -1, P31) % P31 for v in row] for row in TM], dtype=np.int64)
+    return tm, O.coeffs(tm.tolist(), P31, c)[0].copy()
+
+
+@pytest.mark.parametrize("c", [32, 40, 64, 128])
+def test_inverse_lookup_kernel_equals_compare_kernel(capi, monkeypatch, c):
+    """mod p with c >= 32 the one-row search uses the inverse-lookup kernel (a hash probe per coordinate instead of c compares): same
+    (rl, cl, index) as the compare kernel (PLO_LINCOMB_NOINV=1) with and without previous rows and weight seeds, including the
+    value-duplicates of the coefficient list (Q3) and a truncated fourth position."""
+    for blk in (0, 3):
+        tm, cf = _c3_block(blk, c)
+        prev1 = np.array([[1, P31 - 1, 0, 2]], dtype=np.int64)
+        prev2 = np.array([[1, P31 - 1, 0, 2], [0, 1, 1, 0]], dtype=np.int64)
+        cases = [dict(), dict(prev_rows=prev1), dict(prev_rows=prev2), dict(init_rl=30, init_cl=1), dict(init_rl=47, init_cl=3)]
+        got = [capi.lincomb_search(P31, tm, 0, cf, **kw) for kw in cases]
+        got3 = capi.lincomb_search(P31, tm[:3], 0, cf)  # three live positions: the fourth coefficient is truncated (Q4)
+        monkeypatch.setenv("PLO_LINCOMB_NOINV", "1")
+        exp = [capi.lincomb_search(P31, tm, 0, cf, **kw) for kw in cases]
+        exp3 = capi.lincomb_search(P31, tm[:3], 0, cf)
+        monkeypatch.delenv("PLO_LINCOMB_NOINV")
+        assert got == exp and got3 == exp3, (c, blk, got, exp)
+    # a small prime: many coefficients coincide by value (c > p is not allowed; c = 32 < p = 37)
+    tm7 = np.array([[(v.numerator % 37) * pow(v.denominator % 37, -1, 37) % 37 for v in row] for row in transpose([r[:4] for r in O.dense_fractions("4x4x4_48_rational_L")])], dtype=np.int64)
+    cf7 = O.coeffs(tm7.tolist(), 37, 32)[0].copy()
+    a = capi.lincomb_search(37, tm7, 0, cf7)
+    monkeypatch.setenv("PLO_LINCOMB_NOINV", "1")
+    assert a == capi.lincomb_search(37, tm7, 0, cf7)
+
+
+def test_inverse_lookup_kernel_against_the_oracle(capi):
+    """One step at c = 33 against the oracle's literal testLinComb loop (1.2 million candidates on the CPU)."""
+    tm, cf = _c3_block(1, 33)
+    one = np.ones_like(tm)
+    z = np.zeros((4, 4), dtype=np.int64)
+    exp = O.lincomb_search(P31, tm, one, 0, 0, cf, np.ones_like(cf), z, np.ones_like(z))
+    assert capi.lincomb_search(P31, tm, 0, cf) == (exp[0], exp[1], None if exp[2] < 0 else exp[2])

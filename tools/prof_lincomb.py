@@ -19,7 +19,7 @@ tms, cfs = [], []
 for blk in range(4):
     TM = [[L[i][4 * blk + t] for i in range(len(L))] for t in range(4)]
     tm = np.array([[(v.numerator % P31) * pow(v.denominator % P31, -1, P31) % P31 for v in row] for row in TM], dtype=np.int64)
-    tms.append(tm); cfs.append(coeff_list(tm.tolist(), P31, 64))
+    tms.append(tm); cfs.append(coeff_list(tm.tolist(), P31, int(sys.argv[1]) if len(sys.argv) > 1 else 64))
 plan = capi.LincombPlan(P31, np.stack(tms), 0, np.stack(cfs))
 for _ in range(2):
     plan.run()
