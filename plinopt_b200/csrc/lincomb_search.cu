@@ -200,7 +200,10 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_inv_kernel(const LcParams<
     const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
     for (int w = 0; w < ip.cpad; w += 4) *reinterpret_cast<unsigned int*>(hist + w) = 0u;
     int base = 0;  // coordinates that vanish whatever l is
-#pragma unroll
+    // NOT fully unrolled: nothing is kept per coordinate, and 48 copies of the probe loop overflow the instruction cache
+    // (ncu: stall reason no_instruction 7.7 warps per issue with the unrolled body).  A register list of hits instead of the byte
+    // counters was tried and is slower: with Hopcroft-Musinski data hits are common (structured prefixes), not rare.
+#pragma unroll 2
     for (int e = 0; e < MPAD; ++e) {
       if (e < prm.m) {
         unsigned int sum = t0[(size_t)i * MPAD + e] + t1[(size_t)j * MPAD + e];  // p <= 2^31: no overflow
