@@ -34,6 +34,8 @@ struct QuadDesc {  // one problem; built on the host, read by every kernel
   unsigned long long seed_key;   // weight seed of the first row
   long long cmax;                // max |coef| (exact path: magnitude guard of the functionals)
   unsigned long long m64;        // floor((2^64 - 1) / p) for the Barrett reductions (p > 0)
+  unsigned long long inv_off;    // 32-bit word offset of this problem's inverse-lookup tables (mod p, c >= 32)
+  int hbits, pad2;
   long long phi0[16];            // annihilator functionals of the rows known before this call, on the live positions
   long long seedvec[4];          // the vector holding the seed weight, on the live positions (seed_mode == 1)
 };
@@ -143,6 +145,78 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_kernel(const QuadDesc* 
         }
         out[l] = (unsigned char)rl;
       }
+    }
+  }
+}
+
+// ---- the same counts by inverse lookup (mod p, many coefficients; lincomb_common.cuh "inverse lookup") ---------------------------
+// One hash probe per coordinate instead of c compares; the c byte counters of a prefix are built in shared memory and stored as words.
+template <int MPAD>
+__global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDesc* __restrict__ descs, const unsigned int* __restrict__ tables,
+                                                                    const unsigned int* __restrict__ invtabs, unsigned char* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const QuadDesc& d = descs[blockIdx.y];
+  const int c = d.c, hsize = 1 << d.hbits, cpad = (c + 3) & ~3;
+  const unsigned int p = d.p;
+  const unsigned nprefix = (unsigned)c * c * c;
+  if ((unsigned long long)blockIdx.x * kLcThreads >= nprefix) return;
+  unsigned int* ninv = reinterpret_cast<unsigned int*>(smem_raw);
+  uint2* htab = reinterpret_cast<uint2*>(ninv + MPAD);
+  unsigned int* nextdup = reinterpret_cast<unsigned int*>(htab + hsize);
+  unsigned char* hist = reinterpret_cast<unsigned char*>(nextdup + c) + (size_t)threadIdx.x * (cpad + 4);
+  {
+    const unsigned int* src = invtabs + d.inv_off;
+    const int nw = (int)InvTables::words(MPAD, hsize, c);
+    for (int e = threadIdx.x; e < nw; e += kLcThreads) ninv[e] = src[e];
+  }
+  __syncthreads();
+  const size_t tab = (size_t)c * MPAD;
+  const unsigned int* __restrict__ t0 = tables + d.tab_off;
+  const unsigned int* __restrict__ t1 = t0 + tab;
+  const unsigned int* __restrict__ t2 = t1 + tab;
+  unsigned char* __restrict__ cnt = counts + d.cnt_off;
+  const bool words_ok = (c & 3) == 0;
+  for (unsigned q = blockIdx.x * kLcThreads + threadIdx.x; q < nprefix; q += gridDim.x * kLcThreads) {
+    const int k = (int)(q % (unsigned)c);
+    const unsigned qq = q / (unsigned)c;
+    const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
+    for (int w = 0; w < cpad; w += 4) *reinterpret_cast<unsigned int*>(hist + w) = 0u;
+    unsigned base = 0;
+#pragma unroll 2
+    for (int e = 0; e < MPAD; ++e) {
+      if (e < d.m) {
+        unsigned int sum = t0[(size_t)i * MPAD + e] + t1[(size_t)j * MPAD + e];  // p <= 2^31: no overflow
+        sum -= sum >= p ? p : 0u;
+        sum += t2[(size_t)e * c + k];
+        sum -= sum >= p ? p : 0u;
+        const unsigned int ni = ninv[e];
+        if (ni == InvTables::kEmpty) {
+          base += (sum == 0u);
+        } else {
+          const unsigned long long prod = (unsigned long long)sum * ni;
+          unsigned long long r = prod - __umul64hi(prod, d.m64) * p;
+          r -= r >= p ? p : 0;
+          r -= r >= p ? p : 0;
+          const unsigned int x = (unsigned int)r;
+          unsigned h = inv_hash(x, d.hbits);
+          for (;;) {
+            const uint2 ent = htab[h];
+            if (ent.y == InvTables::kEmpty) break;
+            if (ent.x == x) {
+              for (unsigned l = ent.y; l != InvTables::kEmpty; l = nextdup[l]) ++hist[l];
+              break;
+            }
+            h = (h + 1) & (unsigned)(hsize - 1);
+          }
+        }
+      }
+    }
+    unsigned char* out = cnt + (size_t)q * c;
+    if (words_ok) {
+      const unsigned add = base * 0x01010101u;  // counts stay below 256: at most m <= 64 per candidate
+      for (int w = 0; w < c; w += 4) *reinterpret_cast<unsigned int*>(out + w) = *reinterpret_cast<const unsigned int*>(hist + w) + add;
+    } else {
+      for (int l = 0; l < c; ++l) out[l] = (unsigned char)(hist[l] + base);
     }
   }
 }
@@ -351,6 +425,38 @@ __global__ void __launch_bounds__(kPickThreads) quad_pick_kernel(const QuadDesc*
     if (cur > best) best = cur;
   }
   int best_rl1 = (int)(best >> 48);
+  if ((c & 3) == 0) {
+    // c a multiple of 4: a thread takes whole prefix rows (c bytes, word aligned) -- one index decode per c candidates, and four
+    // counters are rejected with ONE per-byte compare (VSETGE.U8x4) once a running best exists.  The scan is then memory-bound.
+    const unsigned nprefix = (unsigned)c * c * c;
+    const unsigned char* __restrict__ bytes = counts + d.cnt_off;
+    for (unsigned q = blockIdx.x * kPickThreads + threadIdx.x; q < nprefix; q += gridDim.x * kPickThreads) {
+      const int k = (int)(q % (unsigned)c);
+      const unsigned qq = q / (unsigned)c;
+      const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
+      const int zc = d.cl_const + zf[i] + zf[c + j] + zf[2 * c + k];
+      const unsigned int* __restrict__ row = reinterpret_cast<const unsigned int*>(bytes + (size_t)q * c);
+      for (int l0 = 0; l0 < c; l0 += 4) {
+        const unsigned int w = __ldg(row + (l0 >> 2));
+        const unsigned thr = (unsigned)(best_rl1 > 0 ? best_rl1 - 1 : 0) * 0x01010101u;
+        if (__vcmpgeu4(w, thr) == 0u) continue;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int rl = (int)((w >> (8 * t)) & 0xFFu);
+          if (rl + 1 >= best_rl1) {
+            const int l = l0 + t;
+            const int cl = zc + zf[3 * c + l];
+            const unsigned long long idx = (unsigned long long)q * (unsigned)c + (unsigned)l;
+            const unsigned long long key = pack_key(rl, cl, kIdxMask - 1ull - idx);
+            if (key > best && quad_independent<MODP>(sh_phi, nphi, coef, d.p, d.m64, i, j, k, l)) {
+              best = key;
+              best_rl1 = rl + 1;
+            }
+          }
+        }
+      }
+    }
+  } else
   for (unsigned long long g = (unsigned long long)blockIdx.x * kPickThreads + threadIdx.x; g < nchunks; g += (unsigned long long)gridDim.x * kPickThreads) {
     const uint4 v = cnt[g];
     const unsigned words[4] = {v.x, v.y, v.z, v.w};
@@ -652,6 +758,26 @@ static cudaError_t launch_quad_count(int mpad, dim3 grid, size_t smem, cudaStrea
   return cudaGetLastError();
 }
 
+static cudaError_t launch_quad_count_inv(int mpad, dim3 grid, size_t smem, cudaStream_t st, const QuadDesc* descs, const uint32_t* tables, const unsigned int* inv,
+                                         unsigned char* counts) {
+#define PLO_QI_CASE(MP)                                                                                       \
+  case MP: {                                                                                                  \
+    auto kern = quad_count_inv_kernel<MP>;                                                                    \
+    if (smem > 48 * 1024) {                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      if (e != cudaSuccess) return e;                                                                         \
+    }                                                                                                         \
+    kern<<<grid, kLcThreads, smem, st>>>(descs, tables, inv, counts);                                         \
+    break;                                                                                                    \
+  }
+  switch (mpad) {
+    PLO_QI_CASE(8) PLO_QI_CASE(16) PLO_QI_CASE(32) PLO_QI_CASE(48) PLO_QI_CASE(64)
+    default: return cudaErrorInvalidValue;
+  }
+#undef PLO_QI_CASE
+  return cudaGetLastError();
+}
+
 }  // namespace plo
 
 using namespace plo;
@@ -673,7 +799,8 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
   // ---- pass 1: validate, canonical copies, functionals, widths, sizes -----------------------------------------------------
   struct Prep { std::vector<int64_t> tm, cf; std::vector<long long> phi; int nphi = 0; bool none = false; int nact = 0, npick = 0; long long cmax = 0; bool has_init = false; int seed_mode = 0; long long seedvec[4] = {0, 0, 0, 0}; };
   std::vector<Prep> prep((size_t)nproblems);
-  int width = 4, cmaxall = 0;
+  int width = 4, cmaxall = 0, cminall = 1 << 30;
+  size_t inv_words = 0;
   size_t stage_i64 = 0, tab_elems = 0, cnt_bytes = 0, zf_bytes = 0;
   try {
     for (int b = 0; b < nproblems; ++b) {
@@ -719,6 +846,8 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
         P.cmax = (long long)mc;
       }
       if (c > cmaxall) cmaxall = c;
+      if (c < cminall) cminall = c;
+      inv_words += (InvTables::words(mpad, 1 << inv_hash_bits(c), c) + 3) / 4 * 4;
       stage_i64 += (size_t)4 * m + c;
       tab_elems += (size_t)4 * c * mpad;
       cnt_bytes += ((size_t)c * c * c * c + 15) / 16 * 16;
@@ -733,7 +862,11 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
   // ---- layout of the staging buffer: descs | int64 inputs ; device-only tail: zflags | results | status ------------------------
   const size_t desc_bytes = ((size_t)nproblems * sizeof(QuadDesc) + 15) / 16 * 16;
   const size_t in_bytes = (stage_i64 * 8 + 15) / 16 * 16;
-  const size_t h2d_bytes = desc_bytes + in_bytes;
+  // inverse-lookup count kernel: residues mod p <= 2^31, every problem with many coefficients, multi-kernel path
+  bool use_inv = p && p <= 0x80000000u && width == 4 && quad_small_smem(cmaxall, mpad, width) > 200 * 1024 &&
+                 cminall >= (getenv("PLO_LINCOMB_INV_MINC") ? atoi(getenv("PLO_LINCOMB_INV_MINC")) : 32) && getenv("PLO_LINCOMB_NOINV") == nullptr;
+  const size_t inv_bytes = use_inv ? inv_words * 4 : 0;
+  const size_t h2d_bytes = desc_bytes + in_bytes + inv_bytes;
   const size_t zf_off0 = h2d_bytes;
   const size_t res_off = zf_off0 + zf_bytes;
   const size_t status_off = res_off + (size_t)nproblems * 4 * 8;
@@ -750,7 +883,7 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
 
   QuadDesc* hd = reinterpret_cast<QuadDesc*>(Q.h_stage);
   long long* hin = reinterpret_cast<long long*>(Q.h_stage + desc_bytes);
-  size_t in_off = 0, tab_off = 0, cnt_off = 0, zf_off = 0;
+  size_t in_off = 0, tab_off = 0, cnt_off = 0, zf_off = 0, inv_off = 0, inv_smem = 0;
   const int max_rows = (int)(65536 / ((size_t)mpad * width));
   unsigned long long max_items = 1, max_chunks = 1, max_tab = 1;
   for (int b = 0; b < nproblems; ++b) {
@@ -765,6 +898,15 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
     d.seed_key = pack_key(q.init_rl, q.init_cl, kIdxMask);
     d.cmax = P.cmax;
     d.m64 = p ? ~0ull / p : 0;
+    if (use_inv) {
+      d.hbits = inv_hash_bits(q.c);
+      d.inv_off = inv_off;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(Q.h_stage + desc_bytes + in_bytes) + inv_off;
+      if (!build_inv_tables(p, m, mpad, q.c, d.hbits, P.nact == 4 ? P.tm.data() + (size_t)3 * m : nullptr, P.cf.data(), dst)) use_inv = false;
+      inv_off += (InvTables::words(mpad, 1 << d.hbits, q.c) + 3) / 4 * 4;
+      const size_t sm = InvTables::words(mpad, 1 << d.hbits, q.c) * 4 + (size_t)kLcThreads * (((q.c + 3) & ~3) + 4);
+      if (sm > inv_smem) inv_smem = sm;
+    }
     for (int t = 0; t < 16; ++t) d.phi0[t] = P.phi[t];
     for (int t = 0; t < 4; ++t) d.seedvec[t] = P.seedvec[t];
     // every SM busy even for small c: split the l range of a prefix across threads
@@ -817,6 +959,12 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
     const size_t smem = (size_t)ltile * mpad * width;
     const unsigned long long blocks = (max_items + kLcThreads - 1) / kLcThreads;
     const dim3 cg((unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(blocks, (unsigned long long)sms * 8ull)), nproblems);
+    if (use_inv && inv_smem <= 200 * 1024) {
+      const unsigned int* dinv = reinterpret_cast<const unsigned int*>(Q.d_stage + desc_bytes + in_bytes);
+      const unsigned long long pb = ((unsigned long long)cmaxall * cmaxall * cmaxall + kLcThreads - 1) / kLcThreads;
+      const dim3 ig((unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(pb, (unsigned long long)sms * 8ull)), nproblems);
+      e = launch_quad_count_inv(mpad, ig, inv_smem, st, dd, (const uint32_t*)Q.d_tables, dinv, Q.d_counts);
+    } else
     if (width == 4) e = p ? launch_quad_count<uint32_t, true>(mpad, cg, smem, st, dd, (const uint32_t*)Q.d_tables, Q.d_counts, max_rows)
                           : launch_quad_count<uint32_t, false>(mpad, cg, smem, st, dd, (const uint32_t*)Q.d_tables, Q.d_counts, max_rows);
     else e = launch_quad_count<uint64_t, false>(mpad, cg, smem, st, dd, (const uint64_t*)Q.d_tables, Q.d_counts, max_rows);

@@ -437,3 +437,21 @@ def test_inverse_lookup_kernel_against_the_oracle(capi):
     z = np.zeros((4, 4), dtype=np.int64)
     exp = O.lincomb_search(P31, tm, one, 0, 0, cf, np.ones_like(cf), z, np.ones_like(z))
     assert capi.lincomb_search(P31, tm, 0, cf) == (exp[0], exp[1], None if exp[2] < 0 else exp[2])
+
+
+@pytest.mark.parametrize("c", [36, 64])
+def test_quad_with_many_coefficients(capi, monkeypatch, c):
+    """c >= 32 mod p: the multi-kernel quad path counts by inverse lookup and picks row-wise; the four rows of two blocks in one call
+    equal four successive one-row searches, with and without the inverse-lookup kernels."""
+    probs = []
+    for blk in (0, 2):
+        tm, cf = _c3_block(blk, c)
+        probs.append(dict(TM=tm, off=0, coeffs=cf))
+    got = capi.lincomb_quad(P31, probs)
+    monkeypatch.setenv("PLO_LINCOMB_NOINV", "1")
+    plain = capi.lincomb_quad(P31, probs)
+    exp = [sequential_rows(capi, P31, pr["TM"], 0, pr["coeffs"], [], (-1, -1), None) for pr in probs]
+    monkeypatch.delenv("PLO_LINCOMB_NOINV")
+    assert got == plain
+    for (status, rows), e in zip(got, exp):
+        assert status == capi.QUAD_DONE and rows == e
