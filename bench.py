@@ -521,8 +521,11 @@ def bench_c3(ctx, steps, warmup, cpu_seconds):
                    "metric": METRIC, "value": value, "unit": "candidates/s", "scaling": "strong", "n_gpus": ctx.world, "steps": steps, "ms_per_step": ms / steps,
                    "candidates_per_step": cand, "gpu_launches": steps * launches, "best_per_block": merged.get("best"),
                    "roofline": {"bound": "int32 alu", "achieved": value / ctx.world * m / 1e12, "peak": pair_peak / 1e12, "unit": "T compare+add pairs/s per GPU",
-                                "frac": value / ctx.world * m / pair_peak, "traffic": None, "kernel": "lincomb_kernel<u32,48,modp>",
+                                "frac": value / ctx.world * m / pair_peak, "traffic": None, "kernel": "lincomb_inv_kernel<48> (c >= 32 mod p; lincomb_kernel<u32,48,modp> below)",
                                 "work_per_candidate": f"{m} compare+add pairs (the 4m MAC of the reference formulation are folded into the host-built product tables)",
+                                "note": "frac > 1 is not a measurement error: for c >= 32 mod p the kernel does not compare every (candidate, coordinate) pair -- per prefix and "
+                                        "coordinate ONE multiplication by -A3^-1 and one hash probe find the l that make the coordinate vanish (lincomb_inv_kernel), c-fold fewer "
+                                        "operations than the compare formulation the unit of work is taken from; results are identical (tests/test_gpu_lincomb.py)",
                                 "peak_source": "plo_measure_peaks ISETP+IADD pair peak, measured in this run"},
                    "e2e": quad},
                "pipeline_c11": None if pipe is None else {

@@ -28,7 +28,7 @@ struct QuadDesc {  // one problem; built on the host, read by every kernel
   int lsplit, npick;             // npick = rows this call decides = nact - (rows of this block already among the previous rows)
   unsigned int p, pad1;
   unsigned long long tab_off;    // element offset of t0 in the table region (t1, t2, t3 follow at + c*mpad each)
-  unsigned long long cnt_off;    // byte offset of the c^4 zero counts (16-byte aligned)
+  unsigned long long cnt_off;    // byte offset of the c^4 zero counts (16-byte aligned), followed by the c^3 per-prefix maxima
   unsigned long long in_off;     // int64 offset of [TM live rows: 4 x m | coef: c] in the staging buffer
   unsigned long long zf_off;     // byte offset of zflag[4][c]
   unsigned long long seed_key;   // weight seed of the first row
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_kernel(const QuadDesc* 
   const T* __restrict__ t2 = t1 + tab;
   const T* __restrict__ t3 = t2 + tab;
   unsigned char* __restrict__ cnt = counts + d.cnt_off;
+  unsigned char* __restrict__ rmax = cnt + ((size_t)c * c * c * c + 15) / 16 * 16;
   const T SENT = (T)(~(T)0) >> (MODP ? 0 : 1);
   const unsigned long long nitems = (unsigned long long)c * c * c * (unsigned)lsplit;
   const unsigned long long nthreads = (unsigned long long)gridDim.x * kLcThreads;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_kernel(const QuadDesc* 
         if (e >= d.m) nb[e] = SENT;
       }
       unsigned char* out = cnt + q * (unsigned)c;
+      int rowmax = 0;
       for (int l = la; l < lb; ++l) {
         const T* row = t3s + (size_t)(l - l0) * MPAD;
         int rl = 0;
@@ -144,7 +146,11 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_kernel(const QuadDesc* 
           }
         }
         out[l] = (unsigned char)rl;
+        rowmax = max(rowmax, rl);
       }
+      // largest count of the prefix row: lets the picks skip whole rows.  A row shared by several threads (l range split, or T3 in
+      // several tiles) gets the conservative 255.
+      if (lsplit == 1 && ltile >= c) rmax[q] = (unsigned char)rowmax; else if (s == 0 && l0 == 0) rmax[q] = 255;
     }
   }
 }
@@ -175,6 +181,7 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDe
   const unsigned int* __restrict__ t1 = t0 + tab;
   const unsigned int* __restrict__ t2 = t1 + tab;
   unsigned char* __restrict__ cnt = counts + d.cnt_off;
+  unsigned char* __restrict__ rmax = cnt + ((size_t)c * c * c * c + 15) / 16 * 16;
   const bool words_ok = (c & 3) == 0;
   for (unsigned q = blockIdx.x * kLcThreads + threadIdx.x; q < nprefix; q += gridDim.x * kLcThreads) {
     const int k = (int)(q % (unsigned)c);
@@ -212,12 +219,19 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDe
       }
     }
     unsigned char* out = cnt + (size_t)q * c;
+    unsigned mx = 0;  // per-byte maximum of the hit counters
     if (words_ok) {
       const unsigned add = base * 0x01010101u;  // counts stay below 256: at most m <= 64 per candidate
-      for (int w = 0; w < c; w += 4) *reinterpret_cast<unsigned int*>(out + w) = *reinterpret_cast<const unsigned int*>(hist + w) + add;
+      for (int w = 0; w < c; w += 4) {
+        const unsigned hw = *reinterpret_cast<const unsigned int*>(hist + w);
+        mx = __vmaxu4(mx, hw);
+        *reinterpret_cast<unsigned int*>(out + w) = hw + add;
+      }
     } else {
-      for (int l = 0; l < c; ++l) out[l] = (unsigned char)(hist[l] + base);
+      for (int l = 0; l < c; ++l) { mx = max(mx, (unsigned)hist[l]); out[l] = (unsigned char)(hist[l] + base); }
     }
+    mx = max(max(mx & 0xFFu, (mx >> 8) & 0xFFu), max((mx >> 16) & 0xFFu, mx >> 24));
+    rmax[q] = (unsigned char)(base + mx);  // largest count of the prefix row: lets the picks skip whole rows
   }
 }
 
@@ -425,59 +439,52 @@ __global__ void __launch_bounds__(kPickThreads) quad_pick_kernel(const QuadDesc*
     if (cur > best) best = cur;
   }
   int best_rl1 = (int)(best >> 48);
-  if ((c & 3) == 0) {
-    // c a multiple of 4: a thread takes whole prefix rows (c bytes, word aligned) -- one index decode per c candidates, and four
-    // counters are rejected with ONE per-byte compare (VSETGE.U8x4) once a running best exists.  The scan is then memory-bound.
+  {
+    // A thread takes whole prefix rows (c bytes): one index decode per c candidates and a running best that has seen whole rows.
+    // The count kernels left the largest count of every row beside the counts (c^3 bytes): a row that cannot reach the best count
+    // known to the BLOCK is skipped without being read, so after the first rows a pick reads c^3 bytes instead of c^4.
+    // (Tried: reading everything -- thread per row, lane per word of a shared row, rows staged through shared memory: 1.1-1.9 ms
+    // per pick at c = 128, latency-bound at ~1 TB/s with the few warps this register-heavy kernel keeps resident.)
+    __shared__ int sh_best_rl1;
+    if (threadIdx.x == 0) sh_best_rl1 = best_rl1;
+    __syncthreads();
     const unsigned nprefix = (unsigned)c * c * c;
     const unsigned char* __restrict__ bytes = counts + d.cnt_off;
+    const unsigned char* __restrict__ rmax = bytes + (N4 + 15) / 16 * 16;
+    const bool words_ok = (c & 3) == 0;
     for (unsigned q = blockIdx.x * kPickThreads + threadIdx.x; q < nprefix; q += gridDim.x * kPickThreads) {
+      const int floor_rl1 = max(best_rl1, *reinterpret_cast<volatile int*>(&sh_best_rl1));
+      if ((int)rmax[q] + 1 < floor_rl1) continue;
       const int k = (int)(q % (unsigned)c);
       const unsigned qq = q / (unsigned)c;
       const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
       const int zc = d.cl_const + zf[i] + zf[c + j] + zf[2 * c + k];
-      const unsigned int* __restrict__ row = reinterpret_cast<const unsigned int*>(bytes + (size_t)q * c);
+      const unsigned char* row = bytes + (size_t)q * c;
       for (int l0 = 0; l0 < c; l0 += 4) {
-        const unsigned int w = __ldg(row + (l0 >> 2));
-        const unsigned thr = (unsigned)(best_rl1 > 0 ? best_rl1 - 1 : 0) * 0x01010101u;
+        unsigned int w;
+        if (words_ok) w = __ldg(reinterpret_cast<const unsigned int*>(row + l0));
+        else {
+          w = 0;
+          for (int t = 0; t < 4 && l0 + t < c; ++t) w |= (unsigned)row[l0 + t] << (8 * t);
+        }
+        const unsigned thr = (unsigned)(floor_rl1 > 0 ? floor_rl1 - 1 : 0) * 0x01010101u;
         if (__vcmpgeu4(w, thr) == 0u) continue;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
+          const int l = l0 + t;
           const int rl = (int)((w >> (8 * t)) & 0xFFu);
-          if (rl + 1 >= best_rl1) {
-            const int l = l0 + t;
+          if (l < c && rl + 1 >= best_rl1) {
             const int cl = zc + zf[3 * c + l];
             const unsigned long long idx = (unsigned long long)q * (unsigned)c + (unsigned)l;
             const unsigned long long key = pack_key(rl, cl, kIdxMask - 1ull - idx);
             if (key > best && quad_independent<MODP>(sh_phi, nphi, coef, d.p, d.m64, i, j, k, l)) {
               best = key;
               best_rl1 = rl + 1;
+              atomicMax(&sh_best_rl1, best_rl1);
             }
           }
         }
       }
-    }
-  } else
-  for (unsigned long long g = (unsigned long long)blockIdx.x * kPickThreads + threadIdx.x; g < nchunks; g += (unsigned long long)gridDim.x * kPickThreads) {
-    const uint4 v = cnt[g];
-    const unsigned words[4] = {v.x, v.y, v.z, v.w};
-    unsigned long long idx = g * 16ull;
-    unsigned long long t = idx;
-    int l = (int)(t % (unsigned)c); t /= (unsigned)c;
-    int k = (int)(t % (unsigned)c); t /= (unsigned)c;
-    int j = (int)(t % (unsigned)c);
-    int i = (int)(t / (unsigned)c);
-#pragma unroll 4
-    for (int e = 0; e < 16; ++e, ++idx) {
-      const int rl = (int)((words[e >> 2] >> (8 * (e & 3))) & 0xFFu);
-      if (idx < N4 && rl + 1 >= best_rl1) {
-        const int cl = d.cl_const + zf[i] + zf[c + j] + zf[2 * c + k] + zf[3 * c + l];
-        const unsigned long long key = pack_key(rl, cl, kIdxMask - 1ull - idx);
-        if (key > best && quad_independent<MODP>(sh_phi, nphi, coef, d.p, d.m64, i, j, k, l)) {
-          best = key;
-          best_rl1 = rl + 1;
-        }
-      }
-      if (++l == c) { l = 0; if (++k == c) { k = 0; if (++j == c) { j = 0; ++i; } } }
     }
   }
 #pragma unroll
@@ -850,7 +857,7 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
       inv_words += (InvTables::words(mpad, 1 << inv_hash_bits(c), c) + 3) / 4 * 4;
       stage_i64 += (size_t)4 * m + c;
       tab_elems += (size_t)4 * c * mpad;
-      cnt_bytes += ((size_t)c * c * c * c + 15) / 16 * 16;
+      cnt_bytes += ((size_t)c * c * c * c + 15) / 16 * 16 + ((size_t)c * c * c + 15) / 16 * 16;
       zf_bytes += ((size_t)4 * c + 15) / 16 * 16;
     }
   } catch (const plo::host::RangeError& e) {
@@ -919,7 +926,7 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
     memcpy(hin + in_off + (size_t)4 * m, P.cf.data(), (size_t)q.c * 8);
     in_off += (size_t)4 * m + q.c;
     tab_off += (size_t)4 * q.c * mpad;
-    cnt_off += ((size_t)q.c * q.c * q.c * q.c + 15) / 16 * 16;
+    cnt_off += ((size_t)q.c * q.c * q.c * q.c + 15) / 16 * 16 + ((size_t)q.c * q.c * q.c + 15) / 16 * 16;
     zf_off += ((size_t)4 * q.c + 15) / 16 * 16;
     max_items = std::max(max_items, nprefix * lsplit);
     max_chunks = std::max(max_chunks, (nprefix * q.c + 15) / 16);
