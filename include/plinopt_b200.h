@@ -272,6 +272,12 @@ int plo_mmcheck_plan_run(plo_mmcheck_plan* plan, uint64_t seed, uint64_t first_s
 int plo_mmcheck_plan_result(plo_mmcheck_plan* plan, void* stream, uint8_t* ok, int* verdict);
 int plo_mmcheck_plan_launches(const plo_mmcheck_plan* plan);
 void plo_mmcheck_plan_destroy(plo_mmcheck_plan* plan);
+/* Host-only check (no device needed) of the matrix encoder behind the plans: encodes A the way plan_create does for `groups`
+ * sample groups (column block sums, row block sums when row_blocks != 0 -- plans use them for P only --, plain pairs and value
+ * groups; see csrc/mmcheck.cu), replays the encoded stream on the CPU for ONE sample and returns y = A.x mod p (x: cols residues,
+ * y: rows).  stats (may be NULL, 8 values): row stride of the row blocks (0: none), column stride of the column blocks (0: none),
+ * chunks, blob bytes, plain entries, units of 4 grouped entries, value groups, X loads per sample after encoding. */
+int plo_mmcheck_encode_check(uint32_t p, const plo_csr* A, int groups, int row_blocks, const uint32_t* x, uint32_t* y, long long* stats);
 
 /* ---------------------------------------------------------------------------
  * Factorizer random restarts  (SURVEY.md section 8 row f2).

@@ -11,17 +11,32 @@
 // product needs for one sample group and one slab of 1024 columns is ONE
 // contiguous 128 KB block: it is brought into shared memory by TMA bulk copies
 // (cp.async.bulk + mbarrier) and stays there while the CTA streams matrix rows
-// against it.  The matrix itself is pre-cut on the host into self-contained
-// "chunk blobs" (row offsets + (column byte offset, value) pairs of a run of
-// rows inside one slab, ~equal non-zero counts); a producer warp streams the
-// blobs through a 4-stage shared-memory ring with bulk copies, 16 consumer
-// warps take rows from the current blob through a shared counter (rows are
-// 16..1024 entries long) and do, per entry, one broadcast LDS.128 per two
-// entries + one LDS + one IMAD.WIDE.U32 with carry-out (+ half an IADD3.X):
-// exact 96-bit accumulation, one Barrett reduction mod p per output.
-// Bound: shared-memory bandwidth (one 128 B wavefront per multiply-add per
-// warp) -- DESIGN.md section 5.3.
+// against it.  The matrix is pre-cut on the host into self-contained "chunk
+// blobs" (row descriptors + row streams of a run of rows inside one slab,
+// about equal cost); a producer warp streams the blobs through a 4-stage
+// shared-memory ring with bulk copies, consumer warps take rows from the
+// current blob through a shared counter.  Lane = sample, so a load of X is one
+// conflict-free 128 B wavefront; exact 96-bit accumulation, one Barrett
+// reduction mod p per output.
+//
+// What makes it fast on Hopcroft-Musinski matrices is done by the ENCODER
+// (host, once per plan; results identical to the plain CSR product, checked by
+// plo_mmcheck_encode_check on the CPU and by the parity tests on the device):
+//  * column block sums: next to the 1024 columns the slab holds the sums of X
+//    over aligned blocks of 4 and of 16 columns (computed by the CTA when the
+//    slab lands).  A row whose block mostly carries one value v takes v times
+//    the block sum and corrects the other columns of the block; L and R of
+//    32x32x32_15096 shrink from 83 to about 10 loads per row.
+//  * row block sums (the transposed trick, for P): entries that most rows of a
+//    block of 4 or 16 rows {base + t * stride} share become entries of a
+//    VIRTUAL row, computed once; mm_verify adds the virtual rows back.
+//  * what is left of a row: plain (column, value) pairs, or -- for a value
+//    that still occurs often in the row -- an add-only group (exact 64-bit
+//    sum of X words, one multiply-add per group).
+// Bound: shared-memory bandwidth (one wavefront per X word per warp, plus the
+// stream at 8 B per wavefront) and issue slots -- DESIGN.md section 5.3.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "plo_device.cuh"
@@ -29,25 +44,30 @@
 namespace plo {
 
 constexpr int kSlabCols = 1024;                         // columns of X resident per CTA
-constexpr int kSlabBytes = kSlabCols * 32 * 4;          // 128 KB
+constexpr int kBlk4 = kSlabCols / 4, kBlk16 = kSlabCols / 16;
+constexpr int kVCols = kSlabCols + kBlk4 + kBlk16;      // + block sums: 1344 virtual columns
+constexpr int kSlabBytes = kVCols * 32 * 4;             // 168 KB
 constexpr int kStages = 4;                              // blob ring depth
-constexpr int kChunkEnt = 2560;                         // max padded entries per blob
-constexpr int kChunkRows = 255;                         // max rows per blob
-constexpr int kHdrBytes = (kChunkRows + 1) * 4;         // 1 KB of row offsets
-constexpr int kStageBytes = kHdrBytes + kChunkEnt * 8;  // 21.5 KB
-constexpr int kConsumerWarps = 24;
+constexpr int kChunkEnt = 1536;                         // max 8-byte stream words per blob
+constexpr int kChunkRows = 192;                         // max rows per blob
+constexpr int kHdrBytes = kChunkRows * 8;               // row descriptors
+constexpr int kStageBytes = kHdrBytes + kChunkEnt * 8;  // 13.5 KB
+constexpr int kConsumerWarps = 28;
 constexpr int kSpThreads = (kConsumerWarps + 1) * 32;   // + one producer warp
-constexpr int kZeroColBytes = 128;                      // slab column 1024: 32 zero words (padding target of the grouped format)
-constexpr int kRingBase = kSlabBytes + kZeroColBytes;
+constexpr int kRingBase = kSlabBytes;
 constexpr int kSpSmem = kRingBase + kStages * kStageBytes;
-constexpr int kGroupedMinAvg = 6;                       // value-grouped format when a (row, value) group averages >= this many entries
+constexpr int kMinGroup = 8;                            // a (row, value) group with fewer entries is stored as plain (column, value) pairs
 
 struct ChunkDesc {
-  int slab, row0, nrows, bytes;  // blob = [nrows+1 offsets, padded to 16 B][stream]; stream = (colbyte, val) pairs (plain format)
-                                 // or, per (row, value) group, {val, nwords} + nwords x 4 columns, two per 32-bit word (grouped format)
+  int slab, row0, nrows, bytes;  // blob = [nrows row descriptors, padded to 16 B][row streams] (format: see mm_slab_spmm_kernel)
   unsigned long long off;        // byte offset of the blob
   unsigned long long pad_;
 };
+
+// Block sums: a block of `lv` (4 or 16) columns of a slab = {hi * lv * cs + t * cs + lo : t < lv} for a column stride cs (a power
+// of two, lv * cs <= 1024); block number hi * cs + lo.  Row blocks (virtual rows) use the same numbering on the whole row index.
+__host__ __device__ __forceinline__ int blk_id(int c, int lv, int cs) { return (c / (lv * cs)) * cs + c % cs; }
+__host__ __device__ __forceinline__ int blk_member(int b, int t, int lv, int cs) { return (b / cs) * (lv * cs) + t * cs + b % cs; }
 
 struct Acc96 {
   unsigned int a0, a1, a2;
@@ -145,36 +165,41 @@ __global__ void mm_transpose_kernel(unsigned int p, int batch, int len, const un
 
 struct SpmmArgs {
   unsigned int p;
-  unsigned long long M;  // floor((2^64-1)/p)
-  int rows, xlen, groups, nchunks;
+  unsigned long long M;   // floor((2^64-1)/p)
+  unsigned int c32, c64;  // 2^32 mod p, 2^64 mod p  (one-step reduction when p < 2^31)
+  int rows, xlen, groups, nchunks;  // rows: real + virtual rows of the matrix
+  int cstride;                      // column stride of the block sums, 0: the matrix uses none
   const ChunkDesc* chunk;
   const unsigned char* blob;
   const unsigned int* X;    // [groups][xlen][32]
   unsigned int* out;        // [nslabs][groups][rows][32]
-  const unsigned int* mul;  // optional [groups][rows][32]: out = (A X) o mul  (fused Hadamard step, single-slab matrices)
+  const unsigned int* mul;  // [groups][rows][32] when HAD: out = (A X) o mul  (fused Hadamard step, single-slab matrices)
 };
 
+// 64-bit sum += x: written as a wide multiply-add by an opaque 1; ptxas fuses two of them into one three-input add with two
+// carry-outs (IADD3 + IADD3.X on the integer pipe): one instruction per entry, exact for any 32-bit residues.
 __device__ __forceinline__ void addwide(unsigned long long& s, unsigned int x, unsigned int one) {
-  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s) : "r"(x), "r"(one));  // 64-bit accumulate on the fma pipe
+  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s) : "r"(x), "r"(one));
 }
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, unsigned int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
 
-// Grouped format: a 32-bit word packs two slab columns, one in bits [10:0], one in bits [31:21].
-// Shared-memory address of this lane's X word = column * 128 + xl:
-//   low field : (w & 0x7ff) * 128 + xl            (LOP3 + IMAD)
-//   high field: hi32(w * 2^18) + xl = (w >> 14) + xl, clean because bits [20:11] of w are zero  (one IMAD.HI)
-__device__ __forceinline__ uint32_t col_lo_addr(unsigned int w, uint32_t xl) {
-  uint32_t t, a;
-  asm volatile("and.b32 %0, %1, 0x7ff;" : "=r"(t) : "r"(w));
-  asm volatile("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(t), "r"(xl));
-  return a;
-}
-__device__ __forceinline__ uint32_t col_hi_addr(unsigned int w, uint32_t xl) {
-  uint32_t a;
-  asm volatile("mad.hi.u32 %0, %1, 262144, %2;" : "=r"(a) : "r"(w), "r"(xl));
-  return a;
-}
-
-template <bool GROUPED>
+// Row descriptor (8 B): {start | np << 16, ng}; row stream, offsets in 8-byte words from `start`, every area 16-byte aligned:
+//   [np plain pairs (byte offset of the virtual column = 128 * column, value); np even, padding = (0, 0)]
+//   [ng group headers (value, nunits), padded to an even count]
+//   [units: 4 byte offsets each, all groups in order; a group is padded with the plain pairs' help, never inside a unit]
+// Virtual columns of a slab: 0..1023 the columns, 1024 + b the sum over block b of 4 columns, 1280 + b over block b of 16.
+template <bool P31, bool HAD>
 __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full[kStages], empty[kStages], slabbar;
@@ -183,7 +208,6 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
   const long long T = (long long)a.groups * a.nchunks;
   const long long i0 = (long long)blockIdx.x * T / gridDim.x, i1 = (long long)(blockIdx.x + 1) * T / gridDim.x;
   const int nitems = (int)(i1 - i0);
-  if (tid < 32) reinterpret_cast<unsigned int*>(smem + kSlabBytes)[tid] = 0u;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
     mbar_init(&slabbar, 1);
@@ -191,12 +215,11 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
   }
   __syncthreads();
   int pg = -1, ps = -1;
+  int g = (int)(i0 / a.nchunks), c = (int)(i0 - (long long)g * a.nchunks);
   if (warp == kConsumerWarps) {
     // ---- producer: one thread feeds the slab and the blob ring ----
     if (lane != 0) return;
     for (int k = 0; k < nitems; ++k) {
-      const long long i = i0 + k;
-      const int g = (int)(i / a.nchunks), c = (int)(i - (long long)g * a.nchunks);
       const ChunkDesc ch = a.chunk[c];
       const int stage = k & (kStages - 1);
       if (g != pg || ch.slab != ps) {
@@ -216,87 +239,109 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&full[stage], (unsigned)ch.bytes);
       bulk_g2s(smem + kRingBase + stage * kStageBytes, a.blob + ch.off, (unsigned)ch.bytes, &full[stage]);
+      if (++c == a.nchunks) { c = 0; ++g; }
     }
     return;
   }
   // ---- consumers: lane = sample of the group, warp takes rows of the current blob ----
   const uint32_t xl = smem_u32(smem) + lane * 4;  // this lane's word of slab column 0
+  const uint32_t ring = smem_u32(smem) + kRingBase;
+  const uint32_t cnt0 = smem_u32(&cnt[0]);
   unsigned int one;
   asm volatile("mov.u32 %0, 1;" : "=r"(one));
   unsigned slabphase = 0;
   for (int k = 0; k < nitems; ++k) {
-    const long long i = i0 + k;
-    const int g = (int)(i / a.nchunks), c = (int)(i - (long long)g * a.nchunks);
     const int4 ch = *reinterpret_cast<const int4*>(a.chunk + c);  // slab, row0, nrows, bytes
     const int stage = k & (kStages - 1);
-    if (g != pg || ch.x != ps) { mbar_wait(&slabbar, slabphase); slabphase ^= 1; pg = g; ps = ch.x; }
+    if (g != pg || ch.x != ps) {
+      mbar_wait(&slabbar, slabphase);
+      slabphase ^= 1; pg = g; ps = ch.x;
+      if (a.cstride) {
+        // block sums of the new slab: X4[b] = sum of 4 columns, X16[b] = sum of the 4 blocks of 4 it consists of (mod p)
+        const int cs = a.cstride;
+        for (int b = warp; b < kBlk4; b += kConsumerWarps) {
+          unsigned long long s = 0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) s += lds_u32(xl + blk_member(b, t, 4, cs) * 128);
+          sts_u32(xl + (kSlabCols + b) * 128, barrett64(s, a.p, a.M));
+        }
+        consumer_sync();
+        for (int b = warp; b < kBlk16; b += kConsumerWarps) {
+          // block b of 16 (stride cs) = the blocks of 4 with stride 4 cs ... whose members are its members: t = 4 u + v  ->  blocks of 4 numbered by (hi, v, lo)
+          unsigned long long s = 0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) s += lds_u32(xl + (kSlabCols + blk_id(blk_member(b, 4 * u, 16, cs), 4, cs)) * 128);
+          sts_u32(xl + (kSlabCols + kBlk4 + b) * 128, barrett64(s, a.p, a.M));
+        }
+        consumer_sync();
+      }
+    }
     mbar_wait(&full[stage], (k / kStages) & 1);
-    const unsigned char* sb = smem + kRingBase + stage * kStageBytes;
-    const unsigned int* hdr = reinterpret_cast<const unsigned int*>(sb);
-    const uint4* ent = reinterpret_cast<const uint4*>(sb + (((ch.z + 1) * 4 + 15) & ~15));
-    const size_t obase = (((size_t)ch.x * a.groups + g) * a.rows + ch.y) * 32 + lane;
-    unsigned int* outp = a.out + obase;
-    const unsigned int* mulp = a.mul ? a.mul + obase : nullptr;
+    const uint32_t hdr = ring + stage * kStageBytes;
+    const uint32_t st = hdr + ((ch.z * 8 + 15) & ~15);
+    const uint32_t cn = cnt0 + stage * 4;
+    unsigned int* outp = a.out + (((size_t)ch.x * a.groups + g) * a.rows + ch.y) * 32 + lane;
+    const unsigned int* mulp = HAD ? a.mul + ((size_t)g * a.rows + ch.y) * 32 + lane : nullptr;
     int cur = 0;
-    if (lane == 0) cur = atomicAdd(&cnt[stage], 1);
+    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(cur) : "r"(cn) : "memory");
     cur = __shfl_sync(0xffffffffu, cur, 0);
     while (cur < ch.z) {
       int nxt = 0;
-      if (lane == 0) nxt = atomicAdd(&cnt[stage], 1);
-      const unsigned o0 = hdr[cur], o1 = hdr[cur + 1];
+      if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(nxt) : "r"(cn) : "memory");
+      const uint2 rd = lds_u64(hdr + cur * 8);
+      unsigned int mulv = 0;
+      if (HAD) mulv = __ldg(mulp + (size_t)cur * 32);  // issued now, needed in the epilogue
+      const unsigned np = rd.x >> 16, ng = rd.y;
+      uint32_t pa = st + (rd.x & 0xffffu) * 8;
       Acc96 A, B;
       A.a0 = A.a1 = A.a2 = 0;
       B.a0 = B.a1 = B.a2 = 0;
-      if (GROUPED) {
-        // stream of 8-byte words: {val, nwords} then nwords words of 4 columns; out += val * sum_cols X[col]
-        const uint2* st = reinterpret_cast<const uint2*>(ent);
-        unsigned w = o0;
-        while (w < o1) {
-          const uint2 h = st[w];
-          const uint2* cw = st + w + 1;
+      for (const uint32_t pe = pa + np * 8; pa != pe; pa += 16) {
+        const uint4 q = lds_u128(pa);
+        const unsigned x0 = lds_u32(xl + q.x);
+        const unsigned x1 = lds_u32(xl + q.z);
+        mac96(A, q.y, x0);
+        mac96(B, q.w, x1);
+      }
+      add96(A, B);
+      if (ng) {
+        uint32_t un = pa + ((ng + 1) & ~1u) * 8;
+        for (const uint32_t ge = pa + ng * 8; pa != ge; pa += 8) {
+          const uint2 h = lds_u64(pa);
           unsigned long long s0 = 0, s1 = 0;
 #pragma unroll 2
           for (unsigned j = 0; j < h.y; ++j) {
-            const uint2 c = cw[j];
-            const unsigned x0 = lds_u32(col_lo_addr(c.x, xl));
-            const unsigned x1 = lds_u32(col_hi_addr(c.x, xl));
-            const unsigned x2 = lds_u32(col_lo_addr(c.y, xl));
-            const unsigned x3 = lds_u32(col_hi_addr(c.y, xl));
+            const uint4 cw = lds_u128(un + j * 16);
+            const unsigned x0 = lds_u32(xl + cw.x);
+            const unsigned x1 = lds_u32(xl + cw.y);
+            const unsigned x2 = lds_u32(xl + cw.z);
+            const unsigned x3 = lds_u32(xl + cw.w);
             addwide(s0, x0, one);
             addwide(s1, x1, one);
             addwide(s0, x2, one);
             addwide(s1, x3, one);
           }
-          s0 += s1;  // < 2^45: at most 2^13 terms below 2^32
-          mac96(A, h.x, (unsigned)s0);
-          asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(B.a1), "+r"(B.a2) : "r"(h.x), "r"((unsigned)(s0 >> 32)));
-          w += h.y + 1;
-        }
-        B.a0 = 0;
-      } else {
-        const uint4* e = ent + (o0 >> 1);
-        const int n = (int)((o1 - o0) >> 1);  // uint4 = 2 entries; rows are padded to 4 entries
-#pragma unroll 2
-        for (int t = 0; t < n; t += 2) {
-          const uint4 q0 = e[t], q1 = e[t + 1];
-          const unsigned x0 = lds_u32(xl + q0.x);
-          const unsigned x1 = lds_u32(xl + q0.z);
-          const unsigned x2 = lds_u32(xl + q1.x);
-          const unsigned x3 = lds_u32(xl + q1.z);
-          mac96(A, q0.y, x0);
-          mac96(B, q0.w, x1);
-          mac96(A, q1.y, x2);
-          mac96(B, q1.w, x3);
+          un += h.y * 16;
+          const unsigned long long s = s0 + s1;  // < 2^45
+          mac96(A, h.x, (unsigned)s);
+          asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(A.a1), "+r"(A.a2) : "r"(h.x), "r"((unsigned)(s >> 32)));
         }
       }
-      add96(A, B);
-      unsigned int res = reduce96(A, a.p, a.M);
-      if (mulp) res = barrett64((unsigned long long)res * mulp[(size_t)cur * 32], a.p, a.M);
+      unsigned int res;
+      if (P31) {
+        // p < 2^31 and a2 < 2^15: a2 c64 + a1 c32 + a0 < 2^46 + 2^63 + 2^32 fits 64 bits -> one Barrett step
+        const unsigned long long x = (unsigned long long)A.a2 * a.c64 + (unsigned long long)A.a1 * a.c32 + A.a0;
+        res = barrett64(x, a.p, a.M);
+      } else {
+        res = reduce96(A, a.p, a.M);
+      }
+      if (HAD) res = barrett64((unsigned long long)res * mulv, a.p, a.M);
       outp[(size_t)cur * 32] = res;
       cur = __shfl_sync(0xffffffffu, nxt, 0);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
+    if (++c == a.nchunks) { c = 0; ++g; }
   }
 }
 
@@ -311,8 +356,22 @@ __global__ void mm_hadamard_kernel(unsigned int p, unsigned long long M, size_t 
   vc[e] = barrett64((unsigned long long)barrett64(x, p, M) * barrett64(y, p, M), p, M);
 }
 
-// bad[b] |= (sum_parts wc[g][o][lane] != sum_t ua[g][i*k+t][lane] * ub[g][t*n+j][lane])  for o = i*n + j, b = 32 g + lane
-__global__ void mm_verify_kernel(unsigned int p, unsigned long long M, int m, int k, int n, int batch, int groups, int parts,
+// Virtual rows of a matrix with `rows` real rows and row stride rs (0: none): rows + b for the blocks of 4 rows, rows + n4 + b
+// for the blocks of 16 (only blocks that lie inside the matrix exist).
+struct RowBlocks {
+  int rows, rs, n4, n16;
+  __host__ __device__ int total() const { return rows + n4 + n16; }
+};
+__host__ __device__ __forceinline__ RowBlocks row_blocks(int rows, int rs) {
+  RowBlocks rb;
+  rb.rows = rows; rb.rs = rs;
+  rb.n4 = rs ? (rows / (4 * rs)) * rs : 0;
+  rb.n16 = rs ? (rows / (16 * rs)) * rs : 0;
+  return rb;
+}
+
+// bad[b] |= (sum_parts wc[g][o][lane] + its virtual rows != sum_t ua[g][i*k+t][lane] * ub[g][t*n+j][lane])  for o = i*n + j, b = 32 g + lane
+__global__ void mm_verify_kernel(unsigned int p, unsigned long long M, int m, int k, int n, int batch, int groups, int parts, RowBlocks rb,
                                  const unsigned int* __restrict__ wc, const unsigned int* __restrict__ ua, const unsigned int* __restrict__ ub,
                                  unsigned int* __restrict__ bad) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -322,8 +381,16 @@ __global__ void mm_verify_kernel(unsigned int p, unsigned long long M, int m, in
   const int o = (int)((e >> 5) % mn), g = (int)((e >> 5) / mn), i = o / n, j = o % n;
   const int b = g * 32 + lane;
   if (b >= batch) return;
+  const int tot = rb.total();
+  const int v4 = rb.rs && o / (4 * rb.rs) * rb.rs < rb.n4 ? rb.rows + blk_id(o, 4, rb.rs) : -1;
+  const int v16 = rb.rs && o / (16 * rb.rs) * rb.rs < rb.n16 ? rb.rows + rb.n4 + blk_id(o, 16, rb.rs) : -1;
   unsigned long long w = 0;
-  for (int q = 0; q < parts; ++q) w += wc[(size_t)q * groups * mn * 32 + e];
+  for (int q = 0; q < parts; ++q) {
+    const unsigned int* base = wc + ((size_t)q * groups + g) * tot * 32 + lane;
+    w += base[(size_t)o * 32];
+    if (v4 >= 0) w += base[(size_t)v4 * 32];
+    if (v16 >= 0) w += base[(size_t)v16 * 32];
+  }
   Acc96 acc;
   acc.a0 = acc.a1 = acc.a2 = 0;
   const unsigned int* pa = ua + ((size_t)g * m * k + (size_t)i * k) * 32 + lane;
@@ -339,8 +406,9 @@ using namespace plo;
 // Device form of one sparse matrix: chunk blobs + chunk table (see the header comment).
 struct DevSlabCsr {
   int rows, cols, nslabs, nchunks;
-  bool grouped;
-  long long nnz;
+  int cstride;   // column stride of the block sums the rows refer to (0: none)
+  RowBlocks rb;  // virtual rows (rb.rs = 0: none)
+  long long nnz, loads;  // entries of the CSR / X loads per sample after encoding
   ChunkDesc* chunk;
   unsigned char* blob;
 };
@@ -362,116 +430,347 @@ static bool csr_valid(const plo_csr* c, uint32_t p) {
   return true;
 }
 
-// Cuts the CSR into slabs of kSlabCols columns and, inside a slab, into runs of rows of about equal
-// cost; serialises every run as a blob and uploads blobs + table.  Format: value-grouped when the
-// matrix has few distinct values per row (HM matrices do: 25-31 distinct values in 32x32x32_15096),
-// plain (column, value) pairs otherwise.
-static int build_slab_csr(const plo_csr* h, int groups, DevSlabCsr* d) {
-  d->rows = h->rows; d->cols = h->cols; d->nnz = h->ptr[h->rows];
-  d->nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
-  d->chunk = nullptr; d->blob = nullptr; d->nchunks = 0; d->grouped = false;
-  const int rows = h->rows, nslabs = d->nslabs;
-  // entries bucketed by (slab, row), each bucket sorted by (value, column)
-  std::vector<long long> start((size_t)nslabs * rows + 1, 0);
-  for (int i = 0; i < rows; ++i)
-    for (long long t = h->ptr[i]; t < h->ptr[i + 1]; ++t) ++start[(size_t)(h->col[t] / kSlabCols) * rows + i + 1];
-  for (size_t q = 1; q < start.size(); ++q) start[q] += start[q - 1];
-  std::vector<uint2> sorted((size_t)d->nnz);  // (local column, value)
-  {
-    std::vector<long long> fill(start.begin(), start.end() - 1);
-    for (int i = 0; i < rows; ++i)
-      for (long long t = h->ptr[i]; t < h->ptr[i + 1]; ++t) {
-        const int s = h->col[t] / kSlabCols;
-        sorted[(size_t)fill[(size_t)s * rows + i]++] = make_uint2((unsigned)(h->col[t] - s * kSlabCols), h->val[t]);
-      }
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; }
+
+namespace {
+struct Ent { unsigned col, val; };  // slab-local (virtual) column, residue
+typedef std::vector<Ent> Row;
+inline bool by_col(const Ent& x, const Ent& y) { return x.col < y.col; }
+inline bool by_val_col(const Ent& x, const Ent& y) { return x.val != y.val ? x.val < y.val : x.col < y.col; }
+inline unsigned sub_mod(unsigned a, unsigned v, unsigned p) { return a >= v ? a - v : a + (p - v); }
+
+// The value most members of a block carry and what replacing them by one block entry saves:
+// gain = (members with that value) - 1 (the block entry) - (members without an entry, which get a correction).
+struct Mode { unsigned val; int gain; };
+inline Mode block_mode(const unsigned* val, const bool* has, int lv) {
+  Mode best{0, -1000};
+  int present = 0;
+  for (int t = 0; t < lv; ++t) present += has[t];
+  for (int t = 0; t < lv; ++t) {
+    if (!has[t]) continue;
+    int cnt = 0;
+    for (int u = 0; u < lv; ++u) cnt += has[u] && val[u] == val[t];
+    const int gain = cnt - 1 - (lv - present);
+    if (gain > best.gain) { best.gain = gain; best.val = val[t]; }
   }
-  long long ngroups = 0;
-  for (size_t q = 0; q + 1 < start.size(); ++q) {
-    std::sort(sorted.begin() + start[q], sorted.begin() + start[q + 1], [](const uint2& x, const uint2& y) { return x.y != y.y ? x.y < y.y : x.x < y.x; });
-    for (long long t = start[q]; t < start[q + 1]; ++t) ngroups += (t == start[q] || sorted[(size_t)t].y != sorted[(size_t)t - 1].y);
+  return best;
+}
+
+// Column block sums of one row inside one slab (levels 16, then 4; stride cs): dense scratch over the 1024 columns.
+struct ColScratch {
+  std::vector<unsigned> val;
+  std::vector<unsigned char> has;
+  ColScratch() : val(kSlabCols), has(kSlabCols) {}
+};
+void col_blocks(Row& row, int ncols, int cs, unsigned p, ColScratch& w, bool apply, long long* gain_out) {
+  std::fill(w.has.begin(), w.has.end(), 0);
+  Row extra;
+  for (const Ent& e : row) {
+    if (e.col < (unsigned)kSlabCols) { w.val[e.col] = e.val; w.has[e.col] = 1; }
+    else extra.push_back(e);
   }
-  const bool grouped = ngroups > 0 && d->nnz >= (long long)kGroupedMinAvg * ngroups;
-  d->grouped = grouped;
-  // per bucket: stream length in 8-byte words and cost in multiply-add slots
-  std::vector<unsigned> words(start.size() - 1), cost(start.size() - 1);
-  long long total_cost = 0;
-  for (size_t q = 0; q + 1 < start.size(); ++q) {
-    long long w = 0, c = 0;
-    if (grouped) {
-      long long t = start[q];
-      while (t < start[q + 1]) {
-        long long u = t;
-        while (u < start[q + 1] && sorted[(size_t)u].y == sorted[(size_t)t].y) ++u;
-        const long long nw = (u - t + 3) / 4;
-        w += 1 + nw; c += 4 * nw + 4;
-        t = u;
+  long long gain = 0;
+  const int levels[2] = {16, 4};
+  for (int li = 0; li < 2; ++li) {
+    const int lv = levels[li], nb = kSlabCols / lv;
+    for (int b = 0; b < nb; ++b) {
+      unsigned v[16];
+      bool h[16];
+      int any = 0, last = 0;
+      for (int t = 0; t < lv; ++t) { const int c = blk_member(b, t, lv, cs); v[t] = w.val[c]; h[t] = w.has[c]; any += h[t]; last = c; }
+      if (any < 2 || last >= ncols) continue;  // the last member is the largest column: the block must lie inside the slab's columns
+      const Mode m = block_mode(v, h, lv);
+      if (m.gain < 1) continue;
+      gain += m.gain;
+      if (!apply) continue;
+      extra.push_back(Ent{(unsigned)(kSlabCols + (lv == 4 ? 0 : kBlk4) + b), m.val});
+      for (int t = 0; t < lv; ++t) {
+        const int c = blk_member(b, t, lv, cs);
+        const unsigned nv = sub_mod(h[t] ? v[t] : 0u, m.val, p);
+        w.val[c] = nv; w.has[c] = nv != 0;
       }
-    } else {
-      w = (start[q + 1] - start[q] + 3) & ~3ll; c = w;
     }
-    if (w > kChunkEnt - 1) { set_error("mmcheck: a row has too many entries inside one %d-column slab (duplicate columns?)", kSlabCols); return PLO_E_ARG; }
-    words[q] = (unsigned)w; cost[q] = (unsigned)c; total_cost += c;
   }
-  long long target = total_cost * groups / ((long long)sm_count() * 16);
-  if (target < 64) target = 64;
-  if (target > 4 * kChunkEnt) target = 4 * kChunkEnt;
+  if (gain_out) *gain_out += gain;
+  if (!apply) return;
+  row.clear();
+  for (int c = 0; c < kSlabCols; ++c) if (w.has[c]) row.push_back(Ent{(unsigned)c, w.val[c]});
+  row.insert(row.end(), extra.begin(), extra.end());
+}
+
+// Row block sums inside one slab: the rows {blk_member(b, t, lv, rs)} of block b; entries most of them share move to `vrow`.
+void row_block(std::vector<Row>& rows, int b, int lv, int rs, unsigned p, Row* vrow, bool apply, long long* gain_out) {
+  struct T { unsigned col, val; int t; };
+  std::vector<T> all;
+  for (int t = 0; t < lv; ++t) for (const Ent& e : rows[(size_t)blk_member(b, t, lv, rs)]) all.push_back(T{e.col, e.val, t});
+  std::sort(all.begin(), all.end(), [](const T& x, const T& y) { return x.col != y.col ? x.col < y.col : x.t < y.t; });
+  std::vector<Row> fresh(apply ? (size_t)lv : 0);
+  long long gain = 0;
+  for (size_t i = 0; i < all.size();) {
+    size_t j = i;
+    unsigned v[16] = {};
+    bool h[16] = {};
+    while (j < all.size() && all[j].col == all[i].col) { v[all[j].t] = all[j].val; h[all[j].t] = true; ++j; }
+    const Mode m = j - i >= 2 ? block_mode(v, h, lv) : Mode{0, -1};
+    if (m.gain >= 1) {
+      gain += m.gain;
+      if (apply) {
+        vrow->push_back(Ent{all[i].col, m.val});
+        for (int t = 0; t < lv; ++t) { const unsigned nv = sub_mod(h[t] ? v[t] : 0u, m.val, p); if (nv) fresh[(size_t)t].push_back(Ent{all[i].col, nv}); }
+      }
+    } else if (apply) {
+      for (int t = 0; t < lv; ++t) if (h[t]) fresh[(size_t)t].push_back(Ent{all[i].col, v[t]});
+    }
+    i = j;
+  }
+  if (gain_out) *gain_out += gain;
+  if (apply) for (int t = 0; t < lv; ++t) rows[(size_t)blk_member(b, t, lv, rs)].swap(fresh[(size_t)t]);
+}
+
+// Serialised form of one row (see the kernel).
+struct RowStream {
+  std::vector<uint2> plain, heads;
+  std::vector<uint4> units;
+  unsigned words() const { return (unsigned)(((plain.size() + 1) & ~(size_t)1) + ((heads.size() + 1) & ~(size_t)1) + 2 * units.size()); }
+  unsigned cost() const { return (unsigned)(24 + 3 * plain.size() + 6 * heads.size() + 5 * units.size()); }
+  unsigned loads() const { return (unsigned)(plain.size() + 4 * units.size()); }
+};
+void encode_row(Row& row, int ming, RowStream* out) {
+  std::sort(row.begin(), row.end(), by_val_col);
+  for (size_t t = 0; t < row.size();) {
+    size_t u = t;
+    while (u < row.size() && row[u].val == row[t].val) ++u;
+    size_t n = u - t;
+    if ((long long)n >= ming) {
+      const size_t nu = n / 4;  // whole units; the up to 3 entries left over become plain pairs
+      out->heads.push_back(make_uint2(row[t].val, (unsigned)nu));
+      for (size_t z = 0; z < nu; ++z) out->units.push_back(make_uint4(row[t + 4 * z].col * 128u, row[t + 4 * z + 1].col * 128u, row[t + 4 * z + 2].col * 128u, row[t + 4 * z + 3].col * 128u));
+      t += 4 * nu;
+    }
+    for (; t < u; ++t) out->plain.push_back(make_uint2(row[t].col * 128u, row[t].val));
+  }
+}
+unsigned write_row(const RowStream& rs, uint2* stream, unsigned o, uint2* desc) {
+  const unsigned np = (unsigned)((rs.plain.size() + 1) & ~(size_t)1), ng = (unsigned)rs.heads.size();
+  uint2* w = stream + o;
+  for (size_t z = 0; z < rs.plain.size(); ++z) w[z] = rs.plain[z];  // padding stays (0, 0): slab column 0 times zero
+  w += np;
+  for (size_t z = 0; z < rs.heads.size(); ++z) w[z] = rs.heads[z];
+  w += (ng + 1) & ~1u;
+  for (size_t z = 0; z < rs.units.size(); ++z) reinterpret_cast<uint4*>(w)[z] = rs.units[z];
+  *desc = make_uint2(o | (np << 16), ng);
+  return rs.words();
+}
+
+struct Encoded {
   std::vector<ChunkDesc> table;
   std::vector<unsigned char> blob;
-  for (int s = 0; s < nslabs; ++s) {
-    int row = 0;
-    while (row < rows) {
-      int nrows = 0;
-      long long w = 0, c = 0;
-      while (row + nrows < rows && nrows < kChunkRows) {
-        const size_t q = (size_t)s * rows + row + nrows;
-        if (nrows > 0 && (c + cost[q] > target || w + words[q] > kChunkEnt - 1)) break;
-        w += words[q]; c += cost[q]; ++nrows;
+  int cstride = 0;
+  RowBlocks rb{};
+  long long loads = 0, plain = 0, units = 0, heads = 0;
+};
+}  // namespace
+
+// Cuts the CSR into slabs of kSlabCols columns, rewrites the rows of every slab with row and column block sums where that saves
+// loads (see the header comment), cuts every slab into runs of rows of about equal cost and serialises every run as a blob.
+static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bool allow_row_blocks, Encoded* out) {
+  const int rows = h->rows, nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
+  static const int ming = std::max(2, env_int("PLO_MM_MINGROUP", kMinGroup));
+  static const int env_cb = env_int("PLO_MM_COLBLOCKS", -1);  // 0: no column block sums; 2^k: force that stride; default: choose
+  static const int env_rb = env_int("PLO_MM_ROWBLOCKS", -1);  // same for the row block sums
+  // rows of every slab, sorted by column
+  std::vector<std::vector<Row>> slab((size_t)nslabs, std::vector<Row>((size_t)rows));
+  for (int i = 0; i < rows; ++i)
+    for (long long t = h->ptr[i]; t < h->ptr[i + 1]; ++t) {
+      if (h->val[t] == 0) continue;
+      slab[(size_t)(h->col[t] / kSlabCols)][(size_t)i].push_back(Ent{(unsigned)(h->col[t] % kSlabCols), h->val[t]});
+    }
+  long long nnz = 0;
+  for (auto& s : slab)
+    for (Row& r : s) {
+      std::sort(r.begin(), r.end(), by_col);
+      // duplicates of a column add up (a CSR may hold them): merge them here
+      size_t o = 0;
+      for (size_t t = 0; t < r.size(); ++t) {
+        if (o && r[o - 1].col == r[t].col) r[o - 1].val = (unsigned)(((unsigned long long)r[o - 1].val + r[t].val) % p);
+        else r[o++] = r[t];
       }
-      const size_t hdr = (((size_t)nrows + 1) * 4 + 15) & ~(size_t)15;
-      ChunkDesc ch;
-      ch.slab = s; ch.row0 = row; ch.nrows = nrows; ch.bytes = (int)((hdr + (size_t)w * 8 + 15) & ~(size_t)15);  // bulk copies move multiples of 16 B
-      ch.off = blob.size(); ch.pad_ = 0;
-      blob.resize(blob.size() + (size_t)ch.bytes, 0);
-      unsigned int* ho = reinterpret_cast<unsigned int*>(blob.data() + ch.off);
-      uint2* eo = reinterpret_cast<uint2*>(blob.data() + ch.off + hdr);
-      unsigned o = 0;
-      for (int qq = 0; qq < nrows; ++qq) {
-        ho[qq] = o;
-        const size_t q = (size_t)s * rows + row + qq;
-        if (grouped) {
-          long long t = start[q];
-          while (t < start[q + 1]) {
-            long long u = t;
-            while (u < start[q + 1] && sorted[(size_t)u].y == sorted[(size_t)t].y) ++u;
-            const unsigned nw = (unsigned)((u - t + 3) / 4);
-            eo[o++] = make_uint2(sorted[(size_t)t].y, nw);
-            for (unsigned j = 0; j < nw; ++j) {
-              unsigned c4[4];
-              for (int z = 0; z < 4; ++z) c4[z] = t + 4 * j + z < u ? sorted[(size_t)(t + 4 * j + z)].x : (unsigned)kSlabCols;  // padding -> zero column
-              eo[o++] = make_uint2(c4[0] | (c4[1] << 21), c4[2] | (c4[3] << 21));
-            }
-            t = u;
-          }
-        } else {
-          for (long long t = start[q]; t < start[q + 1]; ++t) eo[o++] = make_uint2(sorted[(size_t)t].x * 128u, sorted[(size_t)t].y);
-          while (o & 3) eo[o++] = make_uint2(0u, 0u);  // padding: 0 * X[slab column 0]
+      r.resize(o);
+      r.erase(std::remove_if(r.begin(), r.end(), [](const Ent& e) { return e.val == 0; }), r.end());
+      nnz += (long long)r.size();
+    }
+  // ---- row block sums: stride chosen on a sample of blocks of 4 ----
+  int rs = 0;
+  if (allow_row_blocks && env_rb != 0 && rows >= 8) {
+    double best = 0;
+    for (int cand = 1; 4 * cand <= rows; cand <<= 1) {
+      if (env_rb > 0 && cand != env_rb) continue;
+      const int nb = (rows / (4 * cand)) * cand, step = std::max(1, nb / 64);
+      long long gain = 0, ent = 0;
+      for (int s = 0; s < nslabs; s += std::max(1, nslabs / 4))
+        for (int b = 0; b < nb; b += step) {
+          for (int t = 0; t < 4; ++t) ent += (long long)slab[(size_t)s][(size_t)blk_member(b, t, 4, cand)].size();
+          row_block(slab[(size_t)s], b, 4, cand, p, nullptr, false, &gain);
         }
+      const double frac = ent ? (double)gain / (double)ent : 0.0;
+      if (frac > best) { best = frac; rs = cand; }
+    }
+    if (env_rb < 0 && best < 0.2) rs = 0;  // worth it from 20 % of the entries on
+  }
+  const RowBlocks rb = row_blocks(rows, rs);
+  out->rb = rb;
+  if (rs)
+    for (auto& s : slab) {
+      s.resize((size_t)rb.total());
+      for (int b = 0; b < rb.n16; ++b) row_block(s, b, 16, rs, p, &s[(size_t)(rows + rb.n4 + b)], true, nullptr);
+      for (int b = 0; b < rb.n4; ++b) row_block(s, b, 4, rs, p, &s[(size_t)(rows + b)], true, nullptr);
+    }
+  // ---- column block sums: stride chosen on a sample of rows ----
+  ColScratch scratch;
+  int cs = 0;
+  if (env_cb != 0) {
+    long long best = 0, seen = 0;
+    const int step = std::max(1, rb.total() / 128);
+    for (int s = 0; s < nslabs; s += std::max(1, nslabs / 4)) for (int i = 0; i < rb.total(); i += step) seen += (long long)slab[(size_t)s][(size_t)i].size();
+    for (int cand = 1; 16 * cand <= kSlabCols; cand <<= 1) {
+      if (env_cb > 0 && cand != env_cb) continue;
+      long long gain = 0;
+      for (int s = 0; s < nslabs; s += std::max(1, nslabs / 4)) {
+        const int ncols = std::min(kSlabCols, h->cols - s * kSlabCols);
+        for (int i = 0; i < rb.total(); i += step) col_blocks(slab[(size_t)s][(size_t)i], ncols, cand, p, scratch, false, &gain);
       }
-      ho[nrows] = o;
-      table.push_back(ch);
-      row += nrows;
+      if (gain > best) { best = gain; cs = cand; }
+    }
+    if (env_cb < 0 && 10 * best < seen) cs = 0;  // worth the block sums from 10 % of the entries on
+  }
+  out->cstride = cs;
+  // ---- row streams, chunks ----
+  std::vector<RowStream> streams((size_t)rb.total());
+  for (int s = 0; s < nslabs; ++s) {
+    const int ncols = std::min(kSlabCols, h->cols - s * kSlabCols);
+    long long total_cost = 0;
+    for (int i = 0; i < rb.total(); ++i) {
+      Row& r = slab[(size_t)s][(size_t)i];
+      if (cs) col_blocks(r, ncols, cs, p, scratch, true, nullptr);
+      RowStream& st = streams[(size_t)i];
+      st = RowStream();
+      encode_row(r, ming, &st);
+      if (st.words() > (unsigned)kChunkEnt) { set_error("mmcheck: a row has too many entries inside one %d-column slab", kSlabCols); return PLO_E_ARG; }
+      total_cost += st.cost();
+      out->loads += st.loads(); out->plain += (long long)st.plain.size(); out->units += (long long)st.units.size(); out->heads += (long long)st.heads.size();
+    }
+    long long target = total_cost * nslabs * groups / ((long long)nsm * 16);
+    if (target < 512) target = 512;
+    int row = 0;
+    while (row < rb.total()) {
+      int n = 0;
+      long long w = 0, c = 0;
+      while (row + n < rb.total() && n < kChunkRows) {
+        const RowStream& st = streams[(size_t)(row + n)];
+        if (n > 0 && (c + st.cost() > target || w + st.words() > (unsigned)kChunkEnt)) break;
+        w += st.words(); c += st.cost(); ++n;
+      }
+      const size_t hdr = ((size_t)n * 8 + 15) & ~(size_t)15;
+      ChunkDesc ch;
+      ch.slab = s; ch.row0 = row; ch.nrows = n; ch.bytes = (int)(hdr + (size_t)w * 8);  // every area is a multiple of 16 B (bulk copies)
+      ch.off = out->blob.size(); ch.pad_ = 0;
+      out->blob.resize(out->blob.size() + (size_t)ch.bytes, 0);
+      uint2* ho = reinterpret_cast<uint2*>(out->blob.data() + ch.off);
+      uint2* eo = reinterpret_cast<uint2*>(out->blob.data() + ch.off + hdr);
+      unsigned o = 0;
+      for (int z = 0; z < n; ++z) o += write_row(streams[(size_t)(row + z)], eo, o, ho + z);
+      out->table.push_back(ch);
+      row += n;
     }
   }
-  d->nchunks = (int)table.size();
-  PLO_CUDA(pool_alloc(&d->chunk, sizeof(ChunkDesc) * table.size()));
-  PLO_CUDA(pool_alloc(&d->blob, blob.size() ? blob.size() : 16));
-  PLO_CUDA(cudaMemcpy(d->chunk, table.data(), sizeof(ChunkDesc) * table.size(), cudaMemcpyHostToDevice));
-  PLO_CUDA(cudaMemcpy(d->blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  (void)nnz;
   return PLO_OK;
 }
+
+static int build_slab_csr(const plo_csr* h, unsigned p, int groups, bool allow_row_blocks, DevSlabCsr* d) {
+  d->rows = h->rows; d->cols = h->cols; d->nnz = h->ptr[h->rows];
+  d->nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
+  d->chunk = nullptr; d->blob = nullptr; d->nchunks = 0;
+  Encoded enc;
+  const int rc = encode_slab_csr(h, p, groups, sm_count(), allow_row_blocks, &enc);
+  if (rc) return rc;
+  d->cstride = enc.cstride; d->rb = enc.rb; d->loads = enc.loads;
+  d->nchunks = (int)enc.table.size();
+  PLO_CUDA(pool_alloc(&d->chunk, sizeof(ChunkDesc) * enc.table.size()));
+  PLO_CUDA(pool_alloc(&d->blob, enc.blob.size() ? enc.blob.size() : 16));
+  PLO_CUDA(cudaMemcpy(d->chunk, enc.table.data(), sizeof(ChunkDesc) * enc.table.size(), cudaMemcpyHostToDevice));
+  PLO_CUDA(cudaMemcpy(d->blob, enc.blob.data(), enc.blob.size(), cudaMemcpyHostToDevice));
+  return PLO_OK;
+}
+
+// Host twin of the consumer side of mm_slab_spmm_kernel + the fold of mm_verify_kernel for ONE sample: y = A x mod p from the
+// encoded blobs.  Used by the CPU tests to check the encoder without a device; `stats` = {row stride, column stride, chunks,
+// blob bytes, plain entries, units, value groups, X loads per sample}.
+static int decode_check(const plo_csr* h, uint32_t p, int groups, int allow_row_blocks, const uint32_t* x, uint32_t* y, long long* stats) {
+  Encoded enc;
+  const int rc = encode_slab_csr(h, p, groups, 148, allow_row_blocks != 0, &enc);
+  if (rc) return rc;
+  const RowBlocks rb = enc.rb;
+  const int nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
+  std::vector<unsigned long long> ext((size_t)nslabs * rb.total(), 0);
+  std::vector<unsigned long long> xs((size_t)kVCols);
+  int cur_slab = -1;
+  for (const ChunkDesc& ch : enc.table) {
+    if ((size_t)ch.nrows * 8 > (size_t)kHdrBytes || ch.bytes > kStageBytes || (ch.bytes & 15)) { set_error("mmcheck encoder: malformed blob"); return PLO_E_ARG; }
+    if (ch.slab != cur_slab) {
+      cur_slab = ch.slab;
+      const int ncols = std::min(kSlabCols, h->cols - ch.slab * kSlabCols);
+      for (int c = 0; c < kSlabCols; ++c) xs[(size_t)c] = c < ncols ? x[(size_t)ch.slab * kSlabCols + c] : 0xdeadbeefull;  // never referenced
+      if (enc.cstride) {
+        for (int b = 0; b < kBlk4; ++b) { unsigned long long s = 0; for (int t = 0; t < 4; ++t) s += xs[(size_t)blk_member(b, t, 4, enc.cstride)]; xs[(size_t)(kSlabCols + b)] = s % p; }
+        for (int b = 0; b < kBlk16; ++b) { unsigned long long s = 0; for (int u = 0; u < 4; ++u) s += xs[(size_t)(kSlabCols + blk_id(blk_member(b, 4 * u, 16, enc.cstride), 4, enc.cstride))]; xs[(size_t)(kSlabCols + kBlk4 + b)] = s % p; }
+      }
+    }
+    const uint2* hdr = reinterpret_cast<const uint2*>(enc.blob.data() + ch.off);
+    const uint2* st = reinterpret_cast<const uint2*>(enc.blob.data() + ch.off + (((size_t)ch.nrows * 8 + 15) & ~(size_t)15));
+    for (int t = 0; t < ch.nrows; ++t) {
+      const unsigned start = hdr[t].x & 0xffffu, np = hdr[t].x >> 16, ng = hdr[t].y;
+      unsigned __int128 A = 0;
+      auto ld = [&](unsigned off) -> unsigned long long { return (off & 127u) || off / 128u >= (unsigned)kVCols ? ~0ull : xs[off / 128u]; };
+      for (unsigned z = 0; z < np; ++z) A += (unsigned __int128)st[start + z].y * ld(st[start + z].x);
+      const uint2* gh = st + start + np;
+      const uint4* un = reinterpret_cast<const uint4*>(gh + ((ng + 1) & ~1u));
+      for (unsigned gi = 0; gi < ng; ++gi) {
+        unsigned long long s = 0;
+        for (unsigned j = 0; j < gh[gi].y; ++j) s += ld(un[j].x) + ld(un[j].y) + ld(un[j].z) + ld(un[j].w);
+        un += gh[gi].y;
+        A += (unsigned __int128)gh[gi].x * s;
+      }
+      ext[(size_t)ch.slab * rb.total() + ch.row0 + t] = (unsigned long long)(A % p);
+    }
+  }
+  for (int o = 0; o < h->rows; ++o) {
+    const int v4 = rb.rs && o / (4 * rb.rs) * rb.rs < rb.n4 ? rb.rows + blk_id(o, 4, rb.rs) : -1;
+    const int v16 = rb.rs && o / (16 * rb.rs) * rb.rs < rb.n16 ? rb.rows + rb.n4 + blk_id(o, 16, rb.rs) : -1;
+    unsigned long long w = 0;
+    for (int s = 0; s < nslabs; ++s) {
+      const unsigned long long* base = ext.data() + (size_t)s * rb.total();
+      w += base[o];
+      if (v4 >= 0) w += base[v4];
+      if (v16 >= 0) w += base[v16];
+    }
+    y[o] = (uint32_t)(w % p);
+  }
+  if (stats) {
+    const long long st_[8] = {rb.rs, enc.cstride, (long long)enc.table.size(), (long long)enc.blob.size(), enc.plain, enc.units, enc.heads, enc.loads};
+    for (int z = 0; z < 8; ++z) stats[z] = st_[z];
+  }
+  return PLO_OK;
+}
+
 static void free_slab_csr(DevSlabCsr* d) { pool_free(d->chunk); pool_free(d->blob); }
 
 extern "C" {
+
+int plo_mmcheck_encode_check(uint32_t p, const plo_csr* A, int groups, int row_blocks, const uint32_t* x, uint32_t* y, long long* stats) {
+  if (p < 2 || !csr_valid(A, p) || groups < 1 || !x || !y) { set_error("plo_mmcheck_encode_check: bad argument"); return PLO_E_ARG; }
+  return decode_check(A, p, groups, row_blocks, x, y, stats);
+}
 
 void plo_mmcheck_plan_destroy(plo_mmcheck_plan* pl) {
   if (!pl) return;
@@ -490,22 +789,24 @@ int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, i
   if (L->cols != m * k || R->cols != k * n || P->rows != m * n) { set_error("mmcheck: outer dimension mismatch"); return 3; }  // library.inl:487-495
   int rc = check_device();
   if (rc) return rc;
-  PLO_CUDA(cudaFuncSetAttribute(mm_slab_spmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
-  PLO_CUDA(cudaFuncSetAttribute(mm_slab_spmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
+  PLO_CUDA(cudaFuncSetAttribute(mm_slab_spmm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
+  PLO_CUDA(cudaFuncSetAttribute(mm_slab_spmm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
+  PLO_CUDA(cudaFuncSetAttribute(mm_slab_spmm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
+  PLO_CUDA(cudaFuncSetAttribute(mm_slab_spmm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
   plo_mmcheck_plan* pl = new plo_mmcheck_plan();
   memset(pl, 0, sizeof(*pl));
   pl->p = p; pl->M = ~0ull / p; pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->batch = batch;
   pl->groups = (batch + 31) / 32;
   pl->grid_cap = sm_count();
-  rc = build_slab_csr(L, pl->groups, &pl->L);
-  if (!rc) rc = build_slab_csr(R, pl->groups, &pl->R);
-  if (!rc) rc = build_slab_csr(P, pl->groups, &pl->P);
+  rc = build_slab_csr(L, p, pl->groups, false, &pl->L);
+  if (!rc) rc = build_slab_csr(R, p, pl->groups, false, &pl->R);
+  if (!rc) rc = build_slab_csr(P, p, pl->groups, true, &pl->P);  // only mm_verify folds virtual rows
   if (rc) { plo_mmcheck_plan_destroy(pl); return rc; }
   const size_t G32 = (size_t)pl->groups * 32;
   const size_t stage = (size_t)batch * (size_t)(m * k > k * n ? m * k : k * n);
   auto zalloc = [](unsigned int** ptr, size_t words) { return pool_alloc(ptr, 4 * words) == cudaSuccess && cudaMemset(*ptr, 0, 4 * words) == cudaSuccess; };
   const bool ok = zalloc(&pl->ua, G32 * m * k) && zalloc(&pl->ub, G32 * k * n) && zalloc(&pl->va, G32 * r * pl->L.nslabs) &&
-                  zalloc(&pl->vb, G32 * r * pl->R.nslabs) && zalloc(&pl->vc, G32 * r) && zalloc(&pl->wc, G32 * m * n * pl->P.nslabs) &&
+                  zalloc(&pl->vb, G32 * r * pl->R.nslabs) && zalloc(&pl->vc, G32 * r) && zalloc(&pl->wc, G32 * pl->P.rb.total() * pl->P.nslabs) &&
                   zalloc(&pl->bad, (size_t)batch) && zalloc(&pl->stage, stage);
   if (!ok) { set_error("mmcheck: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())); plo_mmcheck_plan_destroy(pl); return PLO_E_CUDA; }
   *plan = pl;
@@ -515,19 +816,29 @@ int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, i
 static void launch_spmm(const plo_mmcheck_plan* pl, const DevSlabCsr& A, const unsigned int* X, unsigned int* out, const unsigned int* mul, cudaStream_t st) {
   SpmmArgs a;
   a.mul = mul;
-  a.p = pl->p; a.M = pl->M; a.rows = A.rows; a.xlen = A.cols; a.groups = pl->groups; a.nchunks = A.nchunks;
+  a.p = pl->p; a.M = pl->M; a.c32 = (unsigned)((1ull << 32) % pl->p); a.c64 = (unsigned)((unsigned long long)a.c32 * a.c32 % pl->p);
+  a.rows = A.rb.total(); a.xlen = A.cols; a.groups = pl->groups; a.nchunks = A.nchunks; a.cstride = A.cstride;
   a.chunk = A.chunk; a.blob = A.blob; a.X = X; a.out = out;
   const long long T = (long long)pl->groups * A.nchunks;
   const int grid = (int)std::min<long long>(T, pl->grid_cap);
-  if (A.grouped) mm_slab_spmm_kernel<true><<<grid, kSpThreads, kSpSmem, st>>>(a);
-  else mm_slab_spmm_kernel<false><<<grid, kSpThreads, kSpSmem, st>>>(a);
+  const bool p31 = pl->p < 0x80000000u;
+  if (p31 && mul) mm_slab_spmm_kernel<true, true><<<grid, kSpThreads, kSpSmem, st>>>(a);
+  else if (p31) mm_slab_spmm_kernel<true, false><<<grid, kSpThreads, kSpSmem, st>>>(a);
+  else if (mul) mm_slab_spmm_kernel<false, true><<<grid, kSpThreads, kSpSmem, st>>>(a);
+  else mm_slab_spmm_kernel<false, false><<<grid, kSpThreads, kSpSmem, st>>>(a);
 }
 
 static int mm_pipeline(plo_mmcheck_plan* pl, cudaStream_t st) {
   const int B = pl->batch;
   const size_t G32 = (size_t)pl->groups * 32;
+  static const bool timing = getenv("PLO_TIMING") != nullptr;  // per-kernel times on stderr (development aid; serialises the stream)
+  cudaEvent_t ev[6] = {};
+  int nev = 0;
+  auto mark = [&]() { if (timing) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); ++nev; } };
   PLO_CUDA(cudaMemsetAsync(pl->bad, 0, 4 * (size_t)B, st));
+  mark();
   launch_spmm(pl, pl->L, pl->ua, pl->va, nullptr, st);
+  mark();
   if (pl->L.nslabs == 1 && pl->R.nslabs == 1) {
     launch_spmm(pl, pl->R, pl->ub, pl->vc, pl->va, st);  // vc = (R ub) o (L ua) in the epilogue
   } else {
@@ -535,10 +846,20 @@ static int mm_pipeline(plo_mmcheck_plan* pl, cudaStream_t st) {
     const size_t cnt = G32 * pl->r;
     mm_hadamard_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(pl->p, pl->M, cnt, pl->L.nslabs, pl->R.nslabs, pl->va, pl->vb, pl->vc);
   }
+  mark();
   launch_spmm(pl, pl->P, pl->vc, pl->wc, nullptr, st);
+  mark();
   const size_t vcnt = G32 * pl->m * pl->n;
-  mm_verify_kernel<<<(unsigned)((vcnt + 255) / 256), 256, 0, st>>>(pl->p, pl->M, pl->m, pl->k, pl->n, B, pl->groups, pl->P.nslabs, pl->wc, pl->ua, pl->ub, pl->bad);
+  mm_verify_kernel<<<(unsigned)((vcnt + 255) / 256), 256, 0, st>>>(pl->p, pl->M, pl->m, pl->k, pl->n, B, pl->groups, pl->P.nslabs, pl->P.rb, pl->wc, pl->ua, pl->ub, pl->bad);
+  mark();
   PLO_CUDA(cudaGetLastError());
+  if (timing) {
+    cudaEventSynchronize(ev[nev - 1]);
+    float t[4];
+    for (int i = 0; i + 1 < nev; ++i) { cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]); }
+    fprintf(stderr, "# mmcheck batch %d: L %.1f us, R(+Hadamard) %.1f us, P %.1f us, verify %.1f us\n", B, 1e3 * t[0], 1e3 * t[1], 1e3 * t[2], 1e3 * t[3]);
+    for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+  }
   return PLO_OK;
 }
 
