@@ -52,7 +52,10 @@ constexpr int kChunkEnt = 1536;                         // max 8-byte stream wor
 constexpr int kChunkRows = 192;                         // max rows per blob
 constexpr int kHdrBytes = kChunkRows * 8;               // row descriptors
 constexpr int kStageBytes = kHdrBytes + kChunkEnt * 8;  // 13.5 KB
-constexpr int kConsumerWarps = 28;
+#ifndef PLO_MM_WARPS
+#define PLO_MM_WARPS 28
+#endif
+constexpr int kConsumerWarps = PLO_MM_WARPS;
 constexpr int kSpThreads = (kConsumerWarps + 1) * 32;   // + one producer warp
 constexpr int kRingBase = kSlabBytes;
 constexpr int kSpSmem = kRingBase + kStages * kStageBytes;
@@ -70,23 +73,35 @@ __host__ __device__ __forceinline__ int blk_id(int c, int lv, int cs) { return (
 __host__ __device__ __forceinline__ int blk_member(int b, int t, int lv, int cs) { return (b / cs) * (lv * cs) + t * cs + b % cs; }
 
 struct Acc96 {
-  unsigned int a0, a1, a2;
+  unsigned long long lo;  // bits 0..63 (one aligned register pair: the multiply-add below becomes a single IMAD.WIDE with carry-out)
+  unsigned int hi;        // bits 64..95
 };
 __device__ __forceinline__ void mac96(Acc96& a, unsigned int x, unsigned int y) {
   asm volatile(
-      "mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-      "addc.u32 %2, %2, 0;"
-      : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2)
+      "{\n\t"
+      ".reg .u32 l, h;\n\t"
+      "mov.b64 {l, h}, %0;\n\t"
+      "mad.lo.cc.u32 l, %2, %3, l;\n\t"
+      "madc.hi.cc.u32 h, %2, %3, h;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "mov.b64 %0, {l, h};\n\t"
+      "}"
+      : "+l"(a.lo), "+r"(a.hi)
       : "r"(x), "r"(y));
 }
 __device__ __forceinline__ void add96(Acc96& a, const Acc96& b) {
   asm volatile(
-      "add.cc.u32 %0, %0, %3;\n\t"
-      "addc.cc.u32 %1, %1, %4;\n\t"
-      "addc.u32 %2, %2, %5;"
-      : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2)
-      : "r"(b.a0), "r"(b.a1), "r"(b.a2));
+      "{\n\t"
+      ".reg .u32 l, h, m, n;\n\t"
+      "mov.b64 {l, h}, %0;\n\t"
+      "mov.b64 {m, n}, %2;\n\t"
+      "add.cc.u32 l, l, m;\n\t"
+      "addc.cc.u32 h, h, n;\n\t"
+      "addc.u32 %1, %1, %3;\n\t"
+      "mov.b64 %0, {l, h};\n\t"
+      "}"
+      : "+l"(a.lo), "+r"(a.hi)
+      : "l"(b.lo), "r"(b.hi));
 }
 // x mod p for any 64-bit x: Barrett with M = floor((2^64-1)/p); q is at most 2 short.
 __device__ __forceinline__ unsigned int barrett64(unsigned long long x, unsigned int p, unsigned long long M) {
@@ -97,8 +112,8 @@ __device__ __forceinline__ unsigned int barrett64(unsigned long long x, unsigned
   return (unsigned int)r;
 }
 __device__ __forceinline__ unsigned int reduce96(const Acc96& a, unsigned int p, unsigned long long M) {
-  const unsigned int t = barrett64(((unsigned long long)a.a2 << 32) | a.a1, p, M);
-  return barrett64(((unsigned long long)t << 32) | a.a0, p, M);
+  const unsigned int t = barrett64(((unsigned long long)a.hi << 32) | (a.lo >> 32), p, M);
+  return barrett64(((unsigned long long)t << 32) | (unsigned int)a.lo, p, M);
 }
 
 // ---- mbarrier / TMA bulk copy (PTX ISA 8.x, sm_90+) -------------------------
@@ -194,7 +209,8 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
 __device__ __forceinline__ void sts_u32(uint32_t addr, unsigned int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
 
-// Row descriptor (8 B): {start | np << 16, ng}; row stream, offsets in 8-byte words from `start`, every area 16-byte aligned:
+// Row descriptor (8 B): {start | np << 16, ng | (row - first row of the blob) << 16}; rows without entries are not stored (their
+// outputs stay at the zeros the plan allocated); row stream, offsets in 8-byte words from `start`, every area 16-byte aligned:
 //   [np plain pairs (byte offset of the virtual column = 128 * column, value); np even, padding = (0, 0)]
 //   [ng group headers (value, nunits), padded to an even count]
 //   [units: 4 byte offsets each, all groups in order; a group is padded with the plain pairs' help, never inside a unit]
@@ -203,7 +219,6 @@ template <bool P31, bool HAD>
 __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full[kStages], empty[kStages], slabbar;
-  __shared__ int cnt[kStages];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long T = (long long)a.groups * a.nchunks;
   const long long i0 = (long long)blockIdx.x * T / gridDim.x, i1 = (long long)(blockIdx.x + 1) * T / gridDim.x;
@@ -235,8 +250,6 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
       } else if (k >= kStages) {
         mbar_wait(&empty[stage], ((k / kStages) - 1) & 1);
       }
-      cnt[stage] = 0;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&full[stage], (unsigned)ch.bytes);
       bulk_g2s(smem + kRingBase + stage * kStageBytes, a.blob + ch.off, (unsigned)ch.bytes, &full[stage]);
       if (++c == a.nchunks) { c = 0; ++g; }
@@ -244,9 +257,10 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
     return;
   }
   // ---- consumers: lane = sample of the group, warp takes rows of the current blob ----
-  const uint32_t xl = smem_u32(smem) + lane * 4;  // this lane's word of slab column 0
-  const uint32_t ring = smem_u32(smem) + kRingBase;
-  const uint32_t cnt0 = smem_u32(&cnt[0]);
+  // loop invariants, made opaque: under the register cap ptxas would otherwise recompute them (S2R + shifts) inside the row loops
+  uint32_t xl, ring;
+  asm volatile("mov.u32 %0, %1;" : "=r"(xl) : "r"(smem_u32(smem) + lane * 4));  // this lane's word of slab column 0
+  asm volatile("mov.u32 %0, %1;" : "=r"(ring) : "r"(smem_u32(smem) + kRingBase));
   unsigned int one;
   asm volatile("mov.u32 %0, 1;" : "=r"(one));
   unsigned slabphase = 0;
@@ -257,20 +271,22 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
       mbar_wait(&slabbar, slabphase);
       slabphase ^= 1; pg = g; ps = ch.x;
       if (a.cstride) {
-        // block sums of the new slab: X4[b] = sum of 4 columns, X16[b] = sum of the 4 blocks of 4 it consists of (mod p)
-        const int cs = a.cstride;
+        // block sums of the new slab (mod p): X4[b] = sum of the 4 columns of block b, X16[b] = sum of the 4 blocks of 4 that make up
+        // block b of 16.  The stride is a power of two: block (hi, lo) of level lv has the members ((hi * lv + t) << sh) | lo.
+        const int sh = 31 - __clz(a.cstride), lomask = a.cstride - 1;
         for (int b = warp; b < kBlk4; b += kConsumerWarps) {
+          const int hi = b >> sh, lo = b & lomask;
           unsigned long long s = 0;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) s += lds_u32(xl + blk_member(b, t, 4, cs) * 128);
+          for (int t = 0; t < 4; ++t) s += lds_u32(xl + ((((hi * 4 + t) << sh) | lo) << 7));
           sts_u32(xl + (kSlabCols + b) * 128, barrett64(s, a.p, a.M));
         }
         consumer_sync();
         for (int b = warp; b < kBlk16; b += kConsumerWarps) {
-          // block b of 16 (stride cs) = the blocks of 4 with stride 4 cs ... whose members are its members: t = 4 u + v  ->  blocks of 4 numbered by (hi, v, lo)
+          const int hi = b >> sh, lo = b & lomask;
           unsigned long long s = 0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) s += lds_u32(xl + (kSlabCols + blk_id(blk_member(b, 4 * u, 16, cs), 4, cs)) * 128);
+          for (int u = 0; u < 4; ++u) s += lds_u32(xl + ((kSlabCols + (((hi * 4 + u) << sh) | lo)) << 7));  // block of 4 number (hi * 4 + u, lo)
           sts_u32(xl + (kSlabCols + kBlk4 + b) * 128, barrett64(s, a.p, a.M));
         }
         consumer_sync();
@@ -279,23 +295,19 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
     mbar_wait(&full[stage], (k / kStages) & 1);
     const uint32_t hdr = ring + stage * kStageBytes;
     const uint32_t st = hdr + ((ch.z * 8 + 15) & ~15);
-    const uint32_t cn = cnt0 + stage * 4;
     unsigned int* outp = a.out + (((size_t)ch.x * a.groups + g) * a.rows + ch.y) * 32 + lane;
     const unsigned int* mulp = HAD ? a.mul + ((size_t)g * a.rows + ch.y) * 32 + lane : nullptr;
-    int cur = 0;
-    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(cur) : "r"(cn) : "memory");
-    cur = __shfl_sync(0xffffffffu, cur, 0);
-    while (cur < ch.z) {
-      int nxt = 0;
-      if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(nxt) : "r"(cn) : "memory");
+    // rows of the blob are dealt round-robin: after the block sums they are short and of similar cost, and four blobs are in flight
+    for (int cur = warp; cur < ch.z; cur += kConsumerWarps) {
       const uint2 rd = lds_u64(hdr + cur * 8);
+      const unsigned np = rd.x >> 16, ng = rd.y & 0xffffu, row = rd.y >> 16;  // row: relative to the first row of the blob
       unsigned int mulv = 0;
-      if (HAD) mulv = __ldg(mulp + (size_t)cur * 32);  // issued now, needed in the epilogue
-      const unsigned np = rd.x >> 16, ng = rd.y;
+      if (HAD) mulv = __ldg(mulp + (size_t)row * 32);  // issued now, needed in the epilogue
       uint32_t pa = st + (rd.x & 0xffffu) * 8;
       Acc96 A, B;
-      A.a0 = A.a1 = A.a2 = 0;
-      B.a0 = B.a1 = B.a2 = 0;
+      A.lo = 0; A.hi = 0;
+      B.lo = 0; B.hi = 0;
+#pragma unroll 1
       for (const uint32_t pe = pa + np * 8; pa != pe; pa += 16) {
         const uint4 q = lds_u128(pa);
         const unsigned x0 = lds_u32(xl + q.x);
@@ -306,12 +318,13 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
       add96(A, B);
       if (ng) {
         uint32_t un = pa + ((ng + 1) & ~1u) * 8;
+#pragma unroll 1
         for (const uint32_t ge = pa + ng * 8; pa != ge; pa += 8) {
           const uint2 h = lds_u64(pa);
           unsigned long long s0 = 0, s1 = 0;
-#pragma unroll 2
-          for (unsigned j = 0; j < h.y; ++j) {
-            const uint4 cw = lds_u128(un + j * 16);
+#pragma unroll 1
+          for (const uint32_t ue = un + h.y * 16; un != ue; un += 16) {
+            const uint4 cw = lds_u128(un);
             const unsigned x0 = lds_u32(xl + cw.x);
             const unsigned x1 = lds_u32(xl + cw.y);
             const unsigned x2 = lds_u32(xl + cw.z);
@@ -321,23 +334,25 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
             addwide(s0, x2, one);
             addwide(s1, x3, one);
           }
-          un += h.y * 16;
           const unsigned long long s = s0 + s1;  // < 2^45
           mac96(A, h.x, (unsigned)s);
-          asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(A.a1), "+r"(A.a2) : "r"(h.x), "r"((unsigned)(s >> 32)));
+          {  // + value * (s >> 32) * 2^32: lands in bits 32..95
+            const unsigned long long t = (unsigned long long)h.x * (unsigned)(s >> 32) + (A.lo >> 32) + ((unsigned long long)A.hi << 32);
+            A.lo = (A.lo & 0xffffffffull) | (t << 32);
+            A.hi = (unsigned)(t >> 32);
+          }
         }
       }
       unsigned int res;
       if (P31) {
         // p < 2^31 and a2 < 2^15: a2 c64 + a1 c32 + a0 < 2^46 + 2^63 + 2^32 fits 64 bits -> one Barrett step
-        const unsigned long long x = (unsigned long long)A.a2 * a.c64 + (unsigned long long)A.a1 * a.c32 + A.a0;
+        const unsigned long long x = (unsigned long long)A.hi * a.c64 + (A.lo >> 32) * a.c32 + (unsigned int)A.lo;
         res = barrett64(x, a.p, a.M);
       } else {
         res = reduce96(A, a.p, a.M);
       }
       if (HAD) res = barrett64((unsigned long long)res * mulv, a.p, a.M);
-      outp[(size_t)cur * 32] = res;
-      cur = __shfl_sync(0xffffffffu, nxt, 0);
+      outp[(size_t)row * 32] = res;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
@@ -392,7 +407,7 @@ __global__ void mm_verify_kernel(unsigned int p, unsigned long long M, int m, in
     if (v16 >= 0) w += base[(size_t)v16 * 32];
   }
   Acc96 acc;
-  acc.a0 = acc.a1 = acc.a2 = 0;
+  acc.lo = 0; acc.hi = 0;
   const unsigned int* pa = ua + ((size_t)g * m * k + (size_t)i * k) * 32 + lane;
   const unsigned int* pb = ub + ((size_t)g * k * n + j) * 32 + lane;
   for (int t = 0; t < k; ++t) mac96(acc, pa[(size_t)t * 32], pb[(size_t)t * n * 32]);
@@ -550,7 +565,7 @@ void encode_row(Row& row, int ming, RowStream* out) {
     for (; t < u; ++t) out->plain.push_back(make_uint2(row[t].col * 128u, row[t].val));
   }
 }
-unsigned write_row(const RowStream& rs, uint2* stream, unsigned o, uint2* desc) {
+unsigned write_row(const RowStream& rs, uint2* stream, unsigned o, unsigned rel_row, uint2* desc) {
   const unsigned np = (unsigned)((rs.plain.size() + 1) & ~(size_t)1), ng = (unsigned)rs.heads.size();
   uint2* w = stream + o;
   for (size_t z = 0; z < rs.plain.size(); ++z) w[z] = rs.plain[z];  // padding stays (0, 0): slab column 0 times zero
@@ -558,7 +573,7 @@ unsigned write_row(const RowStream& rs, uint2* stream, unsigned o, uint2* desc) 
   for (size_t z = 0; z < rs.heads.size(); ++z) w[z] = rs.heads[z];
   w += (ng + 1) & ~1u;
   for (size_t z = 0; z < rs.units.size(); ++z) reinterpret_cast<uint4*>(w)[z] = rs.units[z];
-  *desc = make_uint2(o | (np << 16), ng);
+  *desc = make_uint2(o | (np << 16), ng | (rel_row << 16));
   return rs.words();
 }
 
@@ -663,12 +678,15 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
     if (target < 512) target = 512;
     int row = 0;
     while (row < rb.total()) {
-      int n = 0;
+      while (row < rb.total() && streams[(size_t)row].words() == 0) ++row;  // rows without entries: no task, the output stays zero
+      if (row == rb.total()) break;
+      int n = 0, span = 0;
       long long w = 0, c = 0;
-      while (row + n < rb.total() && n < kChunkRows) {
-        const RowStream& st = streams[(size_t)(row + n)];
+      while (row + span < rb.total() && n < kChunkRows && span < 65536) {
+        const RowStream& st = streams[(size_t)(row + span)];
+        if (st.words() == 0) { ++span; continue; }
         if (n > 0 && (c + st.cost() > target || w + st.words() > (unsigned)kChunkEnt)) break;
-        w += st.words(); c += st.cost(); ++n;
+        w += st.words(); c += st.cost(); ++n; ++span;
       }
       const size_t hdr = ((size_t)n * 8 + 15) & ~(size_t)15;
       ChunkDesc ch;
@@ -678,9 +696,15 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
       uint2* ho = reinterpret_cast<uint2*>(out->blob.data() + ch.off);
       uint2* eo = reinterpret_cast<uint2*>(out->blob.data() + ch.off + hdr);
       unsigned o = 0;
-      for (int z = 0; z < n; ++z) o += write_row(streams[(size_t)(row + z)], eo, o, ho + z);
+      int z = 0;
+      for (int q = 0; q < span; ++q) {
+        const RowStream& st = streams[(size_t)(row + q)];
+        if (st.words() == 0) continue;
+        o += write_row(st, eo, o, (unsigned)q, ho + z);
+        ++z;
+      }
       out->table.push_back(ch);
-      row += n;
+      row += span;
     }
   }
   (void)nnz;
@@ -729,7 +753,7 @@ static int decode_check(const plo_csr* h, uint32_t p, int groups, int allow_row_
     const uint2* hdr = reinterpret_cast<const uint2*>(enc.blob.data() + ch.off);
     const uint2* st = reinterpret_cast<const uint2*>(enc.blob.data() + ch.off + (((size_t)ch.nrows * 8 + 15) & ~(size_t)15));
     for (int t = 0; t < ch.nrows; ++t) {
-      const unsigned start = hdr[t].x & 0xffffu, np = hdr[t].x >> 16, ng = hdr[t].y;
+      const unsigned start = hdr[t].x & 0xffffu, np = hdr[t].x >> 16, ng = hdr[t].y & 0xffffu, rel = hdr[t].y >> 16;
       unsigned __int128 A = 0;
       auto ld = [&](unsigned off) -> unsigned long long { return (off & 127u) || off / 128u >= (unsigned)kVCols ? ~0ull : xs[off / 128u]; };
       for (unsigned z = 0; z < np; ++z) A += (unsigned __int128)st[start + z].y * ld(st[start + z].x);
@@ -741,7 +765,8 @@ static int decode_check(const plo_csr* h, uint32_t p, int groups, int allow_row_
         un += gh[gi].y;
         A += (unsigned __int128)gh[gi].x * s;
       }
-      ext[(size_t)ch.slab * rb.total() + ch.row0 + t] = (unsigned long long)(A % p);
+      if (ch.row0 + (int)rel >= rb.total()) { set_error("mmcheck encoder: row out of range"); return PLO_E_ARG; }
+      ext[(size_t)ch.slab * rb.total() + ch.row0 + rel] = (unsigned long long)(A % p);
     }
   }
   for (int o = 0; o < h->rows; ++o) {
@@ -820,6 +845,7 @@ static void launch_spmm(const plo_mmcheck_plan* pl, const DevSlabCsr& A, const u
   a.rows = A.rb.total(); a.xlen = A.cols; a.groups = pl->groups; a.nchunks = A.nchunks; a.cstride = A.cstride;
   a.chunk = A.chunk; a.blob = A.blob; a.X = X; a.out = out;
   const long long T = (long long)pl->groups * A.nchunks;
+  if (T == 0) return;  // a matrix without entries: its product is the zero vector the plan allocated
   const int grid = (int)std::min<long long>(T, pl->grid_cap);
   const bool p31 = pl->p < 0x80000000u;
   if (p31 && mul) mm_slab_spmm_kernel<true, true><<<grid, kSpThreads, kSpSmem, st>>>(a);
