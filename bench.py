@@ -574,6 +574,7 @@ def bench_c5(ctx, steps, warmup, cpu_seconds):
         e_steps = max(3, min(steps, 10))
         e_dt = wall_steps(ctx, e2e_step, e_steps)
         launches = plan.launches
+        enc = plan.encoding
         plan.close()
         if ctx.rank == 0:
             wave_peak = torch.cuda.get_device_properties(ctx.dev).multi_processor_count * 32 * (ctx.clocks.get("sm_mhz") or 1965.0) * 1e6
@@ -587,9 +588,15 @@ def bench_c5(ctx, steps, warmup, cpu_seconds):
                      "roofline": {"bound": "shared-memory wavefronts", "achieved": per_gpu * mac / 1e12, "peak": wave_peak / 1e12, "unit": "T modular MAC/s per GPU",
                                   "frac": per_gpu * mac / wave_peak, "traffic": (ctx.ncu.get("mm_slab_spmm_kernel") or {}).get("dram_bytes_per_pass"),
                                   "kernel": "mm_slab_spmm_kernel x3 (+ gen, verify)",
-                                  "peak_source": "one 128 B shared-memory wavefront per multiply-add per warp: SMs x 32 lanes x SM clock",
-                                  "hbm": {"csr_bytes_if_streamed_once_per_pass": nnz * 8, "GBs_if_streamed": nnz * 8 / (ms / steps * 1e-3) / 1e9, "peak_GBs": measured_hbm_peak(),
-                                          "note": "the chunk blobs (2.3 B per non-zero) stay L2-resident; small batches are launch-bound, not HBM-bound"}}}
+                                  "peak_source": "one 128 B shared-memory wavefront per multiply-add of the CSR per warp: SMs x 32 lanes x SM clock",
+                                  "encoded": {"x_loads_per_sample": sum(enc["loads"]), "csr_entries": nnz, "col_stride": enc["col_stride"], "row_stride": enc["row_stride"],
+                                              "wavefront_frac": per_gpu * 2 * sum(enc["loads"]) / wave_peak,
+                                              "note": "the plan's encoder rewrites the rows with column / row block sums (csrc/mmcheck.cu): the kernels read x_loads_per_sample "
+                                                      "words of X per sample instead of one per CSR entry, so `frac` (CSR multiply-adds against the one-wavefront-per-entry roof) can "
+                                                      "exceed 1; wavefront_frac = (X loads + as many wavefronts of 8-byte stream words) x samples / 32 against the same peak"},
+                                  "hbm": {"encoded_bytes": sum(enc["blob_bytes"]), "peak_GBs": measured_hbm_peak(),
+                                          "note": "the encoded matrices (3 MB) stay L2-resident; the partial products wc of the 15 slabs of P (batch x 80 KB) are the HBM "
+                                                  "traffic; small batches are latency-bound (slab fill + block sums per launch), not HBM-bound"}}}
             out[f"batch_{batch}"] = entry
     if ctx.rank == 0 and ctx.world == 1 and cpu_seconds > 0:
         out["cpu_baseline"] = cpu_c5(big, 4 * host_threads(), host_threads())

@@ -271,12 +271,17 @@ int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, i
 int plo_mmcheck_plan_run(plo_mmcheck_plan* plan, uint64_t seed, uint64_t first_sample, void* stream);
 int plo_mmcheck_plan_result(plo_mmcheck_plan* plan, void* stream, uint8_t* ok, int* verdict);
 int plo_mmcheck_plan_launches(const plo_mmcheck_plan* plan);
+/* What the encoder made of L, R, P (each array may be NULL): loads[3] = X words read per sample (the CSR has nnz of them),
+ * blob_bytes[3] = size of the encoded matrix, strides[6] = (column stride of the column block sums, row stride of the row block
+ * sums) per matrix, 0 = not used. */
+int plo_mmcheck_plan_encoding(const plo_mmcheck_plan* plan, int64_t* loads, int64_t* blob_bytes, int* strides);
 void plo_mmcheck_plan_destroy(plo_mmcheck_plan* plan);
 /* Host-only check (no device needed) of the matrix encoder behind the plans: encodes A the way plan_create does for `groups`
  * sample groups (column block sums, row block sums when row_blocks != 0 -- plans use them for P only --, plain pairs and value
  * groups; see csrc/mmcheck.cu), replays the encoded stream on the CPU for ONE sample and returns y = A.x mod p (x: cols residues,
- * y: rows).  stats (may be NULL, 8 values): row stride of the row blocks (0: none), column stride of the column blocks (0: none),
- * chunks, blob bytes, plain entries, units of 4 grouped entries, value groups, X loads per sample after encoding. */
+ * y: rows).  stats (may be NULL, 9 values): row stride of the row blocks (0: none), column stride of the column blocks (0: none),
+ * chunks, blob bytes, plain entries, units of 4 grouped entries, value groups, X loads per sample after encoding, stored
+ * (row, slab) tasks. */
 int plo_mmcheck_encode_check(uint32_t p, const plo_csr* A, int groups, int row_blocks, const uint32_t* x, uint32_t* y, long long* stats);
 
 /* ---------------------------------------------------------------------------

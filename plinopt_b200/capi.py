@@ -28,7 +28,7 @@ SYMBOLS = [
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
     "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_pack", "plo_orbit_plan_kernel", "plo_orbit_magnitude_bounds", "plo_orbit_plan_survivors", "plo_selftest_matrix_index", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
-    "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_encode_check", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
+    "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_encoding", "plo_mmcheck_encode_check", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
     "plo_sparsifier", "plo_orbiter", "plo_orbiter_progress", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
     "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
     "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender", "plo_negater", "plo_rotater", "plo_growth_factors",
@@ -481,11 +481,11 @@ def mmcheck_encode_check(p, A, x, groups=1, row_blocks=True):
     xs = np.ascontiguousarray(x, dtype=np.uint32)
     assert xs.size == A[1]
     y = np.zeros(A[0], dtype=np.uint32)
-    st = (C.c_longlong * 8)()
+    st = (C.c_longlong * 9)()
     f = lib().plo_mmcheck_encode_check
     f.argtypes = [C.c_uint32, C.POINTER(Csr), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     _check(f(p, C.byref(h.c), int(groups), int(bool(row_blocks)), _ptr(xs), _ptr(y), C.cast(st, C.c_void_p)))
-    keys = ("row_stride", "col_stride", "chunks", "blob_bytes", "plain_entries", "units", "groups", "loads")
+    keys = ("row_stride", "col_stride", "chunks", "blob_bytes", "plain_entries", "units", "groups", "loads", "tasks")
     return y, dict(zip(keys, [int(v) for v in st]))
 
 
@@ -499,6 +499,12 @@ class MMcheckPlan:
         f.argtypes = [C.POINTER(C.c_void_p), C.c_uint32] + [C.c_int] * 4 + [C.POINTER(Csr)] * 3 + [C.c_int]
         _check(f(C.byref(self._h), p, m, k, n, r, C.byref(self._keep[0].c), C.byref(self._keep[1].c), C.byref(self._keep[2].c), batch))
         self.launches = lib().plo_mmcheck_plan_launches(self._h)
+        loads, blob, strides = (C.c_int64 * 3)(), (C.c_int64 * 3)(), (C.c_int * 6)()
+        g = lib().plo_mmcheck_plan_encoding
+        g.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(g(self._h, C.cast(loads, C.c_void_p), C.cast(blob, C.c_void_p), C.cast(strides, C.c_void_p)))
+        self.encoding = {"loads": [int(v) for v in loads], "blob_bytes": [int(v) for v in blob],
+                         "col_stride": [int(strides[2 * z]) for z in range(3)], "row_stride": [int(strides[2 * z + 1]) for z in range(3)]}
 
     def run(self, seed, first_sample=0, stream=0):
         _check(lib().plo_mmcheck_plan_run(self._h, seed, first_sample, C.c_void_p(stream)))

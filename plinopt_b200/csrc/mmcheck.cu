@@ -385,33 +385,51 @@ __host__ __device__ __forceinline__ RowBlocks row_blocks(int rows, int rs) {
   return rb;
 }
 
-// bad[b] |= (sum_parts wc[g][o][lane] + its virtual rows != sum_t ua[g][i*k+t][lane] * ub[g][t*n+j][lane])  for o = i*n + j, b = 32 g + lane
-__global__ void mm_verify_kernel(unsigned int p, unsigned long long M, int m, int k, int n, int batch, int groups, int parts, RowBlocks rb,
-                                 const unsigned int* __restrict__ wc, const unsigned int* __restrict__ ua, const unsigned int* __restrict__ ub,
-                                 unsigned int* __restrict__ bad) {
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int mn = m * n;
-  if (e >= (size_t)groups * mn * 32) return;
-  const int lane = (int)(e & 31);
-  const int o = (int)((e >> 5) % mn), g = (int)((e >> 5) / mn), i = o / n, j = o % n;
+// bad[b] |= (sum_parts wc[g][o][lane] + its virtual rows != sum_t ua[g][i*k+t][lane] * ub[g][t*n+j][lane])  for o = i*n + j, b = 32 g + lane.
+// One warp per (g, j, block of kVerifyRows values of i), lane = sample: ub[t*n+j] is loaded once for the whole block, and the virtual
+// rows, which P's row blocks share between outputs with the same j (row stride n), once per block instead of once per output.
+constexpr int kVerifyRows = 1;
+__global__ void __launch_bounds__(256) mm_verify_kernel(unsigned int p, unsigned long long M, int m, int k, int n, int batch, int groups, int parts, RowBlocks rb,
+                                                        const unsigned int* __restrict__ wc, const unsigned int* __restrict__ ua,
+                                                        const unsigned int* __restrict__ ub, unsigned int* __restrict__ bad) {
+  const int lane = threadIdx.x & 31;
+  const int nib = (m + kVerifyRows - 1) / kVerifyRows;
+  const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (size_t)groups * n * nib) return;
+  const int j = (int)(wid % n), ib = (int)((wid / n) % nib), g = (int)(wid / ((size_t)n * nib));
   const int b = g * 32 + lane;
   if (b >= batch) return;
-  const int tot = rb.total();
-  const int v4 = rb.rs && o / (4 * rb.rs) * rb.rs < rb.n4 ? rb.rows + blk_id(o, 4, rb.rs) : -1;
-  const int v16 = rb.rs && o / (16 * rb.rs) * rb.rs < rb.n16 ? rb.rows + rb.n4 + blk_id(o, 16, rb.rs) : -1;
-  unsigned long long w = 0;
-  for (int q = 0; q < parts; ++q) {
-    const unsigned int* base = wc + ((size_t)q * groups + g) * tot * 32 + lane;
-    w += base[(size_t)o * 32];
-    if (v4 >= 0) w += base[(size_t)v4 * 32];
-    if (v16 >= 0) w += base[(size_t)v16 * 32];
-  }
-  Acc96 acc;
-  acc.lo = 0; acc.hi = 0;
-  const unsigned int* pa = ua + ((size_t)g * m * k + (size_t)i * k) * 32 + lane;
+  const int i0 = ib * kVerifyRows;
+  Acc96 acc[kVerifyRows];
+#pragma unroll
+  for (int u = 0; u < kVerifyRows; ++u) { acc[u].lo = 0; acc[u].hi = 0; }
+  const unsigned int* pa = ua + ((size_t)g * m * k + (size_t)i0 * k) * 32 + lane;
   const unsigned int* pb = ub + ((size_t)g * k * n + j) * 32 + lane;
-  for (int t = 0; t < k; ++t) mac96(acc, pa[(size_t)t * 32], pb[(size_t)t * n * 32]);
-  if (barrett64(w, p, M) != reduce96(acc, p, M)) atomicOr(bad + b, 1u);
+  for (int t = 0; t < k; ++t) {
+    const unsigned int y = pb[(size_t)t * n * 32];
+#pragma unroll
+    for (int u = 0; u < kVerifyRows; ++u)
+      if (i0 + u < m) mac96(acc[u], pa[((size_t)u * k + t) * 32], y);
+  }
+  const int tot = rb.total();
+  const size_t pstride = (size_t)groups * tot * 32;
+  const unsigned int* base = wc + (size_t)g * tot * 32 + lane;
+  int last4 = -2, last16 = -2;
+  unsigned long long w4 = 0, w16 = 0;
+  unsigned int wrong = 0;
+#pragma unroll
+  for (int u = 0; u < kVerifyRows; ++u) {
+    if (i0 + u >= m) break;
+    const int o = (i0 + u) * n + j;
+    const int v4 = rb.rs && o / (4 * rb.rs) * rb.rs < rb.n4 ? rb.rows + blk_id(o, 4, rb.rs) : -1;
+    const int v16 = rb.rs && o / (16 * rb.rs) * rb.rs < rb.n16 ? rb.rows + rb.n4 + blk_id(o, 16, rb.rs) : -1;
+    if (v4 != last4) { w4 = 0; if (v4 >= 0) for (int q = 0; q < parts; ++q) w4 += base[(size_t)q * pstride + (size_t)v4 * 32]; last4 = v4; }
+    if (v16 != last16) { w16 = 0; if (v16 >= 0) for (int q = 0; q < parts; ++q) w16 += base[(size_t)q * pstride + (size_t)v16 * 32]; last16 = v16; }
+    unsigned long long w = w4 + w16;
+    for (int q = 0; q < parts; ++q) w += base[(size_t)q * pstride + (size_t)o * 32];
+    wrong |= barrett64(w, p, M) != reduce96(acc[u], p, M);
+  }
+  if (wrong) atomicOr(bad + b, 1u);
 }
 
 }  // namespace plo
@@ -423,7 +441,7 @@ struct DevSlabCsr {
   int rows, cols, nslabs, nchunks;
   int cstride;   // column stride of the block sums the rows refer to (0: none)
   RowBlocks rb;  // virtual rows (rb.rs = 0: none)
-  long long nnz, loads;  // entries of the CSR / X loads per sample after encoding
+  long long nnz, loads, blob_bytes;  // entries of the CSR / X loads per sample after encoding / bytes of the encoded matrix
   ChunkDesc* chunk;
   unsigned char* blob;
 };
@@ -582,7 +600,7 @@ struct Encoded {
   std::vector<unsigned char> blob;
   int cstride = 0;
   RowBlocks rb{};
-  long long loads = 0, plain = 0, units = 0, heads = 0;
+  long long loads = 0, plain = 0, units = 0, heads = 0, tasks = 0;
 };
 }  // namespace
 
@@ -672,6 +690,7 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
       encode_row(r, ming, &st);
       if (st.words() > (unsigned)kChunkEnt) { set_error("mmcheck: a row has too many entries inside one %d-column slab", kSlabCols); return PLO_E_ARG; }
       total_cost += st.cost();
+      out->tasks += st.words() != 0;
       out->loads += st.loads(); out->plain += (long long)st.plain.size(); out->units += (long long)st.units.size(); out->heads += (long long)st.heads.size();
     }
     long long target = total_cost * nslabs * groups / ((long long)nsm * 16);
@@ -718,7 +737,7 @@ static int build_slab_csr(const plo_csr* h, unsigned p, int groups, bool allow_r
   Encoded enc;
   const int rc = encode_slab_csr(h, p, groups, sm_count(), allow_row_blocks, &enc);
   if (rc) return rc;
-  d->cstride = enc.cstride; d->rb = enc.rb; d->loads = enc.loads;
+  d->cstride = enc.cstride; d->rb = enc.rb; d->loads = enc.loads; d->blob_bytes = (long long)enc.blob.size();
   d->nchunks = (int)enc.table.size();
   PLO_CUDA(pool_alloc(&d->chunk, sizeof(ChunkDesc) * enc.table.size()));
   PLO_CUDA(pool_alloc(&d->blob, enc.blob.size() ? enc.blob.size() : 16));
@@ -729,7 +748,7 @@ static int build_slab_csr(const plo_csr* h, unsigned p, int groups, bool allow_r
 
 // Host twin of the consumer side of mm_slab_spmm_kernel + the fold of mm_verify_kernel for ONE sample: y = A x mod p from the
 // encoded blobs.  Used by the CPU tests to check the encoder without a device; `stats` = {row stride, column stride, chunks,
-// blob bytes, plain entries, units, value groups, X loads per sample}.
+// blob bytes, plain entries, units, value groups, X loads per sample, stored (row, slab) tasks}.
 static int decode_check(const plo_csr* h, uint32_t p, int groups, int allow_row_blocks, const uint32_t* x, uint32_t* y, long long* stats) {
   Encoded enc;
   const int rc = encode_slab_csr(h, p, groups, 148, allow_row_blocks != 0, &enc);
@@ -782,8 +801,8 @@ static int decode_check(const plo_csr* h, uint32_t p, int groups, int allow_row_
     y[o] = (uint32_t)(w % p);
   }
   if (stats) {
-    const long long st_[8] = {rb.rs, enc.cstride, (long long)enc.table.size(), (long long)enc.blob.size(), enc.plain, enc.units, enc.heads, enc.loads};
-    for (int z = 0; z < 8; ++z) stats[z] = st_[z];
+    const long long st_[9] = {rb.rs, enc.cstride, (long long)enc.table.size(), (long long)enc.blob.size(), enc.plain, enc.units, enc.heads, enc.loads, enc.tasks};
+    for (int z = 0; z < 9; ++z) stats[z] = st_[z];
   }
   return PLO_OK;
 }
@@ -875,7 +894,7 @@ static int mm_pipeline(plo_mmcheck_plan* pl, cudaStream_t st) {
   mark();
   launch_spmm(pl, pl->P, pl->vc, pl->wc, nullptr, st);
   mark();
-  const size_t vcnt = G32 * pl->m * pl->n;
+  const size_t vcnt = G32 * pl->n * ((pl->m + kVerifyRows - 1) / kVerifyRows);
   mm_verify_kernel<<<(unsigned)((vcnt + 255) / 256), 256, 0, st>>>(pl->p, pl->M, pl->m, pl->k, pl->n, B, pl->groups, pl->P.nslabs, pl->P.rb, pl->wc, pl->ua, pl->ub, pl->bad);
   mark();
   PLO_CUDA(cudaGetLastError());
@@ -895,6 +914,17 @@ int plo_mmcheck_plan_run(plo_mmcheck_plan* pl, uint64_t seed, uint64_t first_sam
   const size_t gthreads = (size_t)pl->batch * ((pl->m * pl->k + 3) / 4 + (pl->k * pl->n + 3) / 4);
   mm_gen_kernel<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(pl->p, seed, first_sample, pl->batch, pl->m * pl->k, pl->k * pl->n, pl->ua, pl->ub);
   return mm_pipeline(pl, st);
+}
+
+int plo_mmcheck_plan_encoding(const plo_mmcheck_plan* pl, int64_t* loads, int64_t* blob_bytes, int* strides) {
+  if (!pl) { set_error("plo_mmcheck_plan_encoding: null plan"); return PLO_E_ARG; }
+  const DevSlabCsr* A[3] = {&pl->L, &pl->R, &pl->P};
+  for (int z = 0; z < 3; ++z) {
+    if (loads) loads[z] = A[z]->loads;
+    if (blob_bytes) blob_bytes[z] = A[z]->blob_bytes;
+    if (strides) { strides[2 * z] = A[z]->cstride; strides[2 * z + 1] = A[z]->rb.rs; }
+  }
+  return PLO_OK;
 }
 
 int plo_mmcheck_plan_launches(const plo_mmcheck_plan* pl) { return pl && pl->L.nslabs == 1 && pl->R.nslabs == 1 ? 5 : 6; }

@@ -89,6 +89,30 @@ def test_regenerated_32x32x32_15096_passes_and_corruption_is_caught(capi):
     ua = rng.integers(0, p, (3, 1024)).astype(np.uint32); ub = rng.integers(0, p, (3, 1024)).astype(np.uint32)
     v, ok = capi.mmcheck_batch(p, mkn, r, L2, R2, P2, batch=3, ua=ua, ub=ub)
     assert v == 0 and ok.all()
+    # mod a prime above 2^31 (two-step reduction in the kernels); a flipped residue of L is caught as well
+    pb = 4294967291
+    _, _, (L3, R3, P3) = hm.load_large_csr(pb)
+    v, ok = capi.mmcheck_batch(pb, mkn, r, L3, R3, P3, seed=11, batch=40)
+    assert v == 0 and ok.all()
+    val = L3[4].copy(); val[777] = (int(val[777]) + 1) % pb
+    v, ok = capi.mmcheck_batch(pb, mkn, r, (L3[0], L3[1], L3[2], L3[3], val), R3, P3, seed=11, batch=40)
+    assert v == 1 and ok.sum() < 40
+
+
+def test_plan_reports_its_encoding(capi):
+    """plo_mmcheck_plan_encoding: on 32x32x32_15096 the block sums cut the X loads per sample at least six-fold, L and R use column
+    blocks, P row blocks of stride n = 32; what the plan computes is unchanged (previous test)."""
+    big = hm.load_large_csr(P31)
+    mkn, r, (L, R, P) = big
+    plan = capi.MMcheckPlan(P31, mkn, r, L, R, P, 64)
+    enc = plan.encoding
+    nnz = [len(x[3]) for x in (L, R, P)]
+    assert all(6 * a < b for a, b in zip(enc["loads"], nnz))
+    assert enc["col_stride"][0] == 1 and enc["col_stride"][1] == 1 and enc["row_stride"] == [0, 0, 32]
+    plan.run(3, 0)
+    v, ok = plan.result()
+    assert v == 0 and ok.all()
+    plan.close()
 
 
 def _trivial_algorithm(m, k, n, rng=None, p=P31):
