@@ -13,13 +13,18 @@
 //   * score = (nnz(Res), #entries of Res not in {0,+-1}, nnz(CoB))  (:863-864), minimised
 //     lexicographically (tricOpCount :914-921), lowest candidate index among ties.
 //
-// Mapping: one WARP per candidate, lane j = column j (n <= 32).  The independent rows are kept
-// as a reduced row echelon basis R (pivots normalised to 1) together with the transformation
-// T (R = T.B), both column-distributed in registers: lane j holds R[.][j] and T[.][j].
-// A row v is reduced with n shuffles (c_i = v[pivot column i], all independent because the
-// basis is *reduced*) + n lazy multiply-adds per lane (exact 96-bit accumulation, one Barrett
-// reduction); accepting a row costs one modular inverse (31 squarings, computed by all lanes)
-// and one rank-1 update of R and T.  Arithmetic: Montgomery residues mod an odd p < 2^31.
+// Mapping: one group of W lanes per candidate, lane j = column j (n <= W <= 32).  The independent
+// rows are kept as a reduced row echelon basis R together with the transformation T (R = T.B),
+// both column-distributed in registers (lane j holds R[.][j] and T[.][j]) and both multiplied by
+// ONE common non-zero scale S instead of being normalised: the kernel never divides.  A row v is
+// reduced with n broadcast loads (c_i = v[pivot column i], all independent because the basis is
+// *reduced*) + n lazy multiply-adds per lane (exact 96-bit accumulation, one reduction):
+// S.vr = S.v - sum c_i (S R_i).  Accepting it with pivot S.pv multiplies the scale by S.pv:
+// S R_i <- (S pv)(S R_i) - (S R_i)[pivot column] (S vr), new row S (S vr)  -- two products under one
+// Montgomery reduction per entry, all independent (round 1 normalised the pivot instead: a Fermat
+// inversion, a serial chain of 38 multiplications, per accepted row; ncu: `wait` 3.5, issue 0.54).
+// The score needs no division either: a coordinate x of a solved row is 0, 1 or -1 iff S.x is 0,
+// S or -S.  Arithmetic: Montgomery residues mod an odd p < 2^31.
 // Rationals are scored modulo p on the device; the host layer recomputes the winner over Q
 // (plo_factorizer, host_api.cpp) and verifies the score.
 #include <algorithm>
@@ -75,34 +80,12 @@ __device__ __forceinline__ uint32_t fs_reduce(const FsAcc& a, const FsParams& P)
   const uint32_t u = (uint32_t)(((unsigned long long)s + (unsigned long long)m * P.p) >> 32);
   return u >= P.p ? u - P.p : u;
 }
-// a^-1 in the Montgomery domain: (aR)^(p-2) (p prime).  For p = 2^31-1 (the prime every rational input is scored with) the exponent
-// 2^31-3 = 4.(2^29-1) + 1 has an addition chain of 30 squarings + 8 multiplications through a^(2^k-1), k = 1,2,4,8,16,24,28,29;
-// any other prime takes plain square and multiply (31 squarings + up to 30 multiplications).  The chain is serial: its length is
-// what the kernel waits for when a pivot is not +-1.
-__device__ __forceinline__ uint32_t mont_sqn(uint32_t a, int n, const FsParams& P) {
-#pragma unroll
-  for (int i = 0; i < n; ++i) a = mont_mul(a, a, P.p, P.pinv);
-  return a;
-}
-__device__ __forceinline__ uint32_t mont_inv(uint32_t a, const FsParams& P) {
-  if (P.p == 0x7FFFFFFFu) {
-    const uint32_t t2 = mont_mul(mont_sqn(a, 1, P), a, P.p, P.pinv);
-    const uint32_t t4 = mont_mul(mont_sqn(t2, 2, P), t2, P.p, P.pinv);
-    const uint32_t t8 = mont_mul(mont_sqn(t4, 4, P), t4, P.p, P.pinv);
-    const uint32_t t16 = mont_mul(mont_sqn(t8, 8, P), t8, P.p, P.pinv);
-    const uint32_t t24 = mont_mul(mont_sqn(t16, 8, P), t8, P.p, P.pinv);
-    const uint32_t t28 = mont_mul(mont_sqn(t24, 4, P), t4, P.p, P.pinv);
-    const uint32_t t29 = mont_mul(mont_sqn(t28, 1, P), a, P.p, P.pinv);
-    return mont_mul(mont_sqn(t29, 2, P), a, P.p, P.pinv);
-  }
-  uint32_t result = P.one, base = a;
-  uint32_t e = P.p - 2;
-  while (e) {
-    if (e & 1u) result = mont_mul(result, base, P.p, P.pinv);
-    base = mont_mul(base, base, P.p, P.pinv);
-    e >>= 1;
-  }
-  return result;
+// (a b + c d) R^-1 mod p for Montgomery residues a, b, c, d <= p: both products under one reduction (a b + c d < 2^63, m p < 2^63)
+__device__ __forceinline__ uint32_t mont_mul2(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t p, uint32_t pinv) {
+  const unsigned long long x = (unsigned long long)a * b + (unsigned long long)c * d;
+  const uint32_t m = (uint32_t)x * pinv;
+  const uint32_t t = (uint32_t)((x + (unsigned long long)m * p) >> 32);  // < 2p
+  return t >= p ? t - p : t;
 }
 
 // Philox digit stream of the row order (same definition as the orbit decode)
@@ -174,12 +157,14 @@ __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams
       }
     }
     __syncwarp();
-    // ---- selection pass: reduced echelon basis R with transformation T, column-distributed ----
+    // ---- selection pass: reduced echelon basis with transformation, column-distributed, kept NEGATED and times the scale S:
+    //      Rj[i] = -S R_i[j], Tj[i] = -S T_i[j]  (additions only in the reduction below) ----
     uint32_t Rj[N], Tj[N];
     int pc[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) { Rj[i] = 0; Tj[i] = 0; pc[i] = 0; }
     int nb = 0;
+    uint32_t S = P.one;
     for (int t = 0; t < P.r; ++t) {
       const bool active = valid && nb < P.n;
       if (!__any_sync(kFull, active)) break;
@@ -188,6 +173,8 @@ __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams
       FsAcc ar, at;
       ar.a0 = ar.a1 = ar.a2 = 0;
       at.a0 = at.a1 = at.a2 = 0;
+      fs_mac(ar, S, v);                         // S v
+      fs_mac(at, S, j == nb ? P.one : 0u);      // S e_nb
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if (i < nb) {
@@ -195,29 +182,26 @@ __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams
           fs_mac(ar, c, Rj[i]);
           fs_mac(at, c, Tj[i]);
         }
-      const uint32_t vr = sub_mod(v, fs_reduce(ar, P), P.p);  // v - sum c_i R_i
+      const uint32_t vr = fs_reduce(ar, P);  // S (v - sum c_i R_i)
       const unsigned nzmask = (__ballot_sync(kFull, active && vr != 0) >> gshift) & kGroupMask;
       const bool accept = nzmask != 0;  // else: dependent on the rows kept so far (or nothing left to do for this group)
-      uint32_t vt = fs_reduce(at, P);
-      vt = sub_mod(j == nb ? P.one : 0u, vt, P.p);  // e_nb - sum c_i T_i
-      // pivot: a coordinate equal to +-1 if there is one (its inverse is itself: no modular inversion), else the first
-      // non-zero one.  The coordinates x of the solved rows do not depend on this choice (x.B = row has one solution).
       if (!__any_sync(kFull, accept)) continue;
-      const unsigned unit = (__ballot_sync(kFull, active && (vr == P.one || vr == P.mone)) >> gshift) & kGroupMask;
-      const int pcn = accept ? __ffs(unit ? unit : nzmask) - 1 : 0;
-      const uint32_t pv = __shfl_sync(kFull, vr, pcn, W);
-      uint32_t ip = pv;
-      if (__any_sync(kFull, accept && !unit)) { const uint32_t inv = mont_inv(pv, P); if (!unit) ip = inv; }
-      const uint32_t wr = mont_mul(vr, ip, P.p, P.pinv), wt = mont_mul(vt, ip, P.p, P.pinv);
+      const uint32_t vt = fs_reduce(at, P);  // S (e_nb - sum c_i T_i)
+      // pivot: the first non-zero coordinate.  The coordinates x of the solved rows do not depend on this choice (x.B = row has one solution).
+      const int pcn = accept ? __ffs(nzmask) - 1 : 0;
+      const uint32_t pv = __shfl_sync(kFull, vr, pcn, W);  // S pv: the scale becomes S (S pv)
+      const uint32_t nvr = vr ? P.p - vr : 0u, nvt = vt ? P.p - vt : 0u;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        const uint32_t f = __shfl_sync(kFull, Rj[i], pcn, W);
+        const uint32_t f = __shfl_sync(kFull, Rj[i], pcn, W);  // -S R_i[pivot column]
         if (accept && i < nb) {
-          Rj[i] = sub_mod(Rj[i], mont_mul(f, wr, P.p, P.pinv), P.p);
-          Tj[i] = sub_mod(Tj[i], mont_mul(f, wt, P.p, P.pinv), P.p);
+          // -S' R_i = (S pv)(-S R_i) - (-S R_i[pcn])(-S vr) = pv Rj[i] + f nvr
+          Rj[i] = mont_mul2(pv, Rj[i], f, nvr, P.p, P.pinv);
+          Tj[i] = mont_mul2(pv, Tj[i], f, nvt, P.p, P.pinv);
         }
-        if (accept && i == nb) { Rj[i] = wr; Tj[i] = wt; pc[i] = pcn; }
+        if (accept && i == nb) { Rj[i] = mont_mul(S, nvr, P.p, P.pinv); Tj[i] = mont_mul(S, nvt, P.p, P.pinv); pc[i] = pcn; }  // -S' w = -S (S vr)
       }
+      if (accept) S = mont_mul(S, pv, P.p, P.pinv);
       if (accept && j == 0 && t != nb) { const unsigned char a = perm[nb]; perm[nb] = perm[t]; perm[t] = a; }  // :793-796
       nb += accept ? 1 : 0;
     }
@@ -233,10 +217,10 @@ __global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams
         ax.a0 = ax.a1 = ax.a2 = 0;
 #pragma unroll
         for (int i = 0; i < N; ++i) fs_mac(ax, Msh[row * kFsStride + pc[i]], Tj[i]);  // rows i >= n of T are zero: no guard needed
-        const uint32_t x = fs_reduce(ax, P);  // coordinate of `row` on the j-th independent row
+        const uint32_t x = fs_reduce(ax, P);  // -S times the coordinate of `row` on the j-th independent row
         const bool nz = j < P.n && x != 0;
         nnz_alt += __popc((__ballot_sync(kFull, nz) >> gshift) & kGroupMask);
-        nno_alt += __popc((__ballot_sync(kFull, nz && x != P.one && x != P.mone) >> gshift) & kGroupMask);
+        nno_alt += __popc((__ballot_sync(kFull, nz && x != S && x != P.p - S) >> gshift) & kGroupMask);  // not +-1: neither -S nor S
       }
     }
     const unsigned long long key = ok ? fs_pack(nnz_alt, nno_alt, nnz_cob) : ~0ull;
