@@ -55,7 +55,8 @@ def build_library(force=False, verbose=False):
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + ccbin + NVCC_FLAGS + (["-x", "cu"] if s.endswith(".cpp") else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        extra = os.environ.get("PLO_NVCC_EXTRA", "").split()  # tuning aid, e.g. -DPLO_MM_WARPS=24
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + extra + (["-x", "cu"] if s.endswith(".cpp") else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         p = subprocess.run(cmd, capture_output=True, text=True)
         with open(o + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + p.stdout + p.stderr)

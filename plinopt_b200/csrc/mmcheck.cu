@@ -264,8 +264,18 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
   unsigned int one;
   asm volatile("mov.u32 %0, 1;" : "=r"(one));
   unsigned slabphase = 0;
+  int4 chn = nitems > 0 ? __ldg(reinterpret_cast<const int4*>(a.chunk + c)) : make_int4(0, 0, 0, 0);  // slab, row0, nrows, bytes
   for (int k = 0; k < nitems; ++k) {
-    const int4 ch = *reinterpret_cast<const int4*>(a.chunk + c);  // slab, row0, nrows, bytes
+#ifdef PLO_MM_NOPREFETCH
+    chn = __ldg(reinterpret_cast<const int4*>(a.chunk + c));
+#endif
+    const int4 ch = chn;
+    {  // descriptor of the next item: loaded a whole blob ahead (an L2 round trip otherwise stalls every warp at every blob)
+      const int cn = c + 1 == a.nchunks ? 0 : c + 1;
+#ifndef PLO_MM_NOPREFETCH
+      if (k + 1 < nitems) chn = __ldg(reinterpret_cast<const int4*>(a.chunk + cn));
+#endif
+    }
     const int stage = k & (kStages - 1);
     if (g != pg || ch.x != ps) {
       mbar_wait(&slabbar, slabphase);
