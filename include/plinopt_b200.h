@@ -277,8 +277,8 @@ int plo_mmcheck_plan_launches(const plo_mmcheck_plan* plan);
 int plo_mmcheck_plan_encoding(const plo_mmcheck_plan* plan, int64_t* loads, int64_t* blob_bytes, int* strides);
 void plo_mmcheck_plan_destroy(plo_mmcheck_plan* plan);
 /* Host-only check (no device needed) of the matrix encoder behind the plans: encodes A the way plan_create does for `groups`
- * sample groups (column block sums, row block sums when row_blocks != 0 -- plans use them for P only --, plain pairs and value
- * groups; see csrc/mmcheck.cu), replays the encoded stream on the CPU for ONE sample and returns y = A.x mod p (x: cols residues,
+ * sample groups (column block sums; when row_blocks != 0 also row block sums and outputs numbered by task with fold lists, the
+ * way plans encode P; plain pairs and value groups; see csrc/mmcheck.cu), replays the encoded stream on the CPU for ONE sample and returns y = A.x mod p (x: cols residues,
  * y: rows).  stats (may be NULL, 9 values): row stride of the row blocks (0: none), column stride of the column blocks (0: none),
  * chunks, blob bytes, plain entries, units of 4 grouped entries, value groups, X loads per sample after encoding, stored
  * (row, slab) tasks. */

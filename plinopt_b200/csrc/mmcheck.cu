@@ -182,12 +182,13 @@ struct SpmmArgs {
   unsigned int p;
   unsigned long long M;   // floor((2^64-1)/p)
   unsigned int c32, c64;  // 2^32 mod p, 2^64 mod p  (one-step reduction when p < 2^31)
-  int rows, xlen, groups, nchunks;  // rows: real + virtual rows of the matrix
+  int rows, xlen, groups, nchunks;  // rows: rows of the output per sample group (folded: the stored tasks of all slabs)
+  int folded;                       // outputs numbered by task over all slabs (P: mm_verify adds them up through its fold lists), else by (slab, row)
   int cstride;                      // column stride of the block sums, 0: the matrix uses none
   const ChunkDesc* chunk;
   const unsigned char* blob;
   const unsigned int* X;    // [groups][xlen][32]
-  unsigned int* out;        // [nslabs][groups][rows][32]
+  unsigned int* out;        // [nslabs][groups][rows][32]; folded: [groups][tasks][32]
   const unsigned int* mul;  // [groups][rows][32] when HAD: out = (A X) o mul  (fused Hadamard step, single-slab matrices)
 };
 
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
     mbar_wait(&full[stage], (k / kStages) & 1);
     const uint32_t hdr = ring + stage * kStageBytes;
     const uint32_t st = hdr + ((ch.z * 8 + 15) & ~15);
-    unsigned int* outp = a.out + (((size_t)ch.x * a.groups + g) * a.rows + ch.y) * 32 + lane;
+    unsigned int* outp = a.out + (((size_t)(a.folded ? 0 : ch.x) * a.groups + g) * a.rows + ch.y) * 32 + lane;  // ch.y: first row / first task of the blob
     const unsigned int* mulp = HAD ? a.mul + ((size_t)g * a.rows + ch.y) * 32 + lane : nullptr;
     // rows of the blob are dealt round-robin: after the block sums they are short and of similar cost, and four blobs are in flight
     for (int cur = warp; cur < ch.z; cur += kConsumerWarps) {
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
         res = reduce96(A, a.p, a.M);
       }
       if (HAD) res = barrett64((unsigned long long)res * mulv, a.p, a.M);
-      outp[(size_t)row * 32] = res;
+      outp[(size_t)(a.folded ? cur : row) * 32] = res;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
@@ -395,51 +396,29 @@ __host__ __device__ __forceinline__ RowBlocks row_blocks(int rows, int rs) {
   return rb;
 }
 
-// bad[b] |= (sum_parts wc[g][o][lane] + its virtual rows != sum_t ua[g][i*k+t][lane] * ub[g][t*n+j][lane])  for o = i*n + j, b = 32 g + lane.
-// One warp per (g, j, block of kVerifyRows values of i), lane = sample: ub[t*n+j] is loaded once for the whole block, and the virtual
-// rows, which P's row blocks share between outputs with the same j (row stride n), once per block instead of once per output.
-constexpr int kVerifyRows = 1;
-__global__ void __launch_bounds__(256) mm_verify_kernel(unsigned int p, unsigned long long M, int m, int k, int n, int batch, int groups, int parts, RowBlocks rb,
-                                                        const unsigned int* __restrict__ wc, const unsigned int* __restrict__ ua,
-                                                        const unsigned int* __restrict__ ub, unsigned int* __restrict__ bad) {
-  const int lane = threadIdx.x & 31;
-  const int nib = (m + kVerifyRows - 1) / kVerifyRows;
-  const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wid >= (size_t)groups * n * nib) return;
-  const int j = (int)(wid % n), ib = (int)((wid / n) % nib), g = (int)(wid / ((size_t)n * nib));
+// bad[b] |= (sum of the partial products of output o != sum_t ua[g][i*k+t][lane] * ub[g][t*n+j][lane])  for o = i*n + j, b = 32 g + lane.
+// The partial products of o -- its row in every slab of P plus the virtual rows of the row blocks it belongs to -- are the tasks
+// fold_idx[fold_ptr[o] .. fold_ptr[o+1]) of wc[g][task][lane]  (the encoder lists only tasks that exist).
+__global__ void mm_verify_kernel(unsigned int p, unsigned long long M, int m, int k, int n, int batch, int groups, int ntasks,
+                                 const int* __restrict__ fold_ptr, const int* __restrict__ fold_idx,
+                                 const unsigned int* __restrict__ wc, const unsigned int* __restrict__ ua, const unsigned int* __restrict__ ub,
+                                 unsigned int* __restrict__ bad) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int mn = m * n;
+  if (e >= (size_t)groups * mn * 32) return;
+  const int lane = (int)(e & 31);
+  const int o = (int)((e >> 5) % mn), g = (int)((e >> 5) / mn), i = o / n, j = o % n;
   const int b = g * 32 + lane;
   if (b >= batch) return;
-  const int i0 = ib * kVerifyRows;
-  Acc96 acc[kVerifyRows];
-#pragma unroll
-  for (int u = 0; u < kVerifyRows; ++u) { acc[u].lo = 0; acc[u].hi = 0; }
-  const unsigned int* pa = ua + ((size_t)g * m * k + (size_t)i0 * k) * 32 + lane;
+  unsigned long long w = 0;
+  const unsigned int* base = wc + (size_t)g * ntasks * 32 + lane;
+  for (int q = fold_ptr[o]; q < fold_ptr[o + 1]; ++q) w += base[(size_t)fold_idx[q] * 32];
+  Acc96 acc;
+  acc.lo = 0; acc.hi = 0;
+  const unsigned int* pa = ua + ((size_t)g * m * k + (size_t)i * k) * 32 + lane;
   const unsigned int* pb = ub + ((size_t)g * k * n + j) * 32 + lane;
-  for (int t = 0; t < k; ++t) {
-    const unsigned int y = pb[(size_t)t * n * 32];
-#pragma unroll
-    for (int u = 0; u < kVerifyRows; ++u)
-      if (i0 + u < m) mac96(acc[u], pa[((size_t)u * k + t) * 32], y);
-  }
-  const int tot = rb.total();
-  const size_t pstride = (size_t)groups * tot * 32;
-  const unsigned int* base = wc + (size_t)g * tot * 32 + lane;
-  int last4 = -2, last16 = -2;
-  unsigned long long w4 = 0, w16 = 0;
-  unsigned int wrong = 0;
-#pragma unroll
-  for (int u = 0; u < kVerifyRows; ++u) {
-    if (i0 + u >= m) break;
-    const int o = (i0 + u) * n + j;
-    const int v4 = rb.rs && o / (4 * rb.rs) * rb.rs < rb.n4 ? rb.rows + blk_id(o, 4, rb.rs) : -1;
-    const int v16 = rb.rs && o / (16 * rb.rs) * rb.rs < rb.n16 ? rb.rows + rb.n4 + blk_id(o, 16, rb.rs) : -1;
-    if (v4 != last4) { w4 = 0; if (v4 >= 0) for (int q = 0; q < parts; ++q) w4 += base[(size_t)q * pstride + (size_t)v4 * 32]; last4 = v4; }
-    if (v16 != last16) { w16 = 0; if (v16 >= 0) for (int q = 0; q < parts; ++q) w16 += base[(size_t)q * pstride + (size_t)v16 * 32]; last16 = v16; }
-    unsigned long long w = w4 + w16;
-    for (int q = 0; q < parts; ++q) w += base[(size_t)q * pstride + (size_t)o * 32];
-    wrong |= barrett64(w, p, M) != reduce96(acc[u], p, M);
-  }
-  if (wrong) atomicOr(bad + b, 1u);
+  for (int t = 0; t < k; ++t) mac96(acc, pa[(size_t)t * 32], pb[(size_t)t * n * 32]);
+  if (barrett64(w, p, M) != reduce96(acc, p, M)) atomicOr(bad + b, 1u);
 }
 
 }  // namespace plo
@@ -452,8 +431,10 @@ struct DevSlabCsr {
   int cstride;   // column stride of the block sums the rows refer to (0: none)
   RowBlocks rb;  // virtual rows (rb.rs = 0: none)
   long long nnz, loads, blob_bytes;  // entries of the CSR / X loads per sample after encoding / bytes of the encoded matrix
+  int folded, ntasks;                // folded: outputs per task, added up through fold_ptr / fold_idx (rows + 1 / entries)
   ChunkDesc* chunk;
   unsigned char* blob;
+  int *fold_ptr, *fold_idx;
 };
 
 struct plo_mmcheck_plan {
@@ -611,12 +592,13 @@ struct Encoded {
   int cstride = 0;
   RowBlocks rb{};
   long long loads = 0, plain = 0, units = 0, heads = 0, tasks = 0;
+  std::vector<int> fold_ptr, fold_idx;  // folded matrices: tasks that add up to every real row
 };
 }  // namespace
 
 // Cuts the CSR into slabs of kSlabCols columns, rewrites the rows of every slab with row and column block sums where that saves
 // loads (see the header comment), cuts every slab into runs of rows of about equal cost and serialises every run as a blob.
-static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bool allow_row_blocks, Encoded* out) {
+static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bool folded, Encoded* out) {
   const int rows = h->rows, nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
   static const int ming = std::max(2, env_int("PLO_MM_MINGROUP", kMinGroup));
   static const int env_cb = env_int("PLO_MM_COLBLOCKS", -1);  // 0: no column block sums; 2^k: force that stride; default: choose
@@ -644,7 +626,7 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
     }
   // ---- row block sums: stride chosen on a sample of blocks of 4 ----
   int rs = 0;
-  if (allow_row_blocks && env_rb != 0 && rows >= 8) {
+  if (folded && env_rb != 0 && rows >= 8) {  // virtual rows need a consumer that folds
     double best = 0;
     for (int cand = 1; 4 * cand <= rows; cand <<= 1) {
       if (env_rb > 0 && cand != env_rb) continue;
@@ -689,6 +671,8 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
   out->cstride = cs;
   // ---- row streams, chunks ----
   std::vector<RowStream> streams((size_t)rb.total());
+  std::vector<int> task_of(folded ? (size_t)nslabs * rb.total() : 0, -1);
+  int ntask = 0;
   for (int s = 0; s < nslabs; ++s) {
     const int ncols = std::min(kSlabCols, h->cols - s * kSlabCols);
     long long total_cost = 0;
@@ -719,7 +703,7 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
       }
       const size_t hdr = ((size_t)n * 8 + 15) & ~(size_t)15;
       ChunkDesc ch;
-      ch.slab = s; ch.row0 = row; ch.nrows = n; ch.bytes = (int)(hdr + (size_t)w * 8);  // every area is a multiple of 16 B (bulk copies)
+      ch.slab = s; ch.row0 = folded ? ntask : row; ch.nrows = n; ch.bytes = (int)(hdr + (size_t)w * 8);  // every area is a multiple of 16 B (bulk copies)
       ch.off = out->blob.size(); ch.pad_ = 0;
       out->blob.resize(out->blob.size() + (size_t)ch.bytes, 0);
       uint2* ho = reinterpret_cast<uint2*>(out->blob.data() + ch.off);
@@ -730,6 +714,7 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
         const RowStream& st = streams[(size_t)(row + q)];
         if (st.words() == 0) continue;
         o += write_row(st, eo, o, (unsigned)q, ho + z);
+        if (folded) task_of[(size_t)s * rb.total() + row + q] = ntask++;
         ++z;
       }
       out->table.push_back(ch);
@@ -737,16 +722,34 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
     }
   }
   (void)nnz;
+  if (folded) {
+    out->fold_ptr.assign(1, 0);
+    for (int o = 0; o < rows; ++o) {
+      const int v4 = rb.rs && o / (4 * rb.rs) * rb.rs < rb.n4 ? rb.rows + blk_id(o, 4, rb.rs) : -1;
+      const int v16 = rb.rs && o / (16 * rb.rs) * rb.rs < rb.n16 ? rb.rows + rb.n4 + blk_id(o, 16, rb.rs) : -1;
+      for (int s = 0; s < nslabs; ++s)
+        for (int e : {o, v4, v16})
+          if (e >= 0 && task_of[(size_t)s * rb.total() + e] >= 0) out->fold_idx.push_back(task_of[(size_t)s * rb.total() + e]);
+      out->fold_ptr.push_back((int)out->fold_idx.size());
+    }
+  }
   return PLO_OK;
 }
 
-static int build_slab_csr(const plo_csr* h, unsigned p, int groups, bool allow_row_blocks, DevSlabCsr* d) {
+static int build_slab_csr(const plo_csr* h, unsigned p, int groups, bool folded, DevSlabCsr* d) {
   d->rows = h->rows; d->cols = h->cols; d->nnz = h->ptr[h->rows];
   d->nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
-  d->chunk = nullptr; d->blob = nullptr; d->nchunks = 0;
+  d->chunk = nullptr; d->blob = nullptr; d->nchunks = 0; d->fold_ptr = nullptr; d->fold_idx = nullptr;
   Encoded enc;
-  const int rc = encode_slab_csr(h, p, groups, sm_count(), allow_row_blocks, &enc);
+  const int rc = encode_slab_csr(h, p, groups, sm_count(), folded, &enc);
   if (rc) return rc;
+  d->folded = folded ? 1 : 0; d->ntasks = (int)enc.tasks;
+  if (folded) {
+    PLO_CUDA(pool_alloc(&d->fold_ptr, sizeof(int) * enc.fold_ptr.size()));
+    PLO_CUDA(pool_alloc(&d->fold_idx, sizeof(int) * std::max<size_t>(enc.fold_idx.size(), 1)));
+    PLO_CUDA(cudaMemcpy(d->fold_ptr, enc.fold_ptr.data(), sizeof(int) * enc.fold_ptr.size(), cudaMemcpyHostToDevice));
+    PLO_CUDA(cudaMemcpy(d->fold_idx, enc.fold_idx.data(), sizeof(int) * enc.fold_idx.size(), cudaMemcpyHostToDevice));
+  }
   d->cstride = enc.cstride; d->rb = enc.rb; d->loads = enc.loads; d->blob_bytes = (long long)enc.blob.size();
   d->nchunks = (int)enc.table.size();
   PLO_CUDA(pool_alloc(&d->chunk, sizeof(ChunkDesc) * enc.table.size()));
@@ -759,13 +762,13 @@ static int build_slab_csr(const plo_csr* h, unsigned p, int groups, bool allow_r
 // Host twin of the consumer side of mm_slab_spmm_kernel + the fold of mm_verify_kernel for ONE sample: y = A x mod p from the
 // encoded blobs.  Used by the CPU tests to check the encoder without a device; `stats` = {row stride, column stride, chunks,
 // blob bytes, plain entries, units, value groups, X loads per sample, stored (row, slab) tasks}.
-static int decode_check(const plo_csr* h, uint32_t p, int groups, int allow_row_blocks, const uint32_t* x, uint32_t* y, long long* stats) {
+static int decode_check(const plo_csr* h, uint32_t p, int groups, int folded, const uint32_t* x, uint32_t* y, long long* stats) {
   Encoded enc;
-  const int rc = encode_slab_csr(h, p, groups, 148, allow_row_blocks != 0, &enc);
+  const int rc = encode_slab_csr(h, p, groups, 148, folded != 0, &enc);
   if (rc) return rc;
   const RowBlocks rb = enc.rb;
   const int nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
-  std::vector<unsigned long long> ext((size_t)nslabs * rb.total(), 0);
+  std::vector<unsigned long long> ext(folded ? (size_t)enc.tasks : (size_t)nslabs * rb.total(), 0);  // the kernel's output array for one sample
   std::vector<unsigned long long> xs((size_t)kVCols);
   int cur_slab = -1;
   for (const ChunkDesc& ch : enc.table) {
@@ -794,19 +797,17 @@ static int decode_check(const plo_csr* h, uint32_t p, int groups, int allow_row_
         un += gh[gi].y;
         A += (unsigned __int128)gh[gi].x * s;
       }
-      if (ch.row0 + (int)rel >= rb.total()) { set_error("mmcheck encoder: row out of range"); return PLO_E_ARG; }
-      ext[(size_t)ch.slab * rb.total() + ch.row0 + rel] = (unsigned long long)(A % p);
+      const size_t oi = folded ? (size_t)ch.row0 + t : (size_t)ch.slab * rb.total() + ch.row0 + rel;
+      if (oi >= ext.size() || (!folded && ch.row0 + (int)rel >= rb.total())) { set_error("mmcheck encoder: output out of range"); return PLO_E_ARG; }
+      ext[oi] = (unsigned long long)(A % p);
     }
   }
   for (int o = 0; o < h->rows; ++o) {
-    const int v4 = rb.rs && o / (4 * rb.rs) * rb.rs < rb.n4 ? rb.rows + blk_id(o, 4, rb.rs) : -1;
-    const int v16 = rb.rs && o / (16 * rb.rs) * rb.rs < rb.n16 ? rb.rows + rb.n4 + blk_id(o, 16, rb.rs) : -1;
     unsigned long long w = 0;
-    for (int s = 0; s < nslabs; ++s) {
-      const unsigned long long* base = ext.data() + (size_t)s * rb.total();
-      w += base[o];
-      if (v4 >= 0) w += base[v4];
-      if (v16 >= 0) w += base[v16];
+    if (folded) {  // what mm_verify_kernel does
+      for (int q = enc.fold_ptr[(size_t)o]; q < enc.fold_ptr[(size_t)o + 1]; ++q) w += ext[(size_t)enc.fold_idx[(size_t)q]];
+    } else {       // what mm_hadamard_kernel does with the slabs of a wide L or R (no virtual rows without a folding consumer)
+      for (int s = 0; s < nslabs; ++s) w += ext[(size_t)s * rb.total() + o];
     }
     y[o] = (uint32_t)(w % p);
   }
@@ -817,7 +818,7 @@ static int decode_check(const plo_csr* h, uint32_t p, int groups, int allow_row_
   return PLO_OK;
 }
 
-static void free_slab_csr(DevSlabCsr* d) { pool_free(d->chunk); pool_free(d->blob); }
+static void free_slab_csr(DevSlabCsr* d) { pool_free(d->chunk); pool_free(d->blob); pool_free(d->fold_ptr); pool_free(d->fold_idx); }
 
 extern "C" {
 
@@ -860,7 +861,7 @@ int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, i
   const size_t stage = (size_t)batch * (size_t)(m * k > k * n ? m * k : k * n);
   auto zalloc = [](unsigned int** ptr, size_t words) { return pool_alloc(ptr, 4 * words) == cudaSuccess && cudaMemset(*ptr, 0, 4 * words) == cudaSuccess; };
   const bool ok = zalloc(&pl->ua, G32 * m * k) && zalloc(&pl->ub, G32 * k * n) && zalloc(&pl->va, G32 * r * pl->L.nslabs) &&
-                  zalloc(&pl->vb, G32 * r * pl->R.nslabs) && zalloc(&pl->vc, G32 * r) && zalloc(&pl->wc, G32 * pl->P.rb.total() * pl->P.nslabs) &&
+                  zalloc(&pl->vb, G32 * r * pl->R.nslabs) && zalloc(&pl->vc, G32 * r) && zalloc(&pl->wc, G32 * std::max(pl->P.ntasks, 1)) &&
                   zalloc(&pl->bad, (size_t)batch) && zalloc(&pl->stage, stage);
   if (!ok) { set_error("mmcheck: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())); plo_mmcheck_plan_destroy(pl); return PLO_E_CUDA; }
   *plan = pl;
@@ -871,7 +872,7 @@ static void launch_spmm(const plo_mmcheck_plan* pl, const DevSlabCsr& A, const u
   SpmmArgs a;
   a.mul = mul;
   a.p = pl->p; a.M = pl->M; a.c32 = (unsigned)((1ull << 32) % pl->p); a.c64 = (unsigned)((unsigned long long)a.c32 * a.c32 % pl->p);
-  a.rows = A.rb.total(); a.xlen = A.cols; a.groups = pl->groups; a.nchunks = A.nchunks; a.cstride = A.cstride;
+  a.rows = A.folded ? A.ntasks : A.rb.total(); a.folded = A.folded; a.xlen = A.cols; a.groups = pl->groups; a.nchunks = A.nchunks; a.cstride = A.cstride;
   a.chunk = A.chunk; a.blob = A.blob; a.X = X; a.out = out;
   const long long T = (long long)pl->groups * A.nchunks;
   if (T == 0) return;  // a matrix without entries: its product is the zero vector the plan allocated
@@ -904,8 +905,8 @@ static int mm_pipeline(plo_mmcheck_plan* pl, cudaStream_t st) {
   mark();
   launch_spmm(pl, pl->P, pl->vc, pl->wc, nullptr, st);
   mark();
-  const size_t vcnt = G32 * pl->n * ((pl->m + kVerifyRows - 1) / kVerifyRows);
-  mm_verify_kernel<<<(unsigned)((vcnt + 255) / 256), 256, 0, st>>>(pl->p, pl->M, pl->m, pl->k, pl->n, B, pl->groups, pl->P.nslabs, pl->P.rb, pl->wc, pl->ua, pl->ub, pl->bad);
+  const size_t vcnt = G32 * pl->m * pl->n;
+  mm_verify_kernel<<<(unsigned)((vcnt + 255) / 256), 256, 0, st>>>(pl->p, pl->M, pl->m, pl->k, pl->n, B, pl->groups, pl->P.ntasks, pl->P.fold_ptr, pl->P.fold_idx, pl->wc, pl->ua, pl->ub, pl->bad);
   mark();
   PLO_CUDA(cudaGetLastError());
   if (timing) {
