@@ -275,6 +275,9 @@ int plo_mmcheck_plan_launches(const plo_mmcheck_plan* plan);
  * blob_bytes[3] = size of the encoded matrix, strides[6] = (column stride of the column block sums, row stride of the row block
  * sums) per matrix, 0 = not used. */
 int plo_mmcheck_plan_encoding(const plo_mmcheck_plan* plan, int64_t* loads, int64_t* blob_bytes, int* strides);
+/* The random coordinates plo_mmcheck_plan_run draws are (Philox word & (2^bits - 1)) mod p, bits = 1..32 (default 32): the same
+ * integer point under every modulus, which is what lets plo_mmchecker decide equality over Q from several primes. */
+int plo_mmcheck_plan_input_bits(plo_mmcheck_plan* plan, int bits);
 void plo_mmcheck_plan_destroy(plo_mmcheck_plan* plan);
 /* Host-only check (no device needed) of the matrix encoder behind the plans: encodes A the way plan_create does for `groups`
  * sample groups (column block sums; when row_blocks != 0 also row block sums and outputs numbered by task with fold lists, the
@@ -423,13 +426,22 @@ int plo_orbiter_progress(int measure, int mode, uint64_t seed, uint64_t loops, i
                          const int64_t* Pd, uint64_t capacity, plo_orbit_best* records, uint64_t* count);
 
 /* fMMchecker + MMchecker  src/MMchecker.cpp:48-81, include/plinopt_library.inl:472-558 on dense
- * rational inputs.  modulus == 0: the reference checks over Q with `bitsize`-bit random inputs; this
- * engine checks modulo the word-size prime 2^31-1 (next prime below if a denominator vanishes),
- * `batch` independent samples.  modulus > 0: factors of 2 are stripped first (:123-126).
+ * rational inputs, `batch` independent random evaluations.
+ * modulus > 0: in Z/pZ, p = modulus without its factors of 2 (:123-126).
+ * modulus == 0: over Q.  The reference evaluates both sides exactly at a random point with `bitsize`-bit integer coordinates
+ * (:497-528); this engine takes the same decision from residues: with D a common multiple of all denominators,
+ * N = D.(P.((L.ua) o (R.ub)) - ua.ub) is an integer vector of known size bound, and the samples are checked modulo as many
+ * word-size primes (2^31-1 downwards, skipping primes that divide a denominator) as it takes for their product to exceed 2|N|:
+ * verdict 0 means both sides are EQUAL OVER Q at every sampled point, verdict 1 that they differ at one of them.
+ * plo_mmchecker uses 32-bit coordinates; plo_mmchecker_bits takes the bit size (1..32, larger values are clamped; the reference's
+ * `-b`) and reports the number of primes it used (*nprimes, may be NULL).
  * Returns 0 correct / 1 not an MM algorithm / 2 inner / 3 outer dimension mismatch / PLO_E_*. */
 int plo_mmchecker(uint64_t modulus, uint64_t seed, int batch, int Lrows, int Lcols, int Rrows, int Rcols, int Prows,
                   int Pcols, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
                   const int64_t* Pn, const int64_t* Pd, uint32_t* nnz_nno /* [2], may be NULL */);
+int plo_mmchecker_bits(uint64_t modulus, int bitsize, uint64_t seed, int batch, int Lrows, int Lcols, int Rrows, int Rcols, int Prows,
+                       int Pcols, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                       const int64_t* Pn, const int64_t* Pd, uint32_t* nnz_nno /* [2], may be NULL */, int* nprimes);
 
 /* The same over Z/qZ (`orbiter -m q`, src/orbiter.cpp:419-426): factors of 2 are stripped from q (:421-422), the
  * matrices are reduced first (:232-234), the search, the acceptance and the final MMchecker run in the field

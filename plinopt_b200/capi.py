@@ -28,8 +28,8 @@ SYMBOLS = [
     "plo_orbit_sweep", "plo_orbit_decode", "plo_orbit_space", "plo_orbit_table", "plo_orbit_plan_create",
     "plo_orbit_table_modp", "plo_orbit_sweep64", "plo_orbit_table64", "plo_orbit_plan_run", "plo_orbit_plan_result", "plo_orbit_plan_launches", "plo_orbit_plan_pack", "plo_orbit_plan_kernel", "plo_orbit_magnitude_bounds", "plo_orbit_plan_survivors", "plo_selftest_matrix_index", "plo_orbit_plan_destroy",
     "plo_growth_G2", "plo_mmcheck_batch", "plo_mmcheck_plan_create", "plo_mmcheck_plan_run",
-    "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_encoding", "plo_mmcheck_encode_check", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
-    "plo_sparsifier", "plo_orbiter", "plo_orbiter_progress", "plo_orbiter_modp", "plo_mmchecker", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
+    "plo_mmcheck_plan_result", "plo_mmcheck_plan_launches", "plo_mmcheck_plan_encoding", "plo_mmcheck_plan_input_bits", "plo_mmcheck_encode_check", "plo_mmcheck_plan_destroy", "plo_measure_peaks", "plo_measure_issue_peak",
+    "plo_sparsifier", "plo_orbiter", "plo_orbiter_progress", "plo_orbiter_modp", "plo_mmchecker", "plo_mmchecker_bits", "plo_LRP2MM", "plo_slp_build", "plo_slp_export", "plo_slp_free",
     "plo_factor_sweep", "plo_factor_decode", "plo_factor_plan_create", "plo_factor_plan_run", "plo_factor_plan_result",
     "plo_factor_plan_launches", "plo_factor_plan_destroy", "plo_factorizer", "plo_dependency_explore", "plo_depender", "plo_negater", "plo_rotater", "plo_growth_factors",
 ]
@@ -632,6 +632,19 @@ def mmchecker(L, R, P, modulus=0, seed=0, batch=32):
     rc = _check(f(modulus, seed, batch, len(L), len(L[0]), len(R), len(R[0]), len(P), len(P[0]), _ptr(Ln), _ptr(Ld), _ptr(Rn), _ptr(Rd),
                   _ptr(Pn), _ptr(Pd), _ptr(cnt)), allow=(1, 2, 3))
     return rc, (int(cnt[0]), int(cnt[1]))
+
+
+def mmchecker_bits(L, R, P, modulus=0, bitsize=32, seed=0, batch=32):
+    """plo_mmchecker_bits: over Q (modulus 0) the decision is exact at every sampled point with `bitsize`-bit integer coordinates.
+    Returns (verdict, (nnz, nno), number of primes used)."""
+    Ln, Ld = _numden(L); Rn, Rd = _numden(R); Pn, Pd = _numden(P)
+    cnt = np.zeros(2, dtype=np.uint32)
+    npr = C.c_int()
+    f = lib().plo_mmchecker_bits
+    f.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_int] + [C.c_int] * 6 + [C.c_void_p] * 7 + [C.POINTER(C.c_int)]
+    rc = _check(f(modulus, bitsize, seed, batch, len(L), len(L[0]), len(R), len(R[0]), len(P), len(P[0]), _ptr(Ln), _ptr(Ld), _ptr(Rn), _ptr(Rd),
+                  _ptr(Pn), _ptr(Pd), _ptr(cnt), C.byref(npr)), allow=(1, 2, 3))
+    return rc, (int(cnt[0]), int(cnt[1])), npr.value
 
 
 def slp_to_csr(text, outchar="o"):

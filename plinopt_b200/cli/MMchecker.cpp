@@ -4,19 +4,21 @@
 #include "cli_common.hpp"
 
 static void usage(const char* prg) {
-  std::clog << "Usage: " << prg << " [-h|-b #|-m/-q #|-r # # #] L.sms R.sms P.sms\n"
-            << "  [-b b]: random check with values of size 'bitsize' (batch of b samples here)\n"
+  std::clog << "Usage: " << prg << " [-h|-b #|-m/-q #|-r # # #|--samples #] L.sms R.sms P.sms\n"
+            << "  [-b b]: random check with values of size 'bitsize' (default 32; at most 32 here)\n"
+            << "  [--samples s]: number of random points checked (default 32; the reference checks one)\n"
             << "  [-m/-q m]: check is modulo (mod) or (mod/2^k) (default no)\n"
             << "  [-r r e s]: check is modulo (r^e-s) or ((r^e-s)/2^k) (default no)\n";
   exit(-1);
 }
 
 int main(int argc, char** argv) {
-  unsigned long long bitsize = 32, modulus = 0, seed = 0x504C494E4F505431ull;
+  unsigned long long bitsize = 32, modulus = 0, seed = 0x504C494E4F505431ull, samples = 32;
   std::vector<std::string> files;
   for (int i = 1; i < argc; ++i) {
     const std::string a(argv[i]);
     if (a == "--seed" && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 0);
+    else if (a == "--samples" && i + 1 < argc) samples = strtoull(argv[++i], nullptr, 10);
     else if (a[0] == '-' && a.size() > 1) {
       if (a[1] == 'h') usage(argv[0]);
       else if (a[1] == 'b' && i + 1 < argc) bitsize = strtoull(argv[++i], nullptr, 10);
@@ -33,9 +35,12 @@ int main(int argc, char** argv) {
   if (!cli::read_file(files[0], L) || !cli::read_file(files[1], R) || !cli::read_file(files[2], P)) return -1;
   const cli::NumDen l = cli::flatten(L), r = cli::flatten(R), p = cli::flatten(P);
   uint32_t cnt[2] = {0, 0};
-  const int batch = (int)(bitsize < 1 ? 1 : (bitsize > 4096 ? 4096 : bitsize));
-  const int v = plo_mmchecker(modulus, seed, batch, l.rows, l.cols, r.rows, r.cols, p.rows, p.cols, l.num.data(), l.den.data(), r.num.data(), r.den.data(),
-                              p.num.data(), p.den.data(), cnt);
+  const int batch = (int)(samples < 1 ? 1 : (samples > 4096 ? 4096 : samples));
+  if (bitsize > 32) std::clog << "# NOTE: -b " << bitsize << ": coordinates of at most 32 bits are drawn here (over Q the verdict is exact at every sampled point either way)" << std::endl;
+  int nprimes = 0;
+  const int v = plo_mmchecker_bits(modulus, (int)(bitsize < 1 ? 1 : (bitsize > 32 ? 32 : bitsize)), seed, batch, l.rows, l.cols, r.rows, r.cols, p.rows, p.cols,
+                                   l.num.data(), l.den.data(), r.num.data(), r.den.data(), p.num.data(), p.den.data(), cnt, &nprimes);
+  if (modulus == 0 && v >= 0 && v <= 1) std::clog << "# over Q: " << batch << " points of " << (bitsize > 32 ? 32 : bitsize) << "-bit coordinates, decided modulo " << nprimes << " word-size prime(s)" << std::endl;
   int m, k, n;
   plo_LRP2MM(l.cols, r.cols, p.rows, &m, &k, &n);
   if (v == 2) std::cerr << "# \033[1;31m****** ERROR, inner dimension mismatch: " << l.rows << "(.)" << r.rows << '|' << p.cols << " ******\033[0m" << std::endl;

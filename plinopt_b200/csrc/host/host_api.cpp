@@ -143,28 +143,93 @@ bool is_prime(uint64_t x) {
   return true;
 }
 
-int mmcheck_dense(uint64_t modulus, uint64_t seed, int batch, const Dense<QField>& L, const Dense<QField>& R, const Dense<QField>& P) {
+// log2 of a common multiple of the denominators of M (the product of the distinct ones) and its absolute row sums
+double denominators_log2(const Dense<QField>& M) {
+  std::vector<int64_t> seen;
+  double lg = 0.;
+  for (const Rat& e : M.v) {
+    if (e.num == 0 || e.den == 1) continue;
+    if (std::find(seen.begin(), seen.end(), e.den) != seen.end()) continue;
+    seen.push_back(e.den);
+    lg += std::log2((double)e.den);
+  }
+  return lg;
+}
+std::vector<double> abs_row_sums(const Dense<QField>& M) {
+  std::vector<double> s(M.rows, 0.);
+  for (size_t i = 0; i < M.rows; ++i)
+    for (size_t j = 0; j < M.cols; ++j) s[i] += std::fabs((double)M.at(i, j).num / (double)M.at(i, j).den);
+  return s;
+}
+
+// One modular check of `batch` samples through a plan; *bad = number of samples that disagree.
+int mmcheck_one_prime(uint64_t p, int bits, uint64_t seed, int batch, int m, int k, int n, const Dense<QField>& L, const plo_csr& vl, const plo_csr& vr,
+                      const plo_csr& vp, int* bad) {
+  plo_mmcheck_plan* plan = nullptr;
+  int rc = plo_mmcheck_plan_create(&plan, (uint32_t)p, m, k, n, (int)L.rows, &vl, &vr, &vp, batch);
+  if (rc) return rc;
+  int verdict = 0;
+  rc = plo_mmcheck_plan_input_bits(plan, bits);
+  if (!rc) rc = plo_mmcheck_plan_run(plan, seed, 0, nullptr);
+  if (!rc) rc = plo_mmcheck_plan_result(plan, nullptr, nullptr, &verdict);
+  plo_mmcheck_plan_destroy(plan);
+  *bad = verdict;
+  return rc;
+}
+
+// fMMchecker / MMchecker on dense rational matrices.
+//  modulus > 0: `batch` random evaluations in Z/pZ, p = modulus without its factors of 2 (src/MMchecker.cpp:123-126).
+//  modulus == 0: the reference evaluates both sides EXACTLY over Q at a random point with `bitsize`-bit integer coordinates and
+//  compares (include/plinopt_library.inl:497-528).  Here: the same test at `batch` random integer points with `bits`-bit coordinates
+//  (bits <= 32), decided by residues: with D a common multiple of all denominators, N = D (P.((L ua) o (R ub)) - ua.ub) is an integer
+//  vector with |N| <= D (max_o sum_i |P_oi| |L_i|_1 |R_i|_1 + k) 2^(2 bits); the check runs modulo as many word-size primes as it takes
+//  for their product to exceed 2 |N|.  All samples agree modulo every prime  =>  N = 0: both sides are EQUAL OVER Q at every point.
+//  One sample disagrees modulo one prime => they differ over Q there (no denominator vanishes modulo the primes used).
+int mmcheck_dense(uint64_t modulus, int bits, uint64_t seed, int batch, const Dense<QField>& L, const Dense<QField>& R, const Dense<QField>& P, int* nprimes = nullptr) {
   int m, k, n;
   plo_LRP2MM((int)L.cols, (int)R.cols, (int)P.rows, &m, &k, &n);
   if (L.rows != R.rows || L.rows != P.cols) return 2;                                                   // MMchecker.cpp:65-71
   if ((int)L.cols != m * k || (int)R.cols != k * n || (int)P.rows != m * n) return 3;                  // library.inl:487-495
+  if (bits < 1) bits = 1;
+  if (bits > 32) bits = 32;
   uint64_t p = modulus;
   if (p > 0) { while ((p % 2) == 0) p >>= 1; if (p == 1) p = 2; }                                      // MMchecker.cpp:123-126
   CsrHost cl, cr, cp;
-  if (p == 0) {
-    for (p = 2147483647ull; p > 2; p -= 2) {
-      if (!is_prime(p)) continue;
-      if (to_csr(L, (int64_t)p, cl) && to_csr(R, (int64_t)p, cr) && to_csr(P, (int64_t)p, cp)) break;
-    }
-  } else {
+  if (p > 0) {
     if (p >= (1ull << 32)) { plo::set_error("mmchecker: modulus must be below 2^32 after stripping factors of 2"); return PLO_E_ARG; }
     if (!(to_csr(L, (int64_t)p, cl) && to_csr(R, (int64_t)p, cr) && to_csr(P, (int64_t)p, cp))) {
       plo::set_error("mmchecker: a denominator is not invertible modulo %llu", (unsigned long long)p);
       return PLO_E_ARG;
     }
+    int bad = 0;
+    const int rc = mmcheck_one_prime(p, bits, seed, batch, m, k, n, L, cl.view((int)L.rows, (int)L.cols), cr.view((int)R.rows, (int)R.cols), cp.view((int)P.rows, (int)P.cols), &bad);
+    if (nprimes) *nprimes = 1;
+    return rc ? rc : bad;
   }
-  const plo_csr vl = cl.view((int)L.rows, (int)L.cols), vr = cr.view((int)R.rows, (int)R.cols), vp = cp.view((int)P.rows, (int)P.cols);
-  return plo_mmcheck_batch((uint32_t)p, m, k, n, (int)L.rows, &vl, &vr, &vp, seed, batch, nullptr, nullptr, nullptr);
+  // over Q: size of the integer N above
+  const std::vector<double> sl = abs_row_sums(L), sr = abs_row_sums(R);
+  double worst = 0.;
+  for (size_t o = 0; o < P.rows; ++o) {
+    double t = 0.;
+    for (size_t i = 0; i < P.cols; ++i) if (P.at(o, i).num != 0) t += std::fabs((double)P.at(o, i).num / (double)P.at(o, i).den) * sl[i] * sr[i];
+    worst = std::max(worst, t);
+  }
+  const double need = denominators_log2(L) + denominators_log2(R) + denominators_log2(P) + std::log2(worst + (double)k + 1.) + 2. * bits + 3.;  // + sign, rounding slack
+  double have = 0.;
+  int used = 0;
+  for (p = 2147483647ull; p > (1ull << 30) && have <= need; p -= 2) {
+    if (!is_prime(p)) continue;
+    if (!(to_csr(L, (int64_t)p, cl) && to_csr(R, (int64_t)p, cr) && to_csr(P, (int64_t)p, cp))) continue;  // a denominator vanishes: next prime
+    int bad = 0;
+    const int rc = mmcheck_one_prime(p, bits, seed, batch, m, k, n, L, cl.view((int)L.rows, (int)L.cols), cr.view((int)R.rows, (int)R.cols), cp.view((int)P.rows, (int)P.cols), &bad);
+    if (rc) return rc;
+    ++used;
+    if (nprimes) *nprimes = used;
+    if (bad) return 1;
+    have += std::log2((double)p);
+  }
+  if (have <= need) { plo::set_error("mmchecker: ran out of primes"); return PLO_E_RANGE; }
+  return 0;
 }
 
 }  // namespace
@@ -500,7 +565,7 @@ int plo_orbiter(int measure, int mode, uint64_t seed, uint64_t loops, int r, int
     }
     rep->improved = improved ? 1 : 0;
     store(Lj, oLn, oLd); store(Rg, oRn, oRd); store(hP, oPn, oPd);
-    rep->mm_verdict = mmcheck_dense(0, seed ^ 0x4D4D636865636Bull, 32, Lj, Rg, hP);  // :355
+    rep->mm_verdict = mmcheck_dense(0, 32, seed ^ 0x4D4D636865636Bull, 32, Lj, Rg, hP);  // :355
     return PLO_OK;
   } catch (const RangeError& e) {
     plo::set_error("plo_orbiter: %s", e.what());
@@ -721,9 +786,31 @@ int plo_mmchecker(uint64_t modulus, uint64_t seed, int batch, int Lrows, int Lco
     if (L.rows != R.rows || L.rows != P.cols) return 2;
     int rc = plo::check_device();
     if (rc) return rc;
-    return mmcheck_dense(modulus, seed, batch, L, R, P);
+    return mmcheck_dense(modulus, 32, seed, batch, L, R, P);
   } catch (const RangeError& e) {
     plo::set_error("plo_mmchecker: %s", e.what());
+    return PLO_E_RANGE;
+  }
+}
+
+int plo_mmchecker_bits(uint64_t modulus, int bitsize, uint64_t seed, int batch, int Lrows, int Lcols, int Rrows, int Rcols, int Prows,
+                       int Pcols, const int64_t* Ln, const int64_t* Ld, const int64_t* Rn, const int64_t* Rd,
+                       const int64_t* Pn, const int64_t* Pd, uint32_t* nnz_nno, int* nprimes) {
+  if (!Ln || !Rn || !Pn || batch < 1 || bitsize < 1 || Lrows < 1 || Lcols < 1 || Rrows < 1 || Rcols < 1 || Prows < 1 || Pcols < 1) {
+    plo::set_error("plo_mmchecker_bits: bad argument");
+    return PLO_E_ARG;
+  }
+  try {
+    QField Q;
+    const Dense<QField> L = load(Q, (size_t)Lrows, (size_t)Lcols, Ln, Ld), R = load(Q, (size_t)Rrows, (size_t)Rcols, Rn, Rd), P = load(Q, (size_t)Prows, (size_t)Pcols, Pn, Pd);
+    if (nnz_nno) { nnz_nno[0] = nnz_nno[1] = 0; count_nonzeroes(L, nnz_nno[0], nnz_nno[1]); count_nonzeroes(R, nnz_nno[0], nnz_nno[1]); count_nonzeroes(P, nnz_nno[0], nnz_nno[1]); }
+    if (nprimes) *nprimes = 0;
+    if (L.rows != R.rows || L.rows != P.cols) return 2;
+    int rc = plo::check_device();
+    if (rc) return rc;
+    return mmcheck_dense(modulus, bitsize, seed, batch, L, R, P, nprimes);
+  } catch (const RangeError& e) {
+    plo::set_error("plo_mmchecker_bits: %s", e.what());
     return PLO_E_RANGE;
   }
 }

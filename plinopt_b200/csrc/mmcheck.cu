@@ -151,9 +151,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                : "memory");
 }
 
-// ua[g][j][lane], ub[g][j][lane] = Philox words mod p; counter = (sample, j / 4, which), key = seed.
+// ua[g][j][lane], ub[g][j][lane] = (Philox words & mask) mod p; counter = (sample, j / 4, which), key = seed.
 // One thread per (sample, quad of coordinates); lanes = samples, so the stores are coalesced.
-__global__ void mm_gen_kernel(unsigned int p, unsigned long long seed, unsigned long long first_sample, int batch, int len_a,
+__global__ void mm_gen_kernel(unsigned int p, unsigned int mask, unsigned long long seed, unsigned long long first_sample, int batch, int len_a,
                               int len_b, unsigned int* __restrict__ ua, unsigned int* __restrict__ ub) {
   const int qa = (len_a + 3) >> 2, qb = (len_b + 3) >> 2;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,7 +167,7 @@ __global__ void mm_gen_kernel(unsigned int p, unsigned long long seed, unsigned 
   uint32_t w[4];
   philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)q, (uint32_t)which, (uint32_t)seed, (uint32_t)(seed >> 32), w);
   unsigned int* dst = (which ? ub : ua) + ((size_t)(b >> 5) * len + (size_t)q * 4) * 32 + (b & 31);
-  for (int t = 0; t < 4 && q * 4 + t < len; ++t) dst[(size_t)t * 32] = w[t] % p;
+  for (int t = 0; t < 4 && q * 4 + t < len; ++t) dst[(size_t)t * 32] = (w[t] & mask) % p;  // the integer point is w & mask: the same for every modulus
 }
 
 // [batch][len] (caller layout) -> [g][len][lane], reduced mod p
@@ -441,6 +441,7 @@ struct plo_mmcheck_plan {
   uint32_t p;
   unsigned long long M;
   int m, k, n, r, batch, groups, grid_cap;
+  uint32_t input_mask;  // the random coordinates are Philox words & input_mask (plo_mmcheck_plan_input_bits)
   DevSlabCsr L, R, P;
   unsigned int *ua, *ub, *va, *vb, *vc, *wc, *bad, *stage;
 };
@@ -852,6 +853,7 @@ int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, i
   memset(pl, 0, sizeof(*pl));
   pl->p = p; pl->M = ~0ull / p; pl->m = m; pl->k = k; pl->n = n; pl->r = r; pl->batch = batch;
   pl->groups = (batch + 31) / 32;
+  pl->input_mask = 0xffffffffu;
   pl->grid_cap = sm_count();
   rc = build_slab_csr(L, p, pl->groups, false, &pl->L);
   if (!rc) rc = build_slab_csr(R, p, pl->groups, false, &pl->R);
@@ -923,8 +925,14 @@ int plo_mmcheck_plan_run(plo_mmcheck_plan* pl, uint64_t seed, uint64_t first_sam
   if (!pl) { set_error("plo_mmcheck_plan_run: null plan"); return PLO_E_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t gthreads = (size_t)pl->batch * ((pl->m * pl->k + 3) / 4 + (pl->k * pl->n + 3) / 4);
-  mm_gen_kernel<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(pl->p, seed, first_sample, pl->batch, pl->m * pl->k, pl->k * pl->n, pl->ua, pl->ub);
+  mm_gen_kernel<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(pl->p, pl->input_mask, seed, first_sample, pl->batch, pl->m * pl->k, pl->k * pl->n, pl->ua, pl->ub);
   return mm_pipeline(pl, st);
+}
+
+int plo_mmcheck_plan_input_bits(plo_mmcheck_plan* pl, int bits) {
+  if (!pl || bits < 1 || bits > 32) { set_error("plo_mmcheck_plan_input_bits: bits must be 1..32"); return PLO_E_ARG; }
+  pl->input_mask = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
+  return PLO_OK;
 }
 
 int plo_mmcheck_plan_encoding(const plo_mmcheck_plan* pl, int64_t* loads, int64_t* blob_bytes, int* strides) {

@@ -104,6 +104,25 @@ def test_mmchecker_driver(capi):
     assert capi.mmchecker(L, [row[:-1] for row in R], P)[0] == 3
 
 
+def test_mmchecker_over_Q_is_exact_at_the_sampled_points(capi):
+    """include/plinopt_library.inl:497-528 evaluates both sides exactly over Q.  The engine decides the same equality from residues modulo
+    enough word-size primes (their product exceeds twice the size of the integer D.(lhs - rhs)): a triple that is a matrix-multiplication
+    algorithm modulo 2^31-1 but NOT over Q -- one entry of P shifted by 2^31-1 -- passes the single-prime check and fails the check over Q."""
+    from fractions import Fraction
+    L, R, P = O.triple("3x4x7_63_rational")
+    v, cnt, npr = capi.mmchecker_bits(L, R, P, bitsize=32, seed=3, batch=64)
+    assert v == 0 and npr >= 3          # 64 + log2(sum |P||L||R|) + log2(denominators) bits need at least three 31-bit primes
+    v8, _, npr8 = capi.mmchecker_bits(L, R, P, bitsize=8, seed=3, batch=64)
+    assert v8 == 0 and 1 <= npr8 < npr  # smaller coordinates, smaller integers, fewer primes
+    P2 = [list(row) for row in P]
+    i, j = next((i, j) for i, row in enumerate(P) for j, x in enumerate(row) if x != 0)
+    P2[i][j] = Fraction(P[i][j]) + (2 ** 31 - 1)
+    assert capi.mmchecker(L, R, P2, modulus=2 ** 31 - 1, batch=64)[0] == 0      # invisible modulo this prime
+    v, _, npr = capi.mmchecker_bits(L, R, P2, bitsize=32, seed=3, batch=64)
+    assert v == 1 and npr >= 2                                                    # the second prime sees it
+    assert capi.mmchecker(L, R, P2, batch=64)[0] == 1                            # plo_mmchecker: the same decision with 32-bit coordinates
+
+
 @pytest.mark.parametrize("name,k,q", [("2x2x2_7_Winograd_L", 0, 0), ("4x4x4_48_rational_L", 0, 0), ("4x4x4_48_rational_R", 20, 0),
                                       ("3x4x7_63_rational_R", 0, 0), ("3x3x3_23_58_L", 12, 0), ("4x4x4_48_rational_L", 0, 513083)])
 def test_factorizer_matches_oracle_pipeline(capi, name, k, q):
