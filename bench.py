@@ -586,7 +586,9 @@ def bench_c5(ctx, steps, warmup, cpu_seconds):
                              "api": "plo_mmcheck_plan_run + plo_mmcheck_plan_result (the CSR triple is uploaded once at plan creation, like the reference's loaded matrices; "
                                     f"plan creation {create_s:.2f} s)"},
                      "roofline": {"bound": "shared-memory wavefronts", "achieved": per_gpu * mac / 1e12, "peak": wave_peak / 1e12, "unit": "T modular MAC/s per GPU",
-                                  "frac": per_gpu * mac / wave_peak, "traffic": (ctx.ncu.get("mm_slab_spmm_kernel") or {}).get("dram_bytes_per_pass"),
+                                  "frac": per_gpu * mac / wave_peak, "traffic": (ctx.ncu.get(f"mmcheck_pass|32x32x32_15096|batch_{batch}") or {}).get("dram_bytes_per_pass"),
+                                  "traffic_note": "DRAM bytes of the five launches of one pass (profiles/ncu_inputs.json): the vectors va, vc and the partial products of P "
+                                                  "(batch x 60 / 60 / 48 KB) exceed the L2 at batch 4096 and make one round trip each",
                                   "kernel": "mm_slab_spmm_kernel x3 (+ gen, verify)",
                                   "peak_source": "one 128 B shared-memory wavefront per multiply-add of the CSR per warp: SMs x 32 lanes x SM clock",
                                   "encoded": {"x_loads_per_sample": sum(enc["loads"]), "csr_entries": nnz, "col_stride": enc["col_stride"], "row_stride": enc["row_stride"],

@@ -120,7 +120,10 @@ constexpr int kFsStride = 33;  // row stride of M in shared memory (words): cand
 // exactly what the comments below say for "the warp" of the W = 32 case; ballots are cut into per-group masks, shuffles use
 // width W, and the data-dependent steps (row dependent / accepted, unit pivot / inversion) are predicated per group.
 template <int N, int W>
-__global__ void __launch_bounds__(kFsThreads) factor_sweep_kernel(const FsParams P, const uint32_t* __restrict__ Mg /* r x 32, Montgomery */,
+#ifndef PLO_FS_MINB
+#define PLO_FS_MINB 1
+#endif
+__global__ void __launch_bounds__(kFsThreads, PLO_FS_MINB) factor_sweep_kernel(const FsParams P, const uint32_t* __restrict__ Mg /* r x 32, Montgomery */,
                                                                   const uint32_t* __restrict__ rownnz_g, unsigned long long lo,
                                                                   unsigned long long hi, Key* __restrict__ block_best,
                                                                   uint32_t* __restrict__ table /* 3 x (hi-lo) or null */) {
