@@ -597,8 +597,8 @@ def bench_c5(ctx, steps, warmup, cpu_seconds):
                                                       "words of X per sample instead of one per CSR entry, so `frac` (CSR multiply-adds against the one-wavefront-per-entry roof) can "
                                                       "exceed 1; wavefront_frac = (X loads + as many wavefronts of 8-byte stream words) x samples / 32 against the same peak"},
                                   "hbm": {"encoded_bytes": sum(enc["blob_bytes"]), "peak_GBs": measured_hbm_peak(),
-                                          "note": "the encoded matrices (3 MB) stay L2-resident; the partial products wc of the 15 slabs of P (batch x 80 KB) are the HBM "
-                                                  "traffic; small batches are latency-bound (slab fill + block sums per launch), not HBM-bound"}}}
+                                          "note": "the encoded matrices (3 MB) stay L2-resident; va, vc and the partial products of P (batch x 60 / 60 / 48 KB) are the HBM "
+                                                  "traffic (1.35 GB per pass at batch 4096 = 1 TB/s); small batches are latency-bound (slab fill + block sums per launch)"}}}
             out[f"batch_{batch}"] = entry
     if ctx.rank == 0 and ctx.world == 1 and cpu_seconds > 0:
         out["cpu_baseline"] = cpu_c5(big, 4 * host_threads(), host_threads())
