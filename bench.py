@@ -334,6 +334,11 @@ def orbit_roofline(ctx, plan, ops_int, ops_fp, cand_per_s, kern_ms, units_per_la
         issue = {"thread_instructions_per_candidate": inst, "achieved": inst * cand_per_s / 1e12, "peak": issue_peak, "frac": inst * cand_per_s / 1e12 / issue_peak,
                  "unit": "T thread-instructions/s", "source": prof["source"]}
         traffic = prof.get("dram_bytes_per_launch")
+        if prof.get("smem_wavefronts_per_candidate") and ctx.clock_peak:
+            wpeak = ctx.clock_peak / 128.0  # T wavefronts/s: one 128 B shared-memory wavefront per SM per clock (clock_peak = SMs x 4 x 32 x clock)
+            w = prof["smem_wavefronts_per_candidate"]
+            issue["shared_memory"] = {"wavefronts_per_candidate": w, "achieved": w * cand_per_s / 1e12, "peak": wpeak, "frac": w * cand_per_s / 1e12 / wpeak,
+                                      "unit": "T wavefronts/s", "note": "the table-driven kernels are bound by issue slots and by shared-memory bandwidth together"}
     hbm_peak = measured_hbm_peak()
     return {"bound": "int32", "achieved": achieved, "peak": peak, "unit": "T int32 ops/s (algorithmic)", "frac": achieved / peak, "traffic": traffic,
             "kernel": plan.kernel, "lanes_per_imad": plan.lanes, "kernel_ms": kern_ms,

@@ -121,22 +121,43 @@ struct CsrHost {
   std::vector<uint32_t> val;
   plo_csr view(int rows, int cols) const { plo_csr c; c.rows = rows; c.cols = cols; c.ptr = ptr.data(); c.col = col.data(); c.val = val.data(); return c; }
 };
+// The non-zero entries of a dense rational matrix, row by row (built once; the check over Q reduces them modulo several primes).
+struct SparseQ {
+  size_t rows = 0, cols = 0;
+  std::vector<int64_t> ptr, num, den;
+  std::vector<int32_t> col;
+  explicit SparseQ(const Dense<QField>& M) : rows(M.rows), cols(M.cols) {
+    ptr.assign(1, 0);
+    for (size_t i = 0; i < M.rows; ++i) {
+      for (size_t j = 0; j < M.cols; ++j) {
+        const Rat& e = M.at(i, j);
+        if (e.num == 0) continue;
+        col.push_back((int32_t)j); num.push_back(e.num); den.push_back(e.den);
+      }
+      ptr.push_back((int64_t)col.size());
+    }
+  }
+};
 // a/b -> a.b^-1 mod p ; returns false if some denominator vanishes mod p
-bool to_csr(const Dense<QField>& M, int64_t p, CsrHost& out) {
+bool to_csr(const SparseQ& M, int64_t p, CsrHost& out) {
   ZpField Z(p);
   out.ptr.assign(1, 0); out.col.clear(); out.val.clear();
+  int64_t last_den = 1, last_inv = 1;  // few distinct denominators: the last inverse is usually the one needed
   for (size_t i = 0; i < M.rows; ++i) {
-    for (size_t j = 0; j < M.cols; ++j) {
-      const Rat& e = M.at(i, j);
-      if (e.num == 0) continue;
-      if (Z.canon(e.den) == 0) return false;
-      const int64_t v = Z.div(Z.canon(e.num), Z.canon(e.den));
-      if (v) { out.col.push_back((int32_t)j); out.val.push_back((uint32_t)v); }
+    for (int64_t t = M.ptr[i]; t < M.ptr[i + 1]; ++t) {
+      const int64_t d = M.den[(size_t)t];
+      if (d != last_den) {
+        if (Z.canon(d) == 0) return false;
+        last_den = d; last_inv = Z.div(1, Z.canon(d));
+      }
+      const int64_t v = Z.mul(Z.canon(M.num[(size_t)t]), last_inv);
+      if (v) { out.col.push_back(M.col[(size_t)t]); out.val.push_back((uint32_t)v); }
     }
     out.ptr.push_back((int64_t)out.col.size());
   }
   return true;
 }
+bool to_csr(const Dense<QField>& M, int64_t p, CsrHost& out) { return to_csr(SparseQ(M), p, out); }
 bool is_prime(uint64_t x) {
   if (x < 2) return false;
   for (uint64_t d = 2; d * d <= x; ++d) if (x % d == 0) return false;
@@ -195,9 +216,10 @@ int mmcheck_dense(uint64_t modulus, int bits, uint64_t seed, int batch, const De
   uint64_t p = modulus;
   if (p > 0) { while ((p % 2) == 0) p >>= 1; if (p == 1) p = 2; }                                      // MMchecker.cpp:123-126
   CsrHost cl, cr, cp;
+  const SparseQ sL(L), sR(R), sP(P);
   if (p > 0) {
     if (p >= (1ull << 32)) { plo::set_error("mmchecker: modulus must be below 2^32 after stripping factors of 2"); return PLO_E_ARG; }
-    if (!(to_csr(L, (int64_t)p, cl) && to_csr(R, (int64_t)p, cr) && to_csr(P, (int64_t)p, cp))) {
+    if (!(to_csr(sL, (int64_t)p, cl) && to_csr(sR, (int64_t)p, cr) && to_csr(sP, (int64_t)p, cp))) {
       plo::set_error("mmchecker: a denominator is not invertible modulo %llu", (unsigned long long)p);
       return PLO_E_ARG;
     }
@@ -219,7 +241,7 @@ int mmcheck_dense(uint64_t modulus, int bits, uint64_t seed, int batch, const De
   int used = 0;
   for (p = 2147483647ull; p > (1ull << 30) && have <= need; p -= 2) {
     if (!is_prime(p)) continue;
-    if (!(to_csr(L, (int64_t)p, cl) && to_csr(R, (int64_t)p, cr) && to_csr(P, (int64_t)p, cp))) continue;  // a denominator vanishes: next prime
+    if (!(to_csr(sL, (int64_t)p, cl) && to_csr(sR, (int64_t)p, cr) && to_csr(sP, (int64_t)p, cp))) continue;  // a denominator vanishes: next prime
     int bad = 0;
     const int rc = mmcheck_one_prime(p, bits, seed, batch, m, k, n, L, cl.view((int)L.rows, (int)L.cols), cr.view((int)R.rows, (int)R.cols), cp.view((int)P.rows, (int)P.cols), &bad);
     if (rc) return rc;
