@@ -210,6 +210,40 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
 __device__ __forceinline__ void sts_u32(uint32_t addr, unsigned int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
 
+// the value groups of a row: pa = first group header (the units follow the headers); adds value x (exact 64-bit sum of X words) per group
+__device__ __forceinline__ void spmm_groups(Acc96& A, uint32_t pa, unsigned ng, uint32_t xl, unsigned int one) {
+  uint32_t un = pa + ((ng + 1) & ~1u) * 8;
+#pragma unroll 1
+  for (const uint32_t ge = pa + ng * 8; pa != ge; pa += 8) {
+    const uint2 h = lds_u64(pa);
+    unsigned long long s0 = 0, s1 = 0;
+#pragma unroll 1
+    for (const uint32_t ue = un + h.y * 16; un != ue; un += 16) {
+      const uint4 cw = lds_u128(un);
+      const unsigned x0 = lds_u32(xl + cw.x);
+      const unsigned x1 = lds_u32(xl + cw.y);
+      const unsigned x2 = lds_u32(xl + cw.z);
+      const unsigned x3 = lds_u32(xl + cw.w);
+      addwide(s0, x0, one);
+      addwide(s1, x1, one);
+      addwide(s0, x2, one);
+      addwide(s1, x3, one);
+    }
+    const unsigned long long s = s0 + s1;  // < 2^45
+    mac96(A, h.x, (unsigned)s);
+    // + value * (s >> 32) * 2^32: lands in bits 32..95
+    const unsigned long long t = (unsigned long long)h.x * (unsigned)(s >> 32) + (A.lo >> 32) + ((unsigned long long)A.hi << 32);
+    A.lo = (A.lo & 0xffffffffull) | (t << 32);
+    A.hi = (unsigned)(t >> 32);
+  }
+}
+template <bool P31>
+__device__ __forceinline__ unsigned int spmm_reduce(const Acc96& A, const SpmmArgs& a) {
+  // p < 2^31 and a2 < 2^15: a2 c64 + a1 c32 + a0 < 2^46 + 2^63 + 2^32 fits 64 bits -> one Barrett step
+  if (P31) return barrett64((unsigned long long)A.hi * a.c64 + (A.lo >> 32) * a.c32 + (unsigned int)A.lo, a.p, a.M);
+  return reduce96(A, a.p, a.M);
+}
+
 // Row descriptor (8 B): {start | np << 16, ng | (row - first row of the blob) << 16}; rows without entries are not stored (their
 // outputs stay at the zeros the plan allocated); row stream, offsets in 8-byte words from `start`, every area 16-byte aligned:
 //   [np plain pairs (byte offset of the virtual column = 128 * column, value); np even, padding = (0, 0)]
@@ -327,41 +361,8 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
         mac96(B, q.w, x1);
       }
       add96(A, B);
-      if (ng) {
-        uint32_t un = pa + ((ng + 1) & ~1u) * 8;
-#pragma unroll 1
-        for (const uint32_t ge = pa + ng * 8; pa != ge; pa += 8) {
-          const uint2 h = lds_u64(pa);
-          unsigned long long s0 = 0, s1 = 0;
-#pragma unroll 1
-          for (const uint32_t ue = un + h.y * 16; un != ue; un += 16) {
-            const uint4 cw = lds_u128(un);
-            const unsigned x0 = lds_u32(xl + cw.x);
-            const unsigned x1 = lds_u32(xl + cw.y);
-            const unsigned x2 = lds_u32(xl + cw.z);
-            const unsigned x3 = lds_u32(xl + cw.w);
-            addwide(s0, x0, one);
-            addwide(s1, x1, one);
-            addwide(s0, x2, one);
-            addwide(s1, x3, one);
-          }
-          const unsigned long long s = s0 + s1;  // < 2^45
-          mac96(A, h.x, (unsigned)s);
-          {  // + value * (s >> 32) * 2^32: lands in bits 32..95
-            const unsigned long long t = (unsigned long long)h.x * (unsigned)(s >> 32) + (A.lo >> 32) + ((unsigned long long)A.hi << 32);
-            A.lo = (A.lo & 0xffffffffull) | (t << 32);
-            A.hi = (unsigned)(t >> 32);
-          }
-        }
-      }
-      unsigned int res;
-      if (P31) {
-        // p < 2^31 and a2 < 2^15: a2 c64 + a1 c32 + a0 < 2^46 + 2^63 + 2^32 fits 64 bits -> one Barrett step
-        const unsigned long long x = (unsigned long long)A.hi * a.c64 + (A.lo >> 32) * a.c32 + (unsigned int)A.lo;
-        res = barrett64(x, a.p, a.M);
-      } else {
-        res = reduce96(A, a.p, a.M);
-      }
+      if (ng) spmm_groups(A, pa, ng, xl, one);
+      unsigned int res = spmm_reduce<P31>(A, a);
       if (HAD) res = barrett64((unsigned long long)res * mulv, a.p, a.M);
       outp[(size_t)(a.folded ? cur : row) * 32] = res;
     }
