@@ -116,6 +116,30 @@ __device__ __forceinline__ unsigned int reduce96(const Acc96& a, unsigned int p,
   return barrett64(((unsigned long long)t << 32) | (unsigned int)a.lo, p, M);
 }
 
+// Montgomery reduction of the 96-bit accumulator, p odd, pinv = -p^-1 mod 2^32:  A 2^-64 mod p  (two steps of 32 bits; A < 2^80).
+// The encoder stores the matrix values times 2^64 mod p (times 2^96 where the product is to come out in Montgomery form), so this
+// IS the reduction of the row sum -- 10 instructions where the Barrett route takes 24.
+__device__ __forceinline__ unsigned int mont_reduce96(const Acc96& a, unsigned int p, unsigned int pinv) {
+  const unsigned int m1 = (unsigned int)a.lo * pinv;
+  const unsigned long long mp1 = (unsigned long long)m1 * p;
+  const unsigned long long s1 = a.lo + mp1;                                              // low 32 bits vanish
+  const unsigned long long t = (s1 >> 32) + ((unsigned long long)(a.hi + (s1 < mp1 ? 1u : 0u)) << 32);  // (A + m1 p) / 2^32 < 2^49
+  const unsigned int m2 = (unsigned int)t * pinv;
+  const unsigned long long mp2 = (unsigned long long)m2 * p;
+  const unsigned long long s2 = t + mp2;
+  const unsigned long long u = (s2 >> 32) + ((unsigned long long)(s2 < mp2 ? 1u : 0u) << 32);            // < p (1 + 2^-17): one subtraction
+  return (unsigned int)(u >= p ? u - p : u);
+}
+// a b 2^-32 mod p for a, b < p (any odd p < 2^32)
+__device__ __forceinline__ unsigned int mont_mul32(unsigned int a, unsigned int b, unsigned int p, unsigned int pinv) {
+  const unsigned long long x = (unsigned long long)a * b;
+  const unsigned int m = (unsigned int)x * pinv;
+  const unsigned long long mp = (unsigned long long)m * p;
+  const unsigned long long s = x + mp;
+  const unsigned long long u = (s >> 32) + ((unsigned long long)(s < mp ? 1u : 0u) << 32);  // < 2p
+  return (unsigned int)(u >= p ? u - p : u);
+}
+
 // ---- mbarrier / TMA bulk copy (PTX ISA 8.x, sm_90+) -------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -181,7 +205,7 @@ __global__ void mm_transpose_kernel(unsigned int p, int batch, int len, const un
 struct SpmmArgs {
   unsigned int p;
   unsigned long long M;   // floor((2^64-1)/p)
-  unsigned int c32, c64;  // 2^32 mod p, 2^64 mod p  (one-step reduction when p < 2^31)
+  unsigned int pinv;      // -p^-1 mod 2^32 (odd p: the stored values carry 2^64, the row sum is reduced by mont_reduce96)
   int rows, xlen, groups, nchunks;  // rows: rows of the output per sample group (folded: the stored tasks of all slabs)
   int folded;                       // outputs numbered by task over all slabs (P: mm_verify adds them up through its fold lists), else by (slab, row)
   int cstride;                      // column stride of the block sums, 0: the matrix uses none
@@ -189,7 +213,8 @@ struct SpmmArgs {
   const unsigned char* blob;
   const unsigned int* X;    // [groups][xlen][32]
   unsigned int* out;        // [nslabs][groups][rows][32]; folded: [groups][tasks][32]
-  const unsigned int* mul;  // [groups][rows][32] when HAD: out = (A X) o mul  (fused Hadamard step, single-slab matrices)
+  const unsigned int* mul;  // [groups][rows][32] when HAD: out = (A X) o mul  (fused Hadamard step, single-slab matrices; odd p: mul holds
+                            // Montgomery forms, i.e. the L product was made with values times 2^96)
 };
 
 // 64-bit sum += x: written as a wide multiply-add by an opaque 1; ptxas fuses two of them into one three-input add with two
@@ -237,11 +262,9 @@ __device__ __forceinline__ void spmm_groups(Acc96& A, uint32_t pa, unsigned ng, 
     A.hi = (unsigned)(t >> 32);
   }
 }
-template <bool P31>
+template <bool MONT>
 __device__ __forceinline__ unsigned int spmm_reduce(const Acc96& A, const SpmmArgs& a) {
-  // p < 2^31 and a2 < 2^15: a2 c64 + a1 c32 + a0 < 2^46 + 2^63 + 2^32 fits 64 bits -> one Barrett step
-  if (P31) return barrett64((unsigned long long)A.hi * a.c64 + (A.lo >> 32) * a.c32 + (unsigned int)A.lo, a.p, a.M);
-  return reduce96(A, a.p, a.M);
+  return MONT ? mont_reduce96(A, a.p, a.pinv) : reduce96(A, a.p, a.M);
 }
 
 // Row descriptor (8 B): {start | np << 16, ng | (row - first row of the blob) << 16}; rows without entries are not stored (their
@@ -250,7 +273,7 @@ __device__ __forceinline__ unsigned int spmm_reduce(const Acc96& A, const SpmmAr
 //   [ng group headers (value, nunits), padded to an even count]
 //   [units: 4 byte offsets each, all groups in order; a group is padded with the plain pairs' help, never inside a unit]
 // Virtual columns of a slab: 0..1023 the columns, 1024 + b the sum over block b of 4 columns, 1280 + b over block b of 16.
-template <bool P31, bool HAD>
+template <bool MONT, bool HAD>
 __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full[kStages], empty[kStages], slabbar;
@@ -362,8 +385,8 @@ __global__ void __launch_bounds__(kSpThreads, 1) mm_slab_spmm_kernel(const SpmmA
       }
       add96(A, B);
       if (ng) spmm_groups(A, pa, ng, xl, one);
-      unsigned int res = spmm_reduce<P31>(A, a);
-      if (HAD) res = barrett64((unsigned long long)res * mulv, a.p, a.M);
+      unsigned int res = spmm_reduce<MONT>(A, a);
+      if (HAD) res = MONT ? mont_mul32(res, mulv, a.p, a.pinv) : barrett64((unsigned long long)res * mulv, a.p, a.M);
       outp[(size_t)(a.folded ? cur : row) * 32] = res;
     }
     __syncwarp();
@@ -442,6 +465,7 @@ struct plo_mmcheck_plan {
   uint32_t p;
   unsigned long long M;
   int m, k, n, r, batch, groups, grid_cap;
+  int mont;             // odd p: the encoded values carry 2^64 (L: 2^96 when the Hadamard step is fused), rows are reduced by mont_reduce96
   uint32_t input_mask;  // the random coordinates are Philox words & input_mask (plo_mmcheck_plan_input_bits)
   DevSlabCsr L, R, P;
   unsigned int *ua, *ub, *va, *vb, *vc, *wc, *bad, *stage;
@@ -455,6 +479,10 @@ static bool csr_valid(const plo_csr* c, uint32_t p) {
   for (long long t = 0; t < nnz; ++t) if (c->col[t] < 0 || c->col[t] >= c->cols || c->val[t] >= p) return false;
   return true;
 }
+
+// 2^e mod p, and -p^-1 mod 2^32 for odd p (Newton iteration)
+static unsigned pow2_mod(int e, unsigned p) { unsigned long long r = 1 % p; for (int i = 0; i < e; ++i) r = (r * 2) % p; return (unsigned)r; }
+static unsigned neg_inv32(unsigned p) { unsigned x = p; for (int i = 0; i < 5; ++i) x *= 2u - p * x; return 0u - x; }
 
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; }
 
@@ -561,7 +589,8 @@ struct RowStream {
   unsigned cost() const { return (unsigned)(24 + 3 * plain.size() + 6 * heads.size() + 5 * units.size()); }
   unsigned loads() const { return (unsigned)(plain.size() + 4 * units.size()); }
 };
-void encode_row(Row& row, int ming, RowStream* out) {
+void encode_row(Row& row, int ming, unsigned long long scale, unsigned p, RowStream* out) {
+  auto sc = [&](unsigned v) { return (unsigned)(scale == 1 ? v : (unsigned long long)v * scale % p); };  // values are stored times `scale`
   std::sort(row.begin(), row.end(), by_val_col);
   for (size_t t = 0; t < row.size();) {
     size_t u = t;
@@ -569,11 +598,11 @@ void encode_row(Row& row, int ming, RowStream* out) {
     size_t n = u - t;
     if ((long long)n >= ming) {
       const size_t nu = n / 4;  // whole units; the up to 3 entries left over become plain pairs
-      out->heads.push_back(make_uint2(row[t].val, (unsigned)nu));
+      out->heads.push_back(make_uint2(sc(row[t].val), (unsigned)nu));
       for (size_t z = 0; z < nu; ++z) out->units.push_back(make_uint4(row[t + 4 * z].col * 128u, row[t + 4 * z + 1].col * 128u, row[t + 4 * z + 2].col * 128u, row[t + 4 * z + 3].col * 128u));
       t += 4 * nu;
     }
-    for (; t < u; ++t) out->plain.push_back(make_uint2(row[t].col * 128u, row[t].val));
+    for (; t < u; ++t) out->plain.push_back(make_uint2(row[t].col * 128u, sc(row[t].val)));
   }
 }
 unsigned write_row(const RowStream& rs, uint2* stream, unsigned o, unsigned rel_row, uint2* desc) {
@@ -600,7 +629,7 @@ struct Encoded {
 
 // Cuts the CSR into slabs of kSlabCols columns, rewrites the rows of every slab with row and column block sums where that saves
 // loads (see the header comment), cuts every slab into runs of rows of about equal cost and serialises every run as a blob.
-static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bool folded, Encoded* out) {
+static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bool folded, unsigned scale, Encoded* out) {
   const int rows = h->rows, nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
   static const int ming = std::max(2, env_int("PLO_MM_MINGROUP", kMinGroup));
   static const int env_cb = env_int("PLO_MM_COLBLOCKS", -1);  // 0: no column block sums; 2^k: force that stride; default: choose
@@ -683,7 +712,7 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
       if (cs) col_blocks(r, ncols, cs, p, scratch, true, nullptr);
       RowStream& st = streams[(size_t)i];
       st = RowStream();
-      encode_row(r, ming, &st);
+      encode_row(r, ming, scale, p, &st);
       if (st.words() > (unsigned)kChunkEnt) { set_error("mmcheck: a row has too many entries inside one %d-column slab", kSlabCols); return PLO_E_ARG; }
       total_cost += st.cost();
       out->tasks += st.words() != 0;
@@ -738,12 +767,12 @@ static int encode_slab_csr(const plo_csr* h, unsigned p, int groups, int nsm, bo
   return PLO_OK;
 }
 
-static int build_slab_csr(const plo_csr* h, unsigned p, int groups, bool folded, DevSlabCsr* d) {
+static int build_slab_csr(const plo_csr* h, unsigned p, int groups, bool folded, unsigned scale, DevSlabCsr* d) {
   d->rows = h->rows; d->cols = h->cols; d->nnz = h->ptr[h->rows];
   d->nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
   d->chunk = nullptr; d->blob = nullptr; d->nchunks = 0; d->fold_ptr = nullptr; d->fold_idx = nullptr;
   Encoded enc;
-  const int rc = encode_slab_csr(h, p, groups, sm_count(), folded, &enc);
+  const int rc = encode_slab_csr(h, p, groups, sm_count(), folded, scale, &enc);
   if (rc) return rc;
   d->folded = folded ? 1 : 0; d->ntasks = (int)enc.tasks;
   if (folded) {
@@ -766,8 +795,11 @@ static int build_slab_csr(const plo_csr* h, unsigned p, int groups, bool folded,
 // blob bytes, plain entries, units, value groups, X loads per sample, stored (row, slab) tasks}.
 static int decode_check(const plo_csr* h, uint32_t p, int groups, int folded, const uint32_t* x, uint32_t* y, long long* stats) {
   Encoded enc;
-  const int rc = encode_slab_csr(h, p, groups, 148, folded != 0, &enc);
+  const bool mont = (p & 1u) != 0;  // as in the plans: values times 2^64, rows reduced by a Montgomery step that divides by 2^64
+  const int rc = encode_slab_csr(h, p, groups, 148, folded != 0, mont ? pow2_mod(64, p) : 1u, &enc);
   if (rc) return rc;
+  unsigned long long inv64 = 1;  // 2^-64 mod p = ((p + 1) / 2)^64
+  if (mont) for (int i = 0; i < 64; ++i) inv64 = inv64 * ((p + 1ull) / 2) % p;
   const RowBlocks rb = enc.rb;
   const int nslabs = (h->cols + kSlabCols - 1) / kSlabCols;
   std::vector<unsigned long long> ext(folded ? (size_t)enc.tasks : (size_t)nslabs * rb.total(), 0);  // the kernel's output array for one sample
@@ -801,7 +833,7 @@ static int decode_check(const plo_csr* h, uint32_t p, int groups, int folded, co
       }
       const size_t oi = folded ? (size_t)ch.row0 + t : (size_t)ch.slab * rb.total() + ch.row0 + rel;
       if (oi >= ext.size() || (!folded && ch.row0 + (int)rel >= rb.total())) { set_error("mmcheck encoder: output out of range"); return PLO_E_ARG; }
-      ext[oi] = (unsigned long long)(A % p);
+      ext[oi] = (unsigned long long)(A % p) * inv64 % p;
     }
   }
   for (int o = 0; o < h->rows; ++o) {
@@ -856,9 +888,12 @@ int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, i
   pl->groups = (batch + 31) / 32;
   pl->input_mask = 0xffffffffu;
   pl->grid_cap = sm_count();
-  rc = build_slab_csr(L, p, pl->groups, false, &pl->L);
-  if (!rc) rc = build_slab_csr(R, p, pl->groups, false, &pl->R);
-  if (!rc) rc = build_slab_csr(P, p, pl->groups, true, &pl->P);  // only mm_verify folds virtual rows
+  pl->mont = (p & 1u) && !getenv("PLO_MM_NOMONT") ? 1 : 0;  // PLO_MM_NOMONT=1: Barrett reductions as for p = 2 (A/B timing)
+  const bool fused_hadamard = L->cols <= kSlabCols && R->cols <= kSlabCols;  // then (L ua) must come out in Montgomery form for the multiplication in R's epilogue
+  const unsigned k64 = pl->mont ? pow2_mod(64, p) : 1u, k96 = pl->mont ? pow2_mod(96, p) : 1u;
+  rc = build_slab_csr(L, p, pl->groups, false, fused_hadamard ? k96 : k64, &pl->L);
+  if (!rc) rc = build_slab_csr(R, p, pl->groups, false, k64, &pl->R);
+  if (!rc) rc = build_slab_csr(P, p, pl->groups, true, k64, &pl->P);  // only mm_verify folds virtual rows
   if (rc) { plo_mmcheck_plan_destroy(pl); return rc; }
   const size_t G32 = (size_t)pl->groups * 32;
   const size_t stage = (size_t)batch * (size_t)(m * k > k * n ? m * k : k * n);
@@ -874,15 +909,14 @@ int plo_mmcheck_plan_create(plo_mmcheck_plan** plan, uint32_t p, int m, int k, i
 static void launch_spmm(const plo_mmcheck_plan* pl, const DevSlabCsr& A, const unsigned int* X, unsigned int* out, const unsigned int* mul, cudaStream_t st) {
   SpmmArgs a;
   a.mul = mul;
-  a.p = pl->p; a.M = pl->M; a.c32 = (unsigned)((1ull << 32) % pl->p); a.c64 = (unsigned)((unsigned long long)a.c32 * a.c32 % pl->p);
+  a.p = pl->p; a.M = pl->M; a.pinv = pl->mont ? neg_inv32(pl->p) : 0u;
   a.rows = A.folded ? A.ntasks : A.rb.total(); a.folded = A.folded; a.xlen = A.cols; a.groups = pl->groups; a.nchunks = A.nchunks; a.cstride = A.cstride;
   a.chunk = A.chunk; a.blob = A.blob; a.X = X; a.out = out;
   const long long T = (long long)pl->groups * A.nchunks;
   if (T == 0) return;  // a matrix without entries: its product is the zero vector the plan allocated
   const int grid = (int)std::min<long long>(T, pl->grid_cap);
-  const bool p31 = pl->p < 0x80000000u;
-  if (p31 && mul) mm_slab_spmm_kernel<true, true><<<grid, kSpThreads, kSpSmem, st>>>(a);
-  else if (p31) mm_slab_spmm_kernel<true, false><<<grid, kSpThreads, kSpSmem, st>>>(a);
+  if (pl->mont && mul) mm_slab_spmm_kernel<true, true><<<grid, kSpThreads, kSpSmem, st>>>(a);
+  else if (pl->mont) mm_slab_spmm_kernel<true, false><<<grid, kSpThreads, kSpSmem, st>>>(a);
   else if (mul) mm_slab_spmm_kernel<false, true><<<grid, kSpThreads, kSpSmem, st>>>(a);
   else mm_slab_spmm_kernel<false, false><<<grid, kSpThreads, kSpSmem, st>>>(a);
 }
