@@ -39,7 +39,7 @@ constexpr int kFsThreads = kFsWarps * 32;
 constexpr int kFsMaxRows = 256;
 
 struct FsParams {
-  uint32_t p, pinv, one, mone;  // pinv = -p^-1 mod 2^32; one / mone = Montgomery forms of +-1
+  uint32_t p, pinv, one, one2;  // pinv = -p^-1 mod 2^32; one = R mod p (Montgomery form of 1), one2 = R^2 mod p (the form M is stored in)
   unsigned long long M64;       // floor((2^64-1)/p)
   int r, n, k;
   unsigned long long seed;
@@ -64,21 +64,18 @@ __device__ __forceinline__ void fs_mac(FsAcc& a, unsigned int x, unsigned int y)
       : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2)
       : "r"(x), "r"(y));
 }
-__device__ __forceinline__ uint32_t fs_barrett(unsigned long long x, uint32_t p, unsigned long long M) {
-  const unsigned long long q = __umul64hi(x, M);
-  unsigned long long r = x - q * p;
-  if (r >= p) r -= p;
-  if (r >= p) r -= p;
-  return (uint32_t)r;
-}
-// sum of products of Montgomery residues -> Montgomery residue of the sum of products
+// The matrix M sits in shared memory times R^2 (R = 2^32), the basis in registers times R: a lazily accumulated sum of products
+// sum m_i x_i carries R^3, and two REDC steps of 32 bits bring it to (sum m_i x_i) R -- the Montgomery form the basis is kept in --
+// in 10 instructions (round 1: two Barrett reductions and one REDC, 51).  A < 33 p^2 < 2^67.
 __device__ __forceinline__ uint32_t fs_reduce(const FsAcc& a, const FsParams& P) {
-  const uint32_t t = fs_barrett(((unsigned long long)a.a2 << 32) | a.a1, P.p, P.M64);
-  const uint32_t s = fs_barrett(((unsigned long long)t << 32) | a.a0, P.p, P.M64);
-  // s = (sum aR.bR) mod p = (sum ab) R^2 ; one REDC brings it back to (sum ab) R
-  const uint32_t m = s * P.pinv;
-  const uint32_t u = (uint32_t)(((unsigned long long)s + (unsigned long long)m * P.p) >> 32);
-  return u >= P.p ? u - P.p : u;
+  const unsigned long long lo = ((unsigned long long)a.a1 << 32) | a.a0;
+  const uint32_t m1 = a.a0 * P.pinv;
+  const unsigned long long mp1 = (unsigned long long)m1 * P.p;
+  const unsigned long long s1 = lo + mp1;                                                                  // low 32 bits vanish
+  const unsigned long long t = (s1 >> 32) + ((unsigned long long)(a.a2 + (s1 < mp1 ? 1u : 0u)) << 32);     // (A + m1 p) / 2^32 < 2^36
+  const uint32_t m2 = (uint32_t)t * P.pinv;
+  const unsigned long long u = (t + (unsigned long long)m2 * P.p) >> 32;                                   // < 2^36 + 2^63: no overflow; u < p (1 + 2^-26)
+  return (uint32_t)(u >= P.p ? u - P.p : u);
 }
 // (a b + c d) R^-1 mod p for Montgomery residues a, b, c, d <= p: both products under one reduction (a b + c d < 2^63, m p < 2^63)
 __device__ __forceinline__ uint32_t mont_mul2(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t p, uint32_t pinv) {
@@ -123,7 +120,7 @@ template <int N, int W>
 #ifndef PLO_FS_MINB
 #define PLO_FS_MINB 1
 #endif
-__global__ void __launch_bounds__(kFsThreads, PLO_FS_MINB) factor_sweep_kernel(const FsParams P, const uint32_t* __restrict__ Mg /* r x 32, Montgomery */,
+__global__ void __launch_bounds__(kFsThreads, PLO_FS_MINB) factor_sweep_kernel(const FsParams P, const uint32_t* __restrict__ Mg /* r x 32, times R^2 */,
                                                                   const uint32_t* __restrict__ rownnz_g, unsigned long long lo,
                                                                   unsigned long long hi, Key* __restrict__ block_best,
                                                                   uint32_t* __restrict__ table /* 3 x (hi-lo) or null */) {
@@ -177,7 +174,7 @@ __global__ void __launch_bounds__(kFsThreads, PLO_FS_MINB) factor_sweep_kernel(c
       ar.a0 = ar.a1 = ar.a2 = 0;
       at.a0 = at.a1 = at.a2 = 0;
       fs_mac(ar, S, v);                         // S v
-      fs_mac(at, S, j == nb ? P.one : 0u);      // S e_nb
+      fs_mac(at, S, j == nb ? P.one2 : 0u);     // S e_nb (times R^2, like the entries of M)
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if (i < nb) {
@@ -268,6 +265,7 @@ static int fs_blocks_per_sm(size_t smem) {
 }
 
 static uint32_t host_to_mont(uint64_t a, uint32_t p) { return (uint32_t)((((unsigned __int128)a) << 32) % p); }
+static uint32_t host_to_mont2(uint64_t a, uint32_t p) { return (uint32_t)((((unsigned __int128)(a % p)) << 64) % p); }  // a R^2 mod p
 
 }  // namespace plo
 
@@ -306,10 +304,10 @@ int plo_factor_plan_create(plo_factor_plan** plan, uint32_t p, int r, int n, int
   uint32_t inv = 1;  // Newton: p * inv == 1 mod 2^32
   for (int i = 0; i < 5; ++i) inv *= 2u - p * inv;
   P.pinv = 0u - inv;
-  P.one = host_to_mont(1, p); P.mone = host_to_mont(p - 1, p);
+  P.one = host_to_mont(1, p); P.one2 = host_to_mont2(1, p);
   std::vector<uint32_t> hM((size_t)r * 32, 0), hn(r, 0);
   for (int i = 0; i < r; ++i)
-    for (int j = 0; j < n; ++j) { hM[(size_t)i * 32 + j] = host_to_mont(M[(size_t)i * n + j], p); hn[i] += M[(size_t)i * n + j] != 0; }
+    for (int j = 0; j < n; ++j) { hM[(size_t)i * 32 + j] = host_to_mont2(M[(size_t)i * n + j], p); hn[i] += M[(size_t)i * n + j] != 0; }
   pl->npad = (n + 3) & ~3;
   switch (pl->npad) {
 #define PLO_FS_CASE(NN) case NN: pl->launch = &fs_launch<NN>; break;
