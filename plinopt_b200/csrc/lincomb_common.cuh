@@ -109,8 +109,10 @@ bool annihilators(const F& f, int n, int nprev, const int64_t* prev, int off, in
 }
 
 
-// Builds the inverse-lookup tables of one problem (residues mod p): a3 = the fourth live row of TM (nullptr / zeros when the block has
-// fewer than four live positions), coef = c canonical residues.  Returns false when some A3_e is not invertible (composite modulus).
+// Builds the inverse-lookup tables of one problem (residues mod an ODD p): a3 = the fourth live row of TM (nullptr / zeros when the block has
+// fewer than four live positions), coef = c canonical residues.  ninv[e] = -A3_e^-1 in MONTGOMERY form (times 2^32 mod p): the kernels get
+// s.(-A3_e^-1) mod p from one REDC of the 64-bit product (inv_lookup_value) instead of a Barrett reduction.  Returns false when some A3_e
+// is not invertible (composite modulus).
 inline bool build_inv_tables(uint32_t p, int m, int mpad, int c, int hbits, const int64_t* a3, const int64_t* coef, uint32_t* out) {
   const int hsize = 1 << hbits;
   plo::host::ZpField f((int64_t)p);
@@ -122,7 +124,7 @@ inline bool build_inv_tables(uint32_t p, int m, int mpad, int c, int hbits, cons
     if (v == 0) { ninv[e] = InvTables::kEmpty; continue; }  // the coordinate does not depend on l
     int64_t iv;
     try { iv = f.inv(v); } catch (const plo::host::RangeError&) { return false; }
-    ninv[e] = (uint32_t)f.neg(iv);
+    ninv[e] = (uint32_t)((((unsigned __int128)(uint64_t)f.neg(iv)) << 32) % p);
   }
   for (int h = 0; h < hsize; ++h) { htab[2 * h] = 0; htab[2 * h + 1] = InvTables::kEmpty; }
   for (int l = 0; l < c; ++l) nextdup[l] = InvTables::kEmpty;
@@ -136,6 +138,14 @@ inline bool build_inv_tables(uint32_t p, int m, int mpad, int c, int hbits, cons
     }
   }
   return true;
+}
+// -p^-1 mod 2^32 (odd p) and the value C_l must have at a coordinate: s . ninv_e . 2^-32 mod p, s < p <= 2^31
+inline uint32_t inv_neg_pinv(uint32_t p) { uint32_t x = p; for (int i = 0; i < 5; ++i) x *= 2u - p * x; return 0u - x; }
+__host__ __device__ __forceinline__ unsigned int inv_lookup_value(unsigned int s, unsigned int ninv, unsigned int p, unsigned int pinv) {
+  const unsigned long long prod = (unsigned long long)s * ninv;
+  const unsigned int mq = (unsigned int)prod * pinv;
+  const unsigned int x = (unsigned int)((prod + (unsigned long long)mq * p) >> 32);  // < 2p; prod + mq p < 2^62 + 2^63
+  return x >= p ? x - p : x;
 }
 inline int inv_hash_bits(int c) { int b = 3; while ((1 << b) < 4 * c) ++b; return b; }
 

@@ -34,6 +34,7 @@ struct QuadDesc {  // one problem; built on the host, read by every kernel
   unsigned long long seed_key;   // weight seed of the first row
   long long cmax;                // max |coef| (exact path: magnitude guard of the functionals)
   unsigned long long m64;        // floor((2^64 - 1) / p) for the Barrett reductions (p > 0)
+  unsigned int pinv, pad_;       // -p^-1 mod 2^32 for the inverse-lookup kernel (odd p)
   unsigned long long inv_off;    // 32-bit word offset of this problem's inverse-lookup tables (mod p, c >= 32)
   int hbits, pad2;
   long long phi0[16];            // annihilator functionals of the rows known before this call, on the live positions
@@ -200,11 +201,7 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDe
         if (ni == InvTables::kEmpty) {
           base += (sum == 0u);
         } else {
-          const unsigned long long prod = (unsigned long long)sum * ni;
-          unsigned long long r = prod - __umul64hi(prod, d.m64) * p;
-          r -= r >= p ? p : 0;
-          r -= r >= p ? p : 0;
-          const unsigned int x = (unsigned int)r;
+          const unsigned int x = inv_lookup_value(sum, ni, p, d.pinv);
           unsigned h = inv_hash(x, d.hbits);
           for (;;) {
             const uint2 ent = htab[h];
@@ -870,7 +867,7 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
   const size_t desc_bytes = ((size_t)nproblems * sizeof(QuadDesc) + 15) / 16 * 16;
   const size_t in_bytes = (stage_i64 * 8 + 15) / 16 * 16;
   // inverse-lookup count kernel: residues mod p <= 2^31, every problem with many coefficients, multi-kernel path
-  bool use_inv = p && p <= 0x80000000u && width == 4 && quad_small_smem(cmaxall, mpad, width) > 200 * 1024 &&
+  bool use_inv = p && (p & 1u) && p <= 0x80000000u && width == 4 && quad_small_smem(cmaxall, mpad, width) > 200 * 1024 &&
                  cminall >= (getenv("PLO_LINCOMB_INV_MINC") ? atoi(getenv("PLO_LINCOMB_INV_MINC")) : 32) && getenv("PLO_LINCOMB_NOINV") == nullptr;
   const size_t inv_bytes = use_inv ? inv_words * 4 : 0;
   const size_t h2d_bytes = desc_bytes + in_bytes + inv_bytes;
@@ -905,6 +902,7 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
     d.seed_key = pack_key(q.init_rl, q.init_cl, kIdxMask);
     d.cmax = P.cmax;
     d.m64 = p ? ~0ull / p : 0;
+    d.pinv = (p & 1u) ? inv_neg_pinv((uint32_t)p) : 0u; d.pad_ = 0;
     if (use_inv) {
       d.hbits = inv_hash_bits(q.c);
       d.inv_off = inv_off;

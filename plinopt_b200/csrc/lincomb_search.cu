@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_kernel(const LcParams<T> p
 struct LcInvParams {
   const unsigned int* inv;   // [b][InvTables::words]
   int hbits, cpad;           // hash bits; c rounded up to a multiple of 4
-  unsigned long long m64;    // floor((2^64-1)/p)
+  unsigned int pinv;         // -p^-1 mod 2^32 (p odd)
 };
 
 template <int MPAD>
@@ -214,11 +214,7 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_inv_kernel(const LcParams<
         if (ni == InvTables::kEmpty) {
           base += (sum == 0u);
         } else {
-          const unsigned long long prod = (unsigned long long)sum * ni;
-          unsigned long long r = prod - __umul64hi(prod, ip.m64) * p;
-          r -= r >= p ? p : 0;
-          r -= r >= p ? p : 0;
-          const unsigned int x = (unsigned int)r;  // the value C_l must have
+          const unsigned int x = inv_lookup_value(sum, ni, p, ip.pinv);  // the value C_l must have
           unsigned h = inv_hash(x, ip.hbits);
           for (;;) {
             const uint2 ent = htab[h];
@@ -638,7 +634,7 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
   // inverse lookup: residues mod p <= 2^31, many coefficients, register-resident path
-  if (p && p <= 0x80000000u && !big && width == 4 && c >= (getenv("PLO_LINCOMB_INV_MINC") ? atoi(getenv("PLO_LINCOMB_INV_MINC")) : 32) &&
+  if (p && (p & 1u) && p <= 0x80000000u && !big && width == 4 && c >= (getenv("PLO_LINCOMB_INV_MINC") ? atoi(getenv("PLO_LINCOMB_INV_MINC")) : 32) &&
       getenv("PLO_LINCOMB_NOINV") == nullptr) {
     pl->hbits = inv_hash_bits(c);
     const size_t words = InvTables::words(mpad, 1 << pl->hbits, c);
@@ -718,7 +714,7 @@ int plo_lincomb_plan_run_range(plo_lincomb_plan* pl, uint64_t prefix_lo, uint64_
   } else if (pl->use_inv) {
     auto prm = fill((uint32_t*)pl->d_tables);
     LcInvParams ip;
-    ip.inv = pl->d_inv; ip.hbits = pl->hbits; ip.cpad = (pl->c + 3) & ~3; ip.m64 = ~0ull / pl->p;
+    ip.inv = pl->d_inv; ip.hbits = pl->hbits; ip.cpad = (pl->c + 3) & ~3; ip.pinv = inv_neg_pinv((uint32_t)pl->p);
     e = launch_lincomb_inv(pl->mpad, grid, pl->inv_smem, st, prm, ip);
   } else if (pl->width == 4) {
     auto prm = fill((uint32_t*)pl->d_tables);
