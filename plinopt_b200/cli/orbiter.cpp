@@ -10,7 +10,7 @@
 
 static void usage(const char* prg, size_t loops) {
   std::clog << "Usage: " << prg << "  [-h|-O/-b #|-m/-q #|-r # # #|-s|-g] L.sms R.sms P.sms\n"
-            << "  [-b b]: random check with values of size 'bitsize' (here: b samples modulo a word-size prime)\n"
+            << "  [-b b]: random check with values of size 'bitsize' (at most 32 here)\n"
             << "  [-m/-q m]: check is modulo (mod) or (mod/2^k) (default no)\n"
             << "  [-r r e s]: check is modulo (r^e-s) or ((r^e-s)/2^k) (default no)\n"
             << "  [-s|-g]: search sparser|lower growth factor (default is sparser)\n"
@@ -32,11 +32,11 @@ int main(int argc, char** argv) {
     else if (a[0] == '-' && a.size() > 1) {
       if (a[1] == 'h') usage(argv[0], loops);
       else if (a[1] == 'b' && i + 1 < argc) {
-        // -b is the bit size of the random rational inputs of the reference's over-Q check (plinopt_library.inl:497-500).  This
-        // engine checks modulo a word-size prime on counter-based residues, so the value is used the way bin/MMchecker uses it:
-        // as the number of independent samples of the check (confidence grows with it, as with the bit size) -- and that is said.
+        // -b is the bit size of the random integer inputs of the reference's over-Q check (plinopt_library.inl:497-500); it is used
+        // the same way here, up to 32 bits: the input triple is checked at 32 random points with b-bit coordinates, exactly over Q
+        // (plo_mmchecker_bits) or modulo -m/-q/-r.
         bitsize = strtoull(argv[++i], nullptr, 10);
-        std::cerr << "# \033[1;33mNOTE: -b " << bitsize << ": the MMchecker runs modulo 2^31-1 (or -m/-q/-r) and uses b as its number of samples\033[0m" << std::endl;
+        std::cerr << "# \033[1;33mNOTE: -b " << bitsize << ": 32 random points with " << (bitsize > 32 ? 32 : bitsize) << "-bit coordinates (at most 32 bits here)\033[0m" << std::endl;
       }
       else if ((a[1] == 'm' || a[1] == 'q') && i + 1 < argc) modulus = strtoull(argv[++i], nullptr, 10);
       else if (a[1] == 'r' && i + 3 < argc) {
@@ -61,8 +61,8 @@ int main(int argc, char** argv) {
   }
   const cli::NumDen l = cli::flatten(L), r = cli::flatten(R), p = cli::flatten(P);
   uint32_t cnt[2];
-  const int v0 = plo_mmchecker(modulus, seed, (int)(bitsize < 1 ? 1 : (bitsize > 4096 ? 4096 : bitsize)), l.rows, l.cols, r.rows, r.cols, p.rows, p.cols, l.num.data(), l.den.data(), r.num.data(), r.den.data(),
-                               p.num.data(), p.den.data(), cnt);  // :251 (result ignored by the reference)
+  const int v0 = plo_mmchecker_bits(modulus, (int)(bitsize < 1 ? 1 : (bitsize > 32 ? 32 : bitsize)), seed, 32, l.rows, l.cols, r.rows, r.cols, p.rows, p.cols, l.num.data(), l.den.data(),
+                                    r.num.data(), r.den.data(), p.num.data(), p.den.data(), cnt, nullptr);  // :251 (result ignored by the reference)
   int m, k, n;
   plo_LRP2MM(l.cols, r.cols, p.rows, &m, &k, &n);
   if (v0 == 0) std::clog << "# \033[1;32mSUCCESS: correct " << m << 'x' << k << 'x' << n << " {" << cnt[0] << ',' << cnt[1] << "} Matrix-Multiplication \033[0m" << std::endl;

@@ -61,6 +61,12 @@ def test_mmchecker_cli_exit_codes(capi, tmp_path):
     assert r.returncode == 1 and "ERROR, not a 2x2x2 MM algorithm" in r.stderr
     w = write_triple(tmp_path, "3x3x3_23_58")
     assert run([s[0], w[1], s[2]]).returncode == 2
+    # -b is the reference's bit size of the random coordinates (src/MMchecker.cpp:95-97), --samples the number of points; over Q the
+    # verdict is exact at those points and the CLI says modulo how many primes it was taken
+    r = run(["-b", "8", "--samples", "5"] + w)
+    assert r.returncode == 0 and "# over Q: 5 points of 8-bit coordinates, decided modulo" in r.stderr
+    r = run(["-b", "64"] + w)
+    assert r.returncode == 0 and "NOTE: -b 64" in r.stderr and "32 points of 32-bit coordinates" in r.stderr
 
 
 def test_factorizer_cli(capi, tmp_path):
@@ -150,13 +156,13 @@ def test_growthfactor_cli(capi, tmp_path):
 
 def test_orbiter_cli_progress_lines_and_bitsize(capi, tmp_path):
     """'# Found opt:' records (src/orbiter.cpp:312-315), deterministic: the successive prefix minima in index order; the last one is the
-    winner of the 'Rdcd. opt' line, every record improves on the one before, and they equal plo_orbiter_progress.  -b is used as the
-    number of samples of the MMchecker and says so."""
+    winner of the 'Rdcd. opt' line, every record improves on the one before, and they equal plo_orbiter_progress.  -b is the bit size of
+    the coordinates of the MMchecker's random points (at most 32) and the NOTE says so."""
     import re
     files = write_triple(tmp_path, "3x3x3_23_58")
     p = subprocess.run([os.path.join(BIN, "orbiter"), "-b", "8", "-O", "300000", "--seed", "5"] + files, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr
-    assert "NOTE: -b 8" in p.stderr
+    assert "NOTE: -b 8: 32 random points with 8-bit coordinates" in p.stderr
     recs = [(float(a), int(b), int(c), int(i)) for a, b, c, i in re.findall(r"# Found opt: ([0-9.]+)[<=][0-9.]+\t\{(\d+),(\d+)\}&\{\d+,\d+\}\t\[(\d+)/gpu\]", p.stderr)]
     assert len(recs) >= 2
     assert all(x[3] < y[3] and (x[1], x[2]) > (y[1], y[2]) for x, y in zip(recs, recs[1:]))
