@@ -147,6 +147,60 @@ __host__ __device__ __forceinline__ unsigned int inv_lookup_value(unsigned int s
   const unsigned int x = (unsigned int)((prod + (unsigned long long)mq * p) >> 32);  // < 2p; prod + mq p < 2^62 + 2^63
   return x >= p ? x - p : x;
 }
+#ifdef __CUDACC__
+// The counting loop of the inverse-lookup kernels for ONE prefix (i, j, k): p0 = T0 row i, p1 = T1 row j (m words each), p2 = &T2[0][k]
+// (stride c words).  Every coordinate costs three loads, two modular additions, one REDC, one hash probe; a hit increments the byte
+// counter of every l with that coefficient value.  Returns the number of coordinates that vanish whatever l is.  The shared-memory
+// tables are addressed through 32-bit shared addresses the caller made opaque (under register pressure ptxas re-derives generic
+// shared pointers -- S2R + LEA -- inside the loop, ncu profiles/ncu_r02_ad_lincomb_inv_final.md), the global rows through running
+// pointers instead of 64-bit index arithmetic per load.
+struct InvShared { uint32_t ninv, htab, nextdup, hist; };  // shared addresses: tables of the problem, byte counters of this thread
+__device__ __forceinline__ unsigned inv_count_prefix(const unsigned int* __restrict__ p0, const unsigned int* __restrict__ p1, const unsigned int* __restrict__ p2,
+                                                     int c, int m, unsigned int p, unsigned int pinv, int hbits, const InvShared sh) {
+  unsigned base = 0;
+  const unsigned hmask = (1u << hbits) - 1u;
+#pragma unroll 2
+  for (int e = 0; e < m; ++e, p2 += c) {
+    unsigned int sum = p0[e] + p1[e];  // p <= 2^31: no overflow
+    sum -= sum >= p ? p : 0u;
+    sum += *p2;
+    sum -= sum >= p ? p : 0u;
+    unsigned int ni;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ni) : "r"(sh.ninv + 4u * (unsigned)e));
+    if (ni == InvTables::kEmpty) {
+      base += (sum == 0u);
+    } else {
+      const unsigned int x = inv_lookup_value(sum, ni, p, pinv);  // the value C_l must have
+      unsigned h = inv_hash(x, hbits);
+      for (;;) {
+        unsigned int ex, ey;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(sh.htab + 8u * h));
+        if (ey == InvTables::kEmpty) break;
+        if (ex == x) {
+          for (unsigned l = ey; l != InvTables::kEmpty;) {
+            unsigned int v;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sh.hist + l));
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(sh.hist + l), "r"(v + 1u) : "memory");
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(l) : "r"(sh.nextdup + 4u * l));
+          }
+          break;
+        }
+        h = (h + 1u) & hmask;
+      }
+    }
+  }
+  return base;
+}
+__device__ __forceinline__ InvShared inv_shared_addresses(const void* ninv, const void* htab, const void* nextdup, const void* hist) {
+  InvShared s;
+  asm volatile("mov.u32 %0, %1;" : "=r"(s.ninv) : "r"((uint32_t)__cvta_generic_to_shared(ninv)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s.htab) : "r"((uint32_t)__cvta_generic_to_shared(htab)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s.nextdup) : "r"((uint32_t)__cvta_generic_to_shared(nextdup)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s.hist) : "r"((uint32_t)__cvta_generic_to_shared(hist)));
+  return s;
+}
+#endif
+
 inline int inv_hash_bits(int c) { int b = 3; while ((1 << b) < 4 * c) ++b; return b; }
 
 }  // namespace plo

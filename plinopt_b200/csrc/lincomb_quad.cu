@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDe
     for (int e = threadIdx.x; e < nw; e += kLcThreads) ninv[e] = src[e];
   }
   __syncthreads();
+  const InvShared sh = inv_shared_addresses(ninv, htab, nextdup, hist);
   const size_t tab = (size_t)c * MPAD;
   const unsigned int* __restrict__ t0 = tables + d.tab_off;
   const unsigned int* __restrict__ t1 = t0 + tab;
@@ -189,32 +190,7 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDe
     const unsigned qq = q / (unsigned)c;
     const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
     for (int w = 0; w < cpad; w += 4) *reinterpret_cast<unsigned int*>(hist + w) = 0u;
-    unsigned base = 0;
-#pragma unroll 2
-    for (int e = 0; e < MPAD; ++e) {
-      if (e < d.m) {
-        unsigned int sum = t0[(size_t)i * MPAD + e] + t1[(size_t)j * MPAD + e];  // p <= 2^31: no overflow
-        sum -= sum >= p ? p : 0u;
-        sum += t2[(size_t)e * c + k];
-        sum -= sum >= p ? p : 0u;
-        const unsigned int ni = ninv[e];
-        if (ni == InvTables::kEmpty) {
-          base += (sum == 0u);
-        } else {
-          const unsigned int x = inv_lookup_value(sum, ni, p, d.pinv);
-          unsigned h = inv_hash(x, d.hbits);
-          for (;;) {
-            const uint2 ent = htab[h];
-            if (ent.y == InvTables::kEmpty) break;
-            if (ent.x == x) {
-              for (unsigned l = ent.y; l != InvTables::kEmpty; l = nextdup[l]) ++hist[l];
-              break;
-            }
-            h = (h + 1) & (unsigned)(hsize - 1);
-          }
-        }
-      }
-    }
+    const unsigned base = inv_count_prefix(t0 + (size_t)i * MPAD, t1 + (size_t)j * MPAD, t2 + k, c, d.m, p, d.pinv, d.hbits, sh);
     unsigned char* out = cnt + (size_t)q * c;
     unsigned mx = 0;  // per-byte maximum of the hit counters
     if (words_ok) {

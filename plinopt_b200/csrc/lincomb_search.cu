@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_inv_kernel(const LcParams<
     for (int e = threadIdx.x; e < nw; e += kLcThreads) ninv[e] = src[e];  // ninv | htab | nextdup are contiguous
   }
   __syncthreads();
+  const InvShared sh = inv_shared_addresses(ninv, htab, nextdup, hist);
   const size_t tab = (size_t)c * MPAD;
   const unsigned int* __restrict__ t0 = prm.t0 + b * tab;
   const unsigned int* __restrict__ t1 = prm.t1 + b * tab;
@@ -199,35 +200,11 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_inv_kernel(const LcParams<
     const unsigned long long qq = q / (unsigned)c;
     const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
     for (int w = 0; w < ip.cpad; w += 4) *reinterpret_cast<unsigned int*>(hist + w) = 0u;
-    int base = 0;  // coordinates that vanish whatever l is
-    // NOT fully unrolled: nothing is kept per coordinate, and 48 copies of the probe loop overflow the instruction cache
-    // (ncu: stall reason no_instruction 7.7 warps per issue with the unrolled body).  A register list of hits instead of the byte
-    // counters was tried and is slower: with Hopcroft-Musinski data hits are common (structured prefixes), not rare.
-#pragma unroll 2
-    for (int e = 0; e < MPAD; ++e) {
-      if (e < prm.m) {
-        unsigned int sum = t0[(size_t)i * MPAD + e] + t1[(size_t)j * MPAD + e];  // p <= 2^31: no overflow
-        sum -= sum >= p ? p : 0u;
-        sum += t2[(size_t)e * c + k];
-        sum -= sum >= p ? p : 0u;
-        const unsigned int ni = ninv[e];
-        if (ni == InvTables::kEmpty) {
-          base += (sum == 0u);
-        } else {
-          const unsigned int x = inv_lookup_value(sum, ni, p, ip.pinv);  // the value C_l must have
-          unsigned h = inv_hash(x, ip.hbits);
-          for (;;) {
-            const uint2 ent = htab[h];
-            if (ent.y == InvTables::kEmpty) break;
-            if (ent.x == x) {
-              for (unsigned l = ent.y; l != InvTables::kEmpty; l = nextdup[l]) ++hist[l];
-              break;
-            }
-            h = (h + 1) & (unsigned)(hsize - 1);
-          }
-        }
-      }
-    }
+    // the counting loop is shared with quad_count_inv_kernel (lincomb_common.cuh).  It is NOT fully unrolled: nothing is kept per
+    // coordinate, and 48 copies of the probe loop overflow the instruction cache (ncu: stall reason no_instruction 7.7 warps per issue
+    // with the unrolled body).  A register list of hits instead of the byte counters was tried and is slower: with Hopcroft-Musinski
+    // data hits are common (structured prefixes), not rare.
+    const int base = (int)inv_count_prefix(t0 + (size_t)i * MPAD, t1 + (size_t)j * MPAD, t2 + k, c, prm.m, p, ip.pinv, ip.hbits, sh);
     const int zc = prm.cl_const + zf[i] + zf[c + j] + zf[2 * c + k];
     int best_rl1 = (int)(best >> 48);
     for (int l0 = 0; l0 < c; l0 += 4) {
