@@ -54,25 +54,36 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b, uint32_t p,
 __device__ __forceinline__ uint32_t sub_mod(uint32_t a, uint32_t b, uint32_t p) { return a >= b ? a - b : a + p - b; }
 
 struct FsAcc {
-  unsigned int a0, a1, a2;
+  unsigned long long lo;  // bits 0..63: one aligned register pair, so that the multiply-add below is a single IMAD.WIDE with carry-out
+  unsigned int hi;        // bits 64..95
 };
 __device__ __forceinline__ void fs_mac(FsAcc& a, unsigned int x, unsigned int y) {
   asm volatile(
-      "mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-      "addc.u32 %2, %2, 0;"
-      : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2)
+      "{\n\t"
+      ".reg .u32 l, h;\n\t"
+      "mov.b64 {l, h}, %0;\n\t"
+      "mad.lo.cc.u32 l, %2, %3, l;\n\t"
+      "madc.hi.cc.u32 h, %2, %3, h;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "mov.b64 %0, {l, h};\n\t"
+      "}"
+      : "+l"(a.lo), "+r"(a.hi)
       : "r"(x), "r"(y));
+}
+__device__ __forceinline__ uint32_t fs_lds(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 // The matrix M sits in shared memory times R^2 (R = 2^32), the basis in registers times R: a lazily accumulated sum of products
 // sum m_i x_i carries R^3, and two REDC steps of 32 bits bring it to (sum m_i x_i) R -- the Montgomery form the basis is kept in --
 // in 10 instructions (round 1: two Barrett reductions and one REDC, 51).  A < 33 p^2 < 2^67.
 __device__ __forceinline__ uint32_t fs_reduce(const FsAcc& a, const FsParams& P) {
-  const unsigned long long lo = ((unsigned long long)a.a1 << 32) | a.a0;
-  const uint32_t m1 = a.a0 * P.pinv;
+  const unsigned long long lo = a.lo;
+  const uint32_t m1 = (uint32_t)a.lo * P.pinv;
   const unsigned long long mp1 = (unsigned long long)m1 * P.p;
   const unsigned long long s1 = lo + mp1;                                                                  // low 32 bits vanish
-  const unsigned long long t = (s1 >> 32) + ((unsigned long long)(a.a2 + (s1 < mp1 ? 1u : 0u)) << 32);     // (A + m1 p) / 2^32 < 2^36
+  const unsigned long long t = (s1 >> 32) + ((unsigned long long)(a.hi + (s1 < mp1 ? 1u : 0u)) << 32);     // (A + m1 p) / 2^32 < 2^36
   const uint32_t m2 = (uint32_t)t * P.pinv;
   const unsigned long long u = (t + (unsigned long long)m2 * P.p) >> 32;                                   // < 2^36 + 2^63: no overflow; u < p (1 + 2^-26)
   return (uint32_t)(u >= P.p ? u - P.p : u);
@@ -139,6 +150,8 @@ __global__ void __launch_bounds__(kFsThreads, PLO_FS_MINB) factor_sweep_kernel(c
   for (int e = threadIdx.x; e < P.r * 32; e += kFsThreads) Msh[(e >> 5) * kFsStride + (e & 31)] = Mg[e];
   for (int e = threadIdx.x; e < P.r; e += kFsThreads) nnzsh[e] = rownnz_g[e];
   __syncthreads();
+  uint32_t msh_a;  // 32-bit shared address of M, opaque: ptxas otherwise re-derives the generic pointer (S2R + LEA) inside the row loops
+  asm volatile("mov.u32 %0, %1;" : "=r"(msh_a) : "r"((uint32_t)__cvta_generic_to_shared(Msh)));
 
   Key best;
   best.primary = ~0ull; best.index = ~0ull;
@@ -160,7 +173,7 @@ __global__ void __launch_bounds__(kFsThreads, PLO_FS_MINB) factor_sweep_kernel(c
     // ---- selection pass: reduced echelon basis with transformation, column-distributed, kept NEGATED and times the scale S:
     //      Rj[i] = -S R_i[j], Tj[i] = -S T_i[j]  (additions only in the reduction below) ----
     uint32_t Rj[N], Tj[N];
-    int pc[N];
+    uint32_t pc[N];  // byte offset of the pivot column inside a row of Msh
 #pragma unroll
     for (int i = 0; i < N; ++i) { Rj[i] = 0; Tj[i] = 0; pc[i] = 0; }
     int nb = 0;
@@ -169,16 +182,17 @@ __global__ void __launch_bounds__(kFsThreads, PLO_FS_MINB) factor_sweep_kernel(c
       const bool active = valid && nb < P.n;
       if (!__any_sync(kFull, active)) break;
       const int row = perm[t];
-      const uint32_t v = Msh[row * kFsStride + j];
+      const uint32_t rowa = msh_a + (uint32_t)row * (kFsStride * 4);  // shared address of the row
+      const uint32_t v = fs_lds(rowa + 4u * (uint32_t)j);
       FsAcc ar, at;
-      ar.a0 = ar.a1 = ar.a2 = 0;
-      at.a0 = at.a1 = at.a2 = 0;
+      ar.lo = 0; ar.hi = 0;
+      at.lo = 0; at.hi = 0;
       fs_mac(ar, S, v);                         // S v
       fs_mac(at, S, j == nb ? P.one2 : 0u);     // S e_nb (times R^2, like the entries of M)
 #pragma unroll
       for (int i = 0; i < N; ++i)
         if (i < nb) {
-          const uint32_t c = Msh[row * kFsStride + pc[i]];  // v[pivot column i]: one address per group (broadcast LDS)
+          const uint32_t c = fs_lds(rowa + pc[i]);  // v[pivot column i]: one address per group (broadcast LDS)
           fs_mac(ar, c, Rj[i]);
           fs_mac(at, c, Tj[i]);
         }
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(kFsThreads, PLO_FS_MINB) factor_sweep_kernel(c
           Rj[i] = mont_mul2(pv, Rj[i], f, nvr, P.p, P.pinv);
           Tj[i] = mont_mul2(pv, Tj[i], f, nvt, P.p, P.pinv);
         }
-        if (accept && i == nb) { Rj[i] = mont_mul(S, nvr, P.p, P.pinv); Tj[i] = mont_mul(S, nvt, P.p, P.pinv); pc[i] = pcn; }  // -S' w = -S (S vr)
+        if (accept && i == nb) { Rj[i] = mont_mul(S, nvr, P.p, P.pinv); Tj[i] = mont_mul(S, nvt, P.p, P.pinv); pc[i] = 4u * (uint32_t)pcn; }  // -S' w = -S (S vr)
       }
       if (accept) S = mont_mul(S, pv, P.p, P.pinv);
       if (accept && j == 0 && t != nb) { const unsigned char a = perm[nb]; perm[nb] = perm[t]; perm[t] = a; }  // :793-796
@@ -214,9 +228,10 @@ __global__ void __launch_bounds__(kFsThreads, PLO_FS_MINB) factor_sweep_kernel(c
         const int row = perm[t];
         if (t < P.k) { nnz_alt += 1; nnz_cob += nnzsh[row]; continue; }  // identity row of Res, row of CoB
         FsAcc ax;
-        ax.a0 = ax.a1 = ax.a2 = 0;
+        ax.lo = 0; ax.hi = 0;
+        const uint32_t rowa = msh_a + (uint32_t)row * (kFsStride * 4);
 #pragma unroll
-        for (int i = 0; i < N; ++i) fs_mac(ax, Msh[row * kFsStride + pc[i]], Tj[i]);  // rows i >= n of T are zero: no guard needed
+        for (int i = 0; i < N; ++i) fs_mac(ax, fs_lds(rowa + pc[i]), Tj[i]);  // rows i >= n of T are zero: no guard needed
         const uint32_t x = fs_reduce(ax, P);  // -S times the coordinate of `row` on the j-th independent row
         const bool nz = j < P.n && x != 0;
         nnz_alt += __popc((__ballot_sync(kFull, nz) >> gshift) & kGroupMask);
