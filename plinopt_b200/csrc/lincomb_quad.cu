@@ -185,26 +185,43 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDe
   unsigned char* __restrict__ cnt = counts + d.cnt_off;
   unsigned char* __restrict__ rmax = cnt + ((size_t)c * c * c * c + 15) / 16 * 16;
   const bool words_ok = (c & 3) == 0;
-  for (unsigned q = blockIdx.x * kLcThreads + threadIdx.x; q < nprefix; q += gridDim.x * kLcThreads) {
-    const int k = (int)(q % (unsigned)c);
-    const unsigned qq = q / (unsigned)c;
-    const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
-    for (int w = 0; w < cpad; w += 4) *reinterpret_cast<unsigned int*>(hist + w) = 0u;
-    const unsigned base = inv_count_prefix(t0 + (size_t)i * MPAD, t1 + (size_t)j * MPAD, t2 + k, c, d.m, p, d.pinv, d.hbits, sh);
-    unsigned char* out = cnt + (size_t)q * c;
-    unsigned mx = 0;  // per-byte maximum of the hit counters
+  const int lane = threadIdx.x & 31, hstride = cpad + 4;
+  const unsigned char* hist_w = hist - (size_t)lane * hstride;  // counters of lane 0 of this warp
+  // The 32 prefixes of a warp are consecutive, so their c counts each form ONE contiguous block of 32 c bytes: the warp stores it
+  // together, lane after lane along the block (coalesced 128 B stores; a thread storing its own row word by word costs 32 sectors
+  // per store instruction).
+  for (unsigned q0 = blockIdx.x * kLcThreads + (threadIdx.x - lane); q0 < nprefix; q0 += gridDim.x * kLcThreads) {
+    const unsigned q = q0 + lane;
+    const bool valid = q < nprefix;
+    unsigned base = 0, mx = 0;  // coordinates that vanish for every l; per-byte maximum of the hit counters
+    if (valid) {
+      const int k = (int)(q % (unsigned)c);
+      const unsigned qq = q / (unsigned)c;
+      const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
+      for (int w = 0; w < cpad; w += 4) *reinterpret_cast<unsigned int*>(hist + w) = 0u;
+      base = inv_count_prefix(t0 + (size_t)i * MPAD, t1 + (size_t)j * MPAD, t2 + k, c, d.m, p, d.pinv, d.hbits, sh);
+    }
     if (words_ok) {
-      const unsigned add = base * 0x01010101u;  // counts stay below 256: at most m <= 64 per candidate
-      for (int w = 0; w < c; w += 4) {
-        const unsigned hw = *reinterpret_cast<const unsigned int*>(hist + w);
-        mx = __vmaxu4(mx, hw);
-        *reinterpret_cast<unsigned int*>(out + w) = hw + add;
+      if (valid) {
+        for (int w = 0; w < c; w += 4) mx = __vmaxu4(mx, *reinterpret_cast<const unsigned int*>(hist + w));
       }
-    } else {
+      __syncwarp();
+      const unsigned rows = min(32u, nprefix - q0), wpr = (unsigned)c >> 2, total = rows * wpr;  // words per row, words of the warp's block
+      unsigned int* outw = reinterpret_cast<unsigned int*>(cnt + (size_t)q0 * c);
+      for (unsigned idx = lane; idx < ((total + 31u) & ~31u); idx += 32) {
+        const unsigned r = min(idx / wpr, rows - 1u), w = idx - (idx / wpr) * wpr;
+        const unsigned add = __shfl_sync(0xffffffffu, base, (int)r) * 0x01010101u;  // counts stay below 256: at most m <= 64 per candidate
+        if (idx < total) outw[idx] = *reinterpret_cast<const unsigned int*>(hist_w + (size_t)r * hstride + 4u * w) + add;
+      }
+      __syncwarp();
+    } else if (valid) {
+      unsigned char* out = cnt + (size_t)q * c;
       for (int l = 0; l < c; ++l) { mx = max(mx, (unsigned)hist[l]); out[l] = (unsigned char)(hist[l] + base); }
     }
-    mx = max(max(mx & 0xFFu, (mx >> 8) & 0xFFu), max((mx >> 16) & 0xFFu, mx >> 24));
-    rmax[q] = (unsigned char)(base + mx);  // largest count of the prefix row: lets the picks skip whole rows
+    if (valid) {
+      mx = max(max(mx & 0xFFu, (mx >> 8) & 0xFFu), max((mx >> 16) & 0xFFu, mx >> 24));
+      rmax[q] = (unsigned char)(base + mx);  // largest count of the prefix row: lets the picks skip whole rows
+    }
   }
 }
 
