@@ -11,7 +11,7 @@
 //                        The annihilator functionals of step num are rebuilt by thread 0 of every block from the winners of the
 //                        previous picks (minors of their images under the initial functionals): no host round trip between rows.
 //
-// One host->device copy (descriptors + TM + Coeffs), six launches, one device->host copy per call, for any number of independent
+// One host->device copy (descriptors + TM + Coeffs), six launches (ten with two-phase picks), one device->host copy per call, for any number of independent
 // problems (the column blocks of blockSparsifier, :710-723, advance in lock step).  Winners are bit-identical to four successive
 // plo_lincomb_search calls (tests/test_gpu_lincomb.py).
 #include <cstdlib>
@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_kernel(const QuadDesc* 
 // One hash probe per coordinate instead of c compares; the c byte counters of a prefix are built in shared memory and stored as words.
 template <int MPAD>
 __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDesc* __restrict__ descs, const unsigned int* __restrict__ tables,
-                                                                    const unsigned int* __restrict__ invtabs, unsigned char* __restrict__ counts) {
+                                                                    const unsigned int* __restrict__ invtabs, unsigned char* __restrict__ counts,
+                                                                    unsigned int* __restrict__ rhist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned int sh_hist[256];  // how many prefix rows of this block have which largest count
   const QuadDesc& d = descs[blockIdx.y];
   const int c = d.c, hsize = 1 << d.hbits, cpad = (c + 3) & ~3;
   const unsigned int p = d.p;
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDe
   uint2* htab = reinterpret_cast<uint2*>(ninv + MPAD);
   unsigned int* nextdup = reinterpret_cast<unsigned int*>(htab + hsize);
   unsigned char* hist = reinterpret_cast<unsigned char*>(nextdup + c) + (size_t)threadIdx.x * (cpad + 4);
+  for (int e = threadIdx.x; e < 256; e += kLcThreads) sh_hist[e] = 0u;
   {
     const unsigned int* src = invtabs + d.inv_off;
     const int nw = (int)InvTables::words(MPAD, hsize, c);
@@ -221,8 +224,12 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDe
     if (valid) {
       mx = max(max(mx & 0xFFu, (mx >> 8) & 0xFFu), max((mx >> 16) & 0xFFu, mx >> 24));
       rmax[q] = (unsigned char)(base + mx);  // largest count of the prefix row: lets the picks skip whole rows
+      atomicAdd(&sh_hist[(base + mx) & 0xFFu], 1u);
     }
   }
+  __syncthreads();
+  if (rhist)  // per problem: the picks start from the level the best rows are at instead of climbing there
+    for (int e = threadIdx.x; e < 256; e += kLcThreads) if (sh_hist[e]) atomicAdd(rhist + (size_t)blockIdx.y * 256 + e, sh_hist[e]);
 }
 
 // ---- annihilator functionals of step `num` from the winners of the previous picks --------------------------------------------
@@ -272,6 +279,7 @@ __device__ __forceinline__ void ring_init(QuadRing<true>& R, const QuadDesc& d) 
 //   t = 0: e_0..e_3            t = 1: u_a e_b - u_b e_a, a < b (6)
 //   t = 2: the cross products of (u_0, u_1) restricted to three coordinates (4)      t = 3: the cross product of u_0, u_1, u_2 (1)
 constexpr int kMaxPhi = 6;
+constexpr unsigned int kTopRows = 512;  // phase 1 of a pick looks at (at least) this many best prefix rows
 constexpr int kPrepWords = 16 + 12 + 12 + 6 + 4 * kMaxPhi;  // Psi | winners | u | 2x2 minors | psi
 __device__ __forceinline__ int minor_index(int a, int b) { return a == 0 ? b - 1 : (a == 1 ? b + 1 : 5); }  // a < b: 01 02 03 12 13 23
 
@@ -397,7 +405,12 @@ __device__ __noinline__ bool quad_independent(const long long* phi, int nphi, co
 template <bool MODP>
 __global__ void __launch_bounds__(kPickThreads) quad_pick_kernel(const QuadDesc* __restrict__ descs, const long long* __restrict__ stage,
                                                                  const unsigned char* __restrict__ zflags, const unsigned char* __restrict__ counts,
-                                                                 unsigned long long* __restrict__ results, int* __restrict__ status, int num) {
+                                                                 unsigned long long* __restrict__ results, int* __restrict__ status, int num,
+                                                                 const unsigned int* __restrict__ rhist, int phase) {
+  // phase 0: the whole pick.  With the histogram of the row maxima (inverse-lookup path) a pick is two launches: phase 1 looks only at
+  // the rows whose largest count is among the kTopRows best -- the maximum over the independent candidates is found there unless every
+  // candidate of those rows depends on the rows chosen so far -- and phase 2, the whole pick, returns at once when phase 1 published
+  // a winner (a winner with count >= the floor IS the maximum: everything at or above the floor was looked at).
   __shared__ long long sh_phi[4 * kMaxPhi];
   __shared__ int sh_nphi, sh_stop;
   __shared__ unsigned long long red[32];
@@ -405,6 +418,7 @@ __global__ void __launch_bounds__(kPickThreads) quad_pick_kernel(const QuadDesc*
   const int b = blockIdx.y;
   const QuadDesc& d = descs[b];
   if (num >= d.npick) return;
+  if (phase == 2 && *reinterpret_cast<volatile unsigned long long*>(results + b * 4 + num) > (num == 0 ? d.seed_key : pack_key(-1, -1, kIdxMask))) return;
   const int c = d.c;
   const unsigned long long N4 = (unsigned long long)c * c * c * c;
   const unsigned long long nchunks = (N4 + 15) / 16;
@@ -436,8 +450,18 @@ __global__ void __launch_bounds__(kPickThreads) quad_pick_kernel(const QuadDesc*
     // (Tried: reading everything -- thread per row, lane per word of a shared row, rows staged through shared memory: 1.1-1.9 ms
     // per pick at c = 128, latency-bound at ~1 TB/s with the few warps this register-heavy kernel keeps resident.)
     __shared__ int sh_best_rl1;
-    if (threadIdx.x == 0) sh_best_rl1 = best_rl1;
+    if (threadIdx.x == 0) {
+      int floor1 = best_rl1;
+      if (phase == 1) {
+        unsigned int seen = 0;
+        int v = 255;
+        for (; v > 0; --v) { seen += rhist[(size_t)b * 256 + v]; if (seen >= kTopRows) break; }
+        floor1 = max(floor1, v + 1);  // rows whose largest count is below v are not looked at in this phase
+      }
+      sh_best_rl1 = floor1;
+    }
     __syncthreads();
+    if (phase == 1) best_rl1 = max(best_rl1, sh_best_rl1);
     const unsigned nprefix = (unsigned)c * c * c;
     const unsigned char* __restrict__ bytes = counts + d.cnt_off;
     const unsigned char* __restrict__ rmax = bytes + (N4 + 15) / 16 * 16;
@@ -756,7 +780,7 @@ static cudaError_t launch_quad_count(int mpad, dim3 grid, size_t smem, cudaStrea
 }
 
 static cudaError_t launch_quad_count_inv(int mpad, dim3 grid, size_t smem, cudaStream_t st, const QuadDesc* descs, const uint32_t* tables, const unsigned int* inv,
-                                         unsigned char* counts) {
+                                         unsigned char* counts, unsigned int* rhist) {
 #define PLO_QI_CASE(MP)                                                                                       \
   case MP: {                                                                                                  \
     auto kern = quad_count_inv_kernel<MP>;                                                                    \
@@ -764,7 +788,7 @@ static cudaError_t launch_quad_count_inv(int mpad, dim3 grid, size_t smem, cudaS
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
       if (e != cudaSuccess) return e;                                                                         \
     }                                                                                                         \
-    kern<<<grid, kLcThreads, smem, st>>>(descs, tables, inv, counts);                                         \
+    kern<<<grid, kLcThreads, smem, st>>>(descs, tables, inv, counts, rhist);                                  \
     break;                                                                                                    \
   }
   switch (mpad) {
@@ -867,7 +891,8 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
   const size_t zf_off0 = h2d_bytes;
   const size_t res_off = zf_off0 + zf_bytes;
   const size_t status_off = res_off + (size_t)nproblems * 4 * 8;
-  const size_t stage_total = status_off + ((size_t)nproblems * 4 + 15) / 16 * 16;
+  const size_t rhist_off = status_off + ((size_t)nproblems * 4 + 15) / 16 * 16;  // [nproblems][256] histogram of the row maxima (inverse-lookup path)
+  const size_t stage_total = rhist_off + (size_t)nproblems * 256 * 4;
   const size_t res_bytes = (size_t)nproblems * 4 * 8 + (size_t)nproblems * 4;
   if (!Q.st) PLO_CUDA(cudaStreamCreateWithFlags(&Q.st, cudaStreamNonBlocking));
   cudaError_t e = grow_pinned(&Q.h_stage, &Q.h_cap, h2d_bytes);
@@ -952,6 +977,7 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
       quad_tables_kernel<uint64_t, false><<<tg, 256, 0, st>>>(dd, dstage, (uint64_t*)Q.d_tables, dzf, dres, dstatus);
     }
   }
+  unsigned int* drhist = nullptr;  // set when the count kernel leaves the histogram of the row maxima
   {
     const int ltile = cmaxall < max_rows ? cmaxall : max_rows;
     const size_t smem = (size_t)ltile * mpad * width;
@@ -961,7 +987,9 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
       const unsigned int* dinv = reinterpret_cast<const unsigned int*>(Q.d_stage + desc_bytes + in_bytes);
       const unsigned long long pb = ((unsigned long long)cmaxall * cmaxall * cmaxall + kLcThreads - 1) / kLcThreads;
       const dim3 ig((unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(pb, (unsigned long long)sms * 8ull)), nproblems);
-      e = launch_quad_count_inv(mpad, ig, inv_smem, st, dd, (const uint32_t*)Q.d_tables, dinv, Q.d_counts);
+      drhist = reinterpret_cast<unsigned int*>(Q.d_stage + rhist_off);
+      e = cudaMemsetAsync(drhist, 0, (size_t)nproblems * 256 * 4, st);
+      if (e == cudaSuccess) e = launch_quad_count_inv(mpad, ig, inv_smem, st, dd, (const uint32_t*)Q.d_tables, dinv, Q.d_counts, drhist);
     } else
     if (width == 4) e = p ? launch_quad_count<uint32_t, true>(mpad, cg, smem, st, dd, (const uint32_t*)Q.d_tables, Q.d_counts, max_rows)
                           : launch_quad_count<uint32_t, false>(mpad, cg, smem, st, dd, (const uint32_t*)Q.d_tables, Q.d_counts, max_rows);
@@ -972,8 +1000,12 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
     const unsigned long long blocks = (max_chunks + kPickThreads - 1) / kPickThreads;
     const dim3 pg((unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(blocks, (unsigned long long)sms * 4ull)), nproblems);
     for (int num = 0; num < 4; ++num) {
-      if (p) quad_pick_kernel<true><<<pg, kPickThreads, 0, st>>>(dd, dstage, dzf, Q.d_counts, dres, dstatus, num);
-      else quad_pick_kernel<false><<<pg, kPickThreads, 0, st>>>(dd, dstage, dzf, Q.d_counts, dres, dstatus, num);
+      if (drhist) {  // the best rows first (one wave of blocks), then the whole pick, which returns at once when the first found its winner
+        const dim3 pa(std::min<unsigned>(pg.x, (unsigned)sms), nproblems);
+        if (p) { quad_pick_kernel<true><<<pa, kPickThreads, 0, st>>>(dd, dstage, dzf, Q.d_counts, dres, dstatus, num, drhist, 1); quad_pick_kernel<true><<<pg, kPickThreads, 0, st>>>(dd, dstage, dzf, Q.d_counts, dres, dstatus, num, drhist, 2); }
+        else { quad_pick_kernel<false><<<pa, kPickThreads, 0, st>>>(dd, dstage, dzf, Q.d_counts, dres, dstatus, num, drhist, 1); quad_pick_kernel<false><<<pg, kPickThreads, 0, st>>>(dd, dstage, dzf, Q.d_counts, dres, dstatus, num, drhist, 2); }
+      } else if (p) quad_pick_kernel<true><<<pg, kPickThreads, 0, st>>>(dd, dstage, dzf, Q.d_counts, dres, dstatus, num, nullptr, 0);
+      else quad_pick_kernel<false><<<pg, kPickThreads, 0, st>>>(dd, dstage, dzf, Q.d_counts, dres, dstatus, num, nullptr, 0);
     }
     PLO_CUDA(cudaGetLastError());
   }
