@@ -37,6 +37,7 @@ def time_case(M, q, c, reps=50, blocksize=4):
 if __name__ == "__main__":
     capi.set_device(0)
     for stem, x, q, c in [("2x2x2_7_DPS-smallrat-12.2034", 0, 0, 4), ("4x4x4_48_rational", 0, 2147483647, 11), ("4x4x4_48_rational", 0, 0, 11),
-                          ("3x4x7_63_rational", 1, 0, 11), ("4x4x4_48_rational", 0, 2147483647, 40), ("4x4x4_48_rational", 0, 2147483647, 128)]:
+                          ("3x4x7_63_rational", 1, 0, 11), ("4x4x4_48_rational", 0, 2147483647, 40), ("4x4x4_48_rational", 0, 2147483647, 128),
+                          ("4x4x4_48_rational", 0, 0, 40)]:
         M = hm.load_fixture(stem)[x]
         print(json.dumps(dict(case=f"{stem}_{'LRP'[x]} -q {q} -c {c}", **time_case(M, q, c, reps=50 if c < 100 else 5))))
