@@ -110,9 +110,11 @@ bool annihilators(const F& f, int n, int nprev, const int64_t* prev, int off, in
 
 
 // Builds the inverse-lookup tables of one problem (residues mod an ODD p): a3 = the fourth live row of TM (nullptr / zeros when the block has
-// fewer than four live positions), coef = c canonical residues.  ninv[e] = -A3_e^-1 in MONTGOMERY form (times 2^32 mod p): the kernels get
-// s.(-A3_e^-1) mod p from one REDC of the 64-bit product (inv_lookup_value) instead of a Barrett reduction.  Returns false when some A3_e
-// is not invertible (composite modulus).
+// fewer than four live positions), coef = c canonical residues.  ninv[e] = -A3_e^-1 mod p, or kEmpty when A3_e = 0.  The product tables T0, T1,
+// T2 of a plan that uses the lookup are PRE-MULTIPLIED by ninv[e] (fold_inv_into_tables on the host, quad_tables_kernel on the device), so
+// the value C_l must have at coordinate e is just T0[i][e] + T1[j][e] + T2[e][k] mod p: no multiplication per (prefix, coordinate); the
+// kernels read ninv[e] only to tell the coordinates that do not depend on l.  Returns false when some A3_e is not invertible (composite
+// modulus).
 inline bool build_inv_tables(uint32_t p, int m, int mpad, int c, int hbits, const int64_t* a3, const int64_t* coef, uint32_t* out) {
   const int hsize = 1 << hbits;
   plo::host::ZpField f((int64_t)p);
@@ -124,7 +126,7 @@ inline bool build_inv_tables(uint32_t p, int m, int mpad, int c, int hbits, cons
     if (v == 0) { ninv[e] = InvTables::kEmpty; continue; }  // the coordinate does not depend on l
     int64_t iv;
     try { iv = f.inv(v); } catch (const plo::host::RangeError&) { return false; }
-    ninv[e] = (uint32_t)((((unsigned __int128)(uint64_t)f.neg(iv)) << 32) % p);
+    ninv[e] = (uint32_t)f.neg(iv);
   }
   for (int h = 0; h < hsize; ++h) { htab[2 * h] = 0; htab[2 * h + 1] = InvTables::kEmpty; }
   for (int l = 0; l < c; ++l) nextdup[l] = InvTables::kEmpty;
@@ -139,24 +141,28 @@ inline bool build_inv_tables(uint32_t p, int m, int mpad, int c, int hbits, cons
   }
   return true;
 }
-// -p^-1 mod 2^32 (odd p) and the value C_l must have at a coordinate: s . ninv_e . 2^-32 mod p, s < p <= 2^31
-inline uint32_t inv_neg_pinv(uint32_t p) { uint32_t x = p; for (int i = 0; i < 5; ++i) x *= 2u - p * x; return 0u - x; }
-__host__ __device__ __forceinline__ unsigned int inv_lookup_value(unsigned int s, unsigned int ninv, unsigned int p, unsigned int pinv) {
-  const unsigned long long prod = (unsigned long long)s * ninv;
-  const unsigned int mq = (unsigned int)prod * pinv;
-  const unsigned int x = (unsigned int)((prod + (unsigned long long)mq * p) >> 32);  // < 2p; prod + mq p < 2^62 + 2^63
-  return x >= p ? x - p : x;
+// T0, T1 ([c][mpad]) and T2 ([m][c], transposed) of one problem times ninv[e] where the coordinate depends on l
+inline void fold_inv_into_tables(uint32_t p, int m, int mpad, int c, const uint32_t* ninv, uint32_t* t0, uint32_t* t1, uint32_t* t2) {
+  for (int e = 0; e < m; ++e) {
+    const uint64_t ni = ninv[e];
+    if (ni == InvTables::kEmpty) continue;
+    for (int l = 0; l < c; ++l) {
+      t0[(size_t)l * mpad + e] = (uint32_t)(t0[(size_t)l * mpad + e] * ni % p);
+      t1[(size_t)l * mpad + e] = (uint32_t)(t1[(size_t)l * mpad + e] * ni % p);
+      t2[(size_t)e * c + l] = (uint32_t)(t2[(size_t)e * c + l] * ni % p);
+    }
+  }
 }
 #ifdef __CUDACC__
 // The counting loop of the inverse-lookup kernels for ONE prefix (i, j, k): p0 = T0 row i, p1 = T1 row j (m words each), p2 = &T2[0][k]
-// (stride c words).  Every coordinate costs three loads, two modular additions, one REDC, one hash probe; a hit increments the byte
+// (stride c words), all three pre-multiplied by ninv.  Every coordinate costs three loads, two modular additions, one hash probe; a hit increments the byte
 // counter of every l with that coefficient value.  Returns the number of coordinates that vanish whatever l is.  The shared-memory
 // tables are addressed through 32-bit shared addresses the caller made opaque (under register pressure ptxas re-derives generic
 // shared pointers -- S2R + LEA -- inside the loop, ncu profiles/ncu_r02_ad_lincomb_inv_final.md), the global rows through running
 // pointers instead of 64-bit index arithmetic per load.
 struct InvShared { uint32_t ninv, htab, nextdup, hist; };  // shared addresses: tables of the problem, byte counters of this thread
 __device__ __forceinline__ unsigned inv_count_prefix(const unsigned int* __restrict__ p0, const unsigned int* __restrict__ p1, const unsigned int* __restrict__ p2,
-                                                     int c, int m, unsigned int p, unsigned int pinv, int hbits, const InvShared sh) {
+                                                     int c, int m, unsigned int p, int hbits, const InvShared sh) {
   unsigned base = 0;
   const unsigned hmask = (1u << hbits) - 1u;
 #pragma unroll 2
@@ -170,7 +176,7 @@ __device__ __forceinline__ unsigned inv_count_prefix(const unsigned int* __restr
     if (ni == InvTables::kEmpty) {
       base += (sum == 0u);
     } else {
-      const unsigned int x = inv_lookup_value(sum, ni, p, pinv);  // the value C_l must have
+      const unsigned int x = sum;  // the value C_l must have (the tables carry the factor -A3_e^-1)
       unsigned h = inv_hash(x, hbits);
       for (;;) {
         unsigned int ex, ey;

@@ -34,7 +34,6 @@ struct QuadDesc {  // one problem; built on the host, read by every kernel
   unsigned long long seed_key;   // weight seed of the first row
   long long cmax;                // max |coef| (exact path: magnitude guard of the functionals)
   unsigned long long m64;        // floor((2^64 - 1) / p) for the Barrett reductions (p > 0)
-  unsigned int pinv, pad_;       // -p^-1 mod 2^32 for the inverse-lookup kernel (odd p)
   unsigned long long inv_off;    // 32-bit word offset of this problem's inverse-lookup tables (mod p, c >= 32)
   int hbits, pad2;
   long long phi0[16];            // annihilator functionals of the rows known before this call, on the live positions
@@ -46,7 +45,8 @@ constexpr int kPickThreads = 256;
 // ---- tables -----------------------------------------------------------------------------------------------------------
 template <typename T, bool MODP>
 __global__ void __launch_bounds__(256) quad_tables_kernel(const QuadDesc* __restrict__ descs, const long long* __restrict__ stage, T* __restrict__ tables,
-                                                           unsigned char* __restrict__ zflags, unsigned long long* __restrict__ results, int* __restrict__ status) {
+                                                           unsigned char* __restrict__ zflags, unsigned long long* __restrict__ results, int* __restrict__ status,
+                                                           const unsigned int* __restrict__ invtabs /* inverse-lookup path: T0..T2 are stored times -A3_e^-1, else NULL */) {
   const QuadDesc& d = descs[blockIdx.y];
   const int c = d.c, m = d.m, mpad = d.mpad, nact = d.nact;
   const long long* __restrict__ tm = stage + d.in_off;       // [4][m]
@@ -60,8 +60,13 @@ __global__ void __launch_bounds__(256) quad_tables_kernel(const QuadDesc* __rest
     const int l = (int)(rem / mpad), j = (int)(rem - (size_t)l * mpad);
     T val = 0;
     if (t < nact && j < m) {
-      if (MODP) val = (T)(((unsigned long long)coef[l] * (unsigned long long)tm[(size_t)t * m + j]) % d.p);
-      else val = (T)(coef[l] * tm[(size_t)t * m + j]);
+      if (MODP) {
+        val = (T)(((unsigned long long)coef[l] * (unsigned long long)tm[(size_t)t * m + j]) % d.p);
+        if (invtabs && t < 3) {
+          const unsigned int ni = invtabs[d.inv_off + j];
+          if (ni != InvTables::kEmpty) val = (T)(((unsigned long long)val * ni) % d.p);
+        }
+      } else val = (T)(coef[l] * tm[(size_t)t * m + j]);
     }
     if (t == 2) t0[2 * tab + (size_t)j * c + l] = val;  // transposed: consecutive k coalesce in the count kernel
     else t0[(size_t)t * tab + rem] = val;
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(kLcThreads) quad_count_inv_kernel(const QuadDe
       const unsigned qq = q / (unsigned)c;
       const int j = (int)(qq % (unsigned)c), i = (int)(qq / (unsigned)c);
       for (int w = 0; w < cpad; w += 4) *reinterpret_cast<unsigned int*>(hist + w) = 0u;
-      base = inv_count_prefix(t0 + (size_t)i * MPAD, t1 + (size_t)j * MPAD, t2 + k, c, d.m, p, d.pinv, d.hbits, sh);
+      base = inv_count_prefix(t0 + (size_t)i * MPAD, t1 + (size_t)j * MPAD, t2 + k, c, d.m, p, d.hbits, sh);
     }
     if (words_ok) {
       if (valid) {
@@ -920,7 +925,6 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
     d.seed_key = pack_key(q.init_rl, q.init_cl, kIdxMask);
     d.cmax = P.cmax;
     d.m64 = p ? ~0ull / p : 0;
-    d.pinv = (p & 1u) ? inv_neg_pinv((uint32_t)p) : 0u; d.pad_ = 0;
     if (use_inv) {
       d.hbits = inv_hash_bits(q.c);
       d.inv_off = inv_off;
@@ -970,11 +974,12 @@ int plo_lincomb_quad(uint32_t p, int m, int nproblems, plo_quad_problem* pr) {
   } else {
   {
     const dim3 tg((unsigned)std::min<unsigned long long>((max_tab + 255) / 256, 64), nproblems);
+    const unsigned int* fold = use_inv && inv_smem <= 200 * 1024 ? reinterpret_cast<const unsigned int*>(Q.d_stage + desc_bytes + in_bytes) : nullptr;
     if (width == 4) {
-      if (p) quad_tables_kernel<uint32_t, true><<<tg, 256, 0, st>>>(dd, dstage, (uint32_t*)Q.d_tables, dzf, dres, dstatus);
-      else quad_tables_kernel<uint32_t, false><<<tg, 256, 0, st>>>(dd, dstage, (uint32_t*)Q.d_tables, dzf, dres, dstatus);
+      if (p) quad_tables_kernel<uint32_t, true><<<tg, 256, 0, st>>>(dd, dstage, (uint32_t*)Q.d_tables, dzf, dres, dstatus, fold);
+      else quad_tables_kernel<uint32_t, false><<<tg, 256, 0, st>>>(dd, dstage, (uint32_t*)Q.d_tables, dzf, dres, dstatus, nullptr);
     } else {
-      quad_tables_kernel<uint64_t, false><<<tg, 256, 0, st>>>(dd, dstage, (uint64_t*)Q.d_tables, dzf, dres, dstatus);
+      quad_tables_kernel<uint64_t, false><<<tg, 256, 0, st>>>(dd, dstage, (uint64_t*)Q.d_tables, dzf, dres, dstatus, nullptr);
     }
   }
   unsigned int* drhist = nullptr;  // set when the count kernel leaves the histogram of the row maxima

@@ -163,7 +163,6 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_kernel(const LcParams<T> p
 struct LcInvParams {
   const unsigned int* inv;   // [b][InvTables::words]
   int hbits, cpad;           // hash bits; c rounded up to a multiple of 4
-  unsigned int pinv;         // -p^-1 mod 2^32 (p odd)
 };
 
 template <int MPAD>
@@ -204,7 +203,7 @@ __global__ void __launch_bounds__(kLcThreads) lincomb_inv_kernel(const LcParams<
     // coordinate, and 48 copies of the probe loop overflow the instruction cache (ncu: stall reason no_instruction 7.7 warps per issue
     // with the unrolled body).  A register list of hits instead of the byte counters was tried and is slower: with Hopcroft-Musinski
     // data hits are common (structured prefixes), not rare.
-    const int base = (int)inv_count_prefix(t0 + (size_t)i * MPAD, t1 + (size_t)j * MPAD, t2 + k, c, prm.m, p, ip.pinv, ip.hbits, sh);
+    const int base = (int)inv_count_prefix(t0 + (size_t)i * MPAD, t1 + (size_t)j * MPAD, t2 + k, c, prm.m, p, ip.hbits, sh);
     const int zc = prm.cl_const + zf[i] + zf[c + j] + zf[2 * c + k];
     int best_rl1 = (int)(best >> 48);
     for (int l0 = 0; l0 < c; l0 += 4) {
@@ -622,8 +621,16 @@ int plo_lincomb_plan_create(plo_lincomb_plan** plan, uint32_t p, int nbatch, int
                               inv.data() + (size_t)b * words);
     const int cpad = (c + 3) & ~3;
     pl->inv_smem = words * 4 + (size_t)kLcThreads * (cpad + 4);
-    if (good && pl->inv_smem <= 200 * 1024 && up((void**)&pl->d_inv, inv.data(), inv.size() * 4)) {
+    if (good && pl->inv_smem <= 200 * 1024) {
+      if (!up((void**)&pl->d_inv, inv.data(), inv.size() * 4)) { set_error("lincomb plan: cudaMalloc failed"); plo_lincomb_plan_destroy(pl); return PLO_E_CUDA; }
       pl->use_inv = true;
+      {  // the lookup kernel reads T0, T1, T2 pre-multiplied by -A3_e^-1 (lincomb_common.cuh)
+        const size_t per = (size_t)nbatch * tab;  // words per table kind
+        uint32_t* base = reinterpret_cast<uint32_t*>(tables.data());
+        for (int b = 0; b < nbatch; ++b)
+          fold_inv_into_tables((uint32_t)p, m_tab, mpad, c, inv.data() + (size_t)b * words, base + 0 * per + (size_t)b * tab, base + 1 * per + (size_t)b * tab,
+                               base + 2 * per + (size_t)b * tab);
+      }
       const unsigned long long blocks = (nprefix + kLcThreads - 1) / kLcThreads;
       pl->grid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>(blocks, (unsigned long long)sms * 8ull));
     }
@@ -691,7 +698,7 @@ int plo_lincomb_plan_run_range(plo_lincomb_plan* pl, uint64_t prefix_lo, uint64_
   } else if (pl->use_inv) {
     auto prm = fill((uint32_t*)pl->d_tables);
     LcInvParams ip;
-    ip.inv = pl->d_inv; ip.hbits = pl->hbits; ip.cpad = (pl->c + 3) & ~3; ip.pinv = inv_neg_pinv((uint32_t)pl->p);
+    ip.inv = pl->d_inv; ip.hbits = pl->hbits; ip.cpad = (pl->c + 3) & ~3; 
     e = launch_lincomb_inv(pl->mpad, grid, pl->inv_smem, st, prm, ip);
   } else if (pl->width == 4) {
     auto prm = fill((uint32_t*)pl->d_tables);
