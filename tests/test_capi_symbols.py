@@ -72,6 +72,13 @@ def test_compute_calls_fail_loudly_without_a_device():
     with pytest.raises(capi.PloError) as e:
         capi.measure_peaks(1)
     assert e.value.code == capi.E_NODEVICE
+    # the MMchecker drivers (one prime, and over Q through several primes) and the plans: no CPU path either.  The encoder self-test
+    # (plo_mmcheck_encode_check, tests/test_mm_encoder.py) is host-only by design and is not a way around this.
+    for call in (lambda: capi.mmchecker(L, R, P), lambda: capi.mmchecker_bits(L, R, P, bitsize=8),
+                 lambda: capi.mmcheck_batch(7, (2, 2, 2), 7, hm.csr_modp(L, 7), hm.csr_modp(R, 7), hm.csr_modp(P, 7), batch=4)):
+        with pytest.raises(capi.PloError) as e:
+            call()
+        assert e.value.code == capi.E_NODEVICE
 
 
 def test_argument_errors():
