@@ -158,7 +158,7 @@ inline void fold_inv_into_tables(uint32_t p, int m, int mpad, int c, const uint3
 // (stride c words), all three pre-multiplied by ninv.  Every coordinate costs three loads, two modular additions, one hash probe; a hit increments the byte
 // counter of every l with that coefficient value.  Returns the number of coordinates that vanish whatever l is.  The shared-memory
 // tables are addressed through 32-bit shared addresses the caller made opaque (under register pressure ptxas re-derives generic
-// shared pointers -- S2R + LEA -- inside the loop, ncu profiles/ncu_r02_ad_lincomb_inv_final.md), the global rows through running
+// shared pointers -- S2R + LEA -- inside the loop, ncu profiles/ncu_r02_ad_lincomb_inv_redc.md), the global rows through running
 // pointers instead of 64-bit index arithmetic per load.
 struct InvShared { uint32_t ninv, htab, nextdup, hist; };  // shared addresses: tables of the problem, byte counters of this thread
 __device__ __forceinline__ unsigned inv_count_prefix(const unsigned int* __restrict__ p0, const unsigned int* __restrict__ p1, const unsigned int* __restrict__ p2,
